@@ -1,0 +1,156 @@
+/*
+ * spotv2_gat.h — C ABI of libspotv2_gat.so, the B200 (sm_100a) replacement for
+ * the GAT hot path of loopinf/SpotV2Net.
+ *
+ * What it replaces.  The reference has no native code; its hot path is the
+ * third-party PyG 2.3.0 `GATConv` reached from
+ *     /root/reference/utils/models.py:11      (import)
+ *     /root/reference/utils/models.py:87-113  (layer construction)
+ *     /root/reference/utils/models.py:146     (x = l(x, edge_index, edge_attr))
+ *     /root/reference/5_train_SpotV2Net.py:150-159 (forward + autograd backward)
+ * and the PyG batch collation reached from
+ *     /root/reference/5_train_SpotV2Net.py:90,142-143.
+ * Each entry point below names the eager op(s) it stands in for.  The binding
+ * a maintainer adds on the reference side is a ctypes stub; see INTEGRATION.md.
+ *
+ * Conventions.
+ *  - extern "C", plain pointers and sizes; no torch / ATen types.
+ *  - every pointer is a DEVICE pointer owned by the caller unless it says host.
+ *    The library allocates nothing persistent and keeps no global state.
+ *  - every entry point enqueues work on `stream` (a cudaStream_t passed as
+ *    void*) and returns without synchronising; it is safe to capture into a
+ *    CUDA graph.
+ *  - return value: SPOTV2_OK (0) or a spotv2_status; a human-readable message
+ *    for the calling thread's last failure is at spotv2_last_error().
+ *  - all floating point is IEEE fp32; row-major; leading dimensions in elements.
+ *  - batches are B identical complete directed graphs on N nodes (the only
+ *    topology /root/reference/utils/dataset.py:216-226 produces).  Anything
+ *    else is rejected by spotv2_edge_table_build — there is no generic or CPU
+ *    fallback.
+ */
+#ifndef SPOTV2_GAT_H_
+#define SPOTV2_GAT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPOTV2_ABI_VERSION 1
+
+typedef enum spotv2_status {
+  SPOTV2_OK = 0,
+  SPOTV2_ERR_INVALID_ARG = 1,   /* null pointer, non-positive size, bad stride/alignment */
+  SPOTV2_ERR_UNSUPPORTED = 2,   /* shape outside what the kernels cover (e.g. N > 32) */
+  SPOTV2_ERR_WORKSPACE = 3,     /* workspace too small */
+  SPOTV2_ERR_CUDA = 4,          /* a CUDA runtime call failed */
+  SPOTV2_ERR_NO_DEVICE = 5      /* no sm_100 device / driver */
+} spotv2_status;
+
+/* One GATConv layer applied to one batch.
+ * PyG ctor kwargs used by the reference (utils/models.py:87-113):
+ *   in_channels=F, out_channels=C, heads=H, concat, edge_dim=Fe, negative_slope. */
+typedef struct spotv2_gat_desc {
+  int32_t B;              /* graphs in the batch                                   */
+  int32_t N;              /* nodes per graph (30 by default)                       */
+  int32_t F;              /* in_channels                                           */
+  int32_t Fe;             /* edge_dim; 0 = layer called with edge_attr=None        */
+  int32_t H;              /* heads                                                 */
+  int32_t C;              /* out_channels per head                                 */
+  int32_t R;              /* edge rows per graph in the edge block (N*(N-1) for
+                             PyG order, N*N for a dense target-major tile)         */
+  int32_t concat;         /* 1: out is [B*N, H*C]; 0: head mean, out is [B*N, C]   */
+  float   negative_slope; /* LeakyReLU slope                                       */
+  int32_t ldp;            /* row stride of P_aug / dP_aug: >= H*C + 2*H, % 4 == 0  */
+  int32_t gemm_algo;      /* 0 auto, 1 fp32 SIMT, 2 tcgen05 3xTF32                 */
+  int32_t reserved;
+} spotv2_gat_desc;
+
+/* Row table entry: (i << 16) | j  = "this edge row is j -> i" (i target, j source),
+ * or SPOTV2_ROW_SKIP for rows the layer ignores (self loops in the input, which
+ * PyG's remove_self_loops drops; the diagonal of a dense tile). */
+#define SPOTV2_ROW_SKIP (-1)
+
+const char* spotv2_last_error(void);
+int32_t     spotv2_abi_version(void);
+
+/* Smallest legal ldp for (H, C). */
+int32_t spotv2_gat_ldp(int32_t H, int32_t C);
+
+/* Bytes of scratch each phase wants (device memory, 256-byte aligned). */
+int spotv2_gat_workspace_bytes(const spotv2_gat_desc* d, size_t* proj_fwd, size_t* attn_bwd,
+                               size_t* proj_bwd);
+
+/* Replaces the per-call topology work PyG does on edge_index
+ * (remove_self_loops / add_self_loops / index_select by edge_index[0|1];
+ * [PyG] gat_conv.py forward, utils/loop.py).  Reads edge_index [2, B*R] int64
+ * (PyG concatenated order, node ids offset by b*N), writes table[R] and
+ * status[4] = {ok, first bad edge, reason, 0}.  ok==1 iff every graph repeats
+ * graph 0's local pattern and that pattern holds each ordered pair i!=j once. */
+int spotv2_edge_table_build(const int64_t* edge_index, int64_t num_edges, int32_t B, int32_t N,
+                            int32_t R, int32_t* table, int32_t* status, void* stream);
+/* Table of a dense target-major tile: row r = i*N + j, diagonal skipped. */
+int spotv2_edge_table_dense(int32_t N, int32_t* table, void* stream);
+
+/* Folds the attention vectors into the linear maps:
+ *   W_aug [H*C + 2H, F] = [ W ; u_src ; u_dst ],  u_src,h = W_h^T a_src,h
+ *   v     [H, Fe]       = W_e,h^T a_edge,h            (skipped when Fe == 0)
+ * Stands in for `(x_src * att_src).sum(-1)`, `(x_dst * att_dst).sum(-1)` and
+ * `lin_edge(edge_attr)` + `(e * att_edge).sum(-1)` of [PyG] gat_conv.py. */
+int spotv2_gat_fold(const spotv2_gat_desc* d, const float* W, const float* a_src,
+                    const float* a_dst, const float* W_e, const float* a_edge, float* W_aug,
+                    float* v, void* stream);
+
+/* lin_src: P_aug [B*N, ldp] = x [B*N, F] . W_aug^T ; columns [0,HC) are P,
+ * [HC,HC+H) are s = alpha_src, [HC+H,HC+2H) are d = alpha_dst. */
+int spotv2_proj_fwd(const spotv2_gat_desc* d, const float* x, const float* W_aug, float* P_aug,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* edge_update + softmax + propagate + head reduce + bias ([PyG] gat_conv.py
+ * edge_update/message, utils/softmax.py, aggr='add').  edge_rows is [B, R, Fe]
+ * (ignored when Fe == 0).  alpha_or_null, if given, receives the attention
+ * tile [B, H, N(source j), N(target i)] (for return_attention_weights). */
+int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug, const float* edge_rows,
+                        const int32_t* table, const float* v, const float* bias_or_null,
+                        float* out, float* alpha_or_null, void* stream);
+
+/* autograd of the above with the attention coefficients recomputed, not stored.
+ * dout [B*N, C or HC] -> dP_aug [B*N, ldp] (dP | ds | dd), dv [H, Fe], dbias. */
+int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug, const float* edge_rows,
+                        const int32_t* table, const float* v, const float* dout, float* dP_aug,
+                        float* dv_or_null, float* dbias_or_null, void* ws, size_t ws_bytes,
+                        void* stream);
+
+/* lin_src backward: dW_aug [H*C+2H, F] = dP_aug^T . x  and  dX [B*N, F] = dP_aug . W_aug. */
+int spotv2_proj_bwd_weight(const spotv2_gat_desc* d, const float* x, const float* dP_aug,
+                           float* dW_aug, void* ws, size_t ws_bytes, void* stream);
+int spotv2_proj_bwd_input(const spotv2_gat_desc* d, const float* dP_aug, const float* W_aug,
+                          float* dX, void* ws, size_t ws_bytes, void* stream);
+
+/* Inverse of spotv2_gat_fold for gradients: from dW_aug and dv to the gradients of
+ * lin_src.weight, att_src, att_dst, lin_edge.weight, att_edge (PyG parameter names). */
+int spotv2_gat_unfold(const spotv2_gat_desc* d, const float* W, const float* a_src,
+                      const float* a_dst, const float* W_e, const float* a_edge,
+                      const float* dW_aug, const float* dv, float* dW, float* da_src,
+                      float* da_dst, float* dW_e, float* da_edge, void* stream);
+
+/* return_attention_weights ordering: real edges in batch
+ * order, then the B*N self loops: alpha_pyg [B*R_real + B*N, H]. */
+int spotv2_alpha_to_pyg(const spotv2_gat_desc* d, const float* alpha_tile, const int32_t* table,
+                        float* alpha_pyg, void* stream);
+
+/* Graph-batch collation on the device (replaces PyG DataLoader/Batch.from_data_list
+ * over CovarianceLaggedDataset, /root/reference/utils/dataset.py:182-289 and
+ * 5_train_SpotV2Net.py:90,142-143).  M_vol, M_vv: [T, N, N] fp32 resident in HBM;
+ * t0[B] int32 window starts; L = seq_length.  Writes x [B*N, N*L],
+ * edge_attr [B*N*(N-1), 3L] in PyG row order, y [B*N]. */
+int spotv2_collate_windows(const float* M_vol, const float* M_vv, int32_t T, int32_t N, int32_t L,
+                           const int32_t* t0, int32_t B, float* x, float* edge_attr, float* y,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPOTV2_GAT_H_ */

@@ -1,0 +1,55 @@
+// Error plumbing, descriptor validation and the small ABI queries of libspotv2_gat.so.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace spotv2 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int fail(spotv2_status st, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return (int)st;
+}
+
+int check_desc(const spotv2_gat_desc* d) {
+  if (!d) return fail(SPOTV2_ERR_INVALID_ARG, "descriptor is null");
+  if (d->B <= 0 || d->N <= 0 || d->F <= 0 || d->H <= 0 || d->C <= 0 || d->Fe < 0 || d->R < 0)
+    return fail(SPOTV2_ERR_INVALID_ARG, "non-positive size in descriptor (B=%d N=%d F=%d Fe=%d H=%d C=%d R=%d)",
+                d->B, d->N, d->F, d->Fe, d->H, d->C, d->R);
+  if (d->N > 0xffff) return fail(SPOTV2_ERR_UNSUPPORTED, "N=%d does not fit the 16-bit row table", d->N);
+  if (d->ldp < d->H * d->C + 2 * d->H || d->ldp % 4 != 0)
+    return fail(SPOTV2_ERR_INVALID_ARG, "ldp=%d must be >= H*C+2H=%d and a multiple of 4", d->ldp,
+                d->H * d->C + 2 * d->H);
+  if (d->Fe > 0 && d->R <= 0) return fail(SPOTV2_ERR_INVALID_ARG, "R must be positive when Fe > 0");
+  return SPOTV2_OK;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  cached = n;
+  return n;
+}
+
+}  // namespace spotv2
+
+using namespace spotv2;
+
+extern "C" const char* spotv2_last_error(void) { return g_err; }
+extern "C" int32_t spotv2_abi_version(void) { return SPOTV2_ABI_VERSION; }
+extern "C" int32_t spotv2_gat_ldp(int32_t H, int32_t C) { return (H * C + 2 * H + 3) / 4 * 4; }

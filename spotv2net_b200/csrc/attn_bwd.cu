@@ -1,0 +1,484 @@
+// Fused GAT attention backward with the attention coefficients RECOMPUTED from the inputs
+// (nothing but P_aug is kept from the forward).  Closed form of SURVEY.md Appendix A.3 in the
+// augmented layout: dP_aug = [dP | ds | dd].  Replaces the autograd graph PyG records for
+// edge_update / softmax / propagate ([PyG] nn/conv/gat_conv.py; /root/reference/5_train_SpotV2Net.py:157).
+//
+// Per graph (one CTA iteration, N <= 32):
+//   B1  recompute: edge rows -> g (3xTF32 mma.sync) -> alpha tile, z>0 masks            [ring]
+//   B2  dalpha[h][i][j] = <dO_i,h , P_j,h>: 5x5 register tiles, FFMA2 paired over channels,
+//       operands staged 16 channels at a time with cp.async double buffering            [staging]
+//   B2b thread (h,i): softmax + LeakyReLU backward -> dz ; dd_i ; then ds_j ; then the
+//       self-loop mean-fill redistribution dz'
+//   B3  dP[j,h,c] = sum_i alpha_h[i,j] dO_i,h[c]: thread owns a channel pair, dO in registers
+//   B4  dv[h,:] += sum_e dz'[e,h] * edge_attr[e,:]: second pass over the edge rows         [ring]
+// The ring and the B2 staging alias the same shared memory.  dv and dbias are accumulated per
+// CTA and reduced in a fixed order by a second kernel (deterministic).
+#include "attn_common.cuh"
+
+namespace spotv2 {
+
+constexpr int kCK = 16;        // channels per B2 staging chunk
+constexpr int kCKP = 20;       // padded row stride (floats): 80 B, conflict-free for the 5x5 tiles
+constexpr int kTI = 5;         // register tile: targets
+constexpr int kTJ = 5;         // register tile: sources
+
+struct AttnBwdArgs {
+  AttnParams p;
+  const float* dout;
+  float* dP_aug;
+  float* dv_part;      // [grid][H*Fe]
+  float* dbias_part;   // [grid][ldo]
+};
+
+struct BwdSmem {
+  AttnSmem a;
+  int NP5;                  // rows per head in the staging buffers (N rounded up to kTI)
+  size_t off_D, off_mask, off_dbias, off_union, union_bytes, stage_P_bytes, stage_G_bytes, total;
+};
+
+inline BwdSmem bwd_smem_plan(int N, int Fe, int H, int C, int R, int npairs, int concat, int chunk_rows) {
+  BwdSmem s;
+  s.a = attn_smem_plan(N, Fe, H, R, npairs, chunk_rows);
+  s.NP5 = (N + kTI - 1) / kTI * kTI;
+  const int ldo = concat ? H * C : C;
+  size_t o = s.a.base_total;
+  s.off_D = o;     o += round_up((size_t)H * N * s.a.NS * 4, 16);
+  s.off_mask = o;  o += round_up((size_t)H * N * 4, 16);
+  s.off_dbias = o; o += round_up((size_t)ldo * 4, 16);
+  s.off_union = round_up(o, 128);
+  s.stage_P_bytes = (size_t)H * s.NP5 * kCKP * 4;
+  s.stage_G_bytes = (size_t)(concat ? H : 1) * s.NP5 * kCKP * 4;
+  const size_t staging = 2 * (s.stage_P_bytes + s.stage_G_bytes);
+  const size_t ring = 2 * s.a.ring_stage_bytes;
+  const size_t dvred = (size_t)2 * kAttnThreads * kMaxHeads * 4;   // end-of-kernel dv reduction
+  s.union_bytes = staging > ring ? staging : ring;
+  if (dvred > s.union_bytes) s.union_bytes = dvred;
+  s.total = s.off_union + s.union_bytes;
+  return s;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;   // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+// Stage channels [c_base, c_base + kCK) of this graph's P (all heads) and dO rows.
+__device__ __forceinline__ void stage_chunk(const AttnBwdArgs& a, const BwdSmem& sm, float* Ps,
+                                            float* Gs, int b, int c_base, bool vec4, int tid) {
+  const AttnParams& p = a.p;
+  const int N = p.N, H = p.H, C = p.C, NP5 = sm.NP5;
+  const int g_heads = p.concat ? H : 1;
+  const int rowsP = H * NP5, rowsG = g_heads * NP5;
+  for (int idx = tid; idx < (rowsP + rowsG) * (kCK / 4); idx += kAttnThreads) {
+    const int row = idx >> 2, q = idx & 3;
+    const int c = c_base + 4 * q;
+    float* dst;
+    const float* src;
+    bool row_ok;
+    if (row < rowsP) {
+      const int h = row / NP5, j = row - h * NP5;
+      row_ok = j < N;
+      dst = Ps + (size_t)row * kCKP + 4 * q;
+      src = p.P_aug + ((size_t)b * N + (row_ok ? j : 0)) * p.ldp + (size_t)h * C + c;
+    } else {
+      const int r2 = row - rowsP;
+      const int h = r2 / NP5, i = r2 - h * NP5;
+      row_ok = i < N;
+      dst = Gs + (size_t)r2 * kCKP + 4 * q;
+      src = a.dout + ((size_t)b * N + (row_ok ? i : 0)) * p.ldo + (size_t)h * C + c;
+    }
+    if (vec4) {
+      const bool ok = row_ok && c < C;        // C % 4 == 0 on this path: whole float4 in or out
+      cp_async16(dst, ok ? src : p.P_aug, ok);
+    } else {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_ok) {
+        if (c + 0 < C) v.x = __ldg(src + 0);
+        if (c + 1 < C) v.y = __ldg(src + 1);
+        if (c + 2 < C) v.z = __ldg(src + 2);
+        if (c + 3 < C) v.w = __ldg(src + 3);
+      }
+      *reinterpret_cast<float4*>(dst) = v;
+    }
+  }
+}
+
+template <int NPAIRS>
+__global__ void __launch_bounds__(kAttnThreads, 2)
+gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const AttnParams& p = args.p;
+  const int tid = threadIdx.x;
+  const int N = p.N, H = p.H, C = p.C, NS = sm.a.NS, Fe = p.Fe;
+  const int HC = H * C;
+  const float inv_nm1 = 1.f / (float)(N > 1 ? N - 1 : 1);
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sm.a.off_bar);
+  int32_t* table_s = reinterpret_cast<int32_t*>(smem_raw + sm.a.off_table);
+  float4* vfrag = reinterpret_cast<float4*>(smem_raw + sm.a.off_vfrag);
+  float* sd = reinterpret_cast<float*>(smem_raw + sm.a.off_sd);
+  float* tile = reinterpret_cast<float*>(smem_raw + sm.a.off_tile);     // alpha[h][j][i]
+  float* D = reinterpret_cast<float*>(smem_raw + sm.off_D);             // dalpha -> dz -> dz'
+  uint32_t* pos_mask = reinterpret_cast<uint32_t*>(smem_raw + sm.off_mask);
+  float* dbias_s = reinterpret_cast<float*>(smem_raw + sm.off_dbias);
+  unsigned char* uni = smem_raw + sm.off_union;
+  float* Pst[2] = {reinterpret_cast<float*>(uni), reinterpret_cast<float*>(uni + sm.stage_P_bytes + sm.stage_G_bytes)};
+  float* Gst[2] = {reinterpret_cast<float*>(uni + sm.stage_P_bytes),
+                   reinterpret_cast<float*>(uni + 2 * sm.stage_P_bytes + sm.stage_G_bytes)};
+
+  EdgeRing ring;
+  ring.stage[0] = reinterpret_cast<float*>(uni);
+  ring.stage[1] = reinterpret_cast<float*>(uni + sm.a.ring_stage_bytes);
+  ring.full = bars;
+  ring.uses[0] = ring.uses[1] = 0;
+  ring.chunk_rows = sm.a.chunk_rows;
+  ring.nchunks = Fe > 0 ? (p.R + sm.a.chunk_rows - 1) / sm.a.chunk_rows : 0;
+  ring.p = &p;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  for (int r = tid; r < p.R; r += kAttnThreads) table_s[r] = Fe > 0 ? p.table[r] : -1;
+  if (Fe > 0) build_vfrag(vfrag, p.v, H, Fe, sm.a.KS, sm.a.NT, tid, kAttnThreads);
+  for (int idx = tid; idx < H * N * NS; idx += kAttnThreads) { tile[idx] = 0.f; D[idx] = 0.f; }
+  for (int idx = tid; idx < p.ldo; idx += kAttnThreads) dbias_s[idx] = 0.f;
+  __syncthreads();
+
+  int b = blockIdx.x;
+  if (p.bulk_ok && tid == 0 && b < p.B && ring.nchunks > 0) ring.prefetch_first(b);
+
+  const float g_scale = p.concat ? 1.f : 1.f / (float)H;
+  const bool vec4 = (C % 4 == 0) && (p.ldo % 4 == 0);
+  const int NIG = sm.NP5 / kTI;                       // tile groups along targets and sources
+  const int n_tiles = H * NIG * NIG;
+  const int nchan_chunks = (C + kCK - 1) / kCK;
+  const int CP = (C + 1) / 2;
+  const int n_items = p.concat ? H * CP : CP;
+
+  // dv accumulators: thread (rg, f) owns feature f (and f + 256 when Fe > 256) for row group rg, all heads
+  const int dv_groups = Fe > 0 ? max(1, kAttnThreads / Fe) : 0;
+  const int dv_rg = (Fe > 0 && Fe <= kAttnThreads) ? tid / Fe : 0;
+  const int dv_f = tid - dv_rg * (Fe <= kAttnThreads ? Fe : 0);
+  const bool dv_active = Fe > 0 && dv_rg < dv_groups && dv_f < Fe;
+  const bool dv_second = dv_active && dv_f + kAttnThreads < Fe;
+  float dv_acc[2][kMaxHeads];
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h) dv_acc[0][h] = dv_acc[1][h] = 0.f;
+
+  for (; b < p.B; b += gridDim.x) {
+    // ---- B1: recompute alpha --------------------------------------------------------------
+    for (int idx = tid; idx < N * 2 * H; idx += kAttnThreads) {
+      const int j = idx / (2 * H), k = idx - j * 2 * H;
+      sd[idx] = p.P_aug[((size_t)b * N + j) * p.ldp + HC + k];
+    }
+    if (ring.nchunks > 0) {
+      edge_logit_phase(ring, p, sm.a, tile, table_s, vfrag, b, tid);
+    } else {
+      for (int idx = tid; idx < H * N * NS; idx += kAttnThreads) tile[idx] = 0.f;
+      __syncthreads();
+    }
+    softmax_phase(p, sm.a, tile, sd, 1.f, nullptr, pos_mask, tid);
+    // (no barrier needed before B2's loads: they write the union region, idle since B1's last barrier;
+    //  D is written only after the chunk loop's barriers)
+
+    // ---- B2: dalpha = dO . P^T -------------------------------------------------------------
+    for (int t0 = 0; t0 < n_tiles; t0 += kAttnThreads) {
+      const int t = t0 + tid;
+      const bool active = t < n_tiles;
+      const int ig = t % NIG, cg = (t / NIG) % NIG, h = active ? t / (NIG * NIG) : 0;
+      float2 acc[kTI][kTJ];
+#pragma unroll
+      for (int ii = 0; ii < kTI; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < kTJ; ++jj) acc[ii][jj] = make_float2(0.f, 0.f);
+      stage_chunk(args, sm, Pst[0], Gst[0], b, 0, vec4, tid);
+      cp_async_commit();
+      for (int ch = 0; ch < nchan_chunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < nchan_chunks) stage_chunk(args, sm, Pst[buf ^ 1], Gst[buf ^ 1], b, (ch + 1) * kCK, vec4, tid);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        if (active) {
+          const float* Gb = Gst[buf] + (size_t)((p.concat ? h * sm.NP5 : 0) + ig * kTI) * kCKP;
+          const float* Pb = Pst[buf] + (size_t)(h * sm.NP5 + cg * kTJ) * kCKP;
+#pragma unroll
+          for (int s4 = 0; s4 < kCK / 4; ++s4) {
+            float4 pv[kTJ];
+#pragma unroll
+            for (int jj = 0; jj < kTJ; ++jj) pv[jj] = *reinterpret_cast<const float4*>(Pb + jj * kCKP + 4 * s4);
+#pragma unroll
+            for (int ii = 0; ii < kTI; ++ii) {
+              const float4 g4 = *reinterpret_cast<const float4*>(Gb + ii * kCKP + 4 * s4);
+              const float2 g0 = make_float2(g4.x, g4.y), g1 = make_float2(g4.z, g4.w);
+#pragma unroll
+              for (int jj = 0; jj < kTJ; ++jj) {
+                acc[ii][jj] = ffma2(g0, make_float2(pv[jj].x, pv[jj].y), acc[ii][jj]);
+                acc[ii][jj] = ffma2(g1, make_float2(pv[jj].z, pv[jj].w), acc[ii][jj]);
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+      if (active) {
+#pragma unroll
+        for (int ii = 0; ii < kTI; ++ii) {
+          const int i = ig * kTI + ii;
+#pragma unroll
+          for (int jj = 0; jj < kTJ; ++jj) {
+            const int j = cg * kTJ + jj;
+            if (i < N && j < N) D[(h * N + j) * NS + i] = (acc[ii][jj].x + acc[ii][jj].y) * g_scale;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // staging is idle from here: start the second pass over the edge rows under B2b/B3
+    if (p.bulk_ok && tid == 0 && ring.nchunks > 0) ring.prefetch_first(b);
+
+    // ---- B2b: softmax / LeakyReLU backward ---------------------------------------------------
+    for (int idx = tid; idx < H * N; idx += kAttnThreads) {
+      const int h = idx / N, i = idx - h * N;
+      const float* acol = tile + (size_t)h * N * NS + i;
+      float* dcol = D + (size_t)h * N * NS + i;
+      float dot = 0.f;
+      for (int j = 0; j < N; ++j) dot = fmaf(acol[j * NS], dcol[j * NS], dot);
+      const uint32_t mask = pos_mask[idx];
+      float dd = 0.f;
+      for (int j = 0; j < N; ++j) {
+        const float dl = acol[j * NS] * (dcol[j * NS] - dot);
+        const float dz = ((mask >> j) & 1u) ? dl : dl * p.slope;
+        dd += dz;
+        dcol[j * NS] = dz;
+      }
+      args.dP_aug[((size_t)b * N + i) * p.ldp + HC + H + h] = dd;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < H * N; idx += kAttnThreads) {     // ds_j = sum_i dz_ij
+      const int h = idx / N, j = idx - h * N;
+      const float* drow = D + (size_t)(h * N + j) * NS;
+      float ds = 0.f;
+      for (int k = 0; k < N; ++k) {
+        int i = j + k;                                          // rotated start: conflict-free banks
+        if (i >= N) i -= N;
+        ds += drow[i];
+      }
+      args.dP_aug[((size_t)b * N + j) * p.ldp + HC + h] = ds;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < H * N; idx += kAttnThreads) {     // dz' : gradient through the mean fill
+      const int h = idx / N, i = idx - h * N;
+      float* dcol = D + (size_t)h * N * NS + i;
+      const float share = dcol[i * NS] * inv_nm1;
+      for (int j = 0; j < N; ++j) dcol[j * NS] = (j == i) ? 0.f : dcol[j * NS] + share;
+    }
+    // (D is next read in B4, after B3's trailing barrier)
+
+    // ---- B3: dP = alpha^T dO ------------------------------------------------------------------
+    for (int item = tid; item < n_items; item += kAttnThreads) {
+      const int h0 = p.concat ? item / CP : 0;
+      const int cp = p.concat ? item - h0 * CP : item;
+      const int c0 = 2 * cp;
+      const bool has1 = c0 + 1 < C;
+      const int gcol = h0 * C + c0;                       // column of dout this item reads
+      float2 G[NPAIRS][2];                                // (dO[2ip][c], dO[2ip+1][c]) for c0, c0+1
+      float bsum0 = 0.f, bsum1 = 0.f;
+#pragma unroll
+      for (int ip = 0; ip < NPAIRS; ++ip) {
+        float v[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int i = 2 * ip + half;
+          if (i < N) {
+            const float* src = args.dout + ((size_t)b * N + i) * p.ldo + gcol;
+            if (p.vec2_ok) {
+              const float2 t2 = *reinterpret_cast<const float2*>(src);
+              v[half][0] = t2.x; v[half][1] = t2.y;
+            } else {
+              v[half][0] = __ldg(src);
+              if (has1) v[half][1] = __ldg(src + 1);
+            }
+          }
+        }
+        bsum0 += v[0][0] + v[1][0];
+        bsum1 += v[0][1] + v[1][1];
+        G[ip][0] = make_float2(v[0][0] * g_scale, v[1][0] * g_scale);
+        G[ip][1] = make_float2(v[0][1] * g_scale, v[1][1] * g_scale);
+      }
+      dbias_s[gcol] += bsum0;                              // each column has exactly one owner thread
+      if (has1) dbias_s[gcol + 1] += bsum1;
+
+      const int h_begin = p.concat ? h0 : 0, h_end = p.concat ? h0 + 1 : H;
+      for (int h = h_begin; h < h_end; ++h) {
+        for (int j = 0; j < N; ++j) {
+          const float* ar = tile + (size_t)(h * N + j) * NS;
+          float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int q = 0; q < NPAIRS / 2; ++q) {
+            const float4 a4 = *reinterpret_cast<const float4*>(ar + 4 * q);
+            const float2 a0 = make_float2(a4.x, a4.y), a1 = make_float2(a4.z, a4.w);
+            s0 = ffma2(a0, G[2 * q][0], s0);
+            s1 = ffma2(a0, G[2 * q][1], s1);
+            s0 = ffma2(a1, G[2 * q + 1][0], s0);
+            s1 = ffma2(a1, G[2 * q + 1][1], s1);
+          }
+          if (NPAIRS & 1) {
+            const float2 a0 = *reinterpret_cast<const float2*>(ar + 2 * (NPAIRS - 1));
+            s0 = ffma2(a0, G[NPAIRS - 1][0], s0);
+            s1 = ffma2(a0, G[NPAIRS - 1][1], s1);
+          }
+          float* dst = args.dP_aug + ((size_t)b * N + j) * p.ldp + (size_t)h * C + c0;
+          if (p.vec2_ok) {
+            *reinterpret_cast<float2*>(dst) = make_float2(s0.x + s0.y, s1.x + s1.y);
+          } else {
+            dst[0] = s0.x + s0.y;
+            if (has1) dst[1] = s1.x + s1.y;
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- B4: dv += dz'^T . edge rows -------------------------------------------------------------
+    for (int c = 0; c < ring.nchunks; ++c) {
+      const int s = c & 1;
+      const int rows = ring.rows_in(c);
+      if (p.bulk_ok) {
+        mbar_wait(&ring.full[s], ring.uses[s] & 1);
+        ring.uses[s]++;
+      } else {
+        const float* src = p.edge_rows + ((size_t)b * p.R + (size_t)c * ring.chunk_rows) * Fe;
+        for (int idx = tid; idx < rows * Fe; idx += kAttnThreads) ring.stage[s][idx] = src[idx];
+        __syncthreads();
+      }
+      if (dv_active) {
+        const float* Ts = ring.stage[s];
+        const int row_base = c * ring.chunk_rows;
+        for (int r = dv_rg; r < rows; r += dv_groups) {
+          const int code = table_s[row_base + r];
+          if (code < 0) continue;
+          const float tval = Ts[r * Fe + dv_f];
+          const float tval2 = dv_second ? Ts[r * Fe + dv_f + kAttnThreads] : 0.f;
+          const float* dz = D + (size_t)(code & 0xffff) * NS + (code >> 16);
+#pragma unroll
+          for (int h = 0; h < kMaxHeads; ++h) {
+            if (h < H) {
+              const float dzh = dz[(size_t)h * N * NS];
+              dv_acc[0][h] = fmaf(dzh, tval, dv_acc[0][h]);
+              dv_acc[1][h] = fmaf(dzh, tval2, dv_acc[1][h]);
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (p.bulk_ok && tid == 0 && c + 2 < ring.nchunks) ring.issue(b, c + 2);
+    }
+    if (p.bulk_ok && tid == 0 && b + (int)gridDim.x < p.B && ring.nchunks > 0)
+      ring.prefetch_first(b + gridDim.x);
+  }
+
+  // ---- per-CTA partials ---------------------------------------------------------------------------
+  // A CTA that issued a prefetch always consumes it (the prefetch is only issued for graphs it owns),
+  // so no bulk copy is in flight here and the union region can be reused.
+  __syncthreads();
+  if (Fe > 0) {
+    float* red = reinterpret_cast<float*>(uni);          // [2][kAttnThreads][kMaxHeads]
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) {
+      red[tid * kMaxHeads + h] = dv_acc[0][h];
+      red[(kAttnThreads + tid) * kMaxHeads + h] = dv_acc[1][h];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < H * Fe; idx += kAttnThreads) {
+      const int h = idx / Fe, f = idx - h * Fe;
+      float s = 0.f;
+      if (Fe <= kAttnThreads) {
+        for (int g = 0; g < dv_groups; ++g) s += red[(g * Fe + f) * kMaxHeads + h];
+      } else {
+        s = f < kAttnThreads ? red[f * kMaxHeads + h] : red[(kAttnThreads + f - kAttnThreads) * kMaxHeads + h];
+      }
+      args.dv_part[(size_t)blockIdx.x * H * Fe + idx] = s;
+    }
+  }
+  for (int idx = tid; idx < p.ldo; idx += kAttnThreads)
+    args.dbias_part[(size_t)blockIdx.x * p.ldo + idx] = dbias_s[idx];
+}
+
+__global__ void partial_reduce_kernel(const float* __restrict__ part, int nparts, int len,
+                                      float* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= len) return;
+  float s = 0.f;
+  for (int c = 0; c < nparts; ++c) s += part[(size_t)c * len + k];
+  out[k] = s;
+}
+
+template <int NPAIRS>
+static int launch_bwd(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const AttnParams& p = a.p;
+  // largest ring stage (multiple of 16 rows) that keeps two CTAs per SM, else one
+  BwdSmem sm = bwd_smem_plan(p.N, p.Fe, p.H, p.C, p.R, NPAIRS, p.concat, kBwdChunkRows);
+  for (int rows = kBwdChunkRows - 16; rows >= 16 && sm.total > 113 * 1024; rows -= 16)
+    sm = bwd_smem_plan(p.N, p.Fe, p.H, p.C, p.R, NPAIRS, p.concat, rows);
+  if (sm.total > 227 * 1024)
+    return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd needs %zu B shared memory (> 227 KB)", sm.total);
+  auto kern = gat_attn_bwd_kernel<NPAIRS>;
+  SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm.total));
+  int grid = 2 * sm_count();
+  if (grid > p.B) grid = p.B;
+  const size_t need = ((size_t)grid * ((size_t)p.H * p.Fe + p.ldo)) * sizeof(float);
+  if (!ws || ws_bytes < need)
+    return fail(SPOTV2_ERR_WORKSPACE, "attn_bwd needs %zu B of workspace, got %zu", need, ws_bytes);
+  a.dv_part = static_cast<float*>(ws);
+  a.dbias_part = a.dv_part + (size_t)grid * p.H * p.Fe;
+  kern<<<grid, kAttnThreads, sm.total, st>>>(a, sm);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  if (dv && p.Fe > 0) {
+    const int len = p.H * p.Fe;
+    partial_reduce_kernel<<<(len + 127) / 128, 128, 0, st>>>(a.dv_part, grid, len, dv);
+  }
+  if (dbias) partial_reduce_kernel<<<(p.ldo + 127) / 128, 128, 0, st>>>(a.dbias_part, grid, p.ldo, dbias);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
+}  // namespace spotv2
+
+using namespace spotv2;
+
+extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
+                                   const float* edge_rows, const int32_t* table, const float* v,
+                                   const float* dout, float* dP_aug, float* dv_or_null,
+                                   float* dbias_or_null, void* ws, size_t ws_bytes, void* stream) {
+  if (int rc = check_desc(d)) return rc;
+  SPOTV2_REQUIRE(P_aug && dout && dP_aug, "attn_bwd: P_aug, dout, dP_aug must be non-null");
+  SPOTV2_REQUIRE(d->Fe == 0 || (edge_rows && table && v),
+                 "attn_bwd: edge_rows, table and v are required when Fe > 0");
+  SPOTV2_REQUIRE(aligned16(P_aug) && aligned16(dout) && aligned16(dP_aug),
+                 "attn_bwd: P_aug/dout/dP_aug must be 16-byte aligned");
+  if (d->H > kMaxHeads) return fail(SPOTV2_ERR_UNSUPPORTED, "H=%d > %d", d->H, kMaxHeads);
+  if (d->Fe > kMaxFe) return fail(SPOTV2_ERR_UNSUPPORTED, "Fe=%d > %d", d->Fe, kMaxFe);
+  AttnBwdArgs a;
+  a.p.B = d->B; a.p.N = d->N; a.p.F = d->F; a.p.Fe = d->Fe; a.p.H = d->H; a.p.C = d->C;
+  a.p.R = d->R; a.p.concat = d->concat; a.p.ldp = d->ldp;
+  a.p.ldo = d->concat ? d->H * d->C : d->C;
+  a.p.slope = d->negative_slope;
+  a.p.P_aug = P_aug; a.p.edge_rows = edge_rows; a.p.table = table; a.p.v = v;
+  a.p.bulk_ok = d->Fe > 0 && aligned16(edge_rows) && ((size_t)d->R * d->Fe) % 4 == 0;
+  a.p.vec2_ok = (d->C % 2 == 0);
+  a.dout = dout; a.dP_aug = dP_aug; a.dv_part = nullptr; a.dbias_part = nullptr;
+  cudaStream_t st = as_stream(stream);
+  const int np = (d->N + 1) / 2;
+  if (np <= 4) return launch_bwd<4>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
+  if (np <= 8) return launch_bwd<8>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
+  if (np <= 15) return launch_bwd<15>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
+  if (np <= 16) return launch_bwd<16>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
+  return fail(SPOTV2_ERR_UNSUPPORTED, "N=%d > 32: the one-CTA-per-graph kernel covers N <= 32", d->N);
+}

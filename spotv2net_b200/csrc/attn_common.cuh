@@ -1,0 +1,222 @@
+// Pieces shared by the fused attention forward and backward kernels:
+// shared-memory carve-up, the edge-row ring (1-D bulk async copies), the 3xTF32
+// mma.sync edge-logit phase and the per-(head, target) softmax.
+#pragma once
+#include "common.cuh"
+
+namespace spotv2 {
+
+constexpr int kAttnThreads = 256;
+constexpr int kFwdChunkRows = 64; // edge rows per ring stage, forward  (4 m16 tiles)
+constexpr int kBwdChunkRows = 48; // edge rows per ring stage, backward (3 m16 tiles; smem budget)
+constexpr int kMaxHeads = 8;     // one n8 MMA tile of heads (reference HPO range is 2..7; config C uses 8)
+constexpr int kMaxFe = 512;
+
+struct AttnParams {
+  int B, N, F, Fe, H, C, R, concat, ldp, ldo;
+  float slope;
+  const float* P_aug;
+  const float* edge_rows;
+  const int32_t* table;
+  const float* v;
+  int bulk_ok;     // edge block 16-byte aligned and R*Fe % 4 == 0
+  int vec2_ok;     // C even (8-byte aligned channel pairs)
+};
+
+// Shared-memory plan common to both directions.  All offsets in bytes, 16-aligned.
+struct AttnSmem {
+  int NS;          // tile row stride over targets i (multiple of 4)
+  int KS;          // k-steps of 8 over Fe
+  int NT;          // n-tiles of 8 over H
+  int chunk_rows;  // edge rows per ring stage (multiple of 16)
+  size_t off_bar, off_table, off_vfrag, off_sd, off_tile, off_ring, ring_stage_bytes, base_total;
+};
+
+inline AttnSmem attn_smem_plan(int N, int Fe, int H, int R, int npairs, int chunk_rows) {
+  AttnSmem s;
+  s.chunk_rows = chunk_rows;
+  s.NS = (2 * npairs + 3) / 4 * 4;
+  s.KS = (Fe + 7) / 8;
+  s.NT = (H + 7) / 8;
+  size_t o = 0;
+  s.off_bar = o;   o += 64;
+  s.off_table = o; o += round_up((size_t)R * 4, 16);
+  s.off_vfrag = o; o += (size_t)s.NT * s.KS * 32 * 16;
+  s.off_sd = o;    o += round_up((size_t)N * 2 * H * 4, 16);
+  s.off_tile = o;  o += round_up((size_t)H * N * s.NS * 4, 16);
+  s.off_ring = o;
+  s.ring_stage_bytes = round_up((size_t)chunk_rows * Fe * 4, 128);
+  s.base_total = o;
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------
+// Edge-row ring: two stages of chunk_rows rows, filled by cp.async.bulk (thread 0 issues,
+// an mbarrier counts the bytes) or, for unaligned blocks, by a cooperative copy.
+struct EdgeRing {
+  float* stage[2];
+  uint64_t* full;       // [2]
+  uint32_t uses[2];     // completed waits per stage (uniform across the CTA)
+  int nchunks;
+  int chunk_rows;
+  const AttnParams* p;
+
+  __device__ __forceinline__ int rows_in(int c) const {
+    int r = p->R - c * chunk_rows;
+    return r < chunk_rows ? r : chunk_rows;
+  }
+  __device__ __forceinline__ void issue(int b, int c) {   // call from ONE thread
+    const int s = c & 1;
+    const uint32_t bytes = (uint32_t)rows_in(c) * p->Fe * 4u;
+    const float* src = p->edge_rows + ((size_t)b * p->R + (size_t)c * chunk_rows) * p->Fe;
+    mbar_expect_tx(&full[s], bytes);
+    bulk_g2s(stage[s], src, bytes, &full[s]);
+  }
+  __device__ __forceinline__ void prefetch_first(int b) {  // call from ONE thread
+    issue(b, 0);
+    if (nchunks > 1) issue(b, 1);
+  }
+};
+
+// v [H, Fe] -> B fragments of mma.m16n8k8 (col-major 8x8: b0 = (k=t, n=g), b1 = (k=t+4, n=g)),
+// pre-split into tf32 hi/lo:  vfrag[(nt*KS + ks)*32 + lane] = {b0_hi, b1_hi, b0_lo, b1_lo}.
+__device__ __forceinline__ void build_vfrag(float4* vfrag, const float* v, int H, int Fe, int KS,
+                                            int NT, int tid, int nthreads) {
+  for (int idx = tid; idx < NT * KS * 32; idx += nthreads) {
+    const int lane = idx & 31, ks = (idx >> 5) % KS, nt = (idx >> 5) / KS;
+    const int g = lane >> 2, t = lane & 3;
+    const int n = nt * 8 + g, k0 = ks * 8 + t, k1 = k0 + 4;
+    const float b0 = (n < H && k0 < Fe) ? v[n * Fe + k0] : 0.f;
+    const float b1 = (n < H && k1 < Fe) ? v[n * Fe + k1] : 0.f;
+    uint32_t h0, l0, h1, l1;
+    split_tf32(b0, h0, l0);
+    split_tf32(b1, h1, l1);
+    vfrag[idx] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0),
+                             __uint_as_float(l1));
+  }
+}
+
+// One warp: edge terms g[row, h] = <edge_row, v_h> for the 16 rows [m0, m0+16) of a staged chunk,
+// fp32-accurate through the 3xTF32 split (lo*hi + hi*lo + hi*hi, small terms first).
+// Results go to sink(row_in_chunk, head, value) for the rows/heads this lane owns.
+template <int NT_MAX, class Sink>
+__device__ __forceinline__ void warp_edge_logits(const float* Ts, const float4* vfrag, int Fe, int KS,
+                                                 int NT, int m0, int lane, Sink&& sink) {
+  const int g = lane >> 2, t = lane & 3;
+  float acc[NT_MAX][4];
+#pragma unroll
+  for (int nt = 0; nt < NT_MAX; ++nt)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[nt][q] = 0.f;
+  const float* r0 = Ts + (size_t)(m0 + g) * Fe;
+  const float* r1 = r0 + (size_t)8 * Fe;
+  for (int ks = 0; ks < KS; ++ks) {
+    const int k0 = ks * 8 + t, k1 = k0 + 4;
+    float a[4];
+    a[0] = k0 < Fe ? r0[k0] : 0.f;
+    a[1] = k0 < Fe ? r1[k0] : 0.f;
+    a[2] = k1 < Fe ? r0[k1] : 0.f;
+    a[3] = k1 < Fe ? r1[k1] : 0.f;
+    uint32_t ah[4], al[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split_tf32(a[q], ah[q], al[q]);
+#pragma unroll
+    for (int nt = 0; nt < NT_MAX; ++nt) {
+      if (nt < NT) {
+        const float4 bf = vfrag[(nt * KS + ks) * 32 + lane];
+        const uint32_t bh[2] = {__float_as_uint(bf.x), __float_as_uint(bf.y)};
+        const uint32_t bl[2] = {__float_as_uint(bf.z), __float_as_uint(bf.w)};
+        mma_tf32_16x8x8(acc[nt], al, bh);
+        mma_tf32_16x8x8(acc[nt], ah, bl);
+        mma_tf32_16x8x8(acc[nt], ah, bh);
+      }
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < NT_MAX; ++nt) {
+    if (nt < NT) {
+      const int n = nt * 8 + 2 * t;
+      sink(m0 + g, n, acc[nt][0]);
+      sink(m0 + g, n + 1, acc[nt][1]);
+      sink(m0 + g + 8, n, acc[nt][2]);
+      sink(m0 + g + 8, n + 1, acc[nt][3]);
+    }
+  }
+}
+
+// Phase 1 for one graph: stream the R edge rows through the ring and scatter the edge terms
+// into tile[h][j][i] (i contiguous, stride NS).  Ends with a __syncthreads().
+__device__ __forceinline__ void edge_logit_phase(EdgeRing& ring, const AttnParams& p,
+                                                 const AttnSmem& sm, float* tile,
+                                                 const int32_t* table_s, const float4* vfrag,
+                                                 int b, int tid) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const int N = p.N, H = p.H, NS = sm.NS;
+  for (int c = 0; c < ring.nchunks; ++c) {
+    const int s = c & 1;
+    const int rows = ring.rows_in(c);
+    if (p.bulk_ok) {
+      mbar_wait(&ring.full[s], ring.uses[s] & 1);
+      ring.uses[s]++;
+    } else {
+      const float* src = p.edge_rows + ((size_t)b * p.R + (size_t)c * ring.chunk_rows) * p.Fe;
+      for (int idx = tid; idx < rows * p.Fe; idx += kAttnThreads) ring.stage[s][idx] = src[idx];
+      __syncthreads();
+    }
+    if (warp * 16 < rows) {
+      const int row_base = c * ring.chunk_rows;
+      warp_edge_logits<1>(ring.stage[s], vfrag, p.Fe, sm.KS, sm.NT, warp * 16, lane,
+                          [&](int r, int h, float val) {
+                            if (r < rows && h < H) {
+                              const int code = table_s[row_base + r];
+                              if (code >= 0) tile[(h * N + (code & 0xffff)) * NS + (code >> 16)] = val;
+                            }
+                          });
+    }
+    __syncthreads();
+    if (p.bulk_ok && tid == 0 && c + 2 < ring.nchunks) ring.issue(b, c + 2);
+  }
+}
+
+// Phase 2: thread (h, i) turns the edge terms of target i into attention coefficients in place.
+//   g_ii = mean_{j != i} g_ij (PyG's fill_value='mean' self loop),  z = s_j + d_i + g_ij,
+//   l = leaky_relu(z),  alpha = softmax_j(l)  (max-subtracted, true division as in PyG).
+// tile[h][j][i] <- alpha * out_scale ; optional raw alpha to global ; optional z>0 mask bits.
+__device__ __forceinline__ void softmax_phase(const AttnParams& p, const AttnSmem& sm, float* tile,
+                                              const float* sd, float out_scale, float* alpha_out_b,
+                                              uint32_t* pos_mask, int tid) {
+  const int N = p.N, H = p.H, NS = sm.NS;
+  for (int idx = tid; idx < H * N; idx += kAttnThreads) {
+    const int h = idx / N, i = idx - h * N;
+    float* col = tile + (size_t)h * N * NS + i;
+    float gsum = 0.f;
+    for (int j = 0; j < N; ++j)
+      if (j != i) gsum += col[j * NS];
+    const float gii = gsum / (float)(N > 1 ? N - 1 : 1);
+    const float di = sd[i * 2 * H + H + h];
+    float mx = -INFINITY;
+    uint32_t mask = 0;
+    for (int j = 0; j < N; ++j) {
+      const float z = (j == i ? gii : col[j * NS]) + sd[j * 2 * H + h] + di;
+      if (z > 0.f) mask |= 1u << j;
+      const float l = z > 0.f ? z : z * p.slope;
+      mx = fmaxf(mx, l);
+      col[j * NS] = l;
+    }
+    float sum = 0.f;
+    for (int j = 0; j < N; ++j) {
+      const float e = expf(col[j * NS] - mx);
+      sum += e;
+      col[j * NS] = e;
+    }
+    sum += 1e-16f;
+    for (int j = 0; j < N; ++j) {
+      const float a = col[j * NS] / sum;
+      if (alpha_out_b) alpha_out_b[((size_t)h * N + j) * N + i] = a;
+      col[j * NS] = a * out_scale;
+    }
+    if (pos_mask) pos_mask[idx] = mask;
+  }
+}
+
+}  // namespace spotv2

@@ -1,0 +1,299 @@
+// Parameter folding / gradient unfolding, the edge-row table, the PyG-order view of the attention
+// tile and the device-side window collation.  All small, bandwidth-trivial kernels.
+#include "common.cuh"
+
+namespace spotv2 {
+
+// u[h][f] = sum_c W[(h*C + c)*F + f] * a[h][c] for the two attention vectors at once.
+__global__ void fold_u_kernel(const float* __restrict__ W, const float* __restrict__ a_src,
+                              const float* __restrict__ a_dst, float* __restrict__ u_src,
+                              float* __restrict__ u_dst, int H, int C, int F) {
+  const int h = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const float* Wh = W + (size_t)h * C * F + f;
+  float s0 = 0.f, s1 = 0.f, d0 = 0.f, d1 = 0.f;
+  int c = 0;
+  for (; c + 1 < C; c += 2) {
+    const float w0 = Wh[(size_t)c * F], w1 = Wh[(size_t)(c + 1) * F];
+    s0 = fmaf(w0, a_src[h * C + c], s0);
+    s1 = fmaf(w1, a_src[h * C + c + 1], s1);
+    d0 = fmaf(w0, a_dst[h * C + c], d0);
+    d1 = fmaf(w1, a_dst[h * C + c + 1], d1);
+  }
+  if (c < C) {
+    const float w0 = Wh[(size_t)c * F];
+    s0 = fmaf(w0, a_src[h * C + c], s0);
+    d0 = fmaf(w0, a_dst[h * C + c], d0);
+  }
+  u_src[(size_t)h * F + f] = s0 + s1;
+  u_dst[(size_t)h * F + f] = d0 + d1;
+}
+
+__global__ void fold_v_kernel(const float* __restrict__ We, const float* __restrict__ a_edge,
+                              float* __restrict__ v, int H, int C, int Fe) {
+  const int h = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= Fe) return;
+  const float* Wh = We + (size_t)h * C * Fe + f;
+  float s0 = 0.f, s1 = 0.f;
+  int c = 0;
+  for (; c + 1 < C; c += 2) {
+    s0 = fmaf(Wh[(size_t)c * Fe], a_edge[h * C + c], s0);
+    s1 = fmaf(Wh[(size_t)(c + 1) * Fe], a_edge[h * C + c + 1], s1);
+  }
+  if (c < C) s0 = fmaf(Wh[(size_t)c * Fe], a_edge[h * C + c], s0);
+  v[(size_t)h * Fe + f] = s0 + s1;
+}
+
+__device__ __forceinline__ float block_sum_128(float x, float* red) {
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = x;
+  __syncthreads();
+  return red[0] + red[1] + red[2] + red[3];
+}
+
+// One block (128 threads) per output row hc = h*C + c.
+__global__ void __launch_bounds__(128)
+unfold_kernel(const float* __restrict__ W, const float* __restrict__ a_src,
+              const float* __restrict__ a_dst, const float* __restrict__ We,
+              const float* __restrict__ a_edge, const float* __restrict__ dW_aug,
+              const float* __restrict__ dv, float* __restrict__ dW, float* __restrict__ da_src,
+              float* __restrict__ da_dst, float* __restrict__ dWe, float* __restrict__ da_edge,
+              int H, int C, int F, int Fe) {
+  __shared__ float red[4];
+  const int hc = blockIdx.x, h = hc / C;
+  const int HC = H * C;
+  const float as = a_src[hc], ad = a_dst[hc];
+  const float* dUs = dW_aug + (size_t)(HC + h) * F;
+  const float* dUd = dW_aug + (size_t)(HC + H + h) * F;
+  float ps = 0.f, pd = 0.f;
+  for (int f = threadIdx.x; f < F; f += 128) {
+    const float w = W[(size_t)hc * F + f];
+    const float us = dUs[f], ud = dUd[f];
+    dW[(size_t)hc * F + f] = dW_aug[(size_t)hc * F + f] + as * us + ad * ud;
+    ps = fmaf(w, us, ps);
+    pd = fmaf(w, ud, pd);
+  }
+  ps = block_sum_128(ps, red);
+  pd = block_sum_128(pd, red);
+  if (threadIdx.x == 0) { da_src[hc] = ps; da_dst[hc] = pd; }
+  if (Fe > 0) {
+    const float ae = a_edge[hc];
+    float pe = 0.f;
+    for (int f = threadIdx.x; f < Fe; f += 128) {
+      const float g = dv[(size_t)h * Fe + f];
+      dWe[(size_t)hc * Fe + f] = ae * g;
+      pe = fmaf(We[(size_t)hc * Fe + f], g, pe);
+    }
+    pe = block_sum_128(pe, red);
+    if (threadIdx.x == 0) da_edge[hc] = pe;
+  }
+}
+
+// ---- edge-row table ---------------------------------------------------------------------
+// status[0]=ok, [1]=first offending edge, [2]=reason (1 id out of range, 2 pattern differs between
+// graphs, 3 pair missing or duplicated), [3] unused; status[4 .. 4+N*N) = pair counts.
+__device__ __forceinline__ void table_fail(int32_t* status, int64_t where, int reason) {
+  atomicExch(&status[0], 0);
+  atomicMin(&status[1], (int)(where > 0x7fffffff ? 0x7fffffff : where));
+  atomicMax(&status[2], reason);
+}
+
+__global__ void table_init_kernel(int32_t* status, int NN) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0) { status[0] = 1; status[1] = 0x7fffffff; status[2] = 0; status[3] = 0; }
+  if (idx < NN) status[4 + idx] = 0;
+}
+
+__global__ void table_local_kernel(const int64_t* __restrict__ ei, int64_t E_total, int N, int R,
+                                   int32_t* __restrict__ table, int32_t* status) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int64_t src = ei[r], dst = ei[E_total + r];
+  if (src < 0 || src >= N || dst < 0 || dst >= N) {
+    table[r] = SPOTV2_ROW_SKIP;
+    table_fail(status, r, 1);
+    return;
+  }
+  if (src == dst) { table[r] = SPOTV2_ROW_SKIP; return; }
+  table[r] = (int32_t)((dst << 16) | src);
+  atomicAdd(&status[4 + dst * N + src], 1);
+}
+
+__global__ void table_repeat_kernel(const int64_t* __restrict__ ei, int64_t E_total, int N, int R,
+                                    int32_t* status) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E_total) return;
+  const int64_t b = e / R, r = e - b * R;
+  if (ei[e] - b * N != ei[r] || ei[E_total + e] - b * N != ei[E_total + r]) table_fail(status, e, 2);
+}
+
+__global__ void table_complete_kernel(int N, int32_t* status) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * N) return;
+  const int i = idx / N, j = idx - i * N;
+  if (i != j && status[4 + idx] != 1) table_fail(status, idx, 3);
+}
+
+__global__ void table_dense_kernel(int N, int32_t* table) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * N) return;
+  const int i = idx / N, j = idx - i * N;
+  table[idx] = i == j ? SPOTV2_ROW_SKIP : ((i << 16) | j);
+}
+
+// alpha tile [B, H, N(j), N(i)] -> [B*R rows in input order | B*N loops] x H
+__global__ void alpha_to_pyg_kernel(const float* __restrict__ tile, const int32_t* __restrict__ table,
+                                    float* __restrict__ out, int B, int N, int H, int R) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n_real = (int64_t)B * R * H, n_all = n_real + (int64_t)B * N * H;
+  if (idx >= n_all) return;
+  if (idx < n_real) {
+    const int h = idx % H;
+    const int64_t e = idx / H;
+    const int64_t b = e / R;
+    const int r = (int)(e - b * R);
+    const int code = table[r];
+    float a = 0.f;
+    if (code >= 0) a = tile[(((size_t)b * H + h) * N + (code & 0xffff)) * N + (code >> 16)];
+    out[idx] = a;
+  } else {
+    const int64_t k = idx - n_real;
+    const int h = k % H;
+    const int64_t node = k / H;
+    const int64_t b = node / N;
+    const int i = (int)(node - b * N);
+    out[idx] = tile[(((size_t)b * H + h) * N + i) * N + i];
+  }
+}
+
+// ---- window collation (utils/dataset.py:182-289 layouts) -------------
+__global__ void collate_x_kernel(const float* __restrict__ M_vol, const int32_t* __restrict__ t0,
+                                 int N, int L, float* __restrict__ x, float* __restrict__ y) {
+  const int node = blockIdx.x;            // b*N + i
+  const int b = node / N, i = node - b * N;
+  const int start = t0[b];
+  const int NL = N * L;
+  for (int k = threadIdx.x; k < NL; k += blockDim.x) {
+    const int c = k / L, t = k - c * L;
+    x[(size_t)node * NL + k] = M_vol[((size_t)(start + t) * N + i) * N + c];
+  }
+  if (threadIdx.x == 0) y[node] = M_vol[((size_t)(start + L) * N + i) * N + i];
+}
+
+__device__ __forceinline__ void tri_decode(int idx, int N, int& r, int& c) {
+  // idx = r*(2N-r-1)/2 + (c-r-1), r < c
+  const float fn = (float)(2 * N - 1);
+  r = (int)((fn - sqrtf(fn * fn - 8.f * (float)idx)) * 0.5f);
+  if (r < 0) r = 0;
+  while (r > 0 && r * (2 * N - r - 1) / 2 > idx) --r;
+  while ((r + 1) * (2 * N - r - 2) / 2 <= idx) ++r;
+  c = idx - r * (2 * N - r - 1) / 2 + r + 1;
+}
+
+__global__ void collate_edge_kernel(const float* __restrict__ M_vv, const int32_t* __restrict__ t0,
+                                    int N, int L, float* __restrict__ ea) {
+  const int E = N * (N - 1), half = E / 2;
+  const int b = blockIdx.y;
+  const int e = blockIdx.x;                // one block per edge row
+  int r, c;
+  tri_decode(e < half ? e : e - half, N, r, c);
+  const int src = e < half ? r : c, dst = e < half ? c : r;
+  const int start = t0[b];
+  float* row = ea + ((size_t)b * E + e) * 3 * L;
+  for (int k = threadIdx.x; k < 3 * L; k += blockDim.x) {
+    const int which = k / L, t = k - which * L;
+    const float* M = M_vv + (size_t)(start + t) * N * N;
+    row[k] = which == 0 ? M[r * N + c] : (which == 1 ? M[src * N + src] : M[dst * N + dst]);
+  }
+}
+
+}  // namespace spotv2
+
+using namespace spotv2;
+
+extern "C" int spotv2_gat_fold(const spotv2_gat_desc* d, const float* W, const float* a_src,
+                               const float* a_dst, const float* W_e, const float* a_edge,
+                               float* W_aug, float* v, void* stream) {
+  if (int rc = check_desc(d)) return rc;
+  SPOTV2_REQUIRE(W && a_src && a_dst && W_aug, "fold: W, a_src, a_dst, W_aug must be non-null");
+  SPOTV2_REQUIRE(d->Fe == 0 || (W_e && a_edge && v), "fold: W_e, a_edge, v required when Fe > 0");
+  cudaStream_t st = as_stream(stream);
+  const int HC = d->H * d->C;
+  SPOTV2_CUDA_OK(cudaMemcpyAsync(W_aug, W, (size_t)HC * d->F * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  dim3 g1((d->F + 127) / 128, d->H);
+  fold_u_kernel<<<g1, 128, 0, st>>>(W, a_src, a_dst, W_aug + (size_t)HC * d->F,
+                                    W_aug + (size_t)(HC + d->H) * d->F, d->H, d->C, d->F);
+  if (d->Fe > 0) {
+    dim3 g2((d->Fe + 127) / 128, d->H);
+    fold_v_kernel<<<g2, 128, 0, st>>>(W_e, a_edge, v, d->H, d->C, d->Fe);
+  }
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
+extern "C" int spotv2_gat_unfold(const spotv2_gat_desc* d, const float* W, const float* a_src,
+                                 const float* a_dst, const float* W_e, const float* a_edge,
+                                 const float* dW_aug, const float* dv, float* dW, float* da_src,
+                                 float* da_dst, float* dW_e, float* da_edge, void* stream) {
+  if (int rc = check_desc(d)) return rc;
+  SPOTV2_REQUIRE(W && a_src && a_dst && dW_aug && dW && da_src && da_dst, "unfold: null pointer");
+  SPOTV2_REQUIRE(d->Fe == 0 || (W_e && a_edge && dv && dW_e && da_edge),
+                 "unfold: edge pointers required when Fe > 0");
+  unfold_kernel<<<d->H * d->C, 128, 0, as_stream(stream)>>>(W, a_src, a_dst, W_e, a_edge, dW_aug, dv,
+                                                            dW, da_src, da_dst, dW_e, da_edge, d->H,
+                                                            d->C, d->F, d->Fe);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
+extern "C" int spotv2_edge_table_build(const int64_t* edge_index, int64_t num_edges, int32_t B,
+                                       int32_t N, int32_t R, int32_t* table, int32_t* status,
+                                       void* stream) {
+  SPOTV2_REQUIRE(edge_index && table && status, "edge_table_build: null pointer");
+  SPOTV2_REQUIRE(B > 0 && N > 0 && R > 0 && N <= 0xffff, "edge_table_build: bad B/N/R");
+  SPOTV2_REQUIRE(num_edges == (int64_t)B * R, "edge_table_build: num_edges=%lld != B*R=%lld",
+                 (long long)num_edges, (long long)B * R);
+  cudaStream_t st = as_stream(stream);
+  const int NN = N * N;
+  table_init_kernel<<<(NN + 255) / 256 + 1, 256, 0, st>>>(status, NN);
+  table_local_kernel<<<(R + 255) / 256, 256, 0, st>>>(edge_index, num_edges, N, R, table, status);
+  table_repeat_kernel<<<(unsigned)((num_edges + 255) / 256), 256, 0, st>>>(edge_index, num_edges, N, R, status);
+  table_complete_kernel<<<(NN + 255) / 256, 256, 0, st>>>(N, status);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
+extern "C" int spotv2_edge_table_dense(int32_t N, int32_t* table, void* stream) {
+  SPOTV2_REQUIRE(table && N > 0 && N <= 0xffff, "edge_table_dense: bad arguments");
+  table_dense_kernel<<<(N * N + 255) / 256, 256, 0, as_stream(stream)>>>(N, table);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
+extern "C" int spotv2_alpha_to_pyg(const spotv2_gat_desc* d, const float* alpha_tile,
+                                   const int32_t* table, float* alpha_pyg, void* stream) {
+  if (int rc = check_desc(d)) return rc;
+  SPOTV2_REQUIRE(alpha_tile && table && alpha_pyg, "alpha_to_pyg: null pointer");
+  const int64_t total = ((int64_t)d->B * d->R + (int64_t)d->B * d->N) * d->H;
+  alpha_to_pyg_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
+      alpha_tile, table, alpha_pyg, d->B, d->N, d->H, d->R);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
+extern "C" int spotv2_collate_windows(const float* M_vol, const float* M_vv, int32_t T, int32_t N,
+                                      int32_t L, const int32_t* t0, int32_t B, float* x,
+                                      float* edge_attr, float* y, void* stream) {
+  SPOTV2_REQUIRE(M_vol && M_vv && t0 && x && edge_attr && y, "collate_windows: null pointer");
+  SPOTV2_REQUIRE(T > L && N > 1 && L > 0 && B > 0, "collate_windows: need T > L, N > 1, L > 0, B > 0");
+  cudaStream_t st = as_stream(stream);
+  collate_x_kernel<<<B * N, 256, 0, st>>>(M_vol, t0, N, L, x, y);
+  dim3 ge(N * (N - 1), B);
+  collate_edge_kernel<<<ge, 128, 0, st>>>(M_vv, t0, N, L, edge_attr);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}

@@ -1,0 +1,21 @@
+// GEMM back ends of the projection path.
+#pragma once
+#include "common.cuh"
+
+namespace spotv2 {
+
+// Exact-fp32 CUDA-core GEMM: C[M,N] = sum_k A(m,k) B(n,k).  a_kc / b_kc: the operand is stored
+// K-contiguous ([rows, K]) rather than row-contiguous-in-M|N ([K, rows]).
+int sgemm_simt(bool a_kc, bool b_kc, int M, int N, int K, const float* A, int lda, const float* B,
+               int ldb, float* C, int ldc, int splits, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// Split-K factor used for the weight-gradient GEMM (contraction over all B*N node rows): keeps
+// every fp32 accumulation chain short (<= ~8K terms) and fills the machine.
+inline int weight_grad_splits(int rows) {
+  int s = (rows + 8191) / 8192;
+  if (s < 1) s = 1;
+  if (s > 32) s = 32;
+  return s;
+}
+
+}  // namespace spotv2

@@ -1,0 +1,184 @@
+// Exact-fp32 CUDA-core GEMM (packed FFMA2), the projection path for shapes the tensor-core
+// kernel does not cover (unaligned leading dimensions, tiny problems) and the parity yardstick
+// for it.  C[M,N] = sum_k A(m,k) * B(n,k); each operand is either K-contiguous (row = m|n) or
+// M|N-contiguous (row = k).  Optional split-K through a workspace, reduced in a fixed order.
+#include "gemm.cuh"
+
+namespace spotv2 {
+
+constexpr int BM = 128, BN = 128, BK = 16, PADM = 4;
+
+template <bool KC>
+__device__ __forceinline__ void load_tile(float4 (&reg)[2], const float* __restrict__ P, int ld,
+                                          int rows_total, int row0, int k0, int k_end, bool vec,
+                                          int tid) {
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int idx = tid + p * 256;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (KC) {            // P[(row0+r)*ld + k], 4 consecutive k per thread
+      const int r = idx >> 2, k = k0 + (idx & 3) * 4;
+      if (row0 + r < rows_total) {
+        const float* src = P + (size_t)(row0 + r) * ld + k;
+        if (vec && k + 3 < k_end) {
+          v = *reinterpret_cast<const float4*>(src);
+        } else {
+          if (k + 0 < k_end) v.x = src[0];
+          if (k + 1 < k_end) v.y = src[1];
+          if (k + 2 < k_end) v.z = src[2];
+          if (k + 3 < k_end) v.w = src[3];
+        }
+      }
+    } else {             // P[k*ld + row0 + r], 4 consecutive rows per thread
+      const int k = k0 + (idx >> 5), r = (idx & 31) * 4;
+      if (k < k_end) {
+        const float* src = P + (size_t)k * ld + row0 + r;
+        if (vec && row0 + r + 3 < rows_total) {
+          v = *reinterpret_cast<const float4*>(src);
+        } else {
+          if (row0 + r + 0 < rows_total) v.x = src[0];
+          if (row0 + r + 1 < rows_total) v.y = src[1];
+          if (row0 + r + 2 < rows_total) v.z = src[2];
+          if (row0 + r + 3 < rows_total) v.w = src[3];
+        }
+      }
+    }
+    reg[p] = v;
+  }
+}
+
+template <bool KC>
+__device__ __forceinline__ void store_tile(float (*S)[BM + PADM], const float4 (&reg)[2], int tid) {
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int idx = tid + p * 256;
+    if (KC) {
+      const int r = idx >> 2, k = (idx & 3) * 4;
+      S[k + 0][r] = reg[p].x;
+      S[k + 1][r] = reg[p].y;
+      S[k + 2][r] = reg[p].z;
+      S[k + 3][r] = reg[p].w;
+    } else {
+      const int k = idx >> 5, r = (idx & 31) * 4;
+      *reinterpret_cast<float4*>(&S[k][r]) = reg[p];
+    }
+  }
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(256, 2)
+sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B,
+             int ldb, float* __restrict__ C, int ldc, int k_per_split, size_t split_stride,
+             int vecA, int vecB) {
+  __shared__ __align__(16) float As[2][BK][BM + PADM];
+  __shared__ __align__(16) float Bs[2][BK][BN + PADM];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int k_begin = blockIdx.z * k_per_split;
+  const int k_end = min(K, k_begin + k_per_split);
+  float* Cout = C + (size_t)blockIdx.z * split_stride;
+
+  float2 acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+
+  float4 ra[2], rb[2];
+  load_tile<A_KC>(ra, A, lda, M, m0, k_begin, k_end, vecA, tid);
+  load_tile<B_KC>(rb, B, ldb, N, n0, k_begin, k_end, vecB, tid);
+  store_tile<A_KC>(As[0], ra, tid);
+  store_tile<B_KC>(Bs[0], rb, tid);
+  __syncthreads();
+
+  int buf = 0;
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+    const bool more = k0 + BK < k_end;
+    if (more) {
+      load_tile<A_KC>(ra, A, lda, M, m0, k0 + BK, k_end, vecA, tid);
+      load_tile<B_KC>(rb, B, ldb, N, n0, k0 + BK, k_end, vecB, tid);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float2 bp[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w),
+                            make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 ad = make_float2(a[i], a[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = ffma2(ad, bp[j], acc[i][j]);
+      }
+    }
+    if (more) {
+      store_tile<A_KC>(As[buf ^ 1], ra, tid);
+      store_tile<B_KC>(Bs[buf ^ 1], rb, tid);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + (j < 2 ? tx * 4 + 2 * j : 64 + tx * 4 + 2 * (j - 2));
+      float* dst = Cout + (size_t)m * ldc + n;
+      if (n < N) dst[0] = acc[i][j].x;
+      if (n + 1 < N) dst[1] = acc[i][j].y;
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, size_t split_stride,
+                                     int M, int N, float* __restrict__ C, int ldc) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)M * N) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += ws[(size_t)z * split_stride + idx];
+  const size_t m = idx / N, n = idx - m * N;
+  C[m * ldc + n] = s;
+}
+
+int sgemm_simt(bool a_kc, bool b_kc, int M, int N, int K, const float* A, int lda, const float* B,
+               int ldb, float* C, int ldc, int splits, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (splits < 1) splits = 1;
+  int k_per_split = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+  splits = (K + k_per_split - 1) / k_per_split;
+  float* out = C;
+  int ldo = ldc;
+  size_t stride = 0;
+  if (splits > 1) {
+    stride = (size_t)M * N;
+    if (!ws || ws_bytes < stride * splits * sizeof(float))
+      return fail(SPOTV2_ERR_WORKSPACE, "split-K GEMM needs %zu B of workspace, got %zu",
+                  stride * splits * sizeof(float), ws_bytes);
+    out = static_cast<float*>(ws);
+    ldo = N;
+  }
+  const int vecA = aligned16(A) && lda % 4 == 0, vecB = aligned16(B) && ldb % 4 == 0;
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
+#define SPOTV2_LAUNCH(AK, BK_)                                                                 \
+  sgemm_kernel<AK, BK_><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, out, ldo, k_per_split,  \
+                                              stride, vecA, vecB)
+  if (a_kc && b_kc) SPOTV2_LAUNCH(true, true);
+  else if (a_kc && !b_kc) SPOTV2_LAUNCH(true, false);
+  else if (!a_kc && b_kc) SPOTV2_LAUNCH(false, true);
+  else SPOTV2_LAUNCH(false, false);
+#undef SPOTV2_LAUNCH
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  if (splits > 1) {
+    const size_t total = (size_t)M * N;
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, splits, stride, M, N, C, ldc);
+    SPOTV2_CUDA_OK(cudaGetLastError());
+  }
+  return SPOTV2_OK;
+}
+
+}  // namespace spotv2

@@ -1,0 +1,167 @@
+"""Graph-batch collation on the device.
+
+Replaces, for the default (fully connected, single-output) configuration, the reference's
+``CovarianceLaggedDataset`` + PyG ``DataLoader`` / ``Batch.from_data_list`` pair
+(/root/reference/utils/dataset.py:160-289; 5_train_SpotV2Net.py:66-91,142-143): instead of
+materialising every windowed graph on the host, caching it with ``torch.save`` and concatenating
+samples one by one in Python, the two ``[T, N, N]`` matrix stacks stay resident in HBM and each
+batch is gathered straight into the reference's tensor layouts by one CUDA kernel launch pair
+(``spotv2_collate_windows``).  A batch quacks like a PyG ``Batch`` (``x``, ``edge_index``,
+``edge_attr``, ``y_x``, ``batch``, ``ptr``, ``num_graphs``, ``to()``), so ``GATModel.forward``
+and the reference's training loop consume it unchanged, and it carries the validated topology
+so no per-batch edge_index check is needed.
+"""
+from __future__ import annotations
+
+from typing import Iterator, Optional, Sequence
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import SpotV2Error, check, ptr, stream_ptr
+from .gat_conv import Topology, topology_from_edge_index
+
+REFERENCE_DROP_FIRST = 8357          # hard-coded cut at utils/dataset.py:288
+
+
+def complete_graph_edge_index(N: int) -> Tensor:
+    """Local edge_index [2, N(N-1)] in the reference's order (utils/dataset.py:216-226):
+    upper-triangle pairs (r < c, row-major) as r -> c, then the same pairs as c -> r."""
+    iu = torch.triu_indices(N, N, offset=1)
+    return torch.cat([iu, iu.flip(0)], dim=1)
+
+
+class SpotBatch:
+    """Duck-typed PyG ``Batch`` for identical complete graphs."""
+
+    def __init__(self, x, edge_index, edge_attr, y_x, num_graphs, nodes_per_graph, spot_topology=None):
+        self.x, self.edge_index, self.edge_attr, self.y_x = x, edge_index, edge_attr, y_x
+        self.num_graphs, self.nodes_per_graph, self.spot_topology = num_graphs, nodes_per_graph, spot_topology
+
+    @property
+    def batch(self) -> Tensor:
+        return torch.arange(self.num_graphs, device=self.x.device).repeat_interleave(self.nodes_per_graph)
+
+    @property
+    def ptr(self) -> Tensor:
+        return torch.arange(self.num_graphs + 1, device=self.x.device) * self.nodes_per_graph
+
+    def to(self, device, non_blocking: bool = False):
+        device = torch.device(device)
+        if device == self.x.device:
+            return self
+        moved = [t.to(device, non_blocking=non_blocking) for t in (self.x, self.edge_index, self.edge_attr, self.y_x)]
+        return SpotBatch(*moved, self.num_graphs, self.nodes_per_graph, None)
+
+
+_EDGE_CACHE: dict = {}
+
+
+def batched_topology(B: int, N: int, device) -> tuple[Tensor, Topology]:
+    """edge_index [2, B*N*(N-1)] for B copies of the complete graph plus its validated table (cached)."""
+    key = (B, N, torch.device(device))
+    hit = _EDGE_CACHE.get(key)
+    if hit is None:
+        local = complete_graph_edge_index(N).to(device)
+        offs = (torch.arange(B, device=device) * N).view(1, B, 1)
+        ei = (local.view(2, 1, -1) + offs).reshape(2, -1).contiguous()
+        hit = (ei, topology_from_edge_index(ei, B * N, N))
+        if len(_EDGE_CACHE) > 16:
+            _EDGE_CACHE.clear()
+        _EDGE_CACHE[key] = hit
+    return hit
+
+
+def load_matrix_stack(path: str) -> np.ndarray:
+    """[T, N, N] float64 stack from the reference's H5 layout (keys '0'..'T-1', one N x N matrix
+    each; 3_create_matrix_dataset.py:215-222) or from a .npy file."""
+    if str(path).endswith(".npy"):
+        return np.load(path)
+    try:
+        import h5py  # not in this image; present wherever the reference runs
+    except ImportError as e:
+        raise SpotV2Error(f"reading {path} needs h5py, which is not installed; pass arrays or .npy instead") from e
+    with h5py.File(path, "r") as f:
+        keys = sorted(f.keys(), key=int)
+        return np.stack([np.asarray(f[k]) for k in keys])
+
+
+class WindowDataset:
+    """Device-resident equivalent of ``CovarianceLaggedDataset`` (utils/dataset.py:160-289).
+
+    Sample ``k`` is the window starting at ``t0 = k + drop_first``: ``x[i, c*L + t] = vol[t0+t, i, c]``,
+    ``edge_attr[e, k*L + t]`` = (volvol[t0+t, r, c], volvol[.., src, src], volvol[.., dst, dst]),
+    ``y_x[i] = vol[t0+L, i, i]``.
+    """
+
+    def __init__(self, vol, volvol, seq_length: int, device="cuda", drop_first: int = REFERENCE_DROP_FIRST):
+        vol = torch.as_tensor(np.asarray(vol) if not torch.is_tensor(vol) else vol)
+        volvol = torch.as_tensor(np.asarray(volvol) if not torch.is_tensor(volvol) else volvol)
+        if vol.shape != volvol.shape or vol.dim() != 3 or vol.shape[1] != vol.shape[2]:
+            raise SpotV2Error("vol and volvol must both be [T, N, N]")
+        self.T, self.N = int(vol.shape[0]), int(vol.shape[1])
+        self.L = int(seq_length)
+        self.drop_first = int(drop_first)
+        if self.T - self.L - self.drop_first <= 0:
+            raise SpotV2Error(f"T={self.T} too short for seq_length={self.L} and drop_first={self.drop_first}")
+        self.device = torch.device(device)
+        self.vol = vol.to(self.device, torch.float32).contiguous()          # numpy float64 -> fp32, as torch.tensor(.., dtype=float)
+        self.volvol = volvol.to(self.device, torch.float32).contiguous()
+        self.num_node_features = self.N * self.L
+        self.num_edge_features = 3 * self.L
+
+    def __len__(self) -> int:
+        return self.T - self.L - self.drop_first
+
+    def collate(self, indices: Sequence[int] | Tensor) -> SpotBatch:
+        idx = torch.as_tensor(indices, dtype=torch.int64)
+        if idx.numel() == 0:
+            raise SpotV2Error("empty batch")
+        if int(idx.min()) < 0 or int(idx.max()) >= len(self):
+            raise IndexError("sample index out of range")
+        B, N, L = int(idx.numel()), self.N, self.L
+        t0 = (idx + self.drop_first).to(torch.int32).to(self.device)
+        dev = self.device
+        x = torch.empty(B * N, N * L, device=dev, dtype=torch.float32)
+        ea = torch.empty(B * N * (N - 1), 3 * L, device=dev, dtype=torch.float32)
+        y = torch.empty(B * N, device=dev, dtype=torch.float32)
+        lib = _lib.load()
+        check(lib.spotv2_collate_windows(ptr(self.vol), ptr(self.volvol), self.T, N, L, ptr(t0), B, ptr(x), ptr(ea),
+                                         ptr(y), stream_ptr(dev)), "spotv2_collate_windows")
+        ei, topo = batched_topology(B, N, dev)
+        return SpotBatch(x, ei, ea, y, B, N, topo)
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return _Subset(self, range(*k.indices(len(self))))
+        return self.collate([int(k)])
+
+
+class _Subset:
+    def __init__(self, ds: WindowDataset, rng: range):
+        self.ds, self.rng = ds, rng
+
+    def __len__(self):
+        return len(self.rng)
+
+    def collate(self, indices):
+        base = torch.as_tensor(indices, dtype=torch.int64)
+        return self.ds.collate(base * self.rng.step + self.rng.start)
+
+
+class WindowLoader:
+    """``DataLoader(dataset, batch_size, shuffle)`` stand-in (5_train_SpotV2Net.py:90-91)."""
+
+    def __init__(self, dataset, batch_size: int = 1, shuffle: bool = False, generator: Optional[torch.Generator] = None):
+        self.dataset, self.batch_size, self.shuffle, self.generator = dataset, int(batch_size), shuffle, generator
+
+    def __len__(self) -> int:
+        return (len(self.dataset) + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self) -> Iterator[SpotBatch]:
+        n = len(self.dataset)
+        order = torch.randperm(n, generator=self.generator) if self.shuffle else torch.arange(n)
+        for s in range(0, n, self.batch_size):
+            yield self.dataset.collate(order[s:s + self.batch_size])

@@ -1,0 +1,317 @@
+"""Drop-in ``GATConv`` for batches of identical complete graphs, backed by libspotv2_gat.so.
+
+Constructor kwargs, ``forward(x, edge_index, edge_attr=None, size=None,
+return_attention_weights=None)``, parameter names and init follow PyG 2.3.0
+``torch_geometric.nn.GATConv`` as the reference uses it
+(/root/reference/utils/models.py:11,87-113,146; 6_results.ipynb:213), so
+``state_dict`` files saved by the reference (5_train_SpotV2Net.py:195) load
+unchanged.  All arithmetic runs in the hand-written sm_100a kernels; there is
+no eager or CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+from ._lib import GatDesc, SpotV2Error, check, ptr, stream_ptr
+
+
+# --------------------------------------------------------------------------- topology
+@dataclass
+class Topology:
+    """What the kernels need to know about ``edge_index``: B graphs of N nodes,
+    R edge rows per graph, and the row table (row -> target/source)."""
+    B: int
+    N: int
+    R: int
+    table: Tensor          # int32 [R] on the device
+    has_skips: bool        # some rows are self loops (dropped by PyG's remove_self_loops)
+
+
+_TOPO_CACHE: dict = {}
+_REASONS = {1: "node id outside [0, N) in the first graph",
+            2: "a graph's edge pattern differs from the first graph's",
+            3: "an ordered pair i != j is missing or duplicated (graph is not complete)"}
+
+
+def _try_topology(edge_index: Tensor, n_nodes: int, N: int) -> Optional[Topology]:
+    E = edge_index.shape[1]
+    if N <= 0 or n_nodes % N:
+        return None
+    B = n_nodes // N
+    if B <= 0 or E % B:
+        return None
+    R = E // B
+    if R < N * (N - 1):
+        return None
+    lib = _lib.load()
+    dev = edge_index.device
+    table = torch.empty(R, dtype=torch.int32, device=dev)
+    status = torch.empty(4 + N * N, dtype=torch.int32, device=dev)
+    check(lib.spotv2_edge_table_build(ptr(edge_index), E, B, N, R, ptr(table), ptr(status), stream_ptr(dev)),
+          "spotv2_edge_table_build")
+    ok, where, reason = status[:3].tolist()              # one sync per new topology
+    if not ok:
+        _try_topology.last_failure = f"{_REASONS.get(reason, reason)} (first offending index {where})"
+        return None
+    return Topology(B, N, R, table, bool((table < 0).any().item()))
+
+
+_try_topology.last_failure = ""
+
+
+def topology_from_edge_index(edge_index: Tensor, n_nodes: int, nodes_per_graph: Optional[int] = None) -> Topology:
+    """Validate ``edge_index`` [2, E] (PyG concatenated order) as B identical
+    complete graphs and build the row table.  Cached per tensor identity."""
+    if edge_index.dim() != 2 or edge_index.shape[0] != 2 or edge_index.dtype != torch.int64:
+        raise SpotV2Error("edge_index must be an int64 tensor of shape [2, E]")
+    _lib.require_cuda(edge_index, "edge_index")
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, edge_index.device, n_nodes,
+           nodes_per_graph)
+    hit = _TOPO_CACHE.get(key)
+    if hit is not None:
+        return hit
+    edge_index = edge_index.contiguous()
+    E = edge_index.shape[1]
+    cands = [nodes_per_graph] if nodes_per_graph else []
+    if not cands and n_nodes > 0 and E % n_nodes == 0:
+        cands = [E // n_nodes + 1, E // n_nodes]          # without / with self loops in the input
+    topo = None
+    for N in cands:
+        topo = _try_topology(edge_index, n_nodes, int(N))
+        if topo is not None:
+            break
+    if topo is None:
+        raise SpotV2Error(
+            "edge_index is not a batch of identical complete directed graphs "
+            f"(n_nodes={n_nodes}, E={E}; {_try_topology.last_failure or 'sizes do not factor'}). "
+            "Sparse / irregular graphs (CovarianceSparseDataset) are outside this library's scope; "
+            "there is no generic fallback.")
+    if len(_TOPO_CACHE) > 64:
+        _TOPO_CACHE.clear()
+    _TOPO_CACHE[key] = topo
+    return topo
+
+
+# --------------------------------------------------------------------------- autograd
+def _desc(topo: Topology, F_in: int, Fe: int, H: int, Cc: int, concat: bool, slope: float) -> GatDesc:
+    lib = _lib.load()
+    return GatDesc(topo.B, topo.N, F_in, Fe, H, Cc, topo.R, int(concat), float(slope),
+                   lib.spotv2_gat_ldp(H, Cc), 0, 0)
+
+
+def _workspace(desc: GatDesc):
+    lib = _lib.load()
+    a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    check(lib.spotv2_gat_workspace_bytes(C.byref(desc), C.byref(a), C.byref(b), C.byref(c)), "workspace_bytes")
+    return a.value, b.value, c.value
+
+
+class _GatLayerFn(torch.autograd.Function):
+    """fold -> projection GEMM -> fused attention, and the recompute-based backward."""
+
+    @staticmethod
+    def forward(ctx, x, edge_attr, W, a_src, a_dst, W_e, a_edge, bias, topo, H, Cc, concat, slope, want_alpha):
+        lib = _lib.load()
+        dev = x.device
+        st = stream_ptr(dev)
+        Fe = 0 if edge_attr is None or W_e is None else edge_attr.shape[1]
+        desc = _desc(topo, x.shape[1], Fe, H, Cc, concat, slope)
+        n, HC = x.shape[0], H * Cc
+        x = x.contiguous()
+        ea = edge_attr.contiguous() if Fe else None
+        W, a_src, a_dst = W.contiguous(), a_src.contiguous(), a_dst.contiguous()
+        W_aug = torch.empty(HC + 2 * H, x.shape[1], device=dev, dtype=torch.float32)
+        v = torch.empty(H, Fe, device=dev, dtype=torch.float32) if Fe else None
+        check(lib.spotv2_gat_fold(C.byref(desc), ptr(W), ptr(a_src), ptr(a_dst),
+                                  ptr(W_e.contiguous()) if Fe else None, ptr(a_edge.contiguous()) if Fe else None,
+                                  ptr(W_aug), ptr(v), st), "spotv2_gat_fold")
+        ws_f, _, _ = _workspace(desc)
+        ws = torch.empty(ws_f, device=dev, dtype=torch.uint8)
+        P_aug = torch.empty(n, desc.ldp, device=dev, dtype=torch.float32)
+        check(lib.spotv2_proj_fwd(C.byref(desc), ptr(x), ptr(W_aug), ptr(P_aug), ptr(ws), ws_f, st), "spotv2_proj_fwd")
+        out = torch.empty(n, HC if concat else Cc, device=dev, dtype=torch.float32)
+        alpha = torch.empty(topo.B, H, topo.N, topo.N, device=dev, dtype=torch.float32) if want_alpha else None
+        check(lib.spotv2_gat_attn_fwd(C.byref(desc), ptr(P_aug), ptr(ea), ptr(topo.table) if Fe else None, ptr(v),
+                                      ptr(bias.contiguous()) if bias is not None else None, ptr(out), ptr(alpha), st),
+              "spotv2_gat_attn_fwd")
+        ctx.desc, ctx.topo, ctx.Fe, ctx.has_bias = desc, topo, Fe, bias is not None
+        ctx.save_for_backward(x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug)
+        if want_alpha:
+            ctx.mark_non_differentiable(alpha)
+            return out, alpha
+        return out, None
+
+    @staticmethod
+    def backward(ctx, dout, _dalpha=None):
+        lib = _lib.load()
+        x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug = ctx.saved_tensors
+        desc, topo, Fe = ctx.desc, ctx.topo, ctx.Fe
+        if ctx.needs_input_grad[1]:
+            raise SpotV2Error("gradient w.r.t. edge_attr is not provided (the reference never needs it)")
+        dev = x.device
+        st = stream_ptr(dev)
+        H, Cc = desc.H, desc.C
+        HC = H * Cc
+        dout = dout.contiguous()
+        _, ws_a, ws_p = _workspace(desc)
+        ws = torch.empty(max(ws_a, ws_p), device=dev, dtype=torch.uint8)
+        dP_aug = torch.empty_like(P_aug)
+        dv = torch.empty(H, Fe, device=dev, dtype=torch.float32) if Fe else None
+        dbias = torch.empty(dout.shape[1], device=dev, dtype=torch.float32) if ctx.has_bias else None
+        check(lib.spotv2_gat_attn_bwd(C.byref(desc), ptr(P_aug), ptr(ea), ptr(topo.table) if Fe else None, ptr(v),
+                                      ptr(dout), ptr(dP_aug), ptr(dv), ptr(dbias), ptr(ws), ws.numel(), st),
+              "spotv2_gat_attn_bwd")
+        dW_aug = torch.empty_like(W_aug)
+        check(lib.spotv2_proj_bwd_weight(C.byref(desc), ptr(x), ptr(dP_aug), ptr(dW_aug), ptr(ws), ws.numel(), st),
+              "spotv2_proj_bwd_weight")
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            check(lib.spotv2_proj_bwd_input(C.byref(desc), ptr(dP_aug), ptr(W_aug), ptr(dx), ptr(ws), ws.numel(), st),
+                  "spotv2_proj_bwd_input")
+        dW = torch.empty_like(W)
+        da_src = torch.empty_like(a_src)
+        da_dst = torch.empty_like(a_dst)
+        dW_e = torch.empty_like(W_e) if Fe else None
+        da_edge = torch.empty_like(a_edge) if Fe else None
+        check(lib.spotv2_gat_unfold(C.byref(desc), ptr(W), ptr(a_src), ptr(a_dst), ptr(W_e) if Fe else None,
+                                    ptr(a_edge) if Fe else None, ptr(dW_aug), ptr(dv), ptr(dW), ptr(da_src),
+                                    ptr(da_dst), ptr(dW_e), ptr(da_edge), st), "spotv2_gat_unfold")
+        if not Fe and W_e is not None:          # layer has lin_edge but was called with edge_attr=None
+            dW_e, da_edge = torch.zeros_like(W_e), torch.zeros_like(a_edge)
+        return (dx, None, dW, da_src, da_dst, dW_e, da_edge, dbias, None, None, None, None, None, None)
+
+
+# --------------------------------------------------------------------------- module
+def _glorot_(t: Tensor) -> Tensor:
+    bound = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+    with torch.no_grad():
+        return t.uniform_(-bound, bound)
+
+
+class _Linear(nn.Module):
+    """Weight holder named like PyG's ``Linear(bias=False, weight_initializer='glorot')``."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        _glorot_(self.weight)
+
+    def extra_repr(self):
+        return f"{self.in_channels}, {self.out_channels}, bias=False"
+
+
+class GATConv(nn.Module):
+    """``GATConv(in_channels, out_channels, heads=1, concat=True, negative_slope=0.2,
+    dropout=0.0, add_self_loops=True, edge_dim=None, fill_value='mean', bias=True)``.
+
+    State-dict keys: ``att_src, att_dst, att_edge, bias, lin_src.weight,
+    lin_dst.weight`` (alias of lin_src, as in PyG 2.3.0), ``lin_edge.weight``.
+    """
+
+    def __init__(self, in_channels: int, out_channels: int, heads: int = 1, concat: bool = True,
+                 negative_slope: float = 0.2, dropout: float = 0.0, add_self_loops: bool = True,
+                 edge_dim: Optional[int] = None, fill_value="mean", bias: bool = True, **kwargs):
+        super().__init__()
+        if not isinstance(in_channels, int):
+            raise SpotV2Error("bipartite (tuple) in_channels are outside this library's scope")
+        if not add_self_loops or fill_value != "mean":
+            raise SpotV2Error("only add_self_loops=True with fill_value='mean' (the PyG defaults the "
+                              "reference relies on) is implemented")
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.concat, self.negative_slope, self.dropout = concat, negative_slope, dropout
+        self.add_self_loops, self.edge_dim, self.fill_value = add_self_loops, edge_dim, fill_value
+        self.lin_src = _Linear(in_channels, heads * out_channels)
+        self.lin_dst = self.lin_src
+        self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
+        if edge_dim is not None:
+            self.lin_edge = _Linear(edge_dim, heads * out_channels)
+            self.att_edge = nn.Parameter(torch.empty(1, heads, out_channels))
+        else:
+            self.lin_edge = None
+            self.register_parameter("att_edge", None)
+        if bias:
+            self.bias = nn.Parameter(torch.empty(heads * out_channels if concat else out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.nodes_per_graph: Optional[int] = None     # optional hint; inferred from edge_index otherwise
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        # same RNG draw order as PyG 2.3.0
+        self.lin_src.reset_parameters()
+        self.lin_dst.reset_parameters()
+        if self.lin_edge is not None:
+            self.lin_edge.reset_parameters()
+        _glorot_(self.att_src)
+        _glorot_(self.att_dst)
+        if self.att_edge is not None:
+            _glorot_(self.att_edge)
+        if self.bias is not None:
+            with torch.no_grad():
+                self.bias.zero_()
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # PyG >= 2.5 checkpoints name the shared projection `lin.weight`
+        if prefix + "lin.weight" in state_dict and prefix + "lin_src.weight" not in state_dict:
+            w = state_dict.pop(prefix + "lin.weight")
+            state_dict[prefix + "lin_src.weight"] = w
+            state_dict[prefix + "lin_dst.weight"] = w
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def forward(self, x: Tensor, edge_index, edge_attr: Optional[Tensor] = None, size=None,
+                return_attention_weights=None, topology: Optional[Topology] = None):
+        assert x.dim() == 2, "Static graphs not supported in 'GATConv'"
+        _lib.require_cuda(x, "x")
+        if self.dropout > 0.0 and self.training:
+            raise SpotV2Error("attention dropout (dropout_att > 0) in training mode is not implemented yet; "
+                              "the reference default is 0.0 (config/GNN_param.yaml:36)")
+        if edge_attr is not None:
+            _lib.require_cuda(edge_attr, "edge_attr")
+            if edge_attr.dim() == 1:
+                edge_attr = edge_attr.view(-1, 1)
+        topo = topology or topology_from_edge_index(edge_index, x.shape[0], self.nodes_per_graph)
+        use_edge = edge_attr is not None and self.lin_edge is not None
+        if use_edge and edge_attr.shape[0] != topo.B * topo.R:
+            raise SpotV2Error(f"edge_attr has {edge_attr.shape[0]} rows, edge_index has {topo.B * topo.R} edges")
+        want_alpha = isinstance(return_attention_weights, bool)
+        out, alpha_tile = _GatLayerFn.apply(
+            x, edge_attr if use_edge else None, self.lin_src.weight, self.att_src, self.att_dst,
+            self.lin_edge.weight if self.lin_edge is not None else None, self.att_edge, self.bias,
+            topo, self.heads, self.out_channels, self.concat, self.negative_slope, want_alpha)
+        if not want_alpha:
+            return out
+        return out, self._attention_weights(alpha_tile, topo, edge_index)
+
+    def _attention_weights(self, alpha_tile: Tensor, topo: Topology, edge_index: Tensor):
+        """(edge_index with self loops appended, alpha [E', H]) in PyG order (App. A.4)."""
+        lib = _lib.load()
+        dev = alpha_tile.device
+        H = self.heads
+        desc = GatDesc(topo.B, topo.N, self.in_channels, 0, H, self.out_channels, topo.R, int(self.concat),
+                       float(self.negative_slope), lib.spotv2_gat_ldp(H, self.out_channels), 0, 0)
+        n = topo.B * topo.N
+        alpha = torch.empty(topo.B * topo.R + n, H, device=dev, dtype=torch.float32)
+        check(lib.spotv2_alpha_to_pyg(C.byref(desc), ptr(alpha_tile), ptr(topo.table), ptr(alpha), stream_ptr(dev)),
+              "spotv2_alpha_to_pyg")
+        loops = torch.arange(n, device=dev, dtype=edge_index.dtype)
+        if topo.has_skips:                               # PyG drops input self loops before appending its own
+            keep = edge_index[0] != edge_index[1]
+            edge_index = edge_index[:, keep]
+            alpha = torch.cat([alpha[:topo.B * topo.R][keep], alpha[topo.B * topo.R:]], 0)
+        return torch.cat([edge_index, torch.stack([loops, loops])], 1), alpha
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels}, heads={self.heads})"
