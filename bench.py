@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the SpotV2Net GAT hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # reference arm: the CPU oracle port
+
+A step = GATConv forward + backward (fold -> projection GEMM -> fused attention -> fused attention
+backward with recompute -> weight-gradient GEMM -> unfold [-> NCCL all-reduce of the flat gradient
+arena when N > 1]) over one batch of 4096 synthetic 30-node complete graphs of the standardized H5
+shape, default config/GNN_param.yaml hyper-parameters (BASELINE.json configs[1]), fp32.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SpotV2Net GAT fwd+bwd graphs/sec (30-node, batch 4096)"
+UNIT = "graphs/s"
+# SURVEY.md §8d / BASELINE.md §4, fp32, default geometry (N=30, Fe=126, H=6, C=500)
+ATTN_BYTES_FWD = 858_480
+ATTN_BYTES_BWD = 1_218_480
+PROJ_FLOP_PER_GRAPH = 2 * 226_800_000           # P = x W^T and dW = dP^T x
+CFG = dict(N=30, L=42, H=6, C=500, slope=0.2, concat=False)
+
+
+def cfg_dims():
+    N, L = CFG["N"], CFG["L"]
+    return N, N * L, 3 * L, CFG["H"], CFG["C"]
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU oracle arm
+def oracle_step_factory(B: int, seed: int = 1234):
+    from oracle import pyg_gat, synth
+    N, Fin, Fe, H, Cc = cfg_dims()
+    vol, vv = synth.synthetic_matrices(CFG["L"] + B + 1, N, seed=seed)
+    bt = synth.make_batch(vol, vv, list(range(B)), CFG["L"])
+    torch.manual_seed(seed)
+    layer = pyg_gat.OracleGATConv(Fin, Cc, heads=H, concat=False, negative_slope=CFG["slope"], edge_dim=Fe)
+    dout = torch.randn(B * N, Cc)
+
+    def step():
+        layer.zero_grad(set_to_none=True)
+        out = layer(bt.x, bt.edge_index, bt.edge_attr)
+        out.backward(dout)
+        return out
+    return step
+
+
+def time_oracle(B: int, steps: int, warmup: int):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = oracle_step_factory(B)
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter(); step(); ts.append(time.perf_counter() - t0)
+    return B / statistics.median(ts), cores, ts
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.cpu_batch
+    gps, cores, ts = time_oracle(B, max(1, args.steps), max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * statistics.median(ts), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"default GNN_param.yaml GATConv fwd+bwd; CPU sample of {B} graphs per step "
+                               f"(the 4096-graph batch needs >88 GB of PyG intermediates on a CPU)",
+                   "nodes": 30, "heads": 6, "hidden": 500, "seq_length": 42},
+        "cpu_baseline": {"value": gps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{B} graphs/step, {args.steps} steps, PyG-2.3.0-order torch eager restatement "
+                                   "(PyG itself is not installable here)"},
+        "e2e": {"value": gps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+class HotPath:
+    """The hot path through the C ABI on preallocated buffers (what GATConv.forward/backward call)."""
+
+    def __init__(self, B: int, device, seed: int):
+        import spotv2net_b200 as sv
+        from spotv2net_b200 import _lib
+        self.sv, self._lib = sv, _lib
+        self.lib = sv.load_library()
+        self.dev = device
+        N, Fin, Fe, H, Cc = cfg_dims()
+        self.B, self.N, self.Fin, self.Fe, self.H, self.Cc = B, N, Fin, Fe, H, Cc
+        g = torch.Generator(device=device).manual_seed(seed)
+        T = B + CFG["L"] + 1
+        mats = []
+        for _ in range(2):                       # synthetic standardized H5 content: symmetric N(0,1) [T, N, N]
+            a = torch.randn(T, N, N, device=device, generator=g)
+            mats.append((a + a.transpose(1, 2)) / 2 ** 0.5)
+        self.ds = sv.WindowDataset(mats[0], mats[1], seq_length=CFG["L"], device=device, drop_first=0)
+        self.batch = self.ds.collate(torch.arange(B))
+        torch.manual_seed(seed)
+        self.layer = sv.GATConv(Fin, Cc, heads=H, concat=False, negative_slope=CFG["slope"], edge_dim=Fe).to(device)
+        n, HC = B * N, H * Cc
+        self.desc = _lib.GatDesc(B, N, Fin, Fe, H, Cc, N * (N - 1), 0, CFG["slope"], self.lib.spotv2_gat_ldp(H, Cc), 0, 0)
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _lib.check(self.lib.spotv2_gat_workspace_bytes(C.byref(self.desc), C.byref(a), C.byref(b), C.byref(c)), "ws")
+        f32 = dict(device=device, dtype=torch.float32)
+        self.ws = torch.empty(max(a.value, b.value, c.value), device=device, dtype=torch.uint8)
+        self.W_aug = torch.empty(HC + 2 * H, Fin, **f32)
+        self.v = torch.empty(H, Fe, **f32)
+        self.P_aug = torch.empty(n, self.desc.ldp, **f32)
+        self.out = torch.empty(n, Cc, **f32)
+        self.dout = torch.randn(n, Cc, generator=g, **f32)
+        self.dP_aug = torch.empty(n, self.desc.ldp, **f32)
+        self.dW_aug = torch.empty(HC + 2 * H, Fin, **f32)
+        self.dv = torch.empty(H, Fe, **f32)
+        # flat gradient arena: the one buffer the data-parallel all-reduce moves
+        sizes = [HC * Fin, HC, HC, HC * Fe, HC, Cc]
+        self.arena = torch.empty(sum(sizes), **f32)
+        self.g_W, self.g_as, self.g_ad, self.g_We, self.g_ae, self.g_b = torch.split(self.arena, sizes)
+        self.kernels_per_step = 10
+        self.ev = {}
+
+    def step(self, timed_events=None, allreduce=None):
+        lib, d, p, L = self.lib, C.byref(self.desc), self._lib.ptr, self.layer
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        chk = self._lib.check
+
+        def mark(name):
+            if timed_events is not None:
+                e = torch.cuda.Event(enable_timing=True); e.record(); timed_events.append((name, e))
+        mark("start")
+        chk(lib.spotv2_gat_fold(d, p(L.lin_src.weight), p(L.att_src), p(L.att_dst), p(L.lin_edge.weight),
+                                p(L.att_edge), p(self.W_aug), p(self.v), st), "fold")
+        mark("fold")
+        chk(lib.spotv2_proj_fwd(d, p(self.batch.x), p(self.W_aug), p(self.P_aug), p(self.ws), self.ws.numel(), st), "proj_fwd")
+        mark("proj_fwd")
+        chk(lib.spotv2_gat_attn_fwd(d, p(self.P_aug), p(self.batch.edge_attr), p(self.batch.spot_topology.table),
+                                    p(self.v), p(L.bias), p(self.out), None, st), "attn_fwd")
+        mark("attn_fwd")
+        chk(lib.spotv2_gat_attn_bwd(d, p(self.P_aug), p(self.batch.edge_attr), p(self.batch.spot_topology.table),
+                                    p(self.v), p(self.dout), p(self.dP_aug), p(self.dv), p(self.g_b), p(self.ws),
+                                    self.ws.numel(), st), "attn_bwd")
+        mark("attn_bwd")
+        chk(lib.spotv2_proj_bwd_weight(d, p(self.batch.x), p(self.dP_aug), p(self.dW_aug), p(self.ws), self.ws.numel(), st),
+            "proj_bwd_weight")
+        mark("proj_bwd_weight")
+        chk(lib.spotv2_gat_unfold(d, p(L.lin_src.weight), p(L.att_src), p(L.att_dst), p(L.lin_edge.weight), p(L.att_edge),
+                                  p(self.dW_aug), p(self.dv), p(self.g_W), p(self.g_as), p(self.g_ad), p(self.g_We),
+                                  p(self.g_ae), st), "unfold")
+        mark("unfold")
+        if allreduce is not None:
+            allreduce(self.arena)
+            mark("allreduce")
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    hp = HotPath(B, dev, seed=1234 + rank)
+
+    def allreduce(t):
+        dist.all_reduce(t)
+        t.mul_(1.0 / world)
+    ar = allreduce if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        hp.step(allreduce=ar)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    per_step_events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        evs = []
+        hp.step(timed_events=evs, allreduce=ar)
+        per_step_events.append(evs)
+    e1.record()
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = t.item()
+    ms_per_step = elapsed_ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # per-kernel device times (CUDA events on the launching stream, averaged over the timed steps)
+    phase_ms = {}
+    for evs in per_step_events:
+        for (n0, a), (n1, b) in zip(evs[:-1], evs[1:]):
+            phase_ms.setdefault(n1, []).append(a.elapsed_time(b))
+    phase_ms = {k: sum(v) / len(v) for k, v in phase_ms.items()}
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    t_attn = (phase_ms["attn_fwd"] + phase_ms["attn_bwd"]) * 1e-3
+    attn_gbs = (ATTN_BYTES_FWD + ATTN_BYTES_BWD) * B / t_attn / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "attn_traffic.json")))
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "gat_attn_fwd_kernel + gat_attn_bwd_kernel", "achieved": attn_gbs,
+                "peak": hbm_peak, "unit": "GB/s", "frac": attn_gbs / hbm_peak, "traffic": traffic,
+                "peak_source": peak_src, "frac_of_8TBs": attn_gbs / 8000.0,
+                "fwd": {"ms": phase_ms["attn_fwd"], "GBs": ATTN_BYTES_FWD * B / phase_ms["attn_fwd"] / 1e6},
+                "bwd": {"ms": phase_ms["attn_bwd"], "GBs": ATTN_BYTES_BWD * B / phase_ms["attn_bwd"] / 1e6}}
+    t_proj = (phase_ms["proj_fwd"] + phase_ms["proj_bwd_weight"]) * 1e-3
+    tf32_peak = peaks.get("bf16_tflops_sustained", 1400.0) / 2
+    proj = {"bound": "tensor", "kernel": "projection GEMMs (P = x W^T, dW = dP^T x)",
+            "achieved": PROJ_FLOP_PER_GRAPH * B / t_proj / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+            "frac": PROJ_FLOP_PER_GRAPH * B / t_proj / 1e12 / tf32_peak,
+            "peak_source": "bf16_tflops_sustained / 2 (tf32 dense rate; tf32 not measured separately); algorithmic fp32 flops",
+            "fwd_ms": phase_ms["proj_fwd"], "bwd_ms": phase_ms["proj_bwd_weight"]}
+
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = run_e2e(args, hp, dev, world, rank, barrier)
+        except Exception as ex:           # the device-timed line must still print
+            e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:300]}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            gps, cores, ts = time_oracle(args.cpu_batch, 3, 1)
+            cpu_baseline = {"value": gps, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{args.cpu_batch} graphs/step x 3 steps (+1 warm-up), PyG-order torch eager oracle, "
+                                      f"median {statistics.median(ts):.2f} s/step"}
+        except Exception as ex:
+            cpu_baseline = {"value": None, "error": repr(ex)[:300]}
+
+    if rank == 0:
+        N, Fin, Fe, H, Cc = cfg_dims()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: default GNN_param.yaml hyper-parameters, batch 4096 snapshots per GPU, "
+                                   "fp32, GATConv fwd+bwd" + (" + NCCL gradient all-reduce" if world > 1 else ""),
+                       "nodes": N, "in_channels": Fin, "edge_dim": Fe, "heads": H, "hidden": Cc, "batch_per_gpu": B,
+                       "l2": "inputs (x 619 MB, edge_attr 1.8 GB, P 1.5 GB per step) exceed the 126 MB L2; no flush needed",
+                       "parallelism": f"dp{world}"},
+            "phase_ms": phase_ms, "roofline": roofline, "roofline_projection": proj, "cpu_baseline": cpu_baseline,
+            "e2e": e2e, "gpu_launches": hp.kernels_per_step * args.steps, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, hp, dev, world, rank, barrier):
+    """Same metric through the public module API with HOST buffers: every step copies the batch
+    (x, edge_index, edge_attr, y_x) from pinned host memory, runs GATConv forward + backward through
+    autograd, and reads a scalar back."""
+    import spotv2net_b200 as sv
+    bt = hp.batch
+    host = {k: getattr(bt, k).cpu().pin_memory() for k in ("x", "edge_index", "edge_attr", "y_x")}
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+    layer, dout = hp.layer, hp.dout
+    steps = max(2, min(args.steps, args.e2e_steps))
+
+    def one():
+        dev_t = {k: t.to(dev, non_blocking=True) for k, t in host.items()}
+        layer.zero_grad(set_to_none=True)
+        out = layer(dev_t["x"], dev_t["edge_index"], dev_t["edge_attr"])
+        loss = (out * dout).sum()
+        loss.backward()
+        return loss.item()                      # D2H read of the step's result
+
+    one()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    return {"value": world * hp.B / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+            "ms_per_step": ms, "steps": steps, "api": "spotv2net_b200.GATConv forward + autograd backward, pinned host inputs"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--cpu-batch", type=int, default=128)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

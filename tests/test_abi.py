@@ -1,0 +1,77 @@
+"""The C-ABI library loads and exports every symbol include/spotv2_gat.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import spotv2net_b200
+from spotv2net_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "spotv2_gat.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(spotv2_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_is_built_and_loads():
+    lib = spotv2net_b200.load_library()
+    assert lib.spotv2_abi_version() == 1
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = spotv2net_b200.load_library()
+    names = _declared()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in spotv2_gat.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in spotv2net_b200/_lib.py"
+    assert set(_lib.SIGNATURES) <= set(names)
+
+
+def test_descriptor_layout_matches_header():
+    assert ctypes.sizeof(_lib.GatDesc) == 12 * 4
+    assert [f[0] for f in _lib.GatDesc._fields_] == ["B", "N", "F", "Fe", "H", "C", "R", "concat",
+                                                     "negative_slope", "ldp", "gemm_algo", "reserved"]
+
+
+def test_ldp_query_and_argument_validation_without_a_gpu():
+    lib = spotv2net_b200.load_library()
+    assert lib.spotv2_gat_ldp(6, 500) == 3012 and lib.spotv2_gat_ldp(8, 256) == 2064 and lib.spotv2_gat_ldp(1, 1) == 4
+    bad = _lib.GatDesc(0, 30, 1260, 126, 6, 500, 870, 0, 0.2, 3012, 0, 0)
+    a = ctypes.c_size_t()
+    rc = lib.spotv2_gat_workspace_bytes(ctypes.byref(bad), ctypes.byref(a), None, None)
+    assert rc == 1 and b"non-positive" in lib.spotv2_last_error()
+    bad = _lib.GatDesc(4, 30, 1260, 126, 6, 500, 870, 0, 0.2, 3000, 0, 0)
+    assert lib.spotv2_gat_workspace_bytes(ctypes.byref(bad), ctypes.byref(a), None, None) == 1
+    assert b"ldp" in lib.spotv2_last_error()
+
+
+def test_product_path_refuses_cpu_tensors():
+    layer = spotv2net_b200.GATConv(8, 4, heads=2, edge_dim=3)
+    ei = spotv2net_b200.complete_graph_edge_index(5)
+    with pytest.raises(spotv2net_b200.SpotV2Error, match="no CPU fallback"):
+        layer(torch.zeros(5, 8), ei, torch.zeros(20, 3))
+
+
+def test_missing_library_is_an_error_not_a_fallback(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setenv("SPOTV2_GAT_LIB", str(tmp_path / "nope.so"))
+    with pytest.raises(spotv2net_b200.SpotV2Error, match="not found"):
+        _lib.load()
+    monkeypatch.delenv("SPOTV2_GAT_LIB")
+    monkeypatch.setattr(_lib, "_lib", None)
+    _lib.load()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "spotv2net_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

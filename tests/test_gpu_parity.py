@@ -1,0 +1,344 @@
+"""Parity of the CUDA path against the CPU oracle, through the C ABI (run on the B200 box).
+
+Tolerance (SURVEY.md §8d / north_star): max-norm relative error
+    ||ours - ref||_inf / ||ref||_inf <= 1e-5
+for every output and gradient tensor, ref = the float64 edge-list oracle (PyG 2.3.0 op order).
+"""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import spotv2net_b200 as sv
+from spotv2net_b200 import _lib
+from spotv2net_b200._lib import GatDesc, check, ptr
+from oracle import dense_gat, pyg_gat, synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+DEV = "cuda:0"
+
+
+def relerr(a, ref):
+    a, ref = torch.as_tensor(a).double().cpu(), torch.as_tensor(ref).double().cpu()
+    return ((a - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def make_layers(Fin, C_, H, concat, Fe, slope, seed, wscale=1.0):
+    torch.manual_seed(seed)
+    ref = pyg_gat.OracleGATConv(Fin, C_, heads=H, concat=concat, negative_slope=slope, edge_dim=Fe).double()
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.mul_(wscale)
+        ref.bias.normal_()
+        for p in ref.parameters():
+            p.copy_(p.float().double())
+    ours = sv.GATConv(Fin, C_, heads=H, concat=concat, negative_slope=slope, edge_dim=Fe)
+    ours.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    return ref, ours.to(DEV)
+
+
+def run_both(ref, ours, bt, need_dx=False, seed=0):
+    x64 = bt.x.double().requires_grad_(need_dx)
+    out_ref, (ei2, alpha_ref) = ref(x64, bt.edge_index, bt.edge_attr.double() if bt.edge_attr is not None else None,
+                                    return_attention_weights=True)
+    g = torch.Generator().manual_seed(seed)
+    dout = torch.randn(out_ref.shape, generator=g, dtype=torch.float32)
+    out_ref.backward(dout.double())
+    xg = bt.x.to(DEV).requires_grad_(need_dx)
+    out, (ei2g, alpha) = ours(xg, bt.edge_index.to(DEV), bt.edge_attr.to(DEV) if bt.edge_attr is not None else None,
+                              return_attention_weights=True)
+    out.backward(dout.to(DEV))
+    errs = {"out": relerr(out, out_ref), "alpha": relerr(alpha, alpha_ref)}
+    assert torch.equal(ei2g.cpu(), ei2)
+    for (k, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
+        errs["g_" + k] = relerr(p.grad, q.grad)
+    if need_dx:
+        errs["g_x"] = relerr(xg.grad, x64.grad)
+    return errs
+
+
+# ------------------------------------------------------------------ individual entry points
+def test_fold_and_unfold_entry_points(cuda_lib):
+    H, C_, Fin, Fe = 3, 5, 9, 4
+    torch.manual_seed(0)
+    W, a_s, a_d = torch.randn(H * C_, Fin), torch.randn(1, H, C_), torch.randn(1, H, C_)
+    We, a_e = torch.randn(H * C_, Fe), torch.randn(1, H, C_)
+    W_aug_ref, v_ref = dense_gat.fold_params(W.double(), a_s.double(), a_d.double(), We.double(), a_e.double(), H, C_)
+    d = GatDesc(2, 4, Fin, Fe, H, C_, 12, 0, 0.2, cuda_lib.spotv2_gat_ldp(H, C_), 0, 0)
+    g = lambda t: t.to(DEV).contiguous()
+    Wg, asg, adg, Weg, aeg = map(g, (W, a_s, a_d, We, a_e))
+    W_aug = torch.empty(H * C_ + 2 * H, Fin, device=DEV)
+    v = torch.empty(H, Fe, device=DEV)
+    check(cuda_lib.spotv2_gat_fold(C.byref(d), ptr(Wg), ptr(asg), ptr(adg), ptr(Weg), ptr(aeg), ptr(W_aug), ptr(v), st()), "fold")
+    assert relerr(W_aug, W_aug_ref) < 1e-6 and relerr(v, v_ref) < 1e-6
+    dW_aug, dv = torch.randn(H * C_ + 2 * H, Fin), torch.randn(H, Fe)
+    ref = dense_gat.unfold_grads(dW_aug.double(), dv.double(), W.double(), a_s.double(), a_d.double(), We.double(),
+                                 a_e.double(), H, C_)
+    outs = [torch.empty_like(t) for t in (Wg, asg, adg, Weg, aeg)]
+    check(cuda_lib.spotv2_gat_unfold(C.byref(d), ptr(Wg), ptr(asg), ptr(adg), ptr(Weg), ptr(aeg), ptr(g(dW_aug)),
+                                     ptr(g(dv)), *map(ptr, outs), st()), "unfold")
+    for o, k in zip(outs, ("lin_weight", "att_src", "att_dst", "lin_edge_weight", "att_edge")):
+        assert relerr(o, ref[k]) < 1e-6, k
+
+
+@pytest.mark.parametrize("shape", [(2, 30, 1260, 6, 500), (3, 7, 9, 3, 5), (5, 30, 100, 8, 33), (1, 1, 3, 1, 1)])
+def test_projection_gemms(cuda_lib, shape):
+    B, N, Fin, H, C_ = shape
+    n, n_aug = B * N, H * C_ + 2 * H
+    ldp = cuda_lib.spotv2_gat_ldp(H, C_)
+    d = GatDesc(B, N, Fin, 0, H, C_, 0, 0, 0.2, ldp, 0, 0)
+    torch.manual_seed(1)
+    x, W_aug, dP = torch.randn(n, Fin), torch.randn(n_aug, Fin), torch.randn(n, ldp)
+    xg, Wg, dPg = x.to(DEV), W_aug.to(DEV), dP.to(DEV)
+    a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    check(cuda_lib.spotv2_gat_workspace_bytes(C.byref(d), C.byref(a), C.byref(b), C.byref(c)), "ws")
+    ws = torch.empty(max(a.value, c.value), dtype=torch.uint8, device=DEV)
+    P = torch.zeros(n, ldp, device=DEV)
+    check(cuda_lib.spotv2_proj_fwd(C.byref(d), ptr(xg), ptr(Wg), ptr(P), ptr(ws), ws.numel(), st()), "proj_fwd")
+    assert relerr(P[:, :n_aug], x.double() @ W_aug.double().t()) < TOL
+    dW = torch.empty(n_aug, Fin, device=DEV)
+    check(cuda_lib.spotv2_proj_bwd_weight(C.byref(d), ptr(xg), ptr(dPg), ptr(dW), ptr(ws), ws.numel(), st()), "bwd_w")
+    assert relerr(dW, dP[:, :n_aug].double().t() @ x.double()) < TOL
+    dX = torch.empty(n, Fin, device=DEV)
+    check(cuda_lib.spotv2_proj_bwd_input(C.byref(d), ptr(dPg), ptr(Wg), ptr(dX), ptr(ws), ws.numel(), st()), "bwd_x")
+    assert relerr(dX, dP[:, :n_aug].double() @ W_aug.double()) < TOL
+
+
+def test_edge_table_accepts_reference_order_and_rejects_others(cuda_lib):
+    N, B = 30, 3
+    bt = synth.random_complete_batch(B, N, 4, 2, seed=0)
+    topo = sv.topology_from_edge_index(bt.edge_index.to(DEV), B * N)
+    assert (topo.B, topo.N, topo.R, topo.has_skips) == (B, N, N * (N - 1), False)
+    local = bt.edge_index[:, :topo.R]
+    assert torch.equal(topo.table.cpu(), ((local[1] << 16) | local[0]).int())
+    bad = bt.edge_index.clone()
+    bad[:, 5] = bad[:, 6]                                   # duplicate one edge, drop another
+    with pytest.raises(sv.SpotV2Error, match="complete"):
+        sv.topology_from_edge_index(bad.to(DEV), B * N)
+    bad = bt.edge_index.clone()
+    perm = torch.randperm(topo.R)
+    bad[:, topo.R:2 * topo.R] = bad[:, topo.R:2 * topo.R][:, perm]   # second graph in a different edge order
+    with pytest.raises(sv.SpotV2Error, match="differs"):
+        sv.topology_from_edge_index(bad.to(DEV), B * N)
+
+
+def test_attention_stages_against_dense_oracle(cuda_lib):
+    """attn_fwd / attn_bwd alone (P_aug given), compared stage by stage with oracle/dense_gat.py."""
+    B, N, Fin, Fe, H, C_ = 5, 30, 16, 126, 6, 20
+    for concat in (False, True):
+        bt = synth.random_complete_batch(B, N, Fin, Fe, seed=4)
+        ref, _ = make_layers(Fin, C_, H, concat, Fe, 0.2, seed=9, wscale=2.0)
+        W, a_s, a_d, We, a_e, bias = [p.detach() for p in (ref.lin_src.weight, ref.att_src, ref.att_dst,
+                                                           ref.lin_edge.weight, ref.att_edge, ref.bias)]
+        T = dense_gat.pyg_to_dense_tile(bt.edge_attr.double(), bt.edge_index, B, N)
+        fw = dense_gat.dense_forward(bt.x.double(), T, W, a_s, a_d, We, a_e, bias, H, C_, concat, 0.2)
+        ldp = cuda_lib.spotv2_gat_ldp(H, C_)
+        d = GatDesc(B, N, Fin, Fe, H, C_, N * (N - 1), int(concat), 0.2, ldp, 0, 0)
+        P_aug = torch.zeros(B * N, ldp, device=DEV)
+        P_aug[:, :H * C_ + 2 * H] = fw["P_aug"].float().to(DEV)
+        topo = sv.topology_from_edge_index(bt.edge_index.to(DEV), B * N)
+        ea, v, bg = bt.edge_attr.to(DEV), fw["v"].float().to(DEV).contiguous(), bias.float().to(DEV)
+        ldo = H * C_ if concat else C_
+        out = torch.empty(B * N, ldo, device=DEV)
+        alpha = torch.empty(B, H, N, N, device=DEV)
+        check(cuda_lib.spotv2_gat_attn_fwd(C.byref(d), ptr(P_aug), ptr(ea), ptr(topo.table), ptr(v), ptr(bg), ptr(out),
+                                           ptr(alpha), st()), "attn_fwd")
+        assert relerr(alpha, fw["alpha"].permute(0, 3, 2, 1)) < TOL     # ours is [B, H, j, i]
+        assert relerr(out, fw["out"]) < TOL
+        dout = torch.randn(B * N, ldo)
+        gr = dense_gat.dense_backward(fw, bt.x.double(), T, W, a_s, a_d, We, a_e, dout.double(), H, C_, concat, 0.2)
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        check(cuda_lib.spotv2_gat_workspace_bytes(C.byref(d), C.byref(a), C.byref(b), C.byref(c)), "ws")
+        ws = torch.empty(b.value, dtype=torch.uint8, device=DEV)
+        dP = torch.zeros(B * N, ldp, device=DEV)
+        dv, dbias = torch.empty(H, Fe, device=DEV), torch.empty(ldo, device=DEV)
+        check(cuda_lib.spotv2_gat_attn_bwd(C.byref(d), ptr(P_aug), ptr(ea), ptr(topo.table), ptr(v), ptr(dout.to(DEV)),
+                                           ptr(dP), ptr(dv), ptr(dbias), ptr(ws), ws.numel(), st()), "attn_bwd")
+        HC = H * C_
+        assert relerr(dP[:, :HC], gr["dP_aug"][:, :HC]) < TOL
+        assert relerr(dP[:, HC:HC + 2 * H], gr["dP_aug"][:, HC:]) < TOL
+        assert relerr(dv, gr["dv"]) < TOL and relerr(dbias, gr["bias"]) < TOL
+
+
+# ------------------------------------------------------------------ the layer, end to end
+CASES = [
+    # B, N, Fin, Fe, H, C, concat, slope, wscale
+    (4, 30, 1260, 126, 6, 500, False, 0.2, 1.0),      # default config geometry (config/GNN_param.yaml)
+    (3, 30, 120, 12, 6, 20, True, 0.2, 1.0),
+    (2, 30, 64, 126, 8, 256, True, 0.2, 1.0),         # BASELINE config C layer 0
+    (2, 30, 2048, 126, 8, 256, False, 0.2, 1.0),      # BASELINE config C layer 1
+    (4, 7, 9, 5, 3, 5, False, 0.5, 2.0),              # odd everything -> scalar / unaligned paths
+    (3, 12, 16, 8, 7, 12, False, 0.8, 4.0),
+    (2, 2, 4, 3, 1, 2, True, 0.05, 1.0),
+    (5, 1, 6, 2, 2, 3, False, 0.2, 1.0),              # single-node graphs: only the self loop
+    (2, 32, 10, 7, 2, 6, True, 0.2, 1.0),             # N = 32, the kernel's upper bound
+    (2, 17, 30, 360, 2, 25, False, 0.1, 1.0),         # seq_length 120 -> Fe = 360 (HPO space), odd C
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"B{c[0]}N{c[1]}F{c[2]}Fe{c[3]}H{c[4]}C{c[5]}{'cat' if c[6] else 'mean'}" for c in CASES])
+def test_layer_matches_edge_list_oracle(cuda_lib, case):
+    B, N, Fin, Fe, H, C_, concat, slope, wscale = case
+    ref, ours = make_layers(Fin, C_, H, concat, Fe, slope, seed=B + N, wscale=wscale)
+    if N == 1:
+        bt = synth.Batch(x=torch.randn(B, Fin), edge_index=torch.arange(B).repeat(2, 1),
+                         edge_attr=torch.randn(B, Fe), num_graphs=B)     # input = self loops only
+        ours.nodes_per_graph = 1
+    else:
+        bt = synth.random_complete_batch(B, N, Fin, Fe, seed=17)
+    errs = run_both(ref, ours, bt, need_dx=True)
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, f"max-norm relative errors above {TOL}: {bad} (all: {errs})"
+
+
+def test_layer_without_edge_attr_and_with_input_self_loops(cuda_lib):
+    B, N, Fin, Fe, H, C_ = 3, 9, 10, 4, 2, 6
+    ref, ours = make_layers(Fin, C_, H, True, Fe, 0.2, seed=3)
+    bt = synth.random_complete_batch(B, N, Fin, Fe, seed=5)
+    no_ea = synth.Batch(x=bt.x, edge_index=bt.edge_index, edge_attr=None)
+    out_ref = ref(bt.x.double(), bt.edge_index, None)
+    out = ours(bt.x.to(DEV), bt.edge_index.to(DEV), None)
+    assert relerr(out, out_ref) < TOL                       # Explainer path, 6_results.ipynb:1347
+    del no_ea
+    # self loops present in the input are dropped and replaced by the mean-filled ones
+    ei = torch.cat([bt.edge_index.view(2, B, -1), (torch.arange(B * N).view(1, B, N)).expand(2, B, N)], 2).reshape(2, -1)
+    ea = torch.cat([bt.edge_attr.view(B, -1, Fe), 50 * torch.randn(B, N, Fe)], 1).reshape(-1, Fe)
+    with_loops = synth.Batch(x=bt.x, edge_index=ei, edge_attr=ea)
+    errs = run_both(ref, ours, with_loops)
+    assert max(errs.values()) < TOL, errs
+
+
+def test_dense_tile_input(cuda_lib):
+    """The collation's dense target-major tile [B, N, N, Fe] is accepted through the same entry point."""
+    B, N, Fin, Fe, H, C_ = 3, 30, 8, 12, 6, 10
+    bt = synth.random_complete_batch(B, N, Fin, Fe, seed=8)
+    ref, _ = make_layers(Fin, C_, H, False, Fe, 0.2, seed=2)
+    W, a_s, a_d, We, a_e, bias = [p.detach() for p in (ref.lin_src.weight, ref.att_src, ref.att_dst,
+                                                       ref.lin_edge.weight, ref.att_edge, ref.bias)]
+    T = dense_gat.pyg_to_dense_tile(bt.edge_attr.double(), bt.edge_index, B, N)
+    T = T + torch.eye(N).view(1, N, N, 1) * 1e6            # garbage on the diagonal must be ignored
+    fw = dense_gat.dense_forward(bt.x.double(), T, W, a_s, a_d, We, a_e, bias, H, C_, False, 0.2)
+    ldp = cuda_lib.spotv2_gat_ldp(H, C_)
+    d = GatDesc(B, N, Fin, Fe, H, C_, N * N, 0, 0.2, ldp, 0, 0)
+    table = torch.empty(N * N, dtype=torch.int32, device=DEV)
+    check(cuda_lib.spotv2_edge_table_dense(N, ptr(table), st()), "table_dense")
+    P_aug = torch.zeros(B * N, ldp, device=DEV)
+    P_aug[:, :H * C_ + 2 * H] = fw["P_aug"].float().to(DEV)
+    out = torch.empty(B * N, C_, device=DEV)
+    check(cuda_lib.spotv2_gat_attn_fwd(C.byref(d), ptr(P_aug), ptr(T.float().to(DEV).contiguous()), ptr(table),
+                                       ptr(fw["v"].float().to(DEV).contiguous()), ptr(bias.float().to(DEV)), ptr(out),
+                                       None, st()), "attn_fwd")
+    assert relerr(out, fw["out"]) < TOL
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_fixtures_on_gpu(cuda_lib, path):
+    z = np.load(path)
+    B, N, Fin, Fe, H, C_, concat = [int(v) for v in z["meta"]]
+    layer = sv.GATConv(Fin, C_, heads=H, concat=bool(concat), negative_slope=float(z["slope"]), edge_dim=Fe)
+    t = lambda k: torch.from_numpy(z[k])
+    layer.load_state_dict({"att_src": t("att_src"), "att_dst": t("att_dst"), "att_edge": t("att_edge"),
+                           "bias": t("bias"), "lin_src.weight": t("lin_weight"), "lin_dst.weight": t("lin_weight"),
+                           "lin_edge.weight": t("lin_edge_weight")})
+    layer.to(DEV)
+    out, (ei2, alpha) = layer(t("x").to(DEV), t("edge_index").to(DEV), t("edge_attr").to(DEV), return_attention_weights=True)
+    out.backward(t("dout").to(DEV))
+    assert relerr(out, z["out"]) < TOL and relerr(alpha, z["alpha"]) < TOL
+    assert (ei2.cpu().numpy() == z["edge_index_with_loops"]).all()
+    for k, p in (("lin_weight", layer.lin_src.weight), ("att_src", layer.att_src), ("att_dst", layer.att_dst),
+                 ("lin_edge_weight", layer.lin_edge.weight), ("att_edge", layer.att_edge), ("bias", layer.bias)):
+        assert relerr(p.grad, z["g_" + k]) < TOL, k
+
+
+# ------------------------------------------------------------------ model + collation
+@pytest.mark.parametrize("cfg", [dict(dim_hidden_layers=[40], concat_heads=True),
+                                 dict(dim_hidden_layers=[24, 16], concat_heads=True),
+                                 dict(dim_hidden_layers=[24, 16, 8], concat_heads=False, activation="tanh"),
+                                 dict(dim_hidden_layers=[20], concat_heads=False, standardize=True)])
+def test_model_step_matches_oracle_model(cuda_lib, cfg):
+    N, L, B = 30, 3, 6
+    vol, vv = synth.synthetic_matrices(L + B + 2, N, seed=21)
+    bt = synth.make_batch(vol, vv, list(range(B)), L)
+    kw = dict(num_node_features=N * L, num_edge_features=3 * L, num_heads=3, output_node_channels=1, **cfg)
+    torch.manual_seed(0)
+    ref = pyg_gat.OracleGATModel(**kw).double()
+    ours = sv.GATModel(**kw)
+    ours.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    ours.to(DEV)
+    ref.train(); ours.train()
+    d64 = synth.Batch(x=bt.x.double(), edge_index=bt.edge_index, edge_attr=bt.edge_attr.double())
+    loss_ref = torch.nn.functional.mse_loss(ref(d64), bt.y_x.double())
+    loss_ref.backward()
+    loss = torch.nn.functional.mse_loss(ours(bt.to(DEV)), bt.y_x.to(DEV))
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) <= 2e-5 * abs(loss_ref.item())
+    for (k, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
+        assert relerr(p.grad, q.grad) < 5e-5, k      # several layers deep: a little fp32 headroom
+
+
+def test_device_collation_matches_reference_layouts(cuda_lib):
+    N, L, T = 30, 5, 40
+    vol, vv = synth.synthetic_matrices(T, N, seed=33)
+    ds = sv.WindowDataset(vol, vv, seq_length=L, device=DEV, drop_first=3)
+    assert len(ds) == T - L - 3
+    idx = [0, 7, 31, 2]
+    ours = ds.collate(idx)
+    ref = synth.make_batch(vol, vv, [i + 3 for i in idx], L)
+    assert torch.equal(ours.x.cpu(), ref.x) and torch.equal(ours.edge_attr.cpu(), ref.edge_attr)
+    assert torch.equal(ours.y_x.cpu(), ref.y_x) and torch.equal(ours.edge_index.cpu(), ref.edge_index)
+    assert torch.equal(ours.batch.cpu(), ref.batch) and torch.equal(ours.ptr.cpu(), ref.ptr)
+    loader = sv.WindowLoader(ds[:20], batch_size=8, shuffle=False)
+    sizes = [b.num_graphs for b in loader]
+    assert sizes == [8, 8, 4] and len(loader) == 3
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_batch_properties(cuda_lib):
+    """B = 4096 at the default geometry (BASELINE config 2).  The oracle cannot run this size, so:
+    graphs are independent (a graph's rows equal the small-batch result bit for bit), attention
+    rows sum to one, and the weight gradient is additive over a split of the batch."""
+    B, N, L, H, C_ = 4096, 30, 42, 6, 500
+    Fin, Fe = N * L, 3 * L
+    torch.manual_seed(5)
+    layer = sv.GATConv(Fin, C_, heads=H, concat=False, edge_dim=Fe).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(B * N, Fin, device=DEV, generator=g)
+    ea = torch.randn(B * N * (N - 1), Fe, device=DEV, generator=g)
+    ei, topo = sv.batched_topology(B, N, DEV)
+    out, (ei2, alpha) = layer(x, ei, ea, return_attention_weights=True)
+    sums = torch.zeros(B * N, H, device=DEV).index_add_(0, ei2[1], alpha)
+    assert (sums - 1).abs().max() < 1e-5
+    dout = torch.randn(out.shape, device=DEV, generator=g)
+    out.backward(dout)
+    gW = layer.lin_src.weight.grad.clone()
+    layer.zero_grad()
+    # graph independence + oracle on a few graphs
+    pick = [0, 1, 2047, 4095]
+    rows = torch.cat([torch.arange(b * N, (b + 1) * N) for b in pick]).to(DEV)
+    erow = torch.cat([torch.arange(b * N * (N - 1), (b + 1) * N * (N - 1)) for b in pick]).to(DEV)
+    ei_s, _ = sv.batched_topology(len(pick), N, DEV)
+    out_s = layer(x[rows], ei_s, ea[erow])
+    assert torch.equal(out_s, out[rows])
+    ref = pyg_gat.OracleGATConv(Fin, C_, heads=H, concat=False, edge_dim=Fe).double()
+    ref.load_state_dict({k: v.double().cpu() for k, v in layer.state_dict().items()})
+    out_ref = ref(x[rows].double().cpu(), ei_s.cpu(), ea[erow].double().cpu())
+    assert relerr(out_s, out_ref) < TOL
+    # additivity of dW over a 2-way split of the batch
+    half = B // 2
+    ei_h, _ = sv.batched_topology(half, N, DEV)
+    acc = torch.zeros_like(gW)
+    for s in range(2):
+        layer.zero_grad()
+        o = layer(x[s * half * N:(s + 1) * half * N], ei_h, ea[s * half * N * (N - 1):(s + 1) * half * N * (N - 1)])
+        o.backward(dout[s * half * N:(s + 1) * half * N])
+        acc += layer.lin_src.weight.grad
+    assert relerr(acc, gW) < TOL

@@ -1,0 +1,69 @@
+"""Host-side mirror of the reference interface: constructor rules, state-dict names, init."""
+import numpy as np
+import pytest
+import torch
+
+import spotv2net_b200 as sv
+from oracle import pyg_gat, synth
+
+
+@pytest.mark.parametrize("hidden", [[500], [64, 32], [50, 25, 12]])
+@pytest.mark.parametrize("concat_heads", [True, False])
+@pytest.mark.parametrize("heads", [1, 3])
+def test_ctor_matrix_and_state_dict_parity(hidden, concat_heads, heads):
+    kw = dict(num_node_features=60, num_edge_features=9, num_heads=heads, output_node_channels=1,
+              dim_hidden_layers=hidden, concat_heads=concat_heads, negative_slope=0.1)
+    ours, ref = sv.GATModel(**kw), pyg_gat.OracleGATModel(**kw)
+    so, sr = ours.state_dict(), ref.state_dict()
+    assert list(so.keys()) == list(sr.keys())
+    assert all(so[k].shape == sr[k].shape for k in so)
+    assert sv.gat_layer_plan(60, heads, hidden, concat_heads) == pyg_gat.gat_layer_plan(60, heads, hidden, concat_heads)
+    ours.load_state_dict(sr)                      # weights saved by the reference load by name
+    for k in so:
+        assert torch.equal(ours.state_dict()[k], sr[k])
+    for layer, (fi, fo, cc) in zip(ours.gat_layers, sv.gat_layer_plan(60, heads, hidden, concat_heads)):
+        assert (layer.in_channels, layer.out_channels, layer.concat, layer.heads) == (fi, fo, cc, heads)
+        assert layer.negative_slope == 0.1 and layer.edge_dim == 9 and layer.lin_dst is layer.lin_src
+
+
+def test_default_config_parameter_count():
+    m = sv.GATModel(1260, 126, 6, 1, [500], concat_heads=True)          # config/GNN_param.yaml:26-38
+    assert sum(p.numel() for p in m.parameters()) == 4_168_001
+    assert m.gat_layers[0].concat is False                              # single layer never concatenates
+
+
+def test_init_follows_pyg_draw_order():
+    torch.manual_seed(123)
+    a = sv.GATConv(12, 5, heads=3, edge_dim=4)
+    torch.manual_seed(123)
+    b = pyg_gat.OracleGATConv(12, 5, heads=3, edge_dim=4)
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)
+    bound = (6.0 / (12 + 15)) ** 0.5
+    assert a.lin_src.weight.abs().max() <= bound and torch.all(a.bias == 0)
+
+
+def test_pyg25_checkpoint_alias():
+    a = sv.GATConv(6, 4, heads=2, edge_dim=3)
+    sd = {k: v.clone() for k, v in a.state_dict().items()}
+    w = sd.pop("lin_src.weight"); sd.pop("lin_dst.weight")
+    sd["lin.weight"] = w + 1
+    a.load_state_dict(sd)
+    assert torch.equal(a.lin_src.weight, w + 1)
+
+
+def test_unknown_activation_exits_like_the_reference():
+    with pytest.raises(SystemExit):
+        sv.GATModel(8, 3, 2, 1, [4], activation="gelu")
+
+
+def test_unsupported_layer_options_fail_loudly():
+    with pytest.raises(sv.SpotV2Error):
+        sv.GATConv(8, 4, add_self_loops=False)
+    with pytest.raises(sv.SpotV2Error):
+        sv.GATConv((8, 8), 4)
+
+
+def test_edge_index_order_matches_reference_dataset():
+    for N in (2, 5, 30):
+        assert torch.equal(sv.complete_graph_edge_index(N), synth.complete_graph_edge_index(N))
