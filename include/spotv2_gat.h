@@ -150,6 +150,15 @@ int spotv2_collate_windows(const float* M_vol, const float* M_vv, int32_t T, int
                            const int32_t* t0, int32_t B, float* x, float* edge_attr, float* y,
                            void* stream);
 
+/* ---- diagnostics (bring-up and parity tests of the GEMM back ends; not reference-facing) ----
+ * C[M,N] (ld ldc) = sum_k A(m,k) B(n,k).  a_kc/b_kc = 1: operand stored [rows, K] (K contiguous),
+ * 0: stored [K, rows].  algo 1 = exact-fp32 CUDA-core kernel, 2 = tcgen05 3xTF32 kernel (operands are
+ * split into tf32 hi/lo pairs inside ws).  bn = 128|256 tile width, kb_per_chunk = 32-wide k-blocks
+ * per TMEM accumulation chain (0 = default 4), splits = split-K factor. */
+int spotv2_diag_gemm(int a_kc, int b_kc, int M, int N, int K, const float* A, int lda, const float* B,
+                     int ldb, float* C, int ldc, int algo, int splits, int bn, int kb_per_chunk,
+                     void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,10 +95,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a lost transaction traps instead of hanging the GPU box.
+// Bounded wait: a lost transaction traps (~2 s) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-    if (spins > (1u << 26)) __trap();
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,

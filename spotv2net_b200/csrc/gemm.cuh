@@ -18,4 +18,12 @@ inline int weight_grad_splits(int rows) {
   return s;
 }
 
+// fp32-accurate tensor-core GEMM (tcgen05, 3xTF32, chunked accumulation) on operands pre-split into
+// tf32 hi/lo arrays.  bn = 128 | 256 (tile N); kb_per_chunk = k-blocks of 32 per TMEM accumulation chain.
+bool tc_gemm_supported(bool a_kc, bool b_kc, int M, int N, int K, const float* A_hi, int lda, const float* B_hi, int ldb);
+int split_tf32(const float* src, float* hi, float* lo, size_t n, cudaStream_t st);
+int gemm3x_tf32(bool a_kc, bool b_kc, int M, int N, int K, const float* A_hi, const float* A_lo, int lda,
+                const float* B_hi, const float* B_lo, int ldb, float* C, int ldc, int splits, int bn,
+                int kb_per_chunk, void* ws, size_t ws_bytes, cudaStream_t st);
+
 }  // namespace spotv2

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import weakref
 from dataclasses import dataclass
 from typing import Optional
 
@@ -72,11 +73,16 @@ def topology_from_edge_index(edge_index: Tensor, n_nodes: int, nodes_per_graph: 
     if edge_index.dim() != 2 or edge_index.shape[0] != 2 or edge_index.dtype != torch.int64:
         raise SpotV2Error("edge_index must be an int64 tensor of shape [2, E]")
     _lib.require_cuda(edge_index, "edge_index")
-    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, edge_index.device, n_nodes,
-           nodes_per_graph)
+    # Cached per tensor OBJECT (weak reference), never per address: the caching allocator hands the same
+    # address to unrelated tensors, and a stale hit would silently mis-route edges.
+    key = id(edge_index)
     hit = _TOPO_CACHE.get(key)
     if hit is not None:
-        return hit
+        ref, version, args, topo = hit
+        if ref() is edge_index and version == edge_index._version and args == (n_nodes, nodes_per_graph):
+            return topo
+        del _TOPO_CACHE[key]
+    owner = edge_index
     edge_index = edge_index.contiguous()
     E = edge_index.shape[1]
     cands = [nodes_per_graph] if nodes_per_graph else []
@@ -95,7 +101,7 @@ def topology_from_edge_index(edge_index: Tensor, n_nodes: int, nodes_per_graph: 
             "there is no generic fallback.")
     if len(_TOPO_CACHE) > 64:
         _TOPO_CACHE.clear()
-    _TOPO_CACHE[key] = topo
+    _TOPO_CACHE[key] = (weakref.ref(owner), owner._version, (n_nodes, nodes_per_graph), topo)
     return topo
 
 
@@ -126,12 +132,15 @@ class _GatLayerFn(torch.autograd.Function):
         n, HC = x.shape[0], H * Cc
         x = x.contiguous()
         ea = edge_attr.contiguous() if Fe else None
+        # every tensor whose address is handed to the library is held in a local until the call returns
         W, a_src, a_dst = W.contiguous(), a_src.contiguous(), a_dst.contiguous()
+        W_e = W_e.contiguous() if W_e is not None else None
+        a_edge = a_edge.contiguous() if a_edge is not None else None
+        bias_c = bias.contiguous() if bias is not None else None
         W_aug = torch.empty(HC + 2 * H, x.shape[1], device=dev, dtype=torch.float32)
         v = torch.empty(H, Fe, device=dev, dtype=torch.float32) if Fe else None
-        check(lib.spotv2_gat_fold(C.byref(desc), ptr(W), ptr(a_src), ptr(a_dst),
-                                  ptr(W_e.contiguous()) if Fe else None, ptr(a_edge.contiguous()) if Fe else None,
-                                  ptr(W_aug), ptr(v), st), "spotv2_gat_fold")
+        check(lib.spotv2_gat_fold(C.byref(desc), ptr(W), ptr(a_src), ptr(a_dst), ptr(W_e) if Fe else None,
+                                  ptr(a_edge) if Fe else None, ptr(W_aug), ptr(v), st), "spotv2_gat_fold")
         ws_f, _, _ = _workspace(desc)
         ws = torch.empty(ws_f, device=dev, dtype=torch.uint8)
         P_aug = torch.empty(n, desc.ldp, device=dev, dtype=torch.float32)
@@ -139,8 +148,7 @@ class _GatLayerFn(torch.autograd.Function):
         out = torch.empty(n, HC if concat else Cc, device=dev, dtype=torch.float32)
         alpha = torch.empty(topo.B, H, topo.N, topo.N, device=dev, dtype=torch.float32) if want_alpha else None
         check(lib.spotv2_gat_attn_fwd(C.byref(desc), ptr(P_aug), ptr(ea), ptr(topo.table) if Fe else None, ptr(v),
-                                      ptr(bias.contiguous()) if bias is not None else None, ptr(out), ptr(alpha), st),
-              "spotv2_gat_attn_fwd")
+                                      ptr(bias_c), ptr(out), ptr(alpha), st), "spotv2_gat_attn_fwd")
         ctx.desc, ctx.topo, ctx.Fe, ctx.has_bias = desc, topo, Fe, bias is not None
         ctx.save_for_backward(x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug)
         if want_alpha:
