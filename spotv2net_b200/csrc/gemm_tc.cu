@@ -94,17 +94,21 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1.
-//   K-major : rows of 128 B (32 tf32 along K), 8-row atoms of 1024 B; SBO = 1024 B between row groups.
-//   MN-major: rows of 128 B (32 tf32 along M|N), 8 k-rows per 1024 B atom; LBO = bytes between
-//             32-wide M|N blocks, SBO = 1024 B between k atoms.
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), version 1.
+//   K-major  (layout SWIZZLE_128B = 2): rows of 128 B (32 tf32 along K), 16-byte chunks XOR-swizzled by
+//             row % 8; 8-row atoms of 1024 B; SBO = 1024 B between row groups, LBO unused.
+//   MN-major (layout SWIZZLE_128B_BASE32B = 1, the only legal one for 32-bit MN-major operands): rows of
+//             128 B (32 tf32 along M|N), 32-byte chunks XOR-swizzled by row % 4; 4 k-rows per 512 B
+//             atom; SBO = 512 B between k atoms, LBO = bytes between 32-wide M|N blocks.
+//             TMA writes exactly this with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;     // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;     // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 
@@ -202,8 +206,10 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     if (elect_one()) {
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_KM ? 0u : 1u) << 15) |
                                  ((B_KM ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-      // K-major: LBO unused (1), SBO 1024.  MN-major: LBO = one 32-wide block = TBK rows * 128 B, SBO 1024.
+      // K-major: LBO unused (1), SBO 1024.  MN-major: LBO = one 32-wide block = TBK rows * 128 B, SBO 512.
       constexpr uint32_t a_lbo = A_KM ? 16 : TBK * 128, b_lbo = B_KM ? 16 : TBK * 128;
+      constexpr uint32_t a_sbo = A_KM ? 1024 : 512, b_sbo = B_KM ? 1024 : 512;
+      constexpr uint32_t a_lt = A_KM ? 2 : 1, b_lt = B_KM ? 2 : 1;
       constexpr uint32_t a_kstep = A_KM ? UMMA_K * 4 : UMMA_K * 128;   // bytes per k-step of 8
       constexpr uint32_t b_kstep = B_KM ? UMMA_K * 4 : UMMA_K * 128;
       int stage = 0; uint32_t phase = 0;
@@ -226,10 +232,10 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             const uint32_t sb = sa + 2 * S::kAOp;
 #pragma unroll
             for (int ks = 0; ks < TBK / UMMA_K; ++ks) {
-              const uint64_t ah = make_desc(sa + ks * a_kstep, a_lbo, 1024);
-              const uint64_t al = make_desc(sa + S::kAOp + ks * a_kstep, a_lbo, 1024);
-              const uint64_t bh = make_desc(sb + ks * b_kstep, b_lbo, 1024);
-              const uint64_t bl = make_desc(sb + S::kBOp + ks * b_kstep, b_lbo, 1024);
+              const uint64_t ah = make_desc(sa + ks * a_kstep, a_lbo, a_sbo, a_lt);
+              const uint64_t al = make_desc(sa + S::kAOp + ks * a_kstep, a_lbo, a_sbo, a_lt);
+              const uint64_t bh = make_desc(sb + ks * b_kstep, b_lbo, b_sbo, b_lt);
+              const uint64_t bl = make_desc(sb + S::kBOp + ks * b_kstep, b_lbo, b_sbo, b_lt);
               umma_tf32(d_tmem, al, bh, idesc, accum);
               accum = 1;
               umma_tf32(d_tmem, ah, bl, idesc, 1);
@@ -354,7 +360,7 @@ static EncodeTiledFn encode_fn() {
 // 2-D fp32 tensor [rows, cols] (cols contiguous, row pitch ld), box = box_cols x box_rows, 128B swizzle,
 // out-of-bounds elements read as zero.
 static int make_tmap(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
-                     uint32_t box_rows) {
+                     uint32_t box_rows, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(SPOTV2_ERR_NO_DEVICE, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {cols, rows};
@@ -362,7 +368,7 @@ static int make_tmap(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SPOTV2_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return SPOTV2_OK;
@@ -428,19 +434,20 @@ int gemm3x_tf32(bool a_kc, bool b_kc, int M, int N, int K, const float* A_hi, co
   int rc;
   // K-major operand: tensor [rows = M|N, cols = K], box 32(k) x tile rows.
   // MN-major operand: tensor [rows = K, cols = M|N], box 32(m|n) x 32(k); one box per 32-wide block.
+  const CUtensorMapSwizzle kSw = CU_TENSOR_MAP_SWIZZLE_128B, mnSw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   if (a_kc) {
-    if ((rc = make_tmap(&tAh, A_hi, M, K, lda, TBK, TBM))) return rc;
-    if ((rc = make_tmap(&tAl, A_lo, M, K, lda, TBK, TBM))) return rc;
+    if ((rc = make_tmap(&tAh, A_hi, M, K, lda, TBK, TBM, kSw))) return rc;
+    if ((rc = make_tmap(&tAl, A_lo, M, K, lda, TBK, TBM, kSw))) return rc;
   } else {
-    if ((rc = make_tmap(&tAh, A_hi, K, M, lda, 32, TBK))) return rc;
-    if ((rc = make_tmap(&tAl, A_lo, K, M, lda, 32, TBK))) return rc;
+    if ((rc = make_tmap(&tAh, A_hi, K, M, lda, 32, TBK, mnSw))) return rc;
+    if ((rc = make_tmap(&tAl, A_lo, K, M, lda, 32, TBK, mnSw))) return rc;
   }
   if (b_kc) {
-    if ((rc = make_tmap(&tBh, B_hi, N, K, ldb, TBK, bn))) return rc;
-    if ((rc = make_tmap(&tBl, B_lo, N, K, ldb, TBK, bn))) return rc;
+    if ((rc = make_tmap(&tBh, B_hi, N, K, ldb, TBK, bn, kSw))) return rc;
+    if ((rc = make_tmap(&tBl, B_lo, N, K, ldb, TBK, bn, kSw))) return rc;
   } else {
-    if ((rc = make_tmap(&tBh, B_hi, K, N, ldb, 32, TBK))) return rc;
-    if ((rc = make_tmap(&tBl, B_lo, K, N, ldb, 32, TBK))) return rc;
+    if ((rc = make_tmap(&tBh, B_hi, K, N, ldb, 32, TBK, mnSw))) return rc;
+    if ((rc = make_tmap(&tBl, B_lo, K, N, ldb, 32, TBK, mnSw))) return rc;
   }
 #define SPOTV2_TC(BN_, AK, BK_) rc = launch_tc<BN_, AK, BK_>(tAh, tAl, tBh, tBl, p, st)
   if (bn == 256) {

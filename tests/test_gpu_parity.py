@@ -63,7 +63,7 @@ def make_layers(Fin, C_, H, concat, Fe, slope, seed, wscale=1.0):
 def oracle_pass(ref, bt, dout, dtype, need_dx):
     import copy
     m = copy.deepcopy(ref).to(dtype)
-    x = bt.x.to(dtype).requires_grad_(need_dx)
+    x = bt.x.detach().clone().to(dtype).requires_grad_(need_dx)
     out, (ei2, alpha) = m(x, bt.edge_index, bt.edge_attr.to(dtype) if bt.edge_attr is not None else None,
                           return_attention_weights=True)
     out.backward(dout.to(dtype))
@@ -82,7 +82,7 @@ def run_both(ref, ours, bt, need_dx=False, seed=0):
     dout = torch.randn(bt.x.shape[0], n_out, generator=g, dtype=torch.float32)
     r64, ei2 = oracle_pass(ref, bt, dout, torch.float64, need_dx)
     r32, _ = oracle_pass(ref, bt, dout, torch.float32, need_dx)
-    xg = bt.x.to(DEV).requires_grad_(need_dx)
+    xg = bt.x.detach().clone().to(DEV).requires_grad_(need_dx)
     out, (ei2g, alpha) = ours(xg, bt.edge_index.to(DEV), bt.edge_attr.to(DEV) if bt.edge_attr is not None else None,
                               return_attention_weights=True)
     out.backward(dout.to(DEV))
