@@ -184,9 +184,9 @@ __device__ __forceinline__ void edge_logit_phase(EdgeRing& ring, const AttnParam
 // tile[h][j][i] <- alpha * out_scale ; optional raw alpha to global ; optional z>0 mask bits.
 __device__ __forceinline__ void softmax_phase(const AttnParams& p, const AttnSmem& sm, float* tile,
                                               const float* sd, float out_scale, float* alpha_out_b,
-                                              uint32_t* pos_mask, int tid) {
+                                              uint32_t* pos_mask, int tid, int nthreads = kAttnThreads) {
   const int N = p.N, H = p.H, NS = sm.NS;
-  for (int idx = tid; idx < H * N; idx += kAttnThreads) {
+  for (int idx = tid; idx < H * N; idx += nthreads) {
     const int h = idx / N, i = idx - h * N;
     float* col = tile + (size_t)h * N * NS + i;
     float gsum = 0.f;

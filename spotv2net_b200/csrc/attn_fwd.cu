@@ -1,18 +1,28 @@
-// Fused GAT attention forward for batches of small complete graphs (N <= 32), one graph per
-// CTA iteration.  Replaces, per graph, PyG 2.3.0 GATConv's edge_update (gathers, lin_edge,
-// leaky_relu), utils.softmax, message + 'add' aggregation, head mean/concat and bias
+// Fused GAT attention forward for batches of small complete graphs (N <= 32).
+// Replaces, per graph, PyG 2.3.0 GATConv's edge_update (gathers, lin_edge, leaky_relu),
+// utils.softmax, message + 'add' aggregation, head mean/concat and bias
 // ([PyG] nn/conv/gat_conv.py; reached from /root/reference/utils/models.py:146).
 //
-//   phase 1  edge rows stream through a 2-stage shared-memory ring (1-D bulk async copies);
-//            g[e,h] = <edge_attr[e], v_h> on mma.sync m16n8k8 with a 3xTF32 split (fp32-accurate);
-//            scattered by the row table into tile[h][j][i].
-//   phase 2  thread (h,i): self-loop mean fill, s_j + d_i + g_ij, LeakyReLU, softmax over j.
-//   phase 3  out[i, c] = sum_{h,j} alpha_h[i,j] * P[j, h, c]: each thread owns a channel pair
-//            and all targets (packed FFMA2, alpha broadcast from shared memory, P streamed
-//            straight from HBM with a register double buffer).
+// One persistent CTA per SM, 384 threads, warp-specialised and pipelined ACROSS graphs:
+//
+//   group A (warps 0-3)   for graph b+1: edge rows stream through a 2-stage shared-memory ring
+//                         (cp.async.bulk + mbarrier, issued two chunks ahead, across graph boundaries);
+//                         g[e,h] = <edge_attr[e], v_h> on mma.sync m16n8k8 with a 3xTF32 split;
+//                         self-loop mean fill, s_j + d_i + g_ij, LeakyReLU, softmax over sources
+//                         -> attention tile[buf] in shared memory.
+//   group B (warps 4-11)  for graph b: out[i, c] = sum_{h,j} alpha_h[i,j] P[j,h,c].  A thread owns a
+//                         channel pair and ALL targets (packed FFMA2, alpha broadcast from shared
+//                         memory), P streams straight from HBM through a register double buffer.
+//
+// The two groups hand tiles over through mbarriers (tile_full / tile_empty), so the edge stream and the
+// P stream keep HBM busy at the same time and the softmax never sits on the aggregation's critical path.
 #include "attn_common.cuh"
 
 namespace spotv2 {
+
+constexpr int kFwdThreads = 384;
+constexpr int kGroupA = 128;
+constexpr int kGroupB = 256;
 
 struct AttnFwdArgs {
   AttnParams p;
@@ -21,114 +31,155 @@ struct AttnFwdArgs {
   float* alpha_out;
 };
 
-template <int NPAIRS>
-__global__ void __launch_bounds__(kAttnThreads, 2)
+__device__ __forceinline__ void bar_sync_group_a() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int NPAIRS, int JU, bool VEC2>
+__global__ void __launch_bounds__(kFwdThreads, 1)
 gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const AttnParams& p = args.p;
   const int tid = threadIdx.x;
   const int N = p.N, H = p.H, C = p.C, NS = sm.NS;
   const int HC = H * C;
+  const int tile_floats = H * N * NS;
+  const int sd_floats = N * 2 * H;
 
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sm.off_bar);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sm.off_bar);   // [0,1] ring, [2,3] tile_full, [4,5] tile_empty
+  uint64_t* tile_full = bars + 2;
+  uint64_t* tile_empty = bars + 4;
   int32_t* table_s = reinterpret_cast<int32_t*>(smem_raw + sm.off_table);
   float4* vfrag = reinterpret_cast<float4*>(smem_raw + sm.off_vfrag);
-  float* sd = reinterpret_cast<float*>(smem_raw + sm.off_sd);
-  float* tile = reinterpret_cast<float*>(smem_raw + sm.off_tile);
+  float* sd0 = reinterpret_cast<float*>(smem_raw + sm.off_sd);
+  float* tile0 = reinterpret_cast<float*>(smem_raw + sm.off_tile);
 
-  EdgeRing ring;
-  ring.stage[0] = reinterpret_cast<float*>(smem_raw + sm.off_ring);
-  ring.stage[1] = reinterpret_cast<float*>(smem_raw + sm.off_ring + sm.ring_stage_bytes);
-  ring.full = bars;
-  ring.uses[0] = ring.uses[1] = 0;
-  ring.chunk_rows = sm.chunk_rows;
-  ring.nchunks = p.Fe > 0 ? (p.R + sm.chunk_rows - 1) / sm.chunk_rows : 0;
-  ring.p = &p;
+  const int nchunks = p.Fe > 0 ? (p.R + sm.chunk_rows - 1) / sm.chunk_rows : 0;
+  const int my_graphs = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
+    mbar_init(&tile_full[0], kGroupA);
+    mbar_init(&tile_full[1], kGroupA);
+    mbar_init(&tile_empty[0], kGroupB);
+    mbar_init(&tile_empty[1], kGroupB);
     fence_mbar_init();
   }
-  for (int r = tid; r < p.R; r += kAttnThreads) table_s[r] = p.Fe > 0 ? p.table[r] : -1;
-  if (p.Fe > 0) build_vfrag(vfrag, p.v, H, p.Fe, sm.KS, sm.NT, tid, kAttnThreads);
-  for (int idx = tid; idx < H * N * NS; idx += kAttnThreads) tile[idx] = 0.f;
+  for (int r = tid; r < p.R; r += kFwdThreads) table_s[r] = p.Fe > 0 ? p.table[r] : -1;
+  if (p.Fe > 0) build_vfrag(vfrag, p.v, H, p.Fe, sm.KS, sm.NT, tid, kFwdThreads);
+  for (int idx = tid; idx < 2 * tile_floats; idx += kFwdThreads) tile0[idx] = 0.f;
   __syncthreads();
 
-  int b = blockIdx.x;
-  if (p.bulk_ok && tid == 0 && b < p.B && ring.nchunks > 0) ring.prefetch_first(b);
-
-  const float out_scale = p.concat ? 1.f : 1.f / (float)H;
-  const int CP = (C + 1) / 2;
-  const int n_items = p.concat ? H * CP : CP;
-  const int h_loop = p.concat ? 1 : H;
-
-  for (; b < p.B; b += gridDim.x) {
-    // s_j, d_i of this graph: the 2H augmented columns of P_aug
-    for (int idx = tid; idx < N * 2 * H; idx += kAttnThreads) {
-      const int j = idx / (2 * H), k = idx - j * 2 * H;
-      sd[idx] = p.P_aug[((size_t)b * N + j) * p.ldp + HC + k];
+  if (tid < kGroupA) {
+    // ================================ group A: logits + softmax ================================
+    const int warp = tid >> 5, lane = tid & 31;
+    float* stage[2] = {reinterpret_cast<float*>(smem_raw + sm.off_ring),
+                       reinterpret_cast<float*>(smem_raw + sm.off_ring + sm.ring_stage_bytes)};
+    const int total_chunks = my_graphs * nchunks;      // this CTA's global chunk stream
+    auto rows_in = [&](int c) { const int r = p.R - c * sm.chunk_rows; return r < sm.chunk_rows ? r : sm.chunk_rows; };
+    auto issue = [&](int k) {                           // one thread: start the k-th chunk of the stream
+      const int it = k / nchunks, c = k - it * nchunks;
+      const int b = blockIdx.x + it * gridDim.x;
+      const uint32_t bytes = (uint32_t)rows_in(c) * p.Fe * 4u;
+      mbar_expect_tx(&bars[k & 1], bytes);
+      bulk_g2s(stage[k & 1], p.edge_rows + ((size_t)b * p.R + (size_t)c * sm.chunk_rows) * p.Fe, bytes, &bars[k & 1]);
+    };
+    if (p.bulk_ok && tid == 0) {
+      if (total_chunks > 0) issue(0);
+      if (total_chunks > 1) issue(1);
     }
-    if (ring.nchunks > 0) {
-      edge_logit_phase(ring, p, sm, tile, table_s, vfrag, b, tid);   // ends with a barrier
-    } else {
-      for (int idx = tid; idx < H * N * NS; idx += kAttnThreads) tile[idx] = 0.f;
-      __syncthreads();
-    }
-    softmax_phase(p, sm, tile, sd, out_scale,
-                  args.alpha_out ? args.alpha_out + (size_t)b * H * N * N : nullptr, nullptr, tid);
-    __syncthreads();
-    // the ring is idle from here on: start the next graph's first chunks under phase 3
-    if (p.bulk_ok && tid == 0 && b + (int)gridDim.x < p.B && ring.nchunks > 0)
-      ring.prefetch_first(b + gridDim.x);
-
-    // ---- phase 3: aggregation -------------------------------------------------------------
-    constexpr int JU = 5;
-    for (int item = tid; item < n_items; item += kAttnThreads) {
-      const int h0 = p.concat ? item / CP : 0;
-      const int cp = p.concat ? item - h0 * CP : item;
-      const int c0 = 2 * cp;
-      const bool has1 = c0 + 1 < C;
-      float2 acc[NPAIRS][2];
-#pragma unroll
-      for (int ip = 0; ip < NPAIRS; ++ip) acc[ip][0] = acc[ip][1] = make_float2(0.f, 0.f);
-
-      const int total = h_loop * N;                     // flattened (h, j)
-      const float* prow = p.P_aug + (size_t)b * N * p.ldp + (size_t)h0 * C + c0;
-      const float* arow = tile + (size_t)h0 * N * NS;
-      // running load cursor (one (h,j) row ahead of the math by JU)
-      int lj = 0;
-      const float* lptr = prow;
-      auto load_next = [&](bool valid) -> float2 {
-        float2 v = make_float2(0.f, 0.f);
-        if (valid) {
-          if (p.vec2_ok) {
-            v = ldg_stream2(lptr);
-          } else {
-            v.x = __ldg(lptr);
-            if (has1) v.y = __ldg(lptr + 1);
-          }
-          ++lj;
-          lptr += p.ldp;
-          if (lj == N) { lj = 0; lptr += (ptrdiff_t)C - (ptrdiff_t)N * p.ldp; }
+    const float out_scale = p.concat ? 1.f : 1.f / (float)H;
+    int k = 0;                                          // global chunk counter (stage = k & 1, parity = (k >> 1) & 1)
+    for (int it = 0; it < my_graphs; ++it) {
+      const int b = blockIdx.x + it * gridDim.x;
+      const int buf = it & 1;
+      float* tile = tile0 + buf * tile_floats;
+      float* sd = sd0 + buf * sd_floats;
+      mbar_wait(&tile_empty[buf], ((it >> 1) & 1) ^ 1);   // group B has finished reading this buffer
+      for (int idx = tid; idx < sd_floats; idx += kGroupA) {
+        const int j = idx / (2 * H), kk = idx - j * 2 * H;
+        sd[idx] = p.P_aug[((size_t)b * N + j) * p.ldp + HC + kk];
+      }
+      if (nchunks == 0) {
+        for (int idx = tid; idx < tile_floats; idx += kGroupA) tile[idx] = 0.f;
+      }
+      for (int c = 0; c < nchunks; ++c, ++k) {
+        const int s = k & 1;
+        const int rows = rows_in(c);
+        if (p.bulk_ok) {
+          mbar_wait(&bars[s], (k >> 1) & 1);
+        } else {
+          const float* src = p.edge_rows + ((size_t)b * p.R + (size_t)c * sm.chunk_rows) * p.Fe;
+          for (int idx = tid; idx < rows * p.Fe; idx += kGroupA) stage[s][idx] = src[idx];
+          bar_sync_group_a();
         }
-        return v;
-      };
-      float2 cur[JU], nxt[JU];
+        if (warp * 16 < rows) {
+          const int row_base = c * sm.chunk_rows;
+          warp_edge_logits<1>(stage[s], vfrag, p.Fe, sm.KS, sm.NT, warp * 16, lane, [&](int r, int h, float val) {
+            if (r < rows && h < H) {
+              const int code = table_s[row_base + r];
+              if (code >= 0) tile[(h * N + (code & 0xffff)) * NS + (code >> 16)] = val;
+            }
+          });
+        }
+        bar_sync_group_a();                              // stage s consumed by all four warps
+        if (p.bulk_ok && tid == 0 && k + 2 < total_chunks) issue(k + 2);
+      }
+      if (nchunks == 0) bar_sync_group_a();
+      softmax_phase(p, sm, tile, sd, out_scale, args.alpha_out ? args.alpha_out + (size_t)b * H * N * N : nullptr,
+                    nullptr, tid, kGroupA);
+      mbar_arrive_cta(&tile_full[buf]);                  // release: alpha tile visible to group B
+    }
+  } else {
+    // ================================ group B: aggregation ================================
+    const int t = tid - kGroupA;
+    const int CP = (C + 1) / 2;
+    const int n_items = p.concat ? H * CP : CP;
+    const int h_loop = p.concat ? 1 : H;
+    const int groups_per_head = N / JU;                  // JU divides N (chosen at dispatch)
+    const int total_groups = h_loop * groups_per_head;
+    for (int it = 0; it < my_graphs; ++it) {
+      const int b = blockIdx.x + it * gridDim.x;
+      const int buf = it & 1;
+      const float* tile = tile0 + buf * tile_floats;
+      mbar_wait(&tile_full[buf], (it >> 1) & 1);
+      for (int item = t; item < n_items; item += kGroupB) {
+        const int h0 = p.concat ? item / CP : 0;
+        const int cp = p.concat ? item - h0 * CP : item;
+        const int c0 = 2 * cp;
+        const bool has1 = c0 + 1 < C;
+        float2 acc[NPAIRS][2];
 #pragma unroll
-      for (int u = 0; u < JU; ++u) cur[u] = load_next(u < total);
-      for (int base = 0; base < total; base += JU) {
+        for (int ip = 0; ip < NPAIRS; ++ip) acc[ip][0] = acc[ip][1] = make_float2(0.f, 0.f);
+        const float* pbase = p.P_aug + (size_t)b * N * p.ldp + (size_t)h0 * C + c0;
+        const float* abase = tile + (size_t)h0 * N * NS;
+        auto load_group = [&](int g, float2 (&dst)[JU]) {
+          const int h = g / groups_per_head, j0 = (g - h * groups_per_head) * JU;
+          const float* src = pbase + (size_t)j0 * p.ldp + (size_t)h * C;
 #pragma unroll
-        for (int u = 0; u < JU; ++u) nxt[u] = load_next(base + JU + u < total);
+          for (int u = 0; u < JU; ++u) {
+            if (VEC2) {
+              dst[u] = ldg_stream2(src + (size_t)u * p.ldp);
+            } else {
+              dst[u].x = __ldg(src + (size_t)u * p.ldp);
+              dst[u].y = has1 ? __ldg(src + (size_t)u * p.ldp + 1) : 0.f;
+            }
+          }
+        };
+        float2 cur[JU], nxt[JU];
+        load_group(0, cur);
+        for (int g = 0; g < total_groups; ++g) {
+          if (g + 1 < total_groups) load_group(g + 1, nxt);
+          const float* ar = abase + (size_t)g * JU * NS;  // rows (h, j0..j0+JU-1) are consecutive in the tile
 #pragma unroll
-        for (int u = 0; u < JU; ++u) {
-          if (base + u < total) {
-            const float* ar = arow + (size_t)(base + u) * NS;
+          for (int u = 0; u < JU; ++u) {
             const float2 px = make_float2(cur[u].x, cur[u].x);
             const float2 py = make_float2(cur[u].y, cur[u].y);
 #pragma unroll
             for (int q = 0; q < NPAIRS / 2; ++q) {
-              const float4 a4 = *reinterpret_cast<const float4*>(ar + 4 * q);
+              const float4 a4 = *reinterpret_cast<const float4*>(ar + u * NS + 4 * q);
               const float2 a0 = make_float2(a4.x, a4.y), a1 = make_float2(a4.z, a4.w);
               acc[2 * q][0] = ffma2(a0, px, acc[2 * q][0]);
               acc[2 * q][1] = ffma2(a0, py, acc[2 * q][1]);
@@ -136,67 +187,92 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm) {
               acc[2 * q + 1][1] = ffma2(a1, py, acc[2 * q + 1][1]);
             }
             if (NPAIRS & 1) {
-              const float2 a0 = *reinterpret_cast<const float2*>(ar + 2 * (NPAIRS - 1));
+              const float2 a0 = *reinterpret_cast<const float2*>(ar + u * NS + 2 * (NPAIRS - 1));
               acc[NPAIRS - 1][0] = ffma2(a0, px, acc[NPAIRS - 1][0]);
               acc[NPAIRS - 1][1] = ffma2(a0, py, acc[NPAIRS - 1][1]);
             }
           }
+#pragma unroll
+          for (int u = 0; u < JU; ++u) cur[u] = nxt[u];
         }
+        // epilogue: + bias, rows 2ip and 2ip+1
+        const int col = h0 * C + c0;
+        const float b0 = args.bias ? args.bias[col] : 0.f;
+        const float b1 = (args.bias && has1) ? args.bias[col + 1] : 0.f;
+        float* orow = args.out + (size_t)b * N * p.ldo + col;
 #pragma unroll
-        for (int u = 0; u < JU; ++u) cur[u] = nxt[u];
-      }
-      // epilogue: + bias, store rows 2ip and 2ip+1
-      const int col = h0 * C + c0;
-      const float b0 = args.bias ? args.bias[col] : 0.f;
-      const float b1 = (args.bias && has1) ? args.bias[col + 1] : 0.f;
-      float* orow = args.out + (size_t)b * N * p.ldo + col;
+        for (int ip = 0; ip < NPAIRS; ++ip) {
 #pragma unroll
-      for (int ip = 0; ip < NPAIRS; ++ip) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int i = 2 * ip + half;
-          if (i < N) {
-            const float o0 = (half ? acc[ip][0].y : acc[ip][0].x) + b0;
-            const float o1 = (half ? acc[ip][1].y : acc[ip][1].x) + b1;
-            float* dst = orow + (size_t)i * p.ldo;
-            if (p.vec2_ok) {
-              *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
-            } else {
-              dst[0] = o0;
-              if (has1) dst[1] = o1;
+          for (int half = 0; half < 2; ++half) {
+            const int i = 2 * ip + half;
+            if (i < N) {
+              const float o0 = (half ? acc[ip][0].y : acc[ip][0].x) + b0;
+              const float o1 = (half ? acc[ip][1].y : acc[ip][1].x) + b1;
+              float* dst = orow + (size_t)i * p.ldo;
+              if (VEC2) {
+                *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
+              } else {
+                dst[0] = o0;
+                if (has1) dst[1] = o1;
+              }
             }
           }
         }
       }
+      mbar_arrive_cta(&tile_empty[buf]);                 // this thread is done reading the tile
     }
-    __syncthreads();   // tile and sd are rewritten by the next graph
   }
 }
 
-template <int NPAIRS>
+template <int NPAIRS, int JU, bool VEC2>
 static int launch_fwd(const AttnFwdArgs& a, cudaStream_t st) {
   const AttnParams& p = a.p;
-  AttnSmem sm = attn_smem_plan(p.N, p.Fe, p.H, p.R, NPAIRS, kFwdChunkRows);
-  for (int rows = kFwdChunkRows - 16; rows >= 16 && sm.base_total + 2 * sm.ring_stage_bytes > 113 * 1024; rows -= 16)
-    sm = attn_smem_plan(p.N, p.Fe, p.H, p.R, NPAIRS, rows);
-  const size_t smem = sm.base_total + 2 * sm.ring_stage_bytes;
+  const size_t tile_bytes = round_up((size_t)p.H * p.N * ((2 * NPAIRS + 3) / 4 * 4) * 4, 16);
+  const size_t sd_bytes = round_up((size_t)p.N * 2 * p.H * 4, 16);
+  // the common plan reserves one tile + one sd; this kernel double-buffers both
+  auto finish = [&](AttnSmem s) {
+    s.off_tile = s.off_sd + 2 * sd_bytes;
+    s.off_ring = round_up(s.off_tile + 2 * tile_bytes, 128);
+    s.base_total = s.off_ring;
+    return s;
+  };
+  AttnSmem sm = finish(attn_smem_plan(p.N, p.Fe, p.H, p.R, NPAIRS, kFwdChunkRows));
+  for (int rows = kFwdChunkRows - 16; rows >= 16 && sm.off_ring + 2 * sm.ring_stage_bytes > 227 * 1024; rows -= 16)
+    sm = finish(attn_smem_plan(p.N, p.Fe, p.H, p.R, NPAIRS, rows));
+  const size_t smem = sm.off_ring + 2 * sm.ring_stage_bytes;
   if (smem > 227 * 1024)
     return fail(SPOTV2_ERR_UNSUPPORTED, "attn_fwd needs %zu B shared memory (> 227 KB)", smem);
-  auto kern = gat_attn_fwd_kernel<NPAIRS>;
+  auto kern = gat_attn_fwd_kernel<NPAIRS, JU, VEC2>;
   SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = 2 * sm_count();
+  int grid = sm_count();
   if (grid > p.B) grid = p.B;
-  kern<<<grid, kAttnThreads, smem, st>>>(a, sm);
+  kern<<<grid, kFwdThreads, smem, st>>>(a, sm);
   SPOTV2_CUDA_OK(cudaGetLastError());
   return SPOTV2_OK;
 }
 
+template <int NPAIRS, bool VEC2>
+static int dispatch_ju(const AttnFwdArgs& a, cudaStream_t st) {
+  const int N = a.p.N;
+  if (N % 6 == 0) return launch_fwd<NPAIRS, 6, VEC2>(a, st);
+  if (N % 5 == 0) return launch_fwd<NPAIRS, 5, VEC2>(a, st);
+  if (N % 4 == 0) return launch_fwd<NPAIRS, 4, VEC2>(a, st);
+  if (N % 3 == 0) return launch_fwd<NPAIRS, 3, VEC2>(a, st);
+  if (N % 2 == 0) return launch_fwd<NPAIRS, 2, VEC2>(a, st);
+  return launch_fwd<NPAIRS, 1, VEC2>(a, st);
+}
+
+template <int NPAIRS>
+static int dispatch_vec(const AttnFwdArgs& a, cudaStream_t st) {
+  return a.p.vec2_ok ? dispatch_ju<NPAIRS, true>(a, st) : dispatch_ju<NPAIRS, false>(a, st);
+}
+
 int attn_fwd_dispatch(const AttnFwdArgs& a, cudaStream_t st) {
   const int np = (a.p.N + 1) / 2;
-  if (np <= 4) return launch_fwd<4>(a, st);
-  if (np <= 8) return launch_fwd<8>(a, st);
-  if (np <= 15) return launch_fwd<15>(a, st);
-  if (np <= 16) return launch_fwd<16>(a, st);
+  if (np <= 4) return dispatch_vec<4>(a, st);
+  if (np <= 8) return dispatch_vec<8>(a, st);
+  if (np <= 15) return dispatch_vec<15>(a, st);
+  if (np <= 16) return dispatch_vec<16>(a, st);
   return fail(SPOTV2_ERR_UNSUPPORTED, "N=%d > 32: the one-CTA-per-graph kernel covers N <= 32", a.p.N);
 }
 
