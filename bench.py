@@ -168,13 +168,16 @@ class HotPath:
         self.out = torch.empty(n, Cc, **f32)
         self.dout = torch.randn(n, Cc, generator=g, **f32)
         self.dP_aug = torch.empty(n, self.desc.ldp, **f32)
+        self.tc = bool(self.lib.spotv2_gat_uses_tensor_cores(C.byref(self.desc)))
+        self.dP_lo = torch.empty(n, self.desc.ldp, **f32) if self.tc else None
+        self.x_split = torch.empty(2, n, Fin, **f32) if self.tc else None
         self.dW_aug = torch.empty(HC + 2 * H, Fin, **f32)
         self.dv = torch.empty(H, Fe, **f32)
         # flat gradient arena: the one buffer the data-parallel all-reduce moves
         sizes = [HC * Fin, HC, HC, HC * Fe, HC, Cc]
         self.arena = torch.empty(sum(sizes), **f32)
         self.g_W, self.g_as, self.g_ad, self.g_We, self.g_ae, self.g_b = torch.split(self.arena, sizes)
-        self.kernels_per_step = 10
+        self.kernels_per_step = 13 if self.tc else 10   # fold 2, split x/W 2, GEMM 2 + split-K reduce, attn 2 + 2 reduces, unfold
         self.ev = {}
 
     def step(self, timed_events=None, allreduce=None):
@@ -189,17 +192,22 @@ class HotPath:
         chk(lib.spotv2_gat_fold(d, p(L.lin_src.weight), p(L.att_src), p(L.att_dst), p(L.lin_edge.weight),
                                 p(L.att_edge), p(self.W_aug), p(self.v), st), "fold")
         mark("fold")
-        chk(lib.spotv2_proj_fwd(d, p(self.batch.x), p(self.W_aug), p(self.P_aug), p(self.ws), self.ws.numel(), st), "proj_fwd")
+        xh = self.x_split[0] if self.tc else None
+        xl = self.x_split[1] if self.tc else None
+        if self.tc:      # x is split once per step (forward) and reused by the weight-gradient GEMM
+            chk(lib.spotv2_split_tf32(p(self.batch.x), p(xh), p(xl), self.batch.x.numel(), st), "split_tf32")
+        chk(lib.spotv2_proj_fwd(d, p(self.batch.x), p(xh), p(xl), p(self.W_aug), p(self.P_aug), p(self.ws),
+                                self.ws.numel(), st), "proj_fwd")
         mark("proj_fwd")
         chk(lib.spotv2_gat_attn_fwd(d, p(self.P_aug), p(self.batch.edge_attr), p(self.batch.spot_topology.table),
                                     p(self.v), p(L.bias), p(self.out), None, st), "attn_fwd")
         mark("attn_fwd")
         chk(lib.spotv2_gat_attn_bwd(d, p(self.P_aug), p(self.batch.edge_attr), p(self.batch.spot_topology.table),
-                                    p(self.v), p(self.dout), p(self.dP_aug), p(self.dv), p(self.g_b), p(self.ws),
-                                    self.ws.numel(), st), "attn_bwd")
+                                    p(self.v), p(self.dout), p(self.dP_aug), p(self.dP_lo), p(self.dv), p(self.g_b),
+                                    p(self.ws), self.ws.numel(), st), "attn_bwd")
         mark("attn_bwd")
-        chk(lib.spotv2_proj_bwd_weight(d, p(self.batch.x), p(self.dP_aug), p(self.dW_aug), p(self.ws), self.ws.numel(), st),
-            "proj_bwd_weight")
+        chk(lib.spotv2_proj_bwd_weight(d, p(self.batch.x), p(xh), p(xl), p(self.dP_aug), p(self.dP_lo), p(self.dW_aug),
+                                       p(self.ws), self.ws.numel(), st), "proj_bwd_weight")
         mark("proj_bwd_weight")
         chk(lib.spotv2_gat_unfold(d, p(L.lin_src.weight), p(L.att_src), p(L.att_dst), p(L.lin_edge.weight), p(L.att_edge),
                                   p(self.dW_aug), p(self.dv), p(self.g_W), p(self.g_as), p(self.g_ad), p(self.g_We),

@@ -103,10 +103,19 @@ int spotv2_gat_fold(const spotv2_gat_desc* d, const float* W, const float* a_src
                     const float* a_dst, const float* W_e, const float* a_edge, float* W_aug,
                     float* v, void* stream);
 
+/* 1 when the projection GEMMs of this descriptor run on the tensor cores (tcgen05, 3xTF32 with
+ * operands pre-split into tf32 hi/lo pairs), 0 when they take the exact-fp32 CUDA-core kernel. */
+int spotv2_gat_uses_tensor_cores(const spotv2_gat_desc* d);
+
+/* hi = tf32(src), lo = tf32(src - hi), element-wise over n floats (all pointers 16-byte aligned).
+ * Lets the caller split an operand once and reuse it (x feeds both proj_fwd and proj_bwd_weight). */
+int spotv2_split_tf32(const float* src, float* hi, float* lo, size_t n, void* stream);
+
 /* lin_src: P_aug [B*N, ldp] = x [B*N, F] . W_aug^T ; columns [0,HC) are P,
- * [HC,HC+H) are s = alpha_src, [HC+H,HC+2H) are d = alpha_dst. */
-int spotv2_proj_fwd(const spotv2_gat_desc* d, const float* x, const float* W_aug, float* P_aug,
-                    void* ws, size_t ws_bytes, void* stream);
+ * [HC,HC+H) are s = alpha_src, [HC+H,HC+2H) are d = alpha_dst.
+ * x_hi/x_lo: optional pre-split x (both or neither); otherwise x is split into the workspace. */
+int spotv2_proj_fwd(const spotv2_gat_desc* d, const float* x, const float* x_hi, const float* x_lo,
+                    const float* W_aug, float* P_aug, void* ws, size_t ws_bytes, void* stream);
 
 /* edge_update + softmax + propagate + head reduce + bias ([PyG] gat_conv.py
  * edge_update/message, utils/softmax.py, aggr='add').  edge_rows is [B, R, Fe]
@@ -117,17 +126,21 @@ int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug, const floa
                         float* out, float* alpha_or_null, void* stream);
 
 /* autograd of the above with the attention coefficients recomputed, not stored.
- * dout [B*N, C or HC] -> dP_aug [B*N, ldp] (dP | ds | dd), dv [H, Fe], dbias. */
+ * dout [B*N, C or HC] -> dP_aug [B*N, ldp] (dP | ds | dd), dv [H, Fe], dbias.
+ * dP_lo_or_null: when given, the gradient is emitted already split for the tensor-core GEMMs:
+ * dP_aug receives the tf32 hi part and dP_lo the lo part (hi + lo == dP to ~2^-22). */
 int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug, const float* edge_rows,
                         const int32_t* table, const float* v, const float* dout, float* dP_aug,
-                        float* dv_or_null, float* dbias_or_null, void* ws, size_t ws_bytes,
-                        void* stream);
+                        float* dP_lo_or_null, float* dv_or_null, float* dbias_or_null, void* ws,
+                        size_t ws_bytes, void* stream);
 
-/* lin_src backward: dW_aug [H*C+2H, F] = dP_aug^T . x  and  dX [B*N, F] = dP_aug . W_aug. */
-int spotv2_proj_bwd_weight(const spotv2_gat_desc* d, const float* x, const float* dP_aug,
-                           float* dW_aug, void* ws, size_t ws_bytes, void* stream);
-int spotv2_proj_bwd_input(const spotv2_gat_desc* d, const float* dP_aug, const float* W_aug,
-                          float* dX, void* ws, size_t ws_bytes, void* stream);
+/* lin_src backward: dW_aug [H*C+2H, F] = dP_aug^T . x  and  dX [B*N, F] = dP_aug . W_aug.
+ * x_hi/x_lo and dP_lo: optional pre-split operands (dP_aug is then the hi part). */
+int spotv2_proj_bwd_weight(const spotv2_gat_desc* d, const float* x, const float* x_hi, const float* x_lo,
+                           const float* dP_aug, const float* dP_lo, float* dW_aug, void* ws,
+                           size_t ws_bytes, void* stream);
+int spotv2_proj_bwd_input(const spotv2_gat_desc* d, const float* dP_aug, const float* dP_lo,
+                          const float* W_aug, float* dX, void* ws, size_t ws_bytes, void* stream);
 
 /* Inverse of spotv2_gat_fold for gradients: from dW_aug and dv to the gradients of
  * lin_src.weight, att_src, att_dst, lin_edge.weight, att_edge (PyG parameter names). */

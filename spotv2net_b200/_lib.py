@@ -37,11 +37,13 @@ SIGNATURES = {
     "spotv2_edge_table_build": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
     "spotv2_edge_table_dense": (C.c_int, [_i32, _vp, _vp]),
     "spotv2_gat_fold": (C.c_int, [_DP] + [_vp] * 8),
-    "spotv2_proj_fwd": (C.c_int, [_DP, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "spotv2_gat_uses_tensor_cores": (C.c_int, [_DP]),
+    "spotv2_split_tf32": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
+    "spotv2_proj_fwd": (C.c_int, [_DP, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "spotv2_gat_attn_fwd": (C.c_int, [_DP] + [_vp] * 8),
-    "spotv2_gat_attn_bwd": (C.c_int, [_DP] + [_vp] * 9 + [_sz, _vp]),
-    "spotv2_proj_bwd_weight": (C.c_int, [_DP, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "spotv2_proj_bwd_input": (C.c_int, [_DP, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "spotv2_gat_attn_bwd": (C.c_int, [_DP] + [_vp] * 10 + [_sz, _vp]),
+    "spotv2_proj_bwd_weight": (C.c_int, [_DP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "spotv2_proj_bwd_input": (C.c_int, [_DP, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "spotv2_gat_unfold": (C.c_int, [_DP] + [_vp] * 13),
     "spotv2_alpha_to_pyg": (C.c_int, [_DP, _vp, _vp, _vp, _vp]),
     "spotv2_collate_windows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),

@@ -25,10 +25,22 @@ constexpr int kTJ = 5;         // register tile: sources
 struct AttnBwdArgs {
   AttnParams p;
   const float* dout;
-  float* dP_aug;
+  float* dP_aug;       // fp32 gradient, or its tf32 'hi' part when dP_lo is given
+  float* dP_lo;        // optional: tf32 'lo' part (operand pre-split for the tensor-core dW / dX GEMMs)
   float* dv_part;      // [grid][H*Fe]
   float* dbias_part;   // [grid][ldo]
 };
+
+__device__ __forceinline__ void store_grad(const AttnBwdArgs& a, size_t off, float v) {
+  if (a.dP_lo) {
+    uint32_t hi, lo;
+    split_tf32(v, hi, lo);
+    a.dP_aug[off] = __uint_as_float(hi);
+    a.dP_lo[off] = __uint_as_float(lo);
+  } else {
+    a.dP_aug[off] = v;
+  }
+}
 
 struct BwdSmem {
   AttnSmem a;
@@ -50,9 +62,7 @@ inline BwdSmem bwd_smem_plan(int N, int Fe, int H, int C, int R, int npairs, int
   s.stage_G_bytes = (size_t)(concat ? H : 1) * s.NP5 * kCKP * 4;
   const size_t staging = 2 * (s.stage_P_bytes + s.stage_G_bytes);
   const size_t ring = 2 * s.a.ring_stage_bytes;
-  const size_t dvred = (size_t)2 * kAttnThreads * kMaxHeads * 4;   // end-of-kernel dv reduction
   s.union_bytes = staging > ring ? staging : ring;
-  if (dvred > s.union_bytes) s.union_bytes = dvred;
   s.total = s.off_union + s.union_bytes;
   return s;
 }
@@ -126,9 +136,9 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
   uint32_t* pos_mask = reinterpret_cast<uint32_t*>(smem_raw + sm.off_mask);
   float* dbias_s = reinterpret_cast<float*>(smem_raw + sm.off_dbias);
   unsigned char* uni = smem_raw + sm.off_union;
-  float* Pst[2] = {reinterpret_cast<float*>(uni), reinterpret_cast<float*>(uni + sm.stage_P_bytes + sm.stage_G_bytes)};
-  float* Gst[2] = {reinterpret_cast<float*>(uni + sm.stage_P_bytes),
-                   reinterpret_cast<float*>(uni + 2 * sm.stage_P_bytes + sm.stage_G_bytes)};
+  float* const stage_base = reinterpret_cast<float*>(uni);             // [buf][P rows | G rows]
+  const int stage_floats = (int)((sm.stage_P_bytes + sm.stage_G_bytes) / 4);
+  const int stage_g_off = (int)(sm.stage_P_bytes / 4);
 
   EdgeRing ring;
   ring.stage[0] = reinterpret_cast<float*>(uni);
@@ -161,15 +171,17 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
   const int CP = (C + 1) / 2;
   const int n_items = p.concat ? H * CP : CP;
 
-  // dv accumulators: thread (rg, f) owns feature f (and f + 256 when Fe > 256) for row group rg, all heads
-  const int dv_groups = Fe > 0 ? max(1, kAttnThreads / Fe) : 0;
-  const int dv_rg = (Fe > 0 && Fe <= kAttnThreads) ? tid / Fe : 0;
-  const int dv_f = tid - dv_rg * (Fe <= kAttnThreads ? Fe : 0);
-  const bool dv_active = Fe > 0 && dv_rg < dv_groups && dv_f < Fe;
-  const bool dv_second = dv_active && dv_f + kAttnThreads < Fe;
-  float dv_acc[2][kMaxHeads];
+  // dv^T[f][h] = sum_e T[e][f] * dz'[e][h] on mma.sync m16n8k8 (3xTF32): warp w owns the 16-feature
+  // m-tiles w, w+8, ...; heads are the n dimension.  Each staged chunk is accumulated in a fresh fragment
+  // and folded into dv_run with round-to-nearest adds (tensor-core accumulation truncates).
+  constexpr int kMT = kMaxFe / 16 / (kAttnThreads / 32);     // m-tiles per warp (4)
+  const int warp_id = tid >> 5, lane_id = tid & 31;
+  const int n_mtiles = (Fe + 15) / 16;
+  float dv_run[kMT][4];
 #pragma unroll
-  for (int h = 0; h < kMaxHeads; ++h) dv_acc[0][h] = dv_acc[1][h] = 0.f;
+  for (int m = 0; m < kMT; ++m)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dv_run[m][q] = 0.f;
 
   for (; b < p.B; b += gridDim.x) {
     // ---- B1: recompute alpha --------------------------------------------------------------
@@ -197,17 +209,19 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
       for (int ii = 0; ii < kTI; ++ii)
 #pragma unroll
         for (int jj = 0; jj < kTJ; ++jj) acc[ii][jj] = make_float2(0.f, 0.f);
-      stage_chunk(args, sm, Pst[0], Gst[0], b, 0, vec4, tid);
+      stage_chunk(args, sm, stage_base, stage_base + stage_g_off, b, 0, vec4, tid);
       cp_async_commit();
       for (int ch = 0; ch < nchan_chunks; ++ch) {
         const int buf = ch & 1;
-        if (ch + 1 < nchan_chunks) stage_chunk(args, sm, Pst[buf ^ 1], Gst[buf ^ 1], b, (ch + 1) * kCK, vec4, tid);
+        if (ch + 1 < nchan_chunks)
+          stage_chunk(args, sm, stage_base + (buf ^ 1) * stage_floats, stage_base + (buf ^ 1) * stage_floats + stage_g_off, b,
+                      (ch + 1) * kCK, vec4, tid);
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
         if (active) {
-          const float* Gb = Gst[buf] + (size_t)((p.concat ? h * sm.NP5 : 0) + ig * kTI) * kCKP;
-          const float* Pb = Pst[buf] + (size_t)(h * sm.NP5 + cg * kTJ) * kCKP;
+          const float* Gb = stage_base + buf * stage_floats + stage_g_off + ((p.concat ? h * sm.NP5 : 0) + ig * kTI) * kCKP;
+          const float* Pb = stage_base + buf * stage_floats + (h * sm.NP5 + cg * kTJ) * kCKP;
 #pragma unroll
           for (int s4 = 0; s4 < kCK / 4; ++s4) {
             float4 pv[kTJ];
@@ -258,7 +272,7 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
         dd += dz;
         dcol[j * NS] = dz;
       }
-      args.dP_aug[((size_t)b * N + i) * p.ldp + HC + H + h] = dd;
+      store_grad(args, ((size_t)b * N + i) * p.ldp + HC + H + h, dd);
     }
     __syncthreads();
     for (int idx = tid; idx < H * N; idx += kAttnThreads) {     // ds_j = sum_i dz_ij
@@ -270,7 +284,7 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
         if (i >= N) i -= N;
         ds += drow[i];
       }
-      args.dP_aug[((size_t)b * N + j) * p.ldp + HC + h] = ds;
+      store_grad(args, ((size_t)b * N + j) * p.ldp + HC + h, ds);
     }
     __syncthreads();
     for (int idx = tid; idx < H * N; idx += kAttnThreads) {     // dz' : gradient through the mean fill
@@ -334,12 +348,21 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
             s0 = ffma2(a0, G[NPAIRS - 1][0], s0);
             s1 = ffma2(a0, G[NPAIRS - 1][1], s1);
           }
-          float* dst = args.dP_aug + ((size_t)b * N + j) * p.ldp + (size_t)h * C + c0;
+          const size_t off = ((size_t)b * N + j) * p.ldp + (size_t)h * C + c0;
+          const float v0 = s0.x + s0.y, v1 = s1.x + s1.y;
           if (p.vec2_ok) {
-            *reinterpret_cast<float2*>(dst) = make_float2(s0.x + s0.y, s1.x + s1.y);
+            if (args.dP_lo) {
+              uint32_t h0_, l0_, h1_, l1_;
+              split_tf32(v0, h0_, l0_);
+              split_tf32(v1, h1_, l1_);
+              *reinterpret_cast<float2*>(args.dP_aug + off) = make_float2(__uint_as_float(h0_), __uint_as_float(h1_));
+              *reinterpret_cast<float2*>(args.dP_lo + off) = make_float2(__uint_as_float(l0_), __uint_as_float(l1_));
+            } else {
+              *reinterpret_cast<float2*>(args.dP_aug + off) = make_float2(v0, v1);
+            }
           } else {
-            dst[0] = s0.x + s0.y;
-            if (has1) dst[1] = s1.x + s1.y;
+            store_grad(args, off, v0);
+            if (has1) store_grad(args, off + 1, v1);
           }
         }
       }
@@ -358,24 +381,57 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
         for (int idx = tid; idx < rows * Fe; idx += kAttnThreads) ring.stage[s][idx] = src[idx];
         __syncthreads();
       }
-      if (dv_active) {
+      {
         const float* Ts = ring.stage[s];
         const int row_base = c * ring.chunk_rows;
-        for (int r = dv_rg; r < rows; r += dv_groups) {
-          const int code = table_s[row_base + r];
-          if (code < 0) continue;
-          const float tval = Ts[r * Fe + dv_f];
-          const float tval2 = dv_second ? Ts[r * Fe + dv_f + kAttnThreads] : 0.f;
-          const float* dz = D + (size_t)(code & 0xffff) * NS + (code >> 16);
+        const int g8 = lane_id >> 2, t4 = lane_id & 3;
+        float acc[kMT][4];
 #pragma unroll
-          for (int h = 0; h < kMaxHeads; ++h) {
-            if (h < H) {
-              const float dzh = dz[(size_t)h * N * NS];
-              dv_acc[0][h] = fmaf(dzh, tval, dv_acc[0][h]);
-              dv_acc[1][h] = fmaf(dzh, tval2, dv_acc[1][h]);
+        for (int m = 0; m < kMT; ++m)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[m][q] = 0.f;
+        for (int r0 = 0; r0 < rows; r0 += 8) {
+          // B fragment (k = edge row, n = head): b0 = dz'[r0+t][g], b1 = dz'[r0+t+4][g]
+          float bv[2];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int r = r0 + t4 + 4 * half;
+            float val = 0.f;
+            if (r < rows && g8 < H) {
+              const int code = table_s[row_base + r];
+              if (code >= 0) val = D[(g8 * N + (code & 0xffff)) * NS + (code >> 16)];
+            }
+            bv[half] = val;
+          }
+          uint32_t bh[2], bl[2];
+          split_tf32(bv[0], bh[0], bl[0]);
+          split_tf32(bv[1], bh[1], bl[1]);
+          const bool k0_ok = r0 + t4 < rows, k1_ok = r0 + t4 + 4 < rows;
+          const float* t0p = Ts + (size_t)(r0 + t4) * Fe;
+          const float* t1p = t0p + (size_t)4 * Fe;
+#pragma unroll
+          for (int m = 0; m < kMT; ++m) {
+            const int mt = warp_id + m * (kAttnThreads / 32);
+            if (mt < n_mtiles) {
+              const int f0 = mt * 16 + g8, f1 = f0 + 8;
+              float a[4];
+              a[0] = (k0_ok && f0 < Fe) ? t0p[f0] : 0.f;     // (m = g,   k = t)
+              a[1] = (k0_ok && f1 < Fe) ? t0p[f1] : 0.f;     // (m = g+8, k = t)
+              a[2] = (k1_ok && f0 < Fe) ? t1p[f0] : 0.f;     // (m = g,   k = t+4)
+              a[3] = (k1_ok && f1 < Fe) ? t1p[f1] : 0.f;     // (m = g+8, k = t+4)
+              uint32_t ah[4], al[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) split_tf32(a[q], ah[q], al[q]);
+              mma_tf32_16x8x8(acc[m], al, bh);
+              mma_tf32_16x8x8(acc[m], ah, bl);
+              mma_tf32_16x8x8(acc[m], ah, bh);
             }
           }
         }
+#pragma unroll
+        for (int m = 0; m < kMT; ++m)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dv_run[m][q] += acc[m][q];
       }
       __syncthreads();
       if (p.bulk_ok && tid == 0 && c + 2 < ring.nchunks) ring.issue(b, c + 2);
@@ -389,22 +445,18 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
   // so no bulk copy is in flight here and the union region can be reused.
   __syncthreads();
   if (Fe > 0) {
-    float* red = reinterpret_cast<float*>(uni);          // [2][kAttnThreads][kMaxHeads]
+    // C fragment of dv^T: c0 = (f = g, h = 2t), c1 = (g, 2t+1), c2 = (g+8, 2t), c3 = (g+8, 2t+1)
+    const int g8 = lane_id >> 2, t4 = lane_id & 3;
 #pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) {
-      red[tid * kMaxHeads + h] = dv_acc[0][h];
-      red[(kAttnThreads + tid) * kMaxHeads + h] = dv_acc[1][h];
-    }
-    __syncthreads();
-    for (int idx = tid; idx < H * Fe; idx += kAttnThreads) {
-      const int h = idx / Fe, f = idx - h * Fe;
-      float s = 0.f;
-      if (Fe <= kAttnThreads) {
-        for (int g = 0; g < dv_groups; ++g) s += red[(g * Fe + f) * kMaxHeads + h];
-      } else {
-        s = f < kAttnThreads ? red[f * kMaxHeads + h] : red[(kAttnThreads + f - kAttnThreads) * kMaxHeads + h];
+    for (int m = 0; m < kMT; ++m) {
+      const int mt = warp_id + m * (kAttnThreads / 32);
+      if (mt < n_mtiles) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int f = mt * 16 + g8 + ((q & 2) ? 8 : 0), h = 2 * t4 + (q & 1);
+          if (f < Fe && h < H) args.dv_part[(size_t)blockIdx.x * H * Fe + (size_t)h * Fe + f] = dv_run[m][q];
+        }
       }
-      args.dv_part[(size_t)blockIdx.x * H * Fe + idx] = s;
     }
   }
   for (int idx = tid; idx < p.ldo; idx += kAttnThreads)
@@ -455,7 +507,7 @@ using namespace spotv2;
 
 extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
                                    const float* edge_rows, const int32_t* table, const float* v,
-                                   const float* dout, float* dP_aug, float* dv_or_null,
+                                   const float* dout, float* dP_aug, float* dP_lo_or_null, float* dv_or_null,
                                    float* dbias_or_null, void* ws, size_t ws_bytes, void* stream) {
   if (int rc = check_desc(d)) return rc;
   SPOTV2_REQUIRE(P_aug && dout && dP_aug, "attn_bwd: P_aug, dout, dP_aug must be non-null");
@@ -473,7 +525,8 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
   a.p.P_aug = P_aug; a.p.edge_rows = edge_rows; a.p.table = table; a.p.v = v;
   a.p.bulk_ok = d->Fe > 0 && aligned16(edge_rows) && ((size_t)d->R * d->Fe) % 4 == 0;
   a.p.vec2_ok = (d->C % 2 == 0);
-  a.dout = dout; a.dP_aug = dP_aug; a.dv_part = nullptr; a.dbias_part = nullptr;
+  a.dout = dout; a.dP_aug = dP_aug; a.dP_lo = dP_lo_or_null; a.dv_part = nullptr; a.dbias_part = nullptr;
+  SPOTV2_REQUIRE(!dP_lo_or_null || aligned16(dP_lo_or_null), "attn_bwd: dP_lo must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   const int np = (d->N + 1) / 2;
   if (np <= 4) return launch_bwd<4>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);

@@ -11,8 +11,9 @@
 //                         self-loop mean fill, s_j + d_i + g_ij, LeakyReLU, softmax over sources
 //                         -> attention tile[buf] in shared memory.
 //   group B (warps 4-11)  for graph b: out[i, c] = sum_{h,j} alpha_h[i,j] P[j,h,c].  A thread owns a
-//                         channel pair and ALL targets (packed FFMA2, alpha broadcast from shared
-//                         memory), P streams straight from HBM through a register double buffer.
+//                         channel pair and ALL targets (packed FFMA2, alpha broadcast from shared memory).
+//   warp 12               P-row producer: one cp.async.bulk per source row (all heads, 12 KB) into a
+//                         kPRows-deep shared-memory ring, running ahead across graph boundaries.
 //
 // The two groups hand tiles over through mbarriers (tile_full / tile_empty), so the edge stream and the
 // P stream keep HBM busy at the same time and the softmax never sits on the aggregation's critical path.
@@ -20,9 +21,10 @@
 
 namespace spotv2 {
 
-constexpr int kFwdThreads = 384;
+constexpr int kFwdThreads = 416;
 constexpr int kGroupA = 128;
 constexpr int kGroupB = 256;
+constexpr int kPRows = 4;          // P-row ring depth (rows in flight)
 
 struct AttnFwdArgs {
   AttnParams p;
@@ -36,9 +38,9 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int NPAIRS, int JU, bool VEC2>
+template <int NPAIRS, bool VEC2>
 __global__ void __launch_bounds__(kFwdThreads, 1)
-gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm) {
+gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t off_prow, const uint32_t prow_bytes) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const AttnParams& p = args.p;
   const int tid = threadIdx.x;
@@ -47,9 +49,15 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm) {
   const int tile_floats = H * N * NS;
   const int sd_floats = N * 2 * H;
 
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sm.off_bar);   // [0,1] ring, [2,3] tile_full, [4,5] tile_empty
+  // [0,1] edge ring, [2,3] tile_full, [4,5] tile_empty, [6..6+kPRows) prow_full, then prow_empty
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sm.off_bar);
   uint64_t* tile_full = bars + 2;
   uint64_t* tile_empty = bars + 4;
+  uint64_t* prow_full = bars + 6;
+  uint64_t* prow_empty = bars + 6 + kPRows;
+  const int CP = (C + 1) / 2;
+  const int n_items = p.concat ? H * CP : CP;
+  const int n_pass = (n_items + kGroupB - 1) / kGroupB;
   int32_t* table_s = reinterpret_cast<int32_t*>(smem_raw + sm.off_table);
   float4* vfrag = reinterpret_cast<float4*>(smem_raw + sm.off_vfrag);
   float* sd0 = reinterpret_cast<float*>(smem_raw + sm.off_sd);
@@ -65,6 +73,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm) {
     mbar_init(&tile_full[1], kGroupA);
     mbar_init(&tile_empty[0], kGroupB);
     mbar_init(&tile_empty[1], kGroupB);
+    for (int r = 0; r < kPRows; ++r) { mbar_init(&prow_full[r], 1); mbar_init(&prow_empty[r], kGroupB / 32); }
     fence_mbar_init();
   }
   for (int r = tid; r < p.R; r += kFwdThreads) table_s[r] = p.Fe > 0 ? p.table[r] : -1;
@@ -132,88 +141,83 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm) {
                     nullptr, tid, kGroupA);
       mbar_arrive_cta(&tile_full[buf]);                  // release: alpha tile visible to group B
     }
-  } else {
+  } else if (tid < kGroupA + kGroupB) {
     // ================================ group B: aggregation ================================
     const int t = tid - kGroupA;
-    const int CP = (C + 1) / 2;
-    const int n_items = p.concat ? H * CP : CP;
-    const int h_loop = p.concat ? 1 : H;
-    const int groups_per_head = N / JU;                  // JU divides N (chosen at dispatch)
-    const int total_groups = h_loop * groups_per_head;
+    const int h_begin0 = 0, h_loop = p.concat ? 1 : H;
+    uint32_t rowctr = 0;                                   // position in the P-row stream (graph, pass, j)
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
       const int buf = it & 1;
       const float* tile = tile0 + buf * tile_floats;
       mbar_wait(&tile_full[buf], (it >> 1) & 1);
-      for (int item = t; item < n_items; item += kGroupB) {
-        const int h0 = p.concat ? item / CP : 0;
-        const int cp = p.concat ? item - h0 * CP : item;
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int item = pass * kGroupB + t;
+        const bool valid = item < n_items;
+        const int h0 = (p.concat && valid) ? item / CP : h_begin0;
+        const int cp = valid ? (p.concat ? item - h0 * CP : item) : 0;
         const int c0 = 2 * cp;
         const bool has1 = c0 + 1 < C;
         float2 acc[NPAIRS][2];
 #pragma unroll
         for (int ip = 0; ip < NPAIRS; ++ip) acc[ip][0] = acc[ip][1] = make_float2(0.f, 0.f);
-        const float* pbase = p.P_aug + (size_t)b * N * p.ldp + (size_t)h0 * C + c0;
-        const float* abase = tile + (size_t)h0 * N * NS;
-        auto load_group = [&](int g, float2 (&dst)[JU]) {
-          const int h = g / groups_per_head, j0 = (g - h * groups_per_head) * JU;
-          const float* src = pbase + (size_t)j0 * p.ldp + (size_t)h * C;
-#pragma unroll
-          for (int u = 0; u < JU; ++u) {
-            if (VEC2) {
-              dst[u] = ldg_stream2(src + (size_t)u * p.ldp);
-            } else {
-              dst[u].x = __ldg(src + (size_t)u * p.ldp);
-              dst[u].y = has1 ? __ldg(src + (size_t)u * p.ldp + 1) : 0.f;
-            }
-          }
-        };
-        float2 cur[JU], nxt[JU];
-        load_group(0, cur);
-        for (int g = 0; g < total_groups; ++g) {
-          if (g + 1 < total_groups) load_group(g + 1, nxt);
-          const float* ar = abase + (size_t)g * JU * NS;  // rows (h, j0..j0+JU-1) are consecutive in the tile
-#pragma unroll
-          for (int u = 0; u < JU; ++u) {
-            const float2 px = make_float2(cur[u].x, cur[u].x);
-            const float2 py = make_float2(cur[u].y, cur[u].y);
-#pragma unroll
-            for (int q = 0; q < NPAIRS / 2; ++q) {
-              const float4 a4 = *reinterpret_cast<const float4*>(ar + u * NS + 4 * q);
-              const float2 a0 = make_float2(a4.x, a4.y), a1 = make_float2(a4.z, a4.w);
-              acc[2 * q][0] = ffma2(a0, px, acc[2 * q][0]);
-              acc[2 * q][1] = ffma2(a0, py, acc[2 * q][1]);
-              acc[2 * q + 1][0] = ffma2(a1, px, acc[2 * q + 1][0]);
-              acc[2 * q + 1][1] = ffma2(a1, py, acc[2 * q + 1][1]);
-            }
-            if (NPAIRS & 1) {
-              const float2 a0 = *reinterpret_cast<const float2*>(ar + u * NS + 2 * (NPAIRS - 1));
-              acc[NPAIRS - 1][0] = ffma2(a0, px, acc[NPAIRS - 1][0]);
-              acc[NPAIRS - 1][1] = ffma2(a0, py, acc[NPAIRS - 1][1]);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < JU; ++u) cur[u] = nxt[u];
-        }
-        // epilogue: + bias, rows 2ip and 2ip+1
-        const int col = h0 * C + c0;
-        const float b0 = args.bias ? args.bias[col] : 0.f;
-        const float b1 = (args.bias && has1) ? args.bias[col + 1] : 0.f;
-        float* orow = args.out + (size_t)b * N * p.ldo + col;
-#pragma unroll
-        for (int ip = 0; ip < NPAIRS; ++ip) {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int i = 2 * ip + half;
-            if (i < N) {
-              const float o0 = (half ? acc[ip][0].y : acc[ip][0].x) + b0;
-              const float o1 = (half ? acc[ip][1].y : acc[ip][1].x) + b1;
-              float* dst = orow + (size_t)i * p.ldo;
+        for (int j = 0; j < N; ++j, ++rowctr) {
+          const int slot = rowctr % kPRows;
+          mbar_wait(&prow_full[slot], (rowctr / kPRows) & 1);
+          if (valid) {
+            const float* prow = reinterpret_cast<const float*>(smem_raw + off_prow + (size_t)slot * prow_bytes) + c0;
+            for (int hh = 0; hh < h_loop; ++hh) {
+              const int h = h0 + hh;
+              float2 pv;
               if (VEC2) {
-                *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
+                pv = *reinterpret_cast<const float2*>(prow + h * C);
               } else {
-                dst[0] = o0;
-                if (has1) dst[1] = o1;
+                pv.x = prow[h * C];
+                pv.y = has1 ? prow[h * C + 1] : 0.f;
+              }
+              const float* ar = tile + (size_t)(h * N + j) * NS;
+              const float2 px = make_float2(pv.x, pv.x);
+              const float2 py = make_float2(pv.y, pv.y);
+#pragma unroll
+              for (int q = 0; q < NPAIRS / 2; ++q) {
+                const float4 a4 = *reinterpret_cast<const float4*>(ar + 4 * q);
+                const float2 a0 = make_float2(a4.x, a4.y), a1 = make_float2(a4.z, a4.w);
+                acc[2 * q][0] = ffma2(a0, px, acc[2 * q][0]);
+                acc[2 * q][1] = ffma2(a0, py, acc[2 * q][1]);
+                acc[2 * q + 1][0] = ffma2(a1, px, acc[2 * q + 1][0]);
+                acc[2 * q + 1][1] = ffma2(a1, py, acc[2 * q + 1][1]);
+              }
+              if (NPAIRS & 1) {
+                const float2 a0 = *reinterpret_cast<const float2*>(ar + 2 * (NPAIRS - 1));
+                acc[NPAIRS - 1][0] = ffma2(a0, px, acc[NPAIRS - 1][0]);
+                acc[NPAIRS - 1][1] = ffma2(a0, py, acc[NPAIRS - 1][1]);
+              }
+            }
+          }
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive_cta(&prow_empty[slot]);   // this warp is done with the row
+        }
+        if (valid) {
+          // epilogue: + bias, rows 2ip and 2ip+1
+          const int col = h0 * C + c0;
+          const float b0 = args.bias ? args.bias[col] : 0.f;
+          const float b1 = (args.bias && has1) ? args.bias[col + 1] : 0.f;
+          float* orow = args.out + (size_t)b * N * p.ldo + col;
+#pragma unroll
+          for (int ip = 0; ip < NPAIRS; ++ip) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int i = 2 * ip + half;
+              if (i < N) {
+                const float o0 = (half ? acc[ip][0].y : acc[ip][0].x) + b0;
+                const float o1 = (half ? acc[ip][1].y : acc[ip][1].x) + b1;
+                float* dst = orow + (size_t)i * p.ldo;
+                if (VEC2) {
+                  *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
+                } else {
+                  dst[0] = o0;
+                  if (has1) dst[1] = o1;
+                }
               }
             }
           }
@@ -221,10 +225,25 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm) {
       }
       mbar_arrive_cta(&tile_empty[buf]);                 // this thread is done reading the tile
     }
+  } else if (tid == kGroupA + kGroupB) {
+    // ================================ warp 12, lane 0: P-row producer ================================
+    uint32_t rowctr = 0;
+    for (int it = 0; it < my_graphs; ++it) {
+      const int b = blockIdx.x + it * gridDim.x;
+      for (int pass = 0; pass < n_pass; ++pass) {
+        for (int j = 0; j < N; ++j, ++rowctr) {
+          const int slot = rowctr % kPRows;
+          mbar_wait(&prow_empty[slot], ((rowctr / kPRows) & 1) ^ 1);
+          mbar_expect_tx(&prow_full[slot], prow_bytes);
+          bulk_g2s(smem_raw + off_prow + (size_t)slot * prow_bytes, p.P_aug + ((size_t)b * N + j) * p.ldp, prow_bytes,
+                   &prow_full[slot]);
+        }
+      }
+    }
   }
 }
 
-template <int NPAIRS, int JU, bool VEC2>
+template <int NPAIRS, bool VEC2>
 static int launch_fwd(const AttnFwdArgs& a, cudaStream_t st) {
   const AttnParams& p = a.p;
   const size_t tile_bytes = round_up((size_t)p.H * p.N * ((2 * NPAIRS + 3) / 4 * 4) * 4, 16);
@@ -236,35 +255,27 @@ static int launch_fwd(const AttnFwdArgs& a, cudaStream_t st) {
     s.base_total = s.off_ring;
     return s;
   };
+  const size_t prow_bytes = (size_t)p.ldp * 4;           // one P_aug row (ldp % 4 == 0 -> multiple of 16)
+  auto total = [&](const AttnSmem& s) { return round_up(s.off_ring + 2 * s.ring_stage_bytes, 128) + kPRows * prow_bytes; };
   AttnSmem sm = finish(attn_smem_plan(p.N, p.Fe, p.H, p.R, NPAIRS, kFwdChunkRows));
-  for (int rows = kFwdChunkRows - 16; rows >= 16 && sm.off_ring + 2 * sm.ring_stage_bytes > 227 * 1024; rows -= 16)
+  for (int rows = kFwdChunkRows - 16; rows >= 16 && total(sm) > 227 * 1024; rows -= 16)
     sm = finish(attn_smem_plan(p.N, p.Fe, p.H, p.R, NPAIRS, rows));
-  const size_t smem = sm.off_ring + 2 * sm.ring_stage_bytes;
+  const size_t smem = total(sm);
   if (smem > 227 * 1024)
     return fail(SPOTV2_ERR_UNSUPPORTED, "attn_fwd needs %zu B shared memory (> 227 KB)", smem);
-  auto kern = gat_attn_fwd_kernel<NPAIRS, JU, VEC2>;
+  const uint32_t off_prow = (uint32_t)round_up(sm.off_ring + 2 * sm.ring_stage_bytes, 128);
+  auto kern = gat_attn_fwd_kernel<NPAIRS, VEC2>;
   SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = sm_count();
   if (grid > p.B) grid = p.B;
-  kern<<<grid, kFwdThreads, smem, st>>>(a, sm);
+  kern<<<grid, kFwdThreads, smem, st>>>(a, sm, off_prow, (uint32_t)prow_bytes);
   SPOTV2_CUDA_OK(cudaGetLastError());
   return SPOTV2_OK;
 }
 
-template <int NPAIRS, bool VEC2>
-static int dispatch_ju(const AttnFwdArgs& a, cudaStream_t st) {
-  const int N = a.p.N;
-  if (N % 6 == 0) return launch_fwd<NPAIRS, 6, VEC2>(a, st);
-  if (N % 5 == 0) return launch_fwd<NPAIRS, 5, VEC2>(a, st);
-  if (N % 4 == 0) return launch_fwd<NPAIRS, 4, VEC2>(a, st);
-  if (N % 3 == 0) return launch_fwd<NPAIRS, 3, VEC2>(a, st);
-  if (N % 2 == 0) return launch_fwd<NPAIRS, 2, VEC2>(a, st);
-  return launch_fwd<NPAIRS, 1, VEC2>(a, st);
-}
-
 template <int NPAIRS>
 static int dispatch_vec(const AttnFwdArgs& a, cudaStream_t st) {
-  return a.p.vec2_ok ? dispatch_ju<NPAIRS, true>(a, st) : dispatch_ju<NPAIRS, false>(a, st);
+  return a.p.vec2_ok ? launch_fwd<NPAIRS, true>(a, st) : launch_fwd<NPAIRS, false>(a, st);
 }
 
 int attn_fwd_dispatch(const AttnFwdArgs& a, cudaStream_t st) {

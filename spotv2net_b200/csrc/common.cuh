@@ -100,6 +100,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(32);
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }

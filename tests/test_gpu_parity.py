@@ -137,14 +137,26 @@ def test_projection_gemms(cuda_lib, shape, algo):
     check(cuda_lib.spotv2_gat_workspace_bytes(C.byref(d), C.byref(a), C.byref(b), C.byref(c)), "ws")
     ws = torch.empty(max(a.value, c.value), dtype=torch.uint8, device=DEV)
     P = torch.zeros(n, ldp, device=DEV)
-    check(cuda_lib.spotv2_proj_fwd(C.byref(d), ptr(xg), ptr(Wg), ptr(P), ptr(ws), ws.numel(), st()), "proj_fwd")
+    check(cuda_lib.spotv2_proj_fwd(C.byref(d), ptr(xg), None, None, ptr(Wg), ptr(P), ptr(ws), ws.numel(), st()), "proj_fwd")
     assert relerr(P[:, :n_aug], x.double() @ W_aug.double().t()) < TOL
     dW = torch.empty(n_aug, Fin, device=DEV)
-    check(cuda_lib.spotv2_proj_bwd_weight(C.byref(d), ptr(xg), ptr(dPg), ptr(dW), ptr(ws), ws.numel(), st()), "bwd_w")
+    check(cuda_lib.spotv2_proj_bwd_weight(C.byref(d), ptr(xg), None, None, ptr(dPg), None, ptr(dW), ptr(ws), ws.numel(), st()), "bwd_w")
     assert relerr(dW, dP[:, :n_aug].double().t() @ x.double()) < TOL
     dX = torch.empty(n, Fin, device=DEV)
-    check(cuda_lib.spotv2_proj_bwd_input(C.byref(d), ptr(dPg), ptr(Wg), ptr(dX), ptr(ws), ws.numel(), st()), "bwd_x")
+    check(cuda_lib.spotv2_proj_bwd_input(C.byref(d), ptr(dPg), None, ptr(Wg), ptr(dX), ptr(ws), ws.numel(), st()), "bwd_x")
     assert relerr(dX, dP[:, :n_aug].double() @ W_aug.double()) < TOL
+    if algo == 2:       # the same products from caller-provided tf32 hi/lo pairs
+        assert cuda_lib.spotv2_gat_uses_tensor_cores(C.byref(d)) == 1
+        xs, ps = torch.empty(2, *xg.shape, device=DEV), torch.empty(2, *dPg.shape, device=DEV)
+        check(cuda_lib.spotv2_split_tf32(ptr(xg), ptr(xs[0]), ptr(xs[1]), xg.numel(), st()), "split x")
+        check(cuda_lib.spotv2_split_tf32(ptr(dPg), ptr(ps[0]), ptr(ps[1]), dPg.numel(), st()), "split dP")
+        assert torch.equal(xs[0] + xs[1], xg) or relerr(xs[0] + xs[1], xg) < 1e-6
+        P2, dW2, dX2 = torch.zeros_like(P), torch.empty_like(dW), torch.empty_like(dX)
+        check(cuda_lib.spotv2_proj_fwd(C.byref(d), ptr(xg), ptr(xs[0]), ptr(xs[1]), ptr(Wg), ptr(P2), ptr(ws), ws.numel(), st()), "proj_fwd")
+        check(cuda_lib.spotv2_proj_bwd_weight(C.byref(d), ptr(xg), ptr(xs[0]), ptr(xs[1]), ptr(ps[0]), ptr(ps[1]), ptr(dW2),
+                                              ptr(ws), ws.numel(), st()), "bwd_w")
+        check(cuda_lib.spotv2_proj_bwd_input(C.byref(d), ptr(ps[0]), ptr(ps[1]), ptr(Wg), ptr(dX2), ptr(ws), ws.numel(), st()), "bwd_x")
+        assert torch.equal(P2[:, :n_aug], P[:, :n_aug]) and torch.equal(dW2, dW) and torch.equal(dX2, dX)
 
 
 GEMM_CASES = [
@@ -233,7 +245,13 @@ def test_attention_stages_against_dense_oracle(cuda_lib):
         dv, dbias = torch.empty(H, Fe, device=DEV), torch.empty(ldo, device=DEV)
         dout_g = dout.to(DEV)
         check(cuda_lib.spotv2_gat_attn_bwd(C.byref(d), ptr(P_aug), ptr(ea), ptr(topo.table), ptr(v), ptr(dout_g),
-                                           ptr(dP), ptr(dv), ptr(dbias), ptr(ws), ws.numel(), st()), "attn_bwd")
+                                           ptr(dP), None, ptr(dv), ptr(dbias), ptr(ws), ws.numel(), st()), "attn_bwd")
+        # the pre-split form: hi + lo reproduces the fp32 gradient to ~2^-22
+        dP_hi, dP_lo = torch.zeros_like(dP), torch.zeros_like(dP)
+        check(cuda_lib.spotv2_gat_attn_bwd(C.byref(d), ptr(P_aug), ptr(ea), ptr(topo.table), ptr(v), ptr(dout_g),
+                                           ptr(dP_hi), ptr(dP_lo), ptr(dv), ptr(dbias), ptr(ws), ws.numel(), st()), "attn_bwd")
+        assert relerr((dP_hi + dP_lo)[:, :H * C_ + 2 * H], dP[:, :H * C_ + 2 * H]) < 1e-6
+        assert (dP_hi.view(torch.int32) & 0x1fff).abs().max() == 0      # hi is a valid tf32 value
         HC = H * C_
         assert relerr(dP[:, :HC], gr["dP_aug"][:, :HC]) < TOL
         assert relerr(dP[:, HC:HC + 2 * H], gr["dP_aug"][:, HC:]) < TOL
