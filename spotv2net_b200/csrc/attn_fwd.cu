@@ -3,16 +3,18 @@
 // utils.softmax, message + 'add' aggregation, head mean/concat and bias
 // ([PyG] nn/conv/gat_conv.py; reached from /root/reference/utils/models.py:146).
 //
-// One persistent CTA per SM, 384 threads, warp-specialised and pipelined ACROSS graphs:
+// One persistent CTA per SM, 672 threads, warp-specialised and pipelined ACROSS graphs:
 //
 //   group A (warps 0-3)   for graph b+1: edge rows stream through a 2-stage shared-memory ring
 //                         (cp.async.bulk + mbarrier, issued two chunks ahead, across graph boundaries);
 //                         g[e,h] = <edge_attr[e], v_h> on mma.sync m16n8k8 with a 3xTF32 split;
 //                         self-loop mean fill, s_j + d_i + g_ij, LeakyReLU, softmax over sources
 //                         -> attention tile[buf] in shared memory.
-//   group B (warps 4-11)  for graph b: out[i, c] = sum_{h,j} alpha_h[i,j] P[j,h,c].  A thread owns a
-//                         channel pair and ALL targets (packed FFMA2, alpha broadcast from shared memory).
-//   warp 12               P-row producer: one cp.async.bulk per source row (all heads, 12 KB) into a
+//   group B (warps 4-19)  for graph b: out[i, c] = sum_{h,j} alpha_h[i,j] P[j,h,c].  A thread owns a
+//                         channel pair and half of the targets (packed FFMA2, alpha broadcast from shared
+//                         memory, next alpha row prefetched into registers): 4 warps per scheduler hide
+//                         the shared-memory latency.
+//   warp 20               P-row producer: one cp.async.bulk per source row (all heads, 12 KB) into a
 //                         kPRows-deep shared-memory ring, running ahead across graph boundaries.
 //
 // The two groups hand tiles over through mbarriers (tile_full / tile_empty), so the edge stream and the
@@ -21,9 +23,10 @@
 
 namespace spotv2 {
 
-constexpr int kFwdThreads = 416;
 constexpr int kGroupA = 128;
-constexpr int kGroupB = 256;
+constexpr int kGroupB = 512;          // 16 warps: 256 channel pairs x 2 target halves
+constexpr int kItemsPerPass = kGroupB / 2;
+constexpr int kFwdThreads = kGroupA + kGroupB + 32;
 constexpr int kPRows = 4;          // P-row ring depth (rows in flight)
 
 struct AttnFwdArgs {
@@ -57,7 +60,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
   uint64_t* prow_empty = bars + 6 + kPRows;
   const int CP = (C + 1) / 2;
   const int n_items = p.concat ? H * CP : CP;
-  const int n_pass = (n_items + kGroupB - 1) / kGroupB;
+  const int n_pass = (n_items + kItemsPerPass - 1) / kItemsPerPass;
   int32_t* table_s = reinterpret_cast<int32_t*>(smem_raw + sm.off_table);
   float4* vfrag = reinterpret_cast<float4*>(smem_raw + sm.off_vfrag);
   float* sd0 = reinterpret_cast<float*>(smem_raw + sm.off_sd);
@@ -143,54 +146,63 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
     }
   } else if (tid < kGroupA + kGroupB) {
     // ================================ group B: aggregation ================================
+    constexpr int HP = (NPAIRS + 1) / 2;                   // target pairs per half
+    constexpr int HQ = (HP + 1) / 2;                       // float4 loads per alpha half-row
     const int t = tid - kGroupA;
-    const int h_begin0 = 0, h_loop = p.concat ? 1 : H;
+    const int half = t / kItemsPerPass;                    // which half of the targets
+    const int tt = t - half * kItemsPerPass;
+    const int h_loop = p.concat ? 1 : H;
+    const int a_off = half * 2 * HP;                       // first target of this half (multiple of 4 floats)
     uint32_t rowctr = 0;                                   // position in the P-row stream (graph, pass, j)
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
       const int buf = it & 1;
-      const float* tile = tile0 + buf * tile_floats;
+      const float* tile = tile0 + buf * tile_floats + a_off;
       mbar_wait(&tile_full[buf], (it >> 1) & 1);
       for (int pass = 0; pass < n_pass; ++pass) {
-        const int item = pass * kGroupB + t;
+        const int item = pass * kItemsPerPass + tt;
         const bool valid = item < n_items;
-        const int h0 = (p.concat && valid) ? item / CP : h_begin0;
+        const int h0 = (p.concat && valid) ? item / CP : 0;
         const int cp = valid ? (p.concat ? item - h0 * CP : item) : 0;
         const int c0 = 2 * cp;
         const bool has1 = c0 + 1 < C;
-        float2 acc[NPAIRS][2];
+        float2 acc[HP][2];
 #pragma unroll
-        for (int ip = 0; ip < NPAIRS; ++ip) acc[ip][0] = acc[ip][1] = make_float2(0.f, 0.f);
+        for (int ip = 0; ip < HP; ++ip) acc[ip][0] = acc[ip][1] = make_float2(0.f, 0.f);
         for (int j = 0; j < N; ++j, ++rowctr) {
           const int slot = rowctr % kPRows;
           mbar_wait(&prow_full[slot], (rowctr / kPRows) & 1);
           if (valid) {
-            const float* prow = reinterpret_cast<const float*>(smem_raw + off_prow + (size_t)slot * prow_bytes) + c0;
-            for (int hh = 0; hh < h_loop; ++hh) {
-              const int h = h0 + hh;
-              float2 pv;
-              if (VEC2) {
-                pv = *reinterpret_cast<const float2*>(prow + h * C);
-              } else {
-                pv.x = prow[h * C];
-                pv.y = has1 ? prow[h * C + 1] : 0.f;
-              }
-              const float* ar = tile + (size_t)(h * N + j) * NS;
-              const float2 px = make_float2(pv.x, pv.x);
-              const float2 py = make_float2(pv.y, pv.y);
+            const float* prow = reinterpret_cast<const float*>(smem_raw + off_prow + (size_t)slot * prow_bytes) + h0 * C + c0;
+            const float* ar = tile + (size_t)(h0 * N + j) * NS;
+            float4 an[HQ];                                 // alpha half-row of the NEXT head, prefetched
 #pragma unroll
-              for (int q = 0; q < NPAIRS / 2; ++q) {
-                const float4 a4 = *reinterpret_cast<const float4*>(ar + 4 * q);
-                const float2 a0 = make_float2(a4.x, a4.y), a1 = make_float2(a4.z, a4.w);
+            for (int q = 0; q < HQ; ++q) an[q] = *reinterpret_cast<const float4*>(ar + 4 * q);
+            float2 pn;
+            if (VEC2) pn = *reinterpret_cast<const float2*>(prow);
+            else { pn.x = prow[0]; pn.y = has1 ? prow[1] : 0.f; }
+            for (int hh = 0; hh < h_loop; ++hh) {
+              float4 ac[HQ];
+#pragma unroll
+              for (int q = 0; q < HQ; ++q) ac[q] = an[q];
+              const float2 px = make_float2(pn.x, pn.x), py = make_float2(pn.y, pn.y);
+              if (hh + 1 < h_loop) {
+                ar += (size_t)N * NS;
+                prow += C;
+#pragma unroll
+                for (int q = 0; q < HQ; ++q) an[q] = *reinterpret_cast<const float4*>(ar + 4 * q);
+                if (VEC2) pn = *reinterpret_cast<const float2*>(prow);
+                else { pn.x = prow[0]; pn.y = has1 ? prow[1] : 0.f; }
+              }
+#pragma unroll
+              for (int q = 0; q < HQ; ++q) {
+                const float2 a0 = make_float2(ac[q].x, ac[q].y), a1 = make_float2(ac[q].z, ac[q].w);
                 acc[2 * q][0] = ffma2(a0, px, acc[2 * q][0]);
                 acc[2 * q][1] = ffma2(a0, py, acc[2 * q][1]);
-                acc[2 * q + 1][0] = ffma2(a1, px, acc[2 * q + 1][0]);
-                acc[2 * q + 1][1] = ffma2(a1, py, acc[2 * q + 1][1]);
-              }
-              if (NPAIRS & 1) {
-                const float2 a0 = *reinterpret_cast<const float2*>(ar + 2 * (NPAIRS - 1));
-                acc[NPAIRS - 1][0] = ffma2(a0, px, acc[NPAIRS - 1][0]);
-                acc[NPAIRS - 1][1] = ffma2(a0, py, acc[NPAIRS - 1][1]);
+                if (2 * q + 1 < HP) {
+                  acc[2 * q + 1][0] = ffma2(a1, px, acc[2 * q + 1][0]);
+                  acc[2 * q + 1][1] = ffma2(a1, py, acc[2 * q + 1][1]);
+                }
               }
             }
           }
@@ -198,19 +210,19 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
           if ((tid & 31) == 0) mbar_arrive_cta(&prow_empty[slot]);   // this warp is done with the row
         }
         if (valid) {
-          // epilogue: + bias, rows 2ip and 2ip+1
+          // epilogue: + bias, targets a_off + 2ip and a_off + 2ip + 1
           const int col = h0 * C + c0;
           const float b0 = args.bias ? args.bias[col] : 0.f;
           const float b1 = (args.bias && has1) ? args.bias[col + 1] : 0.f;
           float* orow = args.out + (size_t)b * N * p.ldo + col;
 #pragma unroll
-          for (int ip = 0; ip < NPAIRS; ++ip) {
+          for (int ip = 0; ip < HP; ++ip) {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const int i = 2 * ip + half;
+            for (int hf = 0; hf < 2; ++hf) {
+              const int i = a_off + 2 * ip + hf;
               if (i < N) {
-                const float o0 = (half ? acc[ip][0].y : acc[ip][0].x) + b0;
-                const float o1 = (half ? acc[ip][1].y : acc[ip][1].x) + b1;
+                const float o0 = (hf ? acc[ip][0].y : acc[ip][0].x) + b0;
+                const float o1 = (hf ? acc[ip][1].y : acc[ip][1].x) + b1;
                 float* dst = orow + (size_t)i * p.ldo;
                 if (VEC2) {
                   *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
@@ -226,7 +238,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
       mbar_arrive_cta(&tile_empty[buf]);                 // this thread is done reading the tile
     }
   } else if (tid == kGroupA + kGroupB) {
-    // ================================ warp 12, lane 0: P-row producer ================================
+    // ================================ last warp, lane 0: P-row producer ================================
     uint32_t rowctr = 0;
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;

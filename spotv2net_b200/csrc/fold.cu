@@ -4,46 +4,36 @@
 
 namespace spotv2 {
 
-// u[h][f] = sum_c W[(h*C + c)*F + f] * a[h][c] for the two attention vectors at once.
-__global__ void fold_u_kernel(const float* __restrict__ W, const float* __restrict__ a_src,
-                              const float* __restrict__ a_dst, float* __restrict__ u_src,
-                              float* __restrict__ u_dst, int H, int C, int F) {
+// out_k[h][f] = sum_c M[(h*C + c)*F + f] * a_k[h][c]  (k = 0, 1; a_1 may be null).
+// Block = 32 features x NY channel slices: coalesced 128-byte row reads, NY-way split of the C-long sum,
+// fixed-order shared-memory reduction (deterministic).
+template <int NY>
+__global__ void __launch_bounds__(32 * NY)
+fold_kernel(const float* __restrict__ M, const float* __restrict__ a0, const float* __restrict__ a1,
+            float* __restrict__ out0, float* __restrict__ out1, int C, int F) {
+  __shared__ float red[2][NY][33];
   const int h = blockIdx.y;
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= F) return;
-  const float* Wh = W + (size_t)h * C * F + f;
-  float s0 = 0.f, s1 = 0.f, d0 = 0.f, d1 = 0.f;
-  int c = 0;
-  for (; c + 1 < C; c += 2) {
-    const float w0 = Wh[(size_t)c * F], w1 = Wh[(size_t)(c + 1) * F];
-    s0 = fmaf(w0, a_src[h * C + c], s0);
-    s1 = fmaf(w1, a_src[h * C + c + 1], s1);
-    d0 = fmaf(w0, a_dst[h * C + c], d0);
-    d1 = fmaf(w1, a_dst[h * C + c + 1], d1);
-  }
-  if (c < C) {
-    const float w0 = Wh[(size_t)c * F];
-    s0 = fmaf(w0, a_src[h * C + c], s0);
-    d0 = fmaf(w0, a_dst[h * C + c], d0);
-  }
-  u_src[(size_t)h * F + f] = s0 + s1;
-  u_dst[(size_t)h * F + f] = d0 + d1;
-}
-
-__global__ void fold_v_kernel(const float* __restrict__ We, const float* __restrict__ a_edge,
-                              float* __restrict__ v, int H, int C, int Fe) {
-  const int h = blockIdx.y;
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= Fe) return;
-  const float* Wh = We + (size_t)h * C * Fe + f;
+  const int f = blockIdx.x * 32 + threadIdx.x;
+  const int y = threadIdx.y;
   float s0 = 0.f, s1 = 0.f;
-  int c = 0;
-  for (; c + 1 < C; c += 2) {
-    s0 = fmaf(Wh[(size_t)c * Fe], a_edge[h * C + c], s0);
-    s1 = fmaf(Wh[(size_t)(c + 1) * Fe], a_edge[h * C + c + 1], s1);
+  if (f < F) {
+    const float* Mh = M + (size_t)h * C * F + f;
+    for (int c = y; c < C; c += NY) {
+      const float w = Mh[(size_t)c * F];
+      s0 = fmaf(w, a0[h * C + c], s0);
+      if (a1) s1 = fmaf(w, a1[h * C + c], s1);
+    }
   }
-  if (c < C) s0 = fmaf(Wh[(size_t)c * Fe], a_edge[h * C + c], s0);
-  v[(size_t)h * Fe + f] = s0 + s1;
+  red[0][y][threadIdx.x] = s0;
+  red[1][y][threadIdx.x] = s1;
+  __syncthreads();
+  if (y == 0 && f < F) {
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NY; ++k) { t0 += red[0][k][threadIdx.x]; t1 += red[1][k][threadIdx.x]; }
+    out0[(size_t)h * F + f] = t0;
+    if (a1) out1[(size_t)h * F + f] = t1;
+  }
 }
 
 __device__ __forceinline__ float block_sum_128(float x, float* red) {
@@ -194,20 +184,35 @@ __device__ __forceinline__ void tri_decode(int idx, int N, int& r, int& c) {
   c = idx - r * (2 * N - r - 1) / 2 + r + 1;
 }
 
-__global__ void collate_edge_kernel(const float* __restrict__ M_vv, const int32_t* __restrict__ t0,
-                                    int N, int L, float* __restrict__ ea) {
+// One block per (graph b, 8 consecutive edge rows): 3L floats per row, rows written contiguously.
+__global__ void __launch_bounds__(256)
+collate_edge_kernel(const float* __restrict__ M_vv, const int32_t* __restrict__ t0, int N, int L,
+                    float* __restrict__ ea) {
   const int E = N * (N - 1), half = E / 2;
   const int b = blockIdx.y;
-  const int e = blockIdx.x;                // one block per edge row
-  int r, c;
-  tri_decode(e < half ? e : e - half, N, r, c);
-  const int src = e < half ? r : c, dst = e < half ? c : r;
+  const int e_base = blockIdx.x * 8;
   const int start = t0[b];
-  float* row = ea + ((size_t)b * E + e) * 3 * L;
-  for (int k = threadIdx.x; k < 3 * L; k += blockDim.x) {
+  const int row_len = 3 * L;
+  __shared__ int s_r[8], s_c[8], s_src[8], s_dst[8];
+  if (threadIdx.x < 8) {
+    const int e = e_base + threadIdx.x;
+    if (e < E) {
+      int r, c;
+      tri_decode(e < half ? e : e - half, N, r, c);
+      s_r[threadIdx.x] = r; s_c[threadIdx.x] = c;
+      s_src[threadIdx.x] = e < half ? r : c;
+      s_dst[threadIdx.x] = e < half ? c : r;
+    }
+  }
+  __syncthreads();
+  const int rows = min(8, E - e_base);
+  float* out = ea + ((size_t)b * E + e_base) * row_len;
+  for (int idx = threadIdx.x; idx < rows * row_len; idx += blockDim.x) {
+    const int er = idx / row_len, k = idx - er * row_len;
     const int which = k / L, t = k - which * L;
     const float* M = M_vv + (size_t)(start + t) * N * N;
-    row[k] = which == 0 ? M[r * N + c] : (which == 1 ? M[src * N + src] : M[dst * N + dst]);
+    const int r = s_r[er], c = s_c[er], src = s_src[er], dst = s_dst[er];
+    out[idx] = which == 0 ? M[r * N + c] : (which == 1 ? M[src * N + src] : M[dst * N + dst]);
   }
 }
 
@@ -224,12 +229,12 @@ extern "C" int spotv2_gat_fold(const spotv2_gat_desc* d, const float* W, const f
   cudaStream_t st = as_stream(stream);
   const int HC = d->H * d->C;
   SPOTV2_CUDA_OK(cudaMemcpyAsync(W_aug, W, (size_t)HC * d->F * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  dim3 g1((d->F + 127) / 128, d->H);
-  fold_u_kernel<<<g1, 128, 0, st>>>(W, a_src, a_dst, W_aug + (size_t)HC * d->F,
-                                    W_aug + (size_t)(HC + d->H) * d->F, d->H, d->C, d->F);
+  dim3 g1((d->F + 31) / 32, d->H);
+  fold_kernel<8><<<g1, dim3(32, 8), 0, st>>>(W, a_src, a_dst, W_aug + (size_t)HC * d->F,
+                                             W_aug + (size_t)(HC + d->H) * d->F, d->C, d->F);
   if (d->Fe > 0) {
-    dim3 g2((d->Fe + 127) / 128, d->H);
-    fold_v_kernel<<<g2, 128, 0, st>>>(W_e, a_edge, v, d->H, d->C, d->Fe);
+    dim3 g2((d->Fe + 31) / 32, d->H);
+    fold_kernel<32><<<g2, dim3(32, 32), 0, st>>>(W_e, a_edge, nullptr, v, nullptr, d->C, d->Fe);
   }
   SPOTV2_CUDA_OK(cudaGetLastError());
   return SPOTV2_OK;
@@ -292,8 +297,8 @@ extern "C" int spotv2_collate_windows(const float* M_vol, const float* M_vv, int
   SPOTV2_REQUIRE(T > L && N > 1 && L > 0 && B > 0, "collate_windows: need T > L, N > 1, L > 0, B > 0");
   cudaStream_t st = as_stream(stream);
   collate_x_kernel<<<B * N, 256, 0, st>>>(M_vol, t0, N, L, x, y);
-  dim3 ge(N * (N - 1), B);
-  collate_edge_kernel<<<ge, 128, 0, st>>>(M_vv, t0, N, L, edge_attr);
+  dim3 ge((N * (N - 1) + 7) / 8, B);
+  collate_edge_kernel<<<ge, 256, 0, st>>>(M_vv, t0, N, L, edge_attr);
   SPOTV2_CUDA_OK(cudaGetLastError());
   return SPOTV2_OK;
 }

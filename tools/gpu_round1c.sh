@@ -7,6 +7,6 @@ timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gp
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 160 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_list.log 2>&1
 timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/plain2.log 2>&1 && \
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"gat_attn_fwd|gemm3x" -s 6 -c 3 -o gpurun_out/fwd_full \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"gat_attn" -s 4 -c 2 -o gpurun_out/attn_full2 \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out
