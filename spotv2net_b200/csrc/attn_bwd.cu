@@ -34,7 +34,7 @@ struct AttnBwdArgs {
 __device__ __forceinline__ void store_grad(const AttnBwdArgs& a, size_t off, float v) {
   if (a.dP_lo) {
     uint32_t hi, lo;
-    split_tf32(v, hi, lo);
+    split_tf32_trunc(v, hi, lo);
     a.dP_aug[off] = __uint_as_float(hi);
     a.dP_lo[off] = __uint_as_float(lo);
   } else {
@@ -353,8 +353,8 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
           if (p.vec2_ok) {
             if (args.dP_lo) {
               uint32_t h0_, l0_, h1_, l1_;
-              split_tf32(v0, h0_, l0_);
-              split_tf32(v1, h1_, l1_);
+              split_tf32_trunc(v0, h0_, l0_);
+              split_tf32_trunc(v1, h1_, l1_);
               *reinterpret_cast<float2*>(args.dP_aug + off) = make_float2(__uint_as_float(h0_), __uint_as_float(h1_));
               *reinterpret_cast<float2*>(args.dP_lo + off) = make_float2(__uint_as_float(l0_), __uint_as_float(l1_));
             } else {
@@ -404,8 +404,8 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
             bv[half] = val;
           }
           uint32_t bh[2], bl[2];
-          split_tf32(bv[0], bh[0], bl[0]);
-          split_tf32(bv[1], bh[1], bl[1]);
+          split_tf32_trunc(bv[0], bh[0], bl[0]);
+          split_tf32_trunc(bv[1], bh[1], bl[1]);
           const bool k0_ok = r0 + t4 < rows, k1_ok = r0 + t4 + 4 < rows;
           const float* t0p = Ts + (size_t)(r0 + t4) * Fe;
           const float* t1p = t0p + (size_t)4 * Fe;
@@ -421,7 +421,7 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
               a[3] = (k1_ok && f1 < Fe) ? t1p[f1] : 0.f;     // (m = g+8, k = t+4)
               uint32_t ah[4], al[4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) split_tf32(a[q], ah[q], al[q]);
+              for (int q = 0; q < 4; ++q) split_tf32_trunc(a[q], ah[q], al[q]);
               mma_tf32_16x8x8(acc[m], al, bh);
               mma_tf32_16x8x8(acc[m], ah, bl);
               mma_tf32_16x8x8(acc[m], ah, bh);

@@ -103,43 +103,56 @@ template <int NT_MAX, class Sink>
 __device__ __forceinline__ void warp_edge_logits(const float* Ts, const float4* vfrag, int Fe, int KS,
                                                  int NT, int m0, int lane, Sink&& sink) {
   const int g = lane >> 2, t = lane & 3;
-  float acc[NT_MAX][4];
+  // Four independent accumulation chains per n-tile (even/odd k-step x {hi*hi, cross terms}) so the
+  // HMMAs are not serialised on one accumulator's latency; summed small-terms-first at the end.
+  float acc[NT_MAX][4][4];
 #pragma unroll
   for (int nt = 0; nt < NT_MAX; ++nt)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc[nt][q] = 0.f;
+    for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[nt][ch][q] = 0.f;
   const float* r0 = Ts + (size_t)(m0 + g) * Fe;
   const float* r1 = r0 + (size_t)8 * Fe;
-  for (int ks = 0; ks < KS; ++ks) {
-    const int k0 = ks * 8 + t, k1 = k0 + 4;
-    float a[4];
-    a[0] = k0 < Fe ? r0[k0] : 0.f;
-    a[1] = k0 < Fe ? r1[k0] : 0.f;
-    a[2] = k1 < Fe ? r0[k1] : 0.f;
-    a[3] = k1 < Fe ? r1[k1] : 0.f;
-    uint32_t ah[4], al[4];
+  for (int ks0 = 0; ks0 < KS; ks0 += 2) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) split_tf32(a[q], ah[q], al[q]);
+    for (int par = 0; par < 2; ++par) {
+      const int ks = ks0 + par;
+      if (ks < KS) {
+        const int k0 = ks * 8 + t, k1 = k0 + 4;
+        float a[4];
+        a[0] = k0 < Fe ? r0[k0] : 0.f;
+        a[1] = k0 < Fe ? r1[k0] : 0.f;
+        a[2] = k1 < Fe ? r0[k1] : 0.f;
+        a[3] = k1 < Fe ? r1[k1] : 0.f;
+        uint32_t ah[4], al[4];
 #pragma unroll
-    for (int nt = 0; nt < NT_MAX; ++nt) {
-      if (nt < NT) {
-        const float4 bf = vfrag[(nt * KS + ks) * 32 + lane];
-        const uint32_t bh[2] = {__float_as_uint(bf.x), __float_as_uint(bf.y)};
-        const uint32_t bl[2] = {__float_as_uint(bf.z), __float_as_uint(bf.w)};
-        mma_tf32_16x8x8(acc[nt], al, bh);
-        mma_tf32_16x8x8(acc[nt], ah, bl);
-        mma_tf32_16x8x8(acc[nt], ah, bh);
+        for (int q = 0; q < 4; ++q) split_tf32_trunc(a[q], ah[q], al[q]);
+#pragma unroll
+        for (int nt = 0; nt < NT_MAX; ++nt) {
+          if (nt < NT) {
+            const float4 bf = vfrag[(nt * KS + ks) * 32 + lane];
+            const uint32_t bh[2] = {__float_as_uint(bf.x), __float_as_uint(bf.y)};
+            const uint32_t bl[2] = {__float_as_uint(bf.z), __float_as_uint(bf.w)};
+            mma_tf32_16x8x8(acc[nt][2 * par + 1], al, bh);
+            mma_tf32_16x8x8(acc[nt][2 * par + 1], ah, bl);
+            mma_tf32_16x8x8(acc[nt][2 * par], ah, bh);
+          }
+        }
       }
     }
   }
 #pragma unroll
   for (int nt = 0; nt < NT_MAX; ++nt) {
     if (nt < NT) {
+      float c[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c[q] = (acc[nt][1][q] + acc[nt][3][q]) + (acc[nt][0][q] + acc[nt][2][q]);
       const int n = nt * 8 + 2 * t;
-      sink(m0 + g, n, acc[nt][0]);
-      sink(m0 + g, n + 1, acc[nt][1]);
-      sink(m0 + g + 8, n, acc[nt][2]);
-      sink(m0 + g + 8, n + 1, acc[nt][3]);
+      sink(m0 + g, n, c[0]);
+      sink(m0 + g, n + 1, c[1]);
+      sink(m0 + g + 8, n, c[2]);
+      sink(m0 + g + 8, n + 1, c[3]);
     }
   }
 }

@@ -55,6 +55,13 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   lo = tf32_rna(x - __uint_as_float(hi));
 }
 
+// Cheap split for hot loops (cvt.rna.tf32 is emulated with ~5 ALU ops on sm_100): hi = x truncated to
+// tf32, lo = (x - hi) truncated to tf32; x - hi is exact, so hi + lo == x to 2^-21 |x|.
+__device__ __forceinline__ void split_tf32_trunc(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
+}
+
 // D(16x8, f32) += A(16x8, tf32, row) * B(8x8, tf32, col)
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4],
                                                 const uint32_t (&b)[2]) {
@@ -84,24 +91,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                "r"(bytes)
                : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the
+// hint (ns) elapses, so a waiting warp costs almost no issue slots.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a lost transaction traps (~2 s) instead of hanging the GPU box.
+// Bounded wait: a lost transaction traps (after ~4 s of parked waits) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t tries = 0;
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(32);
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (++tries > 20000u) __trap();
   }
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,

@@ -19,7 +19,8 @@
 //   warp 0   TMA producer (one elected lane)        warp 1   MMA issuer (one elected lane)
 //   warp 2   TMEM allocator                          warps 4-11 accumulate + epilogue: warp w owns TMEM
 //            lane quarter w%4 and columns [(w-4)/4 * BN/2, +BN/2) of the tile, BN/2 running sums per thread
-// Tile 128 x BN x 32, kStages-deep shared-memory ring, two TMEM stages.  Optional split-K writes
+// Tile 128 x BN x BK (BK = 32: 128-byte swizzle rows, or 16: 64-byte rows and a twice deeper ring),
+// kStages-deep shared-memory ring, two TMEM stages.  Optional split-K writes
 // partials to a workspace that a fixed-order reduce sums (deterministic).
 #include <cuda.h>
 
@@ -28,7 +29,6 @@
 namespace spotv2 {
 
 constexpr int TBM = 128;       // UMMA M (cta_group::1)
-constexpr int TBK = 32;        // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 8;      // tf32
 constexpr int kTcThreads = 384;
 constexpr int kEpiWarps = 8;
@@ -112,23 +112,23 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
-template <int BN, bool A_KM, bool B_KM>
+template <int BN, int TBK, bool A_KM, bool B_KM>
 struct TcSmem {
-  static constexpr int kAOp = TBM * TBK * 4;               // one A operand tile (hi or lo): 16 KB
+  static constexpr int kAOp = TBM * TBK * 4;               // one A operand tile (hi or lo)
   static constexpr int kBOp = BN * TBK * 4;                // one B operand tile
   static constexpr int kStage = 2 * kAOp + 2 * kBOp;
-  static constexpr int kStages = (BN == 256) ? 2 : 3;
+  static constexpr int kStages = (200 * 1024) / kStage > 6 ? 6 : (200 * 1024) / kStage;   // 256x32: 2, 256x16: 4, 128x32: 3
   static constexpr int kBarOff = kStages * kStage;
   static constexpr int kTotal = kBarOff + 256 + 1024;      // barriers + tmem ptr + alignment slack
   static constexpr uint32_t kTxBytes = kStage;
 };
 
-template <int BN, bool A_KM, bool B_KM>
+template <int BN, int TBK, bool A_KM, bool B_KM>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                    const TcParams p) {
-  using S = TcSmem<BN, A_KM, B_KM>;
+  using S = TcSmem<BN, TBK, A_KM, B_KM>;
   constexpr int kStages = S::kStages;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -182,8 +182,8 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           } else {
 #pragma unroll
             for (int blk = 0; blk < TBM / 32; ++blk) {
-              tma_load_2d(st + blk * 4096, &tmAh, mt * TBM + blk * 32, k, &full[stage]);
-              tma_load_2d(st + S::kAOp + blk * 4096, &tmAl, mt * TBM + blk * 32, k, &full[stage]);
+              tma_load_2d(st + blk * (TBK * 128), &tmAh, mt * TBM + blk * 32, k, &full[stage]);
+              tma_load_2d(st + S::kAOp + blk * (TBK * 128), &tmAl, mt * TBM + blk * 32, k, &full[stage]);
             }
           }
           unsigned char* sb = st + 2 * S::kAOp;
@@ -193,8 +193,8 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           } else {
 #pragma unroll
             for (int blk = 0; blk < BN / 32; ++blk) {
-              tma_load_2d(sb + blk * 4096, &tmBh, nt * BN + blk * 32, k, &full[stage]);
-              tma_load_2d(sb + S::kBOp + blk * 4096, &tmBl, nt * BN + blk * 32, k, &full[stage]);
+              tma_load_2d(sb + blk * (TBK * 128), &tmBh, nt * BN + blk * 32, k, &full[stage]);
+              tma_load_2d(sb + S::kBOp + blk * (TBK * 128), &tmBl, nt * BN + blk * 32, k, &full[stage]);
             }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -206,10 +206,12 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     if (elect_one()) {
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_KM ? 0u : 1u) << 15) |
                                  ((B_KM ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-      // K-major: LBO unused (1), SBO 1024.  MN-major: LBO = one 32-wide block = TBK rows * 128 B, SBO 512.
+      // K-major: rows of TBK*4 bytes (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B), 8-row atoms, LBO unused.
+      // MN-major: LBO = one 32-wide block = TBK rows * 128 B, SBO 512 (4-row atoms), SWIZZLE_128B_BASE32B.
+      constexpr uint32_t k_sbo = 8 * TBK * 4, k_lt = (TBK == 32) ? 2 : 4;
       constexpr uint32_t a_lbo = A_KM ? 16 : TBK * 128, b_lbo = B_KM ? 16 : TBK * 128;
-      constexpr uint32_t a_sbo = A_KM ? 1024 : 512, b_sbo = B_KM ? 1024 : 512;
-      constexpr uint32_t a_lt = A_KM ? 2 : 1, b_lt = B_KM ? 2 : 1;
+      constexpr uint32_t a_sbo = A_KM ? k_sbo : 512, b_sbo = B_KM ? k_sbo : 512;
+      constexpr uint32_t a_lt = A_KM ? k_lt : 1, b_lt = B_KM ? k_lt : 1;
       constexpr uint32_t a_kstep = A_KM ? UMMA_K * 4 : UMMA_K * 128;   // bytes per k-step of 8
       constexpr uint32_t b_kstep = B_KM ? UMMA_K * 4 : UMMA_K * 128;
       int stage = 0; uint32_t phase = 0;
@@ -383,11 +385,11 @@ bool tc_gemm_supported(bool a_kc, bool b_kc, int M, int N, int K, const float* A
   return encode_fn() != nullptr;
 }
 
-template <int BN, bool A_KM, bool B_KM>
+template <int BN, int TBK, bool A_KM, bool B_KM>
 static int launch_tc(const CUtensorMap& tAh, const CUtensorMap& tAl, const CUtensorMap& tBh, const CUtensorMap& tBl,
                      const TcParams& p, cudaStream_t st) {
-  using S = TcSmem<BN, A_KM, B_KM>;
-  auto kern = gemm3x_tf32_kernel<BN, A_KM, B_KM>;
+  using S = TcSmem<BN, TBK, A_KM, B_KM>;
+  auto kern = gemm3x_tf32_kernel<BN, TBK, A_KM, B_KM>;
   SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
   int grid = sm_count();
   const int total = p.m_tiles * p.n_tiles * p.splits;
@@ -411,6 +413,9 @@ __global__ void tc_splitk_reduce_kernel(const float* __restrict__ ws, int splits
 int gemm3x_tf32(bool a_kc, bool b_kc, int M, int N, int K, const float* A_hi, const float* A_lo, int lda,
                 const float* B_hi, const float* B_lo, int ldb, float* C, int ldc, int splits, int bn,
                 int kb_per_chunk, void* ws, size_t ws_bytes, cudaStream_t st) {
+  // bn encodes the tile: 256 | 128 select BK = 32; 256 + 16 | 128 + 16 select BK = 16 (deeper ring).
+  const int TBK = (bn & 16) ? 16 : 32;
+  bn &= ~16;
   if (!tc_gemm_supported(a_kc, b_kc, M, N, K, A_hi, lda, B_hi, ldb))
     return fail(SPOTV2_ERR_UNSUPPORTED, "tensor-core GEMM needs 16-byte aligned operands and leading dimensions % 4 == 0");
   TcParams p;
@@ -422,7 +427,7 @@ int gemm3x_tf32(bool a_kc, bool b_kc, int M, int N, int K, const float* A_hi, co
   if (splits > p.kb_total) splits = p.kb_total;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
-  p.kb_per_chunk = kb_per_chunk < 1 ? 4 : kb_per_chunk;
+  p.kb_per_chunk = kb_per_chunk < 1 ? 128 / TBK : kb_per_chunk;     // default: 128-element accumulation chains
   p.C = C; p.ldc = ldc; p.split_stride = 0;
   if (p.splits > 1) {
     const size_t need = (size_t)p.splits * M * N * sizeof(float);
@@ -434,7 +439,8 @@ int gemm3x_tf32(bool a_kc, bool b_kc, int M, int N, int K, const float* A_hi, co
   int rc;
   // K-major operand: tensor [rows = M|N, cols = K], box 32(k) x tile rows.
   // MN-major operand: tensor [rows = K, cols = M|N], box 32(m|n) x 32(k); one box per 32-wide block.
-  const CUtensorMapSwizzle kSw = CU_TENSOR_MAP_SWIZZLE_128B, mnSw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  const CUtensorMapSwizzle kSw = TBK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUtensorMapSwizzle mnSw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   if (a_kc) {
     if ((rc = make_tmap(&tAh, A_hi, M, K, lda, TBK, TBM, kSw))) return rc;
     if ((rc = make_tmap(&tAl, A_lo, M, K, lda, TBK, TBM, kSw))) return rc;
@@ -449,20 +455,19 @@ int gemm3x_tf32(bool a_kc, bool b_kc, int M, int N, int K, const float* A_hi, co
     if ((rc = make_tmap(&tBh, B_hi, K, N, ldb, 32, TBK, mnSw))) return rc;
     if ((rc = make_tmap(&tBl, B_lo, K, N, ldb, 32, TBK, mnSw))) return rc;
   }
-#define SPOTV2_TC(BN_, AK, BK_) rc = launch_tc<BN_, AK, BK_>(tAh, tAl, tBh, tBl, p, st)
-  if (bn == 256) {
-    if (a_kc && b_kc) SPOTV2_TC(256, true, true);
-    else if (a_kc) SPOTV2_TC(256, true, false);
-    else if (b_kc) SPOTV2_TC(256, false, true);
-    else SPOTV2_TC(256, false, false);
-  } else if (bn == 128) {
-    if (a_kc && b_kc) SPOTV2_TC(128, true, true);
-    else if (a_kc) SPOTV2_TC(128, true, false);
-    else if (b_kc) SPOTV2_TC(128, false, true);
-    else SPOTV2_TC(128, false, false);
-  } else {
-    return fail(SPOTV2_ERR_INVALID_ARG, "bn must be 128 or 256");
-  }
+#define SPOTV2_TC(BN_, TBK_, AK, BK_) rc = launch_tc<BN_, TBK_, AK, BK_>(tAh, tAl, tBh, tBl, p, st)
+#define SPOTV2_TC_MAJ(BN_, TBK_)                            \
+  do {                                                      \
+    if (a_kc && b_kc) SPOTV2_TC(BN_, TBK_, true, true);     \
+    else if (a_kc) SPOTV2_TC(BN_, TBK_, true, false);       \
+    else if (b_kc) SPOTV2_TC(BN_, TBK_, false, true);       \
+    else SPOTV2_TC(BN_, TBK_, false, false);                \
+  } while (0)
+  if (bn == 256 && TBK == 32) SPOTV2_TC_MAJ(256, 32);
+  else if (bn == 256 && TBK == 16) SPOTV2_TC_MAJ(256, 16);
+  else if (bn == 128 && TBK == 32) SPOTV2_TC_MAJ(128, 32);
+  else return fail(SPOTV2_ERR_INVALID_ARG, "bn must be 128, 256 or 256+16");
+#undef SPOTV2_TC_MAJ
 #undef SPOTV2_TC
   if (rc) return rc;
   if (p.splits > 1) {

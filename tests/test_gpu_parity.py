@@ -165,6 +165,9 @@ GEMM_CASES = [
     (1, 1, 300, 520, 1260, 1, 128, 2), (1, 1, 4096, 3012, 1260, 1, 256, 4), (1, 1, 77, 40, 100, 1, 128, 1),
     (0, 0, 3012, 1260, 6000, 3, 256, 4), (0, 0, 280, 100, 999 * 4, 5, 128, 4), (0, 0, 128, 256, 64, 1, 256, 4),
     (1, 0, 500, 1260, 3012, 1, 256, 4), (1, 0, 130, 64, 280, 1, 128, 4), (0, 1, 260, 300, 512, 2, 256, 8),
+    # bn = 256 + 16 selects the 16-deep k-block variant (64-byte swizzle, 4-stage ring)
+    (1, 1, 300, 520, 1260, 1, 272, 8), (0, 0, 3012, 1260, 6000, 3, 272, 8), (1, 0, 500, 1260, 3012, 1, 272, 0),
+    (0, 1, 260, 300, 520, 2, 272, 3),
 ]
 
 
