@@ -200,6 +200,50 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
     //  D is written only after the chunk loop's barriers)
 
     // ---- B2: dalpha = dO . P^T -------------------------------------------------------------
+    // Per-thread staging descriptors (the float4 a thread copies has the same row and column quarter in
+    // every channel chunk): source pointer at channel 0 (null = zero-fill row) and shared-memory offset.
+    constexpr int kFastIt = 4;
+    const int stage_items = (H * sm.NP5 + (p.concat ? H : 1) * sm.NP5) * (kCK / 4);
+    const bool stage_fast = vec4 && stage_items <= kFastIt * kAttnThreads;
+    const float* st_src[kFastIt];
+    int st_dst[kFastIt];
+    if (stage_fast) {
+      const int rowsP = H * sm.NP5;
+#pragma unroll
+      for (int itn = 0; itn < kFastIt; ++itn) {
+        const int idx = tid + itn * kAttnThreads;
+        const int row = idx >> 2, q = idx & 3;
+        st_src[itn] = nullptr;
+        st_dst[itn] = -1;
+        if (idx < stage_items) {
+          if (row < rowsP) {
+            const int h = row / sm.NP5, j = row - h * sm.NP5;
+            st_dst[itn] = row * kCKP + 4 * q;
+            if (j < N) st_src[itn] = p.P_aug + ((size_t)b * N + j) * p.ldp + (size_t)h * C + 4 * q;
+          } else {
+            const int r2 = row - rowsP;
+            const int h = r2 / sm.NP5, i = r2 - h * sm.NP5;
+            st_dst[itn] = stage_g_off + r2 * kCKP + 4 * q;
+            if (i < N) st_src[itn] = args.dout + ((size_t)b * N + i) * p.ldo + (size_t)h * C + 4 * q;
+          }
+        }
+      }
+    }
+    auto stage = [&](int bufsel, int c_base) {
+      float* base = stage_base + bufsel * stage_floats;
+      if (stage_fast) {
+        const bool col_ok = c_base + 4 * (tid & 3) < C;
+#pragma unroll
+        for (int itn = 0; itn < kFastIt; ++itn) {
+          if (st_dst[itn] >= 0) {
+            const bool ok = col_ok && st_src[itn] != nullptr;
+            cp_async16(base + st_dst[itn], ok ? st_src[itn] + c_base : p.P_aug, ok);
+          }
+        }
+      } else {
+        stage_chunk(args, sm, base, base + stage_g_off, b, c_base, vec4, tid);
+      }
+    };
     for (int t0 = 0; t0 < n_tiles; t0 += kAttnThreads) {
       const int t = t0 + tid;
       const bool active = t < n_tiles;
@@ -209,13 +253,11 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
       for (int ii = 0; ii < kTI; ++ii)
 #pragma unroll
         for (int jj = 0; jj < kTJ; ++jj) acc[ii][jj] = make_float2(0.f, 0.f);
-      stage_chunk(args, sm, stage_base, stage_base + stage_g_off, b, 0, vec4, tid);
+      stage(0, 0);
       cp_async_commit();
       for (int ch = 0; ch < nchan_chunks; ++ch) {
         const int buf = ch & 1;
-        if (ch + 1 < nchan_chunks)
-          stage_chunk(args, sm, stage_base + (buf ^ 1) * stage_floats, stage_base + (buf ^ 1) * stage_floats + stage_g_off, b,
-                      (ch + 1) * kCK, vec4, tid);
+        if (ch + 1 < nchan_chunks) stage(buf ^ 1, (ch + 1) * kCK);
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();

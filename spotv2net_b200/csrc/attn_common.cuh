@@ -39,7 +39,7 @@ inline AttnSmem attn_smem_plan(int N, int Fe, int H, int R, int npairs, int chun
   s.KS = (Fe + 7) / 8;
   s.NT = (H + 7) / 8;
   size_t o = 0;
-  s.off_bar = o;   o += 128;
+  s.off_bar = o;   o += 512;
   s.off_table = o; o += round_up((size_t)R * 4, 16);
   s.off_vfrag = o; o += (size_t)s.NT * s.KS * 32 * 16;
   s.off_sd = o;    o += round_up((size_t)N * 2 * H * 4, 16);

@@ -3,31 +3,35 @@
 // utils.softmax, message + 'add' aggregation, head mean/concat and bias
 // ([PyG] nn/conv/gat_conv.py; reached from /root/reference/utils/models.py:146).
 //
-// One persistent CTA per SM, 672 threads, warp-specialised and pipelined ACROSS graphs:
+// One persistent CTA per SM, 384 threads (12 warps, 168 registers each), warp-specialised and pipelined ACROSS graphs:
 //
-//   group A (warps 0-3)   for graph b+1: edge rows stream through a 2-stage shared-memory ring
+//   group A (warps 0-2)   for graph b+1: edge rows stream through a 2-stage shared-memory ring
 //                         (cp.async.bulk + mbarrier, issued two chunks ahead, across graph boundaries);
 //                         g[e,h] = <edge_attr[e], v_h> on mma.sync m16n8k8 with a 3xTF32 split;
 //                         self-loop mean fill, s_j + d_i + g_ij, LeakyReLU, softmax over sources
-//                         -> attention tile[buf] in shared memory.
-//   group B (warps 4-19)  for graph b: out[i, c] = sum_{h,j} alpha_h[i,j] P[j,h,c].  A thread owns a
-//                         channel pair and half of the targets (packed FFMA2, alpha broadcast from shared
-//                         memory, next alpha row prefetched into registers): 4 warps per scheduler hide
-//                         the shared-memory latency.
-//   warp 20               P-row producer: one cp.async.bulk per source row (all heads, 12 KB) into a
-//                         kPRows-deep shared-memory ring, running ahead across graph boundaries.
+//                         -> attention tile[buf] in shared memory (double buffered).
+//   group B (warps 3-10)  for graph b: O_h[32 x C] = alpha_h[32 x 32] . P_h[32 x C] on mma.sync m16n8k8
+//                         (3xTF32, fp32-accurate).  P arrives as TMA tiles of 32 source rows x 32 channels
+//                         (128B-swizzled, conflict-free fragment reads); a warp owns two channel blocks and
+//                         keeps the alpha fragments of the current head in registers.  Per-head accumulators
+//                         are folded into the running sum with round-to-nearest adds.
+//   warp 11               TMA producer for the P tiles (16-slot ring), running ahead across graphs.
 //
-// The two groups hand tiles over through mbarriers (tile_full / tile_empty), so the edge stream and the
-// P stream keep HBM busy at the same time and the softmax never sits on the aggregation's critical path.
+// Why tensor cores here: with CUDA-core FFMA2 every lane needs the whole alpha row in registers, and the
+// shared-memory return path (512 B per LDS.128 per warp) bounded that version at 38 % of HBM peak
+// (profiles/).  MMA fragments spread alpha and P across the lanes, cutting shared-memory traffic ~8x.
 #include "attn_common.cuh"
+#include "tma.cuh"
 
 namespace spotv2 {
 
-constexpr int kGroupA = 128;
-constexpr int kGroupB = 512;          // 16 warps: 256 channel pairs x 2 target halves
-constexpr int kItemsPerPass = kGroupB / 2;
+constexpr int kGroupA = 96;           // 3 logit/softmax warps (48-row edge chunks)
+constexpr int kGroupB = 256;          // 8 MMA warps
 constexpr int kFwdThreads = kGroupA + kGroupB + 32;
-constexpr int kPRows = 4;          // P-row ring depth (rows in flight)
+constexpr int kFwdChunkRows3 = 48;    // edge rows per ring stage: one m16 tile per group-A warp
+constexpr int kPSlots = 16;           // P-tile ring depth
+constexpr int kPTileBytes = 32 * 128; // 32 source rows x 32 channels fp32, 128B-swizzled
+constexpr int kCbPerPass = 16;        // channel blocks per pass: two per MMA warp
 
 struct AttnFwdArgs {
   AttnParams p;
@@ -36,14 +40,15 @@ struct AttnFwdArgs {
   float* alpha_out;
 };
 
-__device__ __forceinline__ void bar_sync_group_a() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_group_a() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 template <int NPAIRS, bool VEC2>
 __global__ void __launch_bounds__(kFwdThreads, 1)
-gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t off_prow, const uint32_t prow_bytes) {
+gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t off_ptile,
+                    const __grid_constant__ CUtensorMap tmP) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const AttnParams& p = args.p;
   const int tid = threadIdx.x;
@@ -52,15 +57,14 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
   const int tile_floats = H * N * NS;
   const int sd_floats = N * 2 * H;
 
-  // [0,1] edge ring, [2,3] tile_full, [4,5] tile_empty, [6..6+kPRows) prow_full, then prow_empty
+  // [0,1] edge ring, [2,3] tile_full, [4,5] tile_empty, [6..6+kPSlots) ptile_full, then ptile_empty
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sm.off_bar);
   uint64_t* tile_full = bars + 2;
   uint64_t* tile_empty = bars + 4;
-  uint64_t* prow_full = bars + 6;
-  uint64_t* prow_empty = bars + 6 + kPRows;
-  const int CP = (C + 1) / 2;
-  const int n_items = p.concat ? H * CP : CP;
-  const int n_pass = (n_items + kItemsPerPass - 1) / kItemsPerPass;
+  uint64_t* ptile_full = bars + 6;
+  uint64_t* ptile_empty = bars + 6 + kPSlots;
+  const int n_cb = (C + 31) / 32;                                   // 32-channel blocks per head
+  const int n_pass = (n_cb + kCbPerPass - 1) / kCbPerPass;
   int32_t* table_s = reinterpret_cast<int32_t*>(smem_raw + sm.off_table);
   float4* vfrag = reinterpret_cast<float4*>(smem_raw + sm.off_vfrag);
   float* sd0 = reinterpret_cast<float*>(smem_raw + sm.off_sd);
@@ -76,7 +80,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
     mbar_init(&tile_full[1], kGroupA);
     mbar_init(&tile_empty[0], kGroupB);
     mbar_init(&tile_empty[1], kGroupB);
-    for (int r = 0; r < kPRows; ++r) { mbar_init(&prow_full[r], 1); mbar_init(&prow_empty[r], kGroupB / 32); }
+    for (int r = 0; r < kPSlots; ++r) { mbar_init(&ptile_full[r], 1); mbar_init(&ptile_empty[r], 1); }
     fence_mbar_init();
   }
   for (int r = tid; r < p.R; r += kFwdThreads) table_s[r] = p.Fe > 0 ? p.table[r] : -1;
@@ -145,110 +149,163 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
       mbar_arrive_cta(&tile_full[buf]);                  // release: alpha tile visible to group B
     }
   } else if (tid < kGroupA + kGroupB) {
-    // ================================ group B: aggregation ================================
-    constexpr int HP = (NPAIRS + 1) / 2;                   // target pairs per half
-    constexpr int HQ = (HP + 1) / 2;                       // float4 loads per alpha half-row
-    const int t = tid - kGroupA;
-    const int half = t / kItemsPerPass;                    // which half of the targets
-    const int tt = t - half * kItemsPerPass;
-    const int h_loop = p.concat ? 1 : H;
-    const int a_off = half * 2 * HP;                       // first target of this half (multiple of 4 floats)
-    uint32_t rowctr = 0;                                   // position in the P-row stream (graph, pass, j)
+    // ================================ group B: aggregation on mma.sync ================================
+    const int wb = (tid - kGroupA) >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const unsigned char* ptiles = smem_raw + off_ptile;
+    uint32_t q_base = 0;                                   // tiles issued before the current (pass, head) group
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
       const int buf = it & 1;
-      const float* tile = tile0 + buf * tile_floats + a_off;
+      const float* tile = tile0 + buf * tile_floats;
       mbar_wait(&tile_full[buf], (it >> 1) & 1);
       for (int pass = 0; pass < n_pass; ++pass) {
-        const int item = pass * kItemsPerPass + tt;
-        const bool valid = item < n_items;
-        const int h0 = (p.concat && valid) ? item / CP : 0;
-        const int cp = valid ? (p.concat ? item - h0 * CP : item) : 0;
-        const int c0 = 2 * cp;
-        const bool has1 = c0 + 1 < C;
-        float2 acc[HP][2];
+        const int G = min(kCbPerPass, n_cb - pass * kCbPerPass);     // valid channel blocks in this pass
+        float acc[2][2][4][4];                             // [cb slot][m-tile][n-tile][frag]
 #pragma unroll
-        for (int ip = 0; ip < HP; ++ip) acc[ip][0] = acc[ip][1] = make_float2(0.f, 0.f);
-        for (int j = 0; j < N; ++j, ++rowctr) {
-          const int slot = rowctr % kPRows;
-          mbar_wait(&prow_full[slot], (rowctr / kPRows) & 1);
-          if (valid) {
-            const float* prow = reinterpret_cast<const float*>(smem_raw + off_prow + (size_t)slot * prow_bytes) + h0 * C + c0;
-            const float* ar = tile + (size_t)(h0 * N + j) * NS;
-            float4 an[HQ];                                 // alpha half-row of the NEXT head, prefetched
+        for (int s2 = 0; s2 < 2; ++s2)
 #pragma unroll
-            for (int q = 0; q < HQ; ++q) an[q] = *reinterpret_cast<const float4*>(ar + 4 * q);
-            float2 pn;
-            if (VEC2) pn = *reinterpret_cast<const float2*>(prow);
-            else { pn.x = prow[0]; pn.y = has1 ? prow[1] : 0.f; }
-            for (int hh = 0; hh < h_loop; ++hh) {
-              float4 ac[HQ];
+          for (int m = 0; m < 2; ++m)
 #pragma unroll
-              for (int q = 0; q < HQ; ++q) ac[q] = an[q];
-              const float2 px = make_float2(pn.x, pn.x), py = make_float2(pn.y, pn.y);
-              if (hh + 1 < h_loop) {
-                ar += (size_t)N * NS;
-                prow += C;
+            for (int n = 0; n < 4; ++n)
 #pragma unroll
-                for (int q = 0; q < HQ; ++q) an[q] = *reinterpret_cast<const float4*>(ar + 4 * q);
-                if (VEC2) pn = *reinterpret_cast<const float2*>(prow);
-                else { pn.x = prow[0]; pn.y = has1 ? prow[1] : 0.f; }
-              }
+              for (int e = 0; e < 4; ++e) acc[s2][m][n][e] = 0.f;
+        for (int h = 0; h < H; ++h, q_base += G) {
+          // A fragments of alpha_h (rows = targets i, cols = sources j), split once per head
+          uint32_t ah[2][4][4], al[2][4][4];
 #pragma unroll
-              for (int q = 0; q < HQ; ++q) {
-                const float2 a0 = make_float2(ac[q].x, ac[q].y), a1 = make_float2(ac[q].z, ac[q].w);
-                acc[2 * q][0] = ffma2(a0, px, acc[2 * q][0]);
-                acc[2 * q][1] = ffma2(a0, py, acc[2 * q][1]);
-                if (2 * q + 1 < HP) {
-                  acc[2 * q + 1][0] = ffma2(a1, px, acc[2 * q + 1][0]);
-                  acc[2 * q + 1][1] = ffma2(a1, py, acc[2 * q + 1][1]);
+          for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const int i0 = m * 16 + g, j0 = ks * 8 + t;
+              const float* base = tile + (size_t)h * N * NS;
+              const float a0 = (j0 < N) ? base[j0 * NS + i0] : 0.f;
+              const float a1 = (j0 < N) ? base[j0 * NS + i0 + 8] : 0.f;
+              const float a2 = (j0 + 4 < N) ? base[(j0 + 4) * NS + i0] : 0.f;
+              const float a3 = (j0 + 4 < N) ? base[(j0 + 4) * NS + i0 + 8] : 0.f;
+              split_tf32_trunc(a0, ah[m][ks][0], al[m][ks][0]);
+              split_tf32_trunc(a1, ah[m][ks][1], al[m][ks][1]);
+              split_tf32_trunc(a2, ah[m][ks][2], al[m][ks][2]);
+              split_tf32_trunc(a3, ah[m][ks][3], al[m][ks][3]);
+            }
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const int k = wb + 8 * s2;                      // this warp's channel block within the pass
+            if (k < G) {
+              const uint32_t q = q_base + k;
+              const int slot = q % kPSlots;
+              mbar_wait(&ptile_full[slot], (q / kPSlots) & 1);
+              const unsigned char* pt = ptiles + (size_t)slot * kPTileBytes;
+              float hacc[2][4][4];                         // this head's contribution (short MMA chains)
+#pragma unroll
+              for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int n = 0; n < 4; ++n)
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) hacc[m][n][e] = 0.f;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const int r0 = ks * 8 + t, r1 = r0 + 4;     // source rows of b0 / b1
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                  const int c = n * 8 + g;                  // channel within the block
+                  const float b0 = *reinterpret_cast<const float*>(pt + r0 * 128 + ((((c >> 2) ^ (r0 & 7)) << 4) | ((c & 3) << 2)));
+                  const float b1 = *reinterpret_cast<const float*>(pt + r1 * 128 + ((((c >> 2) ^ (r1 & 7)) << 4) | ((c & 3) << 2)));
+                  uint32_t bh[2], bl[2];
+                  split_tf32_trunc(b0, bh[0], bl[0]);
+                  split_tf32_trunc(b1, bh[1], bl[1]);
+#pragma unroll
+                  for (int m = 0; m < 2; ++m) {
+                    mma_tf32_16x8x8(hacc[m][n], al[m][ks], bh);
+                    mma_tf32_16x8x8(hacc[m][n], ah[m][ks], bl);
+                    mma_tf32_16x8x8(hacc[m][n], ah[m][ks], bh);
+                  }
                 }
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cta(&ptile_empty[slot]);    // tile consumed
+              if (p.concat) {
+                // ---- concat: every head is its own output block
+                const int cb = pass * kCbPerPass + k;
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                  for (int n = 0; n < 4; ++n)
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                      const int i = m * 16 + g + 8 * hf, c = cb * 32 + n * 8 + 2 * t;
+                      if (i < N && c < C) {
+                        const int col = h * C + c;
+                        float* dst = args.out + ((size_t)b * N + i) * p.ldo + col;
+                        const float o0 = hacc[m][n][2 * hf] + (args.bias ? args.bias[col] : 0.f);
+                        if (c + 1 < C) {
+                          const float o1 = hacc[m][n][2 * hf + 1] + (args.bias ? args.bias[col + 1] : 0.f);
+                          if (VEC2) *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
+                          else { dst[0] = o0; dst[1] = o1; }
+                        } else {
+                          dst[0] = o0;
+                        }
+                      }
+                    }
+              } else {
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                  for (int n = 0; n < 4; ++n)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[s2][m][n][e] += hacc[m][n][e];
               }
             }
           }
-          __syncwarp();
-          if ((tid & 31) == 0) mbar_arrive_cta(&prow_empty[slot]);   // this warp is done with the row
         }
-        if (valid) {
-          // epilogue: + bias, targets a_off + 2ip and a_off + 2ip + 1
-          const int col = h0 * C + c0;
-          const float b0 = args.bias ? args.bias[col] : 0.f;
-          const float b1 = (args.bias && has1) ? args.bias[col + 1] : 0.f;
-          float* orow = args.out + (size_t)b * N * p.ldo + col;
+        if (!p.concat) {
+          // ---- head mean (alpha was pre-scaled by 1/H) + bias
 #pragma unroll
-          for (int ip = 0; ip < HP; ++ip) {
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const int k = wb + 8 * s2;
+            if (k < G) {
+              const int cb = pass * kCbPerPass + k;
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              const int i = a_off + 2 * ip + hf;
-              if (i < N) {
-                const float o0 = (hf ? acc[ip][0].y : acc[ip][0].x) + b0;
-                const float o1 = (hf ? acc[ip][1].y : acc[ip][1].x) + b1;
-                float* dst = orow + (size_t)i * p.ldo;
-                if (VEC2) {
-                  *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
-                } else {
-                  dst[0] = o0;
-                  if (has1) dst[1] = o1;
-                }
-              }
+              for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int n = 0; n < 4; ++n)
+#pragma unroll
+                  for (int hf = 0; hf < 2; ++hf) {
+                    const int i = m * 16 + g + 8 * hf, c = cb * 32 + n * 8 + 2 * t;
+                    if (i < N && c < C) {
+                      float* dst = args.out + ((size_t)b * N + i) * p.ldo + c;
+                      const float o0 = acc[s2][m][n][2 * hf] + (args.bias ? args.bias[c] : 0.f);
+                      if (c + 1 < C) {
+                        const float o1 = acc[s2][m][n][2 * hf + 1] + (args.bias ? args.bias[c + 1] : 0.f);
+                        if (VEC2) *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
+                        else { dst[0] = o0; dst[1] = o1; }
+                      } else {
+                        dst[0] = o0;
+                      }
+                    }
+                  }
             }
           }
         }
       }
-      mbar_arrive_cta(&tile_empty[buf]);                 // this thread is done reading the tile
+      mbar_arrive_cta(&tile_empty[buf]);                 // this thread is done reading the alpha tile
     }
   } else if (tid == kGroupA + kGroupB) {
-    // ================================ last warp, lane 0: P-row producer ================================
-    uint32_t rowctr = 0;
+    // ================================ warp 11, lane 0: P-tile producer ================================
+    prefetch_tmap(&tmP);
+    uint32_t q = 0;
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
       for (int pass = 0; pass < n_pass; ++pass) {
-        for (int j = 0; j < N; ++j, ++rowctr) {
-          const int slot = rowctr % kPRows;
-          mbar_wait(&prow_empty[slot], ((rowctr / kPRows) & 1) ^ 1);
-          mbar_expect_tx(&prow_full[slot], prow_bytes);
-          bulk_g2s(smem_raw + off_prow + (size_t)slot * prow_bytes, p.P_aug + ((size_t)b * N + j) * p.ldp, prow_bytes,
-                   &prow_full[slot]);
+        const int G = min(kCbPerPass, n_cb - pass * kCbPerPass);
+        for (int h = 0; h < H; ++h) {
+          for (int k = 0; k < G; ++k, ++q) {
+            const int slot = q % kPSlots;
+            mbar_wait(&ptile_empty[slot], ((q / kPSlots) & 1) ^ 1);
+            mbar_expect_tx(&ptile_full[slot], kPTileBytes);
+            tma_load_2d(smem_raw + off_ptile + (size_t)slot * kPTileBytes, &tmP, h * C + (pass * kCbPerPass + k) * 32,
+                        b * N, &ptile_full[slot]);
+          }
         }
       }
     }
@@ -258,29 +315,33 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
 template <int NPAIRS, bool VEC2>
 static int launch_fwd(const AttnFwdArgs& a, cudaStream_t st) {
   const AttnParams& p = a.p;
-  const size_t tile_bytes = round_up((size_t)p.H * p.N * ((2 * NPAIRS + 3) / 4 * 4) * 4, 16);
+  // alpha tile stride 40 floats: fragment reads (4 source rows x 8 targets) hit 32 distinct banks
+  const int NS = 40;
+  const size_t tile_bytes = round_up((size_t)p.H * p.N * NS * 4, 16);
   const size_t sd_bytes = round_up((size_t)p.N * 2 * p.H * 4, 16);
-  // the common plan reserves one tile + one sd; this kernel double-buffers both
-  auto finish = [&](AttnSmem s) {
+  auto finish = [&](AttnSmem s) {                 // the common plan reserves one tile + one sd; double-buffer both
+    s.NS = NS;
     s.off_tile = s.off_sd + 2 * sd_bytes;
     s.off_ring = round_up(s.off_tile + 2 * tile_bytes, 128);
     s.base_total = s.off_ring;
     return s;
   };
-  const size_t prow_bytes = (size_t)p.ldp * 4;           // one P_aug row (ldp % 4 == 0 -> multiple of 16)
-  auto total = [&](const AttnSmem& s) { return round_up(s.off_ring + 2 * s.ring_stage_bytes, 128) + kPRows * prow_bytes; };
-  AttnSmem sm = finish(attn_smem_plan(p.N, p.Fe, p.H, p.R, NPAIRS, kFwdChunkRows));
-  for (int rows = kFwdChunkRows - 16; rows >= 16 && total(sm) > 227 * 1024; rows -= 16)
+  auto ptile_off = [&](const AttnSmem& s) { return round_up(s.off_ring + 2 * s.ring_stage_bytes, 1024); };
+  auto total = [&](const AttnSmem& s) { return ptile_off(s) + (size_t)kPSlots * kPTileBytes; };
+  AttnSmem sm = finish(attn_smem_plan(p.N, p.Fe, p.H, p.R, NPAIRS, kFwdChunkRows3));
+  for (int rows = kFwdChunkRows3 - 16; rows >= 16 && total(sm) > 227 * 1024; rows -= 16)
     sm = finish(attn_smem_plan(p.N, p.Fe, p.H, p.R, NPAIRS, rows));
   const size_t smem = total(sm);
   if (smem > 227 * 1024)
     return fail(SPOTV2_ERR_UNSUPPORTED, "attn_fwd needs %zu B shared memory (> 227 KB)", smem);
-  const uint32_t off_prow = (uint32_t)round_up(sm.off_ring + 2 * sm.ring_stage_bytes, 128);
+  CUtensorMap tmP;      // P_aug as [B*N rows, ldp cols]; tiles of 32 rows x 32 channels
+  if (int rc = make_tmap(&tmP, p.P_aug, (uint64_t)p.B * p.N, (uint64_t)p.ldp, (uint64_t)p.ldp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))
+    return rc;
   auto kern = gat_attn_fwd_kernel<NPAIRS, VEC2>;
   SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = sm_count();
   if (grid > p.B) grid = p.B;
-  kern<<<grid, kFwdThreads, smem, st>>>(a, sm, off_prow, (uint32_t)prow_bytes);
+  kern<<<grid, kFwdThreads, smem, st>>>(a, sm, (uint32_t)ptile_off(sm), tmP);
   SPOTV2_CUDA_OK(cudaGetLastError());
   return SPOTV2_OK;
 }

@@ -22,9 +22,8 @@
 // Tile 128 x BN x BK (BK = 32: 128-byte swizzle rows, or 16: 64-byte rows and a twice deeper ring),
 // kStages-deep shared-memory ring, two TMEM stages.  Optional split-K writes
 // partials to a workspace that a fixed-order reduce sums (deterministic).
-#include <cuda.h>
-
 #include "gemm.cuh"
+#include "tma.cuh"
 
 namespace spotv2 {
 
@@ -42,16 +41,6 @@ struct TcParams {
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -342,47 +331,14 @@ int split_tf32(const float* src, float* hi, float* lo, size_t n, cudaStream_t st
   return SPOTV2_OK;
 }
 
-// ---- host side -------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* sym = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
-      qres != cudaDriverEntryPointSuccess)
-    return nullptr;
-  fn = reinterpret_cast<EncodeTiledFn>(sym);
-  return fn;
-}
-
-// 2-D fp32 tensor [rows, cols] (cols contiguous, row pitch ld), box = box_cols x box_rows, 128B swizzle,
-// out-of-bounds elements read as zero.
-static int make_tmap(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
-                     uint32_t box_rows, CUtensorMapSwizzle swz) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return fail(SPOTV2_ERR_NO_DEVICE, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * sizeof(float)};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(SPOTV2_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return SPOTV2_OK;
-}
-
+// ---- host side (tensor-map helpers: tma.cuh) --------------------------------------------------------
 bool tc_gemm_supported(bool a_kc, bool b_kc, int M, int N, int K, const float* A_hi, int lda, const float* B_hi,
                        int ldb) {
   if (!aligned16(A_hi) || !aligned16(B_hi)) return false;
   if (lda % 4 != 0 || ldb % 4 != 0) return false;          // TMA: 16-byte row pitch
   if (M < 1 || N < 1 || K < 1) return false;
   (void)a_kc; (void)b_kc;
-  return encode_fn() != nullptr;
+  return tma_available();
 }
 
 template <int BN, int TBK, bool A_KM, bool B_KM>

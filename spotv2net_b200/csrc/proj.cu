@@ -122,7 +122,7 @@ extern "C" int spotv2_proj_bwd_weight(const spotv2_gat_desc* d, const float* x, 
   if (!have_x)
     if (int rc = split_tf32(x, xh, xl, (size_t)s.rows * s.F, st)) return rc;
   // contraction over the B*N node rows: both operands are MN-major ([K, rows]) for this product
-  return gemm3x_tf32(false, false, s.n_aug, s.F, s.rows, ph, pl, s.ldp, xh, xl, s.F, dW_aug, s.F, splits, 256, 4,
+  return gemm3x_tf32(false, false, s.n_aug, s.F, s.rows, ph, pl, s.ldp, xh, xl, s.F, dW_aug, s.F, splits, 256 + 16, 0,
                      c.p, c.left, st);
 }
 
@@ -149,5 +149,5 @@ extern "C" int spotv2_proj_bwd_input(const spotv2_gat_desc* d, const float* dP_a
     if (int rc = split_tf32(dP_aug, ph, pl, (size_t)s.rows * s.ldp, st)) return rc;
   if (int rc = split_tf32(W_aug, wh, wl, (size_t)s.n_aug * s.F, st)) return rc;
   // dX[rows, F] = dP_aug[rows, n_aug] . W_aug[n_aug, F]: A K-major, B MN-major
-  return gemm3x_tf32(true, false, s.rows, s.F, s.n_aug, ph, pl, s.ldp, wh, wl, s.F, dX, s.F, 1, 256, 4, nullptr, 0, st);
+  return gemm3x_tf32(true, false, s.rows, s.F, s.n_aug, ph, pl, s.ldp, wh, wl, s.F, dX, s.F, 1, 256 + 16, 0, nullptr, 0, st);
 }
