@@ -33,6 +33,9 @@ constexpr int kPSlots = 16;           // P-tile ring depth
 constexpr int kPTileBytes = 32 * 128; // 32 source rows x 32 channels fp32, 128B-swizzled
 constexpr int kCbPerPass = 16;        // channel blocks per pass: two per MMA warp
 
+// wait-cycle diagnostics of this kernel (see spotv2_diag_counters)
+__device__ unsigned long long g_diag_counters[kNumCounters];
+
 struct AttnFwdArgs {
   AttnParams p;
   const float* bias;
@@ -108,12 +111,14 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
     }
     const float out_scale = p.concat ? 1.f : 1.f / (float)H;
     int k = 0;                                          // global chunk counter (stage = k & 1, parity = (k >> 1) & 1)
+    long long w_ring = 0, w_tile = 0;
+    const long long t_role = clock64();
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
       const int buf = it & 1;
       float* tile = tile0 + buf * tile_floats;
       float* sd = sd0 + buf * sd_floats;
-      mbar_wait(&tile_empty[buf], ((it >> 1) & 1) ^ 1);   // group B has finished reading this buffer
+      mbar_wait_timed(&tile_empty[buf], ((it >> 1) & 1) ^ 1, w_tile);   // group B has finished reading this buffer
       for (int idx = tid; idx < sd_floats; idx += kGroupA) {
         const int j = idx / (2 * H), kk = idx - j * 2 * H;
         sd[idx] = p.P_aug[((size_t)b * N + j) * p.ldp + HC + kk];
@@ -125,7 +130,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
         const int s = k & 1;
         const int rows = rows_in(c);
         if (p.bulk_ok) {
-          mbar_wait(&bars[s], (k >> 1) & 1);
+          mbar_wait_timed(&bars[s], (k >> 1) & 1, w_ring);
         } else {
           const float* src = p.edge_rows + ((size_t)b * p.R + (size_t)c * sm.chunk_rows) * p.Fe;
           for (int idx = tid; idx < rows * p.Fe; idx += kGroupA) stage[s][idx] = src[idx];
@@ -148,17 +153,24 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
                     nullptr, tid, kGroupA);
       mbar_arrive_cta(&tile_full[buf]);                  // release: alpha tile visible to group B
     }
+    if (tid == 0) {
+      atomicAdd(&g_diag_counters[kCntRingFull], (unsigned long long)w_ring);
+      atomicAdd(&g_diag_counters[kCntTileEmpty], (unsigned long long)w_tile);
+      atomicAdd(&g_diag_counters[kCntRoleA], (unsigned long long)(clock64() - t_role));
+    }
   } else if (tid < kGroupA + kGroupB) {
     // ================================ group B: aggregation on mma.sync ================================
     const int wb = (tid - kGroupA) >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const unsigned char* ptiles = smem_raw + off_ptile;
     uint32_t q_base = 0;                                   // tiles issued before the current (pass, head) group
+    long long w_tf = 0, w_pf = 0;
+    const long long t_role = clock64();
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
       const int buf = it & 1;
       const float* tile = tile0 + buf * tile_floats;
-      mbar_wait(&tile_full[buf], (it >> 1) & 1);
+      mbar_wait_timed(&tile_full[buf], (it >> 1) & 1, w_tf);
       for (int pass = 0; pass < n_pass; ++pass) {
         const int G = min(kCbPerPass, n_cb - pass * kCbPerPass);     // valid channel blocks in this pass
         float acc[2][2][4][4];                             // [cb slot][m-tile][n-tile][frag]
@@ -194,7 +206,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
             if (k < G) {
               const uint32_t q = q_base + k;
               const int slot = q % kPSlots;
-              mbar_wait(&ptile_full[slot], (q / kPSlots) & 1);
+              mbar_wait_timed(&ptile_full[slot], (q / kPSlots) & 1, w_pf);
               const unsigned char* pt = ptiles + (size_t)slot * kPTileBytes;
               float hacc[2][4][4];                         // this head's contribution (short MMA chains)
 #pragma unroll
@@ -290,10 +302,17 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
       }
       mbar_arrive_cta(&tile_empty[buf]);                 // this thread is done reading the alpha tile
     }
+    if (tid == kGroupA) {
+      atomicAdd(&g_diag_counters[kCntTileFull], (unsigned long long)w_tf);
+      atomicAdd(&g_diag_counters[kCntPtileFull], (unsigned long long)w_pf);
+      atomicAdd(&g_diag_counters[kCntRoleB], (unsigned long long)(clock64() - t_role));
+    }
   } else if (tid == kGroupA + kGroupB) {
     // ================================ warp 11, lane 0: P-tile producer ================================
     prefetch_tmap(&tmP);
     uint32_t q = 0;
+    long long w_pe = 0;
+    const long long t_role = clock64();
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
       for (int pass = 0; pass < n_pass; ++pass) {
@@ -301,7 +320,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
         for (int h = 0; h < H; ++h) {
           for (int k = 0; k < G; ++k, ++q) {
             const int slot = q % kPSlots;
-            mbar_wait(&ptile_empty[slot], ((q / kPSlots) & 1) ^ 1);
+            mbar_wait_timed(&ptile_empty[slot], ((q / kPSlots) & 1) ^ 1, w_pe);
             mbar_expect_tx(&ptile_full[slot], kPTileBytes);
             tma_load_2d(smem_raw + off_ptile + (size_t)slot * kPTileBytes, &tmP, h * C + (pass * kCbPerPass + k) * 32,
                         b * N, &ptile_full[slot]);
@@ -309,6 +328,8 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
         }
       }
     }
+    atomicAdd(&g_diag_counters[kCntPtileEmpty], (unsigned long long)w_pe);
+    atomicAdd(&g_diag_counters[kCntRoleP], (unsigned long long)(clock64() - t_role));
   }
 }
 
@@ -363,6 +384,17 @@ int attn_fwd_dispatch(const AttnFwdArgs& a, cudaStream_t st) {
 }  // namespace spotv2
 
 using namespace spotv2;
+
+extern "C" int spotv2_diag_counters(unsigned long long* host_out, int reset) {
+  SPOTV2_REQUIRE(host_out, "diag_counters: null pointer");
+  SPOTV2_CUDA_OK(cudaDeviceSynchronize());
+  SPOTV2_CUDA_OK(cudaMemcpyFromSymbol(host_out, g_diag_counters, sizeof(unsigned long long) * kNumCounters));
+  if (reset) {
+    unsigned long long zeros[kNumCounters] = {0};
+    SPOTV2_CUDA_OK(cudaMemcpyToSymbol(g_diag_counters, zeros, sizeof(zeros)));
+  }
+  return SPOTV2_OK;
+}
 
 extern "C" int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug,
                                    const float* edge_rows, const int32_t* table, const float* v,

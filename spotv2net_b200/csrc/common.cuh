@@ -111,6 +111,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++tries > 20000u) __trap();
   }
 }
+// Diagnostics: cycles spent parked on each class of barrier (one sampling thread per role adds its
+// totals at kernel exit); read and reset through spotv2_diag_counters().
+enum { kCntRingFull = 0, kCntTileEmpty, kCntTileFull, kCntPtileFull, kCntPtileEmpty, kCntRoleA, kCntRoleB, kCntRoleP,
+       kCntAux0, kCntAux1, kCntAux2, kCntAux3, kNumCounters = 16 };
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, long long& acc) {
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
                                          uint64_t* bar) {
   asm volatile(
