@@ -52,4 +52,8 @@ using namespace spotv2;
 
 extern "C" const char* spotv2_last_error(void) { return g_err; }
 extern "C" int32_t spotv2_abi_version(void) { return SPOTV2_ABI_VERSION; }
-extern "C" int32_t spotv2_gat_ldp(int32_t H, int32_t C) { return (H * C + 2 * H + 3) / 4 * 4; }
+// >= 32 floats so one P_aug row always spans a full 128-byte TMA tile row
+extern "C" int32_t spotv2_gat_ldp(int32_t H, int32_t C) {
+  const int32_t w = (H * C + 2 * H + 3) / 4 * 4;
+  return w < 32 ? 32 : w;
+}

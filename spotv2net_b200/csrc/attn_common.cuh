@@ -114,6 +114,7 @@ __device__ __forceinline__ void warp_edge_logits(const float* Ts, const float4* 
       for (int q = 0; q < 4; ++q) acc[nt][ch][q] = 0.f;
   const float* r0 = Ts + (size_t)(m0 + g) * Fe;
   const float* r1 = r0 + (size_t)8 * Fe;
+#pragma unroll 2
   for (int ks0 = 0; ks0 < KS; ks0 += 2) {
 #pragma unroll
     for (int par = 0; par < 2; ++par) {
@@ -197,34 +198,45 @@ __device__ __forceinline__ void edge_logit_phase(EdgeRing& ring, const AttnParam
 // tile[h][j][i] <- alpha * out_scale ; optional raw alpha to global ; optional z>0 mask bits.
 __device__ __forceinline__ void softmax_phase(const AttnParams& p, const AttnSmem& sm, float* tile,
                                               const float* sd, float out_scale, float* alpha_out_b,
-                                              uint32_t* pos_mask, int tid, int nthreads = kAttnThreads) {
+                                              uint32_t* pos_mask, int tid, int nthreads = kAttnThreads,
+                                              int sd_j_stride = -1, int sd_swizzled = 0) {
   const int N = p.N, H = p.H, NS = sm.NS;
+  // s_j = sd(j, h), d_i = sd(i, H + h).  sd is either a packed [N][2H] array or (sd_swizzled) a
+  // 128B-swizzled TMA tile of 32 rows x 32 floats holding the 2H augmented columns of P_aug.
+  auto sd_at = [&](int j, int k) -> float {
+    if (sd_swizzled) return sd[j * 32 + ((((k >> 2) ^ (j & 7)) << 2) | (k & 3))];
+    return sd[j * (sd_j_stride < 0 ? 2 * H : sd_j_stride) + k];
+  };
   for (int idx = tid; idx < H * N; idx += nthreads) {
     const int h = idx / N, i = idx - h * N;
     float* col = tile + (size_t)h * N * NS + i;
     float gsum = 0.f;
-    for (int j = 0; j < N; ++j)
-      if (j != i) gsum += col[j * NS];
+#pragma unroll 6
+    for (int j = 0; j < N; ++j) gsum += (j != i) ? col[j * NS] : 0.f;
     const float gii = gsum / (float)(N > 1 ? N - 1 : 1);
-    const float di = sd[i * 2 * H + H + h];
+    const float di = sd_at(i, H + h);
     float mx = -INFINITY;
     uint32_t mask = 0;
+#pragma unroll 6
     for (int j = 0; j < N; ++j) {
-      const float z = (j == i ? gii : col[j * NS]) + sd[j * 2 * H + h] + di;
+      const float z = (j == i ? gii : col[j * NS]) + sd_at(j, h) + di;
       if (z > 0.f) mask |= 1u << j;
       const float l = z > 0.f ? z : z * p.slope;
       mx = fmaxf(mx, l);
       col[j * NS] = l;
     }
     float sum = 0.f;
+#pragma unroll 6
     for (int j = 0; j < N; ++j) {
       const float e = expf(col[j * NS] - mx);
       sum += e;
       col[j * NS] = e;
     }
-    sum += 1e-16f;
+    // PyG divides by (sum + 1e-16); one reciprocal + multiplies differ from that by <= 1 ulp
+    const float inv = 1.f / (sum + 1e-16f);
+#pragma unroll 6
     for (int j = 0; j < N; ++j) {
-      const float a = col[j * NS] / sum;
+      const float a = col[j * NS] * inv;
       if (alpha_out_b) alpha_out_b[((size_t)h * N + j) * N + i] = a;
       col[j * NS] = a * out_scale;
     }

@@ -7,15 +7,16 @@
 //
 //   group A (warps 0-2)   for graph b+1: edge rows stream through a 2-stage shared-memory ring
 //                         (cp.async.bulk + mbarrier, issued two chunks ahead, across graph boundaries);
-//                         g[e,h] = <edge_attr[e], v_h> on mma.sync m16n8k8 with a 3xTF32 split;
-//                         self-loop mean fill, s_j + d_i + g_ij, LeakyReLU, softmax over sources
-//                         -> attention tile[buf] in shared memory (double buffered).
-//   group B (warps 3-10)  for graph b: O_h[32 x C] = alpha_h[32 x 32] . P_h[32 x C] on mma.sync m16n8k8
+//                         g[e,h] = <edge_attr[e], v_h> on mma.sync m16n8k8 with a 3xTF32 split, scattered
+//                         by the row table into tile[buf] (double buffered).
+//   group B (warps 3-10)  for graph b: self-loop mean fill, s_j + d_i + g_ij, LeakyReLU, softmax over
+//                         sources (one (head,target) row per thread, in place); then O_h[32 x C] = alpha_h[32 x 32] . P_h[32 x C] on mma.sync m16n8k8
 //                         (3xTF32, fp32-accurate).  P arrives as TMA tiles of 32 source rows x 32 channels
 //                         (128B-swizzled, conflict-free fragment reads); a warp owns two channel blocks and
 //                         keeps the alpha fragments of the current head in registers.  Per-head accumulators
 //                         are folded into the running sum with round-to-nearest adds.
-//   warp 11               TMA producer for the P tiles (16-slot ring), running ahead across graphs.
+//   warp 11               TMA producer: per graph one tile holding the s|d columns of P_aug, then the P
+//                         tiles (16-slot ring), running ahead across graphs.
 //
 // Why tensor cores here: with CUDA-core FFMA2 every lane needs the whole alpha row in registers, and the
 // shared-memory return path (512 B per LDS.128 per warp) bounded that version at 38 % of HBM peak
@@ -44,6 +45,7 @@ struct AttnFwdArgs {
 };
 
 __device__ __forceinline__ void bar_sync_group_a() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_group_b() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -66,6 +68,9 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
   uint64_t* tile_empty = bars + 4;
   uint64_t* ptile_full = bars + 6;
   uint64_t* ptile_empty = bars + 6 + kPSlots;
+  uint64_t* sd_full = bars + 6 + 2 * kPSlots;          // [2] s|d tile landed
+  uint64_t* sd_empty = sd_full + 2;                     // [2] s|d tile consumed
+  const uint32_t off_sdtile = off_ptile + kPSlots * kPTileBytes;
   const int n_cb = (C + 31) / 32;                                   // 32-channel blocks per head
   const int n_pass = (n_cb + kCbPerPass - 1) / kCbPerPass;
   int32_t* table_s = reinterpret_cast<int32_t*>(smem_raw + sm.off_table);
@@ -84,6 +89,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
     mbar_init(&tile_empty[0], kGroupB);
     mbar_init(&tile_empty[1], kGroupB);
     for (int r = 0; r < kPSlots; ++r) { mbar_init(&ptile_full[r], 1); mbar_init(&ptile_empty[r], 1); }
+    for (int r = 0; r < 2; ++r) { mbar_init(&sd_full[r], 1); mbar_init(&sd_empty[r], 1); }
     fence_mbar_init();
   }
   for (int r = tid; r < p.R; r += kFwdThreads) table_s[r] = p.Fe > 0 ? p.table[r] : -1;
@@ -109,7 +115,6 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
       if (total_chunks > 0) issue(0);
       if (total_chunks > 1) issue(1);
     }
-    const float out_scale = p.concat ? 1.f : 1.f / (float)H;
     int k = 0;                                          // global chunk counter (stage = k & 1, parity = (k >> 1) & 1)
     long long w_ring = 0, w_tile = 0;
     const long long t_role = clock64();
@@ -117,12 +122,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
       const int b = blockIdx.x + it * gridDim.x;
       const int buf = it & 1;
       float* tile = tile0 + buf * tile_floats;
-      float* sd = sd0 + buf * sd_floats;
       mbar_wait_timed(&tile_empty[buf], ((it >> 1) & 1) ^ 1, w_tile);   // group B has finished reading this buffer
-      for (int idx = tid; idx < sd_floats; idx += kGroupA) {
-        const int j = idx / (2 * H), kk = idx - j * 2 * H;
-        sd[idx] = p.P_aug[((size_t)b * N + j) * p.ldp + HC + kk];
-      }
       if (nchunks == 0) {
         for (int idx = tid; idx < tile_floats; idx += kGroupA) tile[idx] = 0.f;
       }
@@ -148,10 +148,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
         bar_sync_group_a();                              // stage s consumed by all four warps
         if (p.bulk_ok && tid == 0 && k + 2 < total_chunks) issue(k + 2);
       }
-      if (nchunks == 0) bar_sync_group_a();
-      softmax_phase(p, sm, tile, sd, out_scale, args.alpha_out ? args.alpha_out + (size_t)b * H * N * N : nullptr,
-                    nullptr, tid, kGroupA);
-      mbar_arrive_cta(&tile_full[buf]);                  // release: alpha tile visible to group B
+      mbar_arrive_cta(&tile_full[buf]);                  // release: edge terms of this graph visible to group B
     }
     if (tid == 0) {
       atomicAdd(&g_diag_counters[kCntRingFull], (unsigned long long)w_ring);
@@ -166,11 +163,18 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
     uint32_t q_base = 0;                                   // tiles issued before the current (pass, head) group
     long long w_tf = 0, w_pf = 0;
     const long long t_role = clock64();
+    const float out_scale = p.concat ? 1.f : 1.f / (float)H;
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
       const int buf = it & 1;
-      const float* tile = tile0 + buf * tile_floats;
+      float* tile = tile0 + buf * tile_floats;
       mbar_wait_timed(&tile_full[buf], (it >> 1) & 1, w_tf);
+      mbar_wait_timed(&sd_full[buf], (it >> 1) & 1, w_tf);
+      softmax_phase(p, sm, tile, reinterpret_cast<const float*>(smem_raw + off_sdtile + buf * kPTileBytes), out_scale,
+                    args.alpha_out ? args.alpha_out + (size_t)b * H * N * N : nullptr, nullptr, tid - kGroupA, kGroupB,
+                    -1, /*sd_swizzled=*/1);
+      bar_sync_group_b();                                // alpha tile complete
+      if (tid == kGroupA) mbar_arrive_cta(&sd_empty[buf]);
       for (int pass = 0; pass < n_pass; ++pass) {
         const int G = min(kCbPerPass, n_cb - pass * kCbPerPass);     // valid channel blocks in this pass
         float acc[2][2][4][4];                             // [cb slot][m-tile][n-tile][frag]
@@ -315,6 +319,12 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
     const long long t_role = clock64();
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
+      {                                                  // the s|d columns [HC, HC + 2H) of this graph's rows
+        const int sb = it & 1;
+        mbar_wait_timed(&sd_empty[sb], ((it >> 1) & 1) ^ 1, w_pe);
+        mbar_expect_tx(&sd_full[sb], kPTileBytes);
+        tma_load_2d(smem_raw + off_sdtile + sb * kPTileBytes, &tmP, HC, b * N, &sd_full[sb]);
+      }
       for (int pass = 0; pass < n_pass; ++pass) {
         const int G = min(kCbPerPass, n_cb - pass * kCbPerPass);
         for (int h = 0; h < H; ++h) {
@@ -348,7 +358,7 @@ static int launch_fwd(const AttnFwdArgs& a, cudaStream_t st) {
     return s;
   };
   auto ptile_off = [&](const AttnSmem& s) { return round_up(s.off_ring + 2 * s.ring_stage_bytes, 1024); };
-  auto total = [&](const AttnSmem& s) { return ptile_off(s) + (size_t)kPSlots * kPTileBytes; };
+  auto total = [&](const AttnSmem& s) { return ptile_off(s) + (size_t)(kPSlots + 2) * kPTileBytes; };
   AttnSmem sm = finish(attn_smem_plan(p.N, p.Fe, p.H, p.R, NPAIRS, kFwdChunkRows3));
   for (int rows = kFwdChunkRows3 - 16; rows >= 16 && total(sm) > 227 * 1024; rows -= 16)
     sm = finish(attn_smem_plan(p.N, p.Fe, p.H, p.R, NPAIRS, rows));

@@ -91,24 +91,28 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                "r"(bytes)
                : "memory");
 }
-// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the
-// hint (ns) elapses, so a waiting warp costs almost no issue slots.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a lost transaction traps (after ~4 s of parked waits) instead of hanging the GPU box.
+// Bounded wait.  try_wait parks the thread for a short hardware-defined interval; after a few misses we
+// back off with short sleeps so parked warps do not eat issue slots (a suspend-time HINT compiles to a
+// 200 us NANOSLEEP and serialises the pipeline - measured).  A lost transaction traps after ~2 s
+// instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t tries = 0;
+  for (int spin = 0; spin < 16; ++spin)
+    if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++tries > 20000u) __trap();
+    __nanosleep(64);
+    if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
 // Diagnostics: cycles spent parked on each class of barrier (one sampling thread per role adds its

@@ -41,7 +41,7 @@ def test_descriptor_layout_matches_header():
 
 def test_ldp_query_and_argument_validation_without_a_gpu():
     lib = spotv2net_b200.load_library()
-    assert lib.spotv2_gat_ldp(6, 500) == 3012 and lib.spotv2_gat_ldp(8, 256) == 2064 and lib.spotv2_gat_ldp(1, 1) == 4
+    assert lib.spotv2_gat_ldp(6, 500) == 3012 and lib.spotv2_gat_ldp(8, 256) == 2064 and lib.spotv2_gat_ldp(1, 1) == 32
     bad = _lib.GatDesc(0, 30, 1260, 126, 6, 500, 870, 0, 0.2, 3012, 0, 0)
     a = ctypes.c_size_t()
     rc = lib.spotv2_gat_workspace_bytes(ctypes.byref(bad), ctypes.byref(a), None, None)
