@@ -172,9 +172,11 @@ int spotv2_diag_gemm(int a_kc, int b_kc, int M, int N, int K, const float* A, in
                      int ldb, float* C, int ldc, int algo, int splits, int bn, int kb_per_chunk,
                      void* ws, size_t ws_bytes, void* stream);
 
-/* Copies (and optionally resets) the 16 device-side wait-cycle counters the pipelined attention kernels
- * accumulate (cycles parked on: edge ring, alpha-tile empty/full, P-tile full/empty, then per-role loop
- * totals).  Host pointer; synchronises the device.  Profiling aid only. */
+/* Copies (and optionally resets) 32 device-side cycle counters.  [0,16): forward kernel, cycles one
+ * sampling thread per role spent parked on the edge ring, alpha-tile empty/full, P-tile full/empty, then
+ * per-role loop totals.  [16,32): backward kernel, cycles per phase (logits, softmax, dalpha GEMM,
+ * softmax backward, dP, dv) summed over CTAs.  host_out: 32 x uint64 on the host; synchronises the device.
+ * Profiling aid only. */
 int spotv2_diag_counters(unsigned long long* host_out, int reset);
 
 #ifdef __cplusplus

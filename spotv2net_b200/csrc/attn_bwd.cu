@@ -22,6 +22,9 @@ constexpr int kCKP = 20;       // padded row stride (floats): 80 B, conflict-fre
 constexpr int kTI = 5;         // register tile: targets
 constexpr int kTJ = 5;         // register tile: sources
 
+// phase-time diagnostics (thread 0 of every CTA; see spotv2_diag_counters, entries 16..31)
+__device__ unsigned long long g_bwd_counters[kNumCounters];
+
 struct AttnBwdArgs {
   AttnParams p;
   const float* dout;
@@ -183,6 +186,9 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) dv_run[m][q] = 0.f;
 
+  long long ph[6] = {0, 0, 0, 0, 0, 0};
+  long long t_ph = clock64();
+  auto lap = [&](int k) { const long long now = clock64(); ph[k] += now - t_ph; t_ph = now; };
   for (; b < p.B; b += gridDim.x) {
     // ---- B1: recompute alpha --------------------------------------------------------------
     for (int idx = tid; idx < N * 2 * H; idx += kAttnThreads) {
@@ -195,7 +201,9 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
       for (int idx = tid; idx < H * N * NS; idx += kAttnThreads) tile[idx] = 0.f;
       __syncthreads();
     }
+    lap(0);
     softmax_phase(p, sm.a, tile, sd, 1.f, nullptr, pos_mask, tid);
+    lap(1);
     // (no barrier needed before B2's loads: they write the union region, idle since B1's last barrier;
     //  D is written only after the chunk loop's barriers)
 
@@ -296,6 +304,7 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
       }
     }
     __syncthreads();
+    lap(2);
     // staging is idle from here: start the second pass over the edge rows under B2b/B3
     if (p.bulk_ok && tid == 0 && ring.nchunks > 0) ring.prefetch_first(b);
 
@@ -337,6 +346,7 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
     }
     // (D is next read in B4, after B3's trailing barrier)
 
+    lap(3);
     // ---- B3: dP = alpha^T dO ------------------------------------------------------------------
     for (int item = tid; item < n_items; item += kAttnThreads) {
       const int h0 = p.concat ? item / CP : 0;
@@ -411,6 +421,7 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
     }
     __syncthreads();
 
+    lap(4);
     // ---- B4: dv += dz'^T . edge rows -------------------------------------------------------------
     for (int c = 0; c < ring.nchunks; ++c) {
       const int s = c & 1;
@@ -427,60 +438,79 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
         const float* Ts = ring.stage[s];
         const int row_base = c * ring.chunk_rows;
         const int g8 = lane_id >> 2, t4 = lane_id & 3;
-        float acc[kMT][4];
+        // mma.sync latency on sm_100 is ~300 cycles: give every k-step slot and product its own
+        // accumulator (kDvSlots x 3 independent chains per m-tile) and sum them after the chunk.
+        constexpr int kDvSlots = 3;
 #pragma unroll
-        for (int m = 0; m < kMT; ++m)
+        for (int m = 0; m < kMT; ++m) {
+          const int mt = warp_id + m * (kAttnThreads / 32);
+          if (mt >= n_mtiles) continue;                    // warp-uniform
+          const int f0 = mt * 16 + g8, f1 = f0 + 8;
+          float acc[kDvSlots][3][4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) acc[m][q] = 0.f;
-        for (int r0 = 0; r0 < rows; r0 += 8) {
-          // B fragment (k = edge row, n = head): b0 = dz'[r0+t][g], b1 = dz'[r0+t+4][g]
-          float bv[2];
+          for (int sl = 0; sl < kDvSlots; ++sl)
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int r = r0 + t4 + 4 * half;
-            float val = 0.f;
-            if (r < rows && g8 < H) {
-              const int code = table_s[row_base + r];
-              if (code >= 0) val = D[(g8 * N + (code & 0xffff)) * NS + (code >> 16)];
+            for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc[sl][pr][q] = 0.f;
+          for (int rb = 0; rb < rows; rb += 8 * kDvSlots) {
+#pragma unroll
+            for (int sl = 0; sl < kDvSlots; ++sl) {
+              const int r0 = rb + 8 * sl;
+              if (r0 < rows) {
+                // B fragment (k = edge row, n = head): b0 = dz'[r0+t][g], b1 = dz'[r0+t+4][g]
+                float bv[2];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                  const int r = r0 + t4 + 4 * half;
+                  float val = 0.f;
+                  if (r < rows && g8 < H) {
+                    const int code = table_s[row_base + r];
+                    if (code >= 0) val = D[(g8 * N + (code & 0xffff)) * NS + (code >> 16)];
+                  }
+                  bv[half] = val;
+                }
+                uint32_t bh[2], bl[2];
+                split_tf32_trunc(bv[0], bh[0], bl[0]);
+                split_tf32_trunc(bv[1], bh[1], bl[1]);
+                const bool k0_ok = r0 + t4 < rows, k1_ok = r0 + t4 + 4 < rows;
+                const float* t0p = Ts + (size_t)(r0 + t4) * Fe;
+                const float* t1p = t0p + (size_t)4 * Fe;
+                float a[4];
+                a[0] = (k0_ok && f0 < Fe) ? t0p[f0] : 0.f;     // (m = g,   k = t)
+                a[1] = (k0_ok && f1 < Fe) ? t0p[f1] : 0.f;     // (m = g+8, k = t)
+                a[2] = (k1_ok && f0 < Fe) ? t1p[f0] : 0.f;     // (m = g,   k = t+4)
+                a[3] = (k1_ok && f1 < Fe) ? t1p[f1] : 0.f;     // (m = g+8, k = t+4)
+                uint32_t ah[4], al[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) split_tf32_trunc(a[q], ah[q], al[q]);
+                mma_tf32_16x8x8(acc[sl][0], al, bh);
+                mma_tf32_16x8x8(acc[sl][1], ah, bl);
+                mma_tf32_16x8x8(acc[sl][2], ah, bh);
+              }
             }
-            bv[half] = val;
           }
-          uint32_t bh[2], bl[2];
-          split_tf32_trunc(bv[0], bh[0], bl[0]);
-          split_tf32_trunc(bv[1], bh[1], bl[1]);
-          const bool k0_ok = r0 + t4 < rows, k1_ok = r0 + t4 + 4 < rows;
-          const float* t0p = Ts + (size_t)(r0 + t4) * Fe;
-          const float* t1p = t0p + (size_t)4 * Fe;
 #pragma unroll
-          for (int m = 0; m < kMT; ++m) {
-            const int mt = warp_id + m * (kAttnThreads / 32);
-            if (mt < n_mtiles) {
-              const int f0 = mt * 16 + g8, f1 = f0 + 8;
-              float a[4];
-              a[0] = (k0_ok && f0 < Fe) ? t0p[f0] : 0.f;     // (m = g,   k = t)
-              a[1] = (k0_ok && f1 < Fe) ? t0p[f1] : 0.f;     // (m = g+8, k = t)
-              a[2] = (k1_ok && f0 < Fe) ? t1p[f0] : 0.f;     // (m = g,   k = t+4)
-              a[3] = (k1_ok && f1 < Fe) ? t1p[f1] : 0.f;     // (m = g+8, k = t+4)
-              uint32_t ah[4], al[4];
+          for (int q = 0; q < 4; ++q) {
+            float corr = 0.f, mainp = 0.f;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) split_tf32_trunc(a[q], ah[q], al[q]);
-              mma_tf32_16x8x8(acc[m], al, bh);
-              mma_tf32_16x8x8(acc[m], ah, bl);
-              mma_tf32_16x8x8(acc[m], ah, bh);
+            for (int sl = 0; sl < kDvSlots; ++sl) {
+              corr += acc[sl][0][q] + acc[sl][1][q];
+              mainp += acc[sl][2][q];
             }
+            dv_run[m][q] += corr + mainp;
           }
         }
-#pragma unroll
-        for (int m = 0; m < kMT; ++m)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) dv_run[m][q] += acc[m][q];
       }
       __syncthreads();
       if (p.bulk_ok && tid == 0 && c + 2 < ring.nchunks) ring.issue(b, c + 2);
     }
     if (p.bulk_ok && tid == 0 && b + (int)gridDim.x < p.B && ring.nchunks > 0)
       ring.prefetch_first(b + gridDim.x);
+    lap(5);
   }
+  if (tid == 0)
+    for (int k = 0; k < 6; ++k) atomicAdd(&g_bwd_counters[k], (unsigned long long)ph[k]);
 
   // ---- per-CTA partials ---------------------------------------------------------------------------
   // A CTA that issued a prefetch always consumes it (the prefetch is only issued for graphs it owns),
@@ -543,6 +573,17 @@ static int launch_bwd(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t 
   return SPOTV2_OK;
 }
 
+}  // namespace spotv2
+
+namespace spotv2 {
+int bwd_diag_read(unsigned long long* host_out, int reset) {
+  SPOTV2_CUDA_OK(cudaMemcpyFromSymbol(host_out, g_bwd_counters, sizeof(unsigned long long) * kNumCounters));
+  if (reset) {
+    unsigned long long zeros[kNumCounters] = {0};
+    SPOTV2_CUDA_OK(cudaMemcpyToSymbol(g_bwd_counters, zeros, sizeof(zeros)));
+  }
+  return SPOTV2_OK;
+}
 }  // namespace spotv2
 
 using namespace spotv2;

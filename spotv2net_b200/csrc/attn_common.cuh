@@ -99,26 +99,28 @@ __device__ __forceinline__ void build_vfrag(float4* vfrag, const float* v, int H
 // One warp: edge terms g[row, h] = <edge_row, v_h> for the 16 rows [m0, m0+16) of a staged chunk,
 // fp32-accurate through the 3xTF32 split (lo*hi + hi*lo + hi*hi, small terms first).
 // Results go to sink(row_in_chunk, head, value) for the rows/heads this lane owns.
-template <int NT_MAX, class Sink>
+template <int NT_MAX, int kSlots, class Sink>
 __device__ __forceinline__ void warp_edge_logits(const float* Ts, const float4* vfrag, int Fe, int KS,
                                                  int NT, int m0, int lane, Sink&& sink) {
   const int g = lane >> 2, t = lane & 3;
-  // Four independent accumulation chains per n-tile (even/odd k-step x {hi*hi, cross terms}) so the
-  // HMMAs are not serialised on one accumulator's latency; summed small-terms-first at the end.
-  float acc[NT_MAX][4][4];
+  // mma.sync on sm_100 has a very long latency (~300 cycles measured through the pipeline stalls), so the
+  // 3*KS MMAs of a row tile are spread over kSlots x 3 independent accumulators (k-step mod kSlots, one per
+  // product) instead of one chain; they are summed small-terms-first at the end.
+  float acc[NT_MAX][kSlots][3][4];
 #pragma unroll
   for (int nt = 0; nt < NT_MAX; ++nt)
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch)
+    for (int sl = 0; sl < kSlots; ++sl)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[nt][ch][q] = 0.f;
+      for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[nt][sl][pr][q] = 0.f;
   const float* r0 = Ts + (size_t)(m0 + g) * Fe;
   const float* r1 = r0 + (size_t)8 * Fe;
-#pragma unroll 2
-  for (int ks0 = 0; ks0 < KS; ks0 += 2) {
+  for (int ks0 = 0; ks0 < KS; ks0 += kSlots) {
 #pragma unroll
-    for (int par = 0; par < 2; ++par) {
-      const int ks = ks0 + par;
+    for (int sl = 0; sl < kSlots; ++sl) {
+      const int ks = ks0 + sl;
       if (ks < KS) {
         const int k0 = ks * 8 + t, k1 = k0 + 4;
         float a[4];
@@ -135,9 +137,9 @@ __device__ __forceinline__ void warp_edge_logits(const float* Ts, const float4* 
             const float4 bf = vfrag[(nt * KS + ks) * 32 + lane];
             const uint32_t bh[2] = {__float_as_uint(bf.x), __float_as_uint(bf.y)};
             const uint32_t bl[2] = {__float_as_uint(bf.z), __float_as_uint(bf.w)};
-            mma_tf32_16x8x8(acc[nt][2 * par + 1], al, bh);
-            mma_tf32_16x8x8(acc[nt][2 * par + 1], ah, bl);
-            mma_tf32_16x8x8(acc[nt][2 * par], ah, bh);
+            mma_tf32_16x8x8(acc[nt][sl][0], al, bh);
+            mma_tf32_16x8x8(acc[nt][sl][1], ah, bl);
+            mma_tf32_16x8x8(acc[nt][sl][2], ah, bh);
           }
         }
       }
@@ -148,7 +150,15 @@ __device__ __forceinline__ void warp_edge_logits(const float* Ts, const float4* 
     if (nt < NT) {
       float c[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) c[q] = (acc[nt][1][q] + acc[nt][3][q]) + (acc[nt][0][q] + acc[nt][2][q]);
+      for (int q = 0; q < 4; ++q) {
+        float corr = 0.f, mainp = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < kSlots; ++sl) {
+          corr += acc[nt][sl][0][q] + acc[nt][sl][1][q];
+          mainp += acc[nt][sl][2][q];
+        }
+        c[q] = corr + mainp;
+      }
       const int n = nt * 8 + 2 * t;
       sink(m0 + g, n, c[0]);
       sink(m0 + g, n + 1, c[1]);
@@ -179,7 +189,7 @@ __device__ __forceinline__ void edge_logit_phase(EdgeRing& ring, const AttnParam
     }
     if (warp * 16 < rows) {
       const int row_base = c * ring.chunk_rows;
-      warp_edge_logits<1>(ring.stage[s], vfrag, p.Fe, sm.KS, sm.NT, warp * 16, lane,
+      warp_edge_logits<1, 4>(ring.stage[s], vfrag, p.Fe, sm.KS, sm.NT, warp * 16, lane,
                           [&](int r, int h, float val) {
                             if (r < rows && h < H) {
                               const int code = table_s[row_base + r];

@@ -32,7 +32,7 @@ constexpr int kFwdThreads = kGroupA + kGroupB + 32;
 constexpr int kFwdChunkRows3 = 48;    // edge rows per ring stage: one m16 tile per group-A warp
 constexpr int kPSlots = 16;           // P-tile ring depth
 constexpr int kPTileBytes = 32 * 128; // 32 source rows x 32 channels fp32, 128B-swizzled
-constexpr int kCbPerPass = 16;        // channel blocks per pass: two per MMA warp
+constexpr int kCbPerPass = 8;         // channel blocks per pass: one per MMA warp
 
 // wait-cycle diagnostics of this kernel (see spotv2_diag_counters)
 __device__ unsigned long long g_diag_counters[kNumCounters];
@@ -138,7 +138,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
         }
         if (warp * 16 < rows) {
           const int row_base = c * sm.chunk_rows;
-          warp_edge_logits<1>(stage[s], vfrag, p.Fe, sm.KS, sm.NT, warp * 16, lane, [&](int r, int h, float val) {
+          warp_edge_logits<1, 8>(stage[s], vfrag, p.Fe, sm.KS, sm.NT, warp * 16, lane, [&](int r, int h, float val) {
             if (r < rows && h < H) {
               const int code = table_s[row_base + r];
               if (code >= 0) tile[(h * N + (code & 0xffff)) * NS + (code >> 16)] = val;
@@ -177,17 +177,45 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
       if (tid == kGroupA) mbar_arrive_cta(&sd_empty[buf]);
       for (int pass = 0; pass < n_pass; ++pass) {
         const int G = min(kCbPerPass, n_cb - pass * kCbPerPass);     // valid channel blocks in this pass
-        float acc[2][2][4][4];                             // [cb slot][m-tile][n-tile][frag]
-#pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2)
+        const bool mine = wb < G;                          // this warp's channel block: pass * 8 + wb
+        const int cb = pass * kCbPerPass + wb;
+        // Two accumulator sets (hi*hi products / cross terms) so that consecutive MMAs never wait on each
+        // other's ~300-cycle latency; in mean mode they run across all heads (alpha carries the 1/H).
+        float cmain[2][4][4], ccorr[2][4][4];
+        auto clear = [&]() {
 #pragma unroll
           for (int m = 0; m < 2; ++m)
 #pragma unroll
             for (int n = 0; n < 4; ++n)
 #pragma unroll
-              for (int e = 0; e < 4; ++e) acc[s2][m][n][e] = 0.f;
+              for (int e = 0; e < 4; ++e) cmain[m][n][e] = ccorr[m][n][e] = 0.f;
+        };
+        auto store = [&](int col0) {                       // out[i, col0 + c] = cmain + ccorr + bias
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                const int i = m * 16 + g + 8 * hf, c = cb * 32 + n * 8 + 2 * t;
+                if (i < N && c < C) {
+                  const int col = col0 + c;
+                  float* dst = args.out + ((size_t)b * N + i) * p.ldo + col;
+                  const float o0 = cmain[m][n][2 * hf] + ccorr[m][n][2 * hf] + (args.bias ? args.bias[col] : 0.f);
+                  if (c + 1 < C) {
+                    const float o1 = cmain[m][n][2 * hf + 1] + ccorr[m][n][2 * hf + 1] + (args.bias ? args.bias[col + 1] : 0.f);
+                    if (VEC2) *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
+                    else { dst[0] = o0; dst[1] = o1; }
+                  } else {
+                    dst[0] = o0;
+                  }
+                }
+              }
+        };
+        clear();
         for (int h = 0; h < H; ++h, q_base += G) {
-          // A fragments of alpha_h (rows = targets i, cols = sources j), split once per head
+          if (!mine) continue;
+          // A fragments of alpha_h (rows = targets i, cols = sources j), split once per (pass, head)
           uint32_t ah[2][4][4], al[2][4][4];
 #pragma unroll
           for (int m = 0; m < 2; ++m)
@@ -204,105 +232,37 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
               split_tf32_trunc(a2, ah[m][ks][2], al[m][ks][2]);
               split_tf32_trunc(a3, ah[m][ks][3], al[m][ks][3]);
             }
+          const uint32_t q = q_base + wb;
+          const int slot = q % kPSlots;
+          mbar_wait_timed(&ptile_full[slot], (q / kPSlots) & 1, w_pf);
+          const unsigned char* pt = ptiles + (size_t)slot * kPTileBytes;
 #pragma unroll
-          for (int s2 = 0; s2 < 2; ++s2) {
-            const int k = wb + 8 * s2;                      // this warp's channel block within the pass
-            if (k < G) {
-              const uint32_t q = q_base + k;
-              const int slot = q % kPSlots;
-              mbar_wait_timed(&ptile_full[slot], (q / kPSlots) & 1, w_pf);
-              const unsigned char* pt = ptiles + (size_t)slot * kPTileBytes;
-              float hacc[2][4][4];                         // this head's contribution (short MMA chains)
+          for (int ks = 0; ks < 4; ++ks) {
+            const int r0 = ks * 8 + t, r1 = r0 + 4;         // source rows of b0 / b1
 #pragma unroll
-              for (int m = 0; m < 2; ++m)
+            for (int n = 0; n < 4; ++n) {
+              const int c = n * 8 + g;                      // channel within the block
+              const float b0 = *reinterpret_cast<const float*>(pt + r0 * 128 + ((((c >> 2) ^ (r0 & 7)) << 4) | ((c & 3) << 2)));
+              const float b1 = *reinterpret_cast<const float*>(pt + r1 * 128 + ((((c >> 2) ^ (r1 & 7)) << 4) | ((c & 3) << 2)));
+              uint32_t bh[2], bl[2];
+              split_tf32_trunc(b0, bh[0], bl[0]);
+              split_tf32_trunc(b1, bh[1], bl[1]);
 #pragma unroll
-                for (int n = 0; n < 4; ++n)
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) hacc[m][n][e] = 0.f;
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const int r0 = ks * 8 + t, r1 = r0 + 4;     // source rows of b0 / b1
-#pragma unroll
-                for (int n = 0; n < 4; ++n) {
-                  const int c = n * 8 + g;                  // channel within the block
-                  const float b0 = *reinterpret_cast<const float*>(pt + r0 * 128 + ((((c >> 2) ^ (r0 & 7)) << 4) | ((c & 3) << 2)));
-                  const float b1 = *reinterpret_cast<const float*>(pt + r1 * 128 + ((((c >> 2) ^ (r1 & 7)) << 4) | ((c & 3) << 2)));
-                  uint32_t bh[2], bl[2];
-                  split_tf32_trunc(b0, bh[0], bl[0]);
-                  split_tf32_trunc(b1, bh[1], bl[1]);
-#pragma unroll
-                  for (int m = 0; m < 2; ++m) {
-                    mma_tf32_16x8x8(hacc[m][n], al[m][ks], bh);
-                    mma_tf32_16x8x8(hacc[m][n], ah[m][ks], bl);
-                    mma_tf32_16x8x8(hacc[m][n], ah[m][ks], bh);
-                  }
-                }
-              }
-              __syncwarp();
-              if (lane == 0) mbar_arrive_cta(&ptile_empty[slot]);    // tile consumed
-              if (p.concat) {
-                // ---- concat: every head is its own output block
-                const int cb = pass * kCbPerPass + k;
-#pragma unroll
-                for (int m = 0; m < 2; ++m)
-#pragma unroll
-                  for (int n = 0; n < 4; ++n)
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                      const int i = m * 16 + g + 8 * hf, c = cb * 32 + n * 8 + 2 * t;
-                      if (i < N && c < C) {
-                        const int col = h * C + c;
-                        float* dst = args.out + ((size_t)b * N + i) * p.ldo + col;
-                        const float o0 = hacc[m][n][2 * hf] + (args.bias ? args.bias[col] : 0.f);
-                        if (c + 1 < C) {
-                          const float o1 = hacc[m][n][2 * hf + 1] + (args.bias ? args.bias[col + 1] : 0.f);
-                          if (VEC2) *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
-                          else { dst[0] = o0; dst[1] = o1; }
-                        } else {
-                          dst[0] = o0;
-                        }
-                      }
-                    }
-              } else {
-#pragma unroll
-                for (int m = 0; m < 2; ++m)
-#pragma unroll
-                  for (int n = 0; n < 4; ++n)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) acc[s2][m][n][e] += hacc[m][n][e];
+              for (int m = 0; m < 2; ++m) {
+                mma_tf32_16x8x8(ccorr[m][n], al[m][ks], bh);
+                mma_tf32_16x8x8(cmain[m][n], ah[m][ks], bh);
+                mma_tf32_16x8x8(ccorr[m][n], ah[m][ks], bl);
               }
             }
           }
-        }
-        if (!p.concat) {
-          // ---- head mean (alpha was pre-scaled by 1/H) + bias
-#pragma unroll
-          for (int s2 = 0; s2 < 2; ++s2) {
-            const int k = wb + 8 * s2;
-            if (k < G) {
-              const int cb = pass * kCbPerPass + k;
-#pragma unroll
-              for (int m = 0; m < 2; ++m)
-#pragma unroll
-                for (int n = 0; n < 4; ++n)
-#pragma unroll
-                  for (int hf = 0; hf < 2; ++hf) {
-                    const int i = m * 16 + g + 8 * hf, c = cb * 32 + n * 8 + 2 * t;
-                    if (i < N && c < C) {
-                      float* dst = args.out + ((size_t)b * N + i) * p.ldo + c;
-                      const float o0 = acc[s2][m][n][2 * hf] + (args.bias ? args.bias[c] : 0.f);
-                      if (c + 1 < C) {
-                        const float o1 = acc[s2][m][n][2 * hf + 1] + (args.bias ? args.bias[c + 1] : 0.f);
-                        if (VEC2) *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
-                        else { dst[0] = o0; dst[1] = o1; }
-                      } else {
-                        dst[0] = o0;
-                      }
-                    }
-                  }
-            }
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cta(&ptile_empty[slot]);        // tile consumed
+          if (p.concat) {                                  // every head is its own output block
+            store(h * C);
+            clear();
           }
         }
+        if (!p.concat && mine) store(0);                   // head mean (alpha pre-scaled by 1/H) + bias
       }
       mbar_arrive_cta(&tile_empty[buf]);                 // this thread is done reading the alpha tile
     }
@@ -393,6 +353,7 @@ int attn_fwd_dispatch(const AttnFwdArgs& a, cudaStream_t st) {
 
 }  // namespace spotv2
 
+namespace spotv2 { int bwd_diag_read(unsigned long long* host_out, int reset); }
 using namespace spotv2;
 
 extern "C" int spotv2_diag_counters(unsigned long long* host_out, int reset) {
@@ -403,7 +364,7 @@ extern "C" int spotv2_diag_counters(unsigned long long* host_out, int reset) {
     unsigned long long zeros[kNumCounters] = {0};
     SPOTV2_CUDA_OK(cudaMemcpyToSymbol(g_diag_counters, zeros, sizeof(zeros)));
   }
-  return SPOTV2_OK;
+  return bwd_diag_read(host_out + kNumCounters, reset);      // entries 16..31: backward phase times
 }
 
 extern "C" int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug,

@@ -9,7 +9,7 @@ import spotv2net_b200 as sv
 dev = torch.device("cuda", 0)
 hp = bench.HotPath(4096, dev, 1234)
 lib = hp.lib
-buf = (C.c_ulonglong * 16)()
+buf = (C.c_ulonglong * 32)()
 for _ in range(3):
     hp.step()
 lib.spotv2_diag_counters(buf, 1)
@@ -27,3 +27,8 @@ ms = sum(a.elapsed_time(b) for e in ev for (n0, a), (n1, b) in zip(e[:-1], e[1:]
 print(f"attn_fwd {ms:.3f} ms/launch")
 for k, nm in enumerate(names):
     print(f"{nm:16s} {buf[k] / n / ctas / 1e3:10.1f} kcycles per CTA per launch")
+
+msb = sum(a.elapsed_time(b) for e in ev for (n0, a), (n1, b) in zip(e[:-1], e[1:]) if n1 == "attn_bwd") / n
+print(f"attn_bwd {msb:.3f} ms/launch (2 CTAs per SM: per-CTA phase totals)")
+for k, nm in enumerate(["B1 logits", "B1 softmax", "B2 dalpha", "B2b softmax bwd", "B3 dP", "B4 dv"]):
+    print(f"{nm:16s} {buf[16 + k] / n / 296 / 1e3:10.1f} kcycles per CTA per launch")
