@@ -101,8 +101,9 @@ __device__ __forceinline__ void build_vfrag(float4* vfrag, const float* v, int H
 // Results go to sink(row_in_chunk, head, value) for the rows/heads this lane owns.
 template <int NT_MAX, int kSlots, class Sink>
 __device__ __forceinline__ void warp_edge_logits(const float* Ts, const float4* vfrag, int Fe, int KS,
-                                                 int NT, int m0, int lane, Sink&& sink) {
+                                                 int NT, int m0, int lane, Sink&& sink, long long* t_mma = nullptr) {
   const int g = lane >> 2, t = lane & 3;
+  const long long t_begin = t_mma ? clock64() : 0;
   // mma.sync on sm_100 has a very long latency (~300 cycles measured through the pipeline stalls), so the
   // 3*KS MMAs of a row tile are spread over kSlots x 3 independent accumulators (k-step mod kSlots, one per
   // product) instead of one chain; they are summed small-terms-first at the end.
@@ -145,10 +146,11 @@ __device__ __forceinline__ void warp_edge_logits(const float* Ts, const float4* 
       }
     }
   }
+  float csum[NT_MAX][4];
 #pragma unroll
   for (int nt = 0; nt < NT_MAX; ++nt) {
     if (nt < NT) {
-      float c[4];
+      float* c = csum[nt];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float corr = 0.f, mainp = 0.f;
@@ -159,6 +161,13 @@ __device__ __forceinline__ void warp_edge_logits(const float* Ts, const float4* 
         }
         c[q] = corr + mainp;
       }
+    }
+  }
+  if (t_mma) *t_mma += clock64() - t_begin;          // includes waiting for the accumulators
+#pragma unroll
+  for (int nt = 0; nt < NT_MAX; ++nt) {
+    if (nt < NT) {
+      const float* c = csum[nt];
       const int n = nt * 8 + 2 * t;
       sink(m0 + g, n, c[0]);
       sink(m0 + g, n + 1, c[1]);

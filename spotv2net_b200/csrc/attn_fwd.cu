@@ -116,7 +116,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
       if (total_chunks > 1) issue(1);
     }
     int k = 0;                                          // global chunk counter (stage = k & 1, parity = (k >> 1) & 1)
-    long long w_ring = 0, w_tile = 0;
+    long long w_ring = 0, w_tile = 0, t_mma = 0, t_call = 0, t_bar = 0;
     const long long t_role = clock64();
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
@@ -136,6 +136,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
           for (int idx = tid; idx < rows * p.Fe; idx += kGroupA) stage[s][idx] = src[idx];
           bar_sync_group_a();
         }
+        const long long tc0 = clock64();
         if (warp * 16 < rows) {
           const int row_base = c * sm.chunk_rows;
           warp_edge_logits<1, 8>(stage[s], vfrag, p.Fe, sm.KS, sm.NT, warp * 16, lane, [&](int r, int h, float val) {
@@ -143,9 +144,12 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
               const int code = table_s[row_base + r];
               if (code >= 0) tile[(h * N + (code & 0xffff)) * NS + (code >> 16)] = val;
             }
-          });
+          }, &t_mma);
         }
-        bar_sync_group_a();                              // stage s consumed by all four warps
+        const long long tc1 = clock64();
+        bar_sync_group_a();                              // stage s consumed by all three warps
+        t_call += tc1 - tc0;
+        t_bar += clock64() - tc1;
         if (p.bulk_ok && tid == 0 && k + 2 < total_chunks) issue(k + 2);
       }
       mbar_arrive_cta(&tile_full[buf]);                  // release: edge terms of this graph visible to group B
@@ -154,6 +158,9 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
       atomicAdd(&g_diag_counters[kCntRingFull], (unsigned long long)w_ring);
       atomicAdd(&g_diag_counters[kCntTileEmpty], (unsigned long long)w_tile);
       atomicAdd(&g_diag_counters[kCntRoleA], (unsigned long long)(clock64() - t_role));
+      atomicAdd(&g_diag_counters[kCntAux0], (unsigned long long)t_mma);
+      atomicAdd(&g_diag_counters[kCntAux1], (unsigned long long)t_call);
+      atomicAdd(&g_diag_counters[kCntAux2], (unsigned long long)t_bar);
     }
   } else if (tid < kGroupA + kGroupB) {
     // ================================ group B: aggregation on mma.sync ================================
@@ -271,9 +278,34 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
       atomicAdd(&g_diag_counters[kCntPtileFull], (unsigned long long)w_pf);
       atomicAdd(&g_diag_counters[kCntRoleB], (unsigned long long)(clock64() - t_role));
     }
-  } else if (tid == kGroupA + kGroupB) {
-    // ================================ warp 11, lane 0: P-tile producer ================================
-    prefetch_tmap(&tmP);
+  } else {
+    // ================================ warp 11: tile producer ================================
+    // TMA when every tile starts on a 16-byte boundary (C % 4 == 0: the reference's shapes); otherwise the
+    // warp gathers the tile itself into the same 128B-swizzled layout.
+    const int lane = tid & 31;
+    const bool tma_ok = (C % 4) == 0;
+    if (lane == 0) prefetch_tmap(&tmP);
+    auto produce = [&](unsigned char* dst, uint64_t* full_bar, int col0, int row0, long long& wacc, uint64_t* empty_bar,
+                       uint32_t empty_parity) {
+      if (lane == 0) mbar_wait_timed(empty_bar, empty_parity, wacc);
+      __syncwarp();
+      if (tma_ok) {
+        if (lane == 0) {
+          mbar_expect_tx(full_bar, kPTileBytes);
+          tma_load_2d(dst, &tmP, col0, row0, full_bar);
+        }
+      } else {
+        const long long n_rows = (long long)p.B * N;
+        for (int idx = lane; idx < 32 * 32; idx += 32) {
+          const int r = idx >> 5, c = idx & 31;
+          float v = 0.f;
+          if (row0 + r < n_rows && col0 + c < p.ldp) v = p.P_aug[((size_t)row0 + r) * p.ldp + col0 + c];
+          *reinterpret_cast<float*>(dst + r * 128 + ((((c >> 2) ^ (r & 7)) << 4) | ((c & 3) << 2))) = v;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cta(full_bar);          // release: the tile is visible to the consumers
+      }
+    };
     uint32_t q = 0;
     long long w_pe = 0;
     const long long t_role = clock64();
@@ -281,25 +313,24 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
       const int b = blockIdx.x + it * gridDim.x;
       {                                                  // the s|d columns [HC, HC + 2H) of this graph's rows
         const int sb = it & 1;
-        mbar_wait_timed(&sd_empty[sb], ((it >> 1) & 1) ^ 1, w_pe);
-        mbar_expect_tx(&sd_full[sb], kPTileBytes);
-        tma_load_2d(smem_raw + off_sdtile + sb * kPTileBytes, &tmP, HC, b * N, &sd_full[sb]);
+        produce(smem_raw + off_sdtile + sb * kPTileBytes, &sd_full[sb], HC, b * N, w_pe, &sd_empty[sb],
+                ((it >> 1) & 1) ^ 1);
       }
       for (int pass = 0; pass < n_pass; ++pass) {
         const int G = min(kCbPerPass, n_cb - pass * kCbPerPass);
         for (int h = 0; h < H; ++h) {
           for (int k = 0; k < G; ++k, ++q) {
             const int slot = q % kPSlots;
-            mbar_wait_timed(&ptile_empty[slot], ((q / kPSlots) & 1) ^ 1, w_pe);
-            mbar_expect_tx(&ptile_full[slot], kPTileBytes);
-            tma_load_2d(smem_raw + off_ptile + (size_t)slot * kPTileBytes, &tmP, h * C + (pass * kCbPerPass + k) * 32,
-                        b * N, &ptile_full[slot]);
+            produce(smem_raw + off_ptile + (size_t)slot * kPTileBytes, &ptile_full[slot],
+                    h * C + (pass * kCbPerPass + k) * 32, b * N, w_pe, &ptile_empty[slot], ((q / kPSlots) & 1) ^ 1);
           }
         }
       }
     }
-    atomicAdd(&g_diag_counters[kCntPtileEmpty], (unsigned long long)w_pe);
-    atomicAdd(&g_diag_counters[kCntRoleP], (unsigned long long)(clock64() - t_role));
+    if (lane == 0) {
+      atomicAdd(&g_diag_counters[kCntPtileEmpty], (unsigned long long)w_pe);
+      atomicAdd(&g_diag_counters[kCntRoleP], (unsigned long long)(clock64() - t_role));
+    }
   }
 }
 

@@ -21,7 +21,7 @@ for _ in range(n):
     ev.append(e)
 torch.cuda.synchronize()
 lib.spotv2_diag_counters(buf, 1)
-names = ["ring_full(A)", "tile_empty(A)", "tile_full(B)", "ptile_full(B)", "ptile_empty(P)", "roleA_total", "roleB_total", "roleP_total"]
+names = ["ring_full(A)", "tile_empty(A)", "tile_full(B)", "ptile_full(B)", "ptile_empty(P)", "roleA_total", "roleB_total", "roleP_total", "A: mma loop", "A: logits call", "A: bar.sync"]
 ctas = 148
 ms = sum(a.elapsed_time(b) for e in ev for (n0, a), (n1, b) in zip(e[:-1], e[1:]) if n1 == "attn_fwd") / n
 print(f"attn_fwd {ms:.3f} ms/launch")
