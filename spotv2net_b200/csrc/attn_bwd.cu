@@ -140,6 +140,11 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
   float* dbias_s = reinterpret_cast<float*>(smem_raw + sm.off_dbias);
   unsigned char* uni = smem_raw + sm.off_union;
   float* const stage_base = reinterpret_cast<float*>(uni);             // [buf][P rows | G rows]
+  // keep the address space visible to the compiler even where these pointers travel through lambdas /
+  // structs (generic LD/ST to shared memory is several times slower than LDS/STS - measured)
+  __builtin_assume(__isShared(table_s)); __builtin_assume(__isShared(vfrag)); __builtin_assume(__isShared(sd));
+  __builtin_assume(__isShared(tile)); __builtin_assume(__isShared(D)); __builtin_assume(__isShared(pos_mask));
+  __builtin_assume(__isShared(dbias_s)); __builtin_assume(__isShared(stage_base)); __builtin_assume(__isShared(uni));
   const int stage_floats = (int)((sm.stage_P_bytes + sm.stage_G_bytes) / 4);
   const int stage_g_off = (int)(sm.stage_P_bytes / 4);
 
@@ -477,10 +482,10 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
                 const float* t0p = Ts + (size_t)(r0 + t4) * Fe;
                 const float* t1p = t0p + (size_t)4 * Fe;
                 float a[4];
-                a[0] = (k0_ok && f0 < Fe) ? t0p[f0] : 0.f;     // (m = g,   k = t)
-                a[1] = (k0_ok && f1 < Fe) ? t0p[f1] : 0.f;     // (m = g+8, k = t)
-                a[2] = (k1_ok && f0 < Fe) ? t1p[f0] : 0.f;     // (m = g,   k = t+4)
-                a[3] = (k1_ok && f1 < Fe) ? t1p[f1] : 0.f;     // (m = g+8, k = t+4)
+                a[0] = (k0_ok && f0 < Fe) ? lds_f32(t0p + f0) : 0.f;     // (m = g,   k = t)
+                a[1] = (k0_ok && f1 < Fe) ? lds_f32(t0p + f1) : 0.f;     // (m = g+8, k = t)
+                a[2] = (k1_ok && f0 < Fe) ? lds_f32(t1p + f0) : 0.f;     // (m = g,   k = t+4)
+                a[3] = (k1_ok && f1 < Fe) ? lds_f32(t1p + f1) : 0.f;     // (m = g+8, k = t+4)
                 uint32_t ah[4], al[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) split_tf32_trunc(a[q], ah[q], al[q]);

@@ -125,10 +125,10 @@ __device__ __forceinline__ void warp_edge_logits(const float* Ts, const float4* 
       if (ks < KS) {
         const int k0 = ks * 8 + t, k1 = k0 + 4;
         float a[4];
-        a[0] = k0 < Fe ? r0[k0] : 0.f;
-        a[1] = k0 < Fe ? r1[k0] : 0.f;
-        a[2] = k1 < Fe ? r0[k1] : 0.f;
-        a[3] = k1 < Fe ? r1[k1] : 0.f;
+        a[0] = k0 < Fe ? lds_f32(r0 + k0) : 0.f;
+        a[1] = k0 < Fe ? lds_f32(r1 + k0) : 0.f;
+        a[2] = k1 < Fe ? lds_f32(r0 + k1) : 0.f;
+        a[3] = k1 < Fe ? lds_f32(r1 + k1) : 0.f;
         uint32_t ah[4], al[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) split_tf32_trunc(a[q], ah[q], al[q]);
