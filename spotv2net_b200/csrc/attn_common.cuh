@@ -36,7 +36,7 @@ inline AttnSmem attn_smem_plan(int N, int Fe, int H, int R, int npairs, int chun
   AttnSmem s;
   s.chunk_rows = chunk_rows;
   s.NS = (2 * npairs + 3) / 4 * 4;
-  s.KS = (Fe + 7) / 8;
+  s.KS = ((Fe + 7) / 8 + 7) / 8 * 8;     // k-steps of 8 over Fe, padded to a multiple of 8 (zero B fragments)
   s.NT = (H + 7) / 8;
   size_t o = 0;
   s.off_bar = o;   o += 512;
@@ -102,79 +102,66 @@ __device__ __forceinline__ void build_vfrag(float4* vfrag, const float* v, int H
 template <int NT_MAX, int kSlots, class Sink>
 __device__ __forceinline__ void warp_edge_logits(const float* Ts, const float4* vfrag, int Fe, int KS,
                                                  int NT, int m0, int lane, Sink&& sink, long long* t_mma = nullptr) {
+  static_assert(NT_MAX == 1, "one n8 tile of heads (H <= 8)");
   const int g = lane >> 2, t = lane & 3;
   const long long t_begin = t_mma ? clock64() : 0;
-  // mma.sync on sm_100 has a very long latency (~300 cycles measured through the pipeline stalls), so the
-  // 3*KS MMAs of a row tile are spread over kSlots x 3 independent accumulators (k-step mod kSlots, one per
-  // product) instead of one chain; they are summed small-terms-first at the end.
-  float acc[NT_MAX][kSlots][3][4];
+  // One warp per scheduler runs this loop, so it has to carry its own instruction-level parallelism:
+  // the body is branch-free (KS is padded to a multiple of kSlots with zero B fragments; out-of-range
+  // feature indices are clamped onto real data and multiplied by those zeros), all fragment loads of a
+  // block of kSlots k-steps are issued up front, and every k-step slot and product has its own
+  // accumulator so no mma.sync waits on another (their latency is long on sm_100).
+  float acc[kSlots][3][4];
 #pragma unroll
-  for (int nt = 0; nt < NT_MAX; ++nt)
+  for (int sl = 0; sl < kSlots; ++sl)
 #pragma unroll
-    for (int sl = 0; sl < kSlots; ++sl)
+    for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
-      for (int pr = 0; pr < 3; ++pr)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[nt][sl][pr][q] = 0.f;
+      for (int q = 0; q < 4; ++q) acc[sl][pr][q] = 0.f;
   const float* r0 = Ts + (size_t)(m0 + g) * Fe;
   const float* r1 = r0 + (size_t)8 * Fe;
+  const int kmax = Fe - 1;
+  (void)NT;
   for (int ks0 = 0; ks0 < KS; ks0 += kSlots) {
+    float a[kSlots][4];
+    float4 bf[kSlots];
 #pragma unroll
     for (int sl = 0; sl < kSlots; ++sl) {
-      const int ks = ks0 + sl;
-      if (ks < KS) {
-        const int k0 = ks * 8 + t, k1 = k0 + 4;
-        float a[4];
-        a[0] = k0 < Fe ? lds_f32(r0 + k0) : 0.f;
-        a[1] = k0 < Fe ? lds_f32(r1 + k0) : 0.f;
-        a[2] = k1 < Fe ? lds_f32(r0 + k1) : 0.f;
-        a[3] = k1 < Fe ? lds_f32(r1 + k1) : 0.f;
-        uint32_t ah[4], al[4];
+      const int k0 = min((ks0 + sl) * 8 + t, kmax), k1 = min((ks0 + sl) * 8 + t + 4, kmax);
+      a[sl][0] = lds_f32(r0 + k0);
+      a[sl][1] = lds_f32(r1 + k0);
+      a[sl][2] = lds_f32(r0 + k1);
+      a[sl][3] = lds_f32(r1 + k1);
+      bf[sl] = vfrag[(ks0 + sl) * 32 + lane];
+    }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) split_tf32_trunc(a[q], ah[q], al[q]);
+    for (int sl = 0; sl < kSlots; ++sl) {
+      uint32_t ah[4], al[4];
 #pragma unroll
-        for (int nt = 0; nt < NT_MAX; ++nt) {
-          if (nt < NT) {
-            const float4 bf = vfrag[(nt * KS + ks) * 32 + lane];
-            const uint32_t bh[2] = {__float_as_uint(bf.x), __float_as_uint(bf.y)};
-            const uint32_t bl[2] = {__float_as_uint(bf.z), __float_as_uint(bf.w)};
-            mma_tf32_16x8x8(acc[nt][sl][0], al, bh);
-            mma_tf32_16x8x8(acc[nt][sl][1], ah, bl);
-            mma_tf32_16x8x8(acc[nt][sl][2], ah, bh);
-          }
-        }
-      }
+      for (int q = 0; q < 4; ++q) split_tf32_trunc(a[sl][q], ah[q], al[q]);
+      const uint32_t bh[2] = {__float_as_uint(bf[sl].x), __float_as_uint(bf[sl].y)};
+      const uint32_t bl[2] = {__float_as_uint(bf[sl].z), __float_as_uint(bf[sl].w)};
+      mma_tf32_16x8x8(acc[sl][0], al, bh);
+      mma_tf32_16x8x8(acc[sl][1], ah, bl);
+      mma_tf32_16x8x8(acc[sl][2], ah, bh);
     }
   }
-  float csum[NT_MAX][4];
+  float c[4];
 #pragma unroll
-  for (int nt = 0; nt < NT_MAX; ++nt) {
-    if (nt < NT) {
-      float* c = csum[nt];
+  for (int q = 0; q < 4; ++q) {
+    float corr = 0.f, mainp = 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float corr = 0.f, mainp = 0.f;
-#pragma unroll
-        for (int sl = 0; sl < kSlots; ++sl) {
-          corr += acc[nt][sl][0][q] + acc[nt][sl][1][q];
-          mainp += acc[nt][sl][2][q];
-        }
-        c[q] = corr + mainp;
-      }
+    for (int sl = 0; sl < kSlots; ++sl) {
+      corr += acc[sl][0][q] + acc[sl][1][q];
+      mainp += acc[sl][2][q];
     }
+    c[q] = corr + mainp;
   }
   if (t_mma) *t_mma += clock64() - t_begin;          // includes waiting for the accumulators
-#pragma unroll
-  for (int nt = 0; nt < NT_MAX; ++nt) {
-    if (nt < NT) {
-      const float* c = csum[nt];
-      const int n = nt * 8 + 2 * t;
-      sink(m0 + g, n, c[0]);
-      sink(m0 + g, n + 1, c[1]);
-      sink(m0 + g + 8, n, c[2]);
-      sink(m0 + g + 8, n + 1, c[3]);
-    }
-  }
+  const int n = 2 * t;
+  sink(m0 + g, n, c[0]);
+  sink(m0 + g, n + 1, c[1]);
+  sink(m0 + g + 8, n, c[2]);
+  sink(m0 + g + 8, n + 1, c[3]);
 }
 
 // Phase 1 for one graph: stream the R edge rows through the ring and scatter the edge terms

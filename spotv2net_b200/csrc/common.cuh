@@ -65,7 +65,7 @@ __device__ __forceinline__ void split_tf32_trunc(float x, uint32_t& hi, uint32_t
 // D(16x8, f32) += A(16x8, tf32, row) * B(8x8, tf32, col)
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4],
                                                 const uint32_t (&b)[2]) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
       "{%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -81,7 +81,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // logit loop ran at ~290 cycles per k-step with generic loads).
 __device__ __forceinline__ float lds_f32(const float* p) {
   float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));      // not volatile: free to be hoisted
   return v;
 }
 
