@@ -448,3 +448,47 @@ def test_full_batch_properties(cuda_lib):
         o.backward(dout[s * half * N:(s + 1) * half * N])
         acc += layer.lin_src.weight.grad
     assert relerr(acc, gW) < TOL
+
+
+# ------------------------------------------------------------------ the caller: training harness
+def test_training_harness_loss_curve_matches_oracle_loop(cuda_lib, tmp_path):
+    """spotv2net_b200.train.train (5_train_SpotV2Net.py:23-203 restated) against the same loop run with the
+    oracle model on the CPU: same seed, same split, same shuffle, Adam; per-epoch train/test losses agree."""
+    from spotv2net_b200.train import train
+    N, L, T = 30, 3, 46
+    vol, vv = synth.synthetic_matrices(T, N, seed=77)
+    p = dict(modelname="t", modeltype="gat", seq_length=L, batch_size=8, dim_hidden_layers=[16], output_node_channels=1,
+             num_heads=3, concat_heads=True, activation="relu", optimizer="adam", learning_rate=1e-3, negative_slope=0.2,
+             dropout_att=0.0, dropout=0.0, standardize=False, num_epochs=2, tolerance=1e-9, split_proportion=0.8,
+             scale_up=None, seed=5)
+    tr, te = train(p=dict(p), vol=vol, volvol=vv, device=DEV, output_root=str(tmp_path), drop_first=2, verbose=False)
+    assert os.path.exists(tmp_path / "t_3" / "t_weights_seed_5.pth") and os.path.exists(tmp_path / "t_3" / "test_losses_seed_5.npy")
+    # oracle loop
+    n = T - L - 2
+    n_train = int(0.8 * n)
+    torch.manual_seed(5)
+    model = pyg_gat.OracleGATModel(N * L, 3 * L, 3, 1, [16], concat_heads=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    gen = torch.Generator().manual_seed(5)
+    crit = torch.nn.MSELoss()
+    tr_ref, te_ref = [], []
+    for _ in range(2):
+        model.train()
+        order = torch.randperm(n_train, generator=gen)
+        tot, steps = 0.0, 0
+        for s in range(0, n_train, 8):
+            bt = synth.make_batch(vol, vv, [int(i) + 2 for i in order[s:s + 8]], L)
+            loss = crit(model(bt), bt.y_x)
+            opt.zero_grad(); loss.backward(); opt.step()
+            tot += loss.item(); steps += 1
+        tr_ref.append(tot / steps)
+        model.eval()
+        tot, nb = 0.0, 0
+        with torch.no_grad():
+            for s in range(n_train, n, 8):
+                bt = synth.make_batch(vol, vv, [i + 2 for i in range(s, min(s + 8, n))], L)
+                tot += crit(model(bt), bt.y_x).item(); nb += 1
+        te_ref.append(tot / nb)
+    assert np.allclose(tr, tr_ref, rtol=2e-4) and np.allclose(te, te_ref, rtol=2e-4), (tr, tr_ref, te, te_ref)
+    sd = torch.load(tmp_path / "t_3" / "t_weights_seed_5.pth")
+    assert list(sd.keys()) == list(model.state_dict().keys())
