@@ -22,7 +22,9 @@
  *    CUDA graph.
  *  - return value: SPOTV2_OK (0) or a spotv2_status; a human-readable message
  *    for the calling thread's last failure is at spotv2_last_error().
- *  - all floating point is IEEE fp32; row-major; leading dimensions in elements.
+ *  - all inputs, outputs and parameters are IEEE fp32; row-major; leading dimensions in elements.
+ *    The only other format is the tensor-core GEMM operand ("fp16 pair", see spotv2_split_f16), an
+ *    internal representation that resolves 22 significand bits and never leaves the library's buffers.
  *  - batches are B identical complete directed graphs on N nodes (the only
  *    topology /root/reference/utils/dataset.py:216-226 produces).  Anything
  *    else is rejected by spotv2_edge_table_build — there is no generic or CPU
@@ -38,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SPOTV2_ABI_VERSION 1
+#define SPOTV2_ABI_VERSION 2
 
 typedef enum spotv2_status {
   SPOTV2_OK = 0,
@@ -64,7 +66,7 @@ typedef struct spotv2_gat_desc {
   int32_t concat;         /* 1: out is [B*N, H*C]; 0: head mean, out is [B*N, C]   */
   float   negative_slope; /* LeakyReLU slope                                       */
   int32_t ldp;            /* row stride of P_aug / dP_aug: >= H*C + 2*H, % 4 == 0  */
-  int32_t gemm_algo;      /* 0 auto, 1 fp32 SIMT, 2 tcgen05 3xTF32                 */
+  int32_t gemm_algo;      /* 0 | 2 tcgen05 (fp16 operand pairs), 1 fp32 CUDA cores */
   int32_t reserved;
 } spotv2_gat_desc;
 
@@ -103,19 +105,30 @@ int spotv2_gat_fold(const spotv2_gat_desc* d, const float* W, const float* a_src
                     const float* a_dst, const float* W_e, const float* a_edge, float* W_aug,
                     float* v, void* stream);
 
-/* 1 when the projection GEMMs of this descriptor run on the tensor cores (tcgen05, 3xTF32 with
- * operands pre-split into tf32 hi/lo pairs), 0 when they take the exact-fp32 CUDA-core kernel. */
+/* 1 when the projection GEMMs of this descriptor run on the tensor cores (tcgen05 kind::f16 on fp16
+ * operand pairs), 0 when they take the exact-fp32 CUDA-core kernel (gemm_algo == 1). */
 int spotv2_gat_uses_tensor_cores(const spotv2_gat_desc* d);
 
-/* hi = tf32(src), lo = tf32(src - hi), element-wise over n floats (all pointers 16-byte aligned).
- * Lets the caller split an operand once and reuse it (x feeds both proj_fwd and proj_bwd_weight). */
-int spotv2_split_tf32(const float* src, float* hi, float* lo, size_t n, void* stream);
+/* Leading dimension (elements) of an fp16-pair array holding `cols` columns: cols rounded up to 8. */
+int32_t spotv2_gat_ld16(int32_t cols);
+
+/* Tensor-core operand preparation ("fp16 pair").  src [rows, cols] fp32 (row pitch ld) becomes
+ *   hi = fp16(src * s),  lo = fp16(src * s - hi)        both [rows, ld16] fp16, ld16 % 8 == 0,
+ * with s a power of two per group that maps the group's largest magnitude into [2^14, 2^15)
+ * (hi + lo == src * s to 2^-22; removing s is exact).  Groups: index < split_at / >= split_at along
+ * split_dim (0 rows, 1 cols); split_at <= 0 means one group.  scale_block (8 floats, device) receives
+ * {bits of max|.| x2, inverse scales x2, scales x2, -, -}; the GEMM entry points read the inverse scales
+ * from it.  Lets the caller prepare x once per step for both proj_fwd and proj_bwd_weight. */
+int spotv2_split_f16(const float* src, int32_t rows, int32_t cols, int32_t ld, int32_t split_dim,
+                     int32_t split_at, void* hi, void* lo, int32_t ld16, float* scale_block, void* stream);
 
 /* lin_src: P_aug [B*N, ldp] = x [B*N, F] . W_aug^T ; columns [0,HC) are P,
  * [HC,HC+H) are s = alpha_src, [HC+H,HC+2H) are d = alpha_dst.
- * x_hi/x_lo: optional pre-split x (both or neither); otherwise x is split into the workspace. */
-int spotv2_proj_fwd(const spotv2_gat_desc* d, const float* x, const float* x_hi, const float* x_lo,
-                    const float* W_aug, float* P_aug, void* ws, size_t ws_bytes, void* stream);
+ * x_hi/x_lo/x_scale: optional fp16 pair of x ([B*N, ld16(F)], all three or none); otherwise x is
+ * prepared inside the workspace. */
+int spotv2_proj_fwd(const spotv2_gat_desc* d, const float* x, const void* x_hi, const void* x_lo,
+                    const float* x_scale, const float* W_aug, float* P_aug, void* ws, size_t ws_bytes,
+                    void* stream);
 
 /* edge_update + softmax + propagate + head reduce + bias ([PyG] gat_conv.py
  * edge_update/message, utils/softmax.py, aggr='add').  edge_rows is [B, R, Fe]
@@ -126,21 +139,24 @@ int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug, const floa
                         float* out, float* alpha_or_null, void* stream);
 
 /* autograd of the above with the attention coefficients recomputed, not stored.
- * dout [B*N, C or HC] -> dP_aug [B*N, ldp] (dP | ds | dd), dv [H, Fe], dbias.
- * dP_lo_or_null: when given, the gradient is emitted already split for the tensor-core GEMMs:
- * dP_aug receives the tf32 hi part and dP_lo the lo part (hi + lo == dP to ~2^-22). */
+ * dout [B*N, C or HC] -> dP_aug (dP | ds | dd), dv [H, Fe], dbias.  The gradient is emitted either as
+ * fp32 dP_aug [B*N, ldp] (CUDA-core GEMM path) or, when dP_hi/dP_lo/dp_scale are given, directly as the
+ * fp16 pair [B*N, ld16(HC+2H)] the tensor-core GEMMs consume (two scale groups: columns < HC from a
+ * bound on max|dout|, the ds|dd columns from their own maximum); dp_scale is an 8-float scale block. */
 int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug, const float* edge_rows,
-                        const int32_t* table, const float* v, const float* dout, float* dP_aug,
-                        float* dP_lo_or_null, float* dv_or_null, float* dbias_or_null, void* ws,
-                        size_t ws_bytes, void* stream);
+                        const int32_t* table, const float* v, const float* dout, float* dP_aug_or_null,
+                        void* dP_hi_or_null, void* dP_lo_or_null, float* dp_scale_or_null,
+                        float* dv_or_null, float* dbias_or_null, void* ws, size_t ws_bytes, void* stream);
 
 /* lin_src backward: dW_aug [H*C+2H, F] = dP_aug^T . x  and  dX [B*N, F] = dP_aug . W_aug.
- * x_hi/x_lo and dP_lo: optional pre-split operands (dP_aug is then the hi part). */
-int spotv2_proj_bwd_weight(const spotv2_gat_desc* d, const float* x, const float* x_hi, const float* x_lo,
-                           const float* dP_aug, const float* dP_lo, float* dW_aug, void* ws,
-                           size_t ws_bytes, void* stream);
-int spotv2_proj_bwd_input(const spotv2_gat_desc* d, const float* dP_aug, const float* dP_lo,
-                          const float* W_aug, float* dX, void* ws, size_t ws_bytes, void* stream);
+ * x and dP_aug are taken as fp16 pairs when given (hi, lo, scale block: all three), else as fp32 and
+ * prepared inside the workspace. */
+int spotv2_proj_bwd_weight(const spotv2_gat_desc* d, const float* x, const void* x_hi, const void* x_lo,
+                           const float* x_scale, const float* dP_aug, const void* dP_hi, const void* dP_lo,
+                           const float* dp_scale, float* dW_aug, void* ws, size_t ws_bytes, void* stream);
+int spotv2_proj_bwd_input(const spotv2_gat_desc* d, const float* dP_aug, const void* dP_hi, const void* dP_lo,
+                          const float* dp_scale, const float* W_aug, float* dX, void* ws, size_t ws_bytes,
+                          void* stream);
 
 /* Inverse of spotv2_gat_fold for gradients: from dW_aug and dv to the gradients of
  * lin_src.weight, att_src, att_dst, lin_edge.weight, att_edge (PyG parameter names). */
@@ -165,9 +181,10 @@ int spotv2_collate_windows(const float* M_vol, const float* M_vv, int32_t T, int
 
 /* ---- diagnostics (bring-up and parity tests of the GEMM back ends; not reference-facing) ----
  * C[M,N] (ld ldc) = sum_k A(m,k) B(n,k).  a_kc/b_kc = 1: operand stored [rows, K] (K contiguous),
- * 0: stored [K, rows].  algo 1 = exact-fp32 CUDA-core kernel, 2 = tcgen05 3xTF32 kernel (operands are
- * split into tf32 hi/lo pairs inside ws).  bn = 128|256 tile width, kb_per_chunk = 32-wide k-blocks
- * per TMEM accumulation chain (0 = default 4), splits = split-K factor. */
+ * 0: stored [K, rows].  algo 1 = exact-fp32 CUDA-core kernel, 2 = tcgen05 3xTF32 kernel (the first
+ * tensor-core version, kept as a yardstick), 3 = tcgen05 fp16-pair kernel (the production path);
+ * operands are split inside ws.  bn = 128|256 tile width (+16: half-depth k-blocks, deeper ring),
+ * kb_per_chunk = k-blocks per TMEM accumulation chain (0 = 128 elements), splits = split-K factor. */
 int spotv2_diag_gemm(int a_kc, int b_kc, int M, int N, int K, const float* A, int lda, const float* B,
                      int ldb, float* C, int ldc, int algo, int splits, int bn, int kb_per_chunk,
                      void* ws, size_t ws_bytes, void* stream);

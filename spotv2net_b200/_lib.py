@@ -38,12 +38,13 @@ SIGNATURES = {
     "spotv2_edge_table_dense": (C.c_int, [_i32, _vp, _vp]),
     "spotv2_gat_fold": (C.c_int, [_DP] + [_vp] * 8),
     "spotv2_gat_uses_tensor_cores": (C.c_int, [_DP]),
-    "spotv2_split_tf32": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
-    "spotv2_proj_fwd": (C.c_int, [_DP, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "spotv2_gat_ld16": (_i32, [_i32]),
+    "spotv2_split_f16": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "spotv2_proj_fwd": (C.c_int, [_DP] + [_vp] * 7 + [_sz, _vp]),
     "spotv2_gat_attn_fwd": (C.c_int, [_DP] + [_vp] * 8),
-    "spotv2_gat_attn_bwd": (C.c_int, [_DP] + [_vp] * 10 + [_sz, _vp]),
-    "spotv2_proj_bwd_weight": (C.c_int, [_DP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "spotv2_proj_bwd_input": (C.c_int, [_DP, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "spotv2_gat_attn_bwd": (C.c_int, [_DP] + [_vp] * 12 + [_sz, _vp]),
+    "spotv2_proj_bwd_weight": (C.c_int, [_DP] + [_vp] * 10 + [_sz, _vp]),
+    "spotv2_proj_bwd_input": (C.c_int, [_DP] + [_vp] * 7 + [_sz, _vp]),
     "spotv2_gat_unfold": (C.c_int, [_DP] + [_vp] * 13),
     "spotv2_alpha_to_pyg": (C.c_int, [_DP, _vp, _vp, _vp, _vp]),
     "spotv2_collate_windows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
@@ -69,8 +70,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.spotv2_abi_version() != 1:
-        raise SpotV2Error(f"ABI version mismatch: library reports {lib.spotv2_abi_version()}, binding expects 1")
+    if lib.spotv2_abi_version() != 2:
+        raise SpotV2Error(f"ABI version mismatch: library reports {lib.spotv2_abi_version()}, binding expects 2")
     _lib = lib
     return lib
 

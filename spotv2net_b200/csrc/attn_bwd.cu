@@ -13,7 +13,10 @@
 //   B4  dv[h,:] += sum_e dz'[e,h] * edge_attr[e,:]: second pass over the edge rows         [ring]
 // The ring and the B2 staging alias the same shared memory.  dv and dbias are accumulated per
 // CTA and reduced in a fixed order by a second kernel (deterministic).
+#include <cuda_fp16.h>
+
 #include "attn_common.cuh"
+#include "gemm.cuh"
 
 namespace spotv2 {
 
@@ -28,21 +31,26 @@ __device__ unsigned long long g_bwd_counters[kNumCounters];
 struct AttnBwdArgs {
   AttnParams p;
   const float* dout;
-  float* dP_aug;       // fp32 gradient, or its tf32 'hi' part when dP_lo is given
-  float* dP_lo;        // optional: tf32 'lo' part (operand pre-split for the tensor-core dW / dX GEMMs)
+  float* dP_aug;       // fp32 gradient [B*N, ldp] (CUDA-core GEMM path), or null
+  // tensor-core path: dP emitted as scaled fp16 hi/lo pairs [B*N, ldp16] (operand format of gemm_f16.cu);
+  // the scale comes from max|dout| (dout_blk[0], bit pattern) times `bound` >= max|dP| / max|dout|.
+  // ds | dd have their own magnitude: they go to dsd [B*N, 2H] in fp32 and are split by the caller.
+  __half* dP_hi16;
+  __half* dP_lo16;
+  int ldp16;
+  const float* dout_blk;
+  float bound;
+  float* dsd;
+  float* dp_blk;       // receives inverse scale [2] and scale [4] of the dP group
   float* dv_part;      // [grid][H*Fe]
   float* dbias_part;   // [grid][ldo]
 };
 
-__device__ __forceinline__ void store_grad(const AttnBwdArgs& a, size_t off, float v) {
-  if (a.dP_lo) {
-    uint32_t hi, lo;
-    split_tf32_trunc(v, hi, lo);
-    a.dP_aug[off] = __uint_as_float(hi);
-    a.dP_lo[off] = __uint_as_float(lo);
-  } else {
-    a.dP_aug[off] = v;
-  }
+__device__ __forceinline__ float dp_scale_from_amax(float amax) {   // same rule as gemm_f16.cu
+  if (!(amax > 0.f) || !(amax < INFINITY)) return 1.f;
+  int ex;
+  frexpf(amax, &ex);
+  return exp2f((float)(15 - ex));
 }
 
 struct BwdSmem {
@@ -172,6 +180,11 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
   if (p.bulk_ok && tid == 0 && b < p.B && ring.nchunks > 0) ring.prefetch_first(b);
 
   const float g_scale = p.concat ? 1.f : 1.f / (float)H;
+  float dp_scale = 1.f;
+  if (args.dP_hi16) {
+    dp_scale = dp_scale_from_amax(__uint_as_float(*reinterpret_cast<const unsigned*>(args.dout_blk)) * args.bound);
+    if (blockIdx.x == 0 && tid == 0) { args.dp_blk[2] = 1.f / dp_scale; args.dp_blk[4] = dp_scale; }
+  }
   const bool vec4 = (C % 4 == 0) && (p.ldo % 4 == 0);
   const int NIG = sm.NP5 / kTI;                       // tile groups along targets and sources
   const int n_tiles = H * NIG * NIG;
@@ -328,7 +341,8 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
         dd += dz;
         dcol[j * NS] = dz;
       }
-      store_grad(args, ((size_t)b * N + i) * p.ldp + HC + H + h, dd);
+      if (args.dsd) args.dsd[((size_t)b * N + i) * 2 * H + H + h] = dd;
+      else args.dP_aug[((size_t)b * N + i) * p.ldp + HC + H + h] = dd;
     }
     __syncthreads();
     for (int idx = tid; idx < H * N; idx += kAttnThreads) {     // ds_j = sum_i dz_ij
@@ -340,7 +354,8 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
         if (i >= N) i -= N;
         ds += drow[i];
       }
-      store_grad(args, ((size_t)b * N + j) * p.ldp + HC + h, ds);
+      if (args.dsd) args.dsd[((size_t)b * N + j) * 2 * H + h] = ds;
+      else args.dP_aug[((size_t)b * N + j) * p.ldp + HC + h] = ds;
     }
     __syncthreads();
     for (int idx = tid; idx < H * N; idx += kAttnThreads) {     // dz' : gradient through the mean fill
@@ -405,21 +420,27 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
             s0 = ffma2(a0, G[NPAIRS - 1][0], s0);
             s1 = ffma2(a0, G[NPAIRS - 1][1], s1);
           }
-          const size_t off = ((size_t)b * N + j) * p.ldp + (size_t)h * C + c0;
           const float v0 = s0.x + s0.y, v1 = s1.x + s1.y;
-          if (p.vec2_ok) {
-            if (args.dP_lo) {
-              uint32_t h0_, l0_, h1_, l1_;
-              split_tf32_trunc(v0, h0_, l0_);
-              split_tf32_trunc(v1, h1_, l1_);
-              *reinterpret_cast<float2*>(args.dP_aug + off) = make_float2(__uint_as_float(h0_), __uint_as_float(h1_));
-              *reinterpret_cast<float2*>(args.dP_lo + off) = make_float2(__uint_as_float(l0_), __uint_as_float(l1_));
+          if (args.dP_hi16) {
+            const size_t off = ((size_t)b * N + j) * args.ldp16 + (size_t)h * C + c0;
+            const float w0 = v0 * dp_scale, w1 = v1 * dp_scale;
+            const __half h0_ = __float2half_rn(w0), h1_ = __float2half_rn(w1);
+            const __half l0_ = __float2half_rn(w0 - __half2float(h0_)), l1_ = __float2half_rn(w1 - __half2float(h1_));
+            if (p.vec2_ok) {
+              *reinterpret_cast<__half2*>(args.dP_hi16 + off) = __halves2half2(h0_, h1_);
+              *reinterpret_cast<__half2*>(args.dP_lo16 + off) = __halves2half2(l0_, l1_);
             } else {
-              *reinterpret_cast<float2*>(args.dP_aug + off) = make_float2(v0, v1);
+              args.dP_hi16[off] = h0_; args.dP_lo16[off] = l0_;
+              if (has1) { args.dP_hi16[off + 1] = h1_; args.dP_lo16[off + 1] = l1_; }
             }
           } else {
-            store_grad(args, off, v0);
-            if (has1) store_grad(args, off + 1, v1);
+            const size_t off = ((size_t)b * N + j) * p.ldp + (size_t)h * C + c0;
+            if (p.vec2_ok) {
+              *reinterpret_cast<float2*>(args.dP_aug + off) = make_float2(v0, v1);
+            } else {
+              args.dP_aug[off] = v0;
+              if (has1) args.dP_aug[off + 1] = v1;
+            }
           }
         }
       }
@@ -549,6 +570,17 @@ __global__ void partial_reduce_kernel(const float* __restrict__ part, int nparts
   out[k] = s;
 }
 
+size_t attn_bwd_partials_bytes(const spotv2_gat_desc* d) {
+  // per-CTA partials of dv [H, Fe] and dbias [C or HC]; at most 2 CTAs per SM
+  const size_t ctas = 2 * (size_t)sm_count();
+  const size_t ldo = d->concat ? (size_t)d->H * d->C : (size_t)d->C;
+  return round_up(ctas * ((size_t)d->H * d->Fe + ldo) * sizeof(float), 256);
+}
+size_t attn_bwd_ws_bytes(const spotv2_gat_desc* d) {
+  // partials | ds,dd in fp32 [B*N, 2H] | two scale blocks
+  return attn_bwd_partials_bytes(d) + round_up((size_t)d->B * d->N * 2 * d->H * sizeof(float), 256) + 256;
+}
+
 template <int NPAIRS>
 static int launch_bwd(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t ws_bytes, cudaStream_t st) {
   const AttnParams& p = a.p;
@@ -595,14 +627,19 @@ using namespace spotv2;
 
 extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
                                    const float* edge_rows, const int32_t* table, const float* v,
-                                   const float* dout, float* dP_aug, float* dP_lo_or_null, float* dv_or_null,
-                                   float* dbias_or_null, void* ws, size_t ws_bytes, void* stream) {
+                                   const float* dout, float* dP_aug_or_null, void* dP_hi_or_null, void* dP_lo_or_null,
+                                   float* dp_scale_or_null, float* dv_or_null, float* dbias_or_null, void* ws,
+                                   size_t ws_bytes, void* stream) {
   if (int rc = check_desc(d)) return rc;
-  SPOTV2_REQUIRE(P_aug && dout && dP_aug, "attn_bwd: P_aug, dout, dP_aug must be non-null");
+  SPOTV2_REQUIRE(P_aug && dout, "attn_bwd: P_aug and dout must be non-null");
+  const bool f16 = dP_hi_or_null != nullptr;
+  SPOTV2_REQUIRE(f16 || dP_aug_or_null, "attn_bwd: give dP_aug (fp32) or dP_hi/dP_lo/dp_scale (fp16 pairs)");
+  SPOTV2_REQUIRE(!f16 || (dP_lo_or_null && dp_scale_or_null), "attn_bwd: dP_hi needs dP_lo and dp_scale");
   SPOTV2_REQUIRE(d->Fe == 0 || (edge_rows && table && v),
                  "attn_bwd: edge_rows, table and v are required when Fe > 0");
-  SPOTV2_REQUIRE(aligned16(P_aug) && aligned16(dout) && aligned16(dP_aug),
-                 "attn_bwd: P_aug/dout/dP_aug must be 16-byte aligned");
+  SPOTV2_REQUIRE(aligned16(P_aug) && aligned16(dout) && (f16 || aligned16(dP_aug_or_null)) &&
+                     (!f16 || (aligned16(dP_hi_or_null) && aligned16(dP_lo_or_null))),
+                 "attn_bwd: P_aug/dout/dP must be 16-byte aligned");
   if (d->H > kMaxHeads) return fail(SPOTV2_ERR_UNSUPPORTED, "H=%d > %d", d->H, kMaxHeads);
   if (d->Fe > kMaxFe) return fail(SPOTV2_ERR_UNSUPPORTED, "Fe=%d > %d", d->Fe, kMaxFe);
   AttnBwdArgs a;
@@ -613,13 +650,44 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
   a.p.P_aug = P_aug; a.p.edge_rows = edge_rows; a.p.table = table; a.p.v = v;
   a.p.bulk_ok = d->Fe > 0 && aligned16(edge_rows) && ((size_t)d->R * d->Fe) % 4 == 0;
   a.p.vec2_ok = (d->C % 2 == 0);
-  a.dout = dout; a.dP_aug = dP_aug; a.dP_lo = dP_lo_or_null; a.dv_part = nullptr; a.dbias_part = nullptr;
-  SPOTV2_REQUIRE(!dP_lo_or_null || aligned16(dP_lo_or_null), "attn_bwd: dP_lo must be 16-byte aligned");
+  a.dout = dout; a.dP_aug = f16 ? nullptr : dP_aug_or_null; a.dv_part = nullptr; a.dbias_part = nullptr;
+  a.dP_hi16 = static_cast<__half*>(dP_hi_or_null); a.dP_lo16 = static_cast<__half*>(dP_lo_or_null);
+  const int HC = d->H * d->C;
+  a.ldp16 = ld16_of(HC + 2 * d->H);
+  a.dout_blk = nullptr; a.bound = 1.f; a.dsd = nullptr; a.dp_blk = dp_scale_or_null;
   cudaStream_t st = as_stream(stream);
+  float* blk_tmp = nullptr;
+  const size_t rows = (size_t)d->B * d->N;
+  if (f16) {
+    const size_t part = attn_bwd_partials_bytes(d);
+    if (!ws || ws_bytes < attn_bwd_ws_bytes(d))
+      return fail(SPOTV2_ERR_WORKSPACE, "attn_bwd needs %zu B of workspace, got %zu", attn_bwd_ws_bytes(d), ws_bytes);
+    unsigned char* w = static_cast<unsigned char*>(ws);
+    a.dsd = reinterpret_cast<float*>(w + part);
+    float* blk_dout = reinterpret_cast<float*>(w + part + round_up(rows * 2 * d->H * sizeof(float), 256));
+    blk_tmp = blk_dout + kScaleBlockFloats;
+    a.dout_blk = blk_dout;
+    // |dP_h[j,c]| = |g sum_i alpha_h[i,j] dO[i,c]| <= g N max|dout|  (g = 1/H for the head mean)
+    a.bound = (float)d->N * (d->concat ? 1.f : 1.f / (float)d->H);
+    SPOTV2_CUDA_OK(cudaMemsetAsync(dp_scale_or_null, 0, kScaleBlockFloats * sizeof(float), st));
+    if (int rc = amax_flat(dout, rows * (size_t)a.p.ldo, blk_dout, st)) return rc;
+  }
   const int np = (d->N + 1) / 2;
-  if (np <= 4) return launch_bwd<4>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
-  if (np <= 8) return launch_bwd<8>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
-  if (np <= 15) return launch_bwd<15>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
-  if (np <= 16) return launch_bwd<16>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
-  return fail(SPOTV2_ERR_UNSUPPORTED, "N=%d > 32: the one-CTA-per-graph kernel covers N <= 32", d->N);
+  int rc;
+  if (np <= 4) rc = launch_bwd<4>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
+  else if (np <= 8) rc = launch_bwd<8>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
+  else if (np <= 15) rc = launch_bwd<15>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
+  else if (np <= 16) rc = launch_bwd<16>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
+  else return fail(SPOTV2_ERR_UNSUPPORTED, "N=%d > 32: the one-CTA-per-graph kernel covers N <= 32", d->N);
+  if (rc) return rc;
+  if (f16) {
+    // ds | dd: own scale group (columns [HC, HC + 2H) of the fp16 pair arrays)
+    const int none = 0x7fffffff;
+    if ((rc = split_f16(a.dsd, (int)rows, 2 * d->H, 2 * d->H, 0, none, nullptr, 0, a.dP_hi16 + HC, a.dP_lo16 + HC,
+                        a.ldp16, blk_tmp, st)))
+      return rc;
+    SPOTV2_CUDA_OK(cudaMemcpyAsync(dp_scale_or_null + 3, blk_tmp + 2, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SPOTV2_CUDA_OK(cudaMemcpyAsync(dp_scale_or_null + 5, blk_tmp + 4, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  return SPOTV2_OK;
 }

@@ -31,6 +31,7 @@ inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
 int check_desc(const spotv2_gat_desc* d);
 int sm_count();
+size_t attn_bwd_ws_bytes(const spotv2_gat_desc* d);      // attn_bwd.cu
 
 // ---- device helpers ---------------------------------------------------------------------
 // Packed fp32 pair FMA (Blackwell FFMA2): d = a * b + c on both halves.

@@ -26,4 +26,25 @@ int gemm3x_tf32(bool a_kc, bool b_kc, int M, int N, int K, const float* A_hi, co
                 const float* B_hi, const float* B_lo, int ldb, float* C, int ldc, int splits, int bn,
                 int kb_per_chunk, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// ---- fp16-pair ("3xFP16") tensor-core GEMM: gemm_f16.cu ----------------------------------------------
+// An operand pre-split into scaled fp16 hi/lo arrays.  inv -> 2 floats on the device: the inverse scales of
+// the operand's two groups (M|N index < split_at / >= split_at); null = unscaled.
+struct F16Operand {
+  const void* hi;
+  const void* lo;
+  int ld;               // elements, % 8 == 0
+  const float* inv;
+  int split_at;
+};
+constexpr int kScaleBlockFloats = 8;   // [0,1] amax bits, [2,3] inverse scales, [4,5] scales
+inline int ld16_of(int cols) { return (cols + 7) / 8 * 8; }
+// blk[0] <- bit pattern of max |src| (blk is zeroed first)
+int amax_flat(const float* src, size_t n, float* blk, cudaStream_t st);
+// src [rows, cols] (pitch ld) -> hi/lo fp16 [rows, ld16]; two scale groups along split_dim (0 rows, 1 cols) at
+// split_at; optional exact pre-multiplier pre2[row >= pre_split] (power of two).  Fills blk.
+int split_f16(const float* src, int rows, int cols, size_t ld, int split_dim, int split_at, const float* pre2,
+              int pre_split, void* hi, void* lo, size_t ld16, float* blk, cudaStream_t st);
+int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, const F16Operand& B, float* C, int ldc,
+               int splits, int bn, int kb_per_chunk, void* ws, size_t ws_bytes, cudaStream_t st);
+
 }  // namespace spotv2

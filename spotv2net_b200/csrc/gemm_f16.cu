@@ -1,0 +1,469 @@
+// fp32-accurate projection GEMM on tcgen05 with fp16 operand pairs ("3xFP16").
+//
+//   C[m,n] = sum_k A(m,k) B(n,k)        A = (A_hi + A_lo) / sA,  B = (B_hi + B_lo) / sB
+//   acc   += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi   (kind::f16 MMAs, fp32 accumulate in TMEM)
+//   C      = acc * (1/sA) * (1/sB)
+//
+// Why fp16 pairs instead of tf32 pairs (gemm_tc.cu): an fp16 significand carries the same 11 bits as
+// tf32, so hi + lo still resolves 22 bits, but kind::f16 issues at twice the tf32 rate and the operands
+// take half the bytes in HBM, L2 and shared memory.  fp16's narrow exponent is handled by a power-of-two
+// scale per operand group (exact to apply and to remove): the group's largest magnitude is mapped into
+// [2^14, 2^15); elements more than ~2^17 below it lose relative precision but their ABSOLUTE error stays
+// below 2^-39 of the group maximum, far inside the 1e-5 max-norm parity budget (fp16 subnormals are
+// honoured by the tensor core).  A group is "rows of the operand below / at-or-above split_at" along its
+// M|N dimension: W_aug = [W ; u] and dP_aug = [dP | ds | dd] carry two magnitudes, x carries one.
+//
+// The accumulation-chain limit of gemm_tc.cu applies unchanged (the tensor core's fp32 adder truncates):
+// TMEM holds 128-element K chunks, eight consumer warps fold them into fp32 registers round-to-nearest.
+//
+// Kernel shape: persistent, one CTA per SM, 384 threads (warp 0 TMA, warp 1 MMA issue, warp 2 TMEM
+// allocator, warps 4-11 accumulate + epilogue), tile 128 x 256 x TBK, TBK = 64 | 32 fp16 elements.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "gemm.cuh"
+#include "tc.cuh"
+#include "tma.cuh"
+
+namespace spotv2 {
+
+namespace {
+
+constexpr int HBM_ = 128;        // UMMA M
+constexpr int HUMMA_K = 16;      // fp16
+constexpr int kHThreads = 384;
+constexpr int kHEpiWarps = 8;
+
+struct HParams {
+  int M, N, K;
+  int ldc;
+  float* C;
+  int m_tiles, n_tiles, splits, kb_per_split, kb_total, kb_per_chunk;
+  size_t split_stride;
+  const float* a_inv;   // 2 inverse scales of A's groups (null = 1)
+  const float* b_inv;
+  int a_split, b_split;
+  int scale_in_kernel;  // 0 when a split-K reduce applies the scales
+};
+
+template <int BN, int TBK, bool A_KM, bool B_KM>
+struct HSmem {
+  static constexpr int kAOp = HBM_ * TBK * 2;              // one A operand tile (hi or lo), bytes
+  static constexpr int kBOp = BN * TBK * 2;
+  static constexpr int kStage = 2 * kAOp + 2 * kBOp;
+  static constexpr int kStages = (200 * 1024) / kStage > 6 ? 6 : (200 * 1024) / kStage;
+  static constexpr int kBarOff = kStages * kStage;
+  static constexpr int kTotal = kBarOff + 256 + 1024;
+  static constexpr uint32_t kTxBytes = kStage;
+};
+
+template <int BN, int TBK, bool A_KM, bool B_KM>
+__global__ void __launch_bounds__(kHThreads, 1)
+gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                  const HParams p) {
+  using S = HSmem<BN, TBK, A_KM, B_KM>;
+  constexpr int kStages = S::kStages;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+  uint64_t* empty = full + kStages;
+  uint64_t* tfull = empty + kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  constexpr uint32_t kTmemCols = 2 * BN;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kHEpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // n fastest: the CTAs of one wave share the A rows (x / dP tiles) through L2, B (weights) is small
+  auto tile_coords = [&](int tile, int& mt, int& nt, int& sp) {
+    nt = tile % p.n_tiles;
+    const int r = tile / p.n_tiles;
+    mt = r % p.m_tiles;
+    sp = r / p.m_tiles;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int mt, nt, sp; tile_coords(tile, mt, nt, sp);
+        const int kb0 = sp * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* st = smem + stage * S::kStage;
+          mbar_expect_tx(&full[stage], S::kTxBytes);
+          const int k = kb * TBK;
+          if (A_KM) {
+            tma_load_2d(st, &tmAh, k, mt * HBM_, &full[stage]);
+            tma_load_2d(st + S::kAOp, &tmAl, k, mt * HBM_, &full[stage]);
+          } else {
+#pragma unroll
+            for (int blk = 0; blk < HBM_ / 64; ++blk) {
+              tma_load_2d(st + blk * (TBK * 128), &tmAh, mt * HBM_ + blk * 64, k, &full[stage]);
+              tma_load_2d(st + S::kAOp + blk * (TBK * 128), &tmAl, mt * HBM_ + blk * 64, k, &full[stage]);
+            }
+          }
+          unsigned char* sb = st + 2 * S::kAOp;
+          if (B_KM) {
+            tma_load_2d(sb, &tmBh, k, nt * BN, &full[stage]);
+            tma_load_2d(sb + S::kBOp, &tmBl, k, nt * BN, &full[stage]);
+          } else {
+#pragma unroll
+            for (int blk = 0; blk < BN / 64; ++blk) {
+              tma_load_2d(sb + blk * (TBK * 128), &tmBh, nt * BN + blk * 64, k, &full[stage]);
+              tma_load_2d(sb + S::kBOp + blk * (TBK * 128), &tmBl, nt * BN + blk * 64, k, &full[stage]);
+            }
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      // instruction descriptor: D = f32 (1 << 4), A/B = f16 (0), majors, N >> 3, M >> 4
+      constexpr uint32_t idesc = (1u << 4) | ((A_KM ? 0u : 1u) << 15) | ((B_KM ? 0u : 1u) << 16) |
+                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(HBM_ >> 4) << 24);
+      // K-major: rows of TBK*2 bytes (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B), 8-row atoms.
+      // MN-major: 64-element (128 B) rows along M|N, 8 k-rows per 1024 B atom (SBO), LBO = one 64-wide block.
+      constexpr uint32_t k_sbo = 8 * TBK * 2, k_lt = (TBK == 64) ? 2 : 4;
+      constexpr uint32_t a_lbo = A_KM ? 16 : TBK * 128, b_lbo = B_KM ? 16 : TBK * 128;
+      constexpr uint32_t a_sbo = A_KM ? k_sbo : 1024, b_sbo = B_KM ? k_sbo : 1024;
+      constexpr uint32_t a_lt = A_KM ? k_lt : 2, b_lt = B_KM ? k_lt : 2;
+      constexpr uint32_t a_kstep = A_KM ? HUMMA_K * 2 : HUMMA_K * 128;   // bytes per k-step of 16
+      constexpr uint32_t b_kstep = B_KM ? HUMMA_K * 2 : HUMMA_K * 128;
+      int stage = 0; uint32_t phase = 0;
+      uint32_t chunk_ctr = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int mt, nt, sp; tile_coords(tile, mt, nt, sp);
+        const int kb0 = sp * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kc = kb0; kc < kb1; kc += p.kb_per_chunk, ++chunk_ctr) {
+          const int as = chunk_ctr & 1;
+          mbar_wait(&tempty[as], ((chunk_ctr >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+          uint32_t accum = 0;
+          const int kce = min(kb1, kc + p.kb_per_chunk);
+          for (int kb = kc; kb < kce; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * S::kStage);
+            const uint32_t sb = sa + 2 * S::kAOp;
+#pragma unroll
+            for (int ks = 0; ks < TBK / HUMMA_K; ++ks) {
+              const uint64_t ah = make_desc(sa + ks * a_kstep, a_lbo, a_sbo, a_lt);
+              const uint64_t al = make_desc(sa + S::kAOp + ks * a_kstep, a_lbo, a_sbo, a_lt);
+              const uint64_t bh = make_desc(sb + ks * b_kstep, b_lbo, b_sbo, b_lt);
+              const uint64_t bl = make_desc(sb + S::kBOp + ks * b_kstep, b_lbo, b_sbo, b_lt);
+              umma_f16(d_tmem, al, bh, idesc, accum);
+              accum = 1;
+              umma_f16(d_tmem, ah, bl, idesc, 1);
+              umma_f16(d_tmem, ah, bh, idesc, 1);
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull[as]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== accumulate + epilogue =====================
+    constexpr int HALF = BN / 2;
+    const int q = warp & 3;
+    const int ch = (warp - 4) >> 2;
+    uint32_t chunk_ctr = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int mt, nt, sp; tile_coords(tile, mt, nt, sp);
+      const int kb0 = sp * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      float acc[HALF];
+#pragma unroll
+      for (int e = 0; e < HALF; ++e) acc[e] = 0.f;
+      for (int kc = kb0; kc < kb1; kc += p.kb_per_chunk, ++chunk_ctr) {
+        const int as = chunk_ctr & 1;
+        mbar_wait(&tfull[as], (chunk_ctr >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + ch * HALF);
+#pragma unroll
+        for (int c0 = 0; c0 < HALF; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) acc[c0 + e] += __uint_as_float(r[e]);   // round-to-nearest adds
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+      }
+      const int row = mt * HBM_ + q * 32 + lane;
+      const int col0 = nt * BN + ch * HALF;
+      if (row < p.M && col0 < p.N) {
+        if (p.scale_in_kernel) {      // powers of two: exact
+          const float ra = p.a_inv ? p.a_inv[row >= p.a_split ? 1 : 0] : 1.f;
+          const float cb0 = ra * (p.b_inv ? p.b_inv[0] : 1.f), cb1 = ra * (p.b_inv ? p.b_inv[1] : 1.f);
+#pragma unroll
+          for (int e = 0; e < HALF; ++e) acc[e] *= (col0 + e >= p.b_split) ? cb1 : cb0;
+        }
+        float* crow = p.C + (size_t)sp * p.split_stride + (size_t)row * p.ldc + col0;
+        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                            (p.split_stride % 4 == 0) && (col0 + HALF <= p.N);
+        if (vec_ok) {
+#pragma unroll
+          for (int v4 = 0; v4 < HALF / 4; ++v4)
+            *reinterpret_cast<float4*>(crow + 4 * v4) =
+                make_float4(acc[4 * v4], acc[4 * v4 + 1], acc[4 * v4 + 2], acc[4 * v4 + 3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < HALF; ++e)
+            if (col0 + e < p.N) crow[e] = acc[e];
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+__global__ void f16_splitk_reduce_kernel(const float* __restrict__ ws, int splits, size_t split_stride, int M, int N,
+                                         float* __restrict__ C, int ldc, const float* __restrict__ a_inv, int a_split,
+                                         const float* __restrict__ b_inv, int b_split) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)M * N) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += ws[(size_t)z * split_stride + idx];
+  const int m = (int)(idx / N), n = (int)(idx - (size_t)m * N);
+  const float f = (a_inv ? a_inv[m >= a_split ? 1 : 0] : 1.f) * (b_inv ? b_inv[n >= b_split ? 1 : 0] : 1.f);
+  C[(size_t)m * ldc + n] = s * f;
+}
+
+template <int BN, int TBK, bool A_KM, bool B_KM>
+int launch_h(const CUtensorMap& tAh, const CUtensorMap& tAl, const CUtensorMap& tBh, const CUtensorMap& tBl,
+             const HParams& p, cudaStream_t st) {
+  using S = HSmem<BN, TBK, A_KM, B_KM>;
+  auto kern = gemm3x_f16_kernel<BN, TBK, A_KM, B_KM>;
+  SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+  int grid = sm_count();
+  const int total = p.m_tiles * p.n_tiles * p.splits;
+  if (grid > total) grid = total;
+  kern<<<grid, kHThreads, S::kTotal, st>>>(tAh, tAl, tBh, tBl, p);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
+// ---- operand preparation ------------------------------------------------------------------------------
+// Scale block (8 floats per operand): [0,1] bit patterns of the group maxima of |x * pre|, [2,3] inverse
+// scales, [4,5] scales.
+__device__ __forceinline__ float scale_from_amax(float amax) {
+  if (!(amax > 0.f) || !(amax < INFINITY)) return 1.f;
+  int ex;
+  frexpf(amax, &ex);                         // amax = m * 2^ex, m in [0.5, 1)
+  return exp2f((float)(15 - ex));            // amax * scale in [2^14, 2^15)
+}
+
+__global__ void amax_kernel(const float* __restrict__ src, int rows, int cols, size_t ld, int split_dim, int split_at,
+                            const float* __restrict__ pre2, int pre_split, unsigned* __restrict__ out_bits) {
+  float m0 = 0.f, m1 = 0.f;
+  const size_t total = (size_t)rows * cols;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / cols), c = (int)(idx - (size_t)r * cols);
+    float v = fabsf(src[(size_t)r * ld + c]);
+    if (pre2) v *= pre2[r >= pre_split ? 1 : 0];
+    const bool g1 = (split_dim == 0 ? r : c) >= split_at;
+    if (g1) m1 = fmaxf(m1, v); else m0 = fmaxf(m0, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (m0 > 0.f) atomicMax(out_bits, __float_as_uint(m0));
+    if (m1 > 0.f) atomicMax(out_bits + 1, __float_as_uint(m1));
+  }
+}
+
+// hi = fp16(x * pre * s), lo = fp16(x * pre * s - hi); s from the group maxima (optionally widened by bound).
+__global__ void split_f16_kernel(const float* __restrict__ src, int rows, int cols, size_t ld, int split_dim,
+                                 int split_at, const float* __restrict__ pre2, int pre_split, float bound,
+                                 __half* __restrict__ hi, __half* __restrict__ lo, size_t ld16, float* __restrict__ blk,
+                                 int vec4) {
+  const unsigned* bits = reinterpret_cast<const unsigned*>(blk);
+  const float s0 = scale_from_amax(__uint_as_float(bits[0]) * bound);
+  const float s1 = scale_from_amax(__uint_as_float(bits[1]) * bound);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    blk[2] = 1.f / s0; blk[3] = 1.f / s1; blk[4] = s0; blk[5] = s1;
+  }
+  auto conv = [&](float x, int r, int c, __half& h, __half& l) {
+    if (pre2) x *= pre2[r >= pre_split ? 1 : 0];
+    x *= ((split_dim == 0 ? r : c) >= split_at) ? s1 : s0;
+    h = __float2half_rn(x);
+    l = __float2half_rn(x - __half2float(h));
+  };
+  if (vec4) {
+    const int c4 = cols / 4;
+    const size_t total = (size_t)rows * c4;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+      const int r = (int)(idx / c4), c = 4 * (int)(idx - (size_t)r * c4);
+      const float4 v = *reinterpret_cast<const float4*>(src + (size_t)r * ld + c);
+      __half h[4], l[4];
+      conv(v.x, r, c, h[0], l[0]); conv(v.y, r, c + 1, h[1], l[1]);
+      conv(v.z, r, c + 2, h[2], l[2]); conv(v.w, r, c + 3, h[3], l[3]);
+      *reinterpret_cast<uint2*>(hi + (size_t)r * ld16 + c) = *reinterpret_cast<uint2*>(h);
+      *reinterpret_cast<uint2*>(lo + (size_t)r * ld16 + c) = *reinterpret_cast<uint2*>(l);
+    }
+  } else {
+    const size_t total = (size_t)rows * cols;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+      const int r = (int)(idx / cols), c = (int)(idx - (size_t)r * cols);
+      __half h, l;
+      conv(src[(size_t)r * ld + c], r, c, h, l);
+      hi[(size_t)r * ld16 + c] = h;
+      lo[(size_t)r * ld16 + c] = l;
+    }
+  }
+}
+
+}  // namespace
+
+__global__ void amax_flat_kernel(const float* __restrict__ src, size_t n, unsigned* __restrict__ out_bits) {
+  float m = 0.f;
+  const size_t n4 = n / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (size_t k = n4 * 4; k < n; ++k) m = fmaxf(m, fabsf(src[k]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
+}
+
+int amax_flat(const float* src, size_t n, float* blk, cudaStream_t st) {
+  SPOTV2_CUDA_OK(cudaMemsetAsync(blk, 0, 8 * sizeof(float), st));
+  const bool al = aligned16(src);
+  const size_t work = al ? n / 4 : 0;
+  if (!al) {        // rare: unaligned view; fall back to the generic kernel as a 1 x n matrix
+    amax_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 4096), 256, 0, st>>>(src, 1, (int)n, n, 0, 1 << 30, nullptr, 0,
+                                                                                  reinterpret_cast<unsigned*>(blk));
+  } else {
+    amax_flat_kernel<<<(unsigned)std::min<size_t>((std::max<size_t>(work, 1) + 255) / 256, 8 * 148), 256, 0, st>>>(
+        src, n, reinterpret_cast<unsigned*>(blk));
+  }
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
+int split_f16(const float* src, int rows, int cols, size_t ld, int split_dim, int split_at, const float* pre2,
+              int pre_split, void* hi, void* lo, size_t ld16, float* blk, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return SPOTV2_OK;
+  SPOTV2_CUDA_OK(cudaMemsetAsync(blk, 0, 8 * sizeof(float), st));
+  const size_t total = (size_t)rows * cols;
+  const unsigned blocks = (unsigned)std::min<size_t>((total + 1023) / 1024, 16 * 148);
+  amax_kernel<<<blocks, 256, 0, st>>>(src, rows, cols, ld, split_dim, split_at, pre2, pre_split,
+                                      reinterpret_cast<unsigned*>(blk));
+  const int vec4 = (cols % 4 == 0) && (ld % 4 == 0) && (ld16 % 4 == 0) && aligned16(src) &&
+                   ((reinterpret_cast<uintptr_t>(hi) & 7) == 0) && ((reinterpret_cast<uintptr_t>(lo) & 7) == 0);
+  split_f16_kernel<<<blocks, 256, 0, st>>>(src, rows, cols, ld, split_dim, split_at, pre2, pre_split, 1.f,
+                                           static_cast<__half*>(hi), static_cast<__half*>(lo), ld16, blk, vec4);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
+// C[M,N] = A . B^T with operands pre-split into scaled fp16 pairs.  bn: 256 -> TBK 64, 256 + 16 -> TBK 32.
+int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, const F16Operand& B, float* C, int ldc,
+               int splits, int bn, int kb_per_chunk, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int TBK = (bn & 16) ? 32 : 64;
+  bn &= ~16;
+  if (!tma_available()) return fail(SPOTV2_ERR_NO_DEVICE, "tensor-core GEMM: TMA descriptor encoding is not available");
+  if (A.ld % 8 != 0 || B.ld % 8 != 0 || !aligned16(A.hi) || !aligned16(A.lo) || !aligned16(B.hi) || !aligned16(B.lo))
+    return fail(SPOTV2_ERR_INVALID_ARG, "fp16 GEMM operands need 16-byte aligned bases and leading dimensions % 8 == 0");
+  HParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.m_tiles = (M + HBM_ - 1) / HBM_;
+  p.n_tiles = (N + bn - 1) / bn;
+  p.kb_total = (K + TBK - 1) / TBK;
+  if (splits < 1) splits = 1;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.kb_per_chunk = kb_per_chunk < 1 ? 128 / TBK : kb_per_chunk;
+  p.C = C; p.ldc = ldc; p.split_stride = 0;
+  p.a_inv = A.inv; p.b_inv = B.inv; p.a_split = A.split_at; p.b_split = B.split_at;
+  p.scale_in_kernel = 1;
+  if (p.splits > 1) {
+    const size_t need = (size_t)p.splits * M * N * sizeof(float);
+    if (!ws || ws_bytes < need)
+      return fail(SPOTV2_ERR_WORKSPACE, "split-K tensor-core GEMM needs %zu B of workspace, got %zu", need, ws_bytes);
+    p.C = static_cast<float*>(ws); p.ldc = N; p.split_stride = (size_t)M * N;
+    p.scale_in_kernel = 0;
+  }
+  CUtensorMap tAh, tAl, tBh, tBl;
+  int rc;
+  // K-major operand: tensor [rows = M|N, cols = K], box TBK(k) x tile rows (rows of 128 or 64 bytes).
+  // MN-major operand: tensor [rows = K, cols = M|N], box 64(m|n) x TBK(k); one box per 64-wide block.
+  const CUtensorMapSwizzle kSw = TBK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUtensorMapSwizzle mnSw = CU_TENSOR_MAP_SWIZZLE_128B;
+  if (a_kc) {
+    if ((rc = make_tmap_f16(&tAh, A.hi, M, K, A.ld, TBK, HBM_, kSw))) return rc;
+    if ((rc = make_tmap_f16(&tAl, A.lo, M, K, A.ld, TBK, HBM_, kSw))) return rc;
+  } else {
+    if ((rc = make_tmap_f16(&tAh, A.hi, K, M, A.ld, 64, TBK, mnSw))) return rc;
+    if ((rc = make_tmap_f16(&tAl, A.lo, K, M, A.ld, 64, TBK, mnSw))) return rc;
+  }
+  if (b_kc) {
+    if ((rc = make_tmap_f16(&tBh, B.hi, N, K, B.ld, TBK, bn, kSw))) return rc;
+    if ((rc = make_tmap_f16(&tBl, B.lo, N, K, B.ld, TBK, bn, kSw))) return rc;
+  } else {
+    if ((rc = make_tmap_f16(&tBh, B.hi, K, N, B.ld, 64, TBK, mnSw))) return rc;
+    if ((rc = make_tmap_f16(&tBl, B.lo, K, N, B.ld, 64, TBK, mnSw))) return rc;
+  }
+#define SPOTV2_H(BN_, TBK_, AK, BK_) rc = launch_h<BN_, TBK_, AK, BK_>(tAh, tAl, tBh, tBl, p, st)
+#define SPOTV2_H_MAJ(BN_, TBK_)                            \
+  do {                                                     \
+    if (a_kc && b_kc) SPOTV2_H(BN_, TBK_, true, true);     \
+    else if (a_kc) SPOTV2_H(BN_, TBK_, true, false);       \
+    else if (b_kc) SPOTV2_H(BN_, TBK_, false, true);       \
+    else SPOTV2_H(BN_, TBK_, false, false);                \
+  } while (0)
+  if (bn == 256 && TBK == 64) SPOTV2_H_MAJ(256, 64);
+  else if (bn == 256 && TBK == 32) SPOTV2_H_MAJ(256, 32);
+  else if (bn == 128 && TBK == 64) SPOTV2_H_MAJ(128, 64);
+  else return fail(SPOTV2_ERR_INVALID_ARG, "bn must be 128, 256 or 256+16");
+#undef SPOTV2_H_MAJ
+#undef SPOTV2_H
+  if (rc) return rc;
+  if (p.splits > 1) {
+    const size_t total = (size_t)M * N;
+    f16_splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.C, p.splits, p.split_stride, M, N, C, ldc,
+                                                                             A.inv, A.split_at, B.inv, B.split_at);
+    SPOTV2_CUDA_OK(cudaGetLastError());
+  }
+  return SPOTV2_OK;
+}
+
+}  // namespace spotv2

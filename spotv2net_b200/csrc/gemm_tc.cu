@@ -23,6 +23,7 @@
 // kStages-deep shared-memory ring, two TMEM stages.  Optional split-K writes
 // partials to a workspace that a fixed-order reduce sums (deterministic).
 #include "gemm.cuh"
+#include "tc.cuh"
 #include "tma.cuh"
 
 namespace spotv2 {
@@ -39,67 +40,6 @@ struct TcParams {
   int m_tiles, n_tiles, splits, kb_per_split, kb_total, kb_per_chunk;
   size_t split_stride;   // elements between split partials (0 when splits == 1)
 };
-
-// ---- PTX wrappers -----------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {   // implies tcgen05.fence::before_thread_sync
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
-      "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t.reg .b32 R;\n\telect.sync R|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), version 1.
-//   K-major  (layout SWIZZLE_128B = 2): rows of 128 B (32 tf32 along K), 16-byte chunks XOR-swizzled by
-//             row % 8; 8-row atoms of 1024 B; SBO = 1024 B between row groups, LBO unused.
-//   MN-major (layout SWIZZLE_128B_BASE32B = 1, the only legal one for 32-bit MN-major operands): rows of
-//             128 B (32 tf32 along M|N), 32-byte chunks XOR-swizzled by row % 4; 4 k-rows per 512 B
-//             atom; SBO = 512 B between k atoms, LBO = bytes between 32-wide M|N blocks.
-//             TMA writes exactly this with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                              uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;     // descriptor version (Blackwell)
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
 
 template <int BN, int TBK, bool A_KM, bool B_KM>
 struct TcSmem {
@@ -444,6 +384,24 @@ extern "C" int spotv2_diag_gemm(int a_kc, int b_kc, int M, int N, int K, const f
   using namespace spotv2;
   cudaStream_t st = as_stream(stream);
   if (algo == 1) return sgemm_simt(a_kc, b_kc, M, N, K, A, lda, B, ldb, C, ldc, splits, ws, ws_bytes, st);
+  if (algo == 3) {
+    // fp16-pair path: [A_hi | A_lo | B_hi | B_lo | scale blocks | split-K partials], per-tensor scales
+    const int a_rows = a_kc ? M : K, a_cols = a_kc ? K : M, b_rows = b_kc ? N : K, b_cols = b_kc ? K : N;
+    const int lda16 = ld16_of(a_cols), ldb16 = ld16_of(b_cols);
+    const size_t a_bytes = round_up((size_t)a_rows * lda16 * 2, 256), b_bytes = round_up((size_t)b_rows * ldb16 * 2, 256);
+    const size_t need = 2 * a_bytes + 2 * b_bytes + 256;
+    if (!ws || ws_bytes < need) return fail(SPOTV2_ERR_WORKSPACE, "diag_gemm needs at least %zu B of workspace", need);
+    unsigned char* w = static_cast<unsigned char*>(ws);
+    float* blk = reinterpret_cast<float*>(w + 2 * a_bytes + 2 * b_bytes);
+    const int none = 0x7fffffff;
+    if (int rc = split_f16(A, a_rows, a_cols, lda, 0, none, nullptr, 0, w, w + a_bytes, lda16, blk, st)) return rc;
+    if (int rc = split_f16(B, b_rows, b_cols, ldb, 0, none, nullptr, 0, w + 2 * a_bytes, w + 2 * a_bytes + b_bytes, ldb16,
+                           blk + kScaleBlockFloats, st))
+      return rc;
+    F16Operand opA{w, w + a_bytes, lda16, blk + 2, none};
+    F16Operand opB{w + 2 * a_bytes, w + 2 * a_bytes + b_bytes, ldb16, blk + kScaleBlockFloats + 2, none};
+    return gemm3x_f16(a_kc, b_kc, M, N, K, opA, opB, C, ldc, splits, bn, kb_per_chunk, w + need, ws_bytes - need, st);
+  }
   // workspace layout: [A_hi | A_lo | B_hi | B_lo | split-K partials]
   const size_t a_elems = (size_t)(a_kc ? M : K) * lda, b_elems = (size_t)(b_kc ? N : K) * ldb;
   const size_t a_bytes = round_up(a_elems * 4, 256), b_bytes = round_up(b_elems * 4, 256);

@@ -144,20 +144,23 @@ class _GatLayerFn(torch.autograd.Function):
         ws_f, _, _ = _workspace(desc)
         ws = torch.empty(ws_f, device=dev, dtype=torch.uint8)
         P_aug = torch.empty(n, desc.ldp, device=dev, dtype=torch.float32)
-        # tensor-core path: split x into tf32 hi/lo once; the weight-gradient GEMM reuses the pair
-        x_split = None
-        if lib.spotv2_gat_uses_tensor_cores(C.byref(desc)) and x.data_ptr() % 16 == 0:
-            x_split = torch.empty(2, n, x.shape[1], device=dev, dtype=torch.float32)
-            check(lib.spotv2_split_tf32(ptr(x), ptr(x_split[0]), ptr(x_split[1]), x.numel(), st), "spotv2_split_tf32")
-        check(lib.spotv2_proj_fwd(C.byref(desc), ptr(x), ptr(x_split[0]) if x_split is not None else None,
-                                  ptr(x_split[1]) if x_split is not None else None, ptr(W_aug), ptr(P_aug), ptr(ws),
+        # tensor-core path: x becomes an fp16 operand pair once; the weight-gradient GEMM reuses it
+        x16 = x_blk = None
+        if lib.spotv2_gat_uses_tensor_cores(C.byref(desc)):
+            ld16 = lib.spotv2_gat_ld16(x.shape[1])
+            x16 = torch.empty(2, n, ld16, device=dev, dtype=torch.float16)
+            x_blk = torch.empty(8, device=dev, dtype=torch.float32)
+            check(lib.spotv2_split_f16(ptr(x), n, x.shape[1], x.shape[1], 0, 0, ptr(x16[0]), ptr(x16[1]), ld16,
+                                       ptr(x_blk), st), "spotv2_split_f16")
+        check(lib.spotv2_proj_fwd(C.byref(desc), ptr(x), ptr(x16[0]) if x16 is not None else None,
+                                  ptr(x16[1]) if x16 is not None else None, ptr(x_blk), ptr(W_aug), ptr(P_aug), ptr(ws),
                                   ws_f, st), "spotv2_proj_fwd")
         out = torch.empty(n, HC if concat else Cc, device=dev, dtype=torch.float32)
         alpha = torch.empty(topo.B, H, topo.N, topo.N, device=dev, dtype=torch.float32) if want_alpha else None
         check(lib.spotv2_gat_attn_fwd(C.byref(desc), ptr(P_aug), ptr(ea), ptr(topo.table) if Fe else None, ptr(v),
                                       ptr(bias_c), ptr(out), ptr(alpha), st), "spotv2_gat_attn_fwd")
         ctx.desc, ctx.topo, ctx.Fe, ctx.has_bias = desc, topo, Fe, bias is not None
-        ctx.save_for_backward(x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x_split)
+        ctx.save_for_backward(x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk)
         if want_alpha:
             ctx.mark_non_differentiable(alpha)
             return out, alpha
@@ -166,7 +169,7 @@ class _GatLayerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, _dalpha=None):
         lib = _lib.load()
-        x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x_split = ctx.saved_tensors
+        x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk = ctx.saved_tensors
         desc, topo, Fe = ctx.desc, ctx.topo, ctx.Fe
         if ctx.needs_input_grad[1]:
             raise SpotV2Error("gradient w.r.t. edge_attr is not provided (the reference never needs it)")
@@ -177,25 +180,31 @@ class _GatLayerFn(torch.autograd.Function):
         dout = dout.contiguous()
         _, ws_a, ws_p = _workspace(desc)
         ws = torch.empty(max(ws_a, ws_p), device=dev, dtype=torch.uint8)
-        # on the tensor-core path the attention backward emits dP already split into tf32 hi/lo
+        # on the tensor-core path the attention backward emits dP directly as the GEMMs' fp16 operand pair
         tc = bool(lib.spotv2_gat_uses_tensor_cores(C.byref(desc)))
-        dP_aug = torch.empty_like(P_aug)
-        dP_lo = torch.empty_like(P_aug) if tc else None
+        dP_aug = dP16 = dp_blk = None
+        if tc:
+            dP16 = torch.empty(2, P_aug.shape[0], lib.spotv2_gat_ld16(HC + 2 * H), device=dev, dtype=torch.float16)
+            dp_blk = torch.empty(8, device=dev, dtype=torch.float32)
+        else:
+            dP_aug = torch.empty_like(P_aug)
+        ph, pl = (dP16[0], dP16[1]) if tc else (None, None)
         dv = torch.empty(H, Fe, device=dev, dtype=torch.float32) if Fe else None
         dbias = torch.empty(dout.shape[1], device=dev, dtype=torch.float32) if ctx.has_bias else None
         check(lib.spotv2_gat_attn_bwd(C.byref(desc), ptr(P_aug), ptr(ea), ptr(topo.table) if Fe else None, ptr(v),
-                                      ptr(dout), ptr(dP_aug), ptr(dP_lo), ptr(dv), ptr(dbias), ptr(ws), ws.numel(), st),
-              "spotv2_gat_attn_bwd")
+                                      ptr(dout), ptr(dP_aug), ptr(ph), ptr(pl), ptr(dp_blk), ptr(dv), ptr(dbias),
+                                      ptr(ws), ws.numel(), st), "spotv2_gat_attn_bwd")
         dW_aug = torch.empty_like(W_aug)
-        xh = x_split[0] if x_split is not None else None
-        xl = x_split[1] if x_split is not None else None
-        check(lib.spotv2_proj_bwd_weight(C.byref(desc), ptr(x), ptr(xh), ptr(xl), ptr(dP_aug), ptr(dP_lo), ptr(dW_aug),
-                                         ptr(ws), ws.numel(), st), "spotv2_proj_bwd_weight")
+        xh = x16[0] if x16 is not None else None
+        xl = x16[1] if x16 is not None else None
+        check(lib.spotv2_proj_bwd_weight(C.byref(desc), ptr(x), ptr(xh), ptr(xl), ptr(x_blk), ptr(dP_aug), ptr(ph),
+                                         ptr(pl), ptr(dp_blk), ptr(dW_aug), ptr(ws), ws.numel(), st),
+              "spotv2_proj_bwd_weight")
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            check(lib.spotv2_proj_bwd_input(C.byref(desc), ptr(dP_aug), ptr(dP_lo), ptr(W_aug), ptr(dx), ptr(ws),
-                                            ws.numel(), st), "spotv2_proj_bwd_input")
+            check(lib.spotv2_proj_bwd_input(C.byref(desc), ptr(dP_aug), ptr(ph), ptr(pl), ptr(dp_blk), ptr(W_aug),
+                                            ptr(dx), ptr(ws), ws.numel(), st), "spotv2_proj_bwd_input")
         dW = torch.empty_like(W)
         da_src = torch.empty_like(a_src)
         da_dst = torch.empty_like(a_dst)

@@ -120,43 +120,92 @@ def test_fold_and_unfold_entry_points(cuda_lib):
         assert relerr(o, ref[k]) < 1e-6, k
 
 
+def f16_pair(cuda_lib, t, split_dim=0, split_at=0):
+    """fp16 operand pair of a [rows, cols] fp32 device tensor: (pair [2, rows, ld16], scale block [8])."""
+    rows, cols = t.shape
+    ld16 = cuda_lib.spotv2_gat_ld16(cols)
+    pair = torch.zeros(2, rows, ld16, device=DEV, dtype=torch.float16)
+    blk = torch.zeros(8, device=DEV)
+    check(cuda_lib.spotv2_split_f16(t.data_ptr(), rows, cols, t.stride(0), split_dim, split_at, ptr(pair[0]), ptr(pair[1]), ld16,
+                                    ptr(blk), st()), "split_f16")
+    return pair, blk
+
+
+def pair_value(pair, blk, cols, split_at=None):
+    """Reconstruct the fp32 values a pair represents (float64 arithmetic)."""
+    val = (pair[0].double() + pair[1].double())[:, :cols]
+    inv = blk[2:4].double()
+    if split_at is None:
+        return val * inv[0]
+    scale = torch.where(torch.arange(cols, device=pair.device) >= split_at, inv[1], inv[0])
+    return val * scale
+
+
 @pytest.mark.parametrize("algo", [1, 2], ids=["cuda_cores", "tcgen05"])
 @pytest.mark.parametrize("shape", [(2, 30, 1260, 6, 500), (3, 7, 9, 3, 5), (5, 30, 100, 8, 33), (1, 1, 3, 1, 1),
                                    (40, 30, 2048, 8, 256), (64, 30, 256, 2, 50)])
 def test_projection_gemms(cuda_lib, shape, algo):
     B, N, Fin, H, C_ = shape
-    if algo == 2 and Fin % 4:
-        pytest.skip("TMA needs a 16-byte row pitch; such shapes take the CUDA-core kernel")
-    n, n_aug = B * N, H * C_ + 2 * H
+    n, n_aug, HC = B * N, H * C_ + 2 * H, H * C_
     ldp = cuda_lib.spotv2_gat_ldp(H, C_)
     d = GatDesc(B, N, Fin, 0, H, C_, 0, 0, 0.2, ldp, algo, 0)
     torch.manual_seed(1)
     x, W_aug, dP = torch.randn(n, Fin), torch.randn(n_aug, Fin), torch.randn(n, ldp)
+    # the folded attention rows of W_aug and the ds|dd columns of dP_aug live on their own scale
+    W_aug[HC:] *= 37.0
+    dP[:, HC:] *= 1e-3
     xg, Wg, dPg = x.to(DEV), W_aug.to(DEV), dP.to(DEV)
     a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
     check(cuda_lib.spotv2_gat_workspace_bytes(C.byref(d), C.byref(a), C.byref(b), C.byref(c)), "ws")
     ws = torch.empty(max(a.value, c.value), dtype=torch.uint8, device=DEV)
+
+    def grouped_relerr(got, ref, split, dim):
+        lo = relerr(got.narrow(dim, 0, split), ref.narrow(dim, 0, split))
+        hi = relerr(got.narrow(dim, split, got.shape[dim] - split), ref.narrow(dim, split, got.shape[dim] - split))
+        return max(lo, hi)
+
     P = torch.zeros(n, ldp, device=DEV)
-    check(cuda_lib.spotv2_proj_fwd(C.byref(d), ptr(xg), None, None, ptr(Wg), ptr(P), ptr(ws), ws.numel(), st()), "proj_fwd")
-    assert relerr(P[:, :n_aug], x.double() @ W_aug.double().t()) < TOL
+    check(cuda_lib.spotv2_proj_fwd(C.byref(d), ptr(xg), None, None, None, ptr(Wg), ptr(P), ptr(ws), ws.numel(), st()), "proj_fwd")
+    assert grouped_relerr(P[:, :n_aug], x.double() @ W_aug.double().t(), HC, 1) < TOL
     dW = torch.empty(n_aug, Fin, device=DEV)
-    check(cuda_lib.spotv2_proj_bwd_weight(C.byref(d), ptr(xg), None, None, ptr(dPg), None, ptr(dW), ptr(ws), ws.numel(), st()), "bwd_w")
-    assert relerr(dW, dP[:, :n_aug].double().t() @ x.double()) < TOL
+    check(cuda_lib.spotv2_proj_bwd_weight(C.byref(d), ptr(xg), None, None, None, ptr(dPg), None, None, None, ptr(dW), ptr(ws),
+                                          ws.numel(), st()), "bwd_w")
+    assert grouped_relerr(dW, dP[:, :n_aug].double().t() @ x.double(), HC, 0) < TOL
     dX = torch.empty(n, Fin, device=DEV)
-    check(cuda_lib.spotv2_proj_bwd_input(C.byref(d), ptr(dPg), None, ptr(Wg), ptr(dX), ptr(ws), ws.numel(), st()), "bwd_x")
+    check(cuda_lib.spotv2_proj_bwd_input(C.byref(d), ptr(dPg), None, None, None, ptr(Wg), ptr(dX), ptr(ws), ws.numel(), st()), "bwd_x")
     assert relerr(dX, dP[:, :n_aug].double() @ W_aug.double()) < TOL
-    if algo == 2:       # the same products from caller-provided tf32 hi/lo pairs
+    if algo == 2:       # the same products from caller-provided fp16 operand pairs
         assert cuda_lib.spotv2_gat_uses_tensor_cores(C.byref(d)) == 1
-        xs, ps = torch.empty(2, *xg.shape, device=DEV), torch.empty(2, *dPg.shape, device=DEV)
-        check(cuda_lib.spotv2_split_tf32(ptr(xg), ptr(xs[0]), ptr(xs[1]), xg.numel(), st()), "split x")
-        check(cuda_lib.spotv2_split_tf32(ptr(dPg), ptr(ps[0]), ptr(ps[1]), dPg.numel(), st()), "split dP")
-        assert torch.equal(xs[0] + xs[1], xg) or relerr(xs[0] + xs[1], xg) < 1e-6
+        xs, xblk = f16_pair(cuda_lib, xg)
+        ps, pblk = f16_pair(cuda_lib, dPg[:, :n_aug], split_dim=1, split_at=HC)
+        assert relerr(pair_value(xs, xblk, Fin), x) < 1e-6
+        assert relerr(pair_value(ps, pblk, n_aug, HC), dP[:, :n_aug]) < 1e-6
+        assert xs[0].abs().max() < 32800 and xs[0].abs().max() >= 16384       # largest magnitude sits in [2^14, 2^15]
         P2, dW2, dX2 = torch.zeros_like(P), torch.empty_like(dW), torch.empty_like(dX)
-        check(cuda_lib.spotv2_proj_fwd(C.byref(d), ptr(xg), ptr(xs[0]), ptr(xs[1]), ptr(Wg), ptr(P2), ptr(ws), ws.numel(), st()), "proj_fwd")
-        check(cuda_lib.spotv2_proj_bwd_weight(C.byref(d), ptr(xg), ptr(xs[0]), ptr(xs[1]), ptr(ps[0]), ptr(ps[1]), ptr(dW2),
-                                              ptr(ws), ws.numel(), st()), "bwd_w")
-        check(cuda_lib.spotv2_proj_bwd_input(C.byref(d), ptr(ps[0]), ptr(ps[1]), ptr(Wg), ptr(dX2), ptr(ws), ws.numel(), st()), "bwd_x")
+        check(cuda_lib.spotv2_proj_fwd(C.byref(d), ptr(xg), ptr(xs[0]), ptr(xs[1]), ptr(xblk), ptr(Wg), ptr(P2), ptr(ws),
+                                       ws.numel(), st()), "proj_fwd")
+        check(cuda_lib.spotv2_proj_bwd_weight(C.byref(d), ptr(xg), ptr(xs[0]), ptr(xs[1]), ptr(xblk), None, ptr(ps[0]),
+                                              ptr(ps[1]), ptr(pblk), ptr(dW2), ptr(ws), ws.numel(), st()), "bwd_w")
+        check(cuda_lib.spotv2_proj_bwd_input(C.byref(d), None, ptr(ps[0]), ptr(ps[1]), ptr(pblk), ptr(Wg), ptr(dX2), ptr(ws),
+                                             ws.numel(), st()), "bwd_x")
         assert torch.equal(P2[:, :n_aug], P[:, :n_aug]) and torch.equal(dW2, dW) and torch.equal(dX2, dX)
+
+
+def test_f16_pair_keeps_absolute_precision_over_a_wide_dynamic_range(cuda_lib):
+    """Operands spanning 12 decades: elements far below the group maximum lose relative precision in the
+    pair but not absolute precision, so the max-norm error of the product stays at the fp32 level."""
+    torch.manual_seed(5)
+    M, N, K = 256, 300, 640
+    A = torch.randn(M, K) * torch.logspace(-9, 3, K)[None, :]
+    Bm = torch.randn(N, K) * torch.logspace(2, -8, N)[:, None]
+    ref = A.double() @ Bm.double().t()
+    Ag, Bg = A.to(DEV), Bm.to(DEV)
+    Cg = torch.empty(M, N, device=DEV)
+    ws = torch.empty(1 << 24, dtype=torch.uint8, device=DEV)
+    check(cuda_lib.spotv2_diag_gemm(1, 1, M, N, K, ptr(Ag), K, ptr(Bg), K, ptr(Cg), N, 3, 1, 256, 0, ptr(ws), ws.numel(),
+                                    st()), "diag_gemm f16")
+    assert relerr(Cg, ref) < 3e-6
+    assert relerr(Cg, ref) < 4 * relerr((A @ Bm.t()), ref) + 1e-6          # on par with an fp32 CPU matmul
 
 
 GEMM_CASES = [
@@ -173,8 +222,9 @@ GEMM_CASES = [
 
 @pytest.mark.parametrize("case", GEMM_CASES, ids=[f"{'KM'[c[0]]}{'KM'[c[1]]}_{c[2]}x{c[3]}x{c[4]}_s{c[5]}_bn{c[6]}_c{c[7]}" for c in GEMM_CASES])
 def test_tensor_core_gemm_all_layouts(cuda_lib, case):
-    """The tcgen05 3xTF32 kernel against float64, for every operand-major combination, ragged tiles,
-    split-K and both tile widths; the CUDA-core kernel is run beside it as the yardstick."""
+    """The tcgen05 kernels (3 = fp16 pairs, the production path; 2 = 3xTF32) against float64, for every
+    operand-major combination, ragged tiles, split-K and both tile widths; the CUDA-core kernel (1) is run
+    beside them as the yardstick."""
     a_kc, b_kc, M, N, K, splits, bn, kbc = case
     torch.manual_seed(M + N + K)
     A = torch.randn(M, K) if a_kc else torch.randn(K, M + (-M) % 4)
@@ -187,7 +237,7 @@ def test_tensor_core_gemm_all_layouts(cuda_lib, case):
     Ag, Bg = A.to(DEV), Bm.to(DEV)
     ldc = N + (-N) % 4
     ws = torch.empty(8 * (A.numel() + Bm.numel()) + 4 * splits * M * N + 8192, dtype=torch.uint8, device=DEV)
-    for algo in (2, 1):
+    for algo in (3, 2, 1):
         Cg = torch.full((M, ldc), float("nan"), device=DEV)
         check(cuda_lib.spotv2_diag_gemm(a_kc, b_kc, M, N, K, ptr(Ag), A.shape[1], ptr(Bg), Bm.shape[1], ptr(Cg), ldc,
                                         algo, splits, bn, kbc, ptr(ws), ws.numel(), st()), f"diag_gemm algo {algo}")
@@ -248,13 +298,17 @@ def test_attention_stages_against_dense_oracle(cuda_lib):
         dv, dbias = torch.empty(H, Fe, device=DEV), torch.empty(ldo, device=DEV)
         dout_g = dout.to(DEV)
         check(cuda_lib.spotv2_gat_attn_bwd(C.byref(d), ptr(P_aug), ptr(ea), ptr(topo.table), ptr(v), ptr(dout_g),
-                                           ptr(dP), None, ptr(dv), ptr(dbias), ptr(ws), ws.numel(), st()), "attn_bwd")
-        # the pre-split form: hi + lo reproduces the fp32 gradient to ~2^-22
-        dP_hi, dP_lo = torch.zeros_like(dP), torch.zeros_like(dP)
+                                           ptr(dP), None, None, None, ptr(dv), ptr(dbias), ptr(ws), ws.numel(), st()), "attn_bwd")
+        # the tensor-core operand form: the fp16 pair reproduces the fp32 gradient to ~2^-22 of each group's scale
+        n_aug = H * C_ + 2 * H
+        dP16 = torch.zeros(2, B * N, cuda_lib.spotv2_gat_ld16(n_aug), device=DEV, dtype=torch.float16)
+        pblk = torch.zeros(8, device=DEV)
         check(cuda_lib.spotv2_gat_attn_bwd(C.byref(d), ptr(P_aug), ptr(ea), ptr(topo.table), ptr(v), ptr(dout_g),
-                                           ptr(dP_hi), ptr(dP_lo), ptr(dv), ptr(dbias), ptr(ws), ws.numel(), st()), "attn_bwd")
-        assert relerr((dP_hi + dP_lo)[:, :H * C_ + 2 * H], dP[:, :H * C_ + 2 * H]) < 1e-6
-        assert (dP_hi.view(torch.int32) & 0x1fff).abs().max() == 0      # hi is a valid tf32 value
+                                           None, ptr(dP16[0]), ptr(dP16[1]), ptr(pblk), ptr(dv), ptr(dbias), ptr(ws),
+                                           ws.numel(), st()), "attn_bwd")
+        got = pair_value(dP16, pblk, n_aug, H * C_)
+        assert relerr(got[:, :H * C_], dP[:, :H * C_]) < 1e-6 and relerr(got[:, H * C_:], dP[:, H * C_:n_aug]) < 1e-6
+        assert torch.isfinite(dP16.float()).all() and dP16[0].abs().max() < 32800
         HC = H * C_
         assert relerr(dP[:, :HC], gr["dP_aug"][:, :HC]) < TOL
         assert relerr(dP[:, HC:HC + 2 * H], gr["dP_aug"][:, HC:]) < TOL
