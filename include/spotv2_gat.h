@@ -67,7 +67,8 @@ typedef struct spotv2_gat_desc {
   float   negative_slope; /* LeakyReLU slope                                       */
   int32_t ldp;            /* row stride of P_aug / dP_aug: >= H*C + 2*H, % 4 == 0  */
   int32_t gemm_algo;      /* 0 | 2 tcgen05 (fp16 operand pairs), 1 fp32 CUDA cores */
-  int32_t reserved;
+  int32_t attn_bwd_algo;  /* 0 auto (pipelined kernel when its shared-memory plan fits), 1 phase-serial
+                             kernel, 2 pipelined or error                           */
 } spotv2_gat_desc;
 
 /* Row table entry: (i << 16) | j  = "this edge row is j -> i" (i target, j source),

@@ -13,10 +13,7 @@
 //   B4  dv[h,:] += sum_e dz'[e,h] * edge_attr[e,:]: second pass over the edge rows         [ring]
 // The ring and the B2 staging alias the same shared memory.  dv and dbias are accumulated per
 // CTA and reduced in a fixed order by a second kernel (deterministic).
-#include <cuda_fp16.h>
-
-#include "attn_common.cuh"
-#include "gemm.cuh"
+#include "attn_bwd.cuh"
 
 namespace spotv2 {
 
@@ -27,31 +24,6 @@ constexpr int kTJ = 5;         // register tile: sources
 
 // phase-time diagnostics (thread 0 of every CTA; see spotv2_diag_counters, entries 16..31)
 __device__ unsigned long long g_bwd_counters[kNumCounters];
-
-struct AttnBwdArgs {
-  AttnParams p;
-  const float* dout;
-  float* dP_aug;       // fp32 gradient [B*N, ldp] (CUDA-core GEMM path), or null
-  // tensor-core path: dP emitted as scaled fp16 hi/lo pairs [B*N, ldp16] (operand format of gemm_f16.cu);
-  // the scale comes from max|dout| (dout_blk[0], bit pattern) times `bound` >= max|dP| / max|dout|.
-  // ds | dd have their own magnitude: they go to dsd [B*N, 2H] in fp32 and are split by the caller.
-  __half* dP_hi16;
-  __half* dP_lo16;
-  int ldp16;
-  const float* dout_blk;
-  float bound;
-  float* dsd;
-  float* dp_blk;       // receives inverse scale [2] and scale [4] of the dP group
-  float* dv_part;      // [grid][H*Fe]
-  float* dbias_part;   // [grid][ldo]
-};
-
-__device__ __forceinline__ float dp_scale_from_amax(float amax) {   // same rule as gemm_f16.cu
-  if (!(amax > 0.f) || !(amax < INFINITY)) return 1.f;
-  int ex;
-  frexpf(amax, &ex);
-  return exp2f((float)(15 - ex));
-}
 
 struct BwdSmem {
   AttnSmem a;
@@ -570,11 +542,19 @@ __global__ void partial_reduce_kernel(const float* __restrict__ part, int nparts
   out[k] = s;
 }
 
+int reduce_partials(const float* part, int nparts, int len, float* out, cudaStream_t st) {
+  partial_reduce_kernel<<<(len + 127) / 128, 128, 0, st>>>(part, nparts, len, out);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
 size_t attn_bwd_partials_bytes(const spotv2_gat_desc* d) {
   // per-CTA partials of dv [H, Fe] and dbias [C or HC]; at most 2 CTAs per SM
   const size_t ctas = 2 * (size_t)sm_count();
   const size_t ldo = d->concat ? (size_t)d->H * d->C : (size_t)d->C;
-  return round_up(ctas * ((size_t)d->H * d->Fe + ldo) * sizeof(float), 256);
+  const size_t legacy = round_up(ctas * ((size_t)d->H * d->Fe + ldo) * sizeof(float), 256);
+  const size_t piped = attn_bwd2_partials_bytes(d);
+  return legacy > piped ? legacy : piped;
 }
 size_t attn_bwd_ws_bytes(const spotv2_gat_desc* d) {
   // partials | ds,dd in fp32 [B*N, 2H] | two scale blocks
@@ -619,7 +599,7 @@ int bwd_diag_read(unsigned long long* host_out, int reset) {
     unsigned long long zeros[kNumCounters] = {0};
     SPOTV2_CUDA_OK(cudaMemcpyToSymbol(g_bwd_counters, zeros, sizeof(zeros)));
   }
-  return SPOTV2_OK;
+  return bwd2_diag_add(host_out, reset);       // whichever kernel ran contributes; the other adds zeros
 }
 }  // namespace spotv2
 
@@ -674,7 +654,11 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
   }
   const int np = (d->N + 1) / 2;
   int rc;
-  if (np <= 4) rc = launch_bwd<4>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
+  // d->attn_bwd_algo selects the kernel: 0 = pipelined (attn_bwd2.cu) whenever its shared-memory plan fits,
+  // 1 = the phase-serial kernel of this file, 2 = pipelined or error
+  if (d->attn_bwd_algo != 1 && (attn_bwd2_fits(a.p) || d->attn_bwd_algo == 2))
+    rc = launch_attn_bwd2(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
+  else if (np <= 4) rc = launch_bwd<4>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
   else if (np <= 8) rc = launch_bwd<8>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
   else if (np <= 15) rc = launch_bwd<15>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
   else if (np <= 16) rc = launch_bwd<16>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);

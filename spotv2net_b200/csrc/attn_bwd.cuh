@@ -1,0 +1,46 @@
+// Argument block shared by the two attention-backward kernels (attn_bwd.cu: phase-serial, two CTAs per SM,
+// any shape; attn_bwd2.cu: warp-specialised and pipelined across graphs, the default whenever its
+// shared-memory plan fits).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "attn_common.cuh"
+#include "gemm.cuh"
+
+namespace spotv2 {
+
+struct AttnBwdArgs {
+  AttnParams p;
+  const float* dout;
+  float* dP_aug;       // fp32 gradient [B*N, ldp] (CUDA-core GEMM path), or null
+  // tensor-core path: dP emitted as scaled fp16 hi/lo pairs [B*N, ldp16] (operand format of gemm_f16.cu);
+  // the scale comes from max|dout| (dout_blk[0], bit pattern) times `bound` >= max|dP| / max|dout|.
+  // ds | dd have their own magnitude: they go to dsd [B*N, 2H] in fp32 and are split by the caller.
+  __half* dP_hi16;
+  __half* dP_lo16;
+  int ldp16;
+  const float* dout_blk;
+  float bound;
+  float* dsd;
+  float* dp_blk;       // receives inverse scale [2] and scale [4] of the dP group
+  float* dv_part;      // [grid][H*Fe]
+  float* dbias_part;   // [grid][ldo]
+};
+
+__device__ __forceinline__ float dp_scale_from_amax(float amax) {   // same rule as gemm_f16.cu
+  if (!(amax > 0.f) || !(amax < INFINITY)) return 1.f;
+  int ex;
+  frexpf(amax, &ex);
+  return exp2f((float)(15 - ex));
+}
+
+// out[k] = sum_c part[c][k] in a fixed order (deterministic)
+int reduce_partials(const float* part, int nparts, int len, float* out, cudaStream_t st);
+
+// Pipelined kernel.  Returns SPOTV2_ERR_UNSUPPORTED (without setting an error) when the plan does not fit.
+bool attn_bwd2_fits(const AttnParams& p);
+int launch_attn_bwd2(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t attn_bwd2_partials_bytes(const spotv2_gat_desc* d);
+int bwd2_diag_add(unsigned long long* host_out, int reset);      // adds its phase counters into host_out[0..5]
+
+}  // namespace spotv2

@@ -106,10 +106,15 @@ def topology_from_edge_index(edge_index: Tensor, n_nodes: int, nodes_per_graph: 
 
 
 # --------------------------------------------------------------------------- autograd
+# Kernel selection knobs of spotv2_gat_desc (0 = the library's choice); tests set them to run every back end.
+GEMM_ALGO = 0
+ATTN_BWD_ALGO = 0
+
+
 def _desc(topo: Topology, F_in: int, Fe: int, H: int, Cc: int, concat: bool, slope: float) -> GatDesc:
     lib = _lib.load()
     return GatDesc(topo.B, topo.N, F_in, Fe, H, Cc, topo.R, int(concat), float(slope),
-                   lib.spotv2_gat_ldp(H, Cc), 0, 0)
+                   lib.spotv2_gat_ldp(H, Cc), GEMM_ALGO, ATTN_BWD_ALGO)
 
 
 def _workspace(desc: GatDesc):

@@ -266,9 +266,12 @@ def test_edge_table_accepts_reference_order_and_rejects_others(cuda_lib):
         sv.topology_from_edge_index(bad.to(DEV), B * N)
 
 
-def test_attention_stages_against_dense_oracle(cuda_lib):
+@pytest.mark.parametrize("bwd_algo", [2, 1], ids=["pipelined", "phase_serial"])
+@pytest.mark.parametrize("geom", [(5, 30, 16, 126, 6, 20), (160, 30, 16, 126, 6, 500), (7, 30, 8, 126, 8, 36), (4, 13, 8, 5, 3, 7)],
+                         ids=["small", "default_channels_2_graphs_per_cta", "H8", "odd"])
+def test_attention_stages_against_dense_oracle(cuda_lib, geom, bwd_algo):
     """attn_fwd / attn_bwd alone (P_aug given), compared stage by stage with oracle/dense_gat.py."""
-    B, N, Fin, Fe, H, C_ = 5, 30, 16, 126, 6, 20
+    B, N, Fin, Fe, H, C_ = geom
     for concat in (False, True):
         bt = synth.random_complete_batch(B, N, Fin, Fe, seed=4)
         ref, _ = make_layers(Fin, C_, H, concat, Fe, 0.2, seed=9, wscale=2.0)
@@ -277,8 +280,8 @@ def test_attention_stages_against_dense_oracle(cuda_lib):
         T = dense_gat.pyg_to_dense_tile(bt.edge_attr.double(), bt.edge_index, B, N)
         fw = dense_gat.dense_forward(bt.x.double(), T, W, a_s, a_d, We, a_e, bias, H, C_, concat, 0.2)
         ldp = cuda_lib.spotv2_gat_ldp(H, C_)
-        d = GatDesc(B, N, Fin, Fe, H, C_, N * (N - 1), int(concat), 0.2, ldp, 0, 0)
-        P_aug = torch.zeros(B * N, ldp, device=DEV)
+        d = GatDesc(B, N, Fin, Fe, H, C_, N * (N - 1), int(concat), 0.2, ldp, 0, bwd_algo)
+        P_aug = torch.full((B * N, ldp), float("nan"), device=DEV)       # padding columns may hold anything
         P_aug[:, :H * C_ + 2 * H] = fw["P_aug"].float().to(DEV)
         topo = sv.topology_from_edge_index(bt.edge_index.to(DEV), B * N)
         ea, v, bg = bt.edge_attr.to(DEV), fw["v"].float().to(DEV).contiguous(), bias.float().to(DEV)
@@ -331,8 +334,24 @@ CASES = [
 ]
 
 
+@pytest.fixture
+def bwd_kernel(request):
+    """Run the test body with a given attention-backward kernel (0 = library's choice: the pipelined kernel,
+    1 = the phase-serial any-shape kernel) and GEMM back end."""
+    from spotv2net_b200 import gat_conv
+    old = (gat_conv.ATTN_BWD_ALGO, gat_conv.GEMM_ALGO)
+    gat_conv.ATTN_BWD_ALGO, gat_conv.GEMM_ALGO = request.param
+    yield request.param
+    gat_conv.ATTN_BWD_ALGO, gat_conv.GEMM_ALGO = old
+
+
+BACKENDS = [(0, 0), (1, 0), (0, 1)]
+BACKEND_IDS = ["piped_bwd+tc_gemm", "serial_bwd+tc_gemm", "piped_bwd+simt_gemm"]
+
+
+@pytest.mark.parametrize("bwd_kernel", BACKENDS, ids=BACKEND_IDS, indirect=True)
 @pytest.mark.parametrize("case", CASES, ids=[f"B{c[0]}N{c[1]}F{c[2]}Fe{c[3]}H{c[4]}C{c[5]}{'cat' if c[6] else 'mean'}" for c in CASES])
-def test_layer_matches_edge_list_oracle(cuda_lib, case):
+def test_layer_matches_edge_list_oracle(cuda_lib, case, bwd_kernel):
     B, N, Fin, Fe, H, C_, concat, slope, wscale = case
     ref, ours = make_layers(Fin, C_, H, concat, Fe, slope, seed=B + N, wscale=wscale)
     if N == 1:
