@@ -4,11 +4,14 @@
 // every operand arrives through asynchronous copies that run ahead of the arithmetic, across phases and
 // across graphs, and every product runs on the tensor cores (mma.sync m16n8k8 TF32 with the 3x split).
 //
-//   producer warp   two independent streams, polled by one lane:
-//                   * edge rows: 1-D bulk copies into a 2-stage ring (twice per graph: logits, then dv)
-//                   * tile groups: 32x32 fp32 TMA tiles (128B-swizzled) of dout and P, 2 groups of <= 7 tiles
+//   producer warp   ONE in-order stream of fixed-size slots (28 KB each, 5 of them at the default geometry),
+//                   filled in exactly the order the compute warps consume them, as far ahead as the ring allows
+//                   (enough bytes in flight to cover the HBM latency at this SM's bandwidth share):
+//                   * edge rows: 1-D bulk copies, 48-row chunks (twice per graph: logits, then dv)
+//                   * tile groups: up to 7 32x32 fp32 TMA tiles (128B-swizzled) of dout and P
 //   compute warps   per graph
-//     L  g[e,h] = <edge row, v_h>        12 warps = 6 m16 row tiles x 2 k halves, red.shared into the tile
+//     L  g[e,h] = <edge row, v_h>        two half-groups of 6 warps take alternate chunks; a half-group =
+//                                        3 m16 row tiles x 2 k halves, red.shared into the tile (2 addends: exact order)
 //     S  self-loop mean fill, LeakyReLU, softmax -> alpha[h][j][i], z>0 masks       (thread per (h, i))
 //     A  dalpha_h = g dO_h P_h^T         warp = (head, 16-target tile); K = channels streamed as tile groups;
 //        softmax/LeakyReLU backward directly on the accumulator fragments (row sums by 4-lane shuffles),
@@ -33,22 +36,23 @@ constexpr int kB2Threads = kCT + 32;    // + producer warp
 constexpr int kTile = 4096;             // 32 rows x 32 fp32, 128B-swizzled
 constexpr int kGrpTiles = 7;            // tiles per group slot
 constexpr int kNS2 = 36;                // alpha / D tile row stride: (g*4 + t) fragment reads hit 32 banks
-constexpr int kMaxDvUnits = 4;          // (feature tile, row group) units per warp in phase V
+constexpr int kMaxDvUnits = 2;          // (feature tile, row group) units per warp in phase V
 
 __device__ unsigned long long g_bwd2_counters[kNumCounters];
 
 struct Bwd2Plan {
-  int KS, NT, chunk_rows, nchunks, n_cb, hpr, n_rounds, n_mt_chunk, ksplit;
-  int n_mtiles, dv_rg, dv_rpu, dv_units, cbs_per_grp_d, tma_ok;
-  uint32_t off_bar, off_table, off_vfrag, off_sd, off_mask, off_dspart, off_dbias, off_tile, off_D, off_ring,
-      ring_stage, off_grp, total;
+  int KS, chunk_rows, nchunks, n_cb, hpr, n_rounds, n_mt_chunk, ksplit;
+  int n_mtiles, dv_rg, dv_rpu, dv_units, cbs_per_grp_d, tma_ok, n_slots;
+  uint32_t off_bar, off_table, off_vfrag, off_sd, off_mask, off_dspart, off_dbias, off_tile, off_D, off_slots,
+      slot_bytes, total;
 };
+
+constexpr int kMaxSlots = 8;
 
 Bwd2Plan make_plan(const AttnParams& p) {
   Bwd2Plan s{};
   const int N = p.N, H = p.H, C = p.C, Fe = p.Fe;
   s.KS = ((Fe + 7) / 8 + 7) / 8 * 8;
-  s.NT = 1;
   s.n_cb = (C + 31) / 32;
   s.hpr = p.concat ? 3 : 6;
   s.n_rounds = (H + s.hpr - 1) / s.hpr;
@@ -65,24 +69,24 @@ Bwd2Plan make_plan(const AttnParams& p) {
   s.off_dbias = o;  o += (uint32_t)round_up((size_t)p.ldo * 4, 16);
   s.off_tile = o;   o += (uint32_t)round_up((size_t)H * N * kNS2 * 4, 16);
   s.off_D = o;      o += (uint32_t)round_up((size_t)H * N * kNS2 * 4, 16);
-  s.off_grp = (uint32_t)round_up(o, 1024);
-  o = s.off_grp + 2 * kGrpTiles * kTile;
-  s.off_ring = o;                                        // 1024-aligned
-  // largest edge ring stage (multiple of 16 rows, <= 96) that fits
-  s.chunk_rows = 0;
-  s.ring_stage = 0;
+  s.off_slots = (uint32_t)round_up(o, 1024);
+  // a slot holds one tile group (7 tiles) or one edge chunk (a multiple of 16 rows, at most 96)
+  s.slot_bytes = kGrpTiles * kTile;
+  if (Fe > 0 && (uint32_t)round_up((size_t)16 * Fe * 4, 1024) > s.slot_bytes) s.slot_bytes = (uint32_t)round_up((size_t)16 * Fe * 4, 1024);
+  const uint32_t avail = 227 * 1024 - 256 > s.off_slots ? 227 * 1024 - 256 - s.off_slots : 0;
+  s.n_slots = (int)(avail / s.slot_bytes);
+  if (s.n_slots > kMaxSlots) s.n_slots = kMaxSlots;
+  if (s.n_slots < 3) { s.total = 0xffffffffu; return s; }
+  s.total = s.off_slots + (uint32_t)s.n_slots * s.slot_bytes + 256;     // + slack: k-steps padded past Fe read a few floats on
   if (Fe > 0) {
-    for (int rows = 96; rows >= 16; rows -= 16) {
-      const uint32_t st = (uint32_t)round_up((size_t)rows * Fe * 4, 128);
-      if (o + 2 * st <= 227 * 1024) { s.chunk_rows = rows; s.ring_stage = st; break; }
-    }
-    if (s.chunk_rows == 0) { s.total = 0xffffffffu; return s; }
-    if (s.chunk_rows > p.R) s.chunk_rows = (p.R + 15) / 16 * 16, s.ring_stage = (uint32_t)round_up((size_t)s.chunk_rows * Fe * 4, 128);
+    s.chunk_rows = (int)(s.slot_bytes / ((uint32_t)Fe * 4)) / 16 * 16;
+    if (s.chunk_rows > 96) s.chunk_rows = 96;
+    if (s.chunk_rows > p.R) s.chunk_rows = (p.R + 15) / 16 * 16;
     s.nchunks = (p.R + s.chunk_rows - 1) / s.chunk_rows;
   }
-  s.total = o + 2 * s.ring_stage;
+  // phase L: a half-group of 6 warps covers one chunk: n_mt_chunk row tiles x ksplit k halves
   s.n_mt_chunk = s.chunk_rows / 16;
-  s.ksplit = (s.n_mt_chunk > 0 && 2 * s.n_mt_chunk <= kW && s.KS >= 16) ? 2 : 1;
+  s.ksplit = (s.n_mt_chunk > 0 && 2 * s.n_mt_chunk <= kW / 2 && s.KS >= 16) ? 2 : 1;
   // phase V units: (16-feature tile, row group)
   s.n_mtiles = (Fe + 15) / 16;
   if (Fe > 0) {
@@ -108,8 +112,30 @@ __device__ __forceinline__ float ld_tile(const unsigned char* t, int r, int c) {
   asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
   return v;
 }
-__device__ __forceinline__ void red_add_shared(float* p, float v) {
-  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v) : "memory");
+// 32-bit shared-window address forms of the hot-loop accesses
+__device__ __forceinline__ float lds_u32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int lds_i32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds128_u32(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void red_add_u32(uint32_t a, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+// tf32 split for mma.sync operands: the tensor core reads only the top 19 bits of a tf32 operand register
+// (verified by the parity tests), so "hi" is the raw fp32 pattern and only lo = x - trunc(x) costs ALU work.
+__device__ __forceinline__ void split_lean(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x);
+  lo = __float_as_uint(x - __uint_as_float(hi & 0xffffe000u));
 }
 
 // Edge terms of the 16 rows [m0, m0+16) of a staged chunk for the k-blocks kb0, kb0+kb_stride, ... (8 k-steps
@@ -167,10 +193,8 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl, const __grid_con
   const int tile_floats = H * N * NS;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + pl.off_bar);
-  uint64_t* edge_full = bars;          // [2]
-  uint64_t* edge_empty = bars + 2;     // [2]
-  uint64_t* grp_full = bars + 4;       // [2]
-  uint64_t* grp_empty = bars + 6;      // [2]
+  uint64_t* full = bars;                // [kMaxSlots]
+  uint64_t* empty = bars + kMaxSlots;   // [kMaxSlots]
   int32_t* table_s = reinterpret_cast<int32_t*>(smem_raw + pl.off_table);
   float4* vfrag = reinterpret_cast<float4*>(smem_raw + pl.off_vfrag);
   float* sd = reinterpret_cast<float*>(smem_raw + pl.off_sd);
@@ -179,13 +203,10 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl, const __grid_con
   float* dbias_s = reinterpret_cast<float*>(smem_raw + pl.off_dbias);
   float* tile = reinterpret_cast<float*>(smem_raw + pl.off_tile);          // alpha[h][j][i]
   float* D = reinterpret_cast<float*>(smem_raw + pl.off_D);                // dz'[h][j][i]
-  unsigned char* grp0 = smem_raw + pl.off_grp;
-  float* stage0 = reinterpret_cast<float*>(smem_raw + pl.off_ring);
-  float* stage1 = reinterpret_cast<float*>(smem_raw + pl.off_ring + pl.ring_stage);
+  unsigned char* slots = smem_raw + pl.off_slots;
   __builtin_assume(__isShared(table_s)); __builtin_assume(__isShared(vfrag)); __builtin_assume(__isShared(sd));
   __builtin_assume(__isShared(pos_mask)); __builtin_assume(__isShared(ds_part)); __builtin_assume(__isShared(dbias_s));
-  __builtin_assume(__isShared(tile)); __builtin_assume(__isShared(D)); __builtin_assume(__isShared(stage0));
-  __builtin_assume(__isShared(stage1));
+  __builtin_assume(__isShared(tile)); __builtin_assume(__isShared(D)); __builtin_assume(__isShared(slots));
 
   const int nchunks = pl.nchunks;
   const int my_graphs = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -193,13 +214,18 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl, const __grid_con
   auto rows_in = [&](int c) { const int r = p.R - c * pl.chunk_rows; return r < pl.chunk_rows ? r : pl.chunk_rows; };
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&edge_full[s], 1); mbar_init(&edge_empty[s], kW);
-      mbar_init(&grp_full[s], 1);  mbar_init(&grp_empty[s], kW);
-    }
+    for (int s = 0; s < pl.n_slots; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kW); }
     fence_mbar_init();
   }
-  for (int r = tid; r < p.R; r += kB2Threads) table_s[r] = Fe > 0 ? p.table[r] : -1;
+  // row -> byte offset of (source j, target i) inside one head of the alpha / dz' tiles (-1: row skipped)
+  for (int r = tid; r < p.R; r += kB2Threads) {
+    const int code = Fe > 0 ? p.table[r] : -1;
+    table_s[r] = code >= 0 ? ((code & 0xffff) * NS + (code >> 16)) * 4 : -1;
+  }
+  // slots start zero-filled: rows and tails a chunk does not cover must read as finite numbers
+  for (uint32_t idx = tid; idx < (uint32_t)pl.n_slots * pl.slot_bytes / 16; idx += kB2Threads)
+    reinterpret_cast<float4*>(smem_raw + pl.off_slots)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_proxy_async();                    // generic-proxy zero fill before the copy engine writes the same bytes
   if (Fe > 0) build_vfrag(vfrag, p.v, H, Fe, pl.KS, 1, tid, kB2Threads);
   for (int idx = tid; idx < tile_floats; idx += kB2Threads) { tile[idx] = 0.f; D[idx] = 0.f; }
   for (int idx = tid; idx < p.ldo; idx += kB2Threads) dbias_s[idx] = 0.f;
@@ -223,106 +249,88 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl, const __grid_con
         }
       }
     };
-    // edge stream state
-    int ek = 0, e_it = 0, e_pass = 0, e_c = 0;
-    bool e_done = (nchunks == 0 || my_graphs == 0);
-    // group stream state: phase 0 = A (per round, per channel block), phase 1 = D (per round, per dO group)
-    int gk = 0, g_it = 0, g_phase = 0, g_r = 0, g_i = 0;
-    bool g_done = (my_graphs == 0);
-    const int n_grp_d = (n_cb + pl.cbs_per_grp_d - 1) / pl.cbs_per_grp_d;
-    long long t_idle0 = clock64();
-    while (!e_done || !g_done) {
-      bool progressed = false;
-      if (!e_done) {
-        const int s = ek & 1;
-        int ok = (lane == 0) ? (int)mbar_try_wait(&edge_empty[s], ((ek >> 1) & 1) ^ 1) : 0;
-        ok = __shfl_sync(0xffffffffu, ok, 0);
-        if (ok) {
-          const int b = blockIdx.x + e_it * gridDim.x;
-          const int rows = rows_in(e_c);
-          const float* src = p.edge_rows + ((size_t)b * p.R + (size_t)e_c * pl.chunk_rows) * Fe;
-          float* dst = s ? stage1 : stage0;
-          if (p.bulk_ok) {
-            if (lane == 0) {
-              const uint32_t bytes = (uint32_t)rows * Fe * 4u;
-              mbar_expect_tx(&edge_full[s], bytes);
-              bulk_g2s(dst, src, bytes, &edge_full[s]);
-            }
-          } else {
-            for (int idx = lane; idx < rows * Fe; idx += 32) dst[idx] = src[idx];
-            __syncwarp();
-            if (lane == 0) mbar_arrive2(&edge_full[s]);
-          }
-          ++ek;
-          if (++e_c == nchunks) { e_c = 0; if (++e_pass == 2) { e_pass = 0; if (++e_it == my_graphs) e_done = true; } }
-          progressed = true;
-        }
+    int slot = 0;
+    uint32_t sph = 0;
+    auto acquire = [&]() -> unsigned char* {
+      if (lane == 0) mbar_wait(&empty[slot], sph ^ 1);
+      __syncwarp();
+      return slots + (size_t)slot * pl.slot_bytes;
+    };
+    auto publish = [&](bool async_done) {          // async_done: completion comes from the copy engine's tx count
+      if (!async_done) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive2(&full[slot]);
       }
-      if (!g_done) {
-        const int s = gk & 1;
-        int ok = (lane == 0) ? (int)mbar_try_wait(&grp_empty[s], ((gk >> 1) & 1) ^ 1) : 0;
-        ok = __shfl_sync(0xffffffffu, ok, 0);
-        if (ok) {
-          const int b = blockIdx.x + g_it * gridDim.x;
-          unsigned char* gb = grp0 + s * (kGrpTiles * kTile);
-          const int h0 = g_r * pl.hpr;
-          const int nh = min(pl.hpr, H - h0);
-          int ntiles;
-          if (g_phase == 0) ntiles = p.concat ? 2 * nh : 1 + nh;
-          else {
-            const int cb0 = g_i * pl.cbs_per_grp_d;
-            const int ncb = min(pl.cbs_per_grp_d, n_cb - cb0);
-            ntiles = p.concat ? ncb * nh : ncb;
-          }
-          if (pl.tma_ok && lane == 0) mbar_expect_tx(&grp_full[s], (uint32_t)ntiles * kTile);
-          if (g_phase == 0) {
-            const int cb = g_i;
-            if (p.concat) {
-              for (int hl = 0; hl < nh; ++hl) {
-                put_tile(gb + (2 * hl) * kTile, &tmG, args.dout, p.ldo, (h0 + hl) * C + cb * 32, b * N, &grp_full[s]);
-                put_tile(gb + (2 * hl + 1) * kTile, &tmP, p.P_aug, p.ldp, (h0 + hl) * C + cb * 32, b * N, &grp_full[s]);
-              }
-            } else {
-              put_tile(gb, &tmG, args.dout, p.ldo, cb * 32, b * N, &grp_full[s]);
-              for (int hl = 0; hl < nh; ++hl)
-                put_tile(gb + (1 + hl) * kTile, &tmP, p.P_aug, p.ldp, (h0 + hl) * C + cb * 32, b * N, &grp_full[s]);
-            }
-          } else {
-            const int cb0 = g_i * pl.cbs_per_grp_d;
-            const int ncb = min(pl.cbs_per_grp_d, n_cb - cb0);
-            for (int k = 0; k < ncb; ++k) {
-              if (p.concat) {
-                for (int hl = 0; hl < nh; ++hl)
-                  put_tile(gb + (k * nh + hl) * kTile, &tmG, args.dout, p.ldo, (h0 + hl) * C + (cb0 + k) * 32, b * N, &grp_full[s]);
-              } else {
-                put_tile(gb + k * kTile, &tmG, args.dout, p.ldo, (cb0 + k) * 32, b * N, &grp_full[s]);
-              }
-            }
-          }
-          if (!pl.tma_ok) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive2(&grp_full[s]);
-          }
-          ++gk;
-          const int lim = (g_phase == 0) ? n_cb : n_grp_d;
-          if (++g_i == lim) {
-            g_i = 0;
-            if (++g_r == pl.n_rounds) { g_r = 0; if (++g_phase == 2) { g_phase = 0; if (++g_it == my_graphs) g_done = true; } }
-          }
-          progressed = true;
+      if (++slot == pl.n_slots) { slot = 0; sph ^= 1; }
+    };
+    auto edge_chunk = [&](int b, int c) {
+      float* dst = reinterpret_cast<float*>(acquire());
+      const int rows = rows_in(c);
+      const float* src = p.edge_rows + ((size_t)b * p.R + (size_t)c * pl.chunk_rows) * Fe;
+      if (p.bulk_ok) {
+        if (lane == 0) {
+          const uint32_t bytes = (uint32_t)rows * Fe * 4u;
+          mbar_expect_tx(&full[slot], bytes);
+          bulk_g2s(dst, src, bytes, &full[slot]);
         }
-      }
-      if (progressed) {
-        t_idle0 = clock64();
       } else {
-        __nanosleep(40);
-        if (clock64() - t_idle0 > 4000000000LL) __trap();
+        for (int idx = lane; idx < rows * Fe; idx += 32) dst[idx] = src[idx];
       }
+      publish(p.bulk_ok != 0);
+    };
+    const int n_grp_d = (n_cb + pl.cbs_per_grp_d - 1) / pl.cbs_per_grp_d;
+    for (int it = 0; it < my_graphs; ++it) {
+      const int b = blockIdx.x + it * gridDim.x;
+      for (int c = 0; c < nchunks; ++c) edge_chunk(b, c);                       // phase L
+      for (int r = 0; r < pl.n_rounds; ++r) {                                   // phase A: one group per channel block
+        const int h0 = r * pl.hpr;
+        const int nh = min(pl.hpr, H - h0);
+        for (int cb = 0; cb < n_cb; ++cb) {
+          unsigned char* gb = acquire();
+          const int ntiles = p.concat ? 2 * nh : 1 + nh;
+          if (pl.tma_ok && lane == 0) mbar_expect_tx(&full[slot], (uint32_t)ntiles * kTile);
+          if (p.concat) {
+            for (int hl = 0; hl < nh; ++hl) {
+              put_tile(gb + (2 * hl) * kTile, &tmG, args.dout, p.ldo, (h0 + hl) * C + cb * 32, b * N, &full[slot]);
+              put_tile(gb + (2 * hl + 1) * kTile, &tmP, p.P_aug, p.ldp, (h0 + hl) * C + cb * 32, b * N, &full[slot]);
+            }
+          } else {
+            put_tile(gb, &tmG, args.dout, p.ldo, cb * 32, b * N, &full[slot]);
+            for (int hl = 0; hl < nh; ++hl)
+              put_tile(gb + (1 + hl) * kTile, &tmP, p.P_aug, p.ldp, (h0 + hl) * C + cb * 32, b * N, &full[slot]);
+          }
+          publish(pl.tma_ok != 0);
+        }
+      }
+      for (int r = 0; r < pl.n_rounds; ++r) {                                   // phase D: groups of dO tiles
+        const int h0 = r * pl.hpr;
+        const int nh = min(pl.hpr, H - h0);
+        for (int gi = 0; gi < n_grp_d; ++gi) {
+          unsigned char* gb = acquire();
+          const int cb0 = gi * pl.cbs_per_grp_d;
+          const int ncb = min(pl.cbs_per_grp_d, n_cb - cb0);
+          const int ntiles = p.concat ? ncb * nh : ncb;
+          if (pl.tma_ok && lane == 0) mbar_expect_tx(&full[slot], (uint32_t)ntiles * kTile);
+          for (int k = 0; k < ncb; ++k) {
+            if (p.concat) {
+              for (int hl = 0; hl < nh; ++hl)
+                put_tile(gb + (k * nh + hl) * kTile, &tmG, args.dout, p.ldo, (h0 + hl) * C + (cb0 + k) * 32, b * N, &full[slot]);
+            } else {
+              put_tile(gb + k * kTile, &tmG, args.dout, p.ldo, (cb0 + k) * 32, b * N, &full[slot]);
+            }
+          }
+          publish(pl.tma_ok != 0);
+        }
+      }
+      for (int c = 0; c < nchunks; ++c) edge_chunk(b, c);                       // phase V
     }
     return;
   }
 
   // ============================================== compute ==============================================
+  // All hot-loop addressing is done on 32-bit shared-window addresses computed once (generic pointers made
+  // the compiler re-derive the window base before every access), swizzled tile offsets are folded into a
+  // per-lane base plus an XOR with a compile-time constant, and table lookups return byte offsets.
   const int g = lane >> 2, t = lane & 3;
   const float g_scale = p.concat ? 1.f : 1.f / (float)H;
   const float inv_nm1 = 1.f / (float)(N > 1 ? N - 1 : 1);
@@ -331,16 +339,62 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl, const __grid_con
     dp_scale = dp_scale_from_amax(__uint_as_float(*reinterpret_cast<const unsigned*>(args.dout_blk)) * args.bound);
     if (blockIdx.x == 0 && tid == 0) { args.dp_blk[2] = 1.f / dp_scale; args.dp_blk[4] = dp_scale; }
   }
+  const bool vec4_out = (C % 4 == 0);     // 8-byte aligned groups of 4 fp16 columns (ldp16 % 8 == 0)
   AttnSmem asm_{};                        // what softmax_phase reads
   asm_.NS = NS; asm_.KS = pl.KS; asm_.NT = 1;
 
+  const uint32_t sbase = smem_u32(smem_raw);
+  const uint32_t a_tile = sbase + pl.off_tile, a_D = sbase + pl.off_D, a_toff = sbase + pl.off_table;
+  const uint32_t a_vfrag = sbase + pl.off_vfrag, a_slots = sbase + pl.off_slots, a_full = sbase + pl.off_bar;
+  const uint32_t head_bytes = (uint32_t)(N * NS * 4);
+  // fragment bases inside a 128B-swizzled 32x32 tile (row r, col c at r*128 + (((c>>2) ^ (r&7)) << 4) + (c&3)*4):
+  //   row-major operand fragments (rows g / 8n+g, cols 8ks+t):  base ^ (ks << 5)  and  base ^ ((2ks+1) << 4)
+  //   k-major operand fragments (rows 8ks+t / +4, cols 8n+g):   base ^ (n << 5), + ks*1024
+  const uint32_t fb_row = (uint32_t)(g * 128 + (g << 4) + (t << 2));
+  const uint32_t fb_k0 = (uint32_t)(t * 128 + ((((g >> 2) ^ t)) << 4) + ((g & 3) << 2));
+  const uint32_t fb_k1 = (uint32_t)((t + 4) * 128 + ((((g >> 2) ^ t ^ 4)) << 4) + ((g & 3) << 2));
+
+  // phase V units of this warp (feature tile, row group): fixed for the whole kernel
+  int dv_mt[kMaxDvUnits], dv_rb[kMaxDvUnits];
   float dv_run[kMaxDvUnits][4];
 #pragma unroll
-  for (int u = 0; u < kMaxDvUnits; ++u)
+  for (int uu = 0; uu < kMaxDvUnits; ++uu) {
+    const int u = warp + uu * kW;
+    const bool ok = u < pl.dv_units;
+    dv_mt[uu] = ok ? u % pl.n_mtiles : -1;
+    dv_rb[uu] = ok ? (u / pl.n_mtiles) * pl.dv_rpu : 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) dv_run[u][q] = 0.f;
+    for (int q = 0; q < 4; ++q) dv_run[uu][q] = 0.f;
+  }
+  // phase L unit of this warp: half-group, row tile, k block start
+  const int l_hg = warp / (kW / 2), l_w6 = warp - l_hg * (kW / 2);
+  const int l_mt = pl.n_mt_chunk > 0 ? l_w6 % pl.n_mt_chunk : 0, l_kh = pl.n_mt_chunk > 0 ? l_w6 / pl.n_mt_chunk : 0;
+  const bool l_on = pl.n_mt_chunk > 0 && l_kh < pl.ksplit;
+  const uint32_t l_row0 = (uint32_t)(((l_mt * 16 + g) * Fe + t) * 4);       // row g of the tile, feature t
+  const uint32_t l_hoff0 = (uint32_t)(2 * t) * head_bytes, l_hoff1 = l_hoff0 + head_bytes;
 
-  int ek = 0, gk = 0;                      // consumed edge chunks / tile groups (all compute warps in step)
+  // slot cursor: every compute warp walks the slots in the producer's order
+  int slot = 0;
+  uint32_t sph = 0;
+  auto wait_slot = [&]() -> uint32_t {
+    const uint32_t bar = a_full + (uint32_t)slot * 8u;
+    uint32_t ok = 0, spins = 0;
+    do {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok) : "r"(bar), "r"(sph) : "memory");
+      if (!ok && ++spins > (1u << 24)) __trap();                 // lost transaction: fail loudly, never hang the box
+    } while (!ok);
+    return a_slots + (uint32_t)slot * pl.slot_bytes;
+  };
+  auto release_slot = [&]() {
+    __syncwarp();
+    if (lane == 0) mbar_arrive2(&empty[slot]);
+    if (++slot == pl.n_slots) { slot = 0; sph ^= 1; }
+  };
+
   long long ph[6] = {0, 0, 0, 0, 0, 0};
   long long t_ph = clock64();
   auto lap = [&](int k) { const long long now = clock64(); ph[k] += now - t_ph; t_ph = now; };
@@ -353,22 +407,59 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl, const __grid_con
       sd[idx] = p.P_aug[((size_t)b * N + j) * p.ldp + HC + k];
     }
     for (int idx = tid; idx < 2 * H * 32; idx += kCT) ds_part[idx] = 0.f;
-    for (int c = 0; c < nchunks; ++c, ++ek) {
-      const int s = ek & 1;
-      mbar_wait(&edge_full[s], (ek >> 1) & 1);
+    for (int c = 0; c < nchunks; ++c) {
+      const uint32_t sa = wait_slot();
       const int rows = rows_in(c);
-      const int mt = warp % pl.n_mt_chunk, kh = warp / pl.n_mt_chunk;
-      if (kh < pl.ksplit && mt * 16 < rows) {
-        const int row_base = c * pl.chunk_rows;
-        edge_logits_part(s ? stage1 : stage0, vfrag, Fe, pl.KS, mt * 16, lane, kh, pl.ksplit, [&](int r, int h, float val) {
-          if (r < rows && h < H) {
-            const int code = table_s[row_base + r];
-            if (code >= 0) red_add_shared(&tile[(h * N + (code & 0xffff)) * NS + (code >> 16)], val);
+      if (l_on && (c & 1) == l_hg && l_mt * 16 < rows) {
+        // 16 rows x this warp's k blocks (4 k-steps each), 3xTF32; features past Fe meet zero B fragments
+        // (rows and slot tails hold finite stale data: the slots are zero-filled at start)
+        float acc[3][4];
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[pr][q] = 0.f;
+        const uint32_t r0 = sa + l_row0, r1 = r0 + (uint32_t)(8 * Fe * 4);
+        for (int kb = l_kh; kb < pl.KS / 4; kb += pl.ksplit) {
+          const uint32_t ko = (uint32_t)kb * 128u;                 // 4 k-steps x 8 features x 4 bytes
+          const uint32_t vf = a_vfrag + ((uint32_t)(kb * 4) * 32u + (uint32_t)lane) * 16u;
+          float a[4][4];
+          float4 bf[4];
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {
+            a[sl][0] = lds_u32(r0 + ko + sl * 32);
+            a[sl][1] = lds_u32(r1 + ko + sl * 32);
+            a[sl][2] = lds_u32(r0 + ko + sl * 32 + 16);
+            a[sl][3] = lds_u32(r1 + ko + sl * 32 + 16);
+            bf[sl] = lds128_u32(vf + sl * 512);
           }
-        });
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {
+            uint32_t ah[4], al[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) split_lean(a[sl][q], ah[q], al[q]);
+            const uint32_t bh[2] = {__float_as_uint(bf[sl].x), __float_as_uint(bf[sl].y)};
+            const uint32_t bl[2] = {__float_as_uint(bf[sl].z), __float_as_uint(bf[sl].w)};
+            mma_tf32_16x8x8(acc[0], al, bh);
+            mma_tf32_16x8x8(acc[1], ah, bl);
+            mma_tf32_16x8x8(acc[2], ah, bh);
+          }
+        }
+        const int row_base = c * pl.chunk_rows + l_mt * 16 + g;
+        const int rl = l_mt * 16 + g;
+        const int to0 = rl < rows ? lds_i32(a_toff + (uint32_t)row_base * 4u) : -1;
+        const int to1 = rl + 8 < rows ? lds_i32(a_toff + (uint32_t)(row_base + 8) * 4u) : -1;
+        const float v0 = (acc[0][0] + acc[1][0]) + acc[2][0], v1 = (acc[0][1] + acc[1][1]) + acc[2][1];
+        const float v2 = (acc[0][2] + acc[1][2]) + acc[2][2], v3 = (acc[0][3] + acc[1][3]) + acc[2][3];
+        if (to0 >= 0) {
+          if (2 * t < H) red_add_u32(a_tile + l_hoff0 + (uint32_t)to0, v0);
+          if (2 * t + 1 < H) red_add_u32(a_tile + l_hoff1 + (uint32_t)to0, v1);
+        }
+        if (to1 >= 0) {
+          if (2 * t < H) red_add_u32(a_tile + l_hoff0 + (uint32_t)to1, v2);
+          if (2 * t + 1 < H) red_add_u32(a_tile + l_hoff1 + (uint32_t)to1, v3);
+        }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive2(&edge_empty[s]);
+      release_slot();
     }
     bar_sync_compute();
     lap(0);
@@ -383,56 +474,52 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl, const __grid_con
       const int hl = warp >> 1, m = warp & 1;
       const bool active = (warp < 2 * nh) && (16 * m < N);
       const int h = h0 + hl;
-      const int dslot = p.concat ? 2 * hl : 0, pslot = p.concat ? 2 * hl + 1 : 1 + hl;
+      const uint32_t d_off = (uint32_t)((p.concat ? 2 * hl : 0) * kTile + m * 2048) + fb_row;
+      const uint32_t p_off = (uint32_t)((p.concat ? 2 * hl + 1 : 1 + hl) * kTile) + fb_row;
       const int i0 = 16 * m + g, i1 = i0 + 8;
       float cmain[4][4], ccorr[4][4], dacc[4][4];
 #pragma unroll
       for (int n = 0; n < 4; ++n)
 #pragma unroll
         for (int q = 0; q < 4; ++q) cmain[n][q] = ccorr[n][q] = dacc[n][q] = 0.f;
-      for (int cb = 0; cb < n_cb; ++cb, ++gk) {
-        const int s = gk & 1;
-        mbar_wait(&grp_full[s], (gk >> 1) & 1);
+      for (int cb = 0; cb < n_cb; ++cb) {
+        const uint32_t sa = wait_slot();
         if (active) {
-          const unsigned char* gb = grp0 + s * (kGrpTiles * kTile);
-          const unsigned char* dOt = gb + dslot * kTile;
-          const unsigned char* Pt = gb + pslot * kTile;
-          const bool tail = (cb * 32 + 32 > C);          // channels beyond C: next head's columns (concat) or zero fill
+          const uint32_t da = sa + d_off, pa = sa + p_off;
+          const bool tail = (cb * 32 + 32 > C);          // channels beyond C: next head's columns (concat) or padding
           uint32_t ah[4][4], al[4][4];
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const int c0 = 8 * ks + t, c1 = c0 + 4;
-            float a0 = ld_tile(dOt, i0, c0), a1 = ld_tile(dOt, i1, c0), a2 = ld_tile(dOt, i0, c1), a3 = ld_tile(dOt, i1, c1);
+            float a0 = lds_u32(da ^ (ks << 5)), a1 = lds_u32((da ^ (ks << 5)) + 1024);
+            float a2 = lds_u32(da ^ ((2 * ks + 1) << 4)), a3 = lds_u32((da ^ ((2 * ks + 1) << 4)) + 1024);
             if (tail) {
-              if (cb * 32 + c0 >= C) a0 = a1 = 0.f;
-              if (cb * 32 + c1 >= C) a2 = a3 = 0.f;
+              if (cb * 32 + 8 * ks + t >= C) a0 = a1 = 0.f;
+              if (cb * 32 + 8 * ks + t + 4 >= C) a2 = a3 = 0.f;
             }
-            split_tf32_trunc(a0, ah[ks][0], al[ks][0]);
-            split_tf32_trunc(a1, ah[ks][1], al[ks][1]);
-            split_tf32_trunc(a2, ah[ks][2], al[ks][2]);
-            split_tf32_trunc(a3, ah[ks][3], al[ks][3]);
+            split_lean(a0, ah[ks][0], al[ks][0]);
+            split_lean(a1, ah[ks][1], al[ks][1]);
+            split_lean(a2, ah[ks][2], al[ks][2]);
+            split_lean(a3, ah[ks][3], al[ks][3]);
           }
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
             for (int n = 0; n < 4; ++n) {
-              const int j = 8 * n + g;
-              float b0 = ld_tile(Pt, j, 8 * ks + t), b1 = ld_tile(Pt, j, 8 * ks + t + 4);
+              float b0 = lds_u32((pa ^ (ks << 5)) + n * 1024), b1 = lds_u32((pa ^ ((2 * ks + 1) << 4)) + n * 1024);
               if (tail) {                                  // never let padding bits (possibly NaN) meet the zeros above
                 if (cb * 32 + 8 * ks + t >= C) b0 = 0.f;
                 if (cb * 32 + 8 * ks + t + 4 >= C) b1 = 0.f;
               }
               uint32_t bh[2], bl[2];
-              split_tf32_trunc(b0, bh[0], bl[0]);
-              split_tf32_trunc(b1, bh[1], bl[1]);
+              split_lean(b0, bh[0], bl[0]);
+              split_lean(b1, bh[1], bl[1]);
               mma_tf32_16x8x8(ccorr[n], al[ks], bh);
               mma_tf32_16x8x8(cmain[n], ah[ks], bh);
               mma_tf32_16x8x8(ccorr[n], ah[ks], bl);
             }
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive2(&grp_empty[s]);
+        release_slot();
         if (active && ((cb & 1) || cb == n_cb - 1)) {       // keep tensor-core accumulation chains short: fold in fp32 RN
 #pragma unroll
           for (int n = 0; n < 4; ++n)
@@ -531,7 +618,6 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl, const __grid_con
       const bool active = (warp < 2 * nh) && (16 * m < N);
       const int h = h0 + hl;
       const int j0 = 16 * m + g, j1 = j0 + 8;
-      const bool bias_owner = active && m == 0 && (p.concat || (r == 0 && hl == 0));
       uint32_t ah[4][4], al[4][4];
       if (active) {
 #pragma unroll
@@ -541,145 +627,166 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl, const __grid_con
           const float a1 = j1 < N ? tile[(h * N + j1) * NS + ia] * g_scale : 0.f;
           const float a2 = j0 < N ? tile[(h * N + j0) * NS + ib] * g_scale : 0.f;
           const float a3 = j1 < N ? tile[(h * N + j1) * NS + ib] * g_scale : 0.f;
-          split_tf32_trunc(a0, ah[ks][0], al[ks][0]);
-          split_tf32_trunc(a1, ah[ks][1], al[ks][1]);
-          split_tf32_trunc(a2, ah[ks][2], al[ks][2]);
-          split_tf32_trunc(a3, ah[ks][3], al[ks][3]);
+          split_lean(a0, ah[ks][0], al[ks][0]);
+          split_lean(a1, ah[ks][1], al[ks][1]);
+          split_lean(a2, ah[ks][2], al[ks][2]);
+          split_lean(a3, ah[ks][3], al[ks][3]);
         }
       }
       const int n_grp = (n_cb + pl.cbs_per_grp_d - 1) / pl.cbs_per_grp_d;
-      for (int gi = 0; gi < n_grp; ++gi, ++gk) {
-        const int s = gk & 1;
-        mbar_wait(&grp_full[s], (gk >> 1) & 1);
+      for (int gi = 0; gi < n_grp; ++gi) {
+        const uint32_t sa = wait_slot();
+        const int cb0 = gi * pl.cbs_per_grp_d;
+        const int ncb = min(pl.cbs_per_grp_d, n_cb - cb0);
+        // dbias: column sums of the staged dO tiles, one tile per warp, one column per lane (tiles of the shared
+        // dO in head-mean mode are summed in round 0 only)
+        if (p.concat || r == 0) {
+          const int n_t = p.concat ? ncb * nh : ncb;
+          for (int k = warp; k < n_t; k += kW) {
+            const int kc = p.concat ? k / nh : k, khl = p.concat ? k - kc * nh : 0;
+            const uint32_t ta = sa + (uint32_t)k * kTile;
+            float sum = 0.f;
+            for (int rr = 0; rr < N; ++rr)
+              sum += lds_u32(ta + rr * 128 + ((((lane >> 2) ^ (rr & 7)) << 4) | ((lane & 3) << 2)));
+            const int c = (cb0 + kc) * 32 + lane;
+            if (c < C) dbias_s[(p.concat ? (h0 + khl) * C : 0) + c] += sum;       // one owner lane per column
+          }
+        }
         if (active) {
-          const unsigned char* gb = grp0 + s * (kGrpTiles * kTile);
-          const int cb0 = gi * pl.cbs_per_grp_d;
-          const int ncb = min(pl.cbs_per_grp_d, n_cb - cb0);
           for (int k = 0; k < ncb; ++k) {
             const int cb = cb0 + k;
-            const unsigned char* Bt = gb + (p.concat ? k * nh + hl : k) * kTile;
+            const uint32_t ta = sa + (uint32_t)(p.concat ? k * nh + hl : k) * kTile;
+            const uint32_t tb0 = ta + fb_k0, tb1 = ta + fb_k1;
             float cmain[4][4], ccorr[4][4];
-            float bsum[4];
 #pragma unroll
-            for (int n = 0; n < 4; ++n) {
-              bsum[n] = 0.f;
+            for (int n = 0; n < 4; ++n)
 #pragma unroll
               for (int q = 0; q < 4; ++q) cmain[n][q] = ccorr[n][q] = 0.f;
-            }
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              const int r0 = 8 * ks + t, r1 = r0 + 4;
 #pragma unroll
               for (int n = 0; n < 4; ++n) {
-                const int c = 8 * n + g;
-                const float b0 = ld_tile(Bt, r0, c), b1 = ld_tile(Bt, r1, c);
-                if (bias_owner) bsum[n] += (r0 < N ? b0 : 0.f) + (r1 < N ? b1 : 0.f);
+                const float b0 = lds_u32((tb0 ^ (n << 5)) + ks * 1024), b1 = lds_u32((tb1 ^ (n << 5)) + ks * 1024);
                 uint32_t bh[2], bl[2];
-                split_tf32_trunc(b0, bh[0], bl[0]);
-                split_tf32_trunc(b1, bh[1], bl[1]);
+                split_lean(b0, bh[0], bl[0]);
+                split_lean(b1, bh[1], bl[1]);
                 mma_tf32_16x8x8(ccorr[n], al[ks], bh);
                 mma_tf32_16x8x8(cmain[n], ah[ks], bh);
                 mma_tf32_16x8x8(ccorr[n], ah[ks], bl);
               }
             }
-            if (bias_owner) {
-#pragma unroll
-              for (int n = 0; n < 4; ++n) {
-                float v = bsum[n];
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                const int c = cb * 32 + 8 * n + g;
-                if (t == 0 && c < C) dbias_s[(p.concat ? h * C : 0) + c] += v;     // one owner lane per column
-              }
-            }
-#pragma unroll
-            for (int n = 0; n < 4; ++n)
+            if (args.dP_hi16 && vec4_out) {
+              // fp16 pairs, coalesced: a quad exchange gives every lane 4 consecutive columns, so one 8-byte
+              // store per lane writes 32 contiguous bytes per row (the fragment's native 4-byte pieces cost
+              // one partial sector each and bounded this phase)
 #pragma unroll
               for (int hf = 0; hf < 2; ++hf) {
                 const int j = hf ? j1 : j0;
-                const int c = cb * 32 + 8 * n + 2 * t;
-                if (j < N && c < C) {
-                  const float v0 = cmain[n][2 * hf] + ccorr[n][2 * hf], v1 = cmain[n][2 * hf + 1] + ccorr[n][2 * hf + 1];
-                  const bool has1 = c + 1 < C;
-                  if (args.dP_hi16) {
+                uint32_t hi32[4], lo32[4];
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                  const float w0 = (cmain[n][2 * hf] + ccorr[n][2 * hf]) * dp_scale;
+                  const float w1 = (cmain[n][2 * hf + 1] + ccorr[n][2 * hf + 1]) * dp_scale;
+                  const __half2 hh = __floats2half2_rn(w0, w1);
+                  const float2 back = __half22float2(hh);
+                  const __half2 ll = __floats2half2_rn(w0 - back.x, w1 - back.y);
+                  hi32[n] = *reinterpret_cast<const uint32_t*>(&hh);
+                  lo32[n] = *reinterpret_cast<const uint32_t*>(&ll);
+                }
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {           // n-tile pairs (0,1) and (2,3): 16 columns each
+                  const int src = (lane & ~3) + 2 * (t & 1);
+                  const uint32_t ha0 = __shfl_sync(0xffffffffu, hi32[2 * pr], src), ha1 = __shfl_sync(0xffffffffu, hi32[2 * pr + 1], src);
+                  const uint32_t hb0 = __shfl_sync(0xffffffffu, hi32[2 * pr], src + 1), hb1 = __shfl_sync(0xffffffffu, hi32[2 * pr + 1], src + 1);
+                  const uint32_t la0 = __shfl_sync(0xffffffffu, lo32[2 * pr], src), la1 = __shfl_sync(0xffffffffu, lo32[2 * pr + 1], src);
+                  const uint32_t lb0 = __shfl_sync(0xffffffffu, lo32[2 * pr], src + 1), lb1 = __shfl_sync(0xffffffffu, lo32[2 * pr + 1], src + 1);
+                  const bool up = (t >> 1) != 0;           // lanes 2,3 of the quad take the second n-tile of the pair
+                  const int c = cb * 32 + 16 * pr + 8 * (t >> 1) + 4 * (t & 1);
+                  if (j < N && c < C) {
                     const size_t off = ((size_t)b * N + j) * args.ldp16 + (size_t)h * C + c;
-                    const float w0 = v0 * dp_scale, w1 = v1 * dp_scale;
-                    const __half h0_ = __float2half_rn(w0), h1_ = __float2half_rn(w1);
-                    const __half l0_ = __float2half_rn(w0 - __half2float(h0_)), l1_ = __float2half_rn(w1 - __half2float(h1_));
-                    if (p.vec2_ok) {
-                      *reinterpret_cast<__half2*>(args.dP_hi16 + off) = __halves2half2(h0_, h1_);
-                      *reinterpret_cast<__half2*>(args.dP_lo16 + off) = __halves2half2(l0_, l1_);
-                    } else {
-                      args.dP_hi16[off] = h0_; args.dP_lo16[off] = l0_;
-                      if (has1) { args.dP_hi16[off + 1] = h1_; args.dP_lo16[off + 1] = l1_; }
-                    }
-                  } else {
-                    const size_t off = ((size_t)b * N + j) * p.ldp + (size_t)h * C + c;
-                    if (p.vec2_ok) {
-                      *reinterpret_cast<float2*>(args.dP_aug + off) = make_float2(v0, v1);
-                    } else {
-                      args.dP_aug[off] = v0;
-                      if (has1) args.dP_aug[off + 1] = v1;
-                    }
+                    *reinterpret_cast<uint2*>(args.dP_hi16 + off) = make_uint2(up ? ha1 : ha0, up ? hb1 : hb0);
+                    *reinterpret_cast<uint2*>(args.dP_lo16 + off) = make_uint2(up ? la1 : la0, up ? lb1 : lb0);
                   }
                 }
               }
+            } else {
+#pragma unroll
+              for (int n = 0; n < 4; ++n)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                  const int j = hf ? j1 : j0;
+                  const int c = cb * 32 + 8 * n + 2 * t;
+                  if (j < N && c < C) {
+                    const float v0 = cmain[n][2 * hf] + ccorr[n][2 * hf], v1 = cmain[n][2 * hf + 1] + ccorr[n][2 * hf + 1];
+                    const bool has1 = c + 1 < C;
+                    if (args.dP_hi16) {
+                      const size_t off = ((size_t)b * N + j) * args.ldp16 + (size_t)h * C + c;
+                      const float w0 = v0 * dp_scale, w1 = v1 * dp_scale;
+                      const __half h0_ = __float2half_rn(w0), h1_ = __float2half_rn(w1);
+                      const __half l0_ = __float2half_rn(w0 - __half2float(h0_)), l1_ = __float2half_rn(w1 - __half2float(h1_));
+                      if (p.vec2_ok) {
+                        *reinterpret_cast<__half2*>(args.dP_hi16 + off) = __halves2half2(h0_, h1_);
+                        *reinterpret_cast<__half2*>(args.dP_lo16 + off) = __halves2half2(l0_, l1_);
+                      } else {
+                        args.dP_hi16[off] = h0_; args.dP_lo16[off] = l0_;
+                        if (has1) { args.dP_hi16[off + 1] = h1_; args.dP_lo16[off + 1] = l1_; }
+                      }
+                    } else {
+                      const size_t off = ((size_t)b * N + j) * p.ldp + (size_t)h * C + c;
+                      if (p.vec2_ok) {
+                        *reinterpret_cast<float2*>(args.dP_aug + off) = make_float2(v0, v1);
+                      } else {
+                        args.dP_aug[off] = v0;
+                        if (has1) args.dP_aug[off + 1] = v1;
+                      }
+                    }
+                  }
+                }
+            }
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive2(&grp_empty[s]);
+        release_slot();
       }
     }
     bar_sync_compute();                                   // every warp is done with alpha; D is complete
     lap(4);
     // ------------------------------------------------ V: dv += dz'^T . edge rows ------------------------------------------------
     for (int idx = tid; idx < tile_floats; idx += kCT) tile[idx] = 0.f;      // next graph's logits accumulate into zeros
-    for (int c = 0; c < nchunks; ++c, ++ek) {
-      const int s = ek & 1;
-      mbar_wait(&edge_full[s], (ek >> 1) & 1);
+    for (int c = 0; c < nchunks; ++c) {
+      const uint32_t sa = wait_slot();
       const int rows = rows_in(c);
-      const float* Ts = s ? stage1 : stage0;
-      const int row_base = c * pl.chunk_rows;
+      const uint32_t trow = a_toff + (uint32_t)(c * pl.chunk_rows) * 4u;
+      const uint32_t dgh = a_D + (uint32_t)g * head_bytes;                   // head g of the dz' tile (B fragment: n = g)
 #pragma unroll
       for (int uu = 0; uu < kMaxDvUnits; ++uu) {
-        const int u = warp + uu * kW;
-        if (u >= pl.dv_units) continue;                   // warp-uniform
-        const int mt = u % pl.n_mtiles, rg = u / pl.n_mtiles;
-        const int rbeg = rg * pl.dv_rpu, rend = min(rows, rbeg + pl.dv_rpu);
-        if (rbeg >= rend) continue;
-        const int f0 = mt * 16 + g, f1 = f0 + 8;
+        if (dv_mt[uu] < 0 || dv_rb[uu] >= rows) continue;                    // warp-uniform
+        const int rbeg = dv_rb[uu], rend = min(rows, rbeg + pl.dv_rpu);
+        // A = T^T: (m = feature f0 + g | + 8, k = row r0 + t | + 4).  Features past Fe only feed discarded
+        // output rows; rows past rend meet zero B fragments.
+        uint32_t ta = sa + (uint32_t)(((rbeg + t) * Fe + dv_mt[uu] * 16 + g) * 4);
+        const uint32_t row4 = (uint32_t)(4 * Fe * 4);
         float acc[3][4];
 #pragma unroll
         for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
           for (int q = 0; q < 4; ++q) acc[pr][q] = 0.f;
-        for (int r0 = rbeg; r0 < rend; r0 += 8) {
-          // B fragment (k = edge row, n = head): b0 = dz'[r0+t][g], b1 = dz'[r0+t+4][g]
-          float bv[2];
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int r = r0 + t + 4 * half;
-            float val = 0.f;
-            if (r < rend && g < H) {
-              const int code = table_s[row_base + r];
-              if (code >= 0) val = D[(g * N + (code & 0xffff)) * NS + (code >> 16)];
-            }
-            bv[half] = val;
-          }
+        for (int r0 = rbeg; r0 < rend; r0 += 8, ta += 2 * row4) {
+          const int ra = r0 + t, rb = ra + 4;
+          const int to0 = (ra < rend && g < H) ? lds_i32(trow + (uint32_t)ra * 4u) : -1;
+          const int to1 = (rb < rend && g < H) ? lds_i32(trow + (uint32_t)rb * 4u) : -1;
+          const float b0 = to0 >= 0 ? lds_u32(dgh + (uint32_t)to0) : 0.f;
+          const float b1 = to1 >= 0 ? lds_u32(dgh + (uint32_t)to1) : 0.f;
           uint32_t bh[2], bl[2];
-          split_tf32_trunc(bv[0], bh[0], bl[0]);
-          split_tf32_trunc(bv[1], bh[1], bl[1]);
-          const bool k0_ok = r0 + t < rend, k1_ok = r0 + t + 4 < rend;
-          const float* t0p = Ts + (size_t)(r0 + t) * Fe;
-          const float* t1p = t0p + (size_t)4 * Fe;
+          split_lean(b0, bh[0], bl[0]);
+          split_lean(b1, bh[1], bl[1]);
           float a[4];
-          a[0] = (k0_ok && f0 < Fe) ? lds_f32(t0p + f0) : 0.f;
-          a[1] = (k0_ok && f1 < Fe) ? lds_f32(t0p + f1) : 0.f;
-          a[2] = (k1_ok && f0 < Fe) ? lds_f32(t1p + f0) : 0.f;
-          a[3] = (k1_ok && f1 < Fe) ? lds_f32(t1p + f1) : 0.f;
+          a[0] = lds_u32(ta);
+          a[1] = lds_u32(ta + 32);
+          a[2] = lds_u32(ta + row4);
+          a[3] = lds_u32(ta + row4 + 32);
           uint32_t ah[4], al[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) split_tf32_trunc(a[q], ah[q], al[q]);
+          for (int q = 0; q < 4; ++q) split_lean(a[q], ah[q], al[q]);
           mma_tf32_16x8x8(acc[0], al, bh);
           mma_tf32_16x8x8(acc[1], ah, bl);
           mma_tf32_16x8x8(acc[2], ah, bh);
@@ -687,8 +794,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl, const __grid_con
 #pragma unroll
         for (int q = 0; q < 4; ++q) dv_run[uu][q] += (acc[0][q] + acc[1][q]) + acc[2][q];
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive2(&edge_empty[s]);
+      release_slot();
     }
     bar_sync_compute();                                   // tile zeroed, D free for the next graph
     lap(5);
@@ -700,9 +806,8 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl, const __grid_con
   if (Fe > 0) {
 #pragma unroll
     for (int uu = 0; uu < kMaxDvUnits; ++uu) {
-      const int u = warp + uu * kW;
-      if (u < pl.dv_units) {
-        const int mt = u % pl.n_mtiles, rg = u / pl.n_mtiles;
+      if (dv_mt[uu] >= 0) {
+        const int mt = dv_mt[uu], rg = dv_rb[uu] / pl.dv_rpu;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int f = mt * 16 + g + ((q & 2) ? 8 : 0), h = 2 * t + (q & 1);

@@ -29,6 +29,6 @@ for k, nm in enumerate(names):
     print(f"{nm:16s} {buf[k] / n / ctas / 1e3:10.1f} kcycles per CTA per launch")
 
 msb = sum(a.elapsed_time(b) for e in ev for (n0, a), (n1, b) in zip(e[:-1], e[1:]) if n1 == "attn_bwd") / n
-print(f"attn_bwd {msb:.3f} ms/launch (2 CTAs per SM: per-CTA phase totals)")
-for k, nm in enumerate(["B1 logits", "B1 softmax", "B2 dalpha", "B2b softmax bwd", "B3 dP", "B4 dv"]):
-    print(f"{nm:16s} {buf[16 + k] / n / 296 / 1e3:10.1f} kcycles per CTA per launch")
+print(f"attn_bwd {msb:.3f} ms/launch (pipelined kernel, 1 CTA per SM: per-CTA phase totals; /27.7 = per graph)")
+for k, nm in enumerate(["L logits", "S softmax", "A dalpha+smx bwd", "ds out", "D dP", "V dv"]):
+    print(f"{nm:16s} {buf[16 + k] / n / 148 / 1e3:10.1f} kcycles per CTA per launch, of which waiting for data {buf[22 + k] / n / 148 / 1e3:10.1f}")
