@@ -182,11 +182,42 @@ __device__ __forceinline__ void edge_logits_part(const float* Ts, const float4* 
   for (int q = 0; q < 4; ++q) sink(m0 + g + ((q & 2) ? 8 : 0), n + (q & 1), (acc[0][q] + acc[1][q]) + acc[2][q]);
 }
 
+// FIX = true: the reference's default geometry (config/GNN_param.yaml: N=30, H=6, C=500, Fe=3*42, head mean) with
+// every size a compile-time constant: index arithmetic folds, loops get fixed trip counts and the kernel stops
+// re-reading its parameter block inside the hot loops.  FIX = false: the same code with run-time sizes.
+struct FixedGeom {
+  static constexpr int N = 30, H = 6, C = 500, Fe = 126, R = 870, ldp = 3012, ldo = 500;
+  static constexpr int KS = 16, chunk_rows = 48, nchunks = 19, n_cb = 16, hpr = 6, n_rounds = 1, n_mt_chunk = 3, ksplit = 2;
+  static constexpr int n_mtiles = 8, dv_rg = 3, dv_rpu = 16, dv_units = 24, cbs_per_grp_d = 7, n_slots = 5;
+  static constexpr uint32_t slot_bytes = kGrpTiles * kTile;
+};
+
+bool plan_is_fixed_geom(const AttnParams& p, const Bwd2Plan& s) {
+  using F = FixedGeom;
+  return p.N == F::N && p.H == F::H && p.C == F::C && p.Fe == F::Fe && p.R == F::R && p.ldp == F::ldp && p.ldo == F::ldo &&
+         !p.concat && p.bulk_ok && p.vec2_ok && s.KS == F::KS && s.chunk_rows == F::chunk_rows && s.nchunks == F::nchunks &&
+         s.n_cb == F::n_cb && s.hpr == F::hpr && s.n_rounds == F::n_rounds && s.n_mt_chunk == F::n_mt_chunk &&
+         s.ksplit == F::ksplit && s.n_mtiles == F::n_mtiles && s.dv_rg == F::dv_rg && s.dv_rpu == F::dv_rpu &&
+         s.dv_units == F::dv_units && s.cbs_per_grp_d == F::cbs_per_grp_d && s.n_slots == F::n_slots &&
+         s.slot_bytes == F::slot_bytes && s.tma_ok == 1;
+}
+
+template <bool FIX>
 __global__ void __launch_bounds__(kB2Threads, 1)
-gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl, const __grid_constant__ CUtensorMap tmP,
+gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_constant__ CUtensorMap tmP,
                      const __grid_constant__ CUtensorMap tmG) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const AttnParams& p = args.p;
+  AttnParams p = args.p;
+  Bwd2Plan pl = pl_;
+  if (FIX) {
+    using F = FixedGeom;
+    p.N = F::N; p.H = F::H; p.C = F::C; p.Fe = F::Fe; p.R = F::R; p.ldp = F::ldp; p.ldo = F::ldo;
+    p.concat = 0; p.bulk_ok = 1; p.vec2_ok = 1;
+    pl.KS = F::KS; pl.chunk_rows = F::chunk_rows; pl.nchunks = F::nchunks; pl.n_cb = F::n_cb; pl.hpr = F::hpr;
+    pl.n_rounds = F::n_rounds; pl.n_mt_chunk = F::n_mt_chunk; pl.ksplit = F::ksplit; pl.n_mtiles = F::n_mtiles;
+    pl.dv_rg = F::dv_rg; pl.dv_rpu = F::dv_rpu; pl.dv_units = F::dv_units; pl.cbs_per_grp_d = F::cbs_per_grp_d;
+    pl.n_slots = F::n_slots; pl.slot_bytes = F::slot_bytes; pl.tma_ok = 1;
+  }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, H = p.H, C = p.C, Fe = p.Fe, HC = H * C;
   constexpr int NS = kNS2;
@@ -854,7 +885,7 @@ int launch_attn_bwd2(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t w
     if (int rc = make_tmap(&tmG, a.dout, (uint64_t)p.B * p.N, (uint64_t)p.ldo, (uint64_t)p.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))
       return rc;
   }
-  auto kern = gat_attn_bwd2_kernel;
+  auto kern = plan_is_fixed_geom(p, pl) ? gat_attn_bwd2_kernel<true> : gat_attn_bwd2_kernel<false>;
   SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
   kern<<<grid, kB2Threads, pl.total, st>>>(a, pl, tmP, tmG);
   SPOTV2_CUDA_OK(cudaGetLastError());
