@@ -16,6 +16,8 @@
 //     A  dalpha_h = g dO_h P_h^T         warp = (head, 16-target tile); K = channels streamed as tile groups;
 //        softmax/LeakyReLU backward directly on the accumulator fragments (row sums by 4-lane shuffles),
 //        dd -> global, ds partials, dz' (mean-fill redistributed) -> shared D tile
+//     (V runs before D so that the second pass over the edge rows still finds them in L2: the first pass
+//      loads them with an evict-last hint, everything else streams evict-first)
 //     D  dP_h = g alpha_h^T dO_h         warp = (head, 16-source tile), alpha^T fragments in registers,
 //        results stored as scaled fp16 hi/lo pairs (tensor-core GEMM operand) or fp32; dbias column sums
 //     V  dv^T[f,h] += T^T dz'            warp = (16-feature tile, row group) over the second edge pass
@@ -270,7 +272,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
     // same swizzled layout
     auto put_tile = [&](unsigned char* dst, const CUtensorMap* tm, const float* base, int ld, int col0, int row0, uint64_t* full) {
       if (pl.tma_ok) {
-        if (lane == 0) tma_load_2d(dst, tm, col0, row0, full);
+        if (lane == 0) tma_load_2d_hint(dst, tm, col0, row0, full, kEvictFirst);
       } else {
         for (int idx = lane; idx < 32 * 32; idx += 32) {
           const int r = idx >> 5, c = idx & 31;
@@ -294,7 +296,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
       }
       if (++slot == pl.n_slots) { slot = 0; sph ^= 1; }
     };
-    auto edge_chunk = [&](int b, int c) {
+    auto edge_chunk = [&](int b, int c, uint64_t hint) {
       float* dst = reinterpret_cast<float*>(acquire());
       const int rows = rows_in(c);
       const float* src = p.edge_rows + ((size_t)b * p.R + (size_t)c * pl.chunk_rows) * Fe;
@@ -302,7 +304,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
         if (lane == 0) {
           const uint32_t bytes = (uint32_t)rows * Fe * 4u;
           mbar_expect_tx(&full[slot], bytes);
-          bulk_g2s(dst, src, bytes, &full[slot]);
+          bulk_g2s_hint(dst, src, bytes, &full[slot], hint);
         }
       } else {
         for (int idx = lane; idx < rows * Fe; idx += 32) dst[idx] = src[idx];
@@ -312,7 +314,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
     const int n_grp_d = (n_cb + pl.cbs_per_grp_d - 1) / pl.cbs_per_grp_d;
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
-      for (int c = 0; c < nchunks; ++c) edge_chunk(b, c);                       // phase L
+      for (int c = 0; c < nchunks; ++c) edge_chunk(b, c, kEvictLast);           // phase L (kept in L2 for phase V)
       for (int r = 0; r < pl.n_rounds; ++r) {                                   // phase A: one group per channel block
         const int h0 = r * pl.hpr;
         const int nh = min(pl.hpr, H - h0);
@@ -333,6 +335,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
           publish(pl.tma_ok != 0);
         }
       }
+      for (int c = 0; c < nchunks; ++c) edge_chunk(b, c, kEvictFirst);          // phase V: second and last use
       for (int r = 0; r < pl.n_rounds; ++r) {                                   // phase D: groups of dO tiles
         const int h0 = r * pl.hpr;
         const int nh = min(pl.hpr, H - h0);
@@ -353,7 +356,6 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
           publish(pl.tma_ok != 0);
         }
       }
-      for (int c = 0; c < nchunks; ++c) edge_chunk(b, c);                       // phase V
     }
     return;
   }
@@ -641,6 +643,52 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
       else args.dP_aug[((size_t)b * N + j) * p.ldp + HC + h] = ds;
     }
     lap(3);
+    // ------------------------------------------------ V: dv += dz'^T . edge rows ------------------------------------------------
+    for (int c = 0; c < nchunks; ++c) {
+      const uint32_t sa = wait_slot();
+      const int rows = rows_in(c);
+      const uint32_t trow = a_toff + (uint32_t)(c * pl.chunk_rows) * 4u;
+      const uint32_t dgh = a_D + (uint32_t)g * head_bytes;                   // head g of the dz' tile (B fragment: n = g)
+#pragma unroll
+      for (int uu = 0; uu < kMaxDvUnits; ++uu) {
+        if (dv_mt[uu] < 0 || dv_rb[uu] >= rows) continue;                    // warp-uniform
+        const int rbeg = dv_rb[uu], rend = min(rows, rbeg + pl.dv_rpu);
+        // A = T^T: (m = feature f0 + g | + 8, k = row r0 + t | + 4).  Features past Fe only feed discarded
+        // output rows; rows past rend meet zero B fragments.
+        uint32_t ta = sa + (uint32_t)(((rbeg + t) * Fe + dv_mt[uu] * 16 + g) * 4);
+        const uint32_t row4 = (uint32_t)(4 * Fe * 4);
+        float acc[3][4];
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[pr][q] = 0.f;
+        for (int r0 = rbeg; r0 < rend; r0 += 8, ta += 2 * row4) {
+          const int ra = r0 + t, rb = ra + 4;
+          const int to0 = (ra < rend && g < H) ? lds_i32(trow + (uint32_t)ra * 4u) : -1;
+          const int to1 = (rb < rend && g < H) ? lds_i32(trow + (uint32_t)rb * 4u) : -1;
+          const float b0 = to0 >= 0 ? lds_u32(dgh + (uint32_t)to0) : 0.f;
+          const float b1 = to1 >= 0 ? lds_u32(dgh + (uint32_t)to1) : 0.f;
+          uint32_t bh[2], bl[2];
+          split_lean(b0, bh[0], bl[0]);
+          split_lean(b1, bh[1], bl[1]);
+          float a[4];
+          a[0] = lds_u32(ta);
+          a[1] = lds_u32(ta + 32);
+          a[2] = lds_u32(ta + row4);
+          a[3] = lds_u32(ta + row4 + 32);
+          uint32_t ah[4], al[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) split_lean(a[q], ah[q], al[q]);
+          mma_tf32_16x8x8(acc[0], al, bh);
+          mma_tf32_16x8x8(acc[1], ah, bl);
+          mma_tf32_16x8x8(acc[2], ah, bh);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dv_run[uu][q] += (acc[0][q] + acc[1][q]) + acc[2][q];
+      }
+      release_slot();
+    }
+    lap(5);
     // ------------------------------------------------ D: dP = g alpha^T dO ------------------------------------------------
     for (int r = 0; r < pl.n_rounds; ++r) {
       const int h0 = r * pl.hpr;
@@ -779,56 +827,10 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
         release_slot();
       }
     }
-    bar_sync_compute();                                   // every warp is done with alpha; D is complete
-    lap(4);
-    // ------------------------------------------------ V: dv += dz'^T . edge rows ------------------------------------------------
+    bar_sync_compute();                                   // every warp is done with alpha and with the dz' tile
     for (int idx = tid; idx < tile_floats; idx += kCT) tile[idx] = 0.f;      // next graph's logits accumulate into zeros
-    for (int c = 0; c < nchunks; ++c) {
-      const uint32_t sa = wait_slot();
-      const int rows = rows_in(c);
-      const uint32_t trow = a_toff + (uint32_t)(c * pl.chunk_rows) * 4u;
-      const uint32_t dgh = a_D + (uint32_t)g * head_bytes;                   // head g of the dz' tile (B fragment: n = g)
-#pragma unroll
-      for (int uu = 0; uu < kMaxDvUnits; ++uu) {
-        if (dv_mt[uu] < 0 || dv_rb[uu] >= rows) continue;                    // warp-uniform
-        const int rbeg = dv_rb[uu], rend = min(rows, rbeg + pl.dv_rpu);
-        // A = T^T: (m = feature f0 + g | + 8, k = row r0 + t | + 4).  Features past Fe only feed discarded
-        // output rows; rows past rend meet zero B fragments.
-        uint32_t ta = sa + (uint32_t)(((rbeg + t) * Fe + dv_mt[uu] * 16 + g) * 4);
-        const uint32_t row4 = (uint32_t)(4 * Fe * 4);
-        float acc[3][4];
-#pragma unroll
-        for (int pr = 0; pr < 3; ++pr)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) acc[pr][q] = 0.f;
-        for (int r0 = rbeg; r0 < rend; r0 += 8, ta += 2 * row4) {
-          const int ra = r0 + t, rb = ra + 4;
-          const int to0 = (ra < rend && g < H) ? lds_i32(trow + (uint32_t)ra * 4u) : -1;
-          const int to1 = (rb < rend && g < H) ? lds_i32(trow + (uint32_t)rb * 4u) : -1;
-          const float b0 = to0 >= 0 ? lds_u32(dgh + (uint32_t)to0) : 0.f;
-          const float b1 = to1 >= 0 ? lds_u32(dgh + (uint32_t)to1) : 0.f;
-          uint32_t bh[2], bl[2];
-          split_lean(b0, bh[0], bl[0]);
-          split_lean(b1, bh[1], bl[1]);
-          float a[4];
-          a[0] = lds_u32(ta);
-          a[1] = lds_u32(ta + 32);
-          a[2] = lds_u32(ta + row4);
-          a[3] = lds_u32(ta + row4 + 32);
-          uint32_t ah[4], al[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) split_lean(a[q], ah[q], al[q]);
-          mma_tf32_16x8x8(acc[0], al, bh);
-          mma_tf32_16x8x8(acc[1], ah, bl);
-          mma_tf32_16x8x8(acc[2], ah, bh);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dv_run[uu][q] += (acc[0][q] + acc[1][q]) + acc[2][q];
-      }
-      release_slot();
-    }
-    bar_sync_compute();                                   // tile zeroed, D free for the next graph
-    lap(5);
+    bar_sync_compute();
+    lap(4);
   }
   if (tid == 0)
     for (int k = 0; k < 6; ++k) atomicAdd(&g_bwd2_counters[k], (unsigned long long)ph[k]);
