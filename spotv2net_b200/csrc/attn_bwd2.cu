@@ -445,7 +445,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
       const int rows = rows_in(c);
       if (l_on && (c & 1) == l_hg && l_mt * 16 < rows) {
         // 16 rows x this warp's k blocks (4 k-steps each), 3xTF32; features past Fe meet zero B fragments
-        // (rows and slot tails hold finite stale data: the slots are zero-filled at start)
+        // (k-blocks reaching past Fe are masked below)
         float acc[3][4];
 #pragma unroll
         for (int pr = 0; pr < 3; ++pr)
@@ -464,6 +464,16 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
             a[sl][2] = lds_u32(r0 + ko + sl * 32 + 16);
             a[sl][3] = lds_u32(r1 + ko + sl * 32 + 16);
             bf[sl] = lds128_u32(vf + sl * 512);
+          }
+          if ((kb + 1) * 32 > Fe) {
+            // k-steps reaching past Fe: whatever lies there (stale slot bytes) must not meet the zero B
+            // fragments as NaN/Inf
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) {
+              const int f = kb * 32 + sl * 8 + t;
+              if (f >= Fe) a[sl][0] = a[sl][1] = 0.f;
+              if (f + 4 >= Fe) a[sl][2] = a[sl][3] = 0.f;
+            }
           }
 #pragma unroll
           for (int sl = 0; sl < 4; ++sl) {
@@ -653,8 +663,9 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
       for (int uu = 0; uu < kMaxDvUnits; ++uu) {
         if (dv_mt[uu] < 0 || dv_rb[uu] >= rows) continue;                    // warp-uniform
         const int rbeg = dv_rb[uu], rend = min(rows, rbeg + pl.dv_rpu);
+        const bool partial = rend < rbeg + pl.dv_rpu;
         // A = T^T: (m = feature f0 + g | + 8, k = row r0 + t | + 4).  Features past Fe only feed discarded
-        // output rows; rows past rend meet zero B fragments.
+        // output rows; rows past rend are masked (they also meet zero B fragments).
         uint32_t ta = sa + (uint32_t)(((rbeg + t) * Fe + dv_mt[uu] * 16 + g) * 4);
         const uint32_t row4 = (uint32_t)(4 * Fe * 4);
         float acc[3][4];
@@ -676,6 +687,10 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
           a[1] = lds_u32(ta + 32);
           a[2] = lds_u32(ta + row4);
           a[3] = lds_u32(ta + row4 + 32);
+          if (partial) {                         // rows past the chunk's end hold stale slot bytes
+            if (ra >= rend) a[0] = a[1] = 0.f;
+            if (rb >= rend) a[2] = a[3] = 0.f;
+          }
           uint32_t ah[4], al[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) split_lean(a[q], ah[q], al[q]);

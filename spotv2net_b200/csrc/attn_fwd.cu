@@ -50,12 +50,45 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int NPAIRS, bool VEC2>
+// 32-bit shared-window address forms of the hot-loop accesses (generic pointers make the compiler re-derive the
+// window base before every access) and the 2-op tf32 split: the tensor core reads only the top 19 bits of a
+// tf32 operand register, so "hi" is the raw fp32 pattern and only lo = x - trunc(x) costs ALU work.
+__device__ __forceinline__ float f_lds(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 f_lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int f_ldsi(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void f_sts(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void split_lean(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x);
+  lo = __float_as_uint(x - __uint_as_float(hi & 0xffffe000u));
+}
+
+// FIX: the reference's default geometry (N=30, H=6, C=500, Fe=126, head mean, PyG edge order) as compile-time
+// constants, so index arithmetic folds and the parameter block is not re-read inside the hot loops.
+template <int NPAIRS, bool VEC2, bool FIX>
 __global__ void __launch_bounds__(kFwdThreads, 1)
-gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t off_ptile,
+gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm_, const uint32_t off_ptile,
                     const __grid_constant__ CUtensorMap tmP) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const AttnParams& p = args.p;
+  AttnParams p = args.p;
+  AttnSmem sm = sm_;
+  if (FIX) {
+    p.N = 30; p.H = 6; p.C = 500; p.Fe = 126; p.R = 870; p.concat = 0; p.ldp = 3012; p.ldo = 500; p.bulk_ok = 1; p.vec2_ok = 1;
+    sm.NS = 40; sm.KS = 16; sm.NT = 1; sm.chunk_rows = kFwdChunkRows3;
+  }
   const int tid = threadIdx.x;
   const int N = p.N, H = p.H, C = p.C, NS = sm.NS;
   const int HC = H * C;
@@ -92,7 +125,16 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
     for (int r = 0; r < 2; ++r) { mbar_init(&sd_full[r], 1); mbar_init(&sd_empty[r], 1); }
     fence_mbar_init();
   }
-  for (int r = tid; r < p.R; r += kFwdThreads) table_s[r] = p.Fe > 0 ? p.table[r] : -1;
+  // row -> byte offset of (source j, target i) inside one head of the alpha tile (-1: row skipped)
+  for (int r = tid; r < p.R; r += kFwdThreads) {
+    const int code = p.Fe > 0 ? p.table[r] : -1;
+    table_s[r] = code >= 0 ? ((code & 0xffff) * NS + (code >> 16)) * 4 : -1;
+  }
+  // the edge ring starts zero-filled: k-steps padded past Fe and rows past the end of a short chunk read stale
+  // bytes (multiplied by zero fragments / discarded), which must be finite numbers
+  for (uint32_t idx = tid; idx < (off_ptile - (uint32_t)sm.off_ring) / 16; idx += kFwdThreads)
+    reinterpret_cast<float4*>(smem_raw + sm.off_ring)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_proxy_async();
   if (p.Fe > 0) build_vfrag(vfrag, p.v, H, p.Fe, sm.KS, sm.NT, tid, kFwdThreads);
   for (int idx = tid; idx < 2 * tile_floats; idx += kFwdThreads) tile0[idx] = 0.f;
   __syncthreads();
@@ -100,6 +142,11 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
   if (tid < kGroupA) {
     // ================================ group A: logits + softmax ================================
     const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t sbase = smem_u32(smem_raw);
+    const uint32_t ring_a[2] = {sbase + (uint32_t)sm.off_ring, sbase + (uint32_t)(sm.off_ring + sm.ring_stage_bytes)};
+    const uint32_t a_vfrag = sbase + (uint32_t)sm.off_vfrag, a_table = sbase + (uint32_t)sm.off_table;
+    const uint32_t a_tile0 = sbase + (uint32_t)sm.off_tile, head_bytes = (uint32_t)(N * NS * 4);
     float* stage[2] = {reinterpret_cast<float*>(smem_raw + sm.off_ring),
                        reinterpret_cast<float*>(smem_raw + sm.off_ring + sm.ring_stage_bytes)};
     const int total_chunks = my_graphs * nchunks;      // this CTA's global chunk stream
@@ -138,17 +185,54 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
         }
         const long long tc0 = clock64();
         if (warp * 16 < rows) {
-          const int row_base = c * sm.chunk_rows;
-          warp_edge_logits<1, 8>(stage[s], vfrag, p.Fe, sm.KS, sm.NT, warp * 16, lane, [&](int r, int h, float val) {
-            if (r < rows && h < H) {
-              const int code = table_s[row_base + r];
-              if (code >= 0) tile[(h * N + (code & 0xffff)) * NS + (code >> 16)] = val;
+          // 16 rows x all k-steps, 3xTF32, 8 k-steps of loads in flight; no index clamps (see the zero fill above)
+          const uint32_t r0 = ring_a[s] + (uint32_t)(((warp * 16 + g) * p.Fe + t) * 4), r1 = r0 + (uint32_t)(8 * p.Fe * 4);
+          float acc[3][4];
+#pragma unroll
+          for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[pr][q] = 0.f;
+          for (int ks0 = 0; ks0 < sm.KS; ks0 += 8) {
+            const uint32_t ko = (uint32_t)ks0 * 32u, vf = a_vfrag + ((uint32_t)ks0 * 32u + (uint32_t)lane) * 16u;
+            float a[8][4];
+            float4 bf[8];
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl) {
+              a[sl][0] = f_lds(r0 + ko + sl * 32);
+              a[sl][1] = f_lds(r1 + ko + sl * 32);
+              a[sl][2] = f_lds(r0 + ko + sl * 32 + 16);
+              a[sl][3] = f_lds(r1 + ko + sl * 32 + 16);
+              bf[sl] = f_lds128(vf + sl * 512);
             }
-          }, &t_mma);
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl) {
+              uint32_t ah[4], al[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) split_lean(a[sl][q], ah[q], al[q]);
+              const uint32_t bh[2] = {__float_as_uint(bf[sl].x), __float_as_uint(bf[sl].y)};
+              const uint32_t bl[2] = {__float_as_uint(bf[sl].z), __float_as_uint(bf[sl].w)};
+              mma_tf32_16x8x8(acc[0], al, bh);
+              mma_tf32_16x8x8(acc[1], ah, bl);
+              mma_tf32_16x8x8(acc[2], ah, bh);
+            }
+          }
+          const int rl = warp * 16 + g, row_base = c * sm.chunk_rows + rl;
+          const int to0 = rl < rows ? f_ldsi(a_table + (uint32_t)row_base * 4u) : -1;
+          const int to1 = rl + 8 < rows ? f_ldsi(a_table + (uint32_t)(row_base + 8) * 4u) : -1;
+          const uint32_t tb = a_tile0 + (uint32_t)(buf * tile_floats * 4) + (uint32_t)(2 * t) * head_bytes;
+          if (to0 >= 0) {
+            if (2 * t < H) f_sts(tb + (uint32_t)to0, (acc[0][0] + acc[1][0]) + acc[2][0]);
+            if (2 * t + 1 < H) f_sts(tb + head_bytes + (uint32_t)to0, (acc[0][1] + acc[1][1]) + acc[2][1]);
+          }
+          if (to1 >= 0) {
+            if (2 * t < H) f_sts(tb + (uint32_t)to1, (acc[0][2] + acc[1][2]) + acc[2][2]);
+            if (2 * t + 1 < H) f_sts(tb + head_bytes + (uint32_t)to1, (acc[0][3] + acc[1][3]) + acc[2][3]);
+          }
         }
         const long long tc1 = clock64();
         bar_sync_group_a();                              // stage s consumed by all three warps
         t_call += tc1 - tc0;
+        (void)t_mma;
         t_bar += clock64() - tc1;
         if (p.bulk_ok && tid == 0 && k + 2 < total_chunks) issue(k + 2);
       }
@@ -166,7 +250,9 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
     // ================================ group B: aggregation on mma.sync ================================
     const int wb = (tid - kGroupA) >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const unsigned char* ptiles = smem_raw + off_ptile;
+    const uint32_t a_ptiles = smem_u32(smem_raw) + off_ptile;
+    const uint32_t fb_k0 = (uint32_t)(t * 128 + ((((g >> 2) ^ t)) << 4) + ((g & 3) << 2));
+    const uint32_t fb_k1 = (uint32_t)((t + 4) * 128 + ((((g >> 2) ^ t ^ 4)) << 4) + ((g & 3) << 2));
     uint32_t q_base = 0;                                   // tiles issued before the current (pass, head) group
     long long w_tf = 0, w_pf = 0;
     const long long t_role = clock64();
@@ -234,26 +320,25 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm, const uint32_t of
               const float a1 = (j0 < N) ? base[j0 * NS + i0 + 8] : 0.f;
               const float a2 = (j0 + 4 < N) ? base[(j0 + 4) * NS + i0] : 0.f;
               const float a3 = (j0 + 4 < N) ? base[(j0 + 4) * NS + i0 + 8] : 0.f;
-              split_tf32_trunc(a0, ah[m][ks][0], al[m][ks][0]);
-              split_tf32_trunc(a1, ah[m][ks][1], al[m][ks][1]);
-              split_tf32_trunc(a2, ah[m][ks][2], al[m][ks][2]);
-              split_tf32_trunc(a3, ah[m][ks][3], al[m][ks][3]);
+              split_lean(a0, ah[m][ks][0], al[m][ks][0]);
+              split_lean(a1, ah[m][ks][1], al[m][ks][1]);
+              split_lean(a2, ah[m][ks][2], al[m][ks][2]);
+              split_lean(a3, ah[m][ks][3], al[m][ks][3]);
             }
           const uint32_t q = q_base + wb;
           const int slot = q % kPSlots;
           mbar_wait_timed(&ptile_full[slot], (q / kPSlots) & 1, w_pf);
-          const unsigned char* pt = ptiles + (size_t)slot * kPTileBytes;
+          // k-major fragment (rows 8ks+t | +4 = sources, cols 8n+g = channels) of the 128B-swizzled tile:
+          // (base ^ (n << 5)) + ks*1024, two per-lane bases for the +0 / +4 rows
+          const uint32_t pt0 = a_ptiles + (uint32_t)slot * kPTileBytes + fb_k0, pt1 = a_ptiles + (uint32_t)slot * kPTileBytes + fb_k1;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const int r0 = ks * 8 + t, r1 = r0 + 4;         // source rows of b0 / b1
 #pragma unroll
             for (int n = 0; n < 4; ++n) {
-              const int c = n * 8 + g;                      // channel within the block
-              const float b0 = *reinterpret_cast<const float*>(pt + r0 * 128 + ((((c >> 2) ^ (r0 & 7)) << 4) | ((c & 3) << 2)));
-              const float b1 = *reinterpret_cast<const float*>(pt + r1 * 128 + ((((c >> 2) ^ (r1 & 7)) << 4) | ((c & 3) << 2)));
+              const float b0 = f_lds((pt0 ^ (n << 5)) + ks * 1024), b1 = f_lds((pt1 ^ (n << 5)) + ks * 1024);
               uint32_t bh[2], bl[2];
-              split_tf32_trunc(b0, bh[0], bl[0]);
-              split_tf32_trunc(b1, bh[1], bl[1]);
+              split_lean(b0, bh[0], bl[0]);
+              split_lean(b1, bh[1], bl[1]);
 #pragma unroll
               for (int m = 0; m < 2; ++m) {
                 mma_tf32_16x8x8(ccorr[m][n], al[m][ks], bh);
@@ -348,7 +433,8 @@ static int launch_fwd(const AttnFwdArgs& a, cudaStream_t st) {
     s.base_total = s.off_ring;
     return s;
   };
-  auto ptile_off = [&](const AttnSmem& s) { return round_up(s.off_ring + 2 * s.ring_stage_bytes, 1024); };
+  // + 256: zero pad behind the ring (k-steps padded past Fe read up to 63 floats beyond the last staged row)
+  auto ptile_off = [&](const AttnSmem& s) { return round_up(s.off_ring + 2 * s.ring_stage_bytes + 256, 1024); };
   auto total = [&](const AttnSmem& s) { return ptile_off(s) + (size_t)(kPSlots + 2) * kPTileBytes; };
   AttnSmem sm = finish(attn_smem_plan(p.N, p.Fe, p.H, p.R, NPAIRS, kFwdChunkRows3));
   for (int rows = kFwdChunkRows3 - 16; rows >= 16 && total(sm) > 227 * 1024; rows -= 16)
@@ -359,7 +445,9 @@ static int launch_fwd(const AttnFwdArgs& a, cudaStream_t st) {
   CUtensorMap tmP;      // P_aug as [B*N rows, ldp cols]; tiles of 32 rows x 32 channels
   if (int rc = make_tmap(&tmP, p.P_aug, (uint64_t)p.B * p.N, (uint64_t)p.ldp, (uint64_t)p.ldp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))
     return rc;
-  auto kern = gat_attn_fwd_kernel<NPAIRS, VEC2>;
+  const bool fix = NPAIRS == 15 && VEC2 && p.N == 30 && p.H == 6 && p.C == 500 && p.Fe == 126 && p.R == 870 && !p.concat && p.ldp == 3012 &&
+                   p.ldo == 500 && p.bulk_ok && sm.NS == 40 && sm.KS == 16 && sm.chunk_rows == kFwdChunkRows3;
+  auto kern = fix ? gat_attn_fwd_kernel<NPAIRS, VEC2, (NPAIRS == 15 && VEC2)> : gat_attn_fwd_kernel<NPAIRS, VEC2, false>;
   SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = sm_count();
   if (grid > p.B) grid = p.B;

@@ -348,6 +348,36 @@ __global__ void split_f16_kernel(const float* __restrict__ src, int rows, int co
   }
 }
 
+// vec4 fast path: one row per block, no index division; 8-byte stores of 4 fp16 values
+__global__ void __launch_bounds__(256)
+split_f16_rows_kernel(const float* __restrict__ src, int cols4, size_t ld, int split_dim, int split_at,
+                      const float* __restrict__ pre2, int pre_split, __half* __restrict__ hi, __half* __restrict__ lo,
+                      size_t ld16, float* __restrict__ blk) {
+  const unsigned* bits = reinterpret_cast<const unsigned*>(blk);
+  const float s0 = scale_from_amax(__uint_as_float(bits[0])), s1 = scale_from_amax(__uint_as_float(bits[1]));
+  if (blockIdx.x == 0 && threadIdx.x == 0) { blk[2] = 1.f / s0; blk[3] = 1.f / s1; blk[4] = s0; blk[5] = s1; }
+  const int r = blockIdx.x;
+  const float pre = pre2 ? pre2[r >= pre_split ? 1 : 0] : 1.f;
+  const float row_scale = pre * ((split_dim == 0 && r >= split_at) ? s1 : s0);
+  const float4* srow = reinterpret_cast<const float4*>(src + (size_t)r * ld);
+  uint2* hrow = reinterpret_cast<uint2*>(hi + (size_t)r * ld16);
+  uint2* lrow = reinterpret_cast<uint2*>(lo + (size_t)r * ld16);
+  for (int c4 = threadIdx.x; c4 < cols4; c4 += 256) {
+    const float4 v = ldg_stream4(reinterpret_cast<const float*>(srow + c4));
+    float sc[4] = {row_scale, row_scale, row_scale, row_scale};
+    if (split_dim == 1) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sc[e] = pre * ((4 * c4 + e >= split_at) ? s1 : s0);
+    }
+    const float x0 = v.x * sc[0], x1 = v.y * sc[1], x2 = v.z * sc[2], x3 = v.w * sc[3];
+    const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+    const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(x0 - b01.x, x1 - b01.y), l23 = __floats2half2_rn(x2 - b23.x, x3 - b23.y);
+    hrow[c4] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    lrow[c4] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+  }
+}
+
 }  // namespace
 
 __global__ void amax_flat_kernel(const float* __restrict__ src, size_t n, unsigned* __restrict__ out_bits) {
@@ -378,18 +408,43 @@ int amax_flat(const float* src, size_t n, float* blk, cudaStream_t st) {
   return SPOTV2_OK;
 }
 
+static int launch_amax_flat(const float* src, size_t n, unsigned* out, cudaStream_t st) {
+  if (n == 0) return SPOTV2_OK;
+  amax_flat_kernel<<<(unsigned)std::min<size_t>((n / 4 + 255) / 256 + 1, 8 * 148), 256, 0, st>>>(src, n, out);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
 int split_f16(const float* src, int rows, int cols, size_t ld, int split_dim, int split_at, const float* pre2,
               int pre_split, void* hi, void* lo, size_t ld16, float* blk, cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return SPOTV2_OK;
   SPOTV2_CUDA_OK(cudaMemsetAsync(blk, 0, 8 * sizeof(float), st));
   const size_t total = (size_t)rows * cols;
   const unsigned blocks = (unsigned)std::min<size_t>((total + 1023) / 1024, 16 * 148);
-  amax_kernel<<<blocks, 256, 0, st>>>(src, rows, cols, ld, split_dim, split_at, pre2, pre_split,
-                                      reinterpret_cast<unsigned*>(blk));
+  unsigned* bits = reinterpret_cast<unsigned*>(blk);
+  // group maxima: contiguous row ranges go through the vectorised flat kernel
+  const bool flat_ok = !pre2 && ld == (size_t)cols && aligned16(src) && (split_dim == 0 || split_at >= cols);
+  if (flat_ok) {
+    const int r_split = (split_dim == 0 && split_at < rows) ? (split_at > 0 ? split_at : 0) : rows;
+    const bool second_aligned = ((size_t)r_split * cols) % 4 == 0;
+    if (r_split < rows && !second_aligned) {
+      amax_kernel<<<blocks, 256, 0, st>>>(src, rows, cols, ld, split_dim, split_at, pre2, pre_split, bits);
+    } else {
+      if (int rc = launch_amax_flat(src, (size_t)r_split * cols, bits, st)) return rc;
+      if (r_split < rows)
+        if (int rc = launch_amax_flat(src + (size_t)r_split * cols, (size_t)(rows - r_split) * cols, bits + 1, st)) return rc;
+    }
+  } else {
+    amax_kernel<<<blocks, 256, 0, st>>>(src, rows, cols, ld, split_dim, split_at, pre2, pre_split, bits);
+  }
   const int vec4 = (cols % 4 == 0) && (ld % 4 == 0) && (ld16 % 4 == 0) && aligned16(src) &&
                    ((reinterpret_cast<uintptr_t>(hi) & 7) == 0) && ((reinterpret_cast<uintptr_t>(lo) & 7) == 0);
-  split_f16_kernel<<<blocks, 256, 0, st>>>(src, rows, cols, ld, split_dim, split_at, pre2, pre_split, 1.f,
-                                           static_cast<__half*>(hi), static_cast<__half*>(lo), ld16, blk, vec4);
+  if (vec4)
+    split_f16_rows_kernel<<<rows, 256, 0, st>>>(src, cols / 4, ld, split_dim, split_at, pre2, pre_split, static_cast<__half*>(hi),
+                                               static_cast<__half*>(lo), ld16, blk);
+  else
+    split_f16_kernel<<<blocks, 256, 0, st>>>(src, rows, cols, ld, split_dim, split_at, pre2, pre_split, 1.f,
+                                             static_cast<__half*>(hi), static_cast<__half*>(lo), ld16, blk, 0);
   SPOTV2_CUDA_OK(cudaGetLastError());
   return SPOTV2_OK;
 }
