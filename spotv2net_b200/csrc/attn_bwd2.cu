@@ -130,8 +130,8 @@ __device__ __forceinline__ float4 lds128_u32(uint32_t a) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
-__device__ __forceinline__ void red_add_u32(uint32_t a, float v) {
-  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+__device__ __forceinline__ void sts_u32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
 }
 // tf32 split for mma.sync operands: the tensor core reads only the top 19 bits of a tf32 operand register
 // (verified by the parity tests), so "hi" is the raw fp32 pattern and only lo = x - trunc(x) costs ALU work.
@@ -382,10 +382,11 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
   const uint32_t head_bytes = (uint32_t)(N * NS * 4);
   // fragment bases inside a 128B-swizzled 32x32 tile (row r, col c at r*128 + (((c>>2) ^ (r&7)) << 4) + (c&3)*4):
   //   row-major operand fragments (rows g / 8n+g, cols 8ks+t):  base ^ (ks << 5)  and  base ^ ((2ks+1) << 4)
-  //   k-major operand fragments (rows 8ks+t / +4, cols 8n+g):   base ^ (n << 5), + ks*1024
+  //   k-major operand fragments (rows 8ks+2t / +1, cols 8n+g):  base ^ (n << 5), + ks*1024
   const uint32_t fb_row = (uint32_t)(g * 128 + (g << 4) + (t << 2));
-  const uint32_t fb_k0 = (uint32_t)(t * 128 + ((((g >> 2) ^ t)) << 4) + ((g & 3) << 2));
-  const uint32_t fb_k1 = (uint32_t)((t + 4) * 128 + ((((g >> 2) ^ t ^ 4)) << 4) + ((g & 3) << 2));
+  // (MMA k index t <-> tile row 2t, t+4 <-> 2t+1: the 4 x 2 chunk slots of one load are then all distinct)
+  const uint32_t fb_k0 = (uint32_t)((2 * t) * 128 + ((((g >> 2) ^ (2 * t))) << 4) + ((g & 3) << 2));
+  const uint32_t fb_k1 = (uint32_t)((2 * t + 1) * 128 + ((((g >> 2) ^ (2 * t + 1))) << 4) + ((g & 3) << 2));
 
   // phase V units of this warp (feature tile, row group): fixed for the whole kernel
   int dv_mt[kMaxDvUnits], dv_rb[kMaxDvUnits];
@@ -403,8 +404,10 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
   const int l_hg = warp / (kW / 2), l_w6 = warp - l_hg * (kW / 2);
   const int l_mt = pl.n_mt_chunk > 0 ? l_w6 % pl.n_mt_chunk : 0, l_kh = pl.n_mt_chunk > 0 ? l_w6 / pl.n_mt_chunk : 0;
   const bool l_on = pl.n_mt_chunk > 0 && l_kh < pl.ksplit;
-  const uint32_t l_row0 = (uint32_t)(((l_mt * 16 + g) * Fe + t) * 4);       // row g of the tile, feature t
-  const uint32_t l_hoff0 = (uint32_t)(2 * t) * head_bytes, l_hoff1 = l_hoff0 + head_bytes;
+  // MMA row g <-> chunk row 2g, row g+8 <-> 2g+1: with the 126-float row pitch the 8 even (odd) rows start 4 banks
+  // apart, so the 32 lanes of a fragment load hit 32 distinct banks
+  const uint32_t l_row0 = (uint32_t)(((l_mt * 16 + 2 * g) * Fe + t) * 4);
+  const uint32_t l_hoff0 = (uint32_t)(2 * t) * head_bytes;
 
   // slot cursor: every compute warp walks the slots in the producer's order
   int slot = 0;
@@ -451,7 +454,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
         for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
           for (int q = 0; q < 4; ++q) acc[pr][q] = 0.f;
-        const uint32_t r0 = sa + l_row0, r1 = r0 + (uint32_t)(8 * Fe * 4);
+        const uint32_t r0 = sa + l_row0, r1 = r0 + (uint32_t)(Fe * 4);
         for (int kb = l_kh; kb < pl.KS / 4; kb += pl.ksplit) {
           const uint32_t ko = (uint32_t)kb * 128u;                 // 4 k-steps x 8 features x 4 bytes
           const uint32_t vf = a_vfrag + ((uint32_t)(kb * 4) * 32u + (uint32_t)lane) * 16u;
@@ -487,19 +490,21 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
             mma_tf32_16x8x8(acc[2], ah, bh);
           }
         }
-        const int row_base = c * pl.chunk_rows + l_mt * 16 + g;
-        const int rl = l_mt * 16 + g;
+        // k half 0 stores into the alpha tile, k half 1 into the (idle) dz' tile; the softmax adds them: no atomics,
+        // fixed summation order
+        const int rl = l_mt * 16 + 2 * g, row_base = c * pl.chunk_rows + rl;
         const int to0 = rl < rows ? lds_i32(a_toff + (uint32_t)row_base * 4u) : -1;
-        const int to1 = rl + 8 < rows ? lds_i32(a_toff + (uint32_t)(row_base + 8) * 4u) : -1;
+        const int to1 = rl + 1 < rows ? lds_i32(a_toff + (uint32_t)(row_base + 1) * 4u) : -1;
         const float v0 = (acc[0][0] + acc[1][0]) + acc[2][0], v1 = (acc[0][1] + acc[1][1]) + acc[2][1];
         const float v2 = (acc[0][2] + acc[1][2]) + acc[2][2], v3 = (acc[0][3] + acc[1][3]) + acc[2][3];
+        const uint32_t tb = (l_kh == 0 ? a_tile : a_D) + l_hoff0;
         if (to0 >= 0) {
-          if (2 * t < H) red_add_u32(a_tile + l_hoff0 + (uint32_t)to0, v0);
-          if (2 * t + 1 < H) red_add_u32(a_tile + l_hoff1 + (uint32_t)to0, v1);
+          if (2 * t < H) sts_u32(tb + (uint32_t)to0, v0);
+          if (2 * t + 1 < H) sts_u32(tb + head_bytes + (uint32_t)to0, v1);
         }
         if (to1 >= 0) {
-          if (2 * t < H) red_add_u32(a_tile + l_hoff0 + (uint32_t)to1, v2);
-          if (2 * t + 1 < H) red_add_u32(a_tile + l_hoff1 + (uint32_t)to1, v3);
+          if (2 * t < H) sts_u32(tb + (uint32_t)to1, v2);
+          if (2 * t + 1 < H) sts_u32(tb + head_bytes + (uint32_t)to1, v3);
         }
       }
       release_slot();
@@ -507,7 +512,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
     bar_sync_compute();
     lap(0);
     // ------------------------------------------------ S: softmax ------------------------------------------------
-    softmax_phase(p, asm_, tile, sd, 1.f, nullptr, pos_mask, tid, kCT);
+    softmax_phase(p, asm_, tile, sd, 1.f, nullptr, pos_mask, tid, kCT, -1, 0, (nchunks > 0 && pl.ksplit == 2) ? D : nullptr);
     bar_sync_compute();
     lap(1);
     // ------------------------------------------------ A: dalpha + softmax backward ------------------------------------------------
@@ -666,15 +671,18 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
         const bool partial = rend < rbeg + pl.dv_rpu;
         // A = T^T: (m = feature f0 + g | + 8, k = row r0 + t | + 4).  Features past Fe only feed discarded
         // output rows; rows past rend are masked (they also meet zero B fragments).
-        uint32_t ta = sa + (uint32_t)(((rbeg + t) * Fe + dv_mt[uu] * 16 + g) * 4);
-        const uint32_t row4 = (uint32_t)(4 * Fe * 4);
+        // k index -> chunk row.  16-row units (the default): k-step s takes rows 4t + 2s (k = t) and 4t + 2s + 1
+        // (k = t+4): rows 4 apart start 8 banks apart with the 126-float pitch, so a fragment load (4 rows x 8
+        // features) is conflict-free.  Other unit sizes: natural order (t, t+4), 8 rows per k-step.
+        const bool perm = pl.dv_rpu == 16;
+        const uint32_t fcol = (uint32_t)((dv_mt[uu] * 16 + g) * 4);
+        const uint32_t rowb = (uint32_t)(Fe * 4);
         float acc[3][4];
 #pragma unroll
         for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
           for (int q = 0; q < 4; ++q) acc[pr][q] = 0.f;
-        for (int r0 = rbeg; r0 < rend; r0 += 8, ta += 2 * row4) {
-          const int ra = r0 + t, rb = ra + 4;
+        auto kstep = [&](int ra, int rb, uint32_t ta, uint32_t tb) {
           const int to0 = (ra < rend && g < H) ? lds_i32(trow + (uint32_t)ra * 4u) : -1;
           const int to1 = (rb < rend && g < H) ? lds_i32(trow + (uint32_t)rb * 4u) : -1;
           const float b0 = to0 >= 0 ? lds_u32(dgh + (uint32_t)to0) : 0.f;
@@ -685,8 +693,8 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
           float a[4];
           a[0] = lds_u32(ta);
           a[1] = lds_u32(ta + 32);
-          a[2] = lds_u32(ta + row4);
-          a[3] = lds_u32(ta + row4 + 32);
+          a[2] = lds_u32(tb);
+          a[3] = lds_u32(tb + 32);
           if (partial) {                         // rows past the chunk's end hold stale slot bytes
             if (ra >= rend) a[0] = a[1] = 0.f;
             if (rb >= rend) a[2] = a[3] = 0.f;
@@ -697,6 +705,15 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
           mma_tf32_16x8x8(acc[0], al, bh);
           mma_tf32_16x8x8(acc[1], ah, bl);
           mma_tf32_16x8x8(acc[2], ah, bh);
+        };
+        if (perm) {
+          const int r4 = rbeg + 4 * t;
+          const uint32_t ta0 = sa + (uint32_t)r4 * rowb + fcol;
+          kstep(r4, r4 + 1, ta0, ta0 + rowb);
+          kstep(r4 + 2, r4 + 3, ta0 + 2 * rowb, ta0 + 3 * rowb);
+        } else {
+          uint32_t ta = sa + (uint32_t)(rbeg + t) * rowb + fcol;
+          for (int r0 = rbeg; r0 < rend; r0 += 8, ta += 8 * rowb) kstep(r0 + t, r0 + t + 4, ta, ta + 4 * rowb);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) dv_run[uu][q] += (acc[0][q] + acc[1][q]) + acc[2][q];
@@ -716,7 +733,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
       if (active) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          const int ia = 8 * ks + t, ib = ia + 4;
+          const int ia = 8 * ks + 2 * t, ib = ia + 1;              // same k permutation as the dO fragments
           const float a0 = j0 < N ? tile[(h * N + j0) * NS + ia] * g_scale : 0.f;
           const float a1 = j1 < N ? tile[(h * N + j1) * NS + ia] * g_scale : 0.f;
           const float a2 = j0 < N ? tile[(h * N + j0) * NS + ib] * g_scale : 0.f;

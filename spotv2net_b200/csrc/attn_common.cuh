@@ -205,7 +205,8 @@ __device__ __forceinline__ void edge_logit_phase(EdgeRing& ring, const AttnParam
 __device__ __forceinline__ void softmax_phase(const AttnParams& p, const AttnSmem& sm, float* tile,
                                               const float* sd, float out_scale, float* alpha_out_b,
                                               uint32_t* pos_mask, int tid, int nthreads = kAttnThreads,
-                                              int sd_j_stride = -1, int sd_swizzled = 0) {
+                                              int sd_j_stride = -1, int sd_swizzled = 0,
+                                              const float* tile_add = nullptr) {
   const int N = p.N, H = p.H, NS = sm.NS;
   // s_j = sd(j, h), d_i = sd(i, H + h).  sd is either a packed [N][2H] array or (sd_swizzled) a
   // 128B-swizzled TMA tile of 32 rows x 32 floats holding the 2H augmented columns of P_aug.
@@ -216,6 +217,12 @@ __device__ __forceinline__ void softmax_phase(const AttnParams& p, const AttnSme
   for (int idx = tid; idx < H * N; idx += nthreads) {
     const int h = idx / N, i = idx - h * N;
     float* col = tile + (size_t)h * N * NS + i;
+    if (tile_add) {            // edge terms arrive as two partial sums (k halves): fold the second one in first
+      const float* col2 = tile_add + (size_t)h * N * NS + i;
+#pragma unroll 6
+      for (int j = 0; j < N; ++j)
+        if (j != i) col[j * NS] += col2[j * NS];
+    }
     float gsum = 0.f;
 #pragma unroll 6
     for (int j = 0; j < N; ++j) gsum += (j != i) ? col[j * NS] : 0.f;

@@ -87,7 +87,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm_, const uint32_t o
   AttnSmem sm = sm_;
   if (FIX) {
     p.N = 30; p.H = 6; p.C = 500; p.Fe = 126; p.R = 870; p.concat = 0; p.ldp = 3012; p.ldo = 500; p.bulk_ok = 1; p.vec2_ok = 1;
-    sm.NS = 40; sm.KS = 16; sm.NT = 1; sm.chunk_rows = kFwdChunkRows3;
+    sm.NS = 36; sm.KS = 16; sm.NT = 1; sm.chunk_rows = kFwdChunkRows3;
   }
   const int tid = threadIdx.x;
   const int N = p.N, H = p.H, C = p.C, NS = sm.NS;
@@ -186,7 +186,8 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm_, const uint32_t o
         const long long tc0 = clock64();
         if (warp * 16 < rows) {
           // 16 rows x all k-steps, 3xTF32, 8 k-steps of loads in flight; no index clamps (see the zero fill above)
-          const uint32_t r0 = ring_a[s] + (uint32_t)(((warp * 16 + g) * p.Fe + t) * 4), r1 = r0 + (uint32_t)(8 * p.Fe * 4);
+          // MMA row g <-> chunk row 2g, g+8 <-> 2g+1: with the 126-float pitch the 8 even (odd) rows start 4 banks apart
+          const uint32_t r0 = ring_a[s] + (uint32_t)(((warp * 16 + 2 * g) * p.Fe + t) * 4), r1 = r0 + (uint32_t)(p.Fe * 4);
           float acc[3][4];
 #pragma unroll
           for (int pr = 0; pr < 3; ++pr)
@@ -216,9 +217,9 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm_, const uint32_t o
               mma_tf32_16x8x8(acc[2], ah, bh);
             }
           }
-          const int rl = warp * 16 + g, row_base = c * sm.chunk_rows + rl;
+          const int rl = warp * 16 + 2 * g, row_base = c * sm.chunk_rows + rl;
           const int to0 = rl < rows ? f_ldsi(a_table + (uint32_t)row_base * 4u) : -1;
-          const int to1 = rl + 8 < rows ? f_ldsi(a_table + (uint32_t)(row_base + 8) * 4u) : -1;
+          const int to1 = rl + 1 < rows ? f_ldsi(a_table + (uint32_t)(row_base + 1) * 4u) : -1;
           const uint32_t tb = a_tile0 + (uint32_t)(buf * tile_floats * 4) + (uint32_t)(2 * t) * head_bytes;
           if (to0 >= 0) {
             if (2 * t < H) f_sts(tb + (uint32_t)to0, (acc[0][0] + acc[1][0]) + acc[2][0]);
@@ -251,8 +252,10 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm_, const uint32_t o
     const int wb = (tid - kGroupA) >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const uint32_t a_ptiles = smem_u32(smem_raw) + off_ptile;
-    const uint32_t fb_k0 = (uint32_t)(t * 128 + ((((g >> 2) ^ t)) << 4) + ((g & 3) << 2));
-    const uint32_t fb_k1 = (uint32_t)((t + 4) * 128 + ((((g >> 2) ^ t ^ 4)) << 4) + ((g & 3) << 2));
+    // MMA k index t <-> source row 2t, t+4 <-> 2t+1 (alpha fragments below use the same permutation): the 4 x 2
+    // chunk slots one fragment load touches in the swizzled tile are then all distinct (no bank conflicts)
+    const uint32_t fb_k0 = (uint32_t)((2 * t) * 128 + ((((g >> 2) ^ (2 * t))) << 4) + ((g & 3) << 2));
+    const uint32_t fb_k1 = (uint32_t)((2 * t + 1) * 128 + ((((g >> 2) ^ (2 * t + 1))) << 4) + ((g & 3) << 2));
     uint32_t q_base = 0;                                   // tiles issued before the current (pass, head) group
     long long w_tf = 0, w_pf = 0;
     const long long t_role = clock64();
@@ -314,12 +317,12 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm_, const uint32_t o
           for (int m = 0; m < 2; ++m)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              const int i0 = m * 16 + g, j0 = ks * 8 + t;
+              const int i0 = m * 16 + g, j0 = ks * 8 + 2 * t;
               const float* base = tile + (size_t)h * N * NS;
               const float a0 = (j0 < N) ? base[j0 * NS + i0] : 0.f;
               const float a1 = (j0 < N) ? base[j0 * NS + i0 + 8] : 0.f;
-              const float a2 = (j0 + 4 < N) ? base[(j0 + 4) * NS + i0] : 0.f;
-              const float a3 = (j0 + 4 < N) ? base[(j0 + 4) * NS + i0 + 8] : 0.f;
+              const float a2 = (j0 + 1 < N) ? base[(j0 + 1) * NS + i0] : 0.f;
+              const float a3 = (j0 + 1 < N) ? base[(j0 + 1) * NS + i0 + 8] : 0.f;
               split_lean(a0, ah[m][ks][0], al[m][ks][0]);
               split_lean(a1, ah[m][ks][1], al[m][ks][1]);
               split_lean(a2, ah[m][ks][2], al[m][ks][2]);
@@ -422,8 +425,9 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm_, const uint32_t o
 template <int NPAIRS, bool VEC2>
 static int launch_fwd(const AttnFwdArgs& a, cudaStream_t st) {
   const AttnParams& p = a.p;
-  // alpha tile stride 40 floats: fragment reads (4 source rows x 8 targets) hit 32 distinct banks
-  const int NS = 40;
+  // alpha tile stride 36 floats: a fragment read touches source rows 2t (t = 0..3) x 8 consecutive targets;
+  // 72 floats between those rows = 8 banks, so the 32 lanes hit 32 distinct banks
+  const int NS = 36;
   const size_t tile_bytes = round_up((size_t)p.H * p.N * NS * 4, 16);
   const size_t sd_bytes = round_up((size_t)p.N * 2 * p.H * 4, 16);
   auto finish = [&](AttnSmem s) {                 // the common plan reserves one tile + one sd; double-buffer both
@@ -446,7 +450,7 @@ static int launch_fwd(const AttnFwdArgs& a, cudaStream_t st) {
   if (int rc = make_tmap(&tmP, p.P_aug, (uint64_t)p.B * p.N, (uint64_t)p.ldp, (uint64_t)p.ldp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))
     return rc;
   const bool fix = NPAIRS == 15 && VEC2 && p.N == 30 && p.H == 6 && p.C == 500 && p.Fe == 126 && p.R == 870 && !p.concat && p.ldp == 3012 &&
-                   p.ldo == 500 && p.bulk_ok && sm.NS == 40 && sm.KS == 16 && sm.chunk_rows == kFwdChunkRows3;
+                   p.ldo == 500 && p.bulk_ok && sm.NS == 36 && sm.KS == 16 && sm.chunk_rows == kFwdChunkRows3;
   auto kern = fix ? gat_attn_fwd_kernel<NPAIRS, VEC2, (NPAIRS == 15 && VEC2)> : gat_attn_fwd_kernel<NPAIRS, VEC2, false>;
   SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = sm_count();
