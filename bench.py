@@ -165,6 +165,7 @@ class HotPath:
         self.W_aug = torch.empty(HC + 2 * H, Fin, **f32)
         self.v = torch.empty(H, Fe, **f32)
         self.P_aug = torch.empty(n, self.desc.ldp, **f32)
+        self.p_amax = torch.empty(8, **f32)
         self.out = torch.empty(n, Cc, **f32)
         self.dout = torch.randn(n, Cc, generator=g, **f32)
         self.tc = bool(self.lib.spotv2_gat_uses_tensor_cores(C.byref(self.desc)))
@@ -206,13 +207,13 @@ class HotPath:
         if self.tc:      # x becomes an fp16 operand pair once per step (forward); the weight-gradient GEMM reuses it
             chk(lib.spotv2_split_f16(p(self.batch.x), self.B * self.N, self.Fin, self.Fin, 0, 0, p(xh), p(xl), self.ldf16,
                                      p(self.x_blk), st), "split_f16")
-        chk(lib.spotv2_proj_fwd(d, p(self.batch.x), p(xh), p(xl), p(self.x_blk), p(self.W_aug), p(self.P_aug), p(self.ws),
-                                self.ws.numel(), st), "proj_fwd")
+        chk(lib.spotv2_proj_fwd(d, p(self.batch.x), p(xh), p(xl), p(self.x_blk), p(self.W_aug), p(self.P_aug), p(self.p_amax),
+                                p(self.ws), self.ws.numel(), st), "proj_fwd")
         mark("proj_fwd")
         chk(lib.spotv2_gat_attn_fwd(d, p(self.P_aug), p(self.batch.edge_attr), p(self.batch.spot_topology.table),
                                     p(self.v), p(L.bias), p(self.out), None, st), "attn_fwd")
         mark("attn_fwd")
-        chk(lib.spotv2_gat_attn_bwd(d, p(self.P_aug), p(self.batch.edge_attr), p(self.batch.spot_topology.table),
+        chk(lib.spotv2_gat_attn_bwd(d, p(self.P_aug), p(self.p_amax), p(self.batch.edge_attr), p(self.batch.spot_topology.table),
                                     p(self.v), p(self.dout), p(self.dP_aug), p(ph), p(pl), p(self.dp_blk), p(self.dv),
                                     p(self.g_b), p(self.ws), self.ws.numel(), st), "attn_bwd")
         mark("attn_bwd")

@@ -126,10 +126,11 @@ int spotv2_split_f16(const float* src, int32_t rows, int32_t cols, int32_t ld, i
 /* lin_src: P_aug [B*N, ldp] = x [B*N, F] . W_aug^T ; columns [0,HC) are P,
  * [HC,HC+H) are s = alpha_src, [HC+H,HC+2H) are d = alpha_dst.
  * x_hi/x_lo/x_scale: optional fp16 pair of x ([B*N, ld16(F)], all three or none); otherwise x is
- * prepared inside the workspace. */
+ * prepared inside the workspace.  p_amax_or_null (8 floats, device): [0] receives the bit pattern of
+ * max |P| over the H*C projection columns, which spotv2_gat_attn_bwd uses to scale its fp16 operands. */
 int spotv2_proj_fwd(const spotv2_gat_desc* d, const float* x, const void* x_hi, const void* x_lo,
-                    const float* x_scale, const float* W_aug, float* P_aug, void* ws, size_t ws_bytes,
-                    void* stream);
+                    const float* x_scale, const float* W_aug, float* P_aug, float* p_amax_or_null,
+                    void* ws, size_t ws_bytes, void* stream);
 
 /* edge_update + softmax + propagate + head reduce + bias ([PyG] gat_conv.py
  * edge_update/message, utils/softmax.py, aggr='add').  edge_rows is [B, R, Fe]
@@ -143,8 +144,10 @@ int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug, const floa
  * dout [B*N, C or HC] -> dP_aug (dP | ds | dd), dv [H, Fe], dbias.  The gradient is emitted either as
  * fp32 dP_aug [B*N, ldp] (CUDA-core GEMM path) or, when dP_hi/dP_lo/dp_scale are given, directly as the
  * fp16 pair [B*N, ld16(HC+2H)] the tensor-core GEMMs consume (two scale groups: columns < HC from a
- * bound on max|dout|, the ds|dd columns from their own maximum); dp_scale is an 8-float scale block. */
-int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug, const float* edge_rows,
+ * bound on max|dout|, the ds|dd columns from their own maximum); dp_scale is an 8-float scale block.
+ * p_amax_or_null: what spotv2_proj_fwd wrote (saves one pass over P_aug). */
+int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug, const float* p_amax_or_null,
+                        const float* edge_rows,
                         const int32_t* table, const float* v, const float* dout, float* dP_aug_or_null,
                         void* dP_hi_or_null, void* dP_lo_or_null, float* dp_scale_or_null,
                         float* dv_or_null, float* dbias_or_null, void* ws, size_t ws_bytes, void* stream);

@@ -40,9 +40,9 @@ SIGNATURES = {
     "spotv2_gat_uses_tensor_cores": (C.c_int, [_DP]),
     "spotv2_gat_ld16": (_i32, [_i32]),
     "spotv2_split_f16": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
-    "spotv2_proj_fwd": (C.c_int, [_DP] + [_vp] * 7 + [_sz, _vp]),
+    "spotv2_proj_fwd": (C.c_int, [_DP] + [_vp] * 8 + [_sz, _vp]),
     "spotv2_gat_attn_fwd": (C.c_int, [_DP] + [_vp] * 8),
-    "spotv2_gat_attn_bwd": (C.c_int, [_DP] + [_vp] * 12 + [_sz, _vp]),
+    "spotv2_gat_attn_bwd": (C.c_int, [_DP] + [_vp] * 13 + [_sz, _vp]),
     "spotv2_proj_bwd_weight": (C.c_int, [_DP] + [_vp] * 10 + [_sz, _vp]),
     "spotv2_proj_bwd_input": (C.c_int, [_DP] + [_vp] * 7 + [_sz, _vp]),
     "spotv2_gat_unfold": (C.c_int, [_DP] + [_vp] * 13),

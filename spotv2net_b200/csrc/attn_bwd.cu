@@ -605,7 +605,7 @@ int bwd_diag_read(unsigned long long* host_out, int reset) {
 
 using namespace spotv2;
 
-extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
+extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug, const float* p_amax_or_null,
                                    const float* edge_rows, const int32_t* table, const float* v,
                                    const float* dout, float* dP_aug_or_null, void* dP_hi_or_null, void* dP_lo_or_null,
                                    float* dp_scale_or_null, float* dv_or_null, float* dbias_or_null, void* ws,
@@ -634,23 +634,30 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
   a.dP_hi16 = static_cast<__half*>(dP_hi_or_null); a.dP_lo16 = static_cast<__half*>(dP_lo_or_null);
   const int HC = d->H * d->C;
   a.ldp16 = ld16_of(HC + 2 * d->H);
-  a.dout_blk = nullptr; a.bound = 1.f; a.dsd = nullptr; a.dp_blk = dp_scale_or_null;
+  a.dout_blk = nullptr; a.p_amax = nullptr; a.bound = 1.f; a.dsd = nullptr; a.dp_blk = dp_scale_or_null;
   cudaStream_t st = as_stream(stream);
-  float* blk_tmp = nullptr;
   const size_t rows = (size_t)d->B * d->N;
+  if (!ws || ws_bytes < attn_bwd_ws_bytes(d))
+    return fail(SPOTV2_ERR_WORKSPACE, "attn_bwd needs %zu B of workspace, got %zu", attn_bwd_ws_bytes(d), ws_bytes);
+  // workspace: per-CTA partials | ds,dd in fp32 [B*N, 2H] | scale blocks (max|dout|, ds|dd scratch, max|P|)
+  const size_t part = attn_bwd_partials_bytes(d);
+  unsigned char* w = static_cast<unsigned char*>(ws);
+  float* blk_dout = reinterpret_cast<float*>(w + part + round_up(rows * 2 * d->H * sizeof(float), 256));
+  float* blk_tmp = blk_dout + kScaleBlockFloats;
+  float* blk_p = blk_tmp + kScaleBlockFloats;
+  // the two big products run on fp16 operand pairs scaled by their tensors' maxima
+  a.dout_blk = blk_dout;
+  if (int rc = amax_flat(dout, rows * (size_t)a.p.ldo, blk_dout, st)) return rc;
+  a.p_amax = p_amax_or_null;
+  if (!a.p_amax) {            // P_aug did not come from spotv2_proj_fwd: one extra pass over it
+    if (int rc = amax_2d(P_aug, (int)rows, HC, (size_t)d->ldp, blk_p, st)) return rc;
+    a.p_amax = blk_p;
+  }
   if (f16) {
-    const size_t part = attn_bwd_partials_bytes(d);
-    if (!ws || ws_bytes < attn_bwd_ws_bytes(d))
-      return fail(SPOTV2_ERR_WORKSPACE, "attn_bwd needs %zu B of workspace, got %zu", attn_bwd_ws_bytes(d), ws_bytes);
-    unsigned char* w = static_cast<unsigned char*>(ws);
     a.dsd = reinterpret_cast<float*>(w + part);
-    float* blk_dout = reinterpret_cast<float*>(w + part + round_up(rows * 2 * d->H * sizeof(float), 256));
-    blk_tmp = blk_dout + kScaleBlockFloats;
-    a.dout_blk = blk_dout;
     // |dP_h[j,c]| = |g sum_i alpha_h[i,j] dO[i,c]| <= g N max|dout|  (g = 1/H for the head mean)
     a.bound = (float)d->N * (d->concat ? 1.f : 1.f / (float)d->H);
     SPOTV2_CUDA_OK(cudaMemsetAsync(dp_scale_or_null, 0, kScaleBlockFloats * sizeof(float), st));
-    if (int rc = amax_flat(dout, rows * (size_t)a.p.ldo, blk_dout, st)) return rc;
   }
   const int np = (d->N + 1) / 2;
   int rc;

@@ -19,7 +19,8 @@ struct AttnBwdArgs {
   __half* dP_hi16;
   __half* dP_lo16;
   int ldp16;
-  const float* dout_blk;
+  const float* dout_blk;   // [0] = bit pattern of max |dout| (always set for the pipelined kernel)
+  const float* p_amax;     // [0] = bit pattern of max |P| over the H*C projection columns (pipelined kernel)
   float bound;
   float* dsd;
   float* dp_blk;       // receives inverse scale [2] and scale [4] of the dP group

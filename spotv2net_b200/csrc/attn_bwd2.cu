@@ -133,6 +133,29 @@ __device__ __forceinline__ float4 lds128_u32(uint32_t a) {
 __device__ __forceinline__ void sts_u32(uint32_t a, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
 }
+__device__ __forceinline__ float2 lds64_u32(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+// D(16x8, f32) += A(16x16, f16, row) * B(16x8, f16, col)
+__device__ __forceinline__ void mma_f16_16x8x16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// Two fp32 values -> packed fp16 "hi" pair and "lo" pair of the scaled values (hi + lo resolves 22 bits; s is a
+// power of two that maps the tensor's largest magnitude below 2^15).  The big products of this kernel run as
+// 3 x m16n8k16 on these pairs: same accuracy as the 3xTF32 split at half the tensor-pipe time (measured:
+// m16n8k16.f16 and m16n8k8.tf32 both issue once per 8 cycles per sub-partition).
+__device__ __forceinline__ void cvt_pair(float x0, float x1, float s, uint32_t& hi, uint32_t& lo) {
+  const float y0 = x0 * s, y1 = x1 * s;
+  const __half2 h = __floats2half2_rn(y0, y1);
+  const float2 b = __half22float2(h);
+  const __half2 l = __floats2half2_rn(y0 - b.x, y1 - b.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 // tf32 split for mma.sync operands: the tensor core reads only the top 19 bits of a tf32 operand register
 // (verified by the parity tests), so "hi" is the raw fp32 pattern and only lo = x - trunc(x) costs ALU work.
 __device__ __forceinline__ void split_lean(float x, uint32_t& hi, uint32_t& lo) {
@@ -372,6 +395,12 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
     dp_scale = dp_scale_from_amax(__uint_as_float(*reinterpret_cast<const unsigned*>(args.dout_blk)) * args.bound);
     if (blockIdx.x == 0 && tid == 0) { args.dp_blk[2] = 1.f / dp_scale; args.dp_blk[4] = dp_scale; }
   }
+  // fp16-pair operand scales of the two big products: dO and P from their tensors' maxima, alpha <= 1 fixed
+  const float s_dO = dp_scale_from_amax(__uint_as_float(*reinterpret_cast<const unsigned*>(args.dout_blk)));
+  const float s_P = dp_scale_from_amax(__uint_as_float(*reinterpret_cast<const unsigned*>(args.p_amax)));
+  constexpr float s_al = 16384.f;
+  const float k_dalpha = g_scale / (s_dO * s_P);                 // accumulator -> dalpha
+  const float k_dp = g_scale * dp_scale / (s_al * s_dO);          // accumulator -> (scaled) dP
   const bool vec4_out = (C % 4 == 0);     // 8-byte aligned groups of 4 fp16 columns (ldp16 % 8 == 0)
   AttnSmem asm_{};                        // what softmax_phase reads
   asm_.NS = NS; asm_.KS = pl.KS; asm_.NT = 1;
@@ -383,7 +412,8 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
   // fragment bases inside a 128B-swizzled 32x32 tile (row r, col c at r*128 + (((c>>2) ^ (r&7)) << 4) + (c&3)*4):
   //   row-major operand fragments (rows g / 8n+g, cols 8ks+t):  base ^ (ks << 5)  and  base ^ ((2ks+1) << 4)
   //   k-major operand fragments (rows 8ks+2t / +1, cols 8n+g):  base ^ (n << 5), + ks*1024
-  const uint32_t fb_row = (uint32_t)(g * 128 + (g << 4) + (t << 2));
+  //   row-major fp16-pair fragments (rows g / 8n+g, col pairs 16ks + 2t + 8hf):  base64 ^ ((4ks + 2hf) << 4)
+  const uint32_t fb_row64 = (uint32_t)(g * 128 + ((g ^ (t >> 1)) << 4) + ((t & 1) << 3));
   // (MMA k index t <-> tile row 2t, t+4 <-> 2t+1: the 4 x 2 chunk slots of one load are then all distinct)
   const uint32_t fb_k0 = (uint32_t)((2 * t) * 128 + ((((g >> 2) ^ (2 * t))) << 4) + ((g & 3) << 2));
   const uint32_t fb_k1 = (uint32_t)((2 * t + 1) * 128 + ((((g >> 2) ^ (2 * t + 1))) << 4) + ((g & 3) << 2));
@@ -522,59 +552,64 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
       const int hl = warp >> 1, m = warp & 1;
       const bool active = (warp < 2 * nh) && (16 * m < N);
       const int h = h0 + hl;
-      const uint32_t d_off = (uint32_t)((p.concat ? 2 * hl : 0) * kTile + m * 2048) + fb_row;
-      const uint32_t p_off = (uint32_t)((p.concat ? 2 * hl + 1 : 1 + hl) * kTile) + fb_row;
+      const uint32_t d_off = (uint32_t)((p.concat ? 2 * hl : 0) * kTile + m * 2048) + fb_row64;
+      const uint32_t p_off = (uint32_t)((p.concat ? 2 * hl + 1 : 1 + hl) * kTile) + fb_row64;
       const int i0 = 16 * m + g, i1 = i0 + 8;
-      float cmain[4][4], ccorr[4][4], dacc[4][4];
+      float cacc[4][4], dacc[4][4];
 #pragma unroll
       for (int n = 0; n < 4; ++n)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) cmain[n][q] = ccorr[n][q] = dacc[n][q] = 0.f;
+        for (int q = 0; q < 4; ++q) cacc[n][q] = dacc[n][q] = 0.f;
       for (int cb = 0; cb < n_cb; ++cb) {
         const uint32_t sa = wait_slot();
         if (active) {
           const uint32_t da = sa + d_off, pa = sa + p_off;
           const bool tail = (cb * 32 + 32 > C);          // channels beyond C: next head's columns (concat) or padding
-          uint32_t ah[4][4], al[4][4];
+          uint32_t ah[2][4], al[2][4];
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            float a0 = lds_u32(da ^ (ks << 5)), a1 = lds_u32((da ^ (ks << 5)) + 1024);
-            float a2 = lds_u32(da ^ ((2 * ks + 1) << 4)), a3 = lds_u32((da ^ ((2 * ks + 1) << 4)) + 1024);
-            if (tail) {
-              if (cb * 32 + 8 * ks + t >= C) a0 = a1 = 0.f;
-              if (cb * 32 + 8 * ks + t + 4 >= C) a2 = a3 = 0.f;
+          for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const uint32_t ad = da ^ ((4 * ks + 2 * hf) << 4);
+              float2 x0 = lds64_u32(ad), x1 = lds64_u32(ad + 1024);
+              if (tail) {
+                const int c = cb * 32 + 16 * ks + 8 * hf + 2 * t;
+                if (c >= C) x0.x = x1.x = 0.f;
+                if (c + 1 >= C) x0.y = x1.y = 0.f;
+              }
+              cvt_pair(x0.x, x0.y, s_dO, ah[ks][2 * hf], al[ks][2 * hf]);
+              cvt_pair(x1.x, x1.y, s_dO, ah[ks][2 * hf + 1], al[ks][2 * hf + 1]);
             }
-            split_lean(a0, ah[ks][0], al[ks][0]);
-            split_lean(a1, ah[ks][1], al[ks][1]);
-            split_lean(a2, ah[ks][2], al[ks][2]);
-            split_lean(a3, ah[ks][3], al[ks][3]);
           }
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
+          for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
             for (int n = 0; n < 4; ++n) {
-              float b0 = lds_u32((pa ^ (ks << 5)) + n * 1024), b1 = lds_u32((pa ^ ((2 * ks + 1) << 4)) + n * 1024);
-              if (tail) {                                  // never let padding bits (possibly NaN) meet the zeros above
-                if (cb * 32 + 8 * ks + t >= C) b0 = 0.f;
-                if (cb * 32 + 8 * ks + t + 4 >= C) b1 = 0.f;
-              }
               uint32_t bh[2], bl[2];
-              split_lean(b0, bh[0], bl[0]);
-              split_lean(b1, bh[1], bl[1]);
-              mma_tf32_16x8x8(ccorr[n], al[ks], bh);
-              mma_tf32_16x8x8(cmain[n], ah[ks], bh);
-              mma_tf32_16x8x8(ccorr[n], ah[ks], bl);
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                float2 y = lds64_u32((pa ^ ((4 * ks + 2 * hf) << 4)) + n * 1024);
+                if (tail) {                                // never let padding bits (possibly NaN) meet the zeros above
+                  const int c = cb * 32 + 16 * ks + 8 * hf + 2 * t;
+                  if (c >= C) y.x = 0.f;
+                  if (c + 1 >= C) y.y = 0.f;
+                }
+                cvt_pair(y.x, y.y, s_P, bh[hf], bl[hf]);
+              }
+              mma_f16_16x8x16(cacc[n], al[ks], bh);        // small terms first
+              mma_f16_16x8x16(cacc[n], ah[ks], bl);
+              mma_f16_16x8x16(cacc[n], ah[ks], bh);
             }
           }
         }
         release_slot();
-        if (active && ((cb & 1) || cb == n_cb - 1)) {       // keep tensor-core accumulation chains short: fold in fp32 RN
+        if (active && ((cb & 3) == 3 || cb == n_cb - 1)) {  // keep tensor-core accumulation chains short: fold in fp32 RN
 #pragma unroll
           for (int n = 0; n < 4; ++n)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              dacc[n][q] += cmain[n][q] + ccorr[n][q];
-              cmain[n][q] = ccorr[n][q] = 0.f;
+              dacc[n][q] += cacc[n][q];
+              cacc[n][q] = 0.f;
             }
         }
       }
@@ -589,7 +624,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
             const int i = (q & 2) ? i1 : i0, j = 8 * n + 2 * t + (q & 1);
             const bool valid = i < N && j < N;
             const float a = valid ? tile[(h * N + j) * NS + i] : 0.f;
-            const float da = valid ? dacc[n][q] * g_scale : 0.f;
+            const float da = valid ? dacc[n][q] * k_dalpha : 0.f;
             al_[n][q] = a;
             dacc[n][q] = da;
             if (q & 2) dot1 = fmaf(a, da, dot1); else dot0 = fmaf(a, da, dot0);
@@ -729,20 +764,19 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
       const bool active = (warp < 2 * nh) && (16 * m < N);
       const int h = h0 + hl;
       const int j0 = 16 * m + g, j1 = j0 + 8;
-      uint32_t ah[4][4], al[4][4];
+      uint32_t ah[2][4], al[2][4];
       if (active) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const int ia = 8 * ks + 2 * t, ib = ia + 1;              // same k permutation as the dO fragments
-          const float a0 = j0 < N ? tile[(h * N + j0) * NS + ia] * g_scale : 0.f;
-          const float a1 = j1 < N ? tile[(h * N + j1) * NS + ia] * g_scale : 0.f;
-          const float a2 = j0 < N ? tile[(h * N + j0) * NS + ib] * g_scale : 0.f;
-          const float a3 = j1 < N ? tile[(h * N + j1) * NS + ib] * g_scale : 0.f;
-          split_lean(a0, ah[ks][0], al[ks][0]);
-          split_lean(a1, ah[ks][1], al[ks][1]);
-          split_lean(a2, ah[ks][2], al[ks][2]);
-          split_lean(a3, ah[ks][3], al[ks][3]);
-        }
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int ia = 16 * ks + 8 * hf + 2 * t;               // k pair (ia, ia+1) = target rows of dO
+            const float2 z = make_float2(0.f, 0.f);
+            const float2 x0 = j0 < N ? *reinterpret_cast<const float2*>(&tile[(h * N + j0) * NS + ia]) : z;
+            const float2 x1 = j1 < N ? *reinterpret_cast<const float2*>(&tile[(h * N + j1) * NS + ia]) : z;
+            cvt_pair(x0.x, x0.y, s_al, ah[ks][2 * hf], al[ks][2 * hf]);
+            cvt_pair(x1.x, x1.y, s_al, ah[ks][2 * hf + 1], al[ks][2 * hf + 1]);
+          }
       }
       const int n_grp = (n_cb + pl.cbs_per_grp_d - 1) / pl.cbs_per_grp_d;
       for (int gi = 0; gi < n_grp; ++gi) {
@@ -768,22 +802,24 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
             const int cb = cb0 + k;
             const uint32_t ta = sa + (uint32_t)(p.concat ? k * nh + hl : k) * kTile;
             const uint32_t tb0 = ta + fb_k0, tb1 = ta + fb_k1;
-            float cmain[4][4], ccorr[4][4];
+            float cacc[4][4];
 #pragma unroll
             for (int n = 0; n < 4; ++n)
 #pragma unroll
-              for (int q = 0; q < 4; ++q) cmain[n][q] = ccorr[n][q] = 0.f;
+              for (int q = 0; q < 4; ++q) cacc[n][q] = 0.f;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
+            for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
               for (int n = 0; n < 4; ++n) {
-                const float b0 = lds_u32((tb0 ^ (n << 5)) + ks * 1024), b1 = lds_u32((tb1 ^ (n << 5)) + ks * 1024);
+                // k pairs (2t, 2t+1) and (2t+8, 2t+9) of this k16 step = dO rows 16ks + ...; column 8n + g
+                const uint32_t a0 = (tb0 ^ (n << 5)) + ks * 2048, a1 = (tb1 ^ (n << 5)) + ks * 2048;
+                const float x0 = lds_u32(a0), x1 = lds_u32(a1), x2 = lds_u32(a0 + 1024), x3 = lds_u32(a1 + 1024);
                 uint32_t bh[2], bl[2];
-                split_lean(b0, bh[0], bl[0]);
-                split_lean(b1, bh[1], bl[1]);
-                mma_tf32_16x8x8(ccorr[n], al[ks], bh);
-                mma_tf32_16x8x8(cmain[n], ah[ks], bh);
-                mma_tf32_16x8x8(ccorr[n], ah[ks], bl);
+                cvt_pair(x0, x1, s_dO, bh[0], bl[0]);
+                cvt_pair(x2, x3, s_dO, bh[1], bl[1]);
+                mma_f16_16x8x16(cacc[n], al[ks], bh);      // small terms first
+                mma_f16_16x8x16(cacc[n], ah[ks], bl);
+                mma_f16_16x8x16(cacc[n], ah[ks], bh);
               }
             }
             if (args.dP_hi16 && vec4_out) {
@@ -796,8 +832,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
                 uint32_t hi32[4], lo32[4];
 #pragma unroll
                 for (int n = 0; n < 4; ++n) {
-                  const float w0 = (cmain[n][2 * hf] + ccorr[n][2 * hf]) * dp_scale;
-                  const float w1 = (cmain[n][2 * hf + 1] + ccorr[n][2 * hf + 1]) * dp_scale;
+                  const float w0 = cacc[n][2 * hf] * k_dp, w1 = cacc[n][2 * hf + 1] * k_dp;
                   const __half2 hh = __floats2half2_rn(w0, w1);
                   const float2 back = __half22float2(hh);
                   const __half2 ll = __floats2half2_rn(w0 - back.x, w1 - back.y);
@@ -828,11 +863,12 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
                   const int j = hf ? j1 : j0;
                   const int c = cb * 32 + 8 * n + 2 * t;
                   if (j < N && c < C) {
-                    const float v0 = cmain[n][2 * hf] + ccorr[n][2 * hf], v1 = cmain[n][2 * hf + 1] + ccorr[n][2 * hf + 1];
+                    // k_dp carries dp_scale (1 in fp32 mode)
+                    const float v0 = cacc[n][2 * hf] * k_dp, v1 = cacc[n][2 * hf + 1] * k_dp;
                     const bool has1 = c + 1 < C;
                     if (args.dP_hi16) {
                       const size_t off = ((size_t)b * N + j) * args.ldp16 + (size_t)h * C + c;
-                      const float w0 = v0 * dp_scale, w1 = v1 * dp_scale;
+                      const float w0 = v0, w1 = v1;
                       const __half h0_ = __float2half_rn(w0), h1_ = __float2half_rn(w1);
                       const __half l0_ = __float2half_rn(w0 - __half2float(h0_)), l1_ = __float2half_rn(w1 - __half2float(h1_));
                       if (p.vec2_ok) {

@@ -45,6 +45,8 @@ struct HParams {
   const float* b_inv;
   int a_split, b_split;
   int scale_in_kernel;  // 0 when a split-K reduce applies the scales
+  unsigned* amax_out;   // optional: bit pattern of max |C[m, n]| over n < amax_cols (splits == 1 only)
+  int amax_cols;
 };
 
 template <int BN, int TBK, bool A_KM, bool B_KM>
@@ -218,12 +220,20 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
       }
       const int row = mt * HBM_ + q * 32 + lane;
       const int col0 = nt * BN + ch * HALF;
+      float row_amax = 0.f;
       if (row < p.M && col0 < p.N) {
         if (p.scale_in_kernel) {      // powers of two: exact
           const float ra = p.a_inv ? p.a_inv[row >= p.a_split ? 1 : 0] : 1.f;
           const float cb0 = ra * (p.b_inv ? p.b_inv[0] : 1.f), cb1 = ra * (p.b_inv ? p.b_inv[1] : 1.f);
 #pragma unroll
           for (int e = 0; e < HALF; ++e) acc[e] *= (col0 + e >= p.b_split) ? cb1 : cb0;
+        }
+        if (p.amax_out) {             // the attention backward sizes its fp16 operand scale from this
+          float mx = 0.f;
+#pragma unroll
+          for (int e = 0; e < HALF; ++e)
+            if (col0 + e < p.amax_cols) mx = fmaxf(mx, fabsf(acc[e]));
+          row_amax = mx;
         }
         float* crow = p.C + (size_t)sp * p.split_stride + (size_t)row * p.ldc + col0;
         const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
@@ -238,6 +248,10 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           for (int e = 0; e < HALF; ++e)
             if (col0 + e < p.N) crow[e] = acc[e];
         }
+      }
+      if (p.amax_out) {
+        for (int o = 16; o > 0; o >>= 1) row_amax = fmaxf(row_amax, __shfl_xor_sync(0xffffffffu, row_amax, o));
+        if (lane == 0 && row_amax > 0.f) atomicMax(p.amax_out, __float_as_uint(row_amax));
       }
     }
   }
@@ -408,6 +422,15 @@ int amax_flat(const float* src, size_t n, float* blk, cudaStream_t st) {
   return SPOTV2_OK;
 }
 
+int amax_2d(const float* src, int rows, int cols, size_t ld, float* blk, cudaStream_t st) {
+  SPOTV2_CUDA_OK(cudaMemsetAsync(blk, 0, 8 * sizeof(float), st));
+  const size_t total = (size_t)rows * cols;
+  const unsigned blocks = (unsigned)std::min<size_t>((total + 1023) / 1024, 16 * 148);
+  amax_kernel<<<blocks, 256, 0, st>>>(src, rows, cols, ld, 0, 0x7fffffff, nullptr, 0, reinterpret_cast<unsigned*>(blk));
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
 static int launch_amax_flat(const float* src, size_t n, unsigned* out, cudaStream_t st) {
   if (n == 0) return SPOTV2_OK;
   amax_flat_kernel<<<(unsigned)std::min<size_t>((n / 4 + 255) / 256 + 1, 8 * 148), 256, 0, st>>>(src, n, out);
@@ -451,7 +474,8 @@ int split_f16(const float* src, int rows, int cols, size_t ld, int split_dim, in
 
 // C[M,N] = A . B^T with operands pre-split into scaled fp16 pairs.  bn: 256 -> TBK 64, 256 + 16 -> TBK 32.
 int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, const F16Operand& B, float* C, int ldc,
-               int splits, int bn, int kb_per_chunk, void* ws, size_t ws_bytes, cudaStream_t st) {
+               int splits, int bn, int kb_per_chunk, void* ws, size_t ws_bytes, cudaStream_t st, float* amax_out,
+               int amax_cols) {
   const int TBK = (bn & 16) ? 32 : 64;
   bn &= ~16;
   if (!tma_available()) return fail(SPOTV2_ERR_NO_DEVICE, "tensor-core GEMM: TMA descriptor encoding is not available");
@@ -470,6 +494,12 @@ int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, c
   p.C = C; p.ldc = ldc; p.split_stride = 0;
   p.a_inv = A.inv; p.b_inv = B.inv; p.a_split = A.split_at; p.b_split = B.split_at;
   p.scale_in_kernel = 1;
+  p.amax_out = reinterpret_cast<unsigned*>(amax_out);
+  p.amax_cols = amax_cols;
+  if (amax_out) {
+    if (splits > 1) return fail(SPOTV2_ERR_INVALID_ARG, "gemm3x_f16: amax_out needs splits == 1");
+    SPOTV2_CUDA_OK(cudaMemsetAsync(amax_out, 0, sizeof(float), st));
+  }
   if (p.splits > 1) {
     const size_t need = (size_t)p.splits * M * N * sizeof(float);
     if (!ws || ws_bytes < need)

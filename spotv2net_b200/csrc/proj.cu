@@ -75,13 +75,16 @@ extern "C" int spotv2_split_f16(const float* src, int32_t rows, int32_t cols, in
 }
 
 extern "C" int spotv2_proj_fwd(const spotv2_gat_desc* d, const float* x, const void* x_hi, const void* x_lo,
-                               const float* x_scale, const float* W_aug, float* P_aug, void* ws, size_t ws_bytes,
-                               void* stream) {
+                               const float* x_scale, const float* W_aug, float* P_aug, float* p_amax_or_null, void* ws,
+                               size_t ws_bytes, void* stream) {
   if (int rc = check_desc(d)) return rc;
   SPOTV2_REQUIRE(x && W_aug && P_aug, "proj_fwd: null pointer");
   const ProjShape s = shape_of(d);
   cudaStream_t st = as_stream(stream);
-  if (!use_tc(d)) return sgemm_simt(true, true, s.rows, s.n_aug, s.F, x, s.F, W_aug, s.F, P_aug, s.ldp, 1, ws, ws_bytes, st);
+  if (!use_tc(d)) {
+    if (int rc = sgemm_simt(true, true, s.rows, s.n_aug, s.F, x, s.F, W_aug, s.F, P_aug, s.ldp, 1, ws, ws_bytes, st)) return rc;
+    return p_amax_or_null ? amax_2d(P_aug, s.rows, s.HC, (size_t)s.ldp, p_amax_or_null, st) : SPOTV2_OK;
+  }
   Carver c{static_cast<unsigned char*>(ws), ws ? ws_bytes : 0};
   float* blk = static_cast<float*>(c.take(2 * kScaleBlockFloats * sizeof(float)));
   const bool have_x = x_hi && x_lo && x_scale;
@@ -99,7 +102,7 @@ extern "C" int spotv2_proj_fwd(const spotv2_gat_desc* d, const float* x, const v
   float* wblk = blk + kScaleBlockFloats;
   if (int rc = split_f16(W_aug, s.n_aug, s.F, s.F, 0, s.HC, nullptr, 0, wh, wl, s.ldf16, wblk, st)) return rc;
   F16Operand A{xh, xl, s.ldf16, xs + 2, kNone}, B{wh, wl, s.ldf16, wblk + 2, s.HC};
-  return gemm3x_f16(true, true, s.rows, s.n_aug, s.F, A, B, P_aug, s.ldp, 1, 256, 0, nullptr, 0, st);
+  return gemm3x_f16(true, true, s.rows, s.n_aug, s.F, A, B, P_aug, s.ldp, 1, 256, 0, nullptr, 0, st, p_amax_or_null, s.HC);
 }
 
 extern "C" int spotv2_proj_bwd_weight(const spotv2_gat_desc* d, const float* x, const void* x_hi, const void* x_lo,

@@ -149,6 +149,7 @@ class _GatLayerFn(torch.autograd.Function):
         ws_f, _, _ = _workspace(desc)
         ws = torch.empty(ws_f, device=dev, dtype=torch.uint8)
         P_aug = torch.empty(n, desc.ldp, device=dev, dtype=torch.float32)
+        p_amax = torch.empty(8, device=dev, dtype=torch.float32)      # max|P|, sizes the backward's fp16 operand scale
         # tensor-core path: x becomes an fp16 operand pair once; the weight-gradient GEMM reuses it
         x16 = x_blk = None
         if lib.spotv2_gat_uses_tensor_cores(C.byref(desc)):
@@ -158,14 +159,14 @@ class _GatLayerFn(torch.autograd.Function):
             check(lib.spotv2_split_f16(ptr(x), n, x.shape[1], x.shape[1], 0, 0, ptr(x16[0]), ptr(x16[1]), ld16,
                                        ptr(x_blk), st), "spotv2_split_f16")
         check(lib.spotv2_proj_fwd(C.byref(desc), ptr(x), ptr(x16[0]) if x16 is not None else None,
-                                  ptr(x16[1]) if x16 is not None else None, ptr(x_blk), ptr(W_aug), ptr(P_aug), ptr(ws),
-                                  ws_f, st), "spotv2_proj_fwd")
+                                  ptr(x16[1]) if x16 is not None else None, ptr(x_blk), ptr(W_aug), ptr(P_aug), ptr(p_amax),
+                                  ptr(ws), ws_f, st), "spotv2_proj_fwd")
         out = torch.empty(n, HC if concat else Cc, device=dev, dtype=torch.float32)
         alpha = torch.empty(topo.B, H, topo.N, topo.N, device=dev, dtype=torch.float32) if want_alpha else None
         check(lib.spotv2_gat_attn_fwd(C.byref(desc), ptr(P_aug), ptr(ea), ptr(topo.table) if Fe else None, ptr(v),
                                       ptr(bias_c), ptr(out), ptr(alpha), st), "spotv2_gat_attn_fwd")
         ctx.desc, ctx.topo, ctx.Fe, ctx.has_bias = desc, topo, Fe, bias is not None
-        ctx.save_for_backward(x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk)
+        ctx.save_for_backward(x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk, p_amax)
         if want_alpha:
             ctx.mark_non_differentiable(alpha)
             return out, alpha
@@ -174,7 +175,7 @@ class _GatLayerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, _dalpha=None):
         lib = _lib.load()
-        x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk = ctx.saved_tensors
+        x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk, p_amax = ctx.saved_tensors
         desc, topo, Fe = ctx.desc, ctx.topo, ctx.Fe
         if ctx.needs_input_grad[1]:
             raise SpotV2Error("gradient w.r.t. edge_attr is not provided (the reference never needs it)")
@@ -196,7 +197,7 @@ class _GatLayerFn(torch.autograd.Function):
         ph, pl = (dP16[0], dP16[1]) if tc else (None, None)
         dv = torch.empty(H, Fe, device=dev, dtype=torch.float32) if Fe else None
         dbias = torch.empty(dout.shape[1], device=dev, dtype=torch.float32) if ctx.has_bias else None
-        check(lib.spotv2_gat_attn_bwd(C.byref(desc), ptr(P_aug), ptr(ea), ptr(topo.table) if Fe else None, ptr(v),
+        check(lib.spotv2_gat_attn_bwd(C.byref(desc), ptr(P_aug), ptr(p_amax), ptr(ea), ptr(topo.table) if Fe else None, ptr(v),
                                       ptr(dout), ptr(dP_aug), ptr(ph), ptr(pl), ptr(dp_blk), ptr(dv), ptr(dbias),
                                       ptr(ws), ws.numel(), st), "spotv2_gat_attn_bwd")
         dW_aug = torch.empty_like(W_aug)

@@ -165,7 +165,9 @@ def test_projection_gemms(cuda_lib, shape, algo):
         return max(lo, hi)
 
     P = torch.zeros(n, ldp, device=DEV)
-    check(cuda_lib.spotv2_proj_fwd(C.byref(d), ptr(xg), None, None, None, ptr(Wg), ptr(P), ptr(ws), ws.numel(), st()), "proj_fwd")
+    pmax = torch.zeros(8, device=DEV)
+    check(cuda_lib.spotv2_proj_fwd(C.byref(d), ptr(xg), None, None, None, ptr(Wg), ptr(P), ptr(pmax), ptr(ws), ws.numel(), st()), "proj_fwd")
+    assert pmax[:1].view(torch.int32).view(torch.float32).item() == P[:, :HC].abs().max().item()   # max|P| as the backward wants it
     assert grouped_relerr(P[:, :n_aug], x.double() @ W_aug.double().t(), HC, 1) < TOL
     dW = torch.empty(n_aug, Fin, device=DEV)
     check(cuda_lib.spotv2_proj_bwd_weight(C.byref(d), ptr(xg), None, None, None, ptr(dPg), None, None, None, ptr(dW), ptr(ws),
@@ -182,7 +184,7 @@ def test_projection_gemms(cuda_lib, shape, algo):
         assert relerr(pair_value(ps, pblk, n_aug, HC), dP[:, :n_aug]) < 1e-6
         assert xs[0].abs().max() < 32800 and xs[0].abs().max() >= 16384       # largest magnitude sits in [2^14, 2^15]
         P2, dW2, dX2 = torch.zeros_like(P), torch.empty_like(dW), torch.empty_like(dX)
-        check(cuda_lib.spotv2_proj_fwd(C.byref(d), ptr(xg), ptr(xs[0]), ptr(xs[1]), ptr(xblk), ptr(Wg), ptr(P2), ptr(ws),
+        check(cuda_lib.spotv2_proj_fwd(C.byref(d), ptr(xg), ptr(xs[0]), ptr(xs[1]), ptr(xblk), ptr(Wg), ptr(P2), None, ptr(ws),
                                        ws.numel(), st()), "proj_fwd")
         check(cuda_lib.spotv2_proj_bwd_weight(C.byref(d), ptr(xg), ptr(xs[0]), ptr(xs[1]), ptr(xblk), None, ptr(ps[0]),
                                               ptr(ps[1]), ptr(pblk), ptr(dW2), ptr(ws), ws.numel(), st()), "bwd_w")
@@ -300,13 +302,13 @@ def test_attention_stages_against_dense_oracle(cuda_lib, geom, bwd_algo):
         dP = torch.zeros(B * N, ldp, device=DEV)
         dv, dbias = torch.empty(H, Fe, device=DEV), torch.empty(ldo, device=DEV)
         dout_g = dout.to(DEV)
-        check(cuda_lib.spotv2_gat_attn_bwd(C.byref(d), ptr(P_aug), ptr(ea), ptr(topo.table), ptr(v), ptr(dout_g),
+        check(cuda_lib.spotv2_gat_attn_bwd(C.byref(d), ptr(P_aug), None, ptr(ea), ptr(topo.table), ptr(v), ptr(dout_g),
                                            ptr(dP), None, None, None, ptr(dv), ptr(dbias), ptr(ws), ws.numel(), st()), "attn_bwd")
         # the tensor-core operand form: the fp16 pair reproduces the fp32 gradient to ~2^-22 of each group's scale
         n_aug = H * C_ + 2 * H
         dP16 = torch.zeros(2, B * N, cuda_lib.spotv2_gat_ld16(n_aug), device=DEV, dtype=torch.float16)
         pblk = torch.zeros(8, device=DEV)
-        check(cuda_lib.spotv2_gat_attn_bwd(C.byref(d), ptr(P_aug), ptr(ea), ptr(topo.table), ptr(v), ptr(dout_g),
+        check(cuda_lib.spotv2_gat_attn_bwd(C.byref(d), ptr(P_aug), None, ptr(ea), ptr(topo.table), ptr(v), ptr(dout_g),
                                            None, ptr(dP16[0]), ptr(dP16[1]), ptr(pblk), ptr(dv), ptr(dbias), ptr(ws),
                                            ws.numel(), st()), "attn_bwd")
         got = pair_value(dP16, pblk, n_aug, H * C_)
