@@ -183,9 +183,9 @@ class HotPath:
         sizes = [HC * Fin, HC, HC, HC * Fe, HC, Cc]
         self.arena = torch.empty(sum(sizes), **f32)
         self.g_W, self.g_as, self.g_ad, self.g_We, self.g_ae, self.g_b = torch.split(self.arena, sizes)
-        # fold 2; x amax+split 2; W amax+split 2; GEMM fwd 1; attn fwd 1; dout amax 1; attn bwd 1 + 2 partial reduces;
-        # ds|dd amax+split 2; GEMM bwd 1 + split-K reduce 1; unfold 2 (memsets / 4-byte copies not counted)
-        self.kernels_per_step = 19 if self.tc else 10
+        # counted from the ncu launch list (profiles/r1m_launch_list_summary.txt): fold 1; amax x5 (x, W_aug x2, dout, ds|dd);
+        # split x3 (x, W_aug, ds|dd); GEMM fwd; attn fwd; attn bwd + 2 partial reduces; GEMM bwd + split-K reduce; unfold
+        self.kernels_per_step = 17 if self.tc else 10
         self.ev = {}
 
     def step(self, timed_events=None, allreduce=None):
@@ -299,8 +299,13 @@ def run_ours(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "attn_traffic.json")))
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "gat_attn_fwd_kernel + gat_attn_bwd_kernel", "achieved": attn_gbs,
+    traffic_detail = traffic
+    if isinstance(traffic, dict):
+        traffic = traffic.get("sum")
+    roofline = {"bound": "hbm", "kernel": "gat_attn_fwd_kernel + gat_attn_bwd2_kernel", "achieved": attn_gbs,
                 "peak": hbm_peak, "unit": "GB/s", "frac": attn_gbs / hbm_peak, "traffic": traffic,
+                "traffic_detail": traffic_detail,
+                "algorithmic_bytes_per_launch_pair": (ATTN_BYTES_FWD + ATTN_BYTES_BWD) * B,
                 "peak_source": peak_src, "frac_of_8TBs": attn_gbs / 8000.0,
                 "fwd": {"ms": phase_ms["attn_fwd"], "GBs": ATTN_BYTES_FWD * B / phase_ms["attn_fwd"] / 1e6},
                 "bwd": {"ms": phase_ms["attn_bwd"], "GBs": ATTN_BYTES_BWD * B / phase_ms["attn_bwd"] / 1e6}}
