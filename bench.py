@@ -319,12 +319,19 @@ def run_ours(args):
                            "algorithmic fp32 flops, the 3-product fp16-pair scheme issues 3x that ('issued_TFLOPs')",
             "fwd_ms": phase_ms["proj_fwd"], "bwd_ms": phase_ms["proj_bwd_weight"]}
 
-    e2e = None
+    # `e2e` is the strict reading: the host tensors the reference's `data.to(device)` moves (x, edge_index,
+    # edge_attr, y_x) cross PCIe every step.  `e2e_windows` is this library's own input path (the [T,N,N] stacks
+    # cross instead, 83x fewer bytes, and the batch is collated on the device); reported beside it, never as `e2e`.
+    e2e = e2e_win = None
     if not args.no_e2e:
         try:
             e2e = run_e2e(args, hp, dev, world, rank, barrier)
         except Exception as ex:           # the device-timed line must still print
             e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:300]}
+        try:
+            e2e_win = run_e2e_windows(args, hp, dev, world, rank, barrier)
+        except Exception as ex:
+            e2e_win = {"value": None, "unit": UNIT, "error": repr(ex)[:300]}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -348,11 +355,56 @@ def run_ours(args):
                        "l2": "inputs (x 619 MB, edge_attr 1.8 GB, P 1.5 GB per step) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"dp{world}"},
             "phase_ms": phase_ms, "roofline": roofline, "roofline_projection": proj, "cpu_baseline": cpu_baseline,
-            "e2e": e2e, "gpu_launches": hp.kernels_per_step * args.steps, "clocks": clocks,
+            "e2e": e2e, "e2e_windows": e2e_win, "gpu_launches": hp.kernels_per_step * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_e2e_windows(args, hp, dev, world, rank, barrier):
+    """The metric end to end through the repo's public API with HOST inputs: the standardized matrix stacks the
+    reference reads from its two H5 files (config/GNN_param.yaml:2-3) sit in pinned host memory; every step
+    copies the [T, N, N] stacks its windows need to the device (WindowDataset.vol / .volvol), collates the batch
+    on the device (`WindowDataset.collate`, the drop-in for CovarianceLaggedDataset + DataLoader,
+    5_train_SpotV2Net.py:90,142-143), runs GATConv forward + backward through autograd and reads the loss back.
+    This is the input path a user of this library's WindowDataset takes (reported as `e2e_windows`); the headline
+    `e2e` leg (`run_e2e`) ships the already-expanded PyG tensors (x, edge_index, edge_attr: 83x the bytes) the
+    way the reference's `data.to(device)` does."""
+    ds, layer, dout = hp.ds, hp.layer, hp.dout
+    vol_h, vv_h = ds.vol.cpu().pin_memory(), ds.volvol.cpu().pin_memory()
+    idx = torch.arange(hp.B)
+    h2d = (vol_h.numel() + vv_h.numel()) * 4 + hp.B * 4        # both stacks + the window starts
+    steps = max(2, min(args.steps, args.e2e_steps))
+
+    def step():
+        ds.vol.copy_(vol_h, non_blocking=True)
+        ds.volvol.copy_(vv_h, non_blocking=True)
+        bt = ds.collate(idx)                                # window starts H2D + device-side gather
+        layer.zero_grad(set_to_none=True)
+        out = layer(bt.x, bt.edge_index, bt.edge_attr, topology=bt.spot_topology)
+        loss = (out * dout).sum()
+        loss.backward()
+        return loss.item()                                  # D2H read of the step's result
+
+    step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    return {"value": world * hp.B / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+            "ms_per_step": ms, "steps": steps,
+            "api": "pinned host [T,N,N] vol / vol-of-vol stacks -> H2D -> spotv2net_b200.WindowDataset.collate (device) -> "
+                   "GATConv forward + autograd backward -> loss.item(); no overlap between steps"}
 
 
 def run_e2e(args, hp, dev, world, rank, barrier):
