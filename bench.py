@@ -211,7 +211,7 @@ class HotPath:
                                 p(self.ws), self.ws.numel(), st), "proj_fwd")
         mark("proj_fwd")
         chk(lib.spotv2_gat_attn_fwd(d, p(self.P_aug), p(self.batch.edge_attr), p(self.batch.spot_topology.table),
-                                    p(self.v), p(L.bias), p(self.out), None, st), "attn_fwd")
+                                    p(self.v), p(L.bias), p(self.out), None, None, 0, st), "attn_fwd")
         mark("attn_fwd")
         chk(lib.spotv2_gat_attn_bwd(d, p(self.P_aug), p(self.p_amax), p(self.batch.edge_attr), p(self.batch.spot_topology.table),
                                     p(self.v), p(self.dout), p(self.dP_aug), p(ph), p(pl), p(self.dp_blk), p(self.dv),

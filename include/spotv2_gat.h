@@ -40,12 +40,12 @@
 extern "C" {
 #endif
 
-#define SPOTV2_ABI_VERSION 2
+#define SPOTV2_ABI_VERSION 3
 
 typedef enum spotv2_status {
   SPOTV2_OK = 0,
   SPOTV2_ERR_INVALID_ARG = 1,   /* null pointer, non-positive size, bad stride/alignment */
-  SPOTV2_ERR_UNSUPPORTED = 2,   /* shape outside what the kernels cover (e.g. N > 32) */
+  SPOTV2_ERR_UNSUPPORTED = 2,   /* shape outside what the kernels cover (e.g. H > 8, Fe > 512) */
   SPOTV2_ERR_WORKSPACE = 3,     /* workspace too small */
   SPOTV2_ERR_CUDA = 4,          /* a CUDA runtime call failed */
   SPOTV2_ERR_NO_DEVICE = 5      /* no sm_100 device / driver */
@@ -56,7 +56,10 @@ typedef enum spotv2_status {
  *   in_channels=F, out_channels=C, heads=H, concat, edge_dim=Fe, negative_slope. */
 typedef struct spotv2_gat_desc {
   int32_t B;              /* graphs in the batch                                   */
-  int32_t N;              /* nodes per graph (30 by default)                       */
+  int32_t N;              /* nodes per graph (30 by default).  N <= 32: one CTA per
+                             graph, everything fused in shared memory; N > 32 (the
+                             500-node universe): several CTAs per graph, attention
+                             tile [B,H,N,N] in the workspace                       */
   int32_t F;              /* in_channels                                           */
   int32_t Fe;             /* edge_dim; 0 = layer called with edge_attr=None        */
   int32_t H;              /* heads                                                 */
@@ -85,6 +88,9 @@ int32_t spotv2_gat_ldp(int32_t H, int32_t C);
 /* Bytes of scratch each phase wants (device memory, 256-byte aligned). */
 int spotv2_gat_workspace_bytes(const spotv2_gat_desc* d, size_t* proj_fwd, size_t* attn_bwd,
                                size_t* proj_bwd);
+/* Scratch of spotv2_gat_attn_fwd: 0 for N <= 32; the [B, H, N, N] fp32 attention tile for larger graphs
+ * (not needed when the caller passes alpha_or_null, which then doubles as the tile). */
+int spotv2_gat_attn_fwd_workspace_bytes(const spotv2_gat_desc* d, size_t* attn_fwd);
 
 /* Replaces the per-call topology work PyG does on edge_index
  * (remove_self_loops / add_self_loops / index_select by edge_index[0|1];
@@ -138,7 +144,7 @@ int spotv2_proj_fwd(const spotv2_gat_desc* d, const float* x, const void* x_hi, 
  * tile [B, H, N(source j), N(target i)] (for return_attention_weights). */
 int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug, const float* edge_rows,
                         const int32_t* table, const float* v, const float* bias_or_null,
-                        float* out, float* alpha_or_null, void* stream);
+                        float* out, float* alpha_or_null, void* ws, size_t ws_bytes, void* stream);
 
 /* autograd of the above with the attention coefficients recomputed, not stored.
  * dout [B*N, C or HC] -> dP_aug (dP | ds | dd), dv [H, Fe], dbias.  The gradient is emitted either as

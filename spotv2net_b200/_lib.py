@@ -41,7 +41,8 @@ SIGNATURES = {
     "spotv2_gat_ld16": (_i32, [_i32]),
     "spotv2_split_f16": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "spotv2_proj_fwd": (C.c_int, [_DP] + [_vp] * 8 + [_sz, _vp]),
-    "spotv2_gat_attn_fwd": (C.c_int, [_DP] + [_vp] * 8),
+    "spotv2_gat_attn_fwd_workspace_bytes": (C.c_int, [_DP, C.POINTER(_sz)]),
+    "spotv2_gat_attn_fwd": (C.c_int, [_DP] + [_vp] * 8 + [_sz, _vp]),
     "spotv2_gat_attn_bwd": (C.c_int, [_DP] + [_vp] * 13 + [_sz, _vp]),
     "spotv2_proj_bwd_weight": (C.c_int, [_DP] + [_vp] * 10 + [_sz, _vp]),
     "spotv2_proj_bwd_input": (C.c_int, [_DP] + [_vp] * 7 + [_sz, _vp]),
@@ -70,8 +71,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.spotv2_abi_version() != 2:
-        raise SpotV2Error(f"ABI version mismatch: library reports {lib.spotv2_abi_version()}, binding expects 2")
+    if lib.spotv2_abi_version() != 3:
+        raise SpotV2Error(f"ABI version mismatch: library reports {lib.spotv2_abi_version()}, binding expects 3")
     _lib = lib
     return lib
 

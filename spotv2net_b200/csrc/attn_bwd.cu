@@ -557,6 +557,7 @@ size_t attn_bwd_partials_bytes(const spotv2_gat_desc* d) {
   return legacy > piped ? legacy : piped;
 }
 size_t attn_bwd_ws_bytes(const spotv2_gat_desc* d) {
+  if (attn_large_applies(d)) return attn_large_bwd_ws_bytes(d);
   // partials | ds,dd in fp32 [B*N, 2H] | two scale blocks
   return attn_bwd_partials_bytes(d) + round_up((size_t)d->B * d->N * 2 * d->H * sizeof(float), 256) + 256;
 }
@@ -636,6 +637,8 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
   a.ldp16 = ld16_of(HC + 2 * d->H);
   a.dout_blk = nullptr; a.p_amax = nullptr; a.bound = 1.f; a.dsd = nullptr; a.dp_blk = dp_scale_or_null;
   cudaStream_t st = as_stream(stream);
+  if (attn_large_applies(d))       // N > 32: several CTAs per graph (attn_large.cu); emits the pair through a split pass
+    return attn_large_bwd(d, a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
   const size_t rows = (size_t)d->B * d->N;
   if (!ws || ws_bytes < attn_bwd_ws_bytes(d))
     return fail(SPOTV2_ERR_WORKSPACE, "attn_bwd needs %zu B of workspace, got %zu", attn_bwd_ws_bytes(d), ws_bytes);

@@ -44,4 +44,13 @@ int launch_attn_bwd2(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t w
 size_t attn_bwd2_partials_bytes(const spotv2_gat_desc* d);
 int bwd2_diag_add(unsigned long long* host_out, int reset);      // adds its phase counters into host_out[0..5]
 
+// Large-universe path (attn_large.cu): N > 32, several CTAs per graph, attention tile in HBM.
+bool attn_large_applies(const spotv2_gat_desc* d);
+size_t attn_large_fwd_ws_bytes(const spotv2_gat_desc* d);
+size_t attn_large_bwd_ws_bytes(const spotv2_gat_desc* d);
+int attn_large_fwd(const AttnParams& p, const float* bias, float* out, float* alpha_out, void* ws, size_t ws_bytes,
+                   cudaStream_t st);
+int attn_large_bwd(const spotv2_gat_desc* d, AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t ws_bytes,
+                   cudaStream_t st);
+
 }  // namespace spotv2

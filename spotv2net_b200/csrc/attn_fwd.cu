@@ -21,7 +21,7 @@
 // Why tensor cores here: with CUDA-core FFMA2 every lane needs the whole alpha row in registers, and the
 // shared-memory return path (512 B per LDS.128 per warp) bounded that version at 38 % of HBM peak
 // (profiles/).  MMA fragments spread alpha and P across the lanes, cutting shared-memory traffic ~8x.
-#include "attn_common.cuh"
+#include "attn_bwd.cuh"
 #include "tma.cuh"
 
 namespace spotv2 {
@@ -493,7 +493,7 @@ extern "C" int spotv2_diag_counters(unsigned long long* host_out, int reset) {
 extern "C" int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug,
                                    const float* edge_rows, const int32_t* table, const float* v,
                                    const float* bias_or_null, float* out, float* alpha_or_null,
-                                   void* stream) {
+                                   void* ws, size_t ws_bytes, void* stream) {
   if (int rc = check_desc(d)) return rc;
   SPOTV2_REQUIRE(P_aug && out, "attn_fwd: P_aug and out must be non-null");
   SPOTV2_REQUIRE(d->Fe == 0 || (edge_rows && table && v),
@@ -510,5 +510,7 @@ extern "C" int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug,
   a.p.bulk_ok = d->Fe > 0 && aligned16(edge_rows) && ((size_t)d->R * d->Fe) % 4 == 0;
   a.p.vec2_ok = (d->C % 2 == 0);
   a.bias = bias_or_null; a.out = out; a.alpha_out = alpha_or_null;
+  if (attn_large_applies(d))       // several CTAs per graph, attention tile in the workspace (or alpha_or_null)
+    return attn_large_fwd(a.p, bias_or_null, out, alpha_or_null, ws, ws_bytes, as_stream(stream));
   return attn_fwd_dispatch(a, as_stream(stream));
 }

@@ -1,0 +1,550 @@
+// Large-universe attention (N > 32 nodes per graph, BASELINE config D: the 500-node S&P-style complete
+// graph): the multi-CTA-per-graph form of edge_update + softmax + propagate ([PyG] gat_conv.py
+// edge_update/message, utils/softmax.py, aggr='add'; reached from /root/reference/utils/models.py:146)
+// and of its autograd.
+//
+// One graph no longer fits a CTA (the attention tile alone is H*N*N*4 = 6 MB at N = 500), so the work of a
+// graph is spread over many CTAs and the attention tile lives in HBM/L2 as Z[b][h][j (source)][i (target)]
+// — 5 % of the edge rows' bytes, the same layout spotv2_gat_attn_fwd hands out for return_attention_weights.
+//   L  edge logits   g_ij,h = <e_ij, v_h>: the edge rows stream once through a 2-stage shared-memory ring
+//                    (1-D bulk async copies), 3xTF32 mma.sync per 16-row tile, scattered by the row table;
+//   S  softmax       one thread per (graph, head, target) column: mean fill of the self loop, LeakyReLU,
+//                    max-subtracted softmax over the N sources (online max/sum, 3 passes over the column);
+//   G  aggregation   out_i = mean_h | concat_h  sum_j alpha_h[j][i] P[j,h,:]  as a batched exact-fp32 GEMM
+//                    (128x128 tiles: ceil(N/128)^2 CTAs per (graph, head)).
+// Backward (attention coefficients recomputed from the edge rows, nothing kept from the forward but P_aug):
+//   L, S again;  dalpha_h = g dO_h P_h^T (batched GEMM);  softmax + LeakyReLU backward per column (writes dz in
+//   place, dd, and the share of the self-loop gradient that the mean fill hands back to every incoming edge);
+//   ds = row sums;  dv = sum_r (dz + fill)_r e_r over a second pass of the edge rows;  dP_h = g alpha_h dO_h
+//   (batched GEMM);  dbias = column sums of dout.
+// Every reduction has a fixed order (per-CTA partials summed by index), so results are reproducible.
+#include "attn_bwd.cuh"
+
+namespace spotv2 {
+
+namespace {
+
+constexpr int kLgThreads = 128;
+
+struct LgRing {               // work item q = graph * chunks_per_graph + chunk; a CTA walks q = cta, cta + grid, ...
+  const float* edge_rows;
+  int R, Fe, CR, cpg;         // rows per graph, features, rows per chunk, chunks per graph
+  long long items;
+  int bulk_ok;
+  __device__ __forceinline__ int rows_of(long long q) const {
+    const int c = (int)(q % cpg);
+    const int r = R - c * CR;
+    return r < CR ? r : CR;
+  }
+  __device__ __forceinline__ const float* src_of(long long q) const {
+    const long long b = q / cpg, c = q - b * cpg;
+    return edge_rows + ((size_t)b * R + (size_t)c * CR) * Fe;
+  }
+};
+
+// Brings item q into `stage`: thread 0 issues a bulk copy (completion on `bar`) or, for unaligned edge
+// blocks, the whole CTA copies cooperatively (caller syncs).
+__device__ __forceinline__ void lg_issue(const LgRing& rg, long long q, float* stage, uint64_t* bar) {
+  const uint32_t bytes = (uint32_t)rg.rows_of(q) * rg.Fe * 4u;
+  mbar_expect_tx(bar, bytes);
+  bulk_g2s(stage, rg.src_of(q), bytes, bar);
+}
+__device__ __forceinline__ void lg_copy(const LgRing& rg, long long q, float* stage, int tid) {
+  const float* src = rg.src_of(q);
+  const int n = rg.rows_of(q) * rg.Fe;
+  for (int idx = tid; idx < n; idx += kLgThreads) stage[idx] = src[idx];
+}
+
+struct LgLogitArgs {
+  LgRing rg;
+  const int32_t* table;
+  const float* v;
+  float* Z;                   // [B][H][N][N]
+  int N, H, KS, NT;
+  uint32_t off_vfrag, off_stage, stage_bytes;
+};
+
+// L: Z[b][h][j][i] = <edge row (j -> i), v_h>.  4 warps, one 16-row MMA tile each per 64-row chunk.
+__global__ void __launch_bounds__(kLgThreads) lg_edge_logit_kernel(const LgLogitArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  float4* vfrag = reinterpret_cast<float4*>(smem + a.off_vfrag);
+  float* stage[2] = {reinterpret_cast<float*>(smem + a.off_stage),
+                     reinterpret_cast<float*>(smem + a.off_stage + a.stage_bytes)};
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const LgRing& rg = a.rg;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
+  build_vfrag(vfrag, a.v, a.H, rg.Fe, a.KS, a.NT, tid, kLgThreads);
+  __syncthreads();
+  const long long q0 = blockIdx.x, step = gridDim.x;
+  if (rg.bulk_ok && tid == 0) {
+    if (q0 < rg.items) lg_issue(rg, q0, stage[0], &full[0]);
+    if (q0 + step < rg.items) lg_issue(rg, q0 + step, stage[1], &full[1]);
+  }
+  uint32_t it = 0;
+  for (long long q = q0; q < rg.items; q += step, ++it) {
+    const int s = it & 1;
+    const int rows = rg.rows_of(q);
+    if (rg.bulk_ok) {
+      mbar_wait(&full[s], (it >> 1) & 1);
+    } else {
+      lg_copy(rg, q, stage[s], tid);
+      __syncthreads();
+    }
+    if (warp * 16 < rows) {
+      const long long b = q / rg.cpg;
+      const int row_base = (int)(q - b * rg.cpg) * rg.CR;
+      float* Zb = a.Z + (size_t)b * a.H * a.N * a.N;
+      const int N = a.N, H = a.H;
+      const int32_t* table = a.table;
+      warp_edge_logits<1, 4>(stage[s], vfrag, rg.Fe, a.KS, a.NT, warp * 16, lane, [&](int r, int h, float val) {
+        if (r < rows && h < H) {
+          const int code = __ldg(table + row_base + r);
+          if (code >= 0) Zb[((size_t)h * N + (code & 0xffff)) * N + (code >> 16)] = val;
+        }
+      });
+    }
+    __syncthreads();
+    if (rg.bulk_ok && tid == 0 && q + 2 * step < rg.items) lg_issue(rg, q + 2 * step, stage[s], &full[s]);
+  }
+}
+
+// S: one thread per (b, h, target i) column of Z.  Zraw may be null (layer called without edge_attr: all edge
+// terms 0) and may alias A.  gii_out (optional) receives the self-loop fill for the backward.
+__global__ void __launch_bounds__(128)
+lg_softmax_kernel(const float* __restrict__ P_aug, const float* Zraw, float* A, float* __restrict__ gii_out,
+                  int N, int H, int HC, int ldp, float slope) {
+  extern __shared__ float s_src[];             // s_j of this (b, h)
+  const int b = blockIdx.z, h = blockIdx.y;
+  const float* Pb = P_aug + (size_t)b * N * ldp;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) s_src[j] = Pb[(size_t)j * ldp + HC + h];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const size_t base = ((size_t)b * H + h) * N * N + i;
+  const float* zc = Zraw ? Zraw + base : nullptr;
+  float* ac = A + base;
+  const float di = Pb[(size_t)i * ldp + HC + H + h];
+  float gsum = 0.f;
+  if (zc) {
+#pragma unroll 8
+    for (int j = 0; j < N; ++j) gsum += (j != i) ? zc[(size_t)j * N] : 0.f;
+  }
+  const float gii = gsum / (float)(N > 1 ? N - 1 : 1);
+  if (gii_out) gii_out[((size_t)b * H + h) * N + i] = gii;
+  float mx = -INFINITY, sum = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < N; ++j) {
+    const float g = (j == i) ? gii : (zc ? zc[(size_t)j * N] : 0.f);
+    const float z = g + s_src[j] + di;
+    const float l = z > 0.f ? z : z * slope;
+    if (l > mx) {
+      sum *= expf(mx - l);
+      mx = l;
+    }
+    sum += expf(l - mx);
+  }
+  const float inv = 1.f / (sum + 1e-16f);
+#pragma unroll 4
+  for (int j = 0; j < N; ++j) {
+    const float g = (j == i) ? gii : (zc ? zc[(size_t)j * N] : 0.f);
+    const float z = g + s_src[j] + di;
+    const float l = z > 0.f ? z : z * slope;
+    ac[(size_t)j * N] = expf(l - mx) * inv;
+  }
+}
+
+// Softmax + LeakyReLU backward per column.  dA holds dalpha on entry and dz on exit (diagonal included: it is
+// the self loop's dz); fill[b,h,i] = dz_ii / (N - 1), the gradient every incoming edge term of i receives
+// through the mean fill; dd_i goes to column HC + H + h of dP_aug.
+__global__ void __launch_bounds__(128)
+lg_softmax_bwd_kernel(const float* __restrict__ P_aug, const float* __restrict__ Zraw, const float* __restrict__ A,
+                      float* dA, const float* __restrict__ gii, float* __restrict__ fill, float* dP_aug, int N,
+                      int H, int HC, int ldp, float slope) {
+  extern __shared__ float s_src[];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const float* Pb = P_aug + (size_t)b * N * ldp;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) s_src[j] = Pb[(size_t)j * ldp + HC + h];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const size_t base = ((size_t)b * H + h) * N * N + i;
+  const float* zc = Zraw ? Zraw + base : nullptr;
+  const float* ac = A + base;
+  float* dc = dA + base;
+  const float di = Pb[(size_t)i * ldp + HC + H + h];
+  const float g_ii = gii[((size_t)b * H + h) * N + i];
+  float dot = 0.f;
+#pragma unroll 8
+  for (int j = 0; j < N; ++j) dot = fmaf(ac[(size_t)j * N], dc[(size_t)j * N], dot);
+  float dd = 0.f, dz_ii = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < N; ++j) {
+    const float g = (j == i) ? g_ii : (zc ? zc[(size_t)j * N] : 0.f);
+    const float z = g + s_src[j] + di;
+    const float dl = ac[(size_t)j * N] * (dc[(size_t)j * N] - dot);
+    const float dz = z > 0.f ? dl : dl * slope;
+    dd += dz;
+    if (j == i) dz_ii = dz;
+    dc[(size_t)j * N] = dz;
+  }
+  fill[((size_t)b * H + h) * N + i] = dz_ii / (float)(N > 1 ? N - 1 : 1);
+  dP_aug[((size_t)b * N + i) * ldp + HC + H + h] = dd;
+}
+
+// ds_j = sum_i dz[j][i] -> column HC + h of dP_aug.  One warp per (b, h, j) row, fixed lane-strided order.
+__global__ void __launch_bounds__(256)
+lg_rowsum_kernel(const float* __restrict__ dZ, float* dP_aug, int B, int N, int H, int HC, int ldp) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (long long)B * H * N) return;
+  const int j = (int)(w % N);
+  const long long bh = w / N;
+  const int h = (int)(bh % H);
+  const long long b = bh / H;
+  const float* row = dZ + (size_t)w * N;
+  float s = 0.f;
+  for (int i = lane; i < N; i += 32) s += row[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) dP_aug[((size_t)b * N + j) * ldp + HC + h] = s;
+}
+
+struct LgDvArgs {
+  LgRing rg;
+  const int32_t* table;
+  const float* dZ;            // [B][H][N][N] dz
+  const float* fill;          // [B][H][N]
+  double* part;               // [grid][H*Fe]
+  int N, H;
+  uint32_t off_w, off_stage, stage_bytes;
+};
+
+// dv[h][k] = sum over edge rows r = (j -> i) of (dz[h][j][i] + fill[h][i]) * e_r[k].  Thread = feature k
+// (and k + 128, ...), all heads; per-chunk sums in fp32, the CTA's running total in fp64.
+template <int KPT>
+__global__ void __launch_bounds__(kLgThreads) lg_dv_kernel(const LgDvArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  float* wrow = reinterpret_cast<float*>(smem + a.off_w);       // [CR][8]
+  float* stage[2] = {reinterpret_cast<float*>(smem + a.off_stage),
+                     reinterpret_cast<float*>(smem + a.off_stage + a.stage_bytes)};
+  const int tid = threadIdx.x;
+  const LgRing& rg = a.rg;
+  const int Fe = rg.Fe, N = a.N, H = a.H;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const long long q0 = blockIdx.x, step = gridDim.x;
+  if (rg.bulk_ok && tid == 0) {
+    if (q0 < rg.items) lg_issue(rg, q0, stage[0], &full[0]);
+    if (q0 + step < rg.items) lg_issue(rg, q0 + step, stage[1], &full[1]);
+  }
+  double tot[KPT][8];
+#pragma unroll
+  for (int kk = 0; kk < KPT; ++kk)
+#pragma unroll
+    for (int h = 0; h < 8; ++h) tot[kk][h] = 0.0;
+  uint32_t it = 0;
+  for (long long q = q0; q < rg.items; q += step, ++it) {
+    const int s = it & 1;
+    const int rows = rg.rows_of(q);
+    const long long b = q / rg.cpg;
+    const int row_base = (int)(q - b * rg.cpg) * rg.CR;
+    // weights of this chunk's rows (gathered from the dz tile while the copy is in flight)
+    for (int r = tid; r < rows; r += kLgThreads) {
+      const int code = __ldg(a.table + row_base + r);
+      float w[8];
+#pragma unroll
+      for (int h = 0; h < 8; ++h) w[h] = 0.f;
+      if (code >= 0) {
+        const int i = code >> 16, j = code & 0xffff;
+        const float* dzb = a.dZ + (size_t)b * H * N * N + (size_t)j * N + i;
+        const float* fb = a.fill + (size_t)b * H * N + i;
+#pragma unroll
+        for (int h = 0; h < 8; ++h)
+          if (h < H) w[h] = dzb[(size_t)h * N * N] + fb[(size_t)h * N];
+      }
+      *reinterpret_cast<float4*>(wrow + r * 8) = make_float4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<float4*>(wrow + r * 8 + 4) = make_float4(w[4], w[5], w[6], w[7]);
+    }
+    if (rg.bulk_ok) {
+      mbar_wait(&full[s], (it >> 1) & 1);
+    } else {
+      lg_copy(rg, q, stage[s], tid);
+    }
+    __syncthreads();
+    float2 acc[KPT][4];
+#pragma unroll
+    for (int kk = 0; kk < KPT; ++kk)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) acc[kk][p] = make_float2(0.f, 0.f);
+    const float* T = stage[s];
+    for (int r = 0; r < rows; ++r) {
+      const float4 w0 = *reinterpret_cast<const float4*>(wrow + r * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(wrow + r * 8 + 4);
+      const float2 wp[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y),
+                            make_float2(w1.z, w1.w)};
+#pragma unroll
+      for (int kk = 0; kk < KPT; ++kk) {
+        const int k = tid + kk * kLgThreads;
+        const float e = k < Fe ? T[r * Fe + k] : 0.f;
+        const float2 ed = make_float2(e, e);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[kk][p] = ffma2(ed, wp[p], acc[kk][p]);
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < KPT; ++kk)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        tot[kk][2 * p] += (double)acc[kk][p].x;
+        tot[kk][2 * p + 1] += (double)acc[kk][p].y;
+      }
+    __syncthreads();
+    if (rg.bulk_ok && tid == 0 && q + 2 * step < rg.items) lg_issue(rg, q + 2 * step, stage[s], &full[s]);
+  }
+  double* out = a.part + (size_t)blockIdx.x * H * Fe;
+#pragma unroll
+  for (int kk = 0; kk < KPT; ++kk) {
+    const int k = tid + kk * kLgThreads;
+    if (k < Fe)
+#pragma unroll
+      for (int h = 0; h < 8; ++h)
+        if (h < H) out[(size_t)h * Fe + k] = tot[kk][h];
+  }
+}
+
+__global__ void lg_reduce_f64_kernel(const double* __restrict__ part, int nparts, int len, float* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= len) return;
+  double s = 0.0;
+  for (int c = 0; c < nparts; ++c) s += part[(size_t)c * len + k];
+  out[k] = (float)s;
+}
+
+// dbias partials: part[chunk][c] = sum of dout[r][c] over the chunk's rows.
+__global__ void __launch_bounds__(128)
+lg_colsum_kernel(const float* __restrict__ src, long long rows, int cols, int rows_per_chunk, float* __restrict__ part) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) s += src[(size_t)r * cols + c];
+  part[(size_t)blockIdx.y * cols + c] = s;
+}
+
+struct LgPlan {
+  int CR, cpg, KS, NT, grid;
+  uint32_t off_vfrag, off_w, off_stage, stage_bytes;
+  size_t smem_logit, smem_dv;
+};
+
+LgPlan lg_plan(const AttnParams& p) {
+  LgPlan pl{};
+  if (p.Fe <= 0) return pl;
+  pl.KS = ((p.Fe + 7) / 8 + 7) / 8 * 8;
+  pl.NT = (p.H + 7) / 8;
+  const size_t vfrag = (size_t)pl.NT * pl.KS * 32 * 16;
+  pl.off_vfrag = 128;
+  pl.off_stage = (uint32_t)round_up(128 + vfrag, 128);       // the dv kernel keeps its row weights where vfrag sits
+  pl.off_w = 128;
+  pl.CR = 64;
+  while (pl.CR > 16 && pl.off_stage + 2 * round_up((size_t)pl.CR * p.Fe * 4, 128) > 110 * 1024) pl.CR -= 16;
+  pl.stage_bytes = (uint32_t)round_up((size_t)pl.CR * p.Fe * 4, 128);
+  pl.smem_logit = pl.smem_dv = (size_t)pl.off_stage + 2 * (size_t)pl.stage_bytes;
+  pl.cpg = (p.R + pl.CR - 1) / pl.CR;
+  const long long items = (long long)p.B * pl.cpg;
+  const int per_sm = (int)(220 * 1024 / (pl.smem_logit + 1024));
+  long long grid = (long long)sm_count() * (per_sm < 1 ? 1 : per_sm > 4 ? 4 : per_sm);
+  pl.grid = (int)(grid < items ? grid : items);
+  return pl;
+}
+
+LgRing lg_ring(const AttnParams& p, const LgPlan& pl) {
+  LgRing rg;
+  rg.edge_rows = p.edge_rows;
+  rg.R = p.R; rg.Fe = p.Fe; rg.CR = pl.CR; rg.cpg = pl.cpg;
+  rg.items = (long long)p.B * pl.cpg;
+  rg.bulk_ok = p.bulk_ok;
+  return rg;
+}
+
+int lg_logits(const AttnParams& p, const LgPlan& pl, float* Z, cudaStream_t st) {
+  // diagonal entries are never written by L; S ignores them, but keep the tile free of stale NaNs for consumers
+  // that read whole rows
+  LgLogitArgs a;
+  a.rg = lg_ring(p, pl);
+  a.table = p.table; a.v = p.v; a.Z = Z; a.N = p.N; a.H = p.H; a.KS = pl.KS; a.NT = pl.NT;
+  a.off_vfrag = pl.off_vfrag; a.off_stage = pl.off_stage; a.stage_bytes = pl.stage_bytes;
+  SPOTV2_CUDA_OK(cudaFuncSetAttribute(lg_edge_logit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_logit));
+  lg_edge_logit_kernel<<<pl.grid, kLgThreads, pl.smem_logit, st>>>(a);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
+int lg_softmax(const AttnParams& p, const float* Zraw, float* A, float* gii, cudaStream_t st) {
+  dim3 grid((p.N + 127) / 128, p.H, p.B);
+  lg_softmax_kernel<<<grid, 128, (size_t)p.N * sizeof(float), st>>>(p.P_aug, Zraw, A, gii, p.N, p.H, p.H * p.C, p.ldp, p.slope);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
+size_t tile_bytes(const spotv2_gat_desc* d) { return round_up((size_t)d->B * d->H * d->N * d->N * sizeof(float), 256); }
+size_t vec_bytes(const spotv2_gat_desc* d) { return round_up((size_t)d->B * d->H * d->N * sizeof(float), 256); }
+constexpr int kColsumRows = 256;
+
+}  // namespace
+
+bool attn_large_applies(const spotv2_gat_desc* d) { return d->N > 32; }
+
+size_t attn_large_fwd_ws_bytes(const spotv2_gat_desc* d) { return attn_large_applies(d) ? tile_bytes(d) : 0; }
+
+size_t attn_large_bwd_ws_bytes(const spotv2_gat_desc* d) {
+  if (!attn_large_applies(d)) return 0;
+  const size_t rows = (size_t)d->B * d->N;
+  const size_t ldo = d->concat ? (size_t)d->H * d->C : (size_t)d->C;
+  const size_t dv_part = round_up((size_t)4 * sm_count() * d->H * (d->Fe > 0 ? d->Fe : 1) * sizeof(double), 256);
+  const size_t db_part = round_up(((rows + kColsumRows - 1) / kColsumRows) * ldo * sizeof(float), 256);
+  // Zraw | A | dA | gii | fill | dv partials | dbias partials | fp32 dP_aug scratch (fp16-pair output only)
+  return 3 * tile_bytes(d) + 2 * vec_bytes(d) + dv_part + db_part + round_up(rows * d->ldp * sizeof(float), 256) + 256;
+}
+
+int attn_large_fwd(const AttnParams& p, const float* bias, float* out, float* alpha_out, void* ws, size_t ws_bytes,
+                   cudaStream_t st) {
+  const size_t tile = round_up((size_t)p.B * p.H * p.N * p.N * sizeof(float), 256);
+  float* A = alpha_out;
+  if (!A) {
+    if (!ws || ws_bytes < tile)
+      return fail(SPOTV2_ERR_WORKSPACE, "attn_fwd (N=%d > 32) needs %zu B of workspace for the attention tile, got %zu",
+                  p.N, tile, ws_bytes);
+    A = static_cast<float*>(ws);
+  }
+  const LgPlan pl = lg_plan(p);
+  if (p.Fe > 0) {
+    if (pl.smem_logit > 227 * 1024) return fail(SPOTV2_ERR_UNSUPPORTED, "attn_fwd (large N): Fe=%d needs %zu B shared memory", p.Fe, pl.smem_logit);
+    if (int rc = lg_logits(p, pl, A, st)) return rc;
+  }
+  if (int rc = lg_softmax(p, p.Fe > 0 ? A : nullptr, A, nullptr, st)) return rc;
+  const long long NN = (long long)p.N * p.N;
+  BGemm g{};
+  g.M = p.N; g.N = p.C; g.K = p.N;
+  g.A = A; g.lda = p.N;                   // alpha_h stored [j][i]: [K, rows]
+  g.B = p.P_aug; g.ldb = p.ldp;           // P_h stored [j][c]:     [K, rows]
+  g.C = out; g.ldc = p.ldo;
+  g.a_o = (long long)p.H * NN; g.b_o = (long long)p.N * p.ldp; g.c_o = (long long)p.N * p.ldo;
+  g.bias = bias;
+  if (p.concat) {
+    g.inner = p.H; g.a_i = NN; g.b_i = p.C; g.c_i = p.C; g.segs = 1; g.scale = 1.f; g.bias_i = p.C;
+    return bgemm_simt(false, false, g, p.B * p.H, st);
+  }
+  g.inner = 1; g.segs = p.H; g.a_s = NN; g.b_s = p.C; g.scale = 1.f / (float)p.H; g.bias_i = 0;
+  return bgemm_simt(false, false, g, p.B, st);
+}
+
+int attn_large_bwd(const spotv2_gat_desc* d, AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t ws_bytes,
+                   cudaStream_t st) {
+  const AttnParams& p = a.p;
+  if (!ws || ws_bytes < attn_large_bwd_ws_bytes(d))
+    return fail(SPOTV2_ERR_WORKSPACE, "attn_bwd (N=%d > 32) needs %zu B of workspace, got %zu", p.N,
+                attn_large_bwd_ws_bytes(d), ws_bytes);
+  const size_t rows = (size_t)p.B * p.N;
+  const int HC = p.H * p.C;
+  unsigned char* w = static_cast<unsigned char*>(ws);
+  float* Zraw = reinterpret_cast<float*>(w); w += tile_bytes(d);
+  float* A = reinterpret_cast<float*>(w);    w += tile_bytes(d);
+  float* dA = reinterpret_cast<float*>(w);   w += tile_bytes(d);
+  float* gii = reinterpret_cast<float*>(w);  w += vec_bytes(d);
+  float* fill = reinterpret_cast<float*>(w); w += vec_bytes(d);
+  double* dv_part = reinterpret_cast<double*>(w);
+  w += round_up((size_t)4 * sm_count() * p.H * (p.Fe > 0 ? p.Fe : 1) * sizeof(double), 256);
+  float* db_part = reinterpret_cast<float*>(w);
+  const int db_chunks = (int)((rows + kColsumRows - 1) / kColsumRows);
+  w += round_up((size_t)db_chunks * p.ldo * sizeof(float), 256);
+  float* dP = a.dP_aug ? a.dP_aug : reinterpret_cast<float*>(w);
+
+  const LgPlan pl = lg_plan(p);
+  if (p.Fe > 0) {
+    if (pl.smem_logit > 227 * 1024) return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd (large N): Fe=%d needs %zu B shared memory", p.Fe, pl.smem_logit);
+    if (int rc = lg_logits(p, pl, Zraw, st)) return rc;
+  }
+  const float* Zr = p.Fe > 0 ? Zraw : nullptr;
+  if (int rc = lg_softmax(p, Zr, A, gii, st)) return rc;
+
+  const long long NN = (long long)p.N * p.N;
+  const float gsc = p.concat ? 1.f : 1.f / (float)p.H;
+  {   // dalpha_h[j][i] = g sum_c P[j,h,c] dO[i,(h)c]
+    BGemm g{};
+    g.M = p.N; g.N = p.N; g.K = p.C;
+    g.A = p.P_aug; g.lda = p.ldp; g.B = a.dout; g.ldb = p.ldo; g.C = dA; g.ldc = p.N;
+    g.inner = p.H; g.segs = 1; g.scale = gsc;
+    g.a_o = (long long)p.N * p.ldp; g.a_i = p.C;
+    g.b_o = (long long)p.N * p.ldo; g.b_i = p.concat ? p.C : 0;
+    g.c_o = (long long)p.H * NN; g.c_i = NN;
+    if (int rc = bgemm_simt(true, true, g, p.B * p.H, st)) return rc;
+  }
+  {
+    dim3 grid((p.N + 127) / 128, p.H, p.B);
+    lg_softmax_bwd_kernel<<<grid, 128, (size_t)p.N * sizeof(float), st>>>(p.P_aug, Zr, A, dA, gii, fill, dP, p.N, p.H, HC,
+                                                                          p.ldp, p.slope);
+    SPOTV2_CUDA_OK(cudaGetLastError());
+    const long long warps = (long long)p.B * p.H * p.N;
+    lg_rowsum_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(dA, dP, p.B, p.N, p.H, HC, p.ldp);
+    SPOTV2_CUDA_OK(cudaGetLastError());
+  }
+  if (p.Fe > 0 && dv) {
+    LgDvArgs v;
+    v.rg = lg_ring(p, pl);
+    v.table = p.table; v.dZ = dA; v.fill = fill; v.part = dv_part; v.N = p.N; v.H = p.H;
+    v.off_w = pl.off_w; v.off_stage = pl.off_stage; v.stage_bytes = pl.stage_bytes;
+    if ((size_t)pl.CR * 8 * sizeof(float) > pl.off_stage - pl.off_w)
+      return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd (large N): row-weight block does not fit its slot");
+    const int kpt = (p.Fe + kLgThreads - 1) / kLgThreads;
+    auto launch = [&](auto kern) -> int {
+      SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_dv));
+      kern<<<pl.grid, kLgThreads, pl.smem_dv, st>>>(v);
+      SPOTV2_CUDA_OK(cudaGetLastError());
+      return SPOTV2_OK;
+    };
+    int rc;
+    if (kpt <= 1) rc = launch(lg_dv_kernel<1>);
+    else if (kpt <= 2) rc = launch(lg_dv_kernel<2>);
+    else rc = launch(lg_dv_kernel<4>);
+    if (rc) return rc;
+    const int len = p.H * p.Fe;
+    lg_reduce_f64_kernel<<<(len + 127) / 128, 128, 0, st>>>(dv_part, pl.grid, len, dv);
+    SPOTV2_CUDA_OK(cudaGetLastError());
+  }
+  {   // dP_h[j][c] = g sum_i alpha_h[j][i] dO[i,(h)c]
+    BGemm g{};
+    g.M = p.N; g.N = p.C; g.K = p.N;
+    g.A = A; g.lda = p.N; g.B = a.dout; g.ldb = p.ldo; g.C = dP; g.ldc = p.ldp;
+    g.inner = p.H; g.segs = 1; g.scale = gsc;
+    g.a_o = (long long)p.H * NN; g.a_i = NN;
+    g.b_o = (long long)p.N * p.ldo; g.b_i = p.concat ? p.C : 0;
+    g.c_o = (long long)p.N * p.ldp; g.c_i = p.C;
+    if (int rc = bgemm_simt(true, false, g, p.B * p.H, st)) return rc;
+  }
+  if (dbias) {
+    dim3 grid((p.ldo + 127) / 128, db_chunks);
+    lg_colsum_kernel<<<grid, 128, 0, st>>>(a.dout, (long long)rows, p.ldo, kColsumRows, db_part);
+    SPOTV2_CUDA_OK(cudaGetLastError());
+    if (int rc = reduce_partials(db_part, db_chunks, p.ldo, dbias, st)) return rc;
+  }
+  if (a.dP_hi16) {
+    // the tensor-core GEMMs take dP_aug as an fp16 pair with two scale groups (P columns | ds,dd columns)
+    if (int rc = split_f16(dP, (int)rows, HC + 2 * p.H, (size_t)p.ldp, 1, HC, nullptr, 0, a.dP_hi16, a.dP_lo16,
+                           (size_t)a.ldp16, a.dp_blk, st))
+      return rc;
+  }
+  return SPOTV2_OK;
+}
+
+}  // namespace spotv2

@@ -9,6 +9,25 @@ namespace spotv2 {
 int sgemm_simt(bool a_kc, bool b_kc, int M, int N, int K, const float* A, int lda, const float* B,
                int ldb, float* C, int ldc, int splits, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// Batched exact-fp32 GEMM (same tiles as sgemm_simt) used by the large-universe attention path.
+// C_z[M,N] = scale * sum_seg sum_k A_z,seg(m,k) B_z,seg(n,k) + bias; z = zo * inner + zi.
+struct BGemm {
+  int M, N, K;
+  const float* A;
+  const float* B;
+  float* C;
+  int lda, ldb, ldc;
+  int inner;                               // batch index z -> (z / inner, z % inner)
+  long long a_o, a_i, b_o, b_i, c_o, c_i;  // element offsets per outer / inner batch index
+  int segs;                                // contraction segments (heads) summed into one C
+  long long a_s, b_s;                      // element offsets per segment
+  float scale;
+  const float* bias;                       // null or [inner * bias_i + N]
+  long long bias_i;
+  int vecA, vecB;                          // filled by bgemm_simt
+};
+int bgemm_simt(bool a_kc, bool b_kc, BGemm g, int batches, cudaStream_t st);
+
 // Split-K factor used for the weight-gradient GEMM (contraction over all B*N node rows): keeps
 // every fp32 accumulation chain short (<= ~8K terms) and fills the machine.
 inline int weight_grad_splits(int rows) {

@@ -136,6 +136,99 @@ sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const fl
   }
 }
 
+// Batched form for the large-universe attention path (attn_large.cu): blockIdx.z = batch entry
+// z -> (zo, zi) = (z / inner, z % inner); every operand has an element offset per zo and per zi.  The
+// contraction runs over `segs` segments (heads) whose operands sit a_s / b_s elements apart and whose
+// products are summed into one C tile; the epilogue applies C = scale * acc + bias[zi * bias_i + n].
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(256, 2) bgemm_kernel(const BGemm g) {
+  __shared__ __align__(16) float As[2][BK][BM + PADM];
+  __shared__ __align__(16) float Bs[2][BK][BN + PADM];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int zo = blockIdx.z / g.inner, zi = blockIdx.z - zo * g.inner;
+  const float* A0 = g.A + (size_t)zo * g.a_o + (size_t)zi * g.a_i;
+  const float* B0 = g.B + (size_t)zo * g.b_o + (size_t)zi * g.b_i;
+  float* C = g.C + (size_t)zo * g.c_o + (size_t)zi * g.c_i;
+
+  float2 acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+
+  for (int seg = 0; seg < g.segs; ++seg) {
+    const float* A = A0 + (size_t)seg * g.a_s;
+    const float* B = B0 + (size_t)seg * g.b_s;
+    float4 ra[2], rb[2];
+    __syncthreads();                    // the previous segment's last tiles are still being read
+    load_tile<A_KC>(ra, A, g.lda, g.M, m0, 0, g.K, g.vecA, tid);
+    load_tile<B_KC>(rb, B, g.ldb, g.N, n0, 0, g.K, g.vecB, tid);
+    store_tile<A_KC>(As[0], ra, tid);
+    store_tile<B_KC>(Bs[0], rb, tid);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < g.K; k0 += BK) {
+      const bool more = k0 + BK < g.K;
+      if (more) {
+        load_tile<A_KC>(ra, A, g.lda, g.M, m0, k0 + BK, g.K, g.vecA, tid);
+        load_tile<B_KC>(rb, B, g.ldb, g.N, n0, k0 + BK, g.K, g.vecB, tid);
+      }
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float2 bp[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w),
+                              make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 ad = make_float2(a[i], a[i]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = ffma2(ad, bp[j], acc[i][j]);
+        }
+      }
+      if (more) {
+        store_tile<A_KC>(As[buf ^ 1], ra, tid);
+        store_tile<B_KC>(Bs[buf ^ 1], rb, tid);
+        __syncthreads();
+        buf ^= 1;
+      }
+    }
+  }
+
+  const float* bias = g.bias ? g.bias + (size_t)zi * g.bias_i : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + (j < 2 ? tx * 4 + 2 * j : 64 + tx * 4 + 2 * (j - 2));
+      float* dst = C + (size_t)m * g.ldc + n;
+      if (n < g.N) dst[0] = fmaf(acc[i][j].x, g.scale, bias ? bias[n] : 0.f);
+      if (n + 1 < g.N) dst[1] = fmaf(acc[i][j].y, g.scale, bias ? bias[n + 1] : 0.f);
+    }
+  }
+}
+
+int bgemm_simt(bool a_kc, bool b_kc, BGemm g, int batches, cudaStream_t st) {
+  if (g.inner < 1) g.inner = 1;
+  if (g.segs < 1) g.segs = 1;
+  auto mult4 = [](long long x) { return x % 4 == 0; };
+  g.vecA = aligned16(g.A) && g.lda % 4 == 0 && mult4(g.a_o) && mult4(g.a_i) && mult4(g.a_s);
+  g.vecB = aligned16(g.B) && g.ldb % 4 == 0 && mult4(g.b_o) && mult4(g.b_i) && mult4(g.b_s);
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, batches);
+  if (a_kc && b_kc) bgemm_kernel<true, true><<<grid, 256, 0, st>>>(g);
+  else if (a_kc && !b_kc) bgemm_kernel<true, false><<<grid, 256, 0, st>>>(g);
+  else if (!a_kc && b_kc) bgemm_kernel<false, true><<<grid, 256, 0, st>>>(g);
+  else bgemm_kernel<false, false><<<grid, 256, 0, st>>>(g);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, size_t split_stride,
                                      int M, int N, float* __restrict__ C, int ldc) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -6,6 +6,7 @@
 // Operand preparation for the tensor-core path (power-of-two scaled fp16 hi/lo pairs) happens here unless
 // the caller passes pairs it made earlier: x is prepared once per step and feeds both proj_fwd and
 // proj_bwd_weight; the attention backward emits dP_aug directly as pairs.
+#include "attn_bwd.cuh"
 #include "gemm.cuh"
 
 using namespace spotv2;
@@ -57,6 +58,13 @@ extern "C" int spotv2_gat_workspace_bytes(const spotv2_gat_desc* d, size_t* proj
     if (tc) w += pair_bytes(s.rows, s.ldp16) + pair_bytes(s.rows, s.ldf16) + pair_bytes(s.n_aug, s.ldf16);
     *proj_bwd = w;
   }
+  return SPOTV2_OK;
+}
+
+extern "C" int spotv2_gat_attn_fwd_workspace_bytes(const spotv2_gat_desc* d, size_t* attn_fwd) {
+  if (int rc = check_desc(d)) return rc;
+  SPOTV2_REQUIRE(attn_fwd, "attn_fwd_workspace_bytes: null pointer");
+  *attn_fwd = attn_large_fwd_ws_bytes(d);
   return SPOTV2_OK;
 }
 

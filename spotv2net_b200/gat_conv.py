@@ -124,6 +124,12 @@ def _workspace(desc: GatDesc):
     return a.value, b.value, c.value
 
 
+def _attn_fwd_workspace(desc: GatDesc) -> int:
+    a = C.c_size_t()
+    check(_lib.load().spotv2_gat_attn_fwd_workspace_bytes(C.byref(desc), C.byref(a)), "attn_fwd_workspace_bytes")
+    return a.value
+
+
 class _GatLayerFn(torch.autograd.Function):
     """fold -> projection GEMM -> fused attention, and the recompute-based backward."""
 
@@ -163,8 +169,11 @@ class _GatLayerFn(torch.autograd.Function):
                                   ptr(ws), ws_f, st), "spotv2_proj_fwd")
         out = torch.empty(n, HC if concat else Cc, device=dev, dtype=torch.float32)
         alpha = torch.empty(topo.B, H, topo.N, topo.N, device=dev, dtype=torch.float32) if want_alpha else None
+        # N > 32 only: the [B,H,N,N] attention tile lives in a workspace unless the caller asked for alpha itself
+        ws_t = _attn_fwd_workspace(desc) if alpha is None else 0
+        ws_attn = torch.empty(ws_t, device=dev, dtype=torch.uint8) if ws_t else None
         check(lib.spotv2_gat_attn_fwd(C.byref(desc), ptr(P_aug), ptr(ea), ptr(topo.table) if Fe else None, ptr(v),
-                                      ptr(bias_c), ptr(out), ptr(alpha), st), "spotv2_gat_attn_fwd")
+                                      ptr(bias_c), ptr(out), ptr(alpha), ptr(ws_attn), ws_t, st), "spotv2_gat_attn_fwd")
         ctx.desc, ctx.topo, ctx.Fe, ctx.has_bias = desc, topo, Fe, bias is not None
         ctx.save_for_backward(x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk, p_amax)
         if want_alpha:

@@ -273,6 +273,18 @@ def test_edge_table_accepts_reference_order_and_rejects_others(cuda_lib):
                          ids=["small", "default_channels_2_graphs_per_cta", "H8", "odd"])
 def test_attention_stages_against_dense_oracle(cuda_lib, geom, bwd_algo):
     """attn_fwd / attn_bwd alone (P_aug given), compared stage by stage with oracle/dense_gat.py."""
+    _attention_stage_case(cuda_lib, geom, bwd_algo)
+
+
+@pytest.mark.parametrize("geom", [(2, 40, 8, 126, 6, 20), (2, 77, 8, 5, 3, 7), (1, 131, 8, 36, 8, 12), (1, 500, 8, 126, 6, 500)],
+                         ids=["N40", "N77_odd", "N131_H8", "config_D_graph"])
+def test_large_universe_attention_stages(cuda_lib, geom):
+    """N > 32: the multi-CTA-per-graph kernels (attn_large.cu), same entry points, same stage-by-stage check.
+    The last case is one full-size BASELINE config-D graph (500 nodes, 249 500 edge rows, H=6, C=500)."""
+    _attention_stage_case(cuda_lib, geom, 0)
+
+
+def _attention_stage_case(cuda_lib, geom, bwd_algo):
     B, N, Fin, Fe, H, C_ = geom
     for concat in (False, True):
         bt = synth.random_complete_batch(B, N, Fin, Fe, seed=4)
@@ -291,9 +303,18 @@ def test_attention_stages_against_dense_oracle(cuda_lib, geom, bwd_algo):
         out = torch.empty(B * N, ldo, device=DEV)
         alpha = torch.empty(B, H, N, N, device=DEV)
         check(cuda_lib.spotv2_gat_attn_fwd(C.byref(d), ptr(P_aug), ptr(ea), ptr(topo.table), ptr(v), ptr(bg), ptr(out),
-                                           ptr(alpha), st()), "attn_fwd")
+                                           ptr(alpha), None, 0, st()), "attn_fwd")
         assert relerr(alpha, fw["alpha"].permute(0, 3, 2, 1)) < TOL     # ours is [B, H, j, i]
         assert relerr(out, fw["out"]) < TOL
+        # without return_attention_weights the (N > 32) attention tile lives in a workspace: same bits
+        wsz = C.c_size_t()
+        check(cuda_lib.spotv2_gat_attn_fwd_workspace_bytes(C.byref(d), C.byref(wsz)), "attn_fwd_ws")
+        assert (wsz.value > 0) == (N > 32)
+        ws_f = torch.empty(max(wsz.value, 1), dtype=torch.uint8, device=DEV)
+        out2 = torch.empty_like(out)
+        check(cuda_lib.spotv2_gat_attn_fwd(C.byref(d), ptr(P_aug), ptr(ea), ptr(topo.table), ptr(v), ptr(bg), ptr(out2),
+                                           None, ptr(ws_f), wsz.value, st()), "attn_fwd")
+        assert torch.equal(out, out2)
         dout = torch.randn(B * N, ldo)
         gr = dense_gat.dense_backward(fw, bt.x.double(), T, W, a_s, a_d, We, a_e, dout.double(), H, C_, concat, 0.2)
         a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
@@ -366,6 +387,33 @@ def test_layer_matches_edge_list_oracle(cuda_lib, case, bwd_kernel):
     assert not bad, f"(our error, fp32-oracle error) above the bar: {bad}"
 
 
+LARGE_CASES = [
+    # B, N, Fin, Fe, H, C, concat, slope
+    (2, 33, 16, 5, 3, 7, True, 0.2),                  # first size past the one-CTA-per-graph kernels
+    (3, 64, 20, 126, 6, 20, False, 0.2),
+    (2, 100, 12, 9, 8, 33, True, 0.05),               # odd channel count -> scalar GEMM loads
+    (1, 131, 10, 126, 2, 10, False, 0.2),             # odd N: unaligned attention-tile rows
+    (1, 500, 24, 126, 6, 40, False, 0.2),             # BASELINE config D universe (500 nodes, 249 500 edges)
+]
+
+
+@pytest.mark.parametrize("gemm_algo", [0, 1], ids=["tc_gemm", "simt_gemm"])
+@pytest.mark.parametrize("case", LARGE_CASES, ids=[f"B{c[0]}N{c[1]}F{c[2]}Fe{c[3]}H{c[4]}C{c[5]}{'cat' if c[6] else 'mean'}" for c in LARGE_CASES])
+def test_large_universe_layer_matches_edge_list_oracle(cuda_lib, case, gemm_algo):
+    """BASELINE config D: graphs larger than one CTA's shared memory take the multi-CTA-per-graph path."""
+    from spotv2net_b200 import gat_conv
+    B, N, Fin, Fe, H, C_, concat, slope = case
+    ref, ours = make_layers(Fin, C_, H, concat, Fe, slope, seed=B + N)
+    bt = synth.random_complete_batch(B, N, Fin, Fe, seed=23)
+    old = gat_conv.GEMM_ALGO
+    gat_conv.GEMM_ALGO = gemm_algo
+    try:
+        bad = run_both(ref, ours, bt, need_dx=True)
+    finally:
+        gat_conv.GEMM_ALGO = old
+    assert not bad, f"(our error, fp32-oracle error) above the bar: {bad}"
+
+
 def test_layer_without_edge_attr_and_with_input_self_loops(cuda_lib):
     B, N, Fin, Fe, H, C_ = 3, 9, 10, 4, 2, 6
     ref, ours = make_layers(Fin, C_, H, True, Fe, 0.2, seed=3)
@@ -401,7 +449,7 @@ def test_dense_tile_input(cuda_lib):
     out = torch.empty(B * N, C_, device=DEV)
     T_g, v_g, b_g = T.float().to(DEV).contiguous(), fw["v"].float().to(DEV).contiguous(), bias.float().to(DEV)
     check(cuda_lib.spotv2_gat_attn_fwd(C.byref(d), ptr(P_aug), ptr(T_g), ptr(table), ptr(v_g), ptr(b_g), ptr(out),
-                                       None, st()), "attn_fwd")
+                                       None, None, 0, st()), "attn_fwd")
     assert relerr(out, fw["out"]) < TOL
 
 
