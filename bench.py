@@ -28,11 +28,25 @@ sys.path.insert(0, ROOT)
 
 METRIC = "SpotV2Net GAT fwd+bwd graphs/sec (30-node, batch 4096)"
 UNIT = "graphs/s"
-# SURVEY.md §8d / BASELINE.md §4, fp32, default geometry (N=30, Fe=126, H=6, C=500)
-ATTN_BYTES_FWD = 858_480
-ATTN_BYTES_BWD = 1_218_480
-PROJ_FLOP_PER_GRAPH = 2 * 226_800_000           # P = x W^T and dW = dP^T x
 CFG = dict(N=30, L=42, H=6, C=500, slope=0.2, concat=False)
+# The bench line is BASELINE configs[1] ("A").  --config D times the 500-node universe (configs[3]) through the
+# same code for DESIGN.md; it is a parity-test case, not the headline.
+CONFIGS = {"A": dict(N=30, batch=4096, name="BASELINE configs[1]: default GNN_param.yaml hyper-parameters, batch 4096 snapshots per GPU"),
+           "D": dict(N=500, batch=32, name="BASELINE configs[3]: 500-node complete graph (249,500 edges per snapshot), batch 32 snapshots per GPU, "
+                                           "multi-CTA-per-graph attention")}
+
+
+def attn_bytes():
+    """Algorithmic bytes per graph of the attention stage: every operand touched once per pass.
+    Default geometry: fwd 858 480 B (edge rows 438 480 + P 360 000 + out 60 000), bwd 1 218 480 B (+ dP 360 000)."""
+    N, Fin, Fe, H, Cc = cfg_dims()
+    edge, P, out = N * (N - 1) * Fe * 4, N * H * Cc * 4, N * Cc * 4
+    return edge + P + out, edge + P + out + P
+
+
+def proj_flop_per_graph():
+    N, Fin, Fe, H, Cc = cfg_dims()
+    return 2 * (2 * N * Fin * H * Cc)            # P = x W^T and dW = dP^T x  (2 x 226.8 MFLOP at the default geometry)
 
 
 def cfg_dims():
@@ -161,7 +175,9 @@ class HotPath:
         a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
         _lib.check(self.lib.spotv2_gat_workspace_bytes(C.byref(self.desc), C.byref(a), C.byref(b), C.byref(c)), "ws")
         f32 = dict(device=device, dtype=torch.float32)
-        self.ws = torch.empty(max(a.value, b.value, c.value), device=device, dtype=torch.uint8)
+        f = C.c_size_t()
+        _lib.check(self.lib.spotv2_gat_attn_fwd_workspace_bytes(C.byref(self.desc), C.byref(f)), "attn_fwd ws")
+        self.ws = torch.empty(max(a.value, b.value, c.value, f.value), device=device, dtype=torch.uint8)
         self.W_aug = torch.empty(HC + 2 * H, Fin, **f32)
         self.v = torch.empty(H, Fe, **f32)
         self.P_aug = torch.empty(n, self.desc.ldp, **f32)
@@ -186,6 +202,9 @@ class HotPath:
         # counted from the ncu launch list (profiles/r1m_launch_list_summary.txt): fold 1; amax x5 (x, W_aug x2, dout, ds|dd);
         # split x3 (x, W_aug, ds|dd); GEMM fwd; attn fwd; attn bwd + 2 partial reduces; GEMM bwd + split-K reduce; unfold
         self.kernels_per_step = 17 if self.tc else 10
+        if N > 32:   # large-universe path: attn fwd 3 (logits, softmax, GEMM); attn bwd 10 (+ amax/split of dP on the tensor-core
+            # path); fold, amax/split of x and W_aug (5), two projection GEMMs + split-K reduce, unfold
+            self.kernels_per_step = 27 if self.tc else 18
         self.ev = {}
 
     def step(self, timed_events=None, allreduce=None):
@@ -211,7 +230,7 @@ class HotPath:
                                 p(self.ws), self.ws.numel(), st), "proj_fwd")
         mark("proj_fwd")
         chk(lib.spotv2_gat_attn_fwd(d, p(self.P_aug), p(self.batch.edge_attr), p(self.batch.spot_topology.table),
-                                    p(self.v), p(L.bias), p(self.out), None, None, 0, st), "attn_fwd")
+                                    p(self.v), p(L.bias), p(self.out), None, p(self.ws), self.ws.numel(), st), "attn_fwd")
         mark("attn_fwd")
         chk(lib.spotv2_gat_attn_bwd(d, p(self.P_aug), p(self.p_amax), p(self.batch.edge_attr), p(self.batch.spot_topology.table),
                                     p(self.v), p(self.dout), p(self.dP_aug), p(ph), p(pl), p(self.dp_blk), p(self.dv),
@@ -292,17 +311,21 @@ def run_ours(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    ATTN_BYTES_FWD, ATTN_BYTES_BWD = attn_bytes()
+    PROJ_FLOP_PER_GRAPH = proj_flop_per_graph()
     t_attn = (phase_ms["attn_fwd"] + phase_ms["attn_bwd"]) * 1e-3
     attn_gbs = (ATTN_BYTES_FWD + ATTN_BYTES_BWD) * B / t_attn / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "attn_traffic.json")))
+        if args.config == "A":
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "attn_traffic.json")))
     except Exception:
         pass
     traffic_detail = traffic
     if isinstance(traffic, dict):
         traffic = traffic.get("sum")
-    roofline = {"bound": "hbm", "kernel": "gat_attn_fwd_kernel + gat_attn_bwd2_kernel", "achieved": attn_gbs,
+    roofline = {"bound": "hbm", "kernel": "gat_attn_fwd_kernel + gat_attn_bwd2_kernel" if CFG["N"] <= 32 else
+                "attn_large.cu (lg_edge_logit, lg_softmax, bgemm, lg_softmax_bwd, lg_dv kernels)", "achieved": attn_gbs,
                 "peak": hbm_peak, "unit": "GB/s", "frac": attn_gbs / hbm_peak, "traffic": traffic,
                 "traffic_detail": traffic_detail,
                 "algorithmic_bytes_per_launch_pair": (ATTN_BYTES_FWD + ATTN_BYTES_BWD) * B,
@@ -334,7 +357,7 @@ def run_ours(args):
             e2e_win = {"value": None, "unit": UNIT, "error": repr(ex)[:300]}
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == "A":
         try:
             gps, cores, ts = time_oracle(args.cpu_batch, 3, 1)
             cpu_baseline = {"value": gps, "unit": UNIT, "cores": cores, "kind": "port",
@@ -349,10 +372,11 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: default GNN_param.yaml hyper-parameters, batch 4096 snapshots per GPU, "
-                                   "fp32, GATConv fwd+bwd" + (" + NCCL gradient all-reduce" if world > 1 else ""),
+            "config": {"workload": CONFIGS[args.config]["name"] + ", fp32, GATConv fwd+bwd" +
+                                   (" + NCCL gradient all-reduce" if world > 1 else ""),
                        "nodes": N, "in_channels": Fin, "edge_dim": Fe, "heads": H, "hidden": Cc, "batch_per_gpu": B,
-                       "l2": "inputs (x 619 MB, edge_attr 1.8 GB, P 1.5 GB per step) exceed the 126 MB L2; no flush needed",
+                       "l2": f"inputs (x {B * N * Fin * 4 / 1e6:.0f} MB, edge_attr {B * N * (N - 1) * Fe * 4 / 1e9:.2f} GB, "
+                             f"P {B * N * H * Cc * 4 / 1e6:.0f} MB per step) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"dp{world}"},
             "phase_ms": phase_ms, "roofline": roofline, "roofline_projection": proj, "cpu_baseline": cpu_baseline,
             "e2e": e2e, "e2e_windows": e2e_win, "gpu_launches": hp.kernels_per_step * args.steps, "clocks": clocks,
@@ -473,12 +497,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--batch", type=int, default=0, help="graphs per GPU (default: 4096 for config A, 32 for config D)")
+    ap.add_argument("--config", default="A", choices=sorted(CONFIGS), help="A = the bench line (default); D = 500-node universe")
     ap.add_argument("--cpu-batch", type=int, default=128)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
+    CFG["N"] = CONFIGS[args.config]["N"]
+    if args.batch <= 0:
+        args.batch = CONFIGS[args.config]["batch"]
     if args.impl == "reference":
         run_reference(args)
     else:

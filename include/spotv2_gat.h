@@ -72,6 +72,14 @@ typedef struct spotv2_gat_desc {
   int32_t gemm_algo;      /* 0 | 2 tcgen05 (fp16 operand pairs), 1 fp32 CUDA cores */
   int32_t attn_bwd_algo;  /* 0 auto (pipelined kernel when its shared-memory plan fits), 1 phase-serial
                              kernel, 2 pipelined or error                           */
+  float   dropout_p;      /* attention dropout of this call: 0 = none (eval mode, or PyG's
+                             dropout=0.0 default, config/GNN_param.yaml:36).  In (0,1): every
+                             attention coefficient is zeroed with probability p and the rest
+                             scaled by 1/(1-p) AFTER the softmax (F.dropout(alpha) in [PyG]
+                             gat_conv.py message); attn_bwd regenerates the same mask            */
+  uint32_t dropout_seed_lo, dropout_seed_hi;   /* Philox4x32-10 key of the mask; element (b,h,i,j)
+                             uses counter ((((b*H+h)*N+i)*N+j) >> 2), lane (.. & 3); pass
+                             the same key to attn_fwd and attn_bwd of one step              */
 } spotv2_gat_desc;
 
 /* Row table entry: (i << 16) | j  = "this edge row is j -> i" (i target, j source),

@@ -90,6 +90,7 @@ def gat_conv_edgelist(
     training: bool = False,
     add_self_loops: bool = True,
     return_attention_weights: bool = False,
+    dropout_mask: Optional[Tensor] = None,
 ):
     """[PyG] nn/conv/gat_conv.py::GATConv.forward + edge_update + message.
 
@@ -117,7 +118,12 @@ def gat_conv_edgelist(
         a = a + (e * att_edge.view(1, H, C)).sum(dim=-1)
     a = F.leaky_relu(a, negative_slope)
     a = segment_softmax(a, dst, n)
-    alpha = F.dropout(a, p=dropout, training=training)
+    if dropout_mask is not None:
+        # test hook: F.dropout with a GIVEN Bernoulli draw ([E', H] of 0/1, PyG edge order with the self loops
+        # last) instead of torch's generator, so another implementation's mask can be replayed exactly
+        alpha = a * dropout_mask.to(a.dtype) / (1.0 - dropout)
+    else:
+        alpha = F.dropout(a, p=dropout, training=training)
 
     msg = alpha.unsqueeze(-1) * xs.index_select(0, src)        # [E', H, C]
     out = xs.new_zeros(n, H, C).index_add_(0, dst, msg)
@@ -194,12 +200,12 @@ class OracleGATConv(nn.Module):
             with torch.no_grad():
                 self.bias.zero_()
 
-    def forward(self, x, edge_index, edge_attr=None, size=None, return_attention_weights=None):
+    def forward(self, x, edge_index, edge_attr=None, size=None, return_attention_weights=None, dropout_mask=None):
         return gat_conv_edgelist(
             x, edge_index, edge_attr, self.lin_src.weight, self.att_src, self.att_dst,
             None if self.lin_edge is None else self.lin_edge.weight, self.att_edge, self.bias,
             self.heads, self.out_channels, self.concat, self.negative_slope, self.dropout,
-            self.training, self.add_self_loops, bool(return_attention_weights))
+            self.training, self.add_self_loops, bool(return_attention_weights), dropout_mask)
 
 
 def gat_layer_plan(num_node_features: int, num_heads: int, dim_hidden_layers: Sequence[int],

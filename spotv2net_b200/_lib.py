@@ -20,7 +20,8 @@ class GatDesc(C.Structure):
     """struct spotv2_gat_desc (include/spotv2_gat.h)."""
     _fields_ = [("B", _i32), ("N", _i32), ("F", _i32), ("Fe", _i32), ("H", _i32), ("C", _i32),
                 ("R", _i32), ("concat", _i32), ("negative_slope", _f32), ("ldp", _i32),
-                ("gemm_algo", _i32), ("attn_bwd_algo", _i32)]
+                ("gemm_algo", _i32), ("attn_bwd_algo", _i32),
+                ("dropout_p", _f32), ("dropout_seed_lo", C.c_uint32), ("dropout_seed_hi", C.c_uint32)]
 
 
 class SpotV2Error(RuntimeError):

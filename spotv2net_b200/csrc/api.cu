@@ -32,6 +32,8 @@ int check_desc(const spotv2_gat_desc* d) {
   if (d->ldp < d->H * d->C + 2 * d->H || d->ldp % 4 != 0)
     return fail(SPOTV2_ERR_INVALID_ARG, "ldp=%d must be >= H*C+2H=%d and a multiple of 4", d->ldp,
                 d->H * d->C + 2 * d->H);
+  if (!(d->dropout_p >= 0.f && d->dropout_p < 1.f))
+    return fail(SPOTV2_ERR_INVALID_ARG, "dropout_p=%g must be in [0, 1)", (double)d->dropout_p);
   if (d->Fe > 0 && d->R <= 0) return fail(SPOTV2_ERR_INVALID_ARG, "R must be positive when Fe > 0");
   return SPOTV2_OK;
 }

@@ -38,7 +38,7 @@ inline BwdSmem bwd_smem_plan(int N, int Fe, int H, int C, int R, int npairs, int
   const int ldo = concat ? H * C : C;
   size_t o = s.a.base_total;
   s.off_D = o;     o += round_up((size_t)H * N * s.a.NS * 4, 16);
-  s.off_mask = o;  o += round_up((size_t)H * N * 4, 16);
+  s.off_mask = o;  o += 2 * round_up((size_t)H * N * 4, 16);      // z > 0 bits | dropout keep bits
   s.off_dbias = o; o += round_up((size_t)ldo * 4, 16);
   s.off_union = round_up(o, 128);
   s.stage_P_bytes = (size_t)H * s.NP5 * kCKP * 4;
@@ -117,6 +117,7 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
   float* tile = reinterpret_cast<float*>(smem_raw + sm.a.off_tile);     // alpha[h][j][i]
   float* D = reinterpret_cast<float*>(smem_raw + sm.off_D);             // dalpha -> dz -> dz'
   uint32_t* pos_mask = reinterpret_cast<uint32_t*>(smem_raw + sm.off_mask);
+  uint32_t* keep_mask = pos_mask + ((H * N + 3) / 4) * 4;
   float* dbias_s = reinterpret_cast<float*>(smem_raw + sm.off_dbias);
   unsigned char* uni = smem_raw + sm.off_union;
   float* const stage_base = reinterpret_cast<float*>(uni);             // [buf][P rows | G rows]
@@ -299,10 +300,19 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
     if (p.bulk_ok && tid == 0 && ring.nchunks > 0) ring.prefetch_first(b);
 
     // ---- B2b: softmax / LeakyReLU backward ---------------------------------------------------
+    // With attention dropout the forward used alpha * m (m = keep / (1 - p)): dalpha = m * d(alpha m), the softmax
+    // backward runs on the un-dropped alpha, and B3 below needs alpha * m (applied in the third loop).
+    const bool drop = p.drop.p > 0.f;
     for (int idx = tid; idx < H * N; idx += kAttnThreads) {
       const int h = idx / N, i = idx - h * N;
       const float* acol = tile + (size_t)h * N * NS + i;
       float* dcol = D + (size_t)h * N * NS + i;
+      uint32_t keep = 0xffffffffu;
+      if (drop) {
+        keep = dropout_keep_bits(p.drop, (((unsigned long long)b * H + h) * N + i) * N, N);
+        keep_mask[idx] = keep;
+        for (int j = 0; j < N; ++j) dcol[j * NS] = ((keep >> j) & 1u) ? dcol[j * NS] * p.drop.scale : 0.f;
+      }
       float dot = 0.f;
       for (int j = 0; j < N; ++j) dot = fmaf(acol[j * NS], dcol[j * NS], dot);
       const uint32_t mask = pos_mask[idx];
@@ -335,6 +345,11 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
       float* dcol = D + (size_t)h * N * NS + i;
       const float share = dcol[i * NS] * inv_nm1;
       for (int j = 0; j < N; ++j) dcol[j * NS] = (j == i) ? 0.f : dcol[j * NS] + share;
+      if (drop) {
+        float* acol = tile + (size_t)h * N * NS + i;
+        const uint32_t keep = keep_mask[idx];
+        for (int j = 0; j < N; ++j) acol[j * NS] = ((keep >> j) & 1u) ? acol[j * NS] * p.drop.scale : 0.f;
+      }
     }
     // (D is next read in B4, after B3's trailing barrier)
 
@@ -628,6 +643,7 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
   a.p.R = d->R; a.p.concat = d->concat; a.p.ldp = d->ldp;
   a.p.ldo = d->concat ? d->H * d->C : d->C;
   a.p.slope = d->negative_slope;
+  a.p.drop = dropout_params(d);
   a.p.P_aug = P_aug; a.p.edge_rows = edge_rows; a.p.table = table; a.p.v = v;
   a.p.bulk_ok = d->Fe > 0 && aligned16(edge_rows) && ((size_t)d->R * d->Fe) % 4 == 0;
   a.p.vec2_ok = (d->C % 2 == 0);
@@ -666,7 +682,10 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
   int rc;
   // d->attn_bwd_algo selects the kernel: 0 = pipelined (attn_bwd2.cu) whenever its shared-memory plan fits,
   // 1 = the phase-serial kernel of this file, 2 = pipelined or error
-  if (d->attn_bwd_algo != 1 && (attn_bwd2_fits(a.p) || d->attn_bwd_algo == 2))
+  // attention dropout (a non-default training option) is implemented in the phase-serial kernel only
+  if (d->dropout_p > 0.f && d->attn_bwd_algo == 2)
+    return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd: the pipelined kernel (attn_bwd_algo = 2) does not implement attention dropout");
+  if (d->dropout_p == 0.f && d->attn_bwd_algo != 1 && (attn_bwd2_fits(a.p) || d->attn_bwd_algo == 2))
     rc = launch_attn_bwd2(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
   else if (np <= 4) rc = launch_bwd<4>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
   else if (np <= 8) rc = launch_bwd<8>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);

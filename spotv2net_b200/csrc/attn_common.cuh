@@ -12,6 +12,67 @@ constexpr int kBwdChunkRows = 48; // edge rows per ring stage, backward (3 m16 t
 constexpr int kMaxHeads = 8;     // one n8 MMA tile of heads (reference HPO range is 2..7; config C uses 8)
 constexpr int kMaxFe = 512;
 
+// Attention dropout (F.dropout(alpha, p, training) in [PyG] gat_conv.py message): a counter-based mask that the
+// forward and the recomputing backward regenerate independently.  Element e = ((b*H + h)*N + i)*N + j takes lane
+// e & 3 of Philox4x32-10(counter = e >> 2, key = seed); kept iff the 32-bit draw >= thresh = p * 2^32.
+struct DropoutParams {
+  float p;          // 0 = off
+  float scale;      // 1 / (1 - p)
+  uint32_t thresh, k0, k1;
+};
+
+inline DropoutParams dropout_params(const spotv2_gat_desc* d) {
+  DropoutParams r{0.f, 1.f, 0u, d->dropout_seed_lo, d->dropout_seed_hi};
+  if (d->dropout_p > 0.f) {
+    r.p = d->dropout_p;
+    r.scale = 1.f / (1.f - d->dropout_p);
+    const double t = (double)d->dropout_p * 4294967296.0;
+    r.thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+  }
+  return r;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+  uint32_t c2 = 0u, c3 = 0u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    c0 = h1 ^ c1 ^ k0;
+    c1 = l1;
+    c2 = h0 ^ c3 ^ k1;
+    c3 = l0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ bool dropout_keep(const DropoutParams& d, unsigned long long e) {
+  const uint4 r = philox4x32_10((uint32_t)(e >> 2), (uint32_t)(e >> 34), d.k0, d.k1);
+  const uint32_t lane = (uint32_t)e & 3u;
+  const uint32_t v = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
+  return v >= d.thresh;
+}
+
+// Bit j = 1 iff element base + j is kept, j < n <= 32 (one Philox call per 4 consecutive elements).
+__device__ __forceinline__ uint32_t dropout_keep_bits(const DropoutParams& d, unsigned long long base, int n) {
+  uint32_t bits = 0u;
+  unsigned long long cur = ~0ull;
+  uint4 r = make_uint4(0u, 0u, 0u, 0u);
+  for (int j = 0; j < n; ++j) {
+    const unsigned long long e = base + (unsigned long long)j;
+    if ((e >> 2) != cur) {
+      cur = e >> 2;
+      r = philox4x32_10((uint32_t)cur, (uint32_t)(cur >> 32), d.k0, d.k1);
+    }
+    const uint32_t lane = (uint32_t)e & 3u;
+    const uint32_t v = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
+    bits |= (v >= d.thresh ? 1u : 0u) << j;
+  }
+  return bits;
+}
+
 struct AttnParams {
   int B, N, F, Fe, H, C, R, concat, ldp, ldo;
   float slope;
@@ -21,6 +82,7 @@ struct AttnParams {
   const float* v;
   int bulk_ok;     // edge block 16-byte aligned and R*Fe % 4 == 0
   int vec2_ok;     // C even (8-byte aligned channel pairs)
+  DropoutParams drop;
 };
 
 // Shared-memory plan common to both directions.  All offsets in bytes, 16-aligned.
@@ -206,7 +268,9 @@ __device__ __forceinline__ void softmax_phase(const AttnParams& p, const AttnSme
                                               const float* sd, float out_scale, float* alpha_out_b,
                                               uint32_t* pos_mask, int tid, int nthreads = kAttnThreads,
                                               int sd_j_stride = -1, int sd_swizzled = 0,
-                                              const float* tile_add = nullptr) {
+                                              const float* tile_add = nullptr, int drop_graph = -1) {
+  // drop_graph >= 0: apply this call's attention dropout to graph `drop_graph` (the forward); the backward
+  // passes -1, recomputes the un-dropped coefficients and applies the mask itself.
   const int N = p.N, H = p.H, NS = sm.NS;
   // s_j = sd(j, h), d_i = sd(i, H + h).  sd is either a packed [N][2H] array or (sd_swizzled) a
   // 128B-swizzled TMA tile of 32 rows x 32 floats holding the 2H augmented columns of P_aug.
@@ -247,9 +311,15 @@ __device__ __forceinline__ void softmax_phase(const AttnParams& p, const AttnSme
     }
     // PyG divides by (sum + 1e-16); one reciprocal + multiplies differ from that by <= 1 ulp
     const float inv = 1.f / (sum + 1e-16f);
+    uint32_t keep = 0xffffffffu;
+    float kscale = 1.f;
+    if (drop_graph >= 0 && p.drop.p > 0.f) {
+      keep = dropout_keep_bits(p.drop, (((unsigned long long)drop_graph * H + h) * N + i) * N, N);
+      kscale = p.drop.scale;
+    }
 #pragma unroll 6
     for (int j = 0; j < N; ++j) {
-      const float a = col[j * NS] * inv;
+      const float a = ((keep >> j) & 1u) ? col[j * NS] * inv * kscale : 0.f;
       if (alpha_out_b) alpha_out_b[((size_t)h * N + j) * N + i] = a;
       col[j * NS] = a * out_scale;
     }

@@ -268,7 +268,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm_, const uint32_t o
       mbar_wait_timed(&sd_full[buf], (it >> 1) & 1, w_tf);
       softmax_phase(p, sm, tile, reinterpret_cast<const float*>(smem_raw + off_sdtile + buf * kPTileBytes), out_scale,
                     args.alpha_out ? args.alpha_out + (size_t)b * H * N * N : nullptr, nullptr, tid - kGroupA, kGroupB,
-                    -1, /*sd_swizzled=*/1);
+                    -1, /*sd_swizzled=*/1, nullptr, b);
       bar_sync_group_b();                                // alpha tile complete
       if (tid == kGroupA) mbar_arrive_cta(&sd_empty[buf]);
       for (int pass = 0; pass < n_pass; ++pass) {
@@ -506,6 +506,7 @@ extern "C" int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug,
   a.p.R = d->R; a.p.concat = d->concat; a.p.ldp = d->ldp;
   a.p.ldo = d->concat ? d->H * d->C : d->C;
   a.p.slope = d->negative_slope;
+  a.p.drop = dropout_params(d);
   a.p.P_aug = P_aug; a.p.edge_rows = edge_rows; a.p.table = table; a.p.v = v;
   a.p.bulk_ok = d->Fe > 0 && aligned16(edge_rows) && ((size_t)d->R * d->Fe) % 4 == 0;
   a.p.vec2_ok = (d->C % 2 == 0);

@@ -113,87 +113,138 @@ __global__ void __launch_bounds__(kLgThreads) lg_edge_logit_kernel(const LgLogit
   }
 }
 
-// S: one thread per (b, h, target i) column of Z.  Zraw may be null (layer called without edge_attr: all edge
-// terms 0) and may alias A.  gii_out (optional) receives the self-loop fill for the backward.
-__global__ void __launch_bounds__(128)
+// S: a block owns 32 target columns i of one (b, h) tile; its 8 thread rows split the N sources (j = ty, ty + 8,
+// ...), so a warp reads 128 contiguous bytes per source row and every column has 8 independent load streams.
+// Partial results meet in shared memory in a fixed order.  Zraw may be null (layer called without edge_attr: all
+// edge terms 0) and may alias A.  gii_out (optional) receives the self-loop fill for the backward.
+constexpr int kSmX = 32, kSmY = 8;
+
+__device__ __forceinline__ float lg_logit(const float* zc, int j, int i, int N, float gii, float sj, float di, float slope) {
+  const float g = (j == i) ? gii : (zc ? zc[(size_t)j * N] : 0.f);
+  const float z = g + sj + di;
+  return z > 0.f ? z : z * slope;
+}
+
+__global__ void __launch_bounds__(kSmX * kSmY)
 lg_softmax_kernel(const float* __restrict__ P_aug, const float* Zraw, float* A, float* __restrict__ gii_out,
-                  int N, int H, int HC, int ldp, float slope) {
+                  int N, int H, int HC, int ldp, float slope, const DropoutParams drop) {
   extern __shared__ float s_src[];             // s_j of this (b, h)
-  const int b = blockIdx.z, h = blockIdx.y;
+  __shared__ float red[2][kSmY][kSmX];
+  const int b = blockIdx.z, h = blockIdx.y, tx = threadIdx.x, ty = threadIdx.y;
   const float* Pb = P_aug + (size_t)b * N * ldp;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) s_src[j] = Pb[(size_t)j * ldp + HC + h];
+  for (int j = ty * kSmX + tx; j < N; j += kSmX * kSmY) s_src[j] = Pb[(size_t)j * ldp + HC + h];
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  const size_t base = ((size_t)b * H + h) * N * N + i;
+  const int i = blockIdx.x * kSmX + tx;
+  const bool live = i < N;
+  const int ic = live ? i : N - 1;             // dead lanes shadow the last column and never store
+  const size_t base = ((size_t)b * H + h) * N * N + ic;
   const float* zc = Zraw ? Zraw + base : nullptr;
   float* ac = A + base;
-  const float di = Pb[(size_t)i * ldp + HC + H + h];
+  const float di = Pb[(size_t)ic * ldp + HC + H + h];
   float gsum = 0.f;
   if (zc) {
 #pragma unroll 8
-    for (int j = 0; j < N; ++j) gsum += (j != i) ? zc[(size_t)j * N] : 0.f;
+    for (int j = ty; j < N; j += kSmY) gsum += (j != ic) ? zc[(size_t)j * N] : 0.f;
   }
+  red[0][ty][tx] = gsum;
+  __syncthreads();
+  gsum = 0.f;
+#pragma unroll
+  for (int k = 0; k < kSmY; ++k) gsum += red[0][k][tx];
   const float gii = gsum / (float)(N > 1 ? N - 1 : 1);
-  if (gii_out) gii_out[((size_t)b * H + h) * N + i] = gii;
+  if (gii_out && live && ty == 0) gii_out[((size_t)b * H + h) * N + i] = gii;
   float mx = -INFINITY, sum = 0.f;
-#pragma unroll 4
-  for (int j = 0; j < N; ++j) {
-    const float g = (j == i) ? gii : (zc ? zc[(size_t)j * N] : 0.f);
-    const float z = g + s_src[j] + di;
-    const float l = z > 0.f ? z : z * slope;
+#pragma unroll 8
+  for (int j = ty; j < N; j += kSmY) {
+    const float l = lg_logit(zc, j, ic, N, gii, s_src[j], di, slope);
     if (l > mx) {
       sum *= expf(mx - l);
       mx = l;
     }
     sum += expf(l - mx);
   }
-  const float inv = 1.f / (sum + 1e-16f);
-#pragma unroll 4
-  for (int j = 0; j < N; ++j) {
-    const float g = (j == i) ? gii : (zc ? zc[(size_t)j * N] : 0.f);
-    const float z = g + s_src[j] + di;
-    const float l = z > 0.f ? z : z * slope;
-    ac[(size_t)j * N] = expf(l - mx) * inv;
+  __syncthreads();
+  red[0][ty][tx] = mx;
+  red[1][ty][tx] = sum;
+  __syncthreads();
+  float M = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < kSmY; ++k) M = fmaxf(M, red[0][k][tx]);
+  float S = 0.f;
+#pragma unroll
+  for (int k = 0; k < kSmY; ++k) S += red[0][k][tx] == -INFINITY ? 0.f : red[1][k][tx] * expf(red[0][k][tx] - M);
+  const float inv = 1.f / (S + 1e-16f);
+  if (!live) return;
+#pragma unroll 8
+  for (int j = ty; j < N; j += kSmY) {
+    const float l = lg_logit(zc, j, ic, N, gii, s_src[j], di, slope);
+    float a = expf(l - M) * inv;
+    if (drop.p > 0.f)        // forward only: the backward recomputes with drop.p = 0 and applies the mask itself
+      a = dropout_keep(drop, (((unsigned long long)b * H + h) * N + i) * N + j) ? a * drop.scale : 0.f;
+    ac[(size_t)j * N] = a;
   }
 }
 
-// Softmax + LeakyReLU backward per column.  dA holds dalpha on entry and dz on exit (diagonal included: it is
-// the self loop's dz); fill[b,h,i] = dz_ii / (N - 1), the gradient every incoming edge term of i receives
+// Softmax + LeakyReLU backward, same thread layout.  dA holds dalpha on entry and dz on exit (diagonal included:
+// it is the self loop's dz); fill[b,h,i] = dz_ii / (N - 1), the gradient every incoming edge term of i receives
 // through the mean fill; dd_i goes to column HC + H + h of dP_aug.
-__global__ void __launch_bounds__(128)
-lg_softmax_bwd_kernel(const float* __restrict__ P_aug, const float* __restrict__ Zraw, const float* __restrict__ A,
+__global__ void __launch_bounds__(kSmX * kSmY)
+lg_softmax_bwd_kernel(const float* __restrict__ P_aug, const float* __restrict__ Zraw, float* A,
                       float* dA, const float* __restrict__ gii, float* __restrict__ fill, float* dP_aug, int N,
-                      int H, int HC, int ldp, float slope) {
+                      int H, int HC, int ldp, float slope, const DropoutParams drop) {
   extern __shared__ float s_src[];
-  const int b = blockIdx.z, h = blockIdx.y;
+  __shared__ float red[kSmY][kSmX];
+  __shared__ float s_dzii[kSmX];
+  const int b = blockIdx.z, h = blockIdx.y, tx = threadIdx.x, ty = threadIdx.y;
   const float* Pb = P_aug + (size_t)b * N * ldp;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) s_src[j] = Pb[(size_t)j * ldp + HC + h];
+  for (int j = ty * kSmX + tx; j < N; j += kSmX * kSmY) s_src[j] = Pb[(size_t)j * ldp + HC + h];
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  const size_t base = ((size_t)b * H + h) * N * N + i;
+  const int i = blockIdx.x * kSmX + tx;
+  const bool live = i < N;
+  const int ic = live ? i : N - 1;
+  const size_t base = ((size_t)b * H + h) * N * N + ic;
   const float* zc = Zraw ? Zraw + base : nullptr;
-  const float* ac = A + base;
+  float* ac = A + base;
   float* dc = dA + base;
-  const float di = Pb[(size_t)i * ldp + HC + H + h];
-  const float g_ii = gii[((size_t)b * H + h) * N + i];
+  const float di = Pb[(size_t)ic * ldp + HC + H + h];
+  const float g_ii = gii[((size_t)b * H + h) * N + ic];
+  // attention dropout: the forward used alpha * m (m = keep / (1 - p)), so dalpha = m * d(alpha m); A leaves this
+  // kernel as alpha * m for the dP product
+  const unsigned long long ebase = (((unsigned long long)b * H + h) * N + ic) * N;
+  auto mfac = [&](int j) { return drop.p > 0.f ? (dropout_keep(drop, ebase + j) ? drop.scale : 0.f) : 1.f; };
   float dot = 0.f;
 #pragma unroll 8
-  for (int j = 0; j < N; ++j) dot = fmaf(ac[(size_t)j * N], dc[(size_t)j * N], dot);
-  float dd = 0.f, dz_ii = 0.f;
-#pragma unroll 4
-  for (int j = 0; j < N; ++j) {
-    const float g = (j == i) ? g_ii : (zc ? zc[(size_t)j * N] : 0.f);
+  for (int j = ty; j < N; j += kSmY) dot = fmaf(ac[(size_t)j * N], dc[(size_t)j * N] * mfac(j), dot);
+  red[ty][tx] = dot;
+  __syncthreads();
+  dot = 0.f;
+#pragma unroll
+  for (int k = 0; k < kSmY; ++k) dot += red[k][tx];
+  __syncthreads();
+  float dd = 0.f;
+#pragma unroll 8
+  for (int j = ty; j < N; j += kSmY) {
+    const float g = (j == ic) ? g_ii : (zc ? zc[(size_t)j * N] : 0.f);
     const float z = g + s_src[j] + di;
-    const float dl = ac[(size_t)j * N] * (dc[(size_t)j * N] - dot);
+    const float m = mfac(j), al = ac[(size_t)j * N];
+    const float dl = al * (dc[(size_t)j * N] * m - dot);
     const float dz = z > 0.f ? dl : dl * slope;
     dd += dz;
-    if (j == i) dz_ii = dz;
-    dc[(size_t)j * N] = dz;
+    if (j == ic) s_dzii[tx] = dz;
+    if (live) {
+      dc[(size_t)j * N] = dz;
+      if (drop.p > 0.f) ac[(size_t)j * N] = al * m;
+    }
   }
-  fill[((size_t)b * H + h) * N + i] = dz_ii / (float)(N > 1 ? N - 1 : 1);
-  dP_aug[((size_t)b * N + i) * ldp + HC + H + h] = dd;
+  red[ty][tx] = dd;
+  __syncthreads();
+  if (ty == 0 && live) {
+    dd = 0.f;
+#pragma unroll
+    for (int k = 0; k < kSmY; ++k) dd += red[k][tx];
+    fill[((size_t)b * H + h) * N + i] = s_dzii[tx] / (float)(N > 1 ? N - 1 : 1);
+    dP_aug[((size_t)b * N + i) * ldp + HC + H + h] = dd;
+  }
 }
 
 // ds_j = sum_i dz[j][i] -> column HC + h of dP_aug.  One warp per (b, h, j) row, fixed lane-strided order.
@@ -229,7 +280,7 @@ template <int KPT>
 __global__ void __launch_bounds__(kLgThreads) lg_dv_kernel(const LgDvArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-  float* wrow = reinterpret_cast<float*>(smem + a.off_w);       // [CR][8]
+  float* wrow = reinterpret_cast<float*>(smem + a.off_w);       // [2][CR][8]
   float* stage[2] = {reinterpret_cast<float*>(smem + a.off_stage),
                      reinterpret_cast<float*>(smem + a.off_stage + a.stage_bytes)};
   const int tid = threadIdx.x;
@@ -251,29 +302,40 @@ __global__ void __launch_bounds__(kLgThreads) lg_dv_kernel(const LgDvArgs a) {
   for (int kk = 0; kk < KPT; ++kk)
 #pragma unroll
     for (int h = 0; h < 8; ++h) tot[kk][h] = 0.0;
+  // Row weights w_r[h] = dz[h][j][i] + fill[h][i] of a chunk: one thread per row (CR <= 128), gathered through the row
+  // table one chunk AHEAD so the two dependent scattered loads hide behind the current chunk's wait and FMAs.
+  auto gather = [&](long long q, float (&w)[8]) {
+#pragma unroll
+    for (int h = 0; h < 8; ++h) w[h] = 0.f;
+    if (tid >= rg.rows_of(q)) return;
+    const long long b = q / rg.cpg;
+    const int code = __ldg(a.table + (int)(q - b * rg.cpg) * rg.CR + tid);
+    if (code < 0) return;
+    const int i = code >> 16, j = code & 0xffff;
+    const float* dzb = a.dZ + (size_t)b * H * N * N + (size_t)j * N + i;
+    const float* fb = a.fill + (size_t)b * H * N + i;
+#pragma unroll
+    for (int h = 0; h < 8; ++h)
+      if (h < H) w[h] = __ldg(dzb + (size_t)h * N * N) + __ldg(fb + (size_t)h * N);
+  };
+  auto put = [&](int buf, const float (&w)[8]) {
+    if (tid < rg.CR) {
+      float* dst = wrow + ((size_t)buf * rg.CR + tid) * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(w[4], w[5], w[6], w[7]);
+    }
+  };
+  float wnext[8];
+  if (q0 < rg.items) {
+    gather(q0, wnext);
+    put(0, wnext);
+  }
   uint32_t it = 0;
   for (long long q = q0; q < rg.items; q += step, ++it) {
     const int s = it & 1;
     const int rows = rg.rows_of(q);
-    const long long b = q / rg.cpg;
-    const int row_base = (int)(q - b * rg.cpg) * rg.CR;
-    // weights of this chunk's rows (gathered from the dz tile while the copy is in flight)
-    for (int r = tid; r < rows; r += kLgThreads) {
-      const int code = __ldg(a.table + row_base + r);
-      float w[8];
-#pragma unroll
-      for (int h = 0; h < 8; ++h) w[h] = 0.f;
-      if (code >= 0) {
-        const int i = code >> 16, j = code & 0xffff;
-        const float* dzb = a.dZ + (size_t)b * H * N * N + (size_t)j * N + i;
-        const float* fb = a.fill + (size_t)b * H * N + i;
-#pragma unroll
-        for (int h = 0; h < 8; ++h)
-          if (h < H) w[h] = dzb[(size_t)h * N * N] + fb[(size_t)h * N];
-      }
-      *reinterpret_cast<float4*>(wrow + r * 8) = make_float4(w[0], w[1], w[2], w[3]);
-      *reinterpret_cast<float4*>(wrow + r * 8 + 4) = make_float4(w[4], w[5], w[6], w[7]);
-    }
+    const bool more = q + step < rg.items;
+    if (more) gather(q + step, wnext);
     if (rg.bulk_ok) {
       mbar_wait(&full[s], (it >> 1) & 1);
     } else {
@@ -286,9 +348,11 @@ __global__ void __launch_bounds__(kLgThreads) lg_dv_kernel(const LgDvArgs a) {
 #pragma unroll
       for (int p = 0; p < 4; ++p) acc[kk][p] = make_float2(0.f, 0.f);
     const float* T = stage[s];
+    const float* wr = wrow + (size_t)s * rg.CR * 8;
+#pragma unroll 4
     for (int r = 0; r < rows; ++r) {
-      const float4 w0 = *reinterpret_cast<const float4*>(wrow + r * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(wrow + r * 8 + 4);
+      const float4 w0 = *reinterpret_cast<const float4*>(wr + r * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(wr + r * 8 + 4);
       const float2 wp[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y),
                             make_float2(w1.z, w1.w)};
 #pragma unroll
@@ -307,6 +371,7 @@ __global__ void __launch_bounds__(kLgThreads) lg_dv_kernel(const LgDvArgs a) {
         tot[kk][2 * p] += (double)acc[kk][p].x;
         tot[kk][2 * p + 1] += (double)acc[kk][p].y;
       }
+    if (more) put(s ^ 1, wnext);
     __syncthreads();
     if (rg.bulk_ok && tid == 0 && q + 2 * step < rg.items) lg_issue(rg, q + 2 * step, stage[s], &full[s]);
   }
@@ -390,9 +455,11 @@ int lg_logits(const AttnParams& p, const LgPlan& pl, float* Z, cudaStream_t st) 
   return SPOTV2_OK;
 }
 
-int lg_softmax(const AttnParams& p, const float* Zraw, float* A, float* gii, cudaStream_t st) {
-  dim3 grid((p.N + 127) / 128, p.H, p.B);
-  lg_softmax_kernel<<<grid, 128, (size_t)p.N * sizeof(float), st>>>(p.P_aug, Zraw, A, gii, p.N, p.H, p.H * p.C, p.ldp, p.slope);
+int lg_softmax(const AttnParams& p, const float* Zraw, float* A, float* gii, bool apply_dropout, cudaStream_t st) {
+  DropoutParams drop = p.drop;
+  if (!apply_dropout) drop.p = 0.f;
+  dim3 grid((p.N + kSmX - 1) / kSmX, p.H, p.B);
+  lg_softmax_kernel<<<grid, dim3(kSmX, kSmY), (size_t)p.N * sizeof(float), st>>>(p.P_aug, Zraw, A, gii, p.N, p.H, p.H * p.C, p.ldp, p.slope, drop);
   SPOTV2_CUDA_OK(cudaGetLastError());
   return SPOTV2_OK;
 }
@@ -432,7 +499,7 @@ int attn_large_fwd(const AttnParams& p, const float* bias, float* out, float* al
     if (pl.smem_logit > 227 * 1024) return fail(SPOTV2_ERR_UNSUPPORTED, "attn_fwd (large N): Fe=%d needs %zu B shared memory", p.Fe, pl.smem_logit);
     if (int rc = lg_logits(p, pl, A, st)) return rc;
   }
-  if (int rc = lg_softmax(p, p.Fe > 0 ? A : nullptr, A, nullptr, st)) return rc;
+  if (int rc = lg_softmax(p, p.Fe > 0 ? A : nullptr, A, nullptr, true, st)) return rc;
   const long long NN = (long long)p.N * p.N;
   BGemm g{};
   g.M = p.N; g.N = p.C; g.K = p.N;
@@ -476,7 +543,7 @@ int attn_large_bwd(const spotv2_gat_desc* d, AttnBwdArgs& a, float* dv, float* d
     if (int rc = lg_logits(p, pl, Zraw, st)) return rc;
   }
   const float* Zr = p.Fe > 0 ? Zraw : nullptr;
-  if (int rc = lg_softmax(p, Zr, A, gii, st)) return rc;
+  if (int rc = lg_softmax(p, Zr, A, gii, false, st)) return rc;
 
   const long long NN = (long long)p.N * p.N;
   const float gsc = p.concat ? 1.f : 1.f / (float)p.H;
@@ -491,9 +558,9 @@ int attn_large_bwd(const spotv2_gat_desc* d, AttnBwdArgs& a, float* dv, float* d
     if (int rc = bgemm_simt(true, true, g, p.B * p.H, st)) return rc;
   }
   {
-    dim3 grid((p.N + 127) / 128, p.H, p.B);
-    lg_softmax_bwd_kernel<<<grid, 128, (size_t)p.N * sizeof(float), st>>>(p.P_aug, Zr, A, dA, gii, fill, dP, p.N, p.H, HC,
-                                                                          p.ldp, p.slope);
+    dim3 grid((p.N + kSmX - 1) / kSmX, p.H, p.B);
+    lg_softmax_bwd_kernel<<<grid, dim3(kSmX, kSmY), (size_t)p.N * sizeof(float), st>>>(p.P_aug, Zr, A, dA, gii, fill, dP, p.N, p.H, HC,
+                                                                          p.ldp, p.slope, p.drop);
     SPOTV2_CUDA_OK(cudaGetLastError());
     const long long warps = (long long)p.B * p.H * p.N;
     lg_rowsum_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(dA, dP, p.B, p.N, p.H, HC, p.ldp);
@@ -504,7 +571,7 @@ int attn_large_bwd(const spotv2_gat_desc* d, AttnBwdArgs& a, float* dv, float* d
     v.rg = lg_ring(p, pl);
     v.table = p.table; v.dZ = dA; v.fill = fill; v.part = dv_part; v.N = p.N; v.H = p.H;
     v.off_w = pl.off_w; v.off_stage = pl.off_stage; v.stage_bytes = pl.stage_bytes;
-    if ((size_t)pl.CR * 8 * sizeof(float) > pl.off_stage - pl.off_w)
+    if ((size_t)2 * pl.CR * 8 * sizeof(float) > pl.off_stage - pl.off_w || pl.CR > kLgThreads)
       return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd (large N): row-weight block does not fit its slot");
     const int kpt = (p.Fe + kLgThreads - 1) / kLgThreads;
     auto launch = [&](auto kern) -> int {

@@ -111,10 +111,12 @@ GEMM_ALGO = 0
 ATTN_BWD_ALGO = 0
 
 
-def _desc(topo: Topology, F_in: int, Fe: int, H: int, Cc: int, concat: bool, slope: float) -> GatDesc:
+def _desc(topo: Topology, F_in: int, Fe: int, H: int, Cc: int, concat: bool, slope: float,
+          dropout_p: float = 0.0, seed: int = 0) -> GatDesc:
     lib = _lib.load()
     return GatDesc(topo.B, topo.N, F_in, Fe, H, Cc, topo.R, int(concat), float(slope),
-                   lib.spotv2_gat_ldp(H, Cc), GEMM_ALGO, ATTN_BWD_ALGO)
+                   lib.spotv2_gat_ldp(H, Cc), GEMM_ALGO, ATTN_BWD_ALGO,
+                   float(dropout_p), seed & 0xffffffff, (seed >> 32) & 0xffffffff)
 
 
 def _workspace(desc: GatDesc):
@@ -134,12 +136,14 @@ class _GatLayerFn(torch.autograd.Function):
     """fold -> projection GEMM -> fused attention, and the recompute-based backward."""
 
     @staticmethod
-    def forward(ctx, x, edge_attr, W, a_src, a_dst, W_e, a_edge, bias, topo, H, Cc, concat, slope, want_alpha):
+    def forward(ctx, x, edge_attr, W, a_src, a_dst, W_e, a_edge, bias, topo, H, Cc, concat, slope, want_alpha,
+                dropout_p=0.0, seed=0):
         lib = _lib.load()
         dev = x.device
         st = stream_ptr(dev)
         Fe = 0 if edge_attr is None or W_e is None else edge_attr.shape[1]
-        desc = _desc(topo, x.shape[1], Fe, H, Cc, concat, slope)
+        # the descriptor (incl. this step's dropout key) is kept for the backward, which regenerates the same mask
+        desc = _desc(topo, x.shape[1], Fe, H, Cc, concat, slope, dropout_p, seed)
         n, HC = x.shape[0], H * Cc
         x = x.contiguous()
         ea = edge_attr.contiguous() if Fe else None
@@ -230,7 +234,7 @@ class _GatLayerFn(torch.autograd.Function):
                                     ptr(da_dst), ptr(dW_e), ptr(da_edge), st), "spotv2_gat_unfold")
         if not Fe and W_e is not None:          # layer has lin_edge but was called with edge_attr=None
             dW_e, da_edge = torch.zeros_like(W_e), torch.zeros_like(a_edge)
-        return (dx, None, dW, da_src, da_dst, dW_e, da_edge, dbias, None, None, None, None, None, None)
+        return (dx, None, dW, da_src, da_dst, dW_e, da_edge, dbias, None, None, None, None, None, None, None, None)
 
 
 # --------------------------------------------------------------------------- module
@@ -319,9 +323,14 @@ class GATConv(nn.Module):
                 return_attention_weights=None, topology: Optional[Topology] = None):
         assert x.dim() == 2, "Static graphs not supported in 'GATConv'"
         _lib.require_cuda(x, "x")
+        # attention dropout (dropout_att; 0.0 by default, config/GNN_param.yaml:36): a fresh 64-bit Philox key per
+        # call from torch's CPU generator (so torch.manual_seed reproduces a run); the kernels derive the mask from it
+        drop_p, seed = 0.0, 0
         if self.dropout > 0.0 and self.training:
-            raise SpotV2Error("attention dropout (dropout_att > 0) in training mode is not implemented yet; "
-                              "the reference default is 0.0 (config/GNN_param.yaml:36)")
+            if not self.dropout < 1.0:
+                raise SpotV2Error("dropout must be in [0, 1)")
+            drop_p = float(self.dropout)
+            seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
         if edge_attr is not None:
             _lib.require_cuda(edge_attr, "edge_attr")
             if edge_attr.dim() == 1:
@@ -334,7 +343,7 @@ class GATConv(nn.Module):
         out, alpha_tile = _GatLayerFn.apply(
             x, edge_attr if use_edge else None, self.lin_src.weight, self.att_src, self.att_dst,
             self.lin_edge.weight if self.lin_edge is not None else None, self.att_edge, self.bias,
-            topo, self.heads, self.out_channels, self.concat, self.negative_slope, want_alpha)
+            topo, self.heads, self.out_channels, self.concat, self.negative_slope, want_alpha, drop_p, seed)
         if not want_alpha:
             return out
         return out, self._attention_weights(alpha_tile, topo, edge_index)
@@ -345,7 +354,7 @@ class GATConv(nn.Module):
         dev = alpha_tile.device
         H = self.heads
         desc = GatDesc(topo.B, topo.N, self.in_channels, 0, H, self.out_channels, topo.R, int(self.concat),
-                       float(self.negative_slope), lib.spotv2_gat_ldp(H, self.out_channels), 0, 0)
+                       float(self.negative_slope), lib.spotv2_gat_ldp(H, self.out_channels), 0, 0, 0.0, 0, 0)
         n = topo.B * topo.N
         alpha = torch.empty(topo.B * topo.R + n, H, device=dev, dtype=torch.float32)
         check(lib.spotv2_alpha_to_pyg(C.byref(desc), ptr(alpha_tile), ptr(topo.table), ptr(alpha), stream_ptr(dev)),

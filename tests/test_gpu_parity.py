@@ -414,6 +414,60 @@ def test_large_universe_layer_matches_edge_list_oracle(cuda_lib, case, gemm_algo
     assert not bad, f"(our error, fp32-oracle error) above the bar: {bad}"
 
 
+@pytest.mark.parametrize("case", [(3, 30, 40, 126, 6, 20, False), (2, 13, 9, 5, 3, 7, True), (2, 40, 12, 9, 4, 10, False)],
+                         ids=["N30_mean", "N13_cat", "N40_large_path"])
+def test_attention_dropout_in_training_mode_replays_in_the_oracle(cuda_lib, case):
+    """dropout_att > 0 (F.dropout(alpha) in [PyG] gat_conv.py message; HPO range of the reference).  The mask comes
+    from the library's own Philox stream, so parity is checked by REPLAYING it: the dropped coefficients returned by
+    return_attention_weights give the Bernoulli draw, the oracle applies the same draw, and outputs and every
+    gradient (whose backward regenerates the mask from the key) must agree to the usual bar."""
+    import copy
+    B, N, Fin, Fe, H, C_, concat = case
+    pdrop = 0.3
+    ref, ours = make_layers(Fin, C_, H, concat, Fe, 0.2, seed=N)
+    ours.dropout = ref.dropout = pdrop
+    bt = synth.random_complete_batch(B, N, Fin, Fe, seed=31)
+    dout = torch.randn(B * N, H * C_ if concat else C_)
+    xg, eig, eag = bt.x.to(DEV).requires_grad_(True), bt.edge_index.to(DEV), bt.edge_attr.to(DEV)
+
+    def ours_pass(seed):
+        ours.zero_grad()
+        xg.grad = None
+        torch.manual_seed(seed)
+        out, (_, a) = ours(xg, eig, eag, return_attention_weights=True)
+        out.backward(dout.to(DEV))
+        res = {"out": out.detach(), "alpha": a.detach(), "g_x": xg.grad.clone()}
+        res.update({"g_" + k: p.grad.clone() for k, p in ours.named_parameters()})
+        return res
+
+    ours.train()
+    mine = ours_pass(7)
+    mask = (mine["alpha"] != 0).cpu()
+    keep = mask.float().mean().item()
+    assert abs(keep - (1 - pdrop)) < 0.03, keep
+    again = ours_pass(7)
+    assert all(torch.equal(mine[k], again[k]) for k in mine)            # same torch seed, same key, same bits
+    other = ours_pass(8)
+    assert not torch.equal((other["alpha"] != 0).cpu(), mask)            # a fresh key per step
+
+    def oracle(dtype):
+        m = copy.deepcopy(ref).to(dtype).train()
+        x = bt.x.to(dtype).requires_grad_(True)
+        out, (_, a) = m(x, bt.edge_index, bt.edge_attr.to(dtype), return_attention_weights=True, dropout_mask=mask)
+        out.backward(dout.to(dtype))
+        res = {"out": out.detach(), "alpha": a.detach(), "g_x": x.grad}
+        res.update({"g_" + k: p.grad for k, p in m.named_parameters()})
+        return res
+
+    bad = parity_failures(mine, oracle(torch.float64), oracle(torch.float32))
+    assert not bad, bad
+    ours.eval()                                                          # eval mode: no dropout
+    out_eval, (_, a_eval) = ours(xg, eig, eag, return_attention_weights=True)
+    assert (a_eval > 0).all()
+    ref_eval = copy.deepcopy(ref).eval()(bt.x.double(), bt.edge_index, bt.edge_attr.double())
+    assert relerr(out_eval, ref_eval) < TOL
+
+
 def test_layer_without_edge_attr_and_with_input_self_loops(cuda_lib):
     B, N, Fin, Fe, H, C_ = 3, 9, 10, 4, 2, 6
     ref, ours = make_layers(Fin, C_, H, True, Fe, 0.2, seed=3)
