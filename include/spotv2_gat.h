@@ -69,7 +69,9 @@ typedef struct spotv2_gat_desc {
   int32_t concat;         /* 1: out is [B*N, H*C]; 0: head mean, out is [B*N, C]   */
   float   negative_slope; /* LeakyReLU slope                                       */
   int32_t ldp;            /* row stride of P_aug / dP_aug: >= H*C + 2*H, % 4 == 0  */
-  int32_t gemm_algo;      /* 0 | 2 tcgen05 (fp16 operand pairs), 1 fp32 CUDA cores */
+  int32_t gemm_algo;      /* 0 | 2 tcgen05, fp32-accurate (fp16 operand pairs, 3 products); 1 fp32 CUDA
+                             cores; 3 tcgen05 half-precision class (one fp16 product, fp32
+                             accumulate: BASELINE config C's "bf16" variant, error ~1e-3)       */
   int32_t attn_bwd_algo;  /* 0 auto (pipelined kernel when its shared-memory plan fits), 1 phase-serial
                              kernel, 2 pipelined or error                           */
   float   dropout_p;      /* attention dropout of this call: 0 = none (eval mode, or PyG's

@@ -274,16 +274,20 @@ struct LgDvArgs {
   uint32_t off_w, off_stage, stage_bytes;
 };
 
-// dv[h][k] = sum over edge rows r = (j -> i) of (dz[h][j][i] + fill[h][i]) * e_r[k].  Thread = feature k
-// (and k + 128, ...), all heads; per-chunk sums in fp32, the CTA's running total in fp64.
-template <int KPT>
-__global__ void __launch_bounds__(kLgThreads) lg_dv_kernel(const LgDvArgs a) {
+// dv[h][k] = sum over edge rows r = (j -> i) of (dz[h][j][i] + fill[h][i]) * e_r[k].  Thread = (feature k [+128, ...],
+// row group rg): the RG row groups take alternate rows of a chunk, so a CTA carries 4*RG warps of independent
+// LDS -> FFMA2 chains (one group alone left the SM at 12 warps and 23 % issue utilisation - ncu).  Per-chunk sums
+// in fp32, each thread's running total in fp64; every (CTA, row group) writes its own partial.
+template <int KPT, int RG>
+__global__ void __launch_bounds__(kLgThreads * RG, RG >= 4 ? 2 : 3) lg_dv_kernel(const LgDvArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int NT = kLgThreads * RG;
+  constexpr int GIT = (64 * 8 + NT - 1) / NT;                    // (row, head) weights each thread gathers per chunk
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   float* wrow = reinterpret_cast<float*>(smem + a.off_w);       // [2][CR][8]
   float* stage[2] = {reinterpret_cast<float*>(smem + a.off_stage),
                      reinterpret_cast<float*>(smem + a.off_stage + a.stage_bytes)};
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, kt = tid & (kLgThreads - 1), rgp = tid / kLgThreads;
   const LgRing& rg = a.rg;
   const int Fe = rg.Fe, N = a.N, H = a.H;
   if (tid == 0) {
@@ -302,30 +306,33 @@ __global__ void __launch_bounds__(kLgThreads) lg_dv_kernel(const LgDvArgs a) {
   for (int kk = 0; kk < KPT; ++kk)
 #pragma unroll
     for (int h = 0; h < 8; ++h) tot[kk][h] = 0.0;
-  // Row weights w_r[h] = dz[h][j][i] + fill[h][i] of a chunk: one thread per row (CR <= 128), gathered through the row
-  // table one chunk AHEAD so the two dependent scattered loads hide behind the current chunk's wait and FMAs.
-  auto gather = [&](long long q, float (&w)[8]) {
-#pragma unroll
-    for (int h = 0; h < 8; ++h) w[h] = 0.f;
-    if (tid >= rg.rows_of(q)) return;
+  // Row weights w_r[h] = dz[h][j][i] + fill[h][i] of a chunk, one (row, head) per thread slot, gathered through the
+  // row table one chunk AHEAD so the two dependent scattered loads hide behind the current chunk's wait and FMAs.
+  auto gather = [&](long long q, float (&w)[GIT]) {
+    const int rows = rg.rows_of(q);
     const long long b = q / rg.cpg;
-    const int code = __ldg(a.table + (int)(q - b * rg.cpg) * rg.CR + tid);
-    if (code < 0) return;
-    const int i = code >> 16, j = code & 0xffff;
-    const float* dzb = a.dZ + (size_t)b * H * N * N + (size_t)j * N + i;
-    const float* fb = a.fill + (size_t)b * H * N + i;
+    const int row_base = (int)(q - b * rg.cpg) * rg.CR;
 #pragma unroll
-    for (int h = 0; h < 8; ++h)
-      if (h < H) w[h] = __ldg(dzb + (size_t)h * N * N) + __ldg(fb + (size_t)h * N);
-  };
-  auto put = [&](int buf, const float (&w)[8]) {
-    if (tid < rg.CR) {
-      float* dst = wrow + ((size_t)buf * rg.CR + tid) * 8;
-      *reinterpret_cast<float4*>(dst) = make_float4(w[0], w[1], w[2], w[3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(w[4], w[5], w[6], w[7]);
+    for (int g = 0; g < GIT; ++g) {
+      const int idx = tid + g * NT, r = idx >> 3, h = idx & 7;
+      w[g] = 0.f;
+      if (r < rows && h < H) {
+        const int code = __ldg(a.table + row_base + r);
+        if (code >= 0) {
+          const int i = code >> 16, j = code & 0xffff;
+          w[g] = __ldg(a.dZ + (((size_t)b * H + h) * N + j) * N + i) + __ldg(a.fill + ((size_t)b * H + h) * N + i);
+        }
+      }
     }
   };
-  float wnext[8];
+  auto put = [&](int buf, const float (&w)[GIT]) {
+#pragma unroll
+    for (int g = 0; g < GIT; ++g) {
+      const int idx = tid + g * NT;
+      if (idx < rg.CR * 8) wrow[(size_t)buf * rg.CR * 8 + idx] = w[g];
+    }
+  };
+  float wnext[GIT];
   if (q0 < rg.items) {
     gather(q0, wnext);
     put(0, wnext);
@@ -339,7 +346,8 @@ __global__ void __launch_bounds__(kLgThreads) lg_dv_kernel(const LgDvArgs a) {
     if (rg.bulk_ok) {
       mbar_wait(&full[s], (it >> 1) & 1);
     } else {
-      lg_copy(rg, q, stage[s], tid);
+      const float* src = rg.src_of(q);
+      for (int idx = tid; idx < rows * Fe; idx += NT) stage[s][idx] = src[idx];
     }
     __syncthreads();
     float2 acc[KPT][4];
@@ -350,14 +358,14 @@ __global__ void __launch_bounds__(kLgThreads) lg_dv_kernel(const LgDvArgs a) {
     const float* T = stage[s];
     const float* wr = wrow + (size_t)s * rg.CR * 8;
 #pragma unroll 4
-    for (int r = 0; r < rows; ++r) {
+    for (int r = rgp; r < rows; r += RG) {
       const float4 w0 = *reinterpret_cast<const float4*>(wr + r * 8);
       const float4 w1 = *reinterpret_cast<const float4*>(wr + r * 8 + 4);
       const float2 wp[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y),
                             make_float2(w1.z, w1.w)};
 #pragma unroll
       for (int kk = 0; kk < KPT; ++kk) {
-        const int k = tid + kk * kLgThreads;
+        const int k = kt + kk * kLgThreads;
         const float e = k < Fe ? T[r * Fe + k] : 0.f;
         const float2 ed = make_float2(e, e);
 #pragma unroll
@@ -375,10 +383,10 @@ __global__ void __launch_bounds__(kLgThreads) lg_dv_kernel(const LgDvArgs a) {
     __syncthreads();
     if (rg.bulk_ok && tid == 0 && q + 2 * step < rg.items) lg_issue(rg, q + 2 * step, stage[s], &full[s]);
   }
-  double* out = a.part + (size_t)blockIdx.x * H * Fe;
+  double* out = a.part + ((size_t)blockIdx.x * RG + rgp) * H * Fe;
 #pragma unroll
   for (int kk = 0; kk < KPT; ++kk) {
-    const int k = tid + kk * kLgThreads;
+    const int k = kt + kk * kLgThreads;
     if (k < Fe)
 #pragma unroll
       for (int h = 0; h < 8; ++h)
@@ -478,7 +486,7 @@ size_t attn_large_bwd_ws_bytes(const spotv2_gat_desc* d) {
   if (!attn_large_applies(d)) return 0;
   const size_t rows = (size_t)d->B * d->N;
   const size_t ldo = d->concat ? (size_t)d->H * d->C : (size_t)d->C;
-  const size_t dv_part = round_up((size_t)4 * sm_count() * d->H * (d->Fe > 0 ? d->Fe : 1) * sizeof(double), 256);
+  const size_t dv_part = round_up((size_t)16 * sm_count() * d->H * (d->Fe > 0 ? d->Fe : 1) * sizeof(double), 256);
   const size_t db_part = round_up(((rows + kColsumRows - 1) / kColsumRows) * ldo * sizeof(float), 256);
   // Zraw | A | dA | gii | fill | dv partials | dbias partials | fp32 dP_aug scratch (fp16-pair output only)
   return 3 * tile_bytes(d) + 2 * vec_bytes(d) + dv_part + db_part + round_up(rows * d->ldp * sizeof(float), 256) + 256;
@@ -531,7 +539,7 @@ int attn_large_bwd(const spotv2_gat_desc* d, AttnBwdArgs& a, float* dv, float* d
   float* gii = reinterpret_cast<float*>(w);  w += vec_bytes(d);
   float* fill = reinterpret_cast<float*>(w); w += vec_bytes(d);
   double* dv_part = reinterpret_cast<double*>(w);
-  w += round_up((size_t)4 * sm_count() * p.H * (p.Fe > 0 ? p.Fe : 1) * sizeof(double), 256);
+  w += round_up((size_t)16 * sm_count() * p.H * (p.Fe > 0 ? p.Fe : 1) * sizeof(double), 256);
   float* db_part = reinterpret_cast<float*>(w);
   const int db_chunks = (int)((rows + kColsumRows - 1) / kColsumRows);
   w += round_up((size_t)db_chunks * p.ldo * sizeof(float), 256);
@@ -571,22 +579,28 @@ int attn_large_bwd(const spotv2_gat_desc* d, AttnBwdArgs& a, float* dv, float* d
     v.rg = lg_ring(p, pl);
     v.table = p.table; v.dZ = dA; v.fill = fill; v.part = dv_part; v.N = p.N; v.H = p.H;
     v.off_w = pl.off_w; v.off_stage = pl.off_stage; v.stage_bytes = pl.stage_bytes;
-    if ((size_t)2 * pl.CR * 8 * sizeof(float) > pl.off_stage - pl.off_w || pl.CR > kLgThreads)
+    if ((size_t)2 * pl.CR * 8 * sizeof(float) > pl.off_stage - pl.off_w || pl.CR > 64)
       return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd (large N): row-weight block does not fit its slot");
     const int kpt = (p.Fe + kLgThreads - 1) / kLgThreads;
-    auto launch = [&](auto kern) -> int {
+    int nparts = 0;
+    auto launch = [&](auto kern, int rgs) -> int {
       SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_dv));
-      kern<<<pl.grid, kLgThreads, pl.smem_dv, st>>>(v);
+      // one wave of resident CTAs (2 per SM with 4 row groups, else what shared memory allows, at most 3)
+      const long long per_sm = rgs >= 4 ? 2 : 3;
+      long long grid = (long long)sm_count() * per_sm;
+      if (grid > pl.grid) grid = pl.grid;
+      kern<<<(unsigned)grid, kLgThreads * rgs, pl.smem_dv, st>>>(v);
       SPOTV2_CUDA_OK(cudaGetLastError());
+      nparts = (int)grid * rgs;
       return SPOTV2_OK;
     };
     int rc;
-    if (kpt <= 1) rc = launch(lg_dv_kernel<1>);
-    else if (kpt <= 2) rc = launch(lg_dv_kernel<2>);
-    else rc = launch(lg_dv_kernel<4>);
+    if (kpt <= 1) rc = launch(lg_dv_kernel<1, 4>, 4);
+    else if (kpt <= 2) rc = launch(lg_dv_kernel<2, 2>, 2);
+    else rc = launch(lg_dv_kernel<4, 1>, 1);
     if (rc) return rc;
     const int len = p.H * p.Fe;
-    lg_reduce_f64_kernel<<<(len + 127) / 128, 128, 0, st>>>(dv_part, pl.grid, len, dv);
+    lg_reduce_f64_kernel<<<(len + 127) / 128, 128, 0, st>>>(dv_part, nparts, len, dv);
     SPOTV2_CUDA_OK(cudaGetLastError());
   }
   {   // dP_h[j][c] = g sum_i alpha_h[j][i] dO[i,(h)c]

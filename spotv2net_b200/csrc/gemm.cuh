@@ -65,7 +65,8 @@ int split_f16(const float* src, int rows, int cols, size_t ld, int split_dim, in
               int pre_split, void* hi, void* lo, size_t ld16, float* blk, cudaStream_t st);
 int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, const F16Operand& B, float* C, int ldc,
                int splits, int bn, int kb_per_chunk, void* ws, size_t ws_bytes, cudaStream_t st,
-               float* amax_out = nullptr, int amax_cols = 0);   // amax_out[0] <- bits of max |C[:, :amax_cols]|
+               float* amax_out = nullptr, int amax_cols = 0,    // amax_out[0] <- bits of max |C[:, :amax_cols]|
+               bool single = false);   // true: one fp16 product (A_hi * B_hi) - the half-precision class of gemm_algo 3
 // blk[0] <- bits of max |src[r, c]| over a [rows, cols] matrix with row pitch ld (blk is zeroed first)
 int amax_2d(const float* src, int rows, int cols, size_t ld, float* blk, cudaStream_t st);
 

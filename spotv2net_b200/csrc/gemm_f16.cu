@@ -47,6 +47,7 @@ struct HParams {
   int scale_in_kernel;  // 0 when a split-K reduce applies the scales
   unsigned* amax_out;   // optional: bit pattern of max |C[m, n]| over n < amax_cols (splits == 1 only)
   int amax_cols;
+  int single;           // 1: half-precision class (gemm_algo 3): only the A_hi * B_hi product, lo tiles not even loaded
 };
 
 template <int BN, int TBK, bool A_KM, bool B_KM>
@@ -112,27 +113,28 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* st = smem + stage * S::kStage;
-          mbar_expect_tx(&full[stage], S::kTxBytes);
+          const bool lo = !p.single;
+          mbar_expect_tx(&full[stage], lo ? S::kTxBytes : S::kTxBytes / 2);
           const int k = kb * TBK;
           if (A_KM) {
             tma_load_2d(st, &tmAh, k, mt * HBM_, &full[stage]);
-            tma_load_2d(st + S::kAOp, &tmAl, k, mt * HBM_, &full[stage]);
+            if (lo) tma_load_2d(st + S::kAOp, &tmAl, k, mt * HBM_, &full[stage]);
           } else {
 #pragma unroll
             for (int blk = 0; blk < HBM_ / 64; ++blk) {
               tma_load_2d(st + blk * (TBK * 128), &tmAh, mt * HBM_ + blk * 64, k, &full[stage]);
-              tma_load_2d(st + S::kAOp + blk * (TBK * 128), &tmAl, mt * HBM_ + blk * 64, k, &full[stage]);
+              if (lo) tma_load_2d(st + S::kAOp + blk * (TBK * 128), &tmAl, mt * HBM_ + blk * 64, k, &full[stage]);
             }
           }
           unsigned char* sb = st + 2 * S::kAOp;
           if (B_KM) {
             tma_load_2d(sb, &tmBh, k, nt * BN, &full[stage]);
-            tma_load_2d(sb + S::kBOp, &tmBl, k, nt * BN, &full[stage]);
+            if (lo) tma_load_2d(sb + S::kBOp, &tmBl, k, nt * BN, &full[stage]);
           } else {
 #pragma unroll
             for (int blk = 0; blk < BN / 64; ++blk) {
               tma_load_2d(sb + blk * (TBK * 128), &tmBh, nt * BN + blk * 64, k, &full[stage]);
-              tma_load_2d(sb + S::kBOp + blk * (TBK * 128), &tmBl, nt * BN + blk * 64, k, &full[stage]);
+              if (lo) tma_load_2d(sb + S::kBOp + blk * (TBK * 128), &tmBl, nt * BN + blk * 64, k, &full[stage]);
             }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -177,10 +179,13 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
               const uint64_t al = make_desc(sa + S::kAOp + ks * a_kstep, a_lbo, a_sbo, a_lt);
               const uint64_t bh = make_desc(sb + ks * b_kstep, b_lbo, b_sbo, b_lt);
               const uint64_t bl = make_desc(sb + S::kBOp + ks * b_kstep, b_lbo, b_sbo, b_lt);
-              umma_f16(d_tmem, al, bh, idesc, accum);
+              if (!p.single) {
+                umma_f16(d_tmem, al, bh, idesc, accum);
+                umma_f16(d_tmem, ah, bl, idesc, 1);
+                accum = 1;
+              }
+              umma_f16(d_tmem, ah, bh, idesc, accum);
               accum = 1;
-              umma_f16(d_tmem, ah, bl, idesc, 1);
-              umma_f16(d_tmem, ah, bh, idesc, 1);
             }
             umma_commit(&empty[stage]);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -475,7 +480,7 @@ int split_f16(const float* src, int rows, int cols, size_t ld, int split_dim, in
 // C[M,N] = A . B^T with operands pre-split into scaled fp16 pairs.  bn: 256 -> TBK 64, 256 + 16 -> TBK 32.
 int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, const F16Operand& B, float* C, int ldc,
                int splits, int bn, int kb_per_chunk, void* ws, size_t ws_bytes, cudaStream_t st, float* amax_out,
-               int amax_cols) {
+               int amax_cols, bool single) {
   const int TBK = (bn & 16) ? 32 : 64;
   bn &= ~16;
   if (!tma_available()) return fail(SPOTV2_ERR_NO_DEVICE, "tensor-core GEMM: TMA descriptor encoding is not available");
@@ -496,6 +501,7 @@ int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, c
   p.scale_in_kernel = 1;
   p.amax_out = reinterpret_cast<unsigned*>(amax_out);
   p.amax_cols = amax_cols;
+  p.single = single ? 1 : 0;
   if (amax_out) {
     if (splits > 1) return fail(SPOTV2_ERR_INVALID_ARG, "gemm3x_f16: amax_out needs splits == 1");
     SPOTV2_CUDA_OK(cudaMemsetAsync(amax_out, 0, sizeof(float), st));

@@ -25,6 +25,9 @@ ProjShape shape_of(const spotv2_gat_desc* d) {
 }
 
 bool use_tc(const spotv2_gat_desc* d) { return d->gemm_algo != 1; }
+// gemm_algo 3: half-precision class (BASELINE config C's "bf16" variant): the same tcgen05 kernel issues only the
+// A_hi * B_hi product of the scaled fp16 operands (11-bit significands, fp32 accumulate): a third of the tensor work.
+bool single_product(const spotv2_gat_desc* d) { return d->gemm_algo == 3; }
 
 struct Carver {
   unsigned char* p;
@@ -110,7 +113,8 @@ extern "C" int spotv2_proj_fwd(const spotv2_gat_desc* d, const float* x, const v
   float* wblk = blk + kScaleBlockFloats;
   if (int rc = split_f16(W_aug, s.n_aug, s.F, s.F, 0, s.HC, nullptr, 0, wh, wl, s.ldf16, wblk, st)) return rc;
   F16Operand A{xh, xl, s.ldf16, xs + 2, kNone}, B{wh, wl, s.ldf16, wblk + 2, s.HC};
-  return gemm3x_f16(true, true, s.rows, s.n_aug, s.F, A, B, P_aug, s.ldp, 1, 256, 0, nullptr, 0, st, p_amax_or_null, s.HC);
+  return gemm3x_f16(true, true, s.rows, s.n_aug, s.F, A, B, P_aug, s.ldp, 1, 256, 0, nullptr, 0, st, p_amax_or_null, s.HC,
+                    single_product(d));
 }
 
 extern "C" int spotv2_proj_bwd_weight(const spotv2_gat_desc* d, const float* x, const void* x_hi, const void* x_lo,
@@ -145,7 +149,8 @@ extern "C" int spotv2_proj_bwd_weight(const spotv2_gat_desc* d, const float* x, 
   }
   // contraction over the B*N node rows: both operands are MN-major ([K, rows]) for this product
   F16Operand A{ph, pl, s.ldp16, ps + 2, s.HC}, B{xh, xl, s.ldf16, xs + 2, kNone};
-  return gemm3x_f16(false, false, s.n_aug, s.F, s.rows, A, B, dW_aug, s.F, splits, 256 + 16, 0, c.p, c.left, st);
+  return gemm3x_f16(false, false, s.n_aug, s.F, s.rows, A, B, dW_aug, s.F, splits, 256 + 16, 0, c.p, c.left, st, nullptr, 0,
+                    single_product(d));
 }
 
 extern "C" int spotv2_proj_bwd_input(const spotv2_gat_desc* d, const float* dP_aug, const void* dP_hi, const void* dP_lo,
@@ -179,5 +184,6 @@ extern "C" int spotv2_proj_bwd_input(const spotv2_gat_desc* d, const float* dP_a
   float* wblk = blk + kScaleBlockFloats;
   if (int rc = split_f16(W_aug, s.n_aug, s.F, s.F, 0, kNone, ps + 2, s.HC, wh, wl, s.ldf16, wblk, st)) return rc;
   F16Operand A{ph, pl, s.ldp16, nullptr, kNone}, B{wh, wl, s.ldf16, wblk + 2, kNone};
-  return gemm3x_f16(true, false, s.rows, s.F, s.n_aug, A, B, dX, s.F, 1, 256 + 16, 0, nullptr, 0, st);
+  return gemm3x_f16(true, false, s.rows, s.F, s.n_aug, A, B, dX, s.F, 1, 256 + 16, 0, nullptr, 0, st, nullptr, 0,
+                    single_product(d));
 }

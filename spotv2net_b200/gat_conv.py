@@ -111,11 +111,14 @@ GEMM_ALGO = 0
 ATTN_BWD_ALGO = 0
 
 
+PRECISIONS = {"fp32": None, "half": 3}      # "half": single fp16 tensor-core product in the projections (config C)
+
+
 def _desc(topo: Topology, F_in: int, Fe: int, H: int, Cc: int, concat: bool, slope: float,
-          dropout_p: float = 0.0, seed: int = 0) -> GatDesc:
+          dropout_p: float = 0.0, seed: int = 0, gemm_algo: Optional[int] = None) -> GatDesc:
     lib = _lib.load()
     return GatDesc(topo.B, topo.N, F_in, Fe, H, Cc, topo.R, int(concat), float(slope),
-                   lib.spotv2_gat_ldp(H, Cc), GEMM_ALGO, ATTN_BWD_ALGO,
+                   lib.spotv2_gat_ldp(H, Cc), GEMM_ALGO if gemm_algo is None else gemm_algo, ATTN_BWD_ALGO,
                    float(dropout_p), seed & 0xffffffff, (seed >> 32) & 0xffffffff)
 
 
@@ -137,13 +140,13 @@ class _GatLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, edge_attr, W, a_src, a_dst, W_e, a_edge, bias, topo, H, Cc, concat, slope, want_alpha,
-                dropout_p=0.0, seed=0):
+                dropout_p=0.0, seed=0, gemm_algo=None):
         lib = _lib.load()
         dev = x.device
         st = stream_ptr(dev)
         Fe = 0 if edge_attr is None or W_e is None else edge_attr.shape[1]
         # the descriptor (incl. this step's dropout key) is kept for the backward, which regenerates the same mask
-        desc = _desc(topo, x.shape[1], Fe, H, Cc, concat, slope, dropout_p, seed)
+        desc = _desc(topo, x.shape[1], Fe, H, Cc, concat, slope, dropout_p, seed, gemm_algo)
         n, HC = x.shape[0], H * Cc
         x = x.contiguous()
         ea = edge_attr.contiguous() if Fe else None
@@ -234,7 +237,7 @@ class _GatLayerFn(torch.autograd.Function):
                                     ptr(da_dst), ptr(dW_e), ptr(da_edge), st), "spotv2_gat_unfold")
         if not Fe and W_e is not None:          # layer has lin_edge but was called with edge_attr=None
             dW_e, da_edge = torch.zeros_like(W_e), torch.zeros_like(a_edge)
-        return (dx, None, dW, da_src, da_dst, dW_e, da_edge, dbias, None, None, None, None, None, None, None, None)
+        return (dx, None, dW, da_src, da_dst, dW_e, da_edge, dbias) + (None,) * 9
 
 
 # --------------------------------------------------------------------------- module
@@ -295,6 +298,10 @@ class GATConv(nn.Module):
         else:
             self.register_parameter("bias", None)
         self.nodes_per_graph: Optional[int] = None     # optional hint; inferred from edge_index otherwise
+        # "fp32" (default): every product fp32-accurate (1e-5 parity).  "half": the projection GEMMs issue one fp16
+        # tensor-core product with fp32 accumulation (BASELINE config C's reduced-precision variant, ~1e-3);
+        # the attention kernels stay fp32-accurate either way.  Not a PyG ctor argument: set the attribute.
+        self.precision = "fp32"
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -343,7 +350,8 @@ class GATConv(nn.Module):
         out, alpha_tile = _GatLayerFn.apply(
             x, edge_attr if use_edge else None, self.lin_src.weight, self.att_src, self.att_dst,
             self.lin_edge.weight if self.lin_edge is not None else None, self.att_edge, self.bias,
-            topo, self.heads, self.out_channels, self.concat, self.negative_slope, want_alpha, drop_p, seed)
+            topo, self.heads, self.out_channels, self.concat, self.negative_slope, want_alpha, drop_p, seed,
+            PRECISIONS[self.precision])
         if not want_alpha:
             return out
         return out, self._attention_weights(alpha_tile, topo, edge_index)

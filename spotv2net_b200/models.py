@@ -58,6 +58,12 @@ class GATModel(nn.Module):
             print('Choose an available activation function')
             sys.exit()
 
+    def set_precision(self, precision: str):
+        """"fp32" (default, 1e-5 parity) or "half" (one fp16 tensor-core product in every layer's projections)."""
+        for layer in self.gat_layers:
+            layer.precision = precision
+        return self
+
     def forward(self, data):
         x, edge_index, edge_attr = data.x, data.edge_index, data.edge_attr
         if self.standardize:
