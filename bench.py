@@ -199,12 +199,14 @@ class HotPath:
         sizes = [HC * Fin, HC, HC, HC * Fe, HC, Cc]
         self.arena = torch.empty(sum(sizes), **f32)
         self.g_W, self.g_as, self.g_ad, self.g_We, self.g_ae, self.g_b = torch.split(self.arena, sizes)
-        # counted from the ncu launch list (profiles/r1m_launch_list_summary.txt): fold 1; amax x5 (x, W_aug x2, dout, ds|dd);
-        # split x3 (x, W_aug, ds|dd); GEMM fwd; attn fwd; attn bwd + 2 partial reduces; GEMM bwd + split-K reduce; unfold
-        self.kernels_per_step = 17 if self.tc else 10
-        if N > 32:   # large-universe path: attn fwd 3 (logits, softmax, GEMM); attn bwd 10 (+ amax/split of dP on the tensor-core
-            # path); fold, amax/split of x and W_aug (5), two projection GEMMs + split-K reduce, unfold
-            self.kernels_per_step = 27 if self.tc else 18
+        # counted from the ncu launch list (profiles/r1t_launch_list_summary.txt): fold x2 (W_aug rows, v); amax x5 (x, W_aug x2,
+        # dout, ds|dd); split x3 (x, W_aug, ds|dd); GEMM fwd; attn fwd; attn bwd + 2 partial reduces; GEMM bwd + split-K
+        # reduce; unfold
+        self.kernels_per_step = 18 if self.tc else 11
+        if N > 32:   # large-universe path (profiles/r1t_config_D_launch_list_summary.txt): attn fwd 3 (logits, softmax, GEMM);
+            # attn bwd 11 (+ amax/split of dP on the tensor-core path); fold x2, amax/split of x and W_aug, two projection
+            # GEMMs + split-K reduce, unfold
+            self.kernels_per_step = 26 if self.tc else 19
         self.ev = {}
 
     def step(self, timed_events=None, allreduce=None):

@@ -394,12 +394,15 @@ __global__ void __launch_bounds__(kLgThreads * RG, RG >= 4 ? 2 : 3) lg_dv_kernel
   }
 }
 
+// out[k] = sum_c part[c][k], fixed order; a warp per output element strides over the partials (lane l takes c = l,
+// l + 32, ...) and combines its 32 lane sums by a butterfly.
 __global__ void lg_reduce_f64_kernel(const double* __restrict__ part, int nparts, int len, float* __restrict__ out) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (k >= len) return;
   double s = 0.0;
-  for (int c = 0; c < nparts; ++c) s += part[(size_t)c * len + k];
-  out[k] = (float)s;
+  for (int c = lane; c < nparts; c += 32) s += part[(size_t)c * len + k];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[k] = (float)s;
 }
 
 // dbias partials: part[chunk][c] = sum of dout[r][c] over the chunk's rows.
@@ -600,7 +603,7 @@ int attn_large_bwd(const spotv2_gat_desc* d, AttnBwdArgs& a, float* dv, float* d
     else rc = launch(lg_dv_kernel<4, 1>, 1);
     if (rc) return rc;
     const int len = p.H * p.Fe;
-    lg_reduce_f64_kernel<<<(len + 127) / 128, 128, 0, st>>>(dv_part, nparts, len, dv);
+    lg_reduce_f64_kernel<<<(len * 32 + 255) / 256, 256, 0, st>>>(dv_part, nparts, len, dv);
     SPOTV2_CUDA_OK(cudaGetLastError());
   }
   {   // dP_h[j][c] = g sum_i alpha_h[j][i] dO[i,(h)c]

@@ -13,8 +13,8 @@ unit = rows[0][13]
 scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0}.get(unit, 1e-6)
 short = lambda n: n.split("(")[0].replace("void ", "").replace("spotv2::", "").replace("<unnamed>::", "")[:70]
 # last step = launches after the last launch of the first kernel name of a step (fold_kernel)
-idx = [i for i, n in enumerate(names) if "fold_kernel" in n]
-first = idx[-2] if len(idx) >= 2 else 0          # fold launches twice per step (W_aug halves and v)
+idx = [i for i, n in enumerate(names) if "fold_kernel<8>" in n or "fold_kernel<(int)8>" in n]
+first = idx[-1] if idx else 0                    # a step starts with fold_kernel<8> (W_aug rows), then fold_kernel<32> (v)
 step = list(zip(names[first:], times[first:]))
 agg = collections.OrderedDict()
 for n, t in step:
