@@ -12,7 +12,7 @@ contents are replaced by symmetric N(0,1) matrices of the same shape
 from __future__ import annotations
 
 from types import SimpleNamespace
-from typing import Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import torch
@@ -39,9 +39,11 @@ def complete_graph_edge_index(N: int) -> torch.Tensor:
     return torch.cat([upper, lower], dim=1)
 
 
-def window_sample(M_vol: np.ndarray, M_vv: np.ndarray, t0: int, L: int):
+def window_sample(M_vol: np.ndarray, M_vv: np.ndarray, t0: int, L: int, future_steps: Optional[int] = None):
     """One Data(x, edge_index, edge_attr, y_x) exactly as utils/dataset.py:200-282
-    builds it (per-lag objects stacked on a new last dim, then flattened)."""
+    builds it (per-lag objects stacked on a new last dim, then flattened).
+    future_steps = K: the multi-output variant (CovarianceLaggedMultiOutputDataset, utils/dataset.py:332-405):
+    y_x [N*K], y_x[i*K + k] = diag(vol[t0 + L + k])[i] (the last lag's [N, K] target block, flattened)."""
     N = M_vol.shape[1]
     xs, eas = [], []
     edge_index = complete_graph_edge_index(N)
@@ -57,7 +59,11 @@ def window_sample(M_vol: np.ndarray, M_vv: np.ndarray, t0: int, L: int):
         cov_e = torch.cat([cov_e, cov_e])
         eas.append(torch.stack([cov_e, variances[edge_index[0]], variances[edge_index[1]]], dim=1))
         xs.append(torch.tensor(cov, dtype=torch.float))
-        y = torch.tensor(np.diag(M_vol[t0 + j + 1]), dtype=torch.float)
+        if future_steps is None:
+            y = torch.tensor(np.diag(M_vol[t0 + j + 1]), dtype=torch.float)
+        else:                                                       # utils/dataset.py:380-386
+            y = torch.stack([torch.tensor(np.diag(M_vol[t0 + j + k + 1]), dtype=torch.float)
+                             for k in range(future_steps)], dim=1).reshape(-1)
     x = torch.stack(xs, dim=2).reshape(N, -1)
     edge_attr = torch.stack(eas, dim=2).reshape(edge_index.shape[1], -1)
     return SimpleNamespace(x=x, edge_index=edge_index, edge_attr=edge_attr, y_x=y)
@@ -93,8 +99,8 @@ def collate(samples: Sequence[SimpleNamespace]) -> Batch:
                  num_graphs=len(samples))
 
 
-def make_batch(M_vol, M_vv, t0s: Sequence[int], L: int) -> Batch:
-    return collate([window_sample(M_vol, M_vv, int(t), L) for t in t0s])
+def make_batch(M_vol, M_vv, t0s: Sequence[int], L: int, future_steps: Optional[int] = None) -> Batch:
+    return collate([window_sample(M_vol, M_vv, int(t), L, future_steps) for t in t0s])
 
 
 def random_complete_batch(B: int, N: int, F_in: int, Fe: int, seed: int = 0, dtype=torch.float32) -> Batch:

@@ -94,9 +94,14 @@ class WindowDataset:
     Sample ``k`` is the window starting at ``t0 = k + drop_first``: ``x[i, c*L + t] = vol[t0+t, i, c]``,
     ``edge_attr[e, k*L + t]`` = (volvol[t0+t, r, c], volvol[.., src, src], volvol[.., dst, dst]),
     ``y_x[i] = vol[t0+L, i, i]``.
+
+    ``future_steps=K`` gives ``CovarianceLaggedMultiOutputDataset`` (utils/dataset.py:293-412; chosen by
+    5_train_SpotV2Net.py:66-76 when ``output_node_channels > 1``): same x / edges, targets
+    ``y_x[i*K + k] = vol[t0+L+k, i, i]``, and ``K - 1`` fewer samples.
     """
 
-    def __init__(self, vol, volvol, seq_length: int, device="cuda", drop_first: int = REFERENCE_DROP_FIRST):
+    def __init__(self, vol, volvol, seq_length: int, device="cuda", drop_first: int = REFERENCE_DROP_FIRST,
+                 future_steps: Optional[int] = None):
         vol = torch.as_tensor(np.asarray(vol) if not torch.is_tensor(vol) else vol)
         volvol = torch.as_tensor(np.asarray(volvol) if not torch.is_tensor(volvol) else volvol)
         if vol.shape != volvol.shape or vol.dim() != 3 or vol.shape[1] != vol.shape[2]:
@@ -104,7 +109,11 @@ class WindowDataset:
         self.T, self.N = int(vol.shape[0]), int(vol.shape[1])
         self.L = int(seq_length)
         self.drop_first = int(drop_first)
-        if self.T - self.L - self.drop_first <= 0:
+        self.future_steps = None if future_steps is None else int(future_steps)
+        if self.future_steps is not None and self.future_steps < 1:
+            raise SpotV2Error("future_steps must be >= 1")
+        self._tail = self.L + (self.future_steps - 1 if self.future_steps else 0)
+        if self.T - self._tail - self.drop_first <= 0:
             raise SpotV2Error(f"T={self.T} too short for seq_length={self.L} and drop_first={self.drop_first}")
         self.device = torch.device(device)
         self.vol = vol.to(self.device, torch.float32).contiguous()          # numpy float64 -> fp32, as torch.tensor(.., dtype=float)
@@ -113,7 +122,7 @@ class WindowDataset:
         self.num_edge_features = 3 * self.L
 
     def __len__(self) -> int:
-        return self.T - self.L - self.drop_first
+        return self.T - self._tail - self.drop_first
 
     def collate(self, indices: Sequence[int] | Tensor) -> SpotBatch:
         idx = torch.as_tensor(indices, dtype=torch.int64)
@@ -130,6 +139,10 @@ class WindowDataset:
         lib = _lib.load()
         check(lib.spotv2_collate_windows(ptr(self.vol), ptr(self.volvol), self.T, N, L, ptr(t0), B, ptr(x), ptr(ea),
                                          ptr(y), stream_ptr(dev)), "spotv2_collate_windows")
+        if self.future_steps is not None:        # [B, K, N] gather of the next K diagonals -> [B*N*K], node major
+            K = self.future_steps
+            t = (t0.to(torch.int64) + L).view(B, 1) + torch.arange(K, device=dev).view(1, K)
+            y = self.vol.diagonal(dim1=1, dim2=2)[t].permute(0, 2, 1).reshape(-1).contiguous()
         ei, topo = batched_topology(B, N, dev)
         return SpotBatch(x, ei, ea, y, B, N, topo)
 

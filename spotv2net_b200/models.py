@@ -39,6 +39,10 @@ class GATModel(nn.Module):
         super().__init__()
         self.dropout = dropout
         self.activation = activation
+        # 6_results.ipynb's analysis variant of this class calls every layer with return_attention_weights=True and keeps
+        # the result in self.attention_weights; set collect_attention = True for the same behaviour
+        self.collect_attention = False
+        self.attention_weights = []
         self.standardize = standardize
         if self.standardize:
             self.bnorm_node = nn.BatchNorm1d(num_node_features, affine=False)
@@ -74,8 +78,14 @@ class GATModel(nn.Module):
         topo = getattr(data, "spot_topology", None)
         if topo is None:
             topo = topology_from_edge_index(edge_index, x.shape[0], getattr(data, "nodes_per_graph", None))
+        if self.collect_attention:
+            self.attention_weights = []
         for layer in self.gat_layers:
-            x = layer(x, edge_index, edge_attr, topology=topo)
+            if self.collect_attention:
+                x, att = layer(x, edge_index, edge_attr, return_attention_weights=True, topology=topo)
+                self.attention_weights.append(att)
+            else:
+                x = layer(x, edge_index, edge_attr, topology=topo)
             x = self.a(x)
             if self.dropout:
                 x = F.dropout(x, p=self.dropout, training=self.training)

@@ -92,6 +92,8 @@ def train(seed: Optional[int] = None, trial=None, p: Optional[dict] = None, *, c
     if vol is None:
         vol, volvol = load_matrix_stack(p["volfile"]), load_matrix_stack(p["volvolfile"])
     kw = {} if drop_first is None else {"drop_first": drop_first}
+    if p["output_node_channels"] > 1:          # 5_train_SpotV2Net.py:66-76: the multi-output dataset, K = output channels
+        kw["future_steps"] = p["output_node_channels"]
     dataset = WindowDataset(vol, volvol, seq_length=p["seq_length"], device=device, **kw)
     train_size = int(p["split_proportion"] * len(dataset))
     train_set, test_set = dataset[:train_size], dataset[train_size:]

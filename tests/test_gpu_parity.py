@@ -665,6 +665,78 @@ def test_device_collation_matches_reference_layouts(cuda_lib):
     assert sizes == [8, 8, 4] and len(loader) == 3
 
 
+def test_multi_output_variant_collation_and_model_step(cuda_lib):
+    """output_node_channels = 14 (config/GNN_param.yaml:29 HPO space; 5_train_SpotV2Net.py:66-76 switches to
+    CovarianceLaggedMultiOutputDataset, utils/dataset.py:293-412): targets are the next K diagonals per node."""
+    N, L, T, K = 30, 4, 40, 14
+    vol, vv = synth.synthetic_matrices(T, N, seed=12)
+    ds = sv.WindowDataset(vol, vv, seq_length=L, device=DEV, drop_first=2, future_steps=K)
+    assert len(ds) == T - L - K + 1 - 2
+    idx = [0, 5, len(ds) - 1]
+    ours_bt = ds.collate(idx)
+    ref_bt = synth.make_batch(vol, vv, [i + 2 for i in idx], L, future_steps=K)
+    assert ours_bt.y_x.shape == (len(idx) * N * K,)
+    assert torch.equal(ours_bt.y_x.cpu(), ref_bt.y_x) and torch.equal(ours_bt.x.cpu(), ref_bt.x)
+    assert torch.equal(ours_bt.edge_attr.cpu(), ref_bt.edge_attr)
+    kw = dict(num_node_features=N * L, num_edge_features=3 * L, num_heads=3, output_node_channels=K,
+              dim_hidden_layers=[20], concat_heads=False)
+    torch.manual_seed(1)
+    ref = pyg_gat.OracleGATModel(**kw).double()
+    ours = sv.GATModel(**kw)
+    ours.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    ours.to(DEV)
+    d64 = synth.Batch(x=ref_bt.x.double(), edge_index=ref_bt.edge_index, edge_attr=ref_bt.edge_attr.double())
+    loss_ref = torch.nn.functional.mse_loss(ref(d64), ref_bt.y_x.double())
+    loss_ref.backward()
+    loss = torch.nn.functional.mse_loss(ours(ours_bt), ours_bt.y_x)
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) <= 2e-5 * abs(loss_ref.item())
+    import copy
+    ref32 = copy.deepcopy(ref).float()
+    ref32.zero_grad()
+    torch.nn.functional.mse_loss(ref32(synth.Batch(x=ref_bt.x, edge_index=ref_bt.edge_index, edge_attr=ref_bt.edge_attr)),
+                                 ref_bt.y_x).backward()
+    bad = parity_failures({k: p.grad for k, p in ours.named_parameters()}, {k: p.grad for k, p in ref.named_parameters()},
+                          {k: p.grad for k, p in ref32.named_parameters()})
+    assert not bad, bad
+
+
+def test_evaluation_loop_and_attention_export_match_the_oracle_model(cuda_lib):
+    """6_results.ipynb: batched no-grad evaluation with de-standardised predictions, and the per-layer attention
+    coefficients of the notebook's GATModel variant."""
+    N, L, T = 30, 3, 30
+    vol, vv = synth.synthetic_matrices(T, N, seed=44)
+    kw = dict(num_node_features=N * L, num_edge_features=3 * L, num_heads=4, output_node_channels=1,
+              dim_hidden_layers=[12, 8], concat_heads=True)
+    torch.manual_seed(3)
+    ref = pyg_gat.OracleGATModel(**kw).double().eval()
+    ours = sv.GATModel(**kw)
+    ours.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    ours.to(DEV)
+    ds = sv.WindowDataset(vol, vv, seq_length=L, device=DEV, drop_first=1)
+    mean, std = 0.37, 2.5
+    res = sv.evaluate(ours, sv.WindowLoader(ds, batch_size=8, shuffle=False), mean=mean, std=std)
+    assert ours.training                                   # mode restored
+    preds, actual, losses = [], [], []
+    with torch.no_grad():
+        for s0 in range(0, len(ds), 8):
+            bt = synth.make_batch(vol, vv, [i + 1 for i in range(s0, min(s0 + 8, len(ds)))], L)
+            d64 = synth.Batch(x=bt.x.double(), edge_index=bt.edge_index, edge_attr=bt.edge_attr.double())
+            yh, y = ref(d64) * std + mean, bt.y_x.double() * std + mean
+            preds.append(yh); actual.append(y); losses.append(torch.nn.functional.mse_loss(yh, y).item())
+    assert relerr(res["preds"], torch.cat(preds)) < TOL and relerr(res["actual"], torch.cat(actual)) < 1e-6
+    assert abs(res["mse"] - sum(losses) / len(losses)) <= 2e-5 * abs(sum(losses) / len(losses))
+    assert res["preds"].view(-1, N).shape[0] == len(ds)
+    # attention export, layer by layer
+    bt = synth.make_batch(vol, vv, [1, 2, 3], L)
+    att = sv.attention_weights(ours, ds.collate([0, 1, 2]))
+    x = bt.x.double()
+    for layer, (ei2, alpha) in zip(ref.gat_layers, att):
+        x, (ei_ref, a_ref) = layer(x, bt.edge_index, bt.edge_attr.double(), return_attention_weights=True)
+        assert torch.equal(ei2.cpu(), ei_ref) and relerr(alpha, a_ref) < TOL
+        x = torch.relu(x)
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_full_batch_properties(cuda_lib):
     """B = 4096 at the default geometry (BASELINE config 2).  The oracle cannot run this size, so:

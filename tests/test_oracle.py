@@ -170,3 +170,20 @@ def test_golden_fixtures(path):
         ref = z["g_" + k]
         assert np.abs(p.grad.numpy() - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()), k
     assert len(GOLDEN) >= 5
+
+
+def test_multi_output_window_targets_follow_the_reference_layout():
+    """CovarianceLaggedMultiOutputDataset (utils/dataset.py:380-405): y_x is the last lag's [N, K] block of the next K
+    diagonals, flattened node-major; x and edge_attr are those of the single-output dataset."""
+    import numpy as np
+    from oracle import synth
+    N, L, K = 5, 3, 4
+    vol, vv = synth.synthetic_matrices(L + K + 3, N, seed=9)
+    vol, vv = np.asarray(vol), np.asarray(vv)
+    t0 = 2
+    s1, sK = synth.window_sample(vol, vv, t0, L), synth.window_sample(vol, vv, t0, L, future_steps=K)
+    assert torch.equal(s1.x, sK.x) and torch.equal(s1.edge_attr, sK.edge_attr) and torch.equal(s1.edge_index, sK.edge_index)
+    y = sK.y_x.view(N, K)
+    for k in range(K):
+        assert torch.equal(y[:, k], torch.tensor(np.diag(vol[t0 + L + k]), dtype=torch.float))
+    assert torch.equal(y[:, 0], s1.y_x)
