@@ -182,6 +182,9 @@ class HotPath:
         self.v = torch.empty(H, Fe, **f32)
         self.P_aug = torch.empty(n, self.desc.ldp, **f32)
         self.p_amax = torch.empty(8, **f32)
+        et = C.c_size_t()
+        _lib.check(self.lib.spotv2_gat_edge_terms_bytes(C.byref(self.desc), C.byref(et)), "edge_terms_bytes")
+        self.edge_terms = torch.empty(et.value // 4, **f32)       # <e_ij, v_h>: written by attn_fwd, read by attn_bwd
         self.out = torch.empty(n, Cc, **f32)
         self.dout = torch.randn(n, Cc, generator=g, **f32)
         self.tc = bool(self.lib.spotv2_gat_uses_tensor_cores(C.byref(self.desc)))
@@ -232,9 +235,10 @@ class HotPath:
                                 p(self.ws), self.ws.numel(), st), "proj_fwd")
         mark("proj_fwd")
         chk(lib.spotv2_gat_attn_fwd(d, p(self.P_aug), p(self.batch.edge_attr), p(self.batch.spot_topology.table),
-                                    p(self.v), p(L.bias), p(self.out), None, p(self.ws), self.ws.numel(), st), "attn_fwd")
+                                    p(self.v), p(L.bias), p(self.out), None, p(self.edge_terms), p(self.ws), self.ws.numel(), st), "attn_fwd")
         mark("attn_fwd")
-        chk(lib.spotv2_gat_attn_bwd(d, p(self.P_aug), p(self.p_amax), p(self.batch.edge_attr), p(self.batch.spot_topology.table),
+        chk(lib.spotv2_gat_attn_bwd(d, p(self.P_aug), p(self.p_amax), p(self.batch.edge_attr), p(self.edge_terms),
+                                    p(self.batch.spot_topology.table),
                                     p(self.v), p(self.dout), p(self.dP_aug), p(ph), p(pl), p(self.dp_blk), p(self.dv),
                                     p(self.g_b), p(self.ws), self.ws.numel(), st), "attn_bwd")
         mark("attn_bwd")

@@ -101,6 +101,11 @@ int spotv2_gat_workspace_bytes(const spotv2_gat_desc* d, size_t* proj_fwd, size_
 /* Scratch of spotv2_gat_attn_fwd: 0 for N <= 32; the [B, H, N, N] fp32 attention tile for larger graphs
  * (not needed when the caller passes alpha_or_null, which then doubles as the tile). */
 int spotv2_gat_attn_fwd_workspace_bytes(const spotv2_gat_desc* d, size_t* attn_fwd);
+/* Size of the optional edge-term buffer g[b][h][j][i] = <e_ij, v_h> (6 floats per edge instead of Fe): when the
+ * caller hands one to spotv2_gat_attn_fwd, the forward fills it, and spotv2_gat_attn_bwd given the same buffer skips
+ * its first pass over the edge rows (it still recomputes the softmax; the rows are read once, for dv).  0 when the
+ * layer has no edge features.  Layout is the kernels' own ([H][N][36] floats per graph for N <= 32, [H][N][N] above). */
+int spotv2_gat_edge_terms_bytes(const spotv2_gat_desc* d, size_t* bytes);
 
 /* Replaces the per-call topology work PyG does on edge_index
  * (remove_self_loops / add_self_loops / index_select by edge_index[0|1];
@@ -154,16 +159,18 @@ int spotv2_proj_fwd(const spotv2_gat_desc* d, const float* x, const void* x_hi, 
  * tile [B, H, N(source j), N(target i)] (for return_attention_weights). */
 int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug, const float* edge_rows,
                         const int32_t* table, const float* v, const float* bias_or_null,
-                        float* out, float* alpha_or_null, void* ws, size_t ws_bytes, void* stream);
+                        float* out, float* alpha_or_null, float* edge_terms_or_null, void* ws, size_t ws_bytes,
+                        void* stream);
 
-/* autograd of the above with the attention coefficients recomputed, not stored.
+/* autograd of the above with the attention coefficients recomputed, not stored (edge_terms_or_null: what the
+ * forward wrote, see spotv2_gat_edge_terms_bytes; null = recompute the edge terms from edge_rows as well).
  * dout [B*N, C or HC] -> dP_aug (dP | ds | dd), dv [H, Fe], dbias.  The gradient is emitted either as
  * fp32 dP_aug [B*N, ldp] (CUDA-core GEMM path) or, when dP_hi/dP_lo/dp_scale are given, directly as the
  * fp16 pair [B*N, ld16(HC+2H)] the tensor-core GEMMs consume (two scale groups: columns < HC from a
  * bound on max|dout|, the ds|dd columns from their own maximum); dp_scale is an 8-float scale block.
  * p_amax_or_null: what spotv2_proj_fwd wrote (saves one pass over P_aug). */
 int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug, const float* p_amax_or_null,
-                        const float* edge_rows,
+                        const float* edge_rows, const float* edge_terms_or_null,
                         const int32_t* table, const float* v, const float* dout, float* dP_aug_or_null,
                         void* dP_hi_or_null, void* dP_lo_or_null, float* dp_scale_or_null,
                         float* dv_or_null, float* dbias_or_null, void* ws, size_t ws_bytes, void* stream);

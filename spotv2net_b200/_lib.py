@@ -43,8 +43,9 @@ SIGNATURES = {
     "spotv2_split_f16": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "spotv2_proj_fwd": (C.c_int, [_DP] + [_vp] * 8 + [_sz, _vp]),
     "spotv2_gat_attn_fwd_workspace_bytes": (C.c_int, [_DP, C.POINTER(_sz)]),
-    "spotv2_gat_attn_fwd": (C.c_int, [_DP] + [_vp] * 8 + [_sz, _vp]),
-    "spotv2_gat_attn_bwd": (C.c_int, [_DP] + [_vp] * 13 + [_sz, _vp]),
+    "spotv2_gat_edge_terms_bytes": (C.c_int, [_DP, C.POINTER(_sz)]),
+    "spotv2_gat_attn_fwd": (C.c_int, [_DP] + [_vp] * 9 + [_sz, _vp]),
+    "spotv2_gat_attn_bwd": (C.c_int, [_DP] + [_vp] * 14 + [_sz, _vp]),
     "spotv2_proj_bwd_weight": (C.c_int, [_DP] + [_vp] * 10 + [_sz, _vp]),
     "spotv2_proj_bwd_input": (C.c_int, [_DP] + [_vp] * 7 + [_sz, _vp]),
     "spotv2_gat_unfold": (C.c_int, [_DP] + [_vp] * 13),

@@ -150,7 +150,9 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
   __syncthreads();
 
   int b = blockIdx.x;
-  if (p.bulk_ok && tid == 0 && b < p.B && ring.nchunks > 0) ring.prefetch_first(b);
+  // the forward kept the edge terms (p.edge_terms): B1 copies them instead of streaming the edge rows a first time
+  const bool use_terms = p.edge_terms != nullptr && ring.nchunks > 0;
+  if (p.bulk_ok && tid == 0 && b < p.B && ring.nchunks > 0 && !use_terms) ring.prefetch_first(b);
 
   const float g_scale = p.concat ? 1.f : 1.f / (float)H;
   float dp_scale = 1.f;
@@ -186,7 +188,14 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
       const int j = idx / (2 * H), k = idx - j * 2 * H;
       sd[idx] = p.P_aug[((size_t)b * N + j) * p.ldp + HC + k];
     }
-    if (ring.nchunks > 0) {
+    if (use_terms) {
+      const float* src = p.edge_terms + (size_t)b * H * N * kEdgeTermNS;
+      for (int idx = tid; idx < H * N * N; idx += kAttnThreads) {
+        const int hj = idx / N, i = idx - hj * N;
+        tile[hj * NS + i] = src[hj * kEdgeTermNS + i];
+      }
+      __syncthreads();
+    } else if (ring.nchunks > 0) {
       edge_logit_phase(ring, p, sm.a, tile, table_s, vfrag, b, tid);
     } else {
       for (int idx = tid; idx < H * N * NS; idx += kAttnThreads) tile[idx] = 0.f;
@@ -518,7 +527,7 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
       __syncthreads();
       if (p.bulk_ok && tid == 0 && c + 2 < ring.nchunks) ring.issue(b, c + 2);
     }
-    if (p.bulk_ok && tid == 0 && b + (int)gridDim.x < p.B && ring.nchunks > 0)
+    if (p.bulk_ok && tid == 0 && b + (int)gridDim.x < p.B && ring.nchunks > 0 && !use_terms)
       ring.prefetch_first(b + gridDim.x);
     lap(5);
   }
@@ -622,7 +631,8 @@ int bwd_diag_read(unsigned long long* host_out, int reset) {
 using namespace spotv2;
 
 extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug, const float* p_amax_or_null,
-                                   const float* edge_rows, const int32_t* table, const float* v,
+                                   const float* edge_rows, const float* edge_terms_or_null, const int32_t* table,
+                                   const float* v,
                                    const float* dout, float* dP_aug_or_null, void* dP_hi_or_null, void* dP_lo_or_null,
                                    float* dp_scale_or_null, float* dv_or_null, float* dbias_or_null, void* ws,
                                    size_t ws_bytes, void* stream) {
@@ -644,6 +654,8 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
   a.p.ldo = d->concat ? d->H * d->C : d->C;
   a.p.slope = d->negative_slope;
   a.p.drop = dropout_params(d);
+  SPOTV2_REQUIRE(!edge_terms_or_null || aligned16(edge_terms_or_null), "attn_bwd: edge_terms must be 16-byte aligned");
+  a.p.edge_terms = d->Fe > 0 ? const_cast<float*>(edge_terms_or_null) : nullptr;
   a.p.P_aug = P_aug; a.p.edge_rows = edge_rows; a.p.table = table; a.p.v = v;
   a.p.bulk_ok = d->Fe > 0 && aligned16(edge_rows) && ((size_t)d->R * d->Fe) % 4 == 0;
   a.p.vec2_ok = (d->C % 2 == 0);

@@ -265,6 +265,8 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
   __builtin_assume(__isShared(tile)); __builtin_assume(__isShared(D)); __builtin_assume(__isShared(slots));
 
   const int nchunks = pl.nchunks;
+  // the forward kept the edge terms: phase L becomes one 26 KB bulk copy instead of a pass over the edge rows
+  const bool use_terms = p.edge_terms != nullptr && nchunks > 0 && (uint32_t)tile_floats * 4u <= pl.slot_bytes;
   const int my_graphs = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int n_cb = pl.n_cb;
   auto rows_in = [&](int c) { const int r = p.R - c * pl.chunk_rows; return r < pl.chunk_rows ? r : pl.chunk_rows; };
@@ -337,7 +339,17 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
     const int n_grp_d = (n_cb + pl.cbs_per_grp_d - 1) / pl.cbs_per_grp_d;
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
-      for (int c = 0; c < nchunks; ++c) edge_chunk(b, c, kEvictLast);           // phase L (kept in L2 for phase V)
+      if (use_terms) {                                                          // phase L': the forward's edge terms, one slot
+        float* dst = reinterpret_cast<float*>(acquire());
+        if (lane == 0) {
+          const uint32_t bytes = (uint32_t)tile_floats * 4u;
+          mbar_expect_tx(&full[slot], bytes);
+          bulk_g2s_hint(dst, p.edge_terms + (size_t)b * tile_floats, bytes, &full[slot], kEvictFirst);
+        }
+        publish(true);
+      } else {
+        for (int c = 0; c < nchunks; ++c) edge_chunk(b, c, kEvictLast);         // phase L (kept in L2 for phase V)
+      }
       for (int r = 0; r < pl.n_rounds; ++r) {                                   // phase A: one group per channel block
         const int h0 = r * pl.hpr;
         const int nh = min(pl.hpr, H - h0);
@@ -473,7 +485,13 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
       sd[idx] = p.P_aug[((size_t)b * N + j) * p.ldp + HC + k];
     }
     for (int idx = tid; idx < 2 * H * 32; idx += kCT) ds_part[idx] = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
+    if (use_terms) {
+      const uint32_t sa = wait_slot();
+      for (int idx = tid; idx < tile_floats / 4; idx += kCT)
+        reinterpret_cast<float4*>(tile)[idx] = lds128_u32(sa + (uint32_t)idx * 16u);
+      release_slot();
+    }
+    for (int c = 0; c < (use_terms ? 0 : nchunks); ++c) {
       const uint32_t sa = wait_slot();
       const int rows = rows_in(c);
       if (l_on && (c & 1) == l_hg && l_mt * 16 < rows) {
@@ -542,7 +560,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
     bar_sync_compute();
     lap(0);
     // ------------------------------------------------ S: softmax ------------------------------------------------
-    softmax_phase(p, asm_, tile, sd, 1.f, nullptr, pos_mask, tid, kCT, -1, 0, (nchunks > 0 && pl.ksplit == 2) ? D : nullptr);
+    softmax_phase(p, asm_, tile, sd, 1.f, nullptr, pos_mask, tid, kCT, -1, 0, (nchunks > 0 && pl.ksplit == 2 && !use_terms) ? D : nullptr);
     bar_sync_compute();
     lap(1);
     // ------------------------------------------------ A: dalpha + softmax backward ------------------------------------------------

@@ -83,7 +83,13 @@ struct AttnParams {
   int bulk_ok;     // edge block 16-byte aligned and R*Fe % 4 == 0
   int vec2_ok;     // C even (8-byte aligned channel pairs)
   DropoutParams drop;
+  // Edge-term tile g[b][h][j][i] = <e_ij, v_h> in the kernels' shared-memory layout ([H][N][kEdgeTermNS] floats per
+  // graph for N <= 32, [H][N][N] for larger graphs).  The forward writes it when given; the backward reads it instead
+  // of streaming the edge rows a first time and recomputing the logits (6 floats per edge instead of Fe).  Null = off.
+  float* edge_terms;
 };
+
+constexpr int kEdgeTermNS = 36;     // == the alpha-tile row stride of attn_fwd.cu / attn_bwd2.cu
 
 // Shared-memory plan common to both directions.  All offsets in bytes, 16-aligned.
 struct AttnSmem {

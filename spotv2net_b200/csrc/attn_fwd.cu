@@ -237,6 +237,15 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm_, const uint32_t o
         t_bar += clock64() - tc1;
         if (p.bulk_ok && tid == 0 && k + 2 < total_chunks) issue(k + 2);
       }
+      if (p.edge_terms && NS == kEdgeTermNS) {
+        // keep the edge terms for the backward (it then reads 6 floats per edge instead of the Fe-wide rows).  All of
+        // group A's scatters are behind the chunk loop's last bar.sync; diagonal entries hold stale finite values
+        // that no consumer reads.
+        if (nchunks == 0) bar_sync_group_a();
+        float4* dst = reinterpret_cast<float4*>(p.edge_terms + (size_t)b * tile_floats);
+        const float4* src = reinterpret_cast<const float4*>(tile);
+        for (int idx = tid; idx < tile_floats / 4; idx += kGroupA) dst[idx] = src[idx];
+      }
       mbar_arrive_cta(&tile_full[buf]);                  // release: edge terms of this graph visible to group B
     }
     if (tid == 0) {
@@ -493,7 +502,7 @@ extern "C" int spotv2_diag_counters(unsigned long long* host_out, int reset) {
 extern "C" int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug,
                                    const float* edge_rows, const int32_t* table, const float* v,
                                    const float* bias_or_null, float* out, float* alpha_or_null,
-                                   void* ws, size_t ws_bytes, void* stream) {
+                                   float* edge_terms_or_null, void* ws, size_t ws_bytes, void* stream) {
   if (int rc = check_desc(d)) return rc;
   SPOTV2_REQUIRE(P_aug && out, "attn_fwd: P_aug and out must be non-null");
   SPOTV2_REQUIRE(d->Fe == 0 || (edge_rows && table && v),
@@ -510,6 +519,8 @@ extern "C" int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug,
   a.p.P_aug = P_aug; a.p.edge_rows = edge_rows; a.p.table = table; a.p.v = v;
   a.p.bulk_ok = d->Fe > 0 && aligned16(edge_rows) && ((size_t)d->R * d->Fe) % 4 == 0;
   a.p.vec2_ok = (d->C % 2 == 0);
+  SPOTV2_REQUIRE(!edge_terms_or_null || aligned16(edge_terms_or_null), "attn_fwd: edge_terms must be 16-byte aligned");
+  a.p.edge_terms = d->Fe > 0 ? edge_terms_or_null : nullptr;
   a.bias = bias_or_null; a.out = out; a.alpha_out = alpha_or_null;
   if (attn_large_applies(d))       // several CTAs per graph, attention tile in the workspace (or alpha_or_null)
     return attn_large_fwd(a.p, bias_or_null, out, alpha_or_null, ws, ws_bytes, as_stream(stream));

@@ -506,11 +506,12 @@ int attn_large_fwd(const AttnParams& p, const float* bias, float* out, float* al
     A = static_cast<float*>(ws);
   }
   const LgPlan pl = lg_plan(p);
+  float* Zraw = p.edge_terms ? p.edge_terms : A;       // kept for the backward when the caller provides the buffer
   if (p.Fe > 0) {
     if (pl.smem_logit > 227 * 1024) return fail(SPOTV2_ERR_UNSUPPORTED, "attn_fwd (large N): Fe=%d needs %zu B shared memory", p.Fe, pl.smem_logit);
-    if (int rc = lg_logits(p, pl, A, st)) return rc;
+    if (int rc = lg_logits(p, pl, Zraw, st)) return rc;
   }
-  if (int rc = lg_softmax(p, p.Fe > 0 ? A : nullptr, A, nullptr, true, st)) return rc;
+  if (int rc = lg_softmax(p, p.Fe > 0 ? Zraw : nullptr, A, nullptr, true, st)) return rc;
   const long long NN = (long long)p.N * p.N;
   BGemm g{};
   g.M = p.N; g.N = p.C; g.K = p.N;
@@ -551,7 +552,8 @@ int attn_large_bwd(const spotv2_gat_desc* d, AttnBwdArgs& a, float* dv, float* d
   const LgPlan pl = lg_plan(p);
   if (p.Fe > 0) {
     if (pl.smem_logit > 227 * 1024) return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd (large N): Fe=%d needs %zu B shared memory", p.Fe, pl.smem_logit);
-    if (int rc = lg_logits(p, pl, Zraw, st)) return rc;
+    if (p.edge_terms) Zraw = p.edge_terms;            // the forward kept them: no first pass over the edge rows
+    else if (int rc = lg_logits(p, pl, Zraw, st)) return rc;
   }
   const float* Zr = p.Fe > 0 ? Zraw : nullptr;
   if (int rc = lg_softmax(p, Zr, A, gii, false, st)) return rc;

@@ -71,6 +71,14 @@ extern "C" int spotv2_gat_attn_fwd_workspace_bytes(const spotv2_gat_desc* d, siz
   return SPOTV2_OK;
 }
 
+extern "C" int spotv2_gat_edge_terms_bytes(const spotv2_gat_desc* d, size_t* bytes) {
+  if (int rc = check_desc(d)) return rc;
+  SPOTV2_REQUIRE(bytes, "edge_terms_bytes: null pointer");
+  const size_t per_graph = (size_t)d->H * d->N * (d->N > 32 ? (size_t)d->N : (size_t)kEdgeTermNS);
+  *bytes = d->Fe > 0 ? (size_t)d->B * per_graph * sizeof(float) : 0;
+  return SPOTV2_OK;
+}
+
 extern "C" int spotv2_gat_uses_tensor_cores(const spotv2_gat_desc* d) {
   if (check_desc(d)) return 0;
   return use_tc(d) ? 1 : 0;

@@ -129,6 +129,12 @@ def _workspace(desc: GatDesc):
     return a.value, b.value, c.value
 
 
+def _edge_terms_bytes(desc: GatDesc) -> int:
+    a = C.c_size_t()
+    check(_lib.load().spotv2_gat_edge_terms_bytes(C.byref(desc), C.byref(a)), "edge_terms_bytes")
+    return a.value
+
+
 def _attn_fwd_workspace(desc: GatDesc) -> int:
     a = C.c_size_t()
     check(_lib.load().spotv2_gat_attn_fwd_workspace_bytes(C.byref(desc), C.byref(a)), "attn_fwd_workspace_bytes")
@@ -179,10 +185,15 @@ class _GatLayerFn(torch.autograd.Function):
         # N > 32 only: the [B,H,N,N] attention tile lives in a workspace unless the caller asked for alpha itself
         ws_t = _attn_fwd_workspace(desc) if alpha is None else 0
         ws_attn = torch.empty(ws_t, device=dev, dtype=torch.uint8) if ws_t else None
+        # the forward keeps the edge terms <e_ij, v_h> (6 floats per edge) when a backward will follow: the backward
+        # then reads the Fe-wide edge rows once (for dv) instead of twice
+        et = None
+        if Fe and any(ctx.needs_input_grad):
+            et = torch.empty(_edge_terms_bytes(desc) // 4, device=dev, dtype=torch.float32)
         check(lib.spotv2_gat_attn_fwd(C.byref(desc), ptr(P_aug), ptr(ea), ptr(topo.table) if Fe else None, ptr(v),
-                                      ptr(bias_c), ptr(out), ptr(alpha), ptr(ws_attn), ws_t, st), "spotv2_gat_attn_fwd")
+                                      ptr(bias_c), ptr(out), ptr(alpha), ptr(et), ptr(ws_attn), ws_t, st), "spotv2_gat_attn_fwd")
         ctx.desc, ctx.topo, ctx.Fe, ctx.has_bias = desc, topo, Fe, bias is not None
-        ctx.save_for_backward(x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk, p_amax)
+        ctx.save_for_backward(x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk, p_amax, et)
         if want_alpha:
             ctx.mark_non_differentiable(alpha)
             return out, alpha
@@ -191,7 +202,7 @@ class _GatLayerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, _dalpha=None):
         lib = _lib.load()
-        x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk, p_amax = ctx.saved_tensors
+        x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk, p_amax, et = ctx.saved_tensors
         desc, topo, Fe = ctx.desc, ctx.topo, ctx.Fe
         if ctx.needs_input_grad[1]:
             raise SpotV2Error("gradient w.r.t. edge_attr is not provided (the reference never needs it)")
@@ -213,7 +224,7 @@ class _GatLayerFn(torch.autograd.Function):
         ph, pl = (dP16[0], dP16[1]) if tc else (None, None)
         dv = torch.empty(H, Fe, device=dev, dtype=torch.float32) if Fe else None
         dbias = torch.empty(dout.shape[1], device=dev, dtype=torch.float32) if ctx.has_bias else None
-        check(lib.spotv2_gat_attn_bwd(C.byref(desc), ptr(P_aug), ptr(p_amax), ptr(ea), ptr(topo.table) if Fe else None, ptr(v),
+        check(lib.spotv2_gat_attn_bwd(C.byref(desc), ptr(P_aug), ptr(p_amax), ptr(ea), ptr(et), ptr(topo.table) if Fe else None, ptr(v),
                                       ptr(dout), ptr(dP_aug), ptr(ph), ptr(pl), ptr(dp_blk), ptr(dv), ptr(dbias),
                                       ptr(ws), ws.numel(), st), "spotv2_gat_attn_bwd")
         dW_aug = torch.empty_like(W_aug)
