@@ -654,6 +654,7 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
   a.p.ldo = d->concat ? d->H * d->C : d->C;
   a.p.slope = d->negative_slope;
   a.p.drop = dropout_params(d);
+  a.p.lg_tensor_cores = d->gemm_algo != 1;
   SPOTV2_REQUIRE(!edge_terms_or_null || aligned16(edge_terms_or_null), "attn_bwd: edge_terms must be 16-byte aligned");
   a.p.edge_terms = d->Fe > 0 ? const_cast<float*>(edge_terms_or_null) : nullptr;
   a.p.P_aug = P_aug; a.p.edge_rows = edge_rows; a.p.table = table; a.p.v = v;

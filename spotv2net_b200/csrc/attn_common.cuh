@@ -87,6 +87,7 @@ struct AttnParams {
   // graph for N <= 32, [H][N][N] for larger graphs).  The forward writes it when given; the backward reads it instead
   // of streaming the edge rows a first time and recomputing the logits (6 floats per edge instead of Fe).  Null = off.
   float* edge_terms;
+  int lg_tensor_cores;   // large-universe path: batched GEMMs on mma.sync (3xTF32) unless gemm_algo == 1 (exact-fp32 FFMA2)
 };
 
 constexpr int kEdgeTermNS = 36;     // == the alpha-tile row stride of attn_fwd.cu / attn_bwd2.cu

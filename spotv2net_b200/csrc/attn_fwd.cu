@@ -516,6 +516,7 @@ extern "C" int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug,
   a.p.ldo = d->concat ? d->H * d->C : d->C;
   a.p.slope = d->negative_slope;
   a.p.drop = dropout_params(d);
+  a.p.lg_tensor_cores = d->gemm_algo != 1;
   a.p.P_aug = P_aug; a.p.edge_rows = edge_rows; a.p.table = table; a.p.v = v;
   a.p.bulk_ok = d->Fe > 0 && aligned16(edge_rows) && ((size_t)d->R * d->Fe) % 4 == 0;
   a.p.vec2_ok = (d->C % 2 == 0);

@@ -514,6 +514,7 @@ int attn_large_fwd(const AttnParams& p, const float* bias, float* out, float* al
   if (int rc = lg_softmax(p, p.Fe > 0 ? Zraw : nullptr, A, nullptr, true, st)) return rc;
   const long long NN = (long long)p.N * p.N;
   BGemm g{};
+  g.tensor_cores = p.lg_tensor_cores;
   g.M = p.N; g.N = p.C; g.K = p.N;
   g.A = A; g.lda = p.N;                   // alpha_h stored [j][i]: [K, rows]
   g.B = p.P_aug; g.ldb = p.ldp;           // P_h stored [j][c]:     [K, rows]
@@ -562,6 +563,7 @@ int attn_large_bwd(const spotv2_gat_desc* d, AttnBwdArgs& a, float* dv, float* d
   const float gsc = p.concat ? 1.f : 1.f / (float)p.H;
   {   // dalpha_h[j][i] = g sum_c P[j,h,c] dO[i,(h)c]
     BGemm g{};
+    g.tensor_cores = p.lg_tensor_cores;
     g.M = p.N; g.N = p.N; g.K = p.C;
     g.A = p.P_aug; g.lda = p.ldp; g.B = a.dout; g.ldb = p.ldo; g.C = dA; g.ldc = p.N;
     g.inner = p.H; g.segs = 1; g.scale = gsc;
@@ -610,6 +612,7 @@ int attn_large_bwd(const spotv2_gat_desc* d, AttnBwdArgs& a, float* dv, float* d
   }
   {   // dP_h[j][c] = g sum_i alpha_h[j][i] dO[i,(h)c]
     BGemm g{};
+    g.tensor_cores = p.lg_tensor_cores;
     g.M = p.N; g.N = p.C; g.K = p.N;
     g.A = A; g.lda = p.N; g.B = a.dout; g.ldb = p.ldo; g.C = dP; g.ldc = p.ldp;
     g.inner = p.H; g.segs = 1; g.scale = gsc;

@@ -25,6 +25,7 @@ struct BGemm {
   const float* bias;                       // null or [inner * bias_i + N]
   long long bias_i;
   int vecA, vecB;                          // filled by bgemm_simt
+  int tensor_cores;                        // 1: mma.sync TF32 with the 3-product split (fp32-accurate); 0: FFMA2
 };
 int bgemm_simt(bool a_kc, bool b_kc, BGemm g, int batches, cudaStream_t st);
 

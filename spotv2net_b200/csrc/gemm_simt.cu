@@ -214,6 +214,127 @@ __global__ void __launch_bounds__(256, 2) bgemm_kernel(const BGemm g) {
   }
 }
 
+// Tensor-core form of bgemm_kernel: same tiles, loaders and epilogue, the 128x128x16 block product on
+// mma.sync.m16n8k8 TF32 with the 3-product split (lo*hi + hi*lo + hi*hi: fp32-accurate).  8 warps in a 2 x 4 grid,
+// warp tile 64 x 32 = 4 x 4 MMA tiles.  The tensor core's fp32 accumulate truncates, so the MMA accumulators are
+// folded into fp32 registers (round-to-nearest adds) every 64 elements of K.  Shared tiles are [k][m] with a pitch
+// of 136 floats: a fragment load touches rows t, t+4 and columns g, g+8 -> banks 8t + g, all distinct.
+constexpr int PADT = 8;
+
+template <bool KC>
+__device__ __forceinline__ void store_tile_t(float (*S)[BM + PADT], const float4 (&reg)[2], int tid) {
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int idx = tid + p * 256;
+    if (KC) {
+      const int r = idx >> 2, k = (idx & 3) * 4;
+      S[k + 0][r] = reg[p].x;
+      S[k + 1][r] = reg[p].y;
+      S[k + 2][r] = reg[p].z;
+      S[k + 3][r] = reg[p].w;
+    } else {
+      const int k = idx >> 5, r = (idx & 31) * 4;
+      *reinterpret_cast<float4*>(&S[k][r]) = reg[p];
+    }
+  }
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(256, 1) bgemm_tc_kernel(const BGemm g) {
+  __shared__ __align__(16) float As[2][BK][BM + PADT];
+  __shared__ __align__(16) float Bs[2][BK][BN + PADT];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int zo = blockIdx.z / g.inner, zi = blockIdx.z - zo * g.inner;
+  const float* A0 = g.A + (size_t)zo * g.a_o + (size_t)zi * g.a_i;
+  const float* B0 = g.B + (size_t)zo * g.b_o + (size_t)zi * g.b_i;
+  float* C = g.C + (size_t)zo * g.c_o + (size_t)zi * g.c_i;
+
+  float run[4][4][4], acc[4][4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) run[i][j][q] = acc[i][j][q] = 0.f;
+  int since_fold = 0;
+
+  for (int seg = 0; seg < g.segs; ++seg) {
+    const float* A = A0 + (size_t)seg * g.a_s;
+    const float* B = B0 + (size_t)seg * g.b_s;
+    float4 ra[2], rb[2];
+    __syncthreads();
+    load_tile<A_KC>(ra, A, g.lda, g.M, m0, 0, g.K, g.vecA, tid);
+    load_tile<B_KC>(rb, B, g.ldb, g.N, n0, 0, g.K, g.vecB, tid);
+    store_tile_t<A_KC>(As[0], ra, tid);
+    store_tile_t<B_KC>(Bs[0], rb, tid);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < g.K; k0 += BK) {
+      const bool more = k0 + BK < g.K;
+      if (more) {
+        load_tile<A_KC>(ra, A, g.lda, g.M, m0, k0 + BK, g.K, g.vecA, tid);
+        load_tile<B_KC>(rb, B, g.ldb, g.N, n0, k0 + BK, g.K, g.vecB, tid);
+      }
+#pragma unroll
+      for (int ks = 0; ks < BK / 8; ++ks) {
+        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          split_tf32_trunc(Bs[buf][ks * 8 + t][wn + j * 8 + gq], bh[j][0], bl[j][0]);
+          split_tf32_trunc(Bs[buf][ks * 8 + t + 4][wn + j * 8 + gq], bh[j][1], bl[j][1]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t ah[4], al[4];
+          split_tf32_trunc(As[buf][ks * 8 + t][wm + i * 16 + gq], ah[0], al[0]);
+          split_tf32_trunc(As[buf][ks * 8 + t][wm + i * 16 + gq + 8], ah[1], al[1]);
+          split_tf32_trunc(As[buf][ks * 8 + t + 4][wm + i * 16 + gq], ah[2], al[2]);
+          split_tf32_trunc(As[buf][ks * 8 + t + 4][wm + i * 16 + gq + 8], ah[3], al[3]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            mma_tf32_16x8x8(acc[i][j], al, bh[j]);
+            mma_tf32_16x8x8(acc[i][j], ah, bl[j]);
+            mma_tf32_16x8x8(acc[i][j], ah, bh[j]);
+          }
+        }
+      }
+      since_fold += BK;
+      if (since_fold >= 64) {
+        since_fold = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { run[i][j][q] += acc[i][j][q]; acc[i][j][q] = 0.f; }
+      }
+      if (more) {
+        store_tile_t<A_KC>(As[buf ^ 1], ra, tid);
+        store_tile_t<B_KC>(Bs[buf ^ 1], rb, tid);
+        __syncthreads();
+        buf ^= 1;
+      }
+    }
+  }
+
+  const float* bias = g.bias ? g.bias + (size_t)zi * g.bias_i : nullptr;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        // C fragment: (row gq | gq+8, col 2t | 2t+1)
+        const int m = m0 + wm + i * 16 + gq + ((q & 2) ? 8 : 0);
+        const int n = n0 + wn + j * 8 + 2 * t + (q & 1);
+        if (m < g.M && n < g.N)
+          C[(size_t)m * g.ldc + n] = fmaf(run[i][j][q] + acc[i][j][q], g.scale, bias ? bias[n] : 0.f);
+      }
+}
+
 int bgemm_simt(bool a_kc, bool b_kc, BGemm g, int batches, cudaStream_t st) {
   if (g.inner < 1) g.inner = 1;
   if (g.segs < 1) g.segs = 1;
@@ -221,7 +342,12 @@ int bgemm_simt(bool a_kc, bool b_kc, BGemm g, int batches, cudaStream_t st) {
   g.vecA = aligned16(g.A) && g.lda % 4 == 0 && mult4(g.a_o) && mult4(g.a_i) && mult4(g.a_s);
   g.vecB = aligned16(g.B) && g.ldb % 4 == 0 && mult4(g.b_o) && mult4(g.b_i) && mult4(g.b_s);
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, batches);
-  if (a_kc && b_kc) bgemm_kernel<true, true><<<grid, 256, 0, st>>>(g);
+  if (g.tensor_cores) {
+    if (a_kc && b_kc) bgemm_tc_kernel<true, true><<<grid, 256, 0, st>>>(g);
+    else if (a_kc && !b_kc) bgemm_tc_kernel<true, false><<<grid, 256, 0, st>>>(g);
+    else if (!a_kc && b_kc) bgemm_tc_kernel<false, true><<<grid, 256, 0, st>>>(g);
+    else bgemm_tc_kernel<false, false><<<grid, 256, 0, st>>>(g);
+  } else if (a_kc && b_kc) bgemm_kernel<true, true><<<grid, 256, 0, st>>>(g);
   else if (a_kc && !b_kc) bgemm_kernel<true, false><<<grid, 256, 0, st>>>(g);
   else if (!a_kc && b_kc) bgemm_kernel<false, true><<<grid, 256, 0, st>>>(g);
   else bgemm_kernel<false, false><<<grid, 256, 0, st>>>(g);
