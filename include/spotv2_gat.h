@@ -79,6 +79,10 @@ typedef struct spotv2_gat_desc {
                              attention coefficient is zeroed with probability p and the rest
                              scaled by 1/(1-p) AFTER the softmax (F.dropout(alpha) in [PyG]
                              gat_conv.py message); attn_bwd regenerates the same mask            */
+  int32_t edge_mode;      /* 0: edge features arrive as rows (edge_rows [B, R, Fe]); the default and the reference
+                             contract.  1: structured source - the caller computed the edge terms itself
+                             (spotv2_edge_terms_from_windows) and passes them as edge_terms; edge_rows and table are
+                             ignored, and attn_bwd returns d(edge terms) instead of dv (N <= 32 only)           */
   uint32_t dropout_seed_lo, dropout_seed_hi;   /* Philox4x32-10 key of the mask; element (b,h,i,j)
                              uses counter ((((b*H+h)*N+i)*N+j) >> 2), lane (.. & 3); pass
                              the same key to attn_fwd and attn_bwd of one step              */
@@ -164,6 +168,8 @@ int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug, const floa
 
 /* autograd of the above with the attention coefficients recomputed, not stored (edge_terms_or_null: what the
  * forward wrote, see spotv2_gat_edge_terms_bytes; null = recompute the edge terms from edge_rows as well).
+ * edge_mode 1: edge_terms is required, d_edge_terms_or_null (same size and layout) receives the gradient w.r.t.
+ * the edge terms and dv is left to spotv2_windows_dv.
  * dout [B*N, C or HC] -> dP_aug (dP | ds | dd), dv [H, Fe], dbias.  The gradient is emitted either as
  * fp32 dP_aug [B*N, ldp] (CUDA-core GEMM path) or, when dP_hi/dP_lo/dp_scale are given, directly as the
  * fp16 pair [B*N, ld16(HC+2H)] the tensor-core GEMMs consume (two scale groups: columns < HC from a
@@ -173,7 +179,21 @@ int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug, const floa
                         const float* edge_rows, const float* edge_terms_or_null,
                         const int32_t* table, const float* v, const float* dout, float* dP_aug_or_null,
                         void* dP_hi_or_null, void* dP_lo_or_null, float* dp_scale_or_null,
-                        float* dv_or_null, float* dbias_or_null, void* ws, size_t ws_bytes, void* stream);
+                        float* dv_or_null, float* d_edge_terms_or_null, float* dbias_or_null, void* ws, size_t ws_bytes,
+                        void* stream);
+
+/* ---- structured edge source (csrc/windows.cu) ---------------------------------------------------
+ * In the reference's dataset (utils/dataset.py:228-242) edge_attr is a pure function of the window of co-volatility
+ * matrices: edge (j -> i), feature k*L + t = vv[t0+t][min][max] | vv[t0+t][j][j] | vv[t0+t][i][i] for k = 0 | 1 | 2.
+ * These two calls replace the passes over the materialised [B*N*(N-1), 3L] rows by passes over the [L, N, N] windows
+ * (2.9x fewer bytes, 3x fewer multiply-adds); use them with desc.edge_mode = 1:
+ *   edge_terms_from_windows -> attn_fwd(edge_terms) ... attn_bwd(edge_terms, d_edge_terms_out) -> windows_dv -> dv.
+ * M_vv [T, N, N] fp32 on the device, t0 [B] int32 window starts, v [H, 3L] from spotv2_gat_fold. */
+int spotv2_edge_terms_from_windows(const spotv2_gat_desc* d, const float* M_vv, int32_t T, int32_t L,
+                                   const int32_t* t0, const float* v, float* edge_terms, void* stream);
+int spotv2_windows_dv_workspace_bytes(const spotv2_gat_desc* d, size_t* bytes);
+int spotv2_windows_dv(const spotv2_gat_desc* d, const float* M_vv, int32_t T, int32_t L, const int32_t* t0,
+                      const float* d_edge_terms, float* dv, void* ws, size_t ws_bytes, void* stream);
 
 /* lin_src backward: dW_aug [H*C+2H, F] = dP_aug^T . x  and  dX [B*N, F] = dP_aug . W_aug.
  * x and dP_aug are taken as fp16 pairs when given (hi, lo, scale block: all three), else as fp32 and
@@ -201,7 +221,7 @@ int spotv2_alpha_to_pyg(const spotv2_gat_desc* d, const float* alpha_tile, const
  * over CovarianceLaggedDataset, /root/reference/utils/dataset.py:182-289 and
  * 5_train_SpotV2Net.py:90,142-143).  M_vol, M_vv: [T, N, N] fp32 resident in HBM;
  * t0[B] int32 window starts; L = seq_length.  Writes x [B*N, N*L],
- * edge_attr [B*N*(N-1), 3L] in PyG row order, y [B*N]. */
+ * edge_attr [B*N*(N-1), 3L] in PyG row order (null: not materialised, see the structured edge source below), y [B*N]. */
 int spotv2_collate_windows(const float* M_vol, const float* M_vv, int32_t T, int32_t N, int32_t L,
                            const int32_t* t0, int32_t B, float* x, float* edge_attr, float* y,
                            void* stream);

@@ -12,11 +12,11 @@ Everything computes in libspotv2_gat.so (include/spotv2_gat.h); importing the pa
 load it, the first call does, and a missing library is an error, never a fallback.
 """
 from ._lib import SpotV2Error, load as load_library          # noqa: F401
-from .gat_conv import GATConv, Topology, topology_from_edge_index   # noqa: F401
+from .gat_conv import GATConv, Topology, WindowSource, topology_from_edge_index   # noqa: F401
 from .models import GATModel, gat_layer_plan                 # noqa: F401
 from .data import SpotBatch, WindowDataset, WindowLoader, complete_graph_edge_index, batched_topology  # noqa: F401
 from .infer import attention_weights, evaluate               # noqa: F401
 
 __all__ = ["GATConv", "GATModel", "WindowDataset", "WindowLoader", "SpotBatch", "SpotV2Error",
-           "Topology", "topology_from_edge_index", "complete_graph_edge_index", "gat_layer_plan",
+           "Topology", "WindowSource", "topology_from_edge_index", "complete_graph_edge_index", "gat_layer_plan",
            "load_library", "batched_topology", "evaluate", "attention_weights"]

@@ -21,7 +21,7 @@ class GatDesc(C.Structure):
     _fields_ = [("B", _i32), ("N", _i32), ("F", _i32), ("Fe", _i32), ("H", _i32), ("C", _i32),
                 ("R", _i32), ("concat", _i32), ("negative_slope", _f32), ("ldp", _i32),
                 ("gemm_algo", _i32), ("attn_bwd_algo", _i32),
-                ("dropout_p", _f32), ("dropout_seed_lo", C.c_uint32), ("dropout_seed_hi", C.c_uint32)]
+                ("dropout_p", _f32), ("edge_mode", _i32), ("dropout_seed_lo", C.c_uint32), ("dropout_seed_hi", C.c_uint32)]
 
 
 class SpotV2Error(RuntimeError):
@@ -45,7 +45,10 @@ SIGNATURES = {
     "spotv2_gat_attn_fwd_workspace_bytes": (C.c_int, [_DP, C.POINTER(_sz)]),
     "spotv2_gat_edge_terms_bytes": (C.c_int, [_DP, C.POINTER(_sz)]),
     "spotv2_gat_attn_fwd": (C.c_int, [_DP] + [_vp] * 9 + [_sz, _vp]),
-    "spotv2_gat_attn_bwd": (C.c_int, [_DP] + [_vp] * 14 + [_sz, _vp]),
+    "spotv2_gat_attn_bwd": (C.c_int, [_DP] + [_vp] * 15 + [_sz, _vp]),
+    "spotv2_edge_terms_from_windows": (C.c_int, [_DP, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "spotv2_windows_dv_workspace_bytes": (C.c_int, [_DP, C.POINTER(_sz)]),
+    "spotv2_windows_dv": (C.c_int, [_DP, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "spotv2_proj_bwd_weight": (C.c_int, [_DP] + [_vp] * 10 + [_sz, _vp]),
     "spotv2_proj_bwd_input": (C.c_int, [_DP] + [_vp] * 7 + [_sz, _vp]),
     "spotv2_gat_unfold": (C.c_int, [_DP] + [_vp] * 13),

@@ -634,15 +634,20 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
                                    const float* edge_rows, const float* edge_terms_or_null, const int32_t* table,
                                    const float* v,
                                    const float* dout, float* dP_aug_or_null, void* dP_hi_or_null, void* dP_lo_or_null,
-                                   float* dp_scale_or_null, float* dv_or_null, float* dbias_or_null, void* ws,
-                                   size_t ws_bytes, void* stream) {
+                                   float* dp_scale_or_null, float* dv_or_null, float* d_edge_terms_or_null,
+                                   float* dbias_or_null, void* ws, size_t ws_bytes, void* stream) {
   if (int rc = check_desc(d)) return rc;
   SPOTV2_REQUIRE(P_aug && dout, "attn_bwd: P_aug and dout must be non-null");
   const bool f16 = dP_hi_or_null != nullptr;
   SPOTV2_REQUIRE(f16 || dP_aug_or_null, "attn_bwd: give dP_aug (fp32) or dP_hi/dP_lo/dp_scale (fp16 pairs)");
   SPOTV2_REQUIRE(!f16 || (dP_lo_or_null && dp_scale_or_null), "attn_bwd: dP_hi needs dP_lo and dp_scale");
-  SPOTV2_REQUIRE(d->Fe == 0 || (edge_rows && table && v),
+  const bool structured = d->edge_mode == 1 && d->Fe > 0;
+  SPOTV2_REQUIRE(d->Fe == 0 || structured || (edge_rows && table && v),
                  "attn_bwd: edge_rows, table and v are required when Fe > 0");
+  SPOTV2_REQUIRE(!structured || (edge_terms_or_null && d_edge_terms_or_null && aligned16(d_edge_terms_or_null)),
+                 "attn_bwd: edge_mode 1 needs edge_terms and a 16-byte aligned d_edge_terms buffer");
+  if (structured && (d->N > 32 || d->attn_bwd_algo == 1 || d->dropout_p > 0.f))
+    return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd: edge_mode 1 runs on the pipelined kernel only (N <= 32, no attention dropout)");
   SPOTV2_REQUIRE(aligned16(P_aug) && aligned16(dout) && (f16 || aligned16(dP_aug_or_null)) &&
                      (!f16 || (aligned16(dP_hi_or_null) && aligned16(dP_lo_or_null))),
                  "attn_bwd: P_aug/dout/dP must be 16-byte aligned");
@@ -657,6 +662,8 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
   a.p.lg_tensor_cores = d->gemm_algo != 1;
   SPOTV2_REQUIRE(!edge_terms_or_null || aligned16(edge_terms_or_null), "attn_bwd: edge_terms must be 16-byte aligned");
   a.p.edge_terms = d->Fe > 0 ? const_cast<float*>(edge_terms_or_null) : nullptr;
+  a.p.terms_in = structured ? 1 : 0;
+  a.p.dterms_out = structured ? d_edge_terms_or_null : nullptr;
   a.p.P_aug = P_aug; a.p.edge_rows = edge_rows; a.p.table = table; a.p.v = v;
   a.p.bulk_ok = d->Fe > 0 && aligned16(edge_rows) && ((size_t)d->R * d->Fe) % 4 == 0;
   a.p.vec2_ok = (d->C % 2 == 0);
@@ -698,8 +705,10 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
   // attention dropout (a non-default training option) is implemented in the phase-serial kernel only
   if (d->dropout_p > 0.f && d->attn_bwd_algo == 2)
     return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd: the pipelined kernel (attn_bwd_algo = 2) does not implement attention dropout");
+  if (structured && !attn_bwd2_fits(a.p))
+    return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd: edge_mode 1 needs the pipelined kernel, whose shared-memory plan does not fit this shape");
   if (d->dropout_p == 0.f && d->attn_bwd_algo != 1 && (attn_bwd2_fits(a.p) || d->attn_bwd_algo == 2))
-    rc = launch_attn_bwd2(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
+    rc = launch_attn_bwd2(a, structured ? nullptr : dv_or_null, dbias_or_null, ws, ws_bytes, st);
   else if (np <= 4) rc = launch_bwd<4>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
   else if (np <= 8) rc = launch_bwd<8>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
   else if (np <= 15) rc = launch_bwd<15>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);

@@ -264,9 +264,13 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
   __builtin_assume(__isShared(pos_mask)); __builtin_assume(__isShared(ds_part)); __builtin_assume(__isShared(dbias_s));
   __builtin_assume(__isShared(tile)); __builtin_assume(__isShared(D)); __builtin_assume(__isShared(slots));
 
-  const int nchunks = pl.nchunks;
-  // the forward kept the edge terms: phase L becomes one 26 KB bulk copy instead of a pass over the edge rows
-  const bool use_terms = p.edge_terms != nullptr && nchunks > 0 && (uint32_t)tile_floats * 4u <= pl.slot_bytes;
+  // edge_mode 1 (structured source): no edge rows at all - the edge terms come in, d(edge terms) goes out
+  const int nchunks = p.terms_in ? 0 : pl.nchunks;
+  // the forward kept the edge terms: phase L becomes a bulk copy of the tile (in slot-sized pieces) instead of a pass
+  // over the edge rows
+  const uint32_t tile_bytes = (uint32_t)tile_floats * 4u;
+  const int term_pieces = (int)((tile_bytes + pl.slot_bytes - 1) / pl.slot_bytes);
+  const bool use_terms = p.edge_terms != nullptr && (nchunks > 0 || p.terms_in);
   const int my_graphs = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int n_cb = pl.n_cb;
   auto rows_in = [&](int c) { const int r = p.R - c * pl.chunk_rows; return r < pl.chunk_rows ? r : pl.chunk_rows; };
@@ -277,14 +281,14 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
   }
   // row -> byte offset of (source j, target i) inside one head of the alpha / dz' tiles (-1: row skipped)
   for (int r = tid; r < p.R; r += kB2Threads) {
-    const int code = Fe > 0 ? p.table[r] : -1;
+    const int code = (Fe > 0 && !p.terms_in) ? p.table[r] : -1;
     table_s[r] = code >= 0 ? ((code & 0xffff) * NS + (code >> 16)) * 4 : -1;
   }
   // slots start zero-filled: rows and tails a chunk does not cover must read as finite numbers
   for (uint32_t idx = tid; idx < (uint32_t)pl.n_slots * pl.slot_bytes / 16; idx += kB2Threads)
     reinterpret_cast<float4*>(smem_raw + pl.off_slots)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
   fence_proxy_async();                    // generic-proxy zero fill before the copy engine writes the same bytes
-  if (Fe > 0) build_vfrag(vfrag, p.v, H, Fe, pl.KS, 1, tid, kB2Threads);
+  if (Fe > 0 && !p.terms_in) build_vfrag(vfrag, p.v, H, Fe, pl.KS, 1, tid, kB2Threads);
   for (int idx = tid; idx < tile_floats; idx += kB2Threads) { tile[idx] = 0.f; D[idx] = 0.f; }
   for (int idx = tid; idx < p.ldo; idx += kB2Threads) dbias_s[idx] = 0.f;
   __syncthreads();
@@ -339,14 +343,18 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
     const int n_grp_d = (n_cb + pl.cbs_per_grp_d - 1) / pl.cbs_per_grp_d;
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
-      if (use_terms) {                                                          // phase L': the forward's edge terms, one slot
-        float* dst = reinterpret_cast<float*>(acquire());
-        if (lane == 0) {
-          const uint32_t bytes = (uint32_t)tile_floats * 4u;
-          mbar_expect_tx(&full[slot], bytes);
-          bulk_g2s_hint(dst, p.edge_terms + (size_t)b * tile_floats, bytes, &full[slot], kEvictFirst);
+      if (use_terms) {                                                          // phase L': the edge-term tile, slot-sized pieces
+        for (int pc = 0; pc < term_pieces; ++pc) {
+          float* dst = reinterpret_cast<float*>(acquire());
+          if (lane == 0) {
+            const uint32_t off = (uint32_t)pc * pl.slot_bytes;
+            const uint32_t bytes = min(pl.slot_bytes, tile_bytes - off);
+            mbar_expect_tx(&full[slot], bytes);
+            bulk_g2s_hint(dst, reinterpret_cast<const unsigned char*>(p.edge_terms + (size_t)b * tile_floats) + off, bytes,
+                          &full[slot], kEvictFirst);
+          }
+          publish(true);
         }
-        publish(true);
       } else {
         for (int c = 0; c < nchunks; ++c) edge_chunk(b, c, kEvictLast);         // phase L (kept in L2 for phase V)
       }
@@ -486,10 +494,14 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
     }
     for (int idx = tid; idx < 2 * H * 32; idx += kCT) ds_part[idx] = 0.f;
     if (use_terms) {
-      const uint32_t sa = wait_slot();
-      for (int idx = tid; idx < tile_floats / 4; idx += kCT)
-        reinterpret_cast<float4*>(tile)[idx] = lds128_u32(sa + (uint32_t)idx * 16u);
-      release_slot();
+      for (int pc = 0; pc < term_pieces; ++pc) {
+        const uint32_t sa = wait_slot();
+        const uint32_t off = (uint32_t)pc * pl.slot_bytes;
+        const int n16 = (int)(min(pl.slot_bytes, tile_bytes - off) / 16u);
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(tile) + off);
+        for (int idx = tid; idx < n16; idx += kCT) dst[idx] = lds128_u32(sa + (uint32_t)idx * 16u);
+        release_slot();
+      }
     }
     for (int c = 0; c < (use_terms ? 0 : nchunks); ++c) {
       const uint32_t sa = wait_slot();
@@ -711,6 +723,13 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
       else args.dP_aug[((size_t)b * N + j) * p.ldp + HC + h] = ds;
     }
     lap(3);
+    if (p.dterms_out) {
+      // edge_mode 1: the gradient w.r.t. the edge terms (dz', diagonal 0) leaves in the tile layout; dv is formed from
+      // the windows by spotv2_windows_dv.  (The D tile is complete: phase A ended with a CTA barrier.)
+      float4* dst = reinterpret_cast<float4*>(p.dterms_out + (size_t)b * tile_floats);
+      const float4* src = reinterpret_cast<const float4*>(D);
+      for (int idx = tid; idx < tile_floats / 4; idx += kCT) dst[idx] = src[idx];
+    }
     // ------------------------------------------------ V: dv += dz'^T . edge rows ------------------------------------------------
     for (int c = 0; c < nchunks; ++c) {
       const uint32_t sa = wait_slot();

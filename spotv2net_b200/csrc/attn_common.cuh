@@ -87,6 +87,8 @@ struct AttnParams {
   // graph for N <= 32, [H][N][N] for larger graphs).  The forward writes it when given; the backward reads it instead
   // of streaming the edge rows a first time and recomputing the logits (6 floats per edge instead of Fe).  Null = off.
   float* edge_terms;
+  int terms_in;          // edge_mode 1: edge_terms is an INPUT (spotv2_edge_terms_from_windows); there are no edge rows
+  float* dterms_out;     // backward, edge_mode 1: receives dz' (gradient w.r.t. the edge terms) in the same tile layout
   int lg_tensor_cores;   // large-universe path: batched GEMMs on mma.sync (3xTF32) unless gemm_algo == 1 (exact-fp32 FFMA2)
 };
 

@@ -111,7 +111,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm_, const uint32_t o
   float* sd0 = reinterpret_cast<float*>(smem_raw + sm.off_sd);
   float* tile0 = reinterpret_cast<float*>(smem_raw + sm.off_tile);
 
-  const int nchunks = p.Fe > 0 ? (p.R + sm.chunk_rows - 1) / sm.chunk_rows : 0;
+  const int nchunks = (p.Fe > 0 && !p.terms_in) ? (p.R + sm.chunk_rows - 1) / sm.chunk_rows : 0;
   const int my_graphs = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (tid == 0) {
@@ -127,7 +127,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm_, const uint32_t o
   }
   // row -> byte offset of (source j, target i) inside one head of the alpha tile (-1: row skipped)
   for (int r = tid; r < p.R; r += kFwdThreads) {
-    const int code = p.Fe > 0 ? p.table[r] : -1;
+    const int code = (p.Fe > 0 && !p.terms_in) ? p.table[r] : -1;
     table_s[r] = code >= 0 ? ((code & 0xffff) * NS + (code >> 16)) * 4 : -1;
   }
   // the edge ring starts zero-filled: k-steps padded past Fe and rows past the end of a short chunk read stale
@@ -135,7 +135,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm_, const uint32_t o
   for (uint32_t idx = tid; idx < (off_ptile - (uint32_t)sm.off_ring) / 16; idx += kFwdThreads)
     reinterpret_cast<float4*>(smem_raw + sm.off_ring)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
   fence_proxy_async();
-  if (p.Fe > 0) build_vfrag(vfrag, p.v, H, p.Fe, sm.KS, sm.NT, tid, kFwdThreads);
+  if (p.Fe > 0 && !p.terms_in) build_vfrag(vfrag, p.v, H, p.Fe, sm.KS, sm.NT, tid, kFwdThreads);
   for (int idx = tid; idx < 2 * tile_floats; idx += kFwdThreads) tile0[idx] = 0.f;
   __syncthreads();
 
@@ -170,6 +170,18 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm_, const uint32_t o
       const int buf = it & 1;
       float* tile = tile0 + buf * tile_floats;
       mbar_wait_timed(&tile_empty[buf], ((it >> 1) & 1) ^ 1, w_tile);   // group B has finished reading this buffer
+      if (p.terms_in) {
+        // structured edge source: the caller computed the edge terms; one bulk copy drops them into the tile buffer.
+        // Thread 0's arrive.expect_tx is its arrival on tile_full; the phase completes when the bytes have landed.
+        if (tid == 0) {
+          const uint32_t bytes = (uint32_t)tile_floats * 4u;
+          mbar_expect_tx(&tile_full[buf], bytes);
+          bulk_g2s(tile, p.edge_terms + (size_t)b * tile_floats, bytes, &tile_full[buf]);
+        } else {
+          mbar_arrive_cta(&tile_full[buf]);
+        }
+        continue;
+      }
       if (nchunks == 0) {
         for (int idx = tid; idx < tile_floats; idx += kGroupA) tile[idx] = 0.f;
       }
@@ -237,7 +249,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm_, const uint32_t o
         t_bar += clock64() - tc1;
         if (p.bulk_ok && tid == 0 && k + 2 < total_chunks) issue(k + 2);
       }
-      if (p.edge_terms && NS == kEdgeTermNS) {
+      if (p.edge_terms && !p.terms_in && NS == kEdgeTermNS) {
         // keep the edge terms for the backward (it then reads 6 floats per edge instead of the Fe-wide rows).  All of
         // group A's scatters are behind the chunk loop's last bar.sync; diagonal entries hold stale finite values
         // that no consumer reads.
@@ -368,6 +380,7 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm_, const uint32_t o
         }
         if (!p.concat && mine) store(0);                   // head mean (alpha pre-scaled by 1/H) + bias
       }
+      if (p.terms_in) fence_proxy_async();               // our generic-proxy writes to the tile precede the next bulk copy into it
       mbar_arrive_cta(&tile_empty[buf]);                 // this thread is done reading the alpha tile
     }
     if (tid == kGroupA) {
@@ -505,8 +518,11 @@ extern "C" int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug,
                                    float* edge_terms_or_null, void* ws, size_t ws_bytes, void* stream) {
   if (int rc = check_desc(d)) return rc;
   SPOTV2_REQUIRE(P_aug && out, "attn_fwd: P_aug and out must be non-null");
-  SPOTV2_REQUIRE(d->Fe == 0 || (edge_rows && table && v),
+  const bool structured = d->edge_mode == 1 && d->Fe > 0;
+  SPOTV2_REQUIRE(d->Fe == 0 || structured || (edge_rows && table && v),
                  "attn_fwd: edge_rows, table and v are required when Fe > 0");
+  SPOTV2_REQUIRE(!structured || edge_terms_or_null, "attn_fwd: edge_mode 1 needs edge_terms (spotv2_edge_terms_from_windows)");
+  if (structured && d->N > 32) return fail(SPOTV2_ERR_UNSUPPORTED, "attn_fwd: edge_mode 1 covers N <= 32");
   SPOTV2_REQUIRE(aligned16(P_aug) && aligned16(out), "attn_fwd: P_aug/out must be 16-byte aligned");
   if (d->H > kMaxHeads) return fail(SPOTV2_ERR_UNSUPPORTED, "H=%d > %d", d->H, kMaxHeads);
   if (d->Fe > kMaxFe) return fail(SPOTV2_ERR_UNSUPPORTED, "Fe=%d > %d", d->Fe, kMaxFe);
@@ -522,6 +538,8 @@ extern "C" int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug,
   a.p.vec2_ok = (d->C % 2 == 0);
   SPOTV2_REQUIRE(!edge_terms_or_null || aligned16(edge_terms_or_null), "attn_fwd: edge_terms must be 16-byte aligned");
   a.p.edge_terms = d->Fe > 0 ? edge_terms_or_null : nullptr;
+  a.p.terms_in = structured ? 1 : 0;
+  a.p.dterms_out = nullptr;
   a.bias = bias_or_null; a.out = out; a.alpha_out = alpha_or_null;
   if (attn_large_applies(d))       // several CTAs per graph, attention tile in the workspace (or alpha_or_null)
     return attn_large_fwd(a.p, bias_or_null, out, alpha_or_null, ws, ws_bytes, as_stream(stream));

@@ -293,12 +293,14 @@ extern "C" int spotv2_alpha_to_pyg(const spotv2_gat_desc* d, const float* alpha_
 extern "C" int spotv2_collate_windows(const float* M_vol, const float* M_vv, int32_t T, int32_t N,
                                       int32_t L, const int32_t* t0, int32_t B, float* x,
                                       float* edge_attr, float* y, void* stream) {
-  SPOTV2_REQUIRE(M_vol && M_vv && t0 && x && edge_attr && y, "collate_windows: null pointer");
+  SPOTV2_REQUIRE(M_vol && M_vv && t0 && x && y, "collate_windows: null pointer");
   SPOTV2_REQUIRE(T > L && N > 1 && L > 0 && B > 0, "collate_windows: need T > L, N > 1, L > 0, B > 0");
   cudaStream_t st = as_stream(stream);
   collate_x_kernel<<<B * N, 256, 0, st>>>(M_vol, t0, N, L, x, y);
-  dim3 ge((N * (N - 1) + 7) / 8, B);
-  collate_edge_kernel<<<ge, 256, 0, st>>>(M_vv, t0, N, L, edge_attr);
+  if (edge_attr) {            // null: the caller keeps the edges structured (window references, csrc/windows.cu)
+    dim3 ge((N * (N - 1) + 7) / 8, B);
+    collate_edge_kernel<<<ge, 256, 0, st>>>(M_vv, t0, N, L, edge_attr);
+  }
   SPOTV2_CUDA_OK(cudaGetLastError());
   return SPOTV2_OK;
 }

@@ -21,7 +21,7 @@ from torch import Tensor
 
 from . import _lib
 from ._lib import SpotV2Error, check, ptr, stream_ptr
-from .gat_conv import Topology, topology_from_edge_index
+from .gat_conv import Topology, WindowSource, topology_from_edge_index
 
 REFERENCE_DROP_FIRST = 8357          # hard-coded cut at utils/dataset.py:288
 
@@ -36,9 +36,10 @@ def complete_graph_edge_index(N: int) -> Tensor:
 class SpotBatch:
     """Duck-typed PyG ``Batch`` for identical complete graphs."""
 
-    def __init__(self, x, edge_index, edge_attr, y_x, num_graphs, nodes_per_graph, spot_topology=None):
+    def __init__(self, x, edge_index, edge_attr, y_x, num_graphs, nodes_per_graph, spot_topology=None, spot_windows=None):
         self.x, self.edge_index, self.edge_attr, self.y_x = x, edge_index, edge_attr, y_x
         self.num_graphs, self.nodes_per_graph, self.spot_topology = num_graphs, nodes_per_graph, spot_topology
+        self.spot_windows = spot_windows        # WindowSource: lets the GAT layers read the windows instead of edge_attr
 
     @property
     def batch(self) -> Tensor:
@@ -52,6 +53,8 @@ class SpotBatch:
         device = torch.device(device)
         if device == self.x.device:
             return self
+        if self.edge_attr is None:
+            raise SpotV2Error("a structured batch (no materialised edge_attr) lives on its dataset's device")
         moved = [t.to(device, non_blocking=non_blocking) for t in (self.x, self.edge_index, self.edge_attr, self.y_x)]
         return SpotBatch(*moved, self.num_graphs, self.nodes_per_graph, None)
 
@@ -101,7 +104,7 @@ class WindowDataset:
     """
 
     def __init__(self, vol, volvol, seq_length: int, device="cuda", drop_first: int = REFERENCE_DROP_FIRST,
-                 future_steps: Optional[int] = None):
+                 future_steps: Optional[int] = None, structured: bool = False):
         vol = torch.as_tensor(np.asarray(vol) if not torch.is_tensor(vol) else vol)
         volvol = torch.as_tensor(np.asarray(volvol) if not torch.is_tensor(volvol) else volvol)
         if vol.shape != volvol.shape or vol.dim() != 3 or vol.shape[1] != vol.shape[2]:
@@ -109,6 +112,9 @@ class WindowDataset:
         self.T, self.N = int(vol.shape[0]), int(vol.shape[1])
         self.L = int(seq_length)
         self.drop_first = int(drop_first)
+        # structured=True: batches carry window references (SpotBatch.spot_windows) instead of the materialised
+        # [B*N*(N-1), 3L] edge_attr (edge_attr is None); GATModel / GATConv then read the [L, N, N] windows directly
+        self.structured = bool(structured)
         self.future_steps = None if future_steps is None else int(future_steps)
         if self.future_steps is not None and self.future_steps < 1:
             raise SpotV2Error("future_steps must be >= 1")
@@ -134,7 +140,7 @@ class WindowDataset:
         t0 = (idx + self.drop_first).to(torch.int32).to(self.device)
         dev = self.device
         x = torch.empty(B * N, N * L, device=dev, dtype=torch.float32)
-        ea = torch.empty(B * N * (N - 1), 3 * L, device=dev, dtype=torch.float32)
+        ea = None if self.structured else torch.empty(B * N * (N - 1), 3 * L, device=dev, dtype=torch.float32)
         y = torch.empty(B * N, device=dev, dtype=torch.float32)
         lib = _lib.load()
         check(lib.spotv2_collate_windows(ptr(self.vol), ptr(self.volvol), self.T, N, L, ptr(t0), B, ptr(x), ptr(ea),
@@ -144,7 +150,7 @@ class WindowDataset:
             t = (t0.to(torch.int64) + L).view(B, 1) + torch.arange(K, device=dev).view(1, K)
             y = self.vol.diagonal(dim1=1, dim2=2)[t].permute(0, 2, 1).reshape(-1).contiguous()
         ei, topo = batched_topology(B, N, dev)
-        return SpotBatch(x, ei, ea, y, B, N, topo)
+        return SpotBatch(x, ei, ea, y, B, N, topo, WindowSource(self.volvol, t0, L))
 
     def __getitem__(self, k):
         if isinstance(k, slice):

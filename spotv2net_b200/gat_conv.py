@@ -25,6 +25,16 @@ from ._lib import GatDesc, SpotV2Error, check, ptr, stream_ptr
 
 # --------------------------------------------------------------------------- topology
 @dataclass
+class WindowSource:
+    """Structured edge source: the [T, N, N] co-volatility stack the reference's dataset builds
+    edge_attr from (utils/dataset.py:228-242) plus each graph's window start.  A layer given this reads the windows
+    (151 KB per graph at the default geometry) instead of the materialised edge rows (438 KB)."""
+    volvol: Tensor         # [T, N, N] fp32 on the device
+    t0: Tensor             # [B] int32 on the device
+    L: int                 # seq_length; edge_dim must be 3 * L
+
+
+@dataclass
 class Topology:
     """What the kernels need to know about ``edge_index``: B graphs of N nodes,
     R edge rows per graph, and the row table (row -> target/source)."""
@@ -115,11 +125,11 @@ PRECISIONS = {"fp32": None, "half": 3}      # "half": single fp16 tensor-core pr
 
 
 def _desc(topo: Topology, F_in: int, Fe: int, H: int, Cc: int, concat: bool, slope: float,
-          dropout_p: float = 0.0, seed: int = 0, gemm_algo: Optional[int] = None) -> GatDesc:
+          dropout_p: float = 0.0, seed: int = 0, gemm_algo: Optional[int] = None, edge_mode: int = 0) -> GatDesc:
     lib = _lib.load()
     return GatDesc(topo.B, topo.N, F_in, Fe, H, Cc, topo.R, int(concat), float(slope),
                    lib.spotv2_gat_ldp(H, Cc), GEMM_ALGO if gemm_algo is None else gemm_algo, ATTN_BWD_ALGO,
-                   float(dropout_p), seed & 0xffffffff, (seed >> 32) & 0xffffffff)
+                   float(dropout_p), int(edge_mode), seed & 0xffffffff, (seed >> 32) & 0xffffffff)
 
 
 def _workspace(desc: GatDesc):
@@ -146,16 +156,18 @@ class _GatLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, edge_attr, W, a_src, a_dst, W_e, a_edge, bias, topo, H, Cc, concat, slope, want_alpha,
-                dropout_p=0.0, seed=0, gemm_algo=None):
+                dropout_p=0.0, seed=0, gemm_algo=None, windows=None):
         lib = _lib.load()
         dev = x.device
         st = stream_ptr(dev)
         Fe = 0 if edge_attr is None or W_e is None else edge_attr.shape[1]
+        if windows is not None:                     # structured edge source: the edge rows are never touched
+            Fe, edge_attr = 3 * windows.L, None
         # the descriptor (incl. this step's dropout key) is kept for the backward, which regenerates the same mask
-        desc = _desc(topo, x.shape[1], Fe, H, Cc, concat, slope, dropout_p, seed, gemm_algo)
+        desc = _desc(topo, x.shape[1], Fe, H, Cc, concat, slope, dropout_p, seed, gemm_algo, 1 if windows is not None else 0)
         n, HC = x.shape[0], H * Cc
         x = x.contiguous()
-        ea = edge_attr.contiguous() if Fe else None
+        ea = edge_attr.contiguous() if (Fe and windows is None) else None
         # every tensor whose address is handed to the library is held in a local until the call returns
         W, a_src, a_dst = W.contiguous(), a_src.contiguous(), a_dst.contiguous()
         W_e = W_e.contiguous() if W_e is not None else None
@@ -188,11 +200,14 @@ class _GatLayerFn(torch.autograd.Function):
         # the forward keeps the edge terms <e_ij, v_h> (6 floats per edge) when a backward will follow: the backward
         # then reads the Fe-wide edge rows once (for dv) instead of twice
         et = None
-        if Fe and any(ctx.needs_input_grad):
+        if Fe and (windows is not None or any(ctx.needs_input_grad)):
             et = torch.empty(_edge_terms_bytes(desc) // 4, device=dev, dtype=torch.float32)
-        check(lib.spotv2_gat_attn_fwd(C.byref(desc), ptr(P_aug), ptr(ea), ptr(topo.table) if Fe else None, ptr(v),
+        if windows is not None:
+            check(lib.spotv2_edge_terms_from_windows(C.byref(desc), ptr(windows.volvol), windows.volvol.shape[0], windows.L,
+                                                     ptr(windows.t0), ptr(v), ptr(et), st), "spotv2_edge_terms_from_windows")
+        check(lib.spotv2_gat_attn_fwd(C.byref(desc), ptr(P_aug), ptr(ea), ptr(topo.table) if (Fe and windows is None) else None, ptr(v),
                                       ptr(bias_c), ptr(out), ptr(alpha), ptr(et), ptr(ws_attn), ws_t, st), "spotv2_gat_attn_fwd")
-        ctx.desc, ctx.topo, ctx.Fe, ctx.has_bias = desc, topo, Fe, bias is not None
+        ctx.desc, ctx.topo, ctx.Fe, ctx.has_bias, ctx.windows = desc, topo, Fe, bias is not None, windows
         ctx.save_for_backward(x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk, p_amax, et)
         if want_alpha:
             ctx.mark_non_differentiable(alpha)
@@ -224,9 +239,18 @@ class _GatLayerFn(torch.autograd.Function):
         ph, pl = (dP16[0], dP16[1]) if tc else (None, None)
         dv = torch.empty(H, Fe, device=dev, dtype=torch.float32) if Fe else None
         dbias = torch.empty(dout.shape[1], device=dev, dtype=torch.float32) if ctx.has_bias else None
-        check(lib.spotv2_gat_attn_bwd(C.byref(desc), ptr(P_aug), ptr(p_amax), ptr(ea), ptr(et), ptr(topo.table) if Fe else None, ptr(v),
-                                      ptr(dout), ptr(dP_aug), ptr(ph), ptr(pl), ptr(dp_blk), ptr(dv), ptr(dbias),
-                                      ptr(ws), ws.numel(), st), "spotv2_gat_attn_bwd")
+        win = ctx.windows
+        d_et = torch.empty_like(et) if win is not None else None     # structured source: d(edge terms) out, dv from the windows
+        check(lib.spotv2_gat_attn_bwd(C.byref(desc), ptr(P_aug), ptr(p_amax), ptr(ea), ptr(et),
+                                      ptr(topo.table) if (Fe and win is None) else None, ptr(v),
+                                      ptr(dout), ptr(dP_aug), ptr(ph), ptr(pl), ptr(dp_blk), ptr(dv) if win is None else None,
+                                      ptr(d_et), ptr(dbias), ptr(ws), ws.numel(), st), "spotv2_gat_attn_bwd")
+        if win is not None:
+            wsz = C.c_size_t()
+            check(lib.spotv2_windows_dv_workspace_bytes(C.byref(desc), C.byref(wsz)), "windows_dv_workspace_bytes")
+            ws_dv = torch.empty(wsz.value, device=dev, dtype=torch.uint8)
+            check(lib.spotv2_windows_dv(C.byref(desc), ptr(win.volvol), win.volvol.shape[0], win.L, ptr(win.t0), ptr(d_et),
+                                        ptr(dv), ptr(ws_dv), wsz.value, st), "spotv2_windows_dv")
         dW_aug = torch.empty_like(W_aug)
         xh = x16[0] if x16 is not None else None
         xl = x16[1] if x16 is not None else None
@@ -248,7 +272,7 @@ class _GatLayerFn(torch.autograd.Function):
                                     ptr(da_dst), ptr(dW_e), ptr(da_edge), st), "spotv2_gat_unfold")
         if not Fe and W_e is not None:          # layer has lin_edge but was called with edge_attr=None
             dW_e, da_edge = torch.zeros_like(W_e), torch.zeros_like(a_edge)
-        return (dx, None, dW, da_src, da_dst, dW_e, da_edge, dbias) + (None,) * 9
+        return (dx, None, dW, da_src, da_dst, dW_e, da_edge, dbias) + (None,) * 10
 
 
 # --------------------------------------------------------------------------- module
@@ -338,7 +362,8 @@ class GATConv(nn.Module):
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
     def forward(self, x: Tensor, edge_index, edge_attr: Optional[Tensor] = None, size=None,
-                return_attention_weights=None, topology: Optional[Topology] = None):
+                return_attention_weights=None, topology: Optional[Topology] = None,
+                windows: Optional[WindowSource] = None):
         assert x.dim() == 2, "Static graphs not supported in 'GATConv'"
         _lib.require_cuda(x, "x")
         # attention dropout (dropout_att; 0.0 by default, config/GNN_param.yaml:36): a fresh 64-bit Philox key per
@@ -354,15 +379,26 @@ class GATConv(nn.Module):
             if edge_attr.dim() == 1:
                 edge_attr = edge_attr.view(-1, 1)
         topo = topology or topology_from_edge_index(edge_index, x.shape[0], self.nodes_per_graph)
-        use_edge = edge_attr is not None and self.lin_edge is not None
-        if use_edge and edge_attr.shape[0] != topo.B * topo.R:
+        # structured edge source (batches of spotv2net_b200.WindowDataset): usable when this layer's edge_dim is the
+        # dataset's 3L on graphs the fused kernels cover; otherwise the materialised edge_attr is required
+        had_windows = windows is not None
+        if windows is not None and not (self.lin_edge is not None and self.edge_dim == 3 * windows.L and topo.N <= 32 and
+                                        topo.R == topo.N * (topo.N - 1) and not topo.has_skips and drop_p == 0.0 and
+                                        ATTN_BWD_ALGO != 1 and windows.t0.numel() == topo.B):
+            windows = None
+        if had_windows and windows is None and edge_attr is None and self.lin_edge is not None:
+            raise SpotV2Error("this batch carries window references instead of a materialised edge_attr, and this layer "
+                              "cannot use them (edge_dim != 3 * seq_length, N > 32, attention dropout in training, ...): "
+                              "collate with structured=False")
+        use_edge = (edge_attr is not None or windows is not None) and self.lin_edge is not None
+        if use_edge and windows is None and edge_attr.shape[0] != topo.B * topo.R:
             raise SpotV2Error(f"edge_attr has {edge_attr.shape[0]} rows, edge_index has {topo.B * topo.R} edges")
         want_alpha = isinstance(return_attention_weights, bool)
         out, alpha_tile = _GatLayerFn.apply(
-            x, edge_attr if use_edge else None, self.lin_src.weight, self.att_src, self.att_dst,
+            x, edge_attr if (use_edge and windows is None) else None, self.lin_src.weight, self.att_src, self.att_dst,
             self.lin_edge.weight if self.lin_edge is not None else None, self.att_edge, self.bias,
             topo, self.heads, self.out_channels, self.concat, self.negative_slope, want_alpha, drop_p, seed,
-            PRECISIONS[self.precision])
+            PRECISIONS[self.precision], windows if use_edge else None)
         if not want_alpha:
             return out
         return out, self._attention_weights(alpha_tile, topo, edge_index)
@@ -373,7 +409,7 @@ class GATConv(nn.Module):
         dev = alpha_tile.device
         H = self.heads
         desc = GatDesc(topo.B, topo.N, self.in_channels, 0, H, self.out_channels, topo.R, int(self.concat),
-                       float(self.negative_slope), lib.spotv2_gat_ldp(H, self.out_channels), 0, 0, 0.0, 0, 0)
+                       float(self.negative_slope), lib.spotv2_gat_ldp(H, self.out_channels), 0, 0, 0.0, 0, 0, 0)
         n = topo.B * topo.N
         alpha = torch.empty(topo.B * topo.R + n, H, device=dev, dtype=torch.float32)
         check(lib.spotv2_alpha_to_pyg(C.byref(desc), ptr(alpha_tile), ptr(topo.table), ptr(alpha), stream_ptr(dev)),

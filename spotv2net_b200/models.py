@@ -71,6 +71,8 @@ class GATModel(nn.Module):
     def forward(self, data):
         x, edge_index, edge_attr = data.x, data.edge_index, data.edge_attr
         if self.standardize:
+            if edge_attr is None:
+                raise ValueError("standardize=True normalises edge_attr: collate with structured=False")
             x = self.bnorm_node(x)
             edge_attr = self.bnorm_edge(edge_attr)
         # one topology check per batch, shared by all layers (a batch produced by
@@ -80,12 +82,15 @@ class GATModel(nn.Module):
             topo = topology_from_edge_index(edge_index, x.shape[0], getattr(data, "nodes_per_graph", None))
         if self.collect_attention:
             self.attention_weights = []
+        # batches of a structured WindowDataset carry window references: the layers read the [L, N, N] windows instead of
+        # edge_attr (not with standardize=True: BatchNorm changes the edge features, which then must be materialised)
+        win = None if self.standardize else getattr(data, "spot_windows", None)
         for layer in self.gat_layers:
             if self.collect_attention:
-                x, att = layer(x, edge_index, edge_attr, return_attention_weights=True, topology=topo)
+                x, att = layer(x, edge_index, edge_attr, return_attention_weights=True, topology=topo, windows=win)
                 self.attention_weights.append(att)
             else:
-                x = layer(x, edge_index, edge_attr, topology=topo)
+                x = layer(x, edge_index, edge_attr, topology=topo, windows=win)
             x = self.a(x)
             if self.dropout:
                 x = F.dropout(x, p=self.dropout, training=self.training)

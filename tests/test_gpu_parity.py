@@ -327,12 +327,12 @@ def _attention_stage_case(cuda_lib, geom, bwd_algo):
         dv, dbias = torch.empty(H, Fe, device=DEV), torch.empty(ldo, device=DEV)
         dout_g = dout.to(DEV)
         check(cuda_lib.spotv2_gat_attn_bwd(C.byref(d), ptr(P_aug), None, ptr(ea), None, ptr(topo.table), ptr(v), ptr(dout_g),
-                                           ptr(dP), None, None, None, ptr(dv), ptr(dbias), ptr(ws), ws.numel(), st()), "attn_bwd")
+                                           ptr(dP), None, None, None, ptr(dv), None, ptr(dbias), ptr(ws), ws.numel(), st()), "attn_bwd")
         # same call with the edge terms the forward kept (no first pass over the edge rows): same results to rounding
         dP_t = torch.zeros(B * N, ldp, device=DEV)
         dv_t, dbias_t = torch.empty(H, Fe, device=DEV), torch.empty(ldo, device=DEV)
         check(cuda_lib.spotv2_gat_attn_bwd(C.byref(d), ptr(P_aug), None, ptr(ea), ptr(terms), ptr(topo.table), ptr(v), ptr(dout_g),
-                                           ptr(dP_t), None, None, None, ptr(dv_t), ptr(dbias_t), ptr(ws), ws.numel(), st()), "attn_bwd")
+                                           ptr(dP_t), None, None, None, ptr(dv_t), None, ptr(dbias_t), ptr(ws), ws.numel(), st()), "attn_bwd")
         assert relerr(dP_t[:, :H * C_ + 2 * H], dP[:, :H * C_ + 2 * H]) < 2e-6 and relerr(dv_t, dv) < 2e-6
         assert torch.equal(dbias_t, dbias)
         # the tensor-core operand form: the fp16 pair reproduces the fp32 gradient to ~2^-22 of each group's scale
@@ -340,7 +340,7 @@ def _attention_stage_case(cuda_lib, geom, bwd_algo):
         dP16 = torch.zeros(2, B * N, cuda_lib.spotv2_gat_ld16(n_aug), device=DEV, dtype=torch.float16)
         pblk = torch.zeros(8, device=DEV)
         check(cuda_lib.spotv2_gat_attn_bwd(C.byref(d), ptr(P_aug), None, ptr(ea), ptr(terms), ptr(topo.table), ptr(v), ptr(dout_g),
-                                           None, ptr(dP16[0]), ptr(dP16[1]), ptr(pblk), ptr(dv), ptr(dbias), ptr(ws),
+                                           None, ptr(dP16[0]), ptr(dP16[1]), ptr(pblk), ptr(dv), None, ptr(dbias), ptr(ws),
                                            ws.numel(), st()), "attn_bwd")
         got = pair_value(dP16, pblk, n_aug, H * C_)
         # (the pair run used the forward's edge terms, the fp32 run recomputed them: two roundings of the same logits)
@@ -746,6 +746,135 @@ def test_evaluation_loop_and_attention_export_match_the_oracle_model(cuda_lib):
         x, (ei_ref, a_ref) = layer(x, bt.edge_index, bt.edge_attr.double(), return_attention_weights=True)
         assert torch.equal(ei2.cpu(), ei_ref) and relerr(alpha, a_ref) < TOL
         x = torch.relu(x)
+
+
+@pytest.mark.parametrize("geom", [(6, 30, 42, 6, 500, False), (5, 30, 7, 8, 24, True), (4, 13, 3, 3, 10, False)],
+                         ids=["default", "H8_cat", "N13"])
+def test_structured_edge_source_layer_parity(cuda_lib, geom):
+    """a layer given the dataset's window references (spot_windows) reads the [L, N, N] co-volatility
+    windows instead of the materialised edge rows.  Same operator, so: outputs, attention coefficients and every
+    gradient against the fp64 edge-list oracle on the MATERIALISED batch, to the usual bar."""
+    B, N, L, H, C_, concat = geom
+    vol, vv = synth.synthetic_matrices(L + B + 3, N, seed=61)
+    ds = sv.WindowDataset(vol, vv, seq_length=L, device=DEV, drop_first=1, structured=True)
+    idx = list(range(B))
+    bt_s = ds.collate(idx)
+    assert bt_s.edge_attr is None and bt_s.spot_windows is not None
+    bt = synth.make_batch(vol, vv, [i + 1 for i in idx], L)
+    ref, ours = make_layers(N * L, C_, H, concat, 3 * L, 0.2, seed=N + L)
+    g = torch.Generator().manual_seed(2)
+    dout = torch.randn(B * N, H * C_ if concat else C_, generator=g)
+    r64, ei2 = oracle_pass(ref, bt, dout, torch.float64, True)
+    r32, _ = oracle_pass(ref, bt, dout, torch.float32, True)
+    xg = bt_s.x.detach().clone().requires_grad_(True)
+    out, (ei2g, alpha) = ours(xg, bt_s.edge_index, None, return_attention_weights=True, topology=bt_s.spot_topology,
+                              windows=bt_s.spot_windows)
+    out.backward(dout.to(DEV))
+    assert torch.equal(ei2g.cpu(), ei2)
+    mine = {"out": out.detach(), "alpha": alpha.detach(), "g_x": xg.grad}
+    mine.update({"g_" + k: p.grad for k, p in ours.named_parameters()})
+    bad = parity_failures(mine, r64, r32)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("geom", [(6, 30, 42, 6, 500, False), (5, 30, 7, 8, 24, True), (4, 13, 3, 3, 10, False), (3, 30, 4, 3, 20, False)],
+                         ids=["default", "H8_cat", "N13", "L4_H3"])
+def test_structured_edge_source_stages(cuda_lib, geom):
+    """The structured entry points against the generic ones on the same inputs: edge terms from the windows ==
+    edge terms the generic forward keeps; forward outputs; dP_aug; dv from the windows == dv from the edge rows."""
+    B, N, L, H, C_, concat = geom
+    Fin, Fe = 8, 3 * L
+    vol, vv = synth.synthetic_matrices(L + B + 2, N, seed=5)
+    bt = synth.make_batch(vol, vv, list(range(B)), L)
+    ref, _ = make_layers(Fin, C_, H, concat, Fe, 0.2, seed=9, wscale=2.0)
+    W, a_s, a_d, We, a_e, bias = [p.detach() for p in (ref.lin_src.weight, ref.att_src, ref.att_dst,
+                                                       ref.lin_edge.weight, ref.att_edge, ref.bias)]
+    x = torch.randn(B * N, Fin, dtype=torch.float64)
+    T = dense_gat.pyg_to_dense_tile(bt.edge_attr.double(), bt.edge_index, B, N)
+    fw = dense_gat.dense_forward(x, T, W, a_s, a_d, We, a_e, bias, H, C_, concat, 0.2)
+    ldp = cuda_lib.spotv2_gat_ldp(H, C_)
+    ldo = H * C_ if concat else C_
+    P_aug = torch.zeros(B * N, ldp, device=DEV)
+    P_aug[:, :H * C_ + 2 * H] = fw["P_aug"].float().to(DEV)
+    topo = sv.topology_from_edge_index(bt.edge_index.to(DEV), B * N)
+    ea, v, bg = bt.edge_attr.to(DEV), fw["v"].float().to(DEV).contiguous(), bias.float().to(DEV)
+    vv_g = torch.as_tensor(vv).float().to(DEV).contiguous()
+    t0 = torch.arange(B, dtype=torch.int32, device=DEV)
+    dout = torch.randn(B * N, ldo).to(DEV)
+    res = {}
+    for mode in (0, 1):
+        d = GatDesc(B, N, Fin, Fe, H, C_, N * (N - 1), int(concat), 0.2, ldp, 0, 0, 0.0, mode)
+        etb = C.c_size_t()
+        check(cuda_lib.spotv2_gat_edge_terms_bytes(C.byref(d), C.byref(etb)), "edge_terms_bytes")
+        terms = torch.full((etb.value // 4,), float("nan"), device=DEV)      # every byte the kernels read must be written
+        if mode == 1:
+            check(cuda_lib.spotv2_edge_terms_from_windows(C.byref(d), ptr(vv_g), vv_g.shape[0], L, ptr(t0), ptr(v), ptr(terms),
+                                                          st()), "edge_terms_from_windows")
+        out = torch.empty(B * N, ldo, device=DEV)
+        check(cuda_lib.spotv2_gat_attn_fwd(C.byref(d), ptr(P_aug), ptr(ea) if mode == 0 else None,
+                                           ptr(topo.table) if mode == 0 else None, ptr(v), ptr(bg), ptr(out), None, ptr(terms),
+                                           None, 0, st()), "attn_fwd")
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        check(cuda_lib.spotv2_gat_workspace_bytes(C.byref(d), C.byref(a), C.byref(b), C.byref(c)), "ws")
+        ws = torch.empty(b.value, dtype=torch.uint8, device=DEV)
+        dP = torch.full((B * N, ldp), float("nan"), device=DEV)
+        dv, dbias = torch.zeros(H, Fe, device=DEV), torch.empty(ldo, device=DEV)
+        d_terms = torch.full_like(terms, float("nan")) if mode == 1 else None
+        check(cuda_lib.spotv2_gat_attn_bwd(C.byref(d), ptr(P_aug), None, ptr(ea) if mode == 0 else None, ptr(terms),
+                                           ptr(topo.table) if mode == 0 else None, ptr(v), ptr(dout), ptr(dP), None, None, None,
+                                           ptr(dv) if mode == 0 else None, ptr(d_terms), ptr(dbias), ptr(ws), ws.numel(), st()),
+              "attn_bwd")
+        if mode == 1:
+            wsz = C.c_size_t()
+            check(cuda_lib.spotv2_windows_dv_workspace_bytes(C.byref(d), C.byref(wsz)), "windows_dv ws")
+            ws2 = torch.empty(wsz.value, dtype=torch.uint8, device=DEV)
+            check(cuda_lib.spotv2_windows_dv(C.byref(d), ptr(vv_g), vv_g.shape[0], L, ptr(t0), ptr(d_terms), ptr(dv), ptr(ws2),
+                                             wsz.value, st()), "windows_dv")
+        # the tensor-core operand form of the same gradient
+        n_aug_ = H * C_ + 2 * H
+        dP16 = torch.zeros(2, B * N, cuda_lib.spotv2_gat_ld16(n_aug_), device=DEV, dtype=torch.float16)
+        pblk = torch.zeros(8, device=DEV)
+        dv2 = torch.zeros(H, Fe, device=DEV)
+        check(cuda_lib.spotv2_gat_attn_bwd(C.byref(d), ptr(P_aug), None, ptr(ea) if mode == 0 else None, ptr(terms),
+                                           ptr(topo.table) if mode == 0 else None, ptr(v), ptr(dout), None, ptr(dP16[0]),
+                                           ptr(dP16[1]), ptr(pblk), ptr(dv2) if mode == 0 else None, ptr(d_terms), ptr(dbias),
+                                           ptr(ws), ws.numel(), st()), "attn_bwd")
+        got = pair_value(dP16, pblk, n_aug_, H * C_)
+        assert relerr(got[:, :H * C_], dP[:, :H * C_]) < 3e-6 and relerr(got[:, H * C_:], dP[:, H * C_:n_aug_]) < 3e-6, mode
+        torch.cuda.synchronize()
+        res[mode] = dict(terms=terms.view(B, H, N, 36)[..., :N].clone(), out=out, dP=dP, dv=dv, dbias=dbias)
+    off = ~torch.eye(N, dtype=torch.bool, device=DEV)
+    g_ref = fw["g"].permute(0, 3, 2, 1).float().to(DEV)              # [b, h, j, i]
+    for mode in (0, 1):
+        assert relerr(res[mode]["terms"][..., off], g_ref[..., off]) < TOL, mode
+    assert relerr(res[1]["out"], fw["out"]) < TOL
+    n_aug = H * C_ + 2 * H
+    assert relerr(res[1]["dP"][:, :n_aug], res[0]["dP"][:, :n_aug]) < 3e-6
+    assert relerr(res[1]["dv"], res[0]["dv"]) < 3e-6 and torch.equal(res[1]["dbias"], res[0]["dbias"])
+
+
+def test_structured_and_materialised_model_steps_agree(cuda_lib):
+    """GATModel on a structured batch (no edge_attr in HBM at all) vs the same batch with edge_attr materialised."""
+    N, L, B = 30, 5, 7
+    vol, vv = synth.synthetic_matrices(L + B + 2, N, seed=8)
+    kw = dict(num_node_features=N * L, num_edge_features=3 * L, num_heads=4, output_node_channels=1,
+              dim_hidden_layers=[16, 12], concat_heads=True)
+    torch.manual_seed(4)
+    model = sv.GATModel(**kw).to(DEV)
+    grads = []
+    for structured in (False, True):
+        ds = sv.WindowDataset(vol, vv, seq_length=L, device=DEV, drop_first=0, structured=structured)
+        bt = ds.collate(list(range(B)))
+        model.zero_grad()
+        loss = torch.nn.functional.mse_loss(model(bt), bt.y_x)
+        loss.backward()
+        grads.append((loss.item(), {k: p.grad.clone() for k, p in model.named_parameters()}))
+    assert abs(grads[0][0] - grads[1][0]) <= 1e-5 * abs(grads[0][0])
+    # layer-1 gradients are exact functions of the same activations; layer-0's pass through a ReLU (kinks): 1e-4
+    for k in grads[0][1]:
+        assert relerr(grads[1][1][k], grads[0][1][k]) < 1e-4, k
+    with pytest.raises(ValueError):
+        sv.GATModel(**dict(kw, standardize=True)).to(DEV)(ds.collate([0, 1]))      # BatchNorm needs the edge features
 
 
 # ------------------------------------------------------------------ full-size properties
