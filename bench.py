@@ -455,7 +455,9 @@ def run_e2e_windows(args, hp, dev, world, rank, barrier):
     This is the input path a user of this library's WindowDataset takes (reported as `e2e_windows`); the headline
     `e2e` leg (`run_e2e`) ships the already-expanded PyG tensors (x, edge_index, edge_attr: 83x the bytes) the
     way the reference's `data.to(device)` does."""
-    ds, layer, dout = hp.ds, hp.layer, hp.dout
+    # structured=True: the batches carry window references, edge_attr is never materialised in HBM (SURVEY 8f-2)
+    ds = hp.sv.WindowDataset(hp.ds.vol, hp.ds.volvol, seq_length=CFG["L"], device=dev, drop_first=0, structured=True)
+    layer, dout = hp.layer, hp.dout
     vol_h, vv_h = ds.vol.cpu().pin_memory(), ds.volvol.cpu().pin_memory()
     idx = torch.arange(hp.B)
     h2d = (vol_h.numel() + vv_h.numel()) * 4 + hp.B * 4        # both stacks + the window starts
@@ -466,7 +468,7 @@ def run_e2e_windows(args, hp, dev, world, rank, barrier):
         ds.volvol.copy_(vv_h, non_blocking=True)
         bt = ds.collate(idx)                                # window starts H2D + device-side gather
         layer.zero_grad(set_to_none=True)
-        out = layer(bt.x, bt.edge_index, bt.edge_attr, topology=bt.spot_topology)
+        out = layer(bt.x, bt.edge_index, bt.edge_attr, topology=bt.spot_topology, windows=bt.spot_windows)
         loss = (out * dout).sum()
         loss.backward()
         return loss.item()                                  # D2H read of the step's result
@@ -487,8 +489,9 @@ def run_e2e_windows(args, hp, dev, world, rank, barrier):
         ms = t.item()
     return {"value": world * hp.B / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
             "ms_per_step": ms, "steps": steps,
-            "api": "pinned host [T,N,N] vol / vol-of-vol stacks -> H2D -> spotv2net_b200.WindowDataset.collate (device) -> "
-                   "GATConv forward + autograd backward -> loss.item(); no overlap between steps"}
+            "api": "pinned host [T,N,N] vol / vol-of-vol stacks -> H2D -> spotv2net_b200.WindowDataset(structured=True).collate "
+                   "(device; edge_attr never materialised) -> GATConv forward + autograd backward on the window references -> "
+                   "loss.item(); no overlap between steps"}
 
 
 def run_e2e(args, hp, dev, world, rank, barrier):

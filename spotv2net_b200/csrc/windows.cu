@@ -18,12 +18,17 @@ namespace {
 
 constexpr int kWinThreads = 256;
 
-// pair index m = j*N + i (source j, target i) -> offset of vv[.][min][max] inside one N x N matrix
-__device__ __forceinline__ int pair_offset(int m, int N) {
-  const int j = m / N, i = m - j * N;
-  return j < i ? j * N + i : i * N + j;
+// Unordered pair u -> (r, c), r < c, row-major over the upper triangle (the order the reference enumerates edges in).
+__device__ __forceinline__ void upper_pair(int u, int N, int& r, int& c) {
+  int rr = 0, left = u;
+  while (left >= N - 1 - rr) { left -= N - 1 - rr; ++rr; }
+  r = rr;
+  c = rr + 1 + left;
 }
 
+// Edge terms of B graphs from their windows.  Per graph: the L x N diagonals go through shared memory (per-node sums
+// a_h[j], b_h[i]); one thread per unordered pair (r, c) contracts the L lags of vv[.][r][c] against v_h[0:L] for all
+// heads (loads of neighbouring threads are contiguous) and writes the two directed edges r -> c and c -> r.
 __global__ void __launch_bounds__(kWinThreads)
 win_edge_terms_kernel(const float* __restrict__ vv, const int32_t* __restrict__ t0, const float* __restrict__ v,
                       float* __restrict__ terms, int B, int N, int L, int H, int NS) {
@@ -31,72 +36,102 @@ win_edge_terms_kernel(const float* __restrict__ vv, const int32_t* __restrict__ 
   float* vs = smem;                       // [3L][8]: v_h[k] for k < 3L, heads padded to 8
   float* as = vs + 3 * L * 8;             // [8][N] source-node term
   float* bs = as + 8 * N;                 // [8][N] target-node term
-  const int tid = threadIdx.x, NN = N * N;
+  float* dg = bs + 8 * N;                 // [L][N] diagonals of the window
+  float* tl = dg + (L * N + 3) / 4 * 4;   // [H][N][NS] the graph's tile, written out with coalesced 16-byte stores
+  short* pr = reinterpret_cast<short*>(tl + H * N * NS);     // [NP] r, [NP] c
+  const int tid = threadIdx.x, NN = N * N, NP = N * (N - 1) / 2;
+  short* pc = pr + NP;
   for (int idx = tid; idx < 3 * L * 8; idx += kWinThreads) {
     const int k = idx >> 3, h = idx & 7;
     vs[idx] = h < H ? v[(size_t)h * 3 * L + k] : 0.f;
   }
+  for (int u = tid; u < NP; u += kWinThreads) {
+    int r, c;
+    upper_pair(u, N, r, c);
+    pr[u] = (short)r;
+    pc[u] = (short)c;
+  }
   __syncthreads();
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const float* W = vv + (size_t)t0[b] * NN;
-    for (int idx = tid; idx < 8 * N; idx += kWinThreads) {       // per-node sums over the matrices' diagonals
+    for (int idx = tid; idx < L * N; idx += kWinThreads) {
+      const int t = idx / N, j = idx - t * N;
+      dg[idx] = W[(size_t)t * NN + j * N + j];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 8 * N; idx += kWinThreads) {
       const int h = idx / N, j = idx - h * N;
       float a = 0.f, c = 0.f;
-      if (h < H)
-        for (int t = 0; t < L; ++t) {
-          const float dg = W[(size_t)t * NN + j * N + j];
-          a = fmaf(dg, vs[(L + t) * 8 + h], a);
-          c = fmaf(dg, vs[(2 * L + t) * 8 + h], c);
-        }
+      for (int t = 0; t < L; ++t) {
+        const float d = dg[t * N + j];
+        a = fmaf(d, vs[(L + t) * 8 + h], a);
+        c = fmaf(d, vs[(2 * L + t) * 8 + h], c);
+      }
       as[idx] = a;
       bs[idx] = c;
     }
     __syncthreads();
-    float* out = terms + (size_t)b * H * N * NS;
-    for (int m = tid; m < NN; m += kWinThreads) {
-      const int j = m / N, i = m - j * N;
+    // zero fill first: the diagonal and the padding columns i in [N, NS) must be zero (the attention kernels copy the
+    // whole tile into shared memory and their MMA fragments contract over all 32 target slots: alpha = 0 there is
+    // what masks the next graph's rows)
+    for (int idx = tid; idx < H * N * NS; idx += kWinThreads) tl[idx] = 0.f;
+    __syncthreads();
+    float* out = tl;
+    for (int u = tid; u < NP; u += kWinThreads) {
+      const int r = pr[u], c = pc[u];
+      const float* src = W + r * N + c;
       float g[8];
 #pragma unroll
       for (int h = 0; h < 8; ++h) g[h] = 0.f;
-      if (i != j) {
-        const float* src = W + pair_offset(m, N);
-#pragma unroll 6
-        for (int t = 0; t < L; ++t) {
-          const float x = src[(size_t)t * NN];
-          const float4 v0 = *reinterpret_cast<const float4*>(vs + t * 8);
-          const float4 v1 = *reinterpret_cast<const float4*>(vs + t * 8 + 4);
-          g[0] = fmaf(x, v0.x, g[0]); g[1] = fmaf(x, v0.y, g[1]); g[2] = fmaf(x, v0.z, g[2]); g[3] = fmaf(x, v0.w, g[3]);
-          g[4] = fmaf(x, v1.x, g[4]); g[5] = fmaf(x, v1.y, g[5]); g[6] = fmaf(x, v1.z, g[6]); g[7] = fmaf(x, v1.w, g[7]);
+      int t = 0;
+      for (; t + 6 <= L; t += 6) {                      // six independent loads in flight
+        float x[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) x[q] = src[(size_t)(t + q) * NN];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const float4 v0 = *reinterpret_cast<const float4*>(vs + (t + q) * 8);
+          const float4 v1 = *reinterpret_cast<const float4*>(vs + (t + q) * 8 + 4);
+          g[0] = fmaf(x[q], v0.x, g[0]); g[1] = fmaf(x[q], v0.y, g[1]); g[2] = fmaf(x[q], v0.z, g[2]); g[3] = fmaf(x[q], v0.w, g[3]);
+          g[4] = fmaf(x[q], v1.x, g[4]); g[5] = fmaf(x[q], v1.y, g[5]); g[6] = fmaf(x[q], v1.z, g[6]); g[7] = fmaf(x[q], v1.w, g[7]);
         }
+      }
+      for (; t < L; ++t) {
+        const float x = src[(size_t)t * NN];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) g[h] = fmaf(x, vs[t * 8 + h], g[h]);
       }
 #pragma unroll
       for (int h = 0; h < 8; ++h)
-        if (h < H) out[((size_t)h * N + j) * NS + i] = (i != j) ? g[h] + as[h * N + j] + bs[h * N + i] : 0.f;
+        if (h < H) {
+          out[((size_t)h * N + r) * NS + c] = g[h] + as[h * N + r] + bs[h * N + c];      // edge r -> c
+          out[((size_t)h * N + c) * NS + r] = g[h] + as[h * N + c] + bs[h * N + r];      // edge c -> r
+        }
     }
-    // the padding columns i in [N, NS) must be zero: the attention kernels copy the whole tile into shared memory and
-    // their MMA fragments contract over all 32 target slots (alpha = 0 there is what masks the next graph's rows)
-    for (int idx = tid; idx < H * N * (NS - N); idx += kWinThreads) {
-      const int hj = idx / (NS - N), i = N + idx - hj * (NS - N);
-      out[(size_t)hj * NS + i] = 0.f;
-    }
+    __syncthreads();
+    float4* gout = reinterpret_cast<float4*>(terms + (size_t)b * H * N * NS);
+    for (int idx = tid; idx < H * N * NS / 4; idx += kWinThreads) gout[idx] = reinterpret_cast<const float4*>(tl)[idx];
     __syncthreads();
   }
 }
 
-// dv[h][k] partials of this CTA's graphs.  dterms = dz' in the tile layout ([H][N][NS], diagonal 0).
+// dv[h][k] partials of this CTA's graphs.  dterms = dz' in the tile layout ([H][N][NS], diagonal 0).  The k = 0 block
+// contracts the symmetric sum dz'[r->c] + dz'[c->r] (kept at the upper-triangle slot, zero elsewhere) against whole
+// matrices, so every lag is a contiguous, coalesced read of N*N floats.
+template <int HT>      // heads rounded up to 2 | 4 | 6 | 8: the hot loop is unrolled over HT with no predicates (rows h >= H are zero)
 __global__ void __launch_bounds__(kWinThreads)
 win_dv_kernel(const float* __restrict__ vv, const int32_t* __restrict__ t0, const float* __restrict__ dterms,
               float* __restrict__ part, int B, int N, int L, int H, int NS) {
   extern __shared__ __align__(16) float smem[];
   const int NN = N * N;
-  float* dzs = smem;                       // [H][NN] compact, diagonal 0
-  float* rs = dzs + H * NN;                // [H][N] sum over targets  (feeds the source-variance features)
+  float* dzs = smem;                       // [HT][NN] compact, diagonal 0; then the symmetric sums (rows h >= H stay 0)
+  float* rs = dzs + HT * NN;               // [H][N] sum over targets  (feeds the source-variance features)
   float* cs = rs + H * N;                  // [H][N] sum over sources  (feeds the target-variance features)
   float* acc = cs + H * N;                 // [H][3L] this CTA's running dv
-  int* poff = reinterpret_cast<int*>(acc + H * 3 * L);          // [NN]
+  float* dg = acc + H * 3 * L;             // [L][N] diagonals of the window
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int idx = tid; idx < H * 3 * L; idx += kWinThreads) acc[idx] = 0.f;
-  for (int m = tid; m < NN; m += kWinThreads) poff[m] = pair_offset(m, N);
+  for (int idx = H * NN + tid; idx < HT * NN; idx += kWinThreads) dzs[idx] = 0.f;
   __syncthreads();
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const float* W = vv + (size_t)t0[b] * NN;
@@ -104,6 +139,10 @@ win_dv_kernel(const float* __restrict__ vv, const int32_t* __restrict__ t0, cons
     for (int idx = tid; idx < H * NN; idx += kWinThreads) {
       const int h = idx / NN, m = idx - h * NN, j = m / N, i = m - j * N;
       dzs[idx] = (i != j) ? src[((size_t)h * N + j) * NS + i] : 0.f;
+    }
+    for (int idx = tid; idx < L * N; idx += kWinThreads) {
+      const int t = idx / N, n = idx - t * N;
+      dg[idx] = W[(size_t)t * NN + n * N + n];
     }
     __syncthreads();
     for (int idx = tid; idx < 2 * H * N; idx += kWinThreads) {
@@ -114,33 +153,62 @@ win_dv_kernel(const float* __restrict__ vv, const int32_t* __restrict__ t0, cons
       (which == 0 ? rs : cs)[r] = s;
     }
     __syncthreads();
-    // k = 0 block: dv[h][t] += sum_m dz'[h][m] vv[t0+t][pair(m)]; one warp per lag, lanes over the pairs
-    for (int t = warp; t < L; t += kWinThreads / 32) {
-      const float* Wt = W + (size_t)t * NN;
-      float a[8];
-#pragma unroll
-      for (int h = 0; h < 8; ++h) a[h] = 0.f;
-      for (int m = lane; m < NN; m += 32) {
-        const float x = Wt[poff[m]];
-#pragma unroll
-        for (int h = 0; h < 8; ++h)
-          if (h < H) a[h] = fmaf(x, dzs[h * NN + m], a[h]);
+    for (int idx = tid; idx < H * NN; idx += kWinThreads) {     // one owner per unordered pair: no conflicts
+      const int h = idx / NN, m = idx - h * NN, j = m / N, i = m - j * N;
+      if (j < i) {
+        const int mt = h * NN + i * N + j;
+        dzs[idx] += dzs[mt];
+        dzs[mt] = 0.f;
       }
+    }
+    __syncthreads();
+    // k = 0 block: dv[h][t] += sum_m sym[h][m] vv[t0+t][m]; a warp takes three lags at a time (one shared-memory read
+    // of sym feeds three FMAs), lanes over the matrix, six independent global loads in flight per lane
+    for (int tb = 3 * warp; tb < L; tb += 3 * (kWinThreads / 32)) {
+      const float* W0 = W + (size_t)tb * NN;
+      const float* W1 = W + (size_t)min(tb + 1, L - 1) * NN;        // lags past L - 1 alias the last one and are not stored
+      const float* W2 = W + (size_t)min(tb + 2, L - 1) * NN;
+      float a[3][HT];
 #pragma unroll
-      for (int h = 0; h < 8; ++h) {
-        if (h < H) {
-          float s = a[h];
-          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          if (lane == 0) acc[h * 3 * L + t] += s;
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int h = 0; h < HT; ++h) a[q][h] = 0.f;
+      int m = lane;
+      for (; m + 32 < NN; m += 64) {
+        const float x00 = W0[m], x01 = W0[m + 32], x10 = W1[m], x11 = W1[m + 32], x20 = W2[m], x21 = W2[m + 32];
+#pragma unroll
+        for (int h = 0; h < HT; ++h) {
+          const float d0 = dzs[h * NN + m], d1 = dzs[h * NN + m + 32];
+          a[0][h] = fmaf(x00, d0, a[0][h]); a[0][h] = fmaf(x01, d1, a[0][h]);
+          a[1][h] = fmaf(x10, d0, a[1][h]); a[1][h] = fmaf(x11, d1, a[1][h]);
+          a[2][h] = fmaf(x20, d0, a[2][h]); a[2][h] = fmaf(x21, d1, a[2][h]);
         }
       }
+      for (; m < NN; m += 32) {
+        const float x0 = W0[m], x1 = W1[m], x2 = W2[m];
+#pragma unroll
+        for (int h = 0; h < HT; ++h) {
+          const float d0 = dzs[h * NN + m];
+          a[0][h] = fmaf(x0, d0, a[0][h]);
+          a[1][h] = fmaf(x1, d0, a[1][h]);
+          a[2][h] = fmaf(x2, d0, a[2][h]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int h = 0; h < HT; ++h) {
+          float sacc = a[q][h];
+          for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+          if (lane == 0 && h < H && tb + q < L) acc[h * 3 * L + tb + q] += sacc;
+        }
     }
     // k = 1, 2 blocks: the diagonals against the row / column sums
     for (int idx = tid; idx < 2 * H * L; idx += kWinThreads) {
       const int which = idx / (H * L), r = idx - which * H * L, h = r / L, t = r - h * L;
       const float* sums = (which == 0 ? rs : cs) + h * N;
       float s = 0.f;
-      for (int n = 0; n < N; ++n) s = fmaf(W[(size_t)t * NN + n * N + n], sums[n], s);
+      for (int n = 0; n < N; ++n) s = fmaf(dg[t * N + n], sums[n], s);
       acc[h * 3 * L + (1 + which) * L + t] += s;
     }
     __syncthreads();
@@ -156,9 +224,11 @@ int check_windows(const spotv2_gat_desc* d, int32_t T, int32_t L) {
   return SPOTV2_OK;
 }
 
-int win_grid(int B) {
-  const int g = 4 * sm_count();
-  return g < B ? g : B;
+int win_grid(int B) {           // at most 8 CTAs per SM, every CTA the same number of graphs (+-1 at most in the last ones)
+  const int g = 8 * sm_count();
+  if (B <= g) return B;
+  const int per = (B + g - 1) / g;
+  return (B + per - 1) / per;
 }
 
 }  // namespace
@@ -171,7 +241,9 @@ extern "C" int spotv2_edge_terms_from_windows(const spotv2_gat_desc* d, const fl
                                               const int32_t* t0, const float* v, float* edge_terms, void* stream) {
   if (int rc = check_windows(d, T, L)) return rc;
   SPOTV2_REQUIRE(M_vv && t0 && v && edge_terms, "edge_terms_from_windows: null pointer");
-  const size_t smem = ((size_t)3 * L * 8 + 16 * d->N) * sizeof(float);
+  const size_t smem = ((size_t)3 * L * 8 + 16 * d->N + (size_t)L * d->N + 4 + (size_t)d->H * d->N * kEdgeTermNS) * sizeof(float) +
+                      (size_t)d->N * (d->N - 1) * sizeof(short) + 16;
+  SPOTV2_CUDA_OK(cudaFuncSetAttribute(win_edge_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   win_edge_terms_kernel<<<win_grid(d->B), kWinThreads, smem, as_stream(stream)>>>(M_vv, t0, v, edge_terms, d->B, d->N, L,
                                                                                  d->H, kEdgeTermNS);
   SPOTV2_CUDA_OK(cudaGetLastError());
@@ -181,7 +253,7 @@ extern "C" int spotv2_edge_terms_from_windows(const spotv2_gat_desc* d, const fl
 extern "C" int spotv2_windows_dv_workspace_bytes(const spotv2_gat_desc* d, size_t* bytes) {
   if (int rc = check_desc(d)) return rc;
   SPOTV2_REQUIRE(bytes, "windows_dv_workspace_bytes: null pointer");
-  *bytes = round_up((size_t)4 * sm_count() * d->H * (d->Fe > 0 ? d->Fe : 1) * sizeof(float), 256);
+  *bytes = round_up((size_t)8 * sm_count() * d->H * (d->Fe > 0 ? d->Fe : 1) * sizeof(float), 256);
   return SPOTV2_OK;
 }
 
@@ -193,10 +265,20 @@ extern "C" int spotv2_windows_dv(const spotv2_gat_desc* d, const float* M_vv, in
   const size_t need = (size_t)grid * d->H * d->Fe * sizeof(float);
   if (!ws || ws_bytes < need) return fail(SPOTV2_ERR_WORKSPACE, "windows_dv needs %zu B of workspace, got %zu", need, ws_bytes);
   const int NN = d->N * d->N;
-  const size_t smem = ((size_t)d->H * NN + 2 * (size_t)d->H * d->N + (size_t)d->H * d->Fe + NN) * sizeof(float);
-  SPOTV2_CUDA_OK(cudaFuncSetAttribute(win_dv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  win_dv_kernel<<<grid, kWinThreads, smem, as_stream(stream)>>>(M_vv, t0, d_edge_terms, static_cast<float*>(ws), d->B, d->N, L,
-                                                               d->H, kEdgeTermNS);
-  SPOTV2_CUDA_OK(cudaGetLastError());
+  const int HT = (d->H + 1) / 2 * 2;
+  const size_t smem = ((size_t)HT * NN + 2 * (size_t)d->H * d->N + (size_t)d->H * d->Fe + (size_t)L * d->N) * sizeof(float);
+  auto launch = [&](auto kern) -> int {
+    SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kWinThreads, smem, as_stream(stream)>>>(M_vv, t0, d_edge_terms, static_cast<float*>(ws), d->B, d->N, L, d->H,
+                                                        kEdgeTermNS);
+    SPOTV2_CUDA_OK(cudaGetLastError());
+    return SPOTV2_OK;
+  };
+  int rc;
+  if (HT <= 2) rc = launch(win_dv_kernel<2>);
+  else if (HT <= 4) rc = launch(win_dv_kernel<4>);
+  else if (HT <= 6) rc = launch(win_dv_kernel<6>);
+  else rc = launch(win_dv_kernel<8>);
+  if (rc) return rc;
   return reduce_partials(static_cast<float*>(ws), grid, d->H * d->Fe, dv, as_stream(stream));
 }
