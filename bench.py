@@ -286,8 +286,7 @@ def run_ours(args):
     hp = HotPath(B, dev, seed=1234 + rank)
 
     def allreduce(t):
-        dist.all_reduce(t)
-        t.mul_(1.0 / world)
+        dist.all_reduce(t, op=dist.ReduceOp.AVG)         # the 1/world scaling rides inside the collective
     ar = allreduce if world > 1 else None
 
     def barrier():

@@ -30,7 +30,7 @@ constexpr int kGroupA = 96;           // 3 logit/softmax warps (48-row edge chun
 constexpr int kGroupB = 256;          // 8 MMA warps
 constexpr int kFwdThreads = kGroupA + kGroupB + 32;
 constexpr int kFwdChunkRows3 = 48;    // edge rows per ring stage: one m16 tile per group-A warp
-constexpr int kPSlots = 16;           // P-tile ring depth
+constexpr int kPSlots = 24;           // P-tile ring depth
 constexpr int kPTileBytes = 32 * 128; // 32 source rows x 32 channels fp32, 128B-swizzled
 constexpr int kCbPerPass = 8;         // channel blocks per pass: one per MMA warp
 
