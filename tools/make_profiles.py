@@ -24,7 +24,7 @@ for n, t in step:
     agg[k][1] += t * scale
 tot = sum(v[1] for v in agg.values())
 with open(f"{out}/{tag}_launch_list_summary.txt", "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-structured\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-structured --no-graph\n")
     f.write("# launches of the LAST step (cold-cache, serialised: the SHARE is what carries over to the bench)\n")
     f.write(f"# {len(step)} launches, {tot:.3f} ms\n")
     for k, (c, t) in agg.items():
@@ -45,7 +45,7 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 traffic = {}
 with open(f"{out}/{tag}_ncu_hot_kernels.txt", "w") as f:
-    f.write("# ncu --set full --clock-control none (one launch each, warm-up skipped), python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-structured\n")
+    f.write("# ncu --set full --clock-control none (one launch each, warm-up skipped), python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-structured --no-graph\n")
     for rep in ("fwd_full", "bwd2_full", "gemm_full"):
         path = f"gpurun_out/{rep}.ncu-rep"
         if not os.path.exists(path):
