@@ -191,6 +191,9 @@ class HotPath:
         wdv = C.c_size_t()
         _lib.check(self.lib.spotv2_windows_dv_workspace_bytes(C.byref(self.desc), C.byref(wdv)), "windows_dv ws")
         self.ws_dv = torch.empty(wdv.value, device=device, dtype=torch.uint8) if structured else None
+        wet = C.c_size_t()
+        _lib.check(self.lib.spotv2_edge_terms_from_windows_workspace_bytes(C.byref(self.desc), C.byref(wet)), "edge_terms ws")
+        self.ws_w = torch.empty(wet.value, device=device, dtype=torch.uint8) if (structured and wet.value) else None
         self.out = torch.empty(n, Cc, **f32)
         self.dout = torch.randn(n, Cc, generator=g, **f32)
         self.tc = bool(self.lib.spotv2_gat_uses_tensor_cores(C.byref(self.desc)))
@@ -243,7 +246,8 @@ class HotPath:
         win = self.batch.spot_windows
         if self.structured:      # structured edge source: the [L,N,N] windows instead of the materialised edge rows
             chk(lib.spotv2_edge_terms_from_windows(d, p(win.volvol), win.volvol.shape[0], win.L, p(win.t0), p(self.v),
-                                                   p(self.edge_terms), st), "edge_terms_from_windows")
+                                                   p(self.edge_terms), p(self.ws_w), self.ws_w.numel() if self.ws_w is not None else 0,
+                                                   st), "edge_terms_from_windows")
             mark("edge_terms")
         ea = None if self.structured else self.batch.edge_attr
         tbl = None if self.structured else self.batch.spot_topology.table
@@ -398,7 +402,7 @@ def run_ours(args):
             graph_info = {"value": None, "error": repr(ex)[:300]}
             torch.cuda.synchronize(dev)
     structured = None
-    if args.config == "A" and not args.no_structured:
+    if not args.no_structured:
         try:
             structured = run_structured(args, dev, world, rank, barrier)
         except Exception as ex:

@@ -82,7 +82,7 @@ typedef struct spotv2_gat_desc {
   int32_t edge_mode;      /* 0: edge features arrive as rows (edge_rows [B, R, Fe]); the default and the reference
                              contract.  1: structured source - the caller computed the edge terms itself
                              (spotv2_edge_terms_from_windows) and passes them as edge_terms; edge_rows and table are
-                             ignored, and attn_bwd returns d(edge terms) instead of dv (N <= 32 only)           */
+                             ignored, and attn_bwd returns d(edge terms) instead of dv                          */
   uint32_t dropout_seed_lo, dropout_seed_hi;   /* Philox4x32-10 key of the mask; element (b,h,i,j)
                              uses counter ((((b*H+h)*N+i)*N+j) >> 2), lane (.. & 3); pass
                              the same key to attn_fwd and attn_bwd of one step              */
@@ -189,8 +189,10 @@ int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug, const floa
  * (2.9x fewer bytes, 3x fewer multiply-adds); use them with desc.edge_mode = 1:
  *   edge_terms_from_windows -> attn_fwd(edge_terms) ... attn_bwd(edge_terms, d_edge_terms_out) -> windows_dv -> dv.
  * M_vv [T, N, N] fp32 on the device, t0 [B] int32 window starts, v [H, 3L] from spotv2_gat_fold. */
+int spotv2_edge_terms_from_windows_workspace_bytes(const spotv2_gat_desc* d, size_t* bytes);   /* 0 for N <= 32 */
 int spotv2_edge_terms_from_windows(const spotv2_gat_desc* d, const float* M_vv, int32_t T, int32_t L,
-                                   const int32_t* t0, const float* v, float* edge_terms, void* stream);
+                                   const int32_t* t0, const float* v, float* edge_terms, void* ws, size_t ws_bytes,
+                                   void* stream);
 int spotv2_windows_dv_workspace_bytes(const spotv2_gat_desc* d, size_t* bytes);
 int spotv2_windows_dv(const spotv2_gat_desc* d, const float* M_vv, int32_t T, int32_t L, const int32_t* t0,
                       const float* d_edge_terms, float* dv, void* ws, size_t ws_bytes, void* stream);

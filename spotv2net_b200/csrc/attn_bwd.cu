@@ -646,8 +646,8 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
                  "attn_bwd: edge_rows, table and v are required when Fe > 0");
   SPOTV2_REQUIRE(!structured || (edge_terms_or_null && d_edge_terms_or_null && aligned16(d_edge_terms_or_null)),
                  "attn_bwd: edge_mode 1 needs edge_terms and a 16-byte aligned d_edge_terms buffer");
-  if (structured && (d->N > 32 || d->attn_bwd_algo == 1 || d->dropout_p > 0.f))
-    return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd: edge_mode 1 runs on the pipelined kernel only (N <= 32, no attention dropout)");
+  if (structured && d->N <= 32 && (d->attn_bwd_algo == 1 || d->dropout_p > 0.f))
+    return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd: for N <= 32, edge_mode 1 runs on the pipelined kernel only (no attention dropout)");
   SPOTV2_REQUIRE(aligned16(P_aug) && aligned16(dout) && (f16 || aligned16(dP_aug_or_null)) &&
                      (!f16 || (aligned16(dP_hi_or_null) && aligned16(dP_lo_or_null))),
                  "attn_bwd: P_aug/dout/dP must be 16-byte aligned");

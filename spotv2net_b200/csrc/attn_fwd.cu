@@ -522,7 +522,6 @@ extern "C" int spotv2_gat_attn_fwd(const spotv2_gat_desc* d, const float* P_aug,
   SPOTV2_REQUIRE(d->Fe == 0 || structured || (edge_rows && table && v),
                  "attn_fwd: edge_rows, table and v are required when Fe > 0");
   SPOTV2_REQUIRE(!structured || edge_terms_or_null, "attn_fwd: edge_mode 1 needs edge_terms (spotv2_edge_terms_from_windows)");
-  if (structured && d->N > 32) return fail(SPOTV2_ERR_UNSUPPORTED, "attn_fwd: edge_mode 1 covers N <= 32");
   SPOTV2_REQUIRE(aligned16(P_aug) && aligned16(out), "attn_fwd: P_aug/out must be 16-byte aligned");
   if (d->H > kMaxHeads) return fail(SPOTV2_ERR_UNSUPPORTED, "H=%d > %d", d->H, kMaxHeads);
   if (d->Fe > kMaxFe) return fail(SPOTV2_ERR_UNSUPPORTED, "Fe=%d > %d", d->Fe, kMaxFe);

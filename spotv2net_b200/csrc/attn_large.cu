@@ -18,6 +18,8 @@
 //   ds = row sums;  dv = sum_r (dz + fill)_r e_r over a second pass of the edge rows;  dP_h = g alpha_h dO_h
 //   (batched GEMM);  dbias = column sums of dout.
 // Every reduction has a fixed order (per-CTA partials summed by index), so results are reproducible.
+#include <algorithm>
+
 #include "attn_bwd.cuh"
 
 namespace spotv2 {
@@ -264,6 +266,16 @@ lg_rowsum_kernel(const float* __restrict__ dZ, float* dP_aug, int B, int N, int 
   if (lane == 0) dP_aug[((size_t)b * N + j) * ldp + HC + h] = s;
 }
 
+// d(edge terms) for the structured source: w[b][h][j][i] = dz[b][h][j][i] + fill[b][h][i] off the diagonal, 0 on it.
+__global__ void __launch_bounds__(256)
+lg_dterms_kernel(const float* __restrict__ dZ, const float* __restrict__ fill, float* __restrict__ out, size_t total, int N) {
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = idx / N;                 // (b*H + h)*N + j
+    const int i = (int)(idx - row * N), j = (int)(row % N);
+    out[idx] = (i != j) ? dZ[idx] + fill[(row / N) * N + i] : 0.f;
+  }
+}
+
 struct LgDvArgs {
   LgRing rg;
   const int32_t* table;
@@ -507,7 +519,7 @@ int attn_large_fwd(const AttnParams& p, const float* bias, float* out, float* al
   }
   const LgPlan pl = lg_plan(p);
   float* Zraw = p.edge_terms ? p.edge_terms : A;       // kept for the backward when the caller provides the buffer
-  if (p.Fe > 0) {
+  if (p.Fe > 0 && !p.terms_in) {          // terms_in: the caller computed the edge terms (structured source)
     if (pl.smem_logit > 227 * 1024) return fail(SPOTV2_ERR_UNSUPPORTED, "attn_fwd (large N): Fe=%d needs %zu B shared memory", p.Fe, pl.smem_logit);
     if (int rc = lg_logits(p, pl, Zraw, st)) return rc;
   }
@@ -581,7 +593,14 @@ int attn_large_bwd(const spotv2_gat_desc* d, AttnBwdArgs& a, float* dv, float* d
     lg_rowsum_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(dA, dP, p.B, p.N, p.H, HC, p.ldp);
     SPOTV2_CUDA_OK(cudaGetLastError());
   }
-  if (p.Fe > 0 && dv) {
+  if (p.Fe > 0 && p.dterms_out) {
+    // structured source: the gradient w.r.t. the edge terms leaves as w[b][h][j][i] = dz + fill[b][h][i] (0 on the
+    // diagonal); dv is formed from the windows by spotv2_windows_dv
+    const size_t total = (size_t)p.B * p.H * p.N * p.N;
+    lg_dterms_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, (size_t)32 * sm_count()), 256, 0, st>>>(dA, fill, p.dterms_out,
+                                                                                                            total, p.N);
+    SPOTV2_CUDA_OK(cudaGetLastError());
+  } else if (p.Fe > 0 && dv) {
     LgDvArgs v;
     v.rg = lg_ring(p, pl);
     v.table = p.table; v.dZ = dA; v.fill = fill; v.part = dv_part; v.N = p.N; v.H = p.H;

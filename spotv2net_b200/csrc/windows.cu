@@ -216,10 +216,200 @@ win_dv_kernel(const float* __restrict__ vv, const int32_t* __restrict__ t0, cons
   for (int idx = tid; idx < H * 3 * L; idx += kWinThreads) part[(size_t)blockIdx.x * H * 3 * L + idx] = acc[idx];
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Large universes (N > 32): the edge-term tile is Z[b][h][j][i] with row stride N (the layout of attn_large.cu).
+
+// Per-node sums over the windows' diagonals: ab[b][0][h][n] = sum_t vv[t0+t][n][n] v_h[L+t]  (source-variance features),
+// ab[b][1][h][n] = sum_t vv[t0+t][n][n] v_h[2L+t]  (target-variance features).  8 head slots per (b, k).
+__global__ void __launch_bounds__(256)
+win_node_terms_kernel(const float* __restrict__ vv, const int32_t* __restrict__ t0, const float* __restrict__ v,
+                      float* __restrict__ ab, int N, int L, int H) {
+  extern __shared__ __align__(16) float vs[];            // [2L][8]: v_h[L + k], k < 2L
+  for (int idx = threadIdx.x; idx < 2 * L * 8; idx += blockDim.x) {
+    const int k = idx >> 3, h = idx & 7;
+    vs[idx] = h < H ? v[(size_t)h * 3 * L + L + k] : 0.f;
+  }
+  __syncthreads();
+  const int b = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* W = vv + (size_t)t0[b] * N * N + (size_t)n * N + n;
+  float a[8], c[8];
+#pragma unroll
+  for (int h = 0; h < 8; ++h) a[h] = c[h] = 0.f;
+  for (int t = 0; t < L; ++t) {
+    const float d = W[(size_t)t * N * N];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      a[h] = fmaf(d, vs[t * 8 + h], a[h]);
+      c[h] = fmaf(d, vs[(L + t) * 8 + h], c[h]);
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 8; ++h) {
+    ab[(((size_t)b * 2 + 0) * 8 + h) * N + n] = a[h];
+    ab[(((size_t)b * 2 + 1) * 8 + h) * N + n] = c[h];
+  }
+}
+
+// Edge terms of the unordered pairs (r, c), r < c, of one graph: block = 32 columns c x 8 rows r.
+__global__ void __launch_bounds__(256)
+win_edge_terms_large_kernel(const float* __restrict__ vv, const int32_t* __restrict__ t0, const float* __restrict__ v,
+                            const float* __restrict__ ab, float* __restrict__ Z, int N, int L, int H) {
+  extern __shared__ __align__(16) float vs[];            // [L][8]: v_h[t]
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int idx = tid; idx < L * 8; idx += 256) {
+    const int k = idx >> 3, h = idx & 7;
+    vs[idx] = h < H ? v[(size_t)h * 3 * L + k] : 0.f;
+  }
+  __syncthreads();
+  const int b = blockIdx.z, c = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 8 + threadIdx.y;
+  if (blockIdx.x * 32 + 31 <= blockIdx.y * 8) return;     // whole block on or below the diagonal
+  if (c >= N || r >= c) return;
+  const size_t NN = (size_t)N * N;
+  const float* src = vv + (size_t)t0[b] * NN + (size_t)r * N + c;
+  float g[8];
+#pragma unroll
+  for (int h = 0; h < 8; ++h) g[h] = 0.f;
+  int t = 0;
+  for (; t + 6 <= L; t += 6) {
+    float x[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) x[q] = src[(size_t)(t + q) * NN];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const float4 v0 = *reinterpret_cast<const float4*>(vs + (t + q) * 8);
+      const float4 v1 = *reinterpret_cast<const float4*>(vs + (t + q) * 8 + 4);
+      g[0] = fmaf(x[q], v0.x, g[0]); g[1] = fmaf(x[q], v0.y, g[1]); g[2] = fmaf(x[q], v0.z, g[2]); g[3] = fmaf(x[q], v0.w, g[3]);
+      g[4] = fmaf(x[q], v1.x, g[4]); g[5] = fmaf(x[q], v1.y, g[5]); g[6] = fmaf(x[q], v1.z, g[6]); g[7] = fmaf(x[q], v1.w, g[7]);
+    }
+  }
+  for (; t < L; ++t) {
+    const float x = src[(size_t)t * NN];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) g[h] = fmaf(x, vs[t * 8 + h], g[h]);
+  }
+  const float* a = ab + (size_t)b * 2 * 8 * N;             // [2][8][N]
+  float* Zb = Z + (size_t)b * H * NN;
+#pragma unroll
+  for (int h = 0; h < 8; ++h)
+    if (h < H) {
+      Zb[(size_t)h * NN + (size_t)r * N + c] = g[h] + a[h * N + r] + a[(8 + h) * N + c];      // edge r -> c (source r, target c)
+      Zb[(size_t)h * NN + (size_t)c * N + r] = g[h] + a[h * N + c] + a[(8 + h) * N + r];      // edge c -> r
+    }
+}
+
+// dv from the windows, large universes.  Work item = (graph, 8 rows r, 256 columns c); a thread keeps the symmetric sums
+// s[h] = w[h][r][c] + w[h][c][r] of its 8 pairs (w = d(edge terms)) in registers, then for every lag adds s . vv[t][r][c]
+// and the CTA reduces the 8 head sums in a fixed order into its running dv.  Persistent CTAs, one partial each.
+__global__ void __launch_bounds__(256)
+win_dv_large_kernel(const float* __restrict__ vv, const int32_t* __restrict__ t0, const float* __restrict__ dterms,
+                    float* __restrict__ part, int B, int N, int L, int H) {
+  extern __shared__ __align__(16) float smem[];
+  float* acc = smem;                        // [H][L]
+  float* red = acc + H * L;                 // [8 warps][8 heads]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t NN = (size_t)N * N;
+  const int rblocks = (N + 7) / 8, cchunks = (N + 255) / 256;
+  const long long items = (long long)B * rblocks * cchunks;
+  for (int idx = tid; idx < H * L; idx += 256) acc[idx] = 0.f;
+  __syncthreads();
+  for (long long q = blockIdx.x; q < items; q += gridDim.x) {
+    const int cc = (int)(q % cchunks);
+    const long long q2 = q / cchunks;
+    const int rb = (int)(q2 % rblocks), b = (int)(q2 / rblocks);
+    const int r0 = rb * 8, c = cc * 256 + tid;
+    if (cc * 256 + 255 <= r0) continue;                   // whole item on or below the diagonal (CTA-uniform)
+    const float* Wb = vv + (size_t)t0[b] * NN;
+    const float* wb = dterms + (size_t)b * H * NN;
+    float s[8][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = r0 + k;
+      const bool ok = c < N && r < N && r < c;
+#pragma unroll
+      for (int h = 0; h < 8; ++h)
+        s[k][h] = (ok && h < H) ? wb[(size_t)h * NN + (size_t)r * N + c] + wb[(size_t)h * NN + (size_t)c * N + r] : 0.f;
+    }
+    for (int t = 0; t < L; ++t) {
+      float a[8];
+#pragma unroll
+      for (int h = 0; h < 8; ++h) a[h] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = r0 + k;
+        const float x = (c < N && r < c) ? Wb[(size_t)t * NN + (size_t)r * N + c] : 0.f;
+#pragma unroll
+        for (int h = 0; h < 8; ++h) a[h] = fmaf(x, s[k][h], a[h]);
+      }
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        float sv = a[h];
+        for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        if (lane == 0) red[warp * 8 + h] = sv;
+      }
+      __syncthreads();
+      if (tid < H) {
+        float sv = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sv += red[w * 8 + tid];
+        acc[tid * L + t] += sv;
+      }
+      __syncthreads();
+    }
+  }
+  for (int idx = tid; idx < H * L; idx += 256) part[(size_t)blockIdx.x * H * L + idx] = acc[idx];
+}
+
+// Row sums rs[b][h][j] = sum_i w[h][j][i] and column sums cs[b][h][i] = sum_j w[h][j][i] of d(edge terms) (diagonal 0).
+__global__ void __launch_bounds__(256)
+win_rowcol_sums_kernel(const float* __restrict__ dterms, float* __restrict__ rs, float* __restrict__ cs, int N, int H) {
+  const int bh = blockIdx.y;                               // b * H + h
+  const float* w = dterms + (size_t)bh * N * N;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float c = 0.f;
+  for (int j = 0; j < N; ++j) c += w[(size_t)j * N + n];   // coalesced over n
+  cs[(size_t)bh * N + n] = c;
+  float r = 0.f;
+  for (int i = 0; i < N; ++i) r += w[(size_t)n * N + i];   // each thread walks its own row (L2-resident after the pass above)
+  rs[(size_t)bh * N + n] = r;
+}
+
+// dv[h][L + t] += sum_j diag_t[j] rs[h][j];  dv[h][2L + t] += sum_i diag_t[i] cs[h][i].  One CTA per graph, thread = (h, t, k);
+// partial per graph.
+__global__ void __launch_bounds__(256)
+win_dv_diag_kernel(const float* __restrict__ vv, const int32_t* __restrict__ t0, const float* __restrict__ rs,
+                   const float* __restrict__ cs, float* __restrict__ part, int N, int L, int H) {
+  const int b = blockIdx.x;
+  const float* W = vv + (size_t)t0[b] * N * N;
+  for (int idx = threadIdx.x; idx < 2 * H * L; idx += blockDim.x) {
+    const int k = idx / (H * L), r = idx - k * H * L, h = r / L, t = r - h * L;
+    const float* sums = (k == 0 ? rs : cs) + ((size_t)b * H + h) * N;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s = fmaf(W[(size_t)t * N * N + (size_t)n * N + n], sums[n], s);
+    part[(size_t)b * 2 * H * L + idx] = s;
+  }
+}
+
+// dv[h][k] (k < 3L) from the two partial sets, fixed order.
+__global__ void win_dv_finish_kernel(const float* __restrict__ part0, int n0, const float* __restrict__ partd, int B, int L, int H,
+                                     float* __restrict__ dv) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * 3 * L) return;
+  const int h = idx / (3 * L), k = idx - h * 3 * L;
+  float s = 0.f;
+  if (k < L) {
+    for (int c = 0; c < n0; ++c) s += part0[(size_t)c * H * L + h * L + k];
+  } else {
+    const int which = (k - L) / L, t = (k - L) - which * L;
+    for (int b = 0; b < B; ++b) s += partd[(size_t)b * 2 * H * L + (size_t)which * H * L + h * L + t];
+  }
+  dv[idx] = s;
+}
+
 int check_windows(const spotv2_gat_desc* d, int32_t T, int32_t L) {
   if (int rc = check_desc(d)) return rc;
   SPOTV2_REQUIRE(L > 0 && T > L && d->Fe == 3 * L, "windows: edge_dim must equal 3 * seq_length (got Fe=%d, L=%d)", d->Fe, L);
-  if (d->N > 32) return fail(SPOTV2_ERR_UNSUPPORTED, "windows: the structured edge source covers N <= 32 in this version");
   if (d->H > kMaxHeads) return fail(SPOTV2_ERR_UNSUPPORTED, "H=%d > %d", d->H, kMaxHeads);
   return SPOTV2_OK;
 }
@@ -237,23 +427,51 @@ int win_grid(int B) {           // at most 8 CTAs per SM, every CTA the same num
 
 using namespace spotv2;
 
+extern "C" int spotv2_edge_terms_from_windows_workspace_bytes(const spotv2_gat_desc* d, size_t* bytes) {
+  if (int rc = check_desc(d)) return rc;
+  SPOTV2_REQUIRE(bytes, "edge_terms_from_windows_workspace_bytes: null pointer");
+  *bytes = d->N > 32 ? round_up((size_t)d->B * 2 * 8 * d->N * sizeof(float), 256) : 0;      // per-node sums
+  return SPOTV2_OK;
+}
+
 extern "C" int spotv2_edge_terms_from_windows(const spotv2_gat_desc* d, const float* M_vv, int32_t T, int32_t L,
-                                              const int32_t* t0, const float* v, float* edge_terms, void* stream) {
+                                              const int32_t* t0, const float* v, float* edge_terms, void* ws, size_t ws_bytes,
+                                              void* stream) {
   if (int rc = check_windows(d, T, L)) return rc;
   SPOTV2_REQUIRE(M_vv && t0 && v && edge_terms, "edge_terms_from_windows: null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (d->N > 32) {
+    const size_t need = (size_t)d->B * 2 * 8 * d->N * sizeof(float);
+    if (!ws || ws_bytes < need) return fail(SPOTV2_ERR_WORKSPACE, "edge_terms_from_windows needs %zu B of workspace, got %zu", need, ws_bytes);
+    float* ab = static_cast<float*>(ws);
+    win_node_terms_kernel<<<dim3((d->N + 255) / 256, d->B), 256, (size_t)2 * L * 8 * sizeof(float), st>>>(M_vv, t0, v, ab, d->N, L, d->H);
+    SPOTV2_CUDA_OK(cudaGetLastError());
+    dim3 grid((d->N + 31) / 32, (d->N + 7) / 8, d->B);
+    win_edge_terms_large_kernel<<<grid, dim3(32, 8), (size_t)L * 8 * sizeof(float), st>>>(M_vv, t0, v, ab, edge_terms, d->N, L, d->H);
+    SPOTV2_CUDA_OK(cudaGetLastError());
+    return SPOTV2_OK;
+  }
   const size_t smem = ((size_t)3 * L * 8 + 16 * d->N + (size_t)L * d->N + 4 + (size_t)d->H * d->N * kEdgeTermNS) * sizeof(float) +
                       (size_t)d->N * (d->N - 1) * sizeof(short) + 16;
   SPOTV2_CUDA_OK(cudaFuncSetAttribute(win_edge_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  win_edge_terms_kernel<<<win_grid(d->B), kWinThreads, smem, as_stream(stream)>>>(M_vv, t0, v, edge_terms, d->B, d->N, L,
-                                                                                 d->H, kEdgeTermNS);
+  win_edge_terms_kernel<<<win_grid(d->B), kWinThreads, smem, st>>>(M_vv, t0, v, edge_terms, d->B, d->N, L, d->H, kEdgeTermNS);
   SPOTV2_CUDA_OK(cudaGetLastError());
   return SPOTV2_OK;
 }
 
+static int dv_large_grid() { return 2 * sm_count(); }
+
 extern "C" int spotv2_windows_dv_workspace_bytes(const spotv2_gat_desc* d, size_t* bytes) {
   if (int rc = check_desc(d)) return rc;
   SPOTV2_REQUIRE(bytes, "windows_dv_workspace_bytes: null pointer");
-  *bytes = round_up((size_t)8 * sm_count() * d->H * (d->Fe > 0 ? d->Fe : 1) * sizeof(float), 256);
+  if (d->N > 32) {
+    const size_t L = (size_t)(d->Fe > 0 ? d->Fe / 3 : 1);
+    *bytes = round_up((size_t)dv_large_grid() * d->H * L * sizeof(float), 256) +              // pair partials
+             2 * round_up((size_t)d->B * d->H * d->N * sizeof(float), 256) +                   // row / column sums
+             round_up((size_t)d->B * 2 * d->H * L * sizeof(float), 256);                       // diagonal partials
+  } else {
+    *bytes = round_up((size_t)8 * sm_count() * d->H * (d->Fe > 0 ? d->Fe : 1) * sizeof(float), 256);
+  }
   return SPOTV2_OK;
 }
 
@@ -261,6 +479,27 @@ extern "C" int spotv2_windows_dv(const spotv2_gat_desc* d, const float* M_vv, in
                                  const float* d_edge_terms, float* dv, void* ws, size_t ws_bytes, void* stream) {
   if (int rc = check_windows(d, T, L)) return rc;
   SPOTV2_REQUIRE(M_vv && t0 && d_edge_terms && dv, "windows_dv: null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (d->N > 32) {
+    size_t need = 0;
+    spotv2_windows_dv_workspace_bytes(d, &need);
+    if (!ws || ws_bytes < need) return fail(SPOTV2_ERR_WORKSPACE, "windows_dv needs %zu B of workspace, got %zu", need, ws_bytes);
+    unsigned char* w = static_cast<unsigned char*>(ws);
+    const int grid = dv_large_grid();
+    float* part0 = reinterpret_cast<float*>(w); w += round_up((size_t)grid * d->H * L * sizeof(float), 256);
+    float* rs = reinterpret_cast<float*>(w);    w += round_up((size_t)d->B * d->H * d->N * sizeof(float), 256);
+    float* cs = reinterpret_cast<float*>(w);    w += round_up((size_t)d->B * d->H * d->N * sizeof(float), 256);
+    float* partd = reinterpret_cast<float*>(w);
+    win_dv_large_kernel<<<grid, 256, ((size_t)d->H * L + 64) * sizeof(float), st>>>(M_vv, t0, d_edge_terms, part0, d->B, d->N, L, d->H);
+    SPOTV2_CUDA_OK(cudaGetLastError());
+    win_rowcol_sums_kernel<<<dim3((d->N + 255) / 256, d->B * d->H), 256, 0, st>>>(d_edge_terms, rs, cs, d->N, d->H);
+    SPOTV2_CUDA_OK(cudaGetLastError());
+    win_dv_diag_kernel<<<d->B, 256, 0, st>>>(M_vv, t0, rs, cs, partd, d->N, L, d->H);
+    SPOTV2_CUDA_OK(cudaGetLastError());
+    win_dv_finish_kernel<<<(d->H * 3 * L + 127) / 128, 128, 0, st>>>(part0, grid, partd, d->B, L, d->H, dv);
+    SPOTV2_CUDA_OK(cudaGetLastError());
+    return SPOTV2_OK;
+  }
   const int grid = win_grid(d->B);
   const size_t need = (size_t)grid * d->H * d->Fe * sizeof(float);
   if (!ws || ws_bytes < need) return fail(SPOTV2_ERR_WORKSPACE, "windows_dv needs %zu B of workspace, got %zu", need, ws_bytes);
@@ -269,8 +508,7 @@ extern "C" int spotv2_windows_dv(const spotv2_gat_desc* d, const float* M_vv, in
   const size_t smem = ((size_t)HT * NN + 2 * (size_t)d->H * d->N + (size_t)d->H * d->Fe + (size_t)L * d->N) * sizeof(float);
   auto launch = [&](auto kern) -> int {
     SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kWinThreads, smem, as_stream(stream)>>>(M_vv, t0, d_edge_terms, static_cast<float*>(ws), d->B, d->N, L, d->H,
-                                                        kEdgeTermNS);
+    kern<<<grid, kWinThreads, smem, st>>>(M_vv, t0, d_edge_terms, static_cast<float*>(ws), d->B, d->N, L, d->H, kEdgeTermNS);
     SPOTV2_CUDA_OK(cudaGetLastError());
     return SPOTV2_OK;
   };
@@ -280,5 +518,5 @@ extern "C" int spotv2_windows_dv(const spotv2_gat_desc* d, const float* M_vv, in
   else if (HT <= 6) rc = launch(win_dv_kernel<6>);
   else rc = launch(win_dv_kernel<8>);
   if (rc) return rc;
-  return reduce_partials(static_cast<float*>(ws), grid, d->H * d->Fe, dv, as_stream(stream));
+  return reduce_partials(static_cast<float*>(ws), grid, d->H * d->Fe, dv, st);
 }

@@ -203,8 +203,12 @@ class _GatLayerFn(torch.autograd.Function):
         if Fe and (windows is not None or any(ctx.needs_input_grad)):
             et = torch.empty(_edge_terms_bytes(desc) // 4, device=dev, dtype=torch.float32)
         if windows is not None:
+            wsz = C.c_size_t()
+            check(lib.spotv2_edge_terms_from_windows_workspace_bytes(C.byref(desc), C.byref(wsz)), "edge_terms_from_windows ws")
+            ws_w = torch.empty(wsz.value, device=dev, dtype=torch.uint8) if wsz.value else None
             check(lib.spotv2_edge_terms_from_windows(C.byref(desc), ptr(windows.volvol), windows.volvol.shape[0], windows.L,
-                                                     ptr(windows.t0), ptr(v), ptr(et), st), "spotv2_edge_terms_from_windows")
+                                                     ptr(windows.t0), ptr(v), ptr(et), ptr(ws_w), wsz.value, st),
+                  "spotv2_edge_terms_from_windows")
         check(lib.spotv2_gat_attn_fwd(C.byref(desc), ptr(P_aug), ptr(ea), ptr(topo.table) if (Fe and windows is None) else None, ptr(v),
                                       ptr(bias_c), ptr(out), ptr(alpha), ptr(et), ptr(ws_attn), ws_t, st), "spotv2_gat_attn_fwd")
         ctx.desc, ctx.topo, ctx.Fe, ctx.has_bias, ctx.windows = desc, topo, Fe, bias is not None, windows
@@ -382,13 +386,15 @@ class GATConv(nn.Module):
         # structured edge source (batches of spotv2net_b200.WindowDataset): usable when this layer's edge_dim is the
         # dataset's 3L on graphs the fused kernels cover; otherwise the materialised edge_attr is required
         had_windows = windows is not None
-        if windows is not None and not (self.lin_edge is not None and self.edge_dim == 3 * windows.L and topo.N <= 32 and
-                                        topo.R == topo.N * (topo.N - 1) and not topo.has_skips and drop_p == 0.0 and
-                                        ATTN_BWD_ALGO != 1 and windows.t0.numel() == topo.B):
+        small = topo.N <= 32            # the fused small-graph kernels take the structured source on the pipelined backward only
+        if windows is not None and not (self.lin_edge is not None and self.edge_dim == 3 * windows.L and
+                                        topo.R == topo.N * (topo.N - 1) and not topo.has_skips and
+                                        (not small or (drop_p == 0.0 and ATTN_BWD_ALGO != 1)) and
+                                        windows.t0.numel() == topo.B):
             windows = None
         if had_windows and windows is None and edge_attr is None and self.lin_edge is not None:
             raise SpotV2Error("this batch carries window references instead of a materialised edge_attr, and this layer "
-                              "cannot use them (edge_dim != 3 * seq_length, N > 32, attention dropout in training, ...): "
+                              "cannot use them (edge_dim != 3 * seq_length, attention dropout in training on small graphs, ...): "
                               "collate with structured=False")
         use_edge = (edge_attr is not None or windows is not None) and self.lin_edge is not None
         if use_edge and windows is None and edge_attr.shape[0] != topo.B * topo.R:

@@ -748,8 +748,9 @@ def test_evaluation_loop_and_attention_export_match_the_oracle_model(cuda_lib):
         x = torch.relu(x)
 
 
-@pytest.mark.parametrize("geom", [(6, 30, 42, 6, 500, False), (5, 30, 7, 8, 24, True), (4, 13, 3, 3, 10, False)],
-                         ids=["default", "H8_cat", "N13"])
+@pytest.mark.parametrize("geom", [(6, 30, 42, 6, 500, False), (5, 30, 7, 8, 24, True), (4, 13, 3, 3, 10, False),
+                                  (2, 40, 5, 4, 12, False), (2, 77, 3, 3, 7, True), (1, 300, 4, 6, 16, False)],
+                         ids=["default", "H8_cat", "N13", "N40_large", "N77_large_cat", "N300_large"])
 def test_structured_edge_source_layer_parity(cuda_lib, geom):
     """a layer given the dataset's window references (spot_windows) reads the [L, N, N] co-volatility
     windows instead of the materialised edge rows.  Same operator, so: outputs, attention coefficients and every
@@ -808,8 +809,11 @@ def test_structured_edge_source_stages(cuda_lib, geom):
         check(cuda_lib.spotv2_gat_edge_terms_bytes(C.byref(d), C.byref(etb)), "edge_terms_bytes")
         terms = torch.full((etb.value // 4,), float("nan"), device=DEV)      # every byte the kernels read must be written
         if mode == 1:
+            wse = C.c_size_t()
+            check(cuda_lib.spotv2_edge_terms_from_windows_workspace_bytes(C.byref(d), C.byref(wse)), "edge_terms ws")
+            ws_e = torch.empty(max(wse.value, 1), dtype=torch.uint8, device=DEV)
             check(cuda_lib.spotv2_edge_terms_from_windows(C.byref(d), ptr(vv_g), vv_g.shape[0], L, ptr(t0), ptr(v), ptr(terms),
-                                                          st()), "edge_terms_from_windows")
+                                                          ptr(ws_e), wse.value, st()), "edge_terms_from_windows")
         out = torch.empty(B * N, ldo, device=DEV)
         check(cuda_lib.spotv2_gat_attn_fwd(C.byref(d), ptr(P_aug), ptr(ea) if mode == 0 else None,
                                            ptr(topo.table) if mode == 0 else None, ptr(v), ptr(bg), ptr(out), None, ptr(terms),
