@@ -305,13 +305,13 @@ __global__ void __launch_bounds__(256)
 win_dv_large_kernel(const float* __restrict__ vv, const int32_t* __restrict__ t0, const float* __restrict__ dterms,
                     float* __restrict__ part, int B, int N, int L, int H) {
   extern __shared__ __align__(16) float smem[];
-  float* acc = smem;                        // [H][L]
-  float* red = acc + H * L;                 // [8 warps][8 heads]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* acc = smem + (size_t)(threadIdx.x >> 5) * H * L;     // [8 warps][H][L]: every warp keeps its own running sums (no
+                                                              // CTA barrier per lag), added up in a fixed order at the end
+  const int tid = threadIdx.x, lane = tid & 31;
   const size_t NN = (size_t)N * N;
   const int rblocks = (N + 7) / 8, cchunks = (N + 255) / 256;
   const long long items = (long long)B * rblocks * cchunks;
-  for (int idx = tid; idx < H * L; idx += 256) acc[idx] = 0.f;
+  for (int idx = tid; idx < 8 * H * L; idx += 256) smem[idx] = 0.f;
   __syncthreads();
   for (long long q = blockIdx.x; q < items; q += gridDim.x) {
     const int cc = (int)(q % cchunks);
@@ -343,50 +343,135 @@ win_dv_large_kernel(const float* __restrict__ vv, const int32_t* __restrict__ t0
       }
 #pragma unroll
       for (int h = 0; h < 8; ++h) {
-        float sv = a[h];
-        for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
-        if (lane == 0) red[warp * 8 + h] = sv;
+        if (h < H) {
+          float sv = a[h];
+          for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+          if (lane == 0) acc[h * L + t] += sv;
+        }
       }
-      __syncthreads();
-      if (tid < H) {
-        float sv = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) sv += red[w * 8 + tid];
-        acc[tid * L + t] += sv;
-      }
-      __syncthreads();
     }
   }
-  for (int idx = tid; idx < H * L; idx += 256) part[(size_t)blockIdx.x * H * L + idx] = acc[idx];
+  __syncthreads();
+  for (int idx = tid; idx < H * L; idx += 256) {
+    float sv = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sv += smem[(size_t)w * H * L + idx];
+    part[(size_t)blockIdx.x * H * L + idx] = sv;
+  }
+}
+
+// Same contraction, organised so that nothing is reduced until the CTA is done: the CTA builds the symmetric sums of a
+// work item in shared memory (s[h][8 rows][256 cols]); warp w then owns the lags w*TL .. w*TL+TL-1 and walks the item's
+// pairs with lanes along the columns (coalesced window reads), keeping its TL x HT running sums in registers across all
+// of the CTA's items.  One butterfly per accumulator at the very end.  (L <= 8*TL.)
+template <int TL, int HT>
+__global__ void __launch_bounds__(256)
+win_dv_large2_kernel(const float* __restrict__ vv, const int32_t* __restrict__ t0, const float* __restrict__ dterms,
+                     float* __restrict__ part, int B, int N, int L, int H) {
+  extern __shared__ __align__(16) float sS[];              // [HT][8][256]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t NN = (size_t)N * N;
+  const int rblocks = (N + 7) / 8, cchunks = (N + 255) / 256;
+  const long long items = (long long)B * rblocks * cchunks;
+  float acc[TL][HT];
+#pragma unroll
+  for (int q = 0; q < TL; ++q)
+#pragma unroll
+    for (int h = 0; h < HT; ++h) acc[q][h] = 0.f;
+  const int tl0 = warp * TL;
+  for (long long q = blockIdx.x; q < items; q += gridDim.x) {
+    const int cc = (int)(q % cchunks);
+    const long long q2 = q / cchunks;
+    const int rb = (int)(q2 % rblocks), b = (int)(q2 / rblocks);
+    const int r0 = rb * 8, c0 = cc * 256;
+    if (c0 + 255 <= r0) continue;                         // whole item on or below the diagonal (CTA-uniform)
+    const float* Wb = vv + (size_t)t0[b] * NN;
+    const float* wb = dterms + (size_t)b * H * NN;
+    __syncthreads();                                      // the previous item's readers are done with sS
+    {
+      const int c = c0 + tid;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = r0 + k;
+        const bool ok = c < N && r < N && r < c;
+#pragma unroll
+        for (int h = 0; h < HT; ++h)
+          sS[(h * 8 + k) * 256 + tid] =
+              (ok && h < H) ? wb[(size_t)h * NN + (size_t)r * N + c] + wb[(size_t)h * NN + (size_t)c * N + r] : 0.f;
+      }
+    }
+    __syncthreads();
+    for (int k = 0; k < 8; ++k) {
+      const int r = r0 + k;
+      if (r >= N) break;
+      const int cbeg = max(c0, (r + 1) & ~31);             // 32-column groups entirely left of the diagonal hold zeros
+      for (int cg = cbeg; cg < min(N, c0 + 256); cg += 32) {
+        const int c = cg + lane;
+        float x[TL];
+#pragma unroll
+        for (int u = 0; u < TL; ++u)
+          x[u] = (c < N && tl0 + u < L) ? Wb[(size_t)(tl0 + u) * NN + (size_t)r * N + c] : 0.f;
+#pragma unroll
+        for (int h = 0; h < HT; ++h) {
+          const float sv = sS[(h * 8 + k) * 256 + (c - c0)];
+#pragma unroll
+          for (int u = 0; u < TL; ++u) acc[u][h] = fmaf(x[u], sv, acc[u][h]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < TL; ++u)
+#pragma unroll
+    for (int h = 0; h < HT; ++h) {
+      float sv = acc[u][h];
+      for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+      if (lane == 0 && h < H && tl0 + u < L) part[(size_t)blockIdx.x * H * L + h * L + tl0 + u] = sv;
+    }
 }
 
 // Row sums rs[b][h][j] = sum_i w[h][j][i] and column sums cs[b][h][i] = sum_j w[h][j][i] of d(edge terms) (diagonal 0).
+// Block = 256 nodes of one (b, h): thread n sums column n (coalesced over n); the 8 warps then take the block's rows,
+// lanes striding along a row (coalesced), butterfly reduce.
 __global__ void __launch_bounds__(256)
 win_rowcol_sums_kernel(const float* __restrict__ dterms, float* __restrict__ rs, float* __restrict__ cs, int N, int H) {
   const int bh = blockIdx.y;                               // b * H + h
   const float* w = dterms + (size_t)bh * N * N;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  float c = 0.f;
-  for (int j = 0; j < N; ++j) c += w[(size_t)j * N + n];   // coalesced over n
-  cs[(size_t)bh * N + n] = c;
-  float r = 0.f;
-  for (int i = 0; i < N; ++i) r += w[(size_t)n * N + i];   // each thread walks its own row (L2-resident after the pass above)
-  rs[(size_t)bh * N + n] = r;
+  const int n0 = blockIdx.x * 256, n = n0 + threadIdx.x;
+  if (n < N) {
+    float c = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < N; ++j) c += w[(size_t)j * N + n];
+    cs[(size_t)bh * N + n] = c;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = n0 + warp; j < min(N, n0 + 256); j += 8) {
+    const float* row = w + (size_t)j * N;
+    float r = 0.f;
+    for (int i = lane; i < N; i += 32) r += row[i];
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if (lane == 0) rs[(size_t)bh * N + j] = r;
+  }
 }
 
-// dv[h][L + t] += sum_j diag_t[j] rs[h][j];  dv[h][2L + t] += sum_i diag_t[i] cs[h][i].  One CTA per graph, thread = (h, t, k);
-// partial per graph.
+// dv[h][L + t] += sum_j diag_t[j] rs[h][j];  dv[h][2L + t] += sum_i diag_t[i] cs[h][i].  One CTA per graph: the L x N
+// diagonals are staged in shared memory by all threads, then thread = (k, h, t); one partial per graph.
 __global__ void __launch_bounds__(256)
 win_dv_diag_kernel(const float* __restrict__ vv, const int32_t* __restrict__ t0, const float* __restrict__ rs,
                    const float* __restrict__ cs, float* __restrict__ part, int N, int L, int H) {
+  extern __shared__ __align__(16) float dg[];              // [L][N]
   const int b = blockIdx.x;
   const float* W = vv + (size_t)t0[b] * N * N;
+  for (int idx = threadIdx.x; idx < L * N; idx += blockDim.x) {
+    const int t = idx / N, n = idx - t * N;
+    dg[idx] = W[(size_t)t * N * N + (size_t)n * N + n];
+  }
+  __syncthreads();
   for (int idx = threadIdx.x; idx < 2 * H * L; idx += blockDim.x) {
     const int k = idx / (H * L), r = idx - k * H * L, h = r / L, t = r - h * L;
     const float* sums = (k == 0 ? rs : cs) + ((size_t)b * H + h) * N;
     float s = 0.f;
-    for (int n = 0; n < N; ++n) s = fmaf(W[(size_t)t * N * N + (size_t)n * N + n], sums[n], s);
+    for (int n = 0; n < N; ++n) s = fmaf(dg[t * N + n], sums[n], s);
     part[(size_t)b * 2 * H * L + idx] = s;
   }
 }
@@ -490,11 +575,34 @@ extern "C" int spotv2_windows_dv(const spotv2_gat_desc* d, const float* M_vv, in
     float* rs = reinterpret_cast<float*>(w);    w += round_up((size_t)d->B * d->H * d->N * sizeof(float), 256);
     float* cs = reinterpret_cast<float*>(w);    w += round_up((size_t)d->B * d->H * d->N * sizeof(float), 256);
     float* partd = reinterpret_cast<float*>(w);
-    win_dv_large_kernel<<<grid, 256, ((size_t)d->H * L + 64) * sizeof(float), st>>>(M_vv, t0, d_edge_terms, part0, d->B, d->N, L, d->H);
-    SPOTV2_CUDA_OK(cudaGetLastError());
+    {
+      const int TL = (L + 7) / 8, HT = (d->H + 1) / 2 * 2;
+      auto launch2 = [&](auto kern) -> int {
+        const size_t smem = (size_t)HT * 8 * 256 * sizeof(float);
+        SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 256, smem, st>>>(M_vv, t0, d_edge_terms, part0, d->B, d->N, L, d->H);
+        SPOTV2_CUDA_OK(cudaGetLastError());
+        return SPOTV2_OK;
+      };
+      int rc = -1;
+      if (TL <= 6) {                // L <= 48: lag-per-warp kernel, no reductions inside the loop
+        if (HT <= 2) rc = launch2(win_dv_large2_kernel<6, 2>);
+        else if (HT <= 4) rc = launch2(win_dv_large2_kernel<6, 4>);
+        else if (HT <= 6) rc = launch2(win_dv_large2_kernel<6, 6>);
+        else rc = launch2(win_dv_large2_kernel<6, 8>);
+      } else {                      // longer windows: the register-light kernel (one butterfly per lag)
+        win_dv_large_kernel<<<grid, 256, (size_t)8 * d->H * L * sizeof(float), st>>>(M_vv, t0, d_edge_terms, part0, d->B, d->N, L, d->H);
+        SPOTV2_CUDA_OK(cudaGetLastError());
+        rc = SPOTV2_OK;
+      }
+      if (rc) return rc;
+    }
     win_rowcol_sums_kernel<<<dim3((d->N + 255) / 256, d->B * d->H), 256, 0, st>>>(d_edge_terms, rs, cs, d->N, d->H);
     SPOTV2_CUDA_OK(cudaGetLastError());
-    win_dv_diag_kernel<<<d->B, 256, 0, st>>>(M_vv, t0, rs, cs, partd, d->N, L, d->H);
+    const size_t dg_bytes = (size_t)L * d->N * sizeof(float);
+    if (dg_bytes > 200 * 1024) return fail(SPOTV2_ERR_UNSUPPORTED, "windows_dv: L*N = %d exceeds the diagonal staging buffer", L * d->N);
+    SPOTV2_CUDA_OK(cudaFuncSetAttribute(win_dv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dg_bytes));
+    win_dv_diag_kernel<<<d->B, 256, dg_bytes, st>>>(M_vv, t0, rs, cs, partd, d->N, L, d->H);
     SPOTV2_CUDA_OK(cudaGetLastError());
     win_dv_finish_kernel<<<(d->H * 3 * L + 127) / 128, 128, 0, st>>>(part0, grid, partd, d->B, L, d->H, dv);
     SPOTV2_CUDA_OK(cudaGetLastError());

@@ -749,8 +749,9 @@ def test_evaluation_loop_and_attention_export_match_the_oracle_model(cuda_lib):
 
 
 @pytest.mark.parametrize("geom", [(6, 30, 42, 6, 500, False), (5, 30, 7, 8, 24, True), (4, 13, 3, 3, 10, False),
-                                  (2, 40, 5, 4, 12, False), (2, 77, 3, 3, 7, True), (1, 300, 4, 6, 16, False)],
-                         ids=["default", "H8_cat", "N13", "N40_large", "N77_large_cat", "N300_large"])
+                                  (2, 40, 5, 4, 12, False), (2, 77, 3, 3, 7, True), (1, 300, 4, 6, 16, False),
+                                  (1, 40, 50, 2, 8, False)],
+                         ids=["default", "H8_cat", "N13", "N40_large", "N77_large_cat", "N300_large", "N40_L50"])
 def test_structured_edge_source_layer_parity(cuda_lib, geom):
     """a layer given the dataset's window references (spot_windows) reads the [L, N, N] co-volatility
     windows instead of the materialised edge rows.  Same operator, so: outputs, attention coefficients and every
