@@ -646,8 +646,8 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
                  "attn_bwd: edge_rows, table and v are required when Fe > 0");
   SPOTV2_REQUIRE(!structured || (edge_terms_or_null && d_edge_terms_or_null && aligned16(d_edge_terms_or_null)),
                  "attn_bwd: edge_mode 1 needs edge_terms and a 16-byte aligned d_edge_terms buffer");
-  if (structured && d->N <= 32 && (d->attn_bwd_algo == 1 || d->dropout_p > 0.f))
-    return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd: for N <= 32, edge_mode 1 runs on the pipelined kernel only (no attention dropout)");
+  if (structured && d->N <= 32 && d->attn_bwd_algo == 1)
+    return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd: for N <= 32, edge_mode 1 runs on the pipelined kernel only");
   SPOTV2_REQUIRE(aligned16(P_aug) && aligned16(dout) && (f16 || aligned16(dP_aug_or_null)) &&
                      (!f16 || (aligned16(dP_hi_or_null) && aligned16(dP_lo_or_null))),
                  "attn_bwd: P_aug/dout/dP must be 16-byte aligned");
@@ -702,12 +702,9 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
   int rc;
   // d->attn_bwd_algo selects the kernel: 0 = pipelined (attn_bwd2.cu) whenever its shared-memory plan fits,
   // 1 = the phase-serial kernel of this file, 2 = pipelined or error
-  // attention dropout (a non-default training option) is implemented in the phase-serial kernel only
-  if (d->dropout_p > 0.f && d->attn_bwd_algo == 2)
-    return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd: the pipelined kernel (attn_bwd_algo = 2) does not implement attention dropout");
   if (structured && !attn_bwd2_fits(a.p))
     return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd: edge_mode 1 needs the pipelined kernel, whose shared-memory plan does not fit this shape");
-  if (d->dropout_p == 0.f && d->attn_bwd_algo != 1 && (attn_bwd2_fits(a.p) || d->attn_bwd_algo == 2))
+  if (d->attn_bwd_algo != 1 && (attn_bwd2_fits(a.p) || d->attn_bwd_algo == 2))
     rc = launch_attn_bwd2(a, structured ? nullptr : dv_or_null, dbias_or_null, ws, ws_bytes, st);
   else if (np <= 4) rc = launch_bwd<4>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
   else if (np <= 8) rc = launch_bwd<8>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);

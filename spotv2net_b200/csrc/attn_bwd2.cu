@@ -66,7 +66,7 @@ Bwd2Plan make_plan(const AttnParams& p) {
   s.off_table = o;  o += (uint32_t)round_up((size_t)(p.R > 0 ? p.R : 1) * 4, 16);
   s.off_vfrag = o;  o += (uint32_t)((Fe > 0 ? s.KS : 0) * 32 * 16);
   s.off_sd = o;     o += (uint32_t)round_up((size_t)N * 2 * H * 4, 16);
-  s.off_mask = o;   o += (uint32_t)round_up((size_t)H * N * 4, 16);
+  s.off_mask = o;   o += 2 * (uint32_t)round_up((size_t)H * N * 4, 16);      // z > 0 bits | dropout keep bits
   s.off_dspart = o; o += (uint32_t)(2 * H * 32 * 4);
   s.off_dbias = o;  o += (uint32_t)round_up((size_t)p.ldo * 4, 16);
   s.off_tile = o;   o += (uint32_t)round_up((size_t)H * N * kNS2 * 4, 16);
@@ -227,7 +227,9 @@ bool plan_is_fixed_geom(const AttnParams& p, const Bwd2Plan& s) {
          s.slot_bytes == F::slot_bytes && s.tma_ok == 1;
 }
 
-template <bool FIX>
+// DROP: attention dropout in training mode (the mask is regenerated from the descriptor's Philox key, see attn_common.cuh);
+// a separate instantiation so that the default path carries none of it.
+template <bool FIX, bool DROP>
 __global__ void __launch_bounds__(kB2Threads, 1)
 gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_constant__ CUtensorMap tmP,
                      const __grid_constant__ CUtensorMap tmG) {
@@ -255,6 +257,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
   float4* vfrag = reinterpret_cast<float4*>(smem_raw + pl.off_vfrag);
   float* sd = reinterpret_cast<float*>(smem_raw + pl.off_sd);
   uint32_t* pos_mask = reinterpret_cast<uint32_t*>(smem_raw + pl.off_mask);
+  uint32_t* keep_mask = pos_mask + ((H * N + 3) / 4) * 4;                  // [H][N] dropout keep bits (bit j = source j kept)
   float* ds_part = reinterpret_cast<float*>(smem_raw + pl.off_dspart);     // [2][H][32]
   float* dbias_s = reinterpret_cast<float*>(smem_raw + pl.off_dbias);
   float* tile = reinterpret_cast<float*>(smem_raw + pl.off_tile);          // alpha[h][j][i]
@@ -647,6 +650,17 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
         // softmax / LeakyReLU backward on the fragment: lane holds rows i0, i1 and columns j = 8n + 2t + {0,1}
         float al_[4][4];
         float dot0 = 0.f, dot1 = 0.f;
+        uint32_t keep0 = 0xffffffffu, keep1 = 0xffffffffu;
+        if (DROP) {
+          // the forward used alpha * m (m = keep / (1 - p)): dalpha = m * d(alpha m); the bits also go to shared memory
+          // for phase D, which needs alpha * m
+          if (i0 < N) keep0 = dropout_keep_bits(p.drop, (((unsigned long long)b * H + h) * N + i0) * N, N);
+          if (i1 < N) keep1 = dropout_keep_bits(p.drop, (((unsigned long long)b * H + h) * N + i1) * N, N);
+          if (t == 0) {
+            if (i0 < N) keep_mask[h * N + i0] = keep0;
+            if (i1 < N) keep_mask[h * N + i1] = keep1;
+          }
+        }
 #pragma unroll
         for (int n = 0; n < 4; ++n)
 #pragma unroll
@@ -654,7 +668,8 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
             const int i = (q & 2) ? i1 : i0, j = 8 * n + 2 * t + (q & 1);
             const bool valid = i < N && j < N;
             const float a = valid ? tile[(h * N + j) * NS + i] : 0.f;
-            const float da = valid ? dacc[n][q] * k_dalpha : 0.f;
+            float da = valid ? dacc[n][q] * k_dalpha : 0.f;
+            if (DROP) da = ((((q & 2) ? keep1 : keep0) >> j) & 1u) ? da * p.drop.scale : 0.f;
             al_[n][q] = a;
             dacc[n][q] = da;
             if (q & 2) dot1 = fmaf(a, da, dot1); else dot0 = fmaf(a, da, dot0);
@@ -809,8 +824,15 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
           for (int hf = 0; hf < 2; ++hf) {
             const int ia = 16 * ks + 8 * hf + 2 * t;               // k pair (ia, ia+1) = target rows of dO
             const float2 z = make_float2(0.f, 0.f);
-            const float2 x0 = j0 < N ? *reinterpret_cast<const float2*>(&tile[(h * N + j0) * NS + ia]) : z;
-            const float2 x1 = j1 < N ? *reinterpret_cast<const float2*>(&tile[(h * N + j1) * NS + ia]) : z;
+            float2 x0 = j0 < N ? *reinterpret_cast<const float2*>(&tile[(h * N + j0) * NS + ia]) : z;
+            float2 x1 = j1 < N ? *reinterpret_cast<const float2*>(&tile[(h * N + j1) * NS + ia]) : z;
+            if (DROP) {            // alpha[h][source j][target ia | ia+1] * m: keep bits of the TARGET rows, bit = source
+              const uint32_t ka = ia < N ? keep_mask[h * N + ia] : 0u, kb = ia + 1 < N ? keep_mask[h * N + ia + 1] : 0u;
+              x0.x = ((ka >> j0) & 1u) ? x0.x * p.drop.scale : 0.f;
+              x0.y = ((kb >> j0) & 1u) ? x0.y * p.drop.scale : 0.f;
+              x1.x = ((ka >> j1) & 1u) ? x1.x * p.drop.scale : 0.f;
+              x1.y = ((kb >> j1) & 1u) ? x1.y * p.drop.scale : 0.f;
+            }
             cvt_pair(x0.x, x0.y, s_al, ah[ks][2 * hf], al[ks][2 * hf]);
             cvt_pair(x1.x, x1.y, s_al, ah[ks][2 * hf + 1], al[ks][2 * hf + 1]);
           }
@@ -992,7 +1014,9 @@ int launch_attn_bwd2(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t w
     if (int rc = make_tmap(&tmG, a.dout, (uint64_t)p.B * p.N, (uint64_t)p.ldo, (uint64_t)p.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))
       return rc;
   }
-  auto kern = plan_is_fixed_geom(p, pl) ? gat_attn_bwd2_kernel<true> : gat_attn_bwd2_kernel<false>;
+  const bool fixg = plan_is_fixed_geom(p, pl), drop = p.drop.p > 0.f;
+  auto kern = drop ? (fixg ? gat_attn_bwd2_kernel<true, true> : gat_attn_bwd2_kernel<false, true>)
+                   : (fixg ? gat_attn_bwd2_kernel<true, false> : gat_attn_bwd2_kernel<false, false>);
   SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
   kern<<<grid, kB2Threads, pl.total, st>>>(a, pl, tmP, tmG);
   SPOTV2_CUDA_OK(cudaGetLastError());

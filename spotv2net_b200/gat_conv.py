@@ -389,12 +389,11 @@ class GATConv(nn.Module):
         small = topo.N <= 32            # the fused small-graph kernels take the structured source on the pipelined backward only
         if windows is not None and not (self.lin_edge is not None and self.edge_dim == 3 * windows.L and
                                         topo.R == topo.N * (topo.N - 1) and not topo.has_skips and
-                                        (not small or (drop_p == 0.0 and ATTN_BWD_ALGO != 1)) and
-                                        windows.t0.numel() == topo.B):
+                                        (not small or ATTN_BWD_ALGO != 1) and windows.t0.numel() == topo.B):
             windows = None
         if had_windows and windows is None and edge_attr is None and self.lin_edge is not None:
             raise SpotV2Error("this batch carries window references instead of a materialised edge_attr, and this layer "
-                              "cannot use them (edge_dim != 3 * seq_length, attention dropout in training on small graphs, ...): "
+                              "cannot use them (edge_dim != 3 * seq_length, irregular edge order, ...): "
                               "collate with structured=False")
         use_edge = (edge_attr is not None or windows is not None) and self.lin_edge is not None
         if use_edge and windows is None and edge_attr.shape[0] != topo.B * topo.R:

@@ -425,16 +425,29 @@ def test_large_universe_layer_matches_edge_list_oracle(cuda_lib, case, gemm_algo
     assert not bad, f"(our error, fp32-oracle error) above the bar: {bad}"
 
 
-@pytest.mark.parametrize("case", [(3, 30, 40, 126, 6, 20, False), (2, 13, 9, 5, 3, 7, True), (2, 40, 12, 9, 4, 10, False)],
-                         ids=["N30_mean", "N13_cat", "N40_large_path"])
-def test_attention_dropout_in_training_mode_replays_in_the_oracle(cuda_lib, case):
+@pytest.mark.parametrize("bwd_algo", [0, 1], ids=["pipelined_bwd", "serial_bwd"])
+@pytest.mark.parametrize("case", [(3, 30, 40, 126, 6, 20, False), (2, 13, 9, 5, 3, 7, True), (2, 40, 12, 9, 4, 10, False),
+                                  (3, 30, 1260, 126, 6, 500, False), (2, 30, 64, 126, 8, 32, True)],
+                         ids=["N30_mean", "N13_cat", "N40_large_path", "default_geometry", "H8_cat"])
+def test_attention_dropout_in_training_mode_replays_in_the_oracle(cuda_lib, case, bwd_algo):
     """dropout_att > 0 (F.dropout(alpha) in [PyG] gat_conv.py message; HPO range of the reference).  The mask comes
     from the library's own Philox stream, so parity is checked by REPLAYING it: the dropped coefficients returned by
     return_attention_weights give the Bernoulli draw, the oracle applies the same draw, and outputs and every
     gradient (whose backward regenerates the mask from the key) must agree to the usual bar."""
     import copy
+    from spotv2net_b200 import gat_conv
     B, N, Fin, Fe, H, C_, concat = case
     pdrop = 0.3
+    old_algo = gat_conv.ATTN_BWD_ALGO
+    gat_conv.ATTN_BWD_ALGO = bwd_algo
+    try:
+        _dropout_case(B, N, Fin, Fe, H, C_, concat, pdrop)
+    finally:
+        gat_conv.ATTN_BWD_ALGO = old_algo
+
+
+def _dropout_case(B, N, Fin, Fe, H, C_, concat, pdrop):
+    import copy
     ref, ours = make_layers(Fin, C_, H, concat, Fe, 0.2, seed=N)
     ours.dropout = ref.dropout = pdrop
     bt = synth.random_complete_batch(B, N, Fin, Fe, seed=31)
@@ -856,6 +869,29 @@ def test_structured_edge_source_stages(cuda_lib, geom):
     n_aug = H * C_ + 2 * H
     assert relerr(res[1]["dP"][:, :n_aug], res[0]["dP"][:, :n_aug]) < 3e-6
     assert relerr(res[1]["dv"], res[0]["dv"]) < 3e-6 and torch.equal(res[1]["dbias"], res[0]["dbias"])
+
+
+def test_structured_edge_source_with_attention_dropout(cuda_lib):
+    """Same Philox key, same element indexing: the structured and the materialised path drop the same coefficients."""
+    N, L, B, H, C_ = 30, 6, 4, 4, 16
+    vol, vv = synth.synthetic_matrices(L + B + 2, N, seed=19)
+    _, layer = make_layers(N * L, C_, H, False, 3 * L, 0.2, seed=5)
+    layer.dropout = 0.25
+    layer.train()
+    res = []
+    for structured in (False, True):
+        ds = sv.WindowDataset(vol, vv, seq_length=L, device=DEV, drop_first=0, structured=structured)
+        bt = ds.collate(list(range(B)))
+        layer.zero_grad()
+        torch.manual_seed(11)
+        out, (_, alpha) = layer(bt.x, bt.edge_index, bt.edge_attr, return_attention_weights=True, topology=bt.spot_topology,
+                                windows=bt.spot_windows if structured else None)
+        out.sum().backward()
+        res.append((out.detach(), alpha.detach(), {k: p.grad.clone() for k, p in layer.named_parameters()}))
+    assert torch.equal(res[0][1] != 0, res[1][1] != 0) and 0.6 < (res[0][1] != 0).float().mean() < 0.9
+    assert relerr(res[1][0], res[0][0]) < 3e-6
+    for k in res[0][2]:
+        assert relerr(res[1][2][k], res[0][2][k]) < 2e-5, k
 
 
 def test_structured_and_materialised_model_steps_agree(cuda_lib):
