@@ -367,22 +367,60 @@ __global__ void split_f16_kernel(const float* __restrict__ src, int rows, int co
   }
 }
 
-// vec4 fast path: one row per block, no index division; 8-byte stores of 4 fp16 values
+// vec4 fast path: a block walks groups of four rows (grid stride), no index division; every thread has four 16-byte
+// loads in flight (one per row) before it converts, 8-byte stores of 4 fp16 values
+constexpr int kSplitRows = 4;
 __global__ void __launch_bounds__(256)
-split_f16_rows_kernel(const float* __restrict__ src, int cols4, size_t ld, int split_dim, int split_at,
+split_f16_rows_kernel(const float* __restrict__ src, int rows, int cols4, size_t ld, int split_dim, int split_at,
                       const float* __restrict__ pre2, int pre_split, __half* __restrict__ hi, __half* __restrict__ lo,
                       size_t ld16, float* __restrict__ blk) {
   const unsigned* bits = reinterpret_cast<const unsigned*>(blk);
   const float s0 = scale_from_amax(__uint_as_float(bits[0])), s1 = scale_from_amax(__uint_as_float(bits[1]));
   if (blockIdx.x == 0 && threadIdx.x == 0) { blk[2] = 1.f / s0; blk[3] = 1.f / s1; blk[4] = s0; blk[5] = s1; }
-  const int r = blockIdx.x;
-  const float pre = pre2 ? pre2[r >= pre_split ? 1 : 0] : 1.f;
-  const float row_scale = pre * ((split_dim == 0 && r >= split_at) ? s1 : s0);
-  const float4* srow = reinterpret_cast<const float4*>(src + (size_t)r * ld);
-  uint2* hrow = reinterpret_cast<uint2*>(hi + (size_t)r * ld16);
-  uint2* lrow = reinterpret_cast<uint2*>(lo + (size_t)r * ld16);
-  for (int c4 = threadIdx.x; c4 < cols4; c4 += 256) {
-    const float4 v = ldg_stream4(reinterpret_cast<const float*>(srow + c4));
+  for (int r0 = blockIdx.x * kSplitRows; r0 < rows; r0 += gridDim.x * kSplitRows) {
+    for (int c4 = threadIdx.x; c4 < cols4; c4 += 256) {
+      float4 v[kSplitRows];
+#pragma unroll
+      for (int k = 0; k < kSplitRows; ++k)
+        if (r0 + k < rows) v[k] = ldg_stream4(src + (size_t)(r0 + k) * ld + 4 * (size_t)c4);
+#pragma unroll
+      for (int k = 0; k < kSplitRows; ++k) {
+        const int r = r0 + k;
+        if (r >= rows) break;
+        const float pre = pre2 ? pre2[r >= pre_split ? 1 : 0] : 1.f;
+        const float row_scale = pre * ((split_dim == 0 && r >= split_at) ? s1 : s0);
+        float sc[4] = {row_scale, row_scale, row_scale, row_scale};
+        if (split_dim == 1) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sc[e] = pre * ((4 * c4 + e >= split_at) ? s1 : s0);
+        }
+        const float x0 = v[k].x * sc[0], x1 = v[k].y * sc[1], x2 = v[k].z * sc[2], x3 = v[k].w * sc[3];
+        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+        const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(x0 - b01.x, x1 - b01.y), l23 = __floats2half2_rn(x2 - b23.x, x3 - b23.y);
+        reinterpret_cast<uint2*>(hi + (size_t)r * ld16)[c4] =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        reinterpret_cast<uint2*>(lo + (size_t)r * ld16)[c4] =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+      }
+    }
+  }
+}
+
+// Narrow matrices (a few float4 per row, e.g. the ds|dd block [B*N, 2H]): one thread per (row, float4), flat index.
+__global__ void __launch_bounds__(256)
+split_f16_narrow_kernel(const float* __restrict__ src, int rows, int cols4, size_t ld, int split_dim, int split_at,
+                        const float* __restrict__ pre2, int pre_split, __half* __restrict__ hi, __half* __restrict__ lo,
+                        size_t ld16, float* __restrict__ blk) {
+  const unsigned* bits = reinterpret_cast<const unsigned*>(blk);
+  const float s0 = scale_from_amax(__uint_as_float(bits[0])), s1 = scale_from_amax(__uint_as_float(bits[1]));
+  if (blockIdx.x == 0 && threadIdx.x == 0) { blk[2] = 1.f / s0; blk[3] = 1.f / s1; blk[4] = s0; blk[5] = s1; }
+  const size_t total = (size_t)rows * cols4;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / cols4), c4 = (int)(idx - (size_t)r * cols4);
+    const float4 v = ldg_stream4(src + (size_t)r * ld + 4 * (size_t)c4);
+    const float pre = pre2 ? pre2[r >= pre_split ? 1 : 0] : 1.f;
+    const float row_scale = pre * ((split_dim == 0 && r >= split_at) ? s1 : s0);
     float sc[4] = {row_scale, row_scale, row_scale, row_scale};
     if (split_dim == 1) {
 #pragma unroll
@@ -392,8 +430,10 @@ split_f16_rows_kernel(const float* __restrict__ src, int cols4, size_t ld, int s
     const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
     const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
     const __half2 l01 = __floats2half2_rn(x0 - b01.x, x1 - b01.y), l23 = __floats2half2_rn(x2 - b23.x, x3 - b23.y);
-    hrow[c4] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-    lrow[c4] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    reinterpret_cast<uint2*>(hi + (size_t)r * ld16)[c4] =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    reinterpret_cast<uint2*>(lo + (size_t)r * ld16)[c4] =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
   }
 }
 
@@ -467,9 +507,12 @@ int split_f16(const float* src, int rows, int cols, size_t ld, int split_dim, in
   }
   const int vec4 = (cols % 4 == 0) && (ld % 4 == 0) && (ld16 % 4 == 0) && aligned16(src) &&
                    ((reinterpret_cast<uintptr_t>(hi) & 7) == 0) && ((reinterpret_cast<uintptr_t>(lo) & 7) == 0);
-  if (vec4)
-    split_f16_rows_kernel<<<rows, 256, 0, st>>>(src, cols / 4, ld, split_dim, split_at, pre2, pre_split, static_cast<__half*>(hi),
-                                               static_cast<__half*>(lo), ld16, blk);
+  if (vec4 && cols / 4 < 64)
+    split_f16_narrow_kernel<<<(unsigned)std::min<size_t>(((size_t)rows * (cols / 4) + 255) / 256, (size_t)16 * 148), 256, 0, st>>>(
+        src, rows, cols / 4, ld, split_dim, split_at, pre2, pre_split, static_cast<__half*>(hi), static_cast<__half*>(lo), ld16, blk);
+  else if (vec4)
+    split_f16_rows_kernel<<<std::min((rows + kSplitRows - 1) / kSplitRows, 32 * 148), 256, 0, st>>>(
+        src, rows, cols / 4, ld, split_dim, split_at, pre2, pre_split, static_cast<__half*>(hi), static_cast<__half*>(lo), ld16, blk);
   else
     split_f16_kernel<<<blocks, 256, 0, st>>>(src, rows, cols, ld, split_dim, split_at, pre2, pre_split, 1.f,
                                              static_cast<__half*>(hi), static_cast<__half*>(lo), ld16, blk, 0);
