@@ -16,7 +16,7 @@
 //                         keeps the alpha fragments of the current head in registers.  Per-head accumulators
 //                         are folded into the running sum with round-to-nearest adds.
 //   warp 11               TMA producer: per graph one tile holding the s|d columns of P_aug, then the P
-//                         tiles (16-slot ring), running ahead across graphs.
+//                         tiles (24-slot ring), running ahead across graphs.
 //
 // Why tensor cores here: with CUDA-core FFMA2 every lane needs the whole alpha row in registers, and the
 // shared-memory return path (512 B per LDS.128 per warp) bounded that version at 38 % of HBM peak

@@ -57,7 +57,9 @@ struct HSmem {
   static constexpr int kStage = 2 * kAOp + 2 * kBOp;
   static constexpr int kStages = (200 * 1024) / kStage > 6 ? 6 : (200 * 1024) / kStage;
   static constexpr int kBarOff = kStages * kStage;
-  static constexpr int kTotal = kBarOff + 256 + 1024;
+  static constexpr int kEpiOff = kBarOff + 256;                      // 8 epilogue warps x [32][33] floats: transposes of
+  static constexpr int kEpiBytes = kHEpiWarps * 32 * 33 * 4;        // 32 x 32 output blocks for row-contiguous stores
+  static constexpr int kTotal = kEpiOff + kEpiBytes + 1024;
   static constexpr uint32_t kTxBytes = kStage;
 };
 
@@ -240,18 +242,26 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             if (col0 + e < p.amax_cols) mx = fmaxf(mx, fabsf(acc[e]));
           row_amax = mx;
         }
-        float* crow = p.C + (size_t)sp * p.split_stride + (size_t)row * p.ldc + col0;
-        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
-                            (p.split_stride % 4 == 0) && (col0 + HALF <= p.N);
-        if (vec_ok) {
+      }
+      {
+        // Stores: a lane owns an output ROW, so storing straight from registers makes every warp store touch 32 rows
+        // (16 bytes each; ncu showed the LSU queue throttling the K = 1260 product).  Instead each 32 x 32 block goes
+        // through a padded shared-memory transpose and leaves as 32 stores of 128 contiguous bytes.
+        float* stage = reinterpret_cast<float*>(smem + S::kEpiOff) + (warp - 4) * 32 * 33;
+        const int row_base = mt * HBM_ + q * 32;
+        float* cbase = p.C + (size_t)sp * p.split_stride + (size_t)row_base * p.ldc;
 #pragma unroll
-          for (int v4 = 0; v4 < HALF / 4; ++v4)
-            *reinterpret_cast<float4*>(crow + 4 * v4) =
-                make_float4(acc[4 * v4], acc[4 * v4 + 1], acc[4 * v4 + 2], acc[4 * v4 + 3]);
-        } else {
+        for (int cc = 0; cc < HALF / 32; ++cc) {
 #pragma unroll
-          for (int e = 0; e < HALF; ++e)
-            if (col0 + e < p.N) crow[e] = acc[e];
+          for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = acc[cc * 32 + j];
+          __syncwarp();
+          const int col = col0 + cc * 32 + lane;
+          if (col < p.N) {
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr)
+              if (row_base + rr < p.M) cbase[(size_t)rr * p.ldc + col] = stage[rr * 33 + lane];
+          }
+          __syncwarp();
         }
       }
       if (p.amax_out) {
