@@ -267,13 +267,15 @@ lg_rowsum_kernel(const float* __restrict__ dZ, float* dP_aug, int B, int N, int 
 }
 
 // d(edge terms) for the structured source: w[b][h][j][i] = dz[b][h][j][i] + fill[b][h][i] off the diagonal, 0 on it.
-__global__ void __launch_bounds__(256)
-lg_dterms_kernel(const float* __restrict__ dZ, const float* __restrict__ fill, float* __restrict__ out, size_t total, int N) {
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const size_t row = idx / N;                 // (b*H + h)*N + j
-    const int i = (int)(idx - row * N), j = (int)(row % N);
-    out[idx] = (i != j) ? dZ[idx] + fill[(row / N) * N + i] : 0.f;
-  }
+// One block per row (b*H + h)*N + j, threads along i: no index divisions in the hot path.
+__global__ void __launch_bounds__(128)
+lg_dterms_kernel(const float* __restrict__ dZ, const float* __restrict__ fill, float* __restrict__ out, int N) {
+  const size_t row = blockIdx.x;
+  const int j = (int)(row % N);
+  const float* fl = fill + (row / N) * N;
+  const float* src = dZ + row * N;
+  float* dst = out + row * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) dst[i] = (i != j) ? src[i] + fl[i] : 0.f;
 }
 
 struct LgDvArgs {
@@ -596,9 +598,7 @@ int attn_large_bwd(const spotv2_gat_desc* d, AttnBwdArgs& a, float* dv, float* d
   if (p.Fe > 0 && p.dterms_out) {
     // structured source: the gradient w.r.t. the edge terms leaves as w[b][h][j][i] = dz + fill[b][h][i] (0 on the
     // diagonal); dv is formed from the windows by spotv2_windows_dv
-    const size_t total = (size_t)p.B * p.H * p.N * p.N;
-    lg_dterms_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, (size_t)32 * sm_count()), 256, 0, st>>>(dA, fill, p.dterms_out,
-                                                                                                            total, p.N);
+    lg_dterms_kernel<<<(unsigned)((size_t)p.B * p.H * p.N), 128, 0, st>>>(dA, fill, p.dterms_out, p.N);
     SPOTV2_CUDA_OK(cudaGetLastError());
   } else if (p.Fe > 0 && dv) {
     LgDvArgs v;

@@ -454,25 +454,21 @@ win_rowcol_sums_kernel(const float* __restrict__ dterms, float* __restrict__ rs,
   }
 }
 
-// dv[h][L + t] += sum_j diag_t[j] rs[h][j];  dv[h][2L + t] += sum_i diag_t[i] cs[h][i].  One CTA per graph: the L x N
-// diagonals are staged in shared memory by all threads, then thread = (k, h, t); one partial per graph.
+// dv[h][L + t] += sum_j diag_t[j] rs[h][j];  dv[h][2L + t] += sum_i diag_t[i] cs[h][i].  One CTA per (graph, k, head): a warp
+// per lag, lanes over the nodes (the diagonal reads are strided; they stay in L2 across the 2H CTAs of a graph).
 __global__ void __launch_bounds__(256)
 win_dv_diag_kernel(const float* __restrict__ vv, const int32_t* __restrict__ t0, const float* __restrict__ rs,
                    const float* __restrict__ cs, float* __restrict__ part, int N, int L, int H) {
-  extern __shared__ __align__(16) float dg[];              // [L][N]
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, k = blockIdx.y / H, h = blockIdx.y - k * H;
   const float* W = vv + (size_t)t0[b] * N * N;
-  for (int idx = threadIdx.x; idx < L * N; idx += blockDim.x) {
-    const int t = idx / N, n = idx - t * N;
-    dg[idx] = W[(size_t)t * N * N + (size_t)n * N + n];
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < 2 * H * L; idx += blockDim.x) {
-    const int k = idx / (H * L), r = idx - k * H * L, h = r / L, t = r - h * L;
-    const float* sums = (k == 0 ? rs : cs) + ((size_t)b * H + h) * N;
+  const float* sums = (k == 0 ? rs : cs) + ((size_t)b * H + h) * N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = warp; t < L; t += 8) {
+    const float* Wt = W + (size_t)t * N * N;
     float s = 0.f;
-    for (int n = 0; n < N; ++n) s = fmaf(dg[t * N + n], sums[n], s);
-    part[(size_t)b * 2 * H * L + idx] = s;
+    for (int n = lane; n < N; n += 32) s = fmaf(Wt[(size_t)n * N + n], sums[n], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) part[(size_t)b * 2 * H * L + (size_t)k * H * L + h * L + t] = s;
   }
 }
 
@@ -599,10 +595,7 @@ extern "C" int spotv2_windows_dv(const spotv2_gat_desc* d, const float* M_vv, in
     }
     win_rowcol_sums_kernel<<<dim3((d->N + 255) / 256, d->B * d->H), 256, 0, st>>>(d_edge_terms, rs, cs, d->N, d->H);
     SPOTV2_CUDA_OK(cudaGetLastError());
-    const size_t dg_bytes = (size_t)L * d->N * sizeof(float);
-    if (dg_bytes > 200 * 1024) return fail(SPOTV2_ERR_UNSUPPORTED, "windows_dv: L*N = %d exceeds the diagonal staging buffer", L * d->N);
-    SPOTV2_CUDA_OK(cudaFuncSetAttribute(win_dv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dg_bytes));
-    win_dv_diag_kernel<<<d->B, 256, dg_bytes, st>>>(M_vv, t0, rs, cs, partd, d->N, L, d->H);
+    win_dv_diag_kernel<<<dim3(d->B, 2 * d->H), 256, 0, st>>>(M_vv, t0, rs, cs, partd, d->N, L, d->H);
     SPOTV2_CUDA_OK(cudaGetLastError());
     win_dv_finish_kernel<<<(d->H * 3 * L + 127) / 128, 128, 0, st>>>(part0, grid, partd, d->B, L, d->H, dv);
     SPOTV2_CUDA_OK(cudaGetLastError());
