@@ -557,17 +557,28 @@ gat_attn_bwd_kernel(const AttnBwdArgs args, const BwdSmem sm) {
     args.dbias_part[(size_t)blockIdx.x * p.ldo + idx] = dbias_s[idx];
 }
 
-__global__ void partial_reduce_kernel(const float* __restrict__ part, int nparts, int len,
-                                      float* __restrict__ out) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= len) return;
+// out[k] = sum_c part[c][k].  Block = 32 outputs x 8 partial groups (group g takes c = g, g + 8, ...: eight independent
+// load streams per output, coalesced along k), combined through shared memory in a fixed order: deterministic.
+__global__ void __launch_bounds__(256)
+partial_reduce_kernel(const float* __restrict__ part, int nparts, int len, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int c = 0; c < nparts; ++c) s += part[(size_t)c * len + k];
-  out[k] = s;
+  if (k < len)
+    for (int c = ty; c < nparts; c += 8) s += part[(size_t)c * len + k];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && k < len) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][tx];
+    out[k] = t;
+  }
 }
 
 int reduce_partials(const float* part, int nparts, int len, float* out, cudaStream_t st) {
-  partial_reduce_kernel<<<(len + 127) / 128, 128, 0, st>>>(part, nparts, len, out);
+  partial_reduce_kernel<<<(len + 31) / 32, 256, 0, st>>>(part, nparts, len, out);
   SPOTV2_CUDA_OK(cudaGetLastError());
   return SPOTV2_OK;
 }
@@ -608,9 +619,9 @@ static int launch_bwd(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t 
   SPOTV2_CUDA_OK(cudaGetLastError());
   if (dv && p.Fe > 0) {
     const int len = p.H * p.Fe;
-    partial_reduce_kernel<<<(len + 127) / 128, 128, 0, st>>>(a.dv_part, grid, len, dv);
+    partial_reduce_kernel<<<(len + 31) / 32, 256, 0, st>>>(a.dv_part, grid, len, dv);
   }
-  if (dbias) partial_reduce_kernel<<<(p.ldo + 127) / 128, 128, 0, st>>>(a.dbias_part, grid, p.ldo, dbias);
+  if (dbias) partial_reduce_kernel<<<(p.ldo + 31) / 32, 256, 0, st>>>(a.dbias_part, grid, p.ldo, dbias);
   SPOTV2_CUDA_OK(cudaGetLastError());
   return SPOTV2_OK;
 }

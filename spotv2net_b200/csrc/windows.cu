@@ -132,13 +132,24 @@ win_dv_kernel(const float* __restrict__ vv, const int32_t* __restrict__ t0, cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int idx = tid; idx < H * 3 * L; idx += kWinThreads) acc[idx] = 0.f;
   for (int idx = H * NN + tid; idx < HT * NN; idx += kWinThreads) dzs[idx] = 0.f;
+  // this thread's pair slots m = tid + 256 k (k < 4: N <= 32) and their (j, i), computed once: no divisions per graph
+  int pm_j[4], pm_i[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int m = tid + k * kWinThreads;
+    pm_j[k] = m < NN ? m / N : -1;
+    pm_i[k] = m < NN ? m - (m / N) * N : 0;
+  }
   __syncthreads();
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const float* W = vv + (size_t)t0[b] * NN;
     const float* src = dterms + (size_t)b * H * N * NS;
-    for (int idx = tid; idx < H * NN; idx += kWinThreads) {
-      const int h = idx / NN, m = idx - h * NN, j = m / N, i = m - j * N;
-      dzs[idx] = (i != j) ? src[((size_t)h * N + j) * NS + i] : 0.f;
+    for (int h = 0; h < H; ++h) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = pm_j[k], i = pm_i[k];
+        if (j >= 0) dzs[h * NN + tid + k * kWinThreads] = (i != j) ? src[((size_t)h * N + j) * NS + i] : 0.f;
+      }
     }
     for (int idx = tid; idx < L * N; idx += kWinThreads) {
       const int t = idx / N, n = idx - t * N;
@@ -153,12 +164,15 @@ win_dv_kernel(const float* __restrict__ vv, const int32_t* __restrict__ t0, cons
       (which == 0 ? rs : cs)[r] = s;
     }
     __syncthreads();
-    for (int idx = tid; idx < H * NN; idx += kWinThreads) {     // one owner per unordered pair: no conflicts
-      const int h = idx / NN, m = idx - h * NN, j = m / N, i = m - j * N;
-      if (j < i) {
-        const int mt = h * NN + i * N + j;
-        dzs[idx] += dzs[mt];
-        dzs[mt] = 0.f;
+    for (int h = 0; h < H; ++h) {                               // one owner per unordered pair: no conflicts
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = pm_j[k], i = pm_i[k];
+        if (j >= 0 && j < i) {
+          const int mt = h * NN + i * N + j, mm = h * NN + tid + k * kWinThreads;
+          dzs[mm] += dzs[mt];
+          dzs[mt] = 0.f;
+        }
       }
     }
     __syncthreads();
