@@ -19,6 +19,8 @@
 // Kernel shape: persistent, one CTA per SM, 384 threads (warp 0 TMA, warp 1 MMA issue, warp 2 TMEM
 // allocator, warps 4-11 accumulate + epilogue), tile 128 x 256 x TBK, TBK = 64 | 32 fp16 elements.
 #include <cuda_fp16.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -48,6 +50,9 @@ struct HParams {
   unsigned* amax_out;   // optional: bit pattern of max |C[m, n]| over n < amax_cols (splits == 1 only)
   int amax_cols;
   int single;           // 1: half-precision class (gemm_algo 3): only the A_hi * B_hi product, lo tiles not even loaded
+  int tma_store;        // 1: C tiles leave through TMA bulk stores (splits == 1, 16-byte aligned rows); 0: st.global
+  int dbg;              // bring-up probe (env SPOTV2_GEMM_DBG): bit 0 skip the global stores, bit 1 skip scale + amax,
+                        // bit 2 skip the per-chunk register accumulation (results are then wrong: timing only)
 };
 
 template <int BN, int TBK, bool A_KM, bool B_KM>
@@ -57,8 +62,9 @@ struct HSmem {
   static constexpr int kStage = 2 * kAOp + 2 * kBOp;
   static constexpr int kStages = (200 * 1024) / kStage > 6 ? 6 : (200 * 1024) / kStage;
   static constexpr int kBarOff = kStages * kStage;
-  static constexpr int kEpiOff = kBarOff + 256;                      // 8 epilogue warps x [32][33] floats: transposes of
-  static constexpr int kEpiBytes = kHEpiWarps * 32 * 33 * 4;        // 32 x 32 output blocks for row-contiguous stores
+  static constexpr int kEpiOff = kBarOff + 1024;                     // 8 epilogue warps x 4224 B: a 32 x 32 fp32 output block each
+  static constexpr int kEpiWarpBytes = 32 * 33 * 4;                  // ([32][33] transpose, or a 4 KB 128B-swizzled TMA store box)
+  static constexpr int kEpiBytes = kHEpiWarps * kEpiWarpBytes;
   static constexpr int kTotal = kEpiOff + kEpiBytes + 1024;
   static constexpr uint32_t kTxBytes = kStage;
 };
@@ -67,7 +73,7 @@ template <int BN, int TBK, bool A_KM, bool B_KM>
 __global__ void __launch_bounds__(kHThreads, 1)
 gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                  const HParams p) {
+                  const __grid_constant__ CUtensorMap tmC, const HParams p) {
   using S = HSmem<BN, TBK, A_KM, B_KM>;
   constexpr int kStages = S::kStages;
   extern __shared__ unsigned char smem_dyn[];
@@ -219,7 +225,10 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           uint32_t r[32];
           tmem_ld32(taddr + c0, r);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) acc[c0 + e] += __uint_as_float(r[e]);   // round-to-nearest adds
+          if (!(p.dbg & 4))
+#pragma unroll
+            for (int e = 0; e < 32; ++e) acc[c0 + e] += __uint_as_float(r[e]);   // round-to-nearest adds
+          else acc[c0] += __uint_as_float(r[0]);
         }
         tc_fence_before();
         __syncwarp();
@@ -228,7 +237,7 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
       const int row = mt * HBM_ + q * 32 + lane;
       const int col0 = nt * BN + ch * HALF;
       float row_amax = 0.f;
-      if (row < p.M && col0 < p.N) {
+      if (row < p.M && col0 < p.N && !(p.dbg & 2)) {
         if (p.scale_in_kernel) {      // powers of two: exact
           const float ra = p.a_inv ? p.a_inv[row >= p.a_split ? 1 : 0] : 1.f;
           const float cb0 = ra * (p.b_inv ? p.b_inv[0] : 1.f), cb1 = ra * (p.b_inv ? p.b_inv[1] : 1.f);
@@ -243,11 +252,37 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           row_amax = mx;
         }
       }
-      {
+      if (p.tma_store && !(p.dbg & 1)) {
+        // Asynchronous stores (measured: with st.global the epilogue warps sat in the LSU queue for ~0.5 ms of the K = 1260
+        // product while the MMA warp waited for them to drain TMEM).  Each warp parks 32 x 16 pieces of its block in two
+        // alternating swizzled shared-memory boxes and one lane hands each to the TMA engine; the warp only waits for the
+        // engine to have READ the box written two pieces ago before refilling it.  Rows >= M and columns >= N are clipped by the tensor map.
+        unsigned char* box = smem + S::kEpiOff + (warp - 4) * 4096;      // two 2 KB half-boxes (32 rows x 16 columns, 64B swizzle)
+        const int row_base = mt * HBM_ + q * 32;
+#pragma unroll
+        for (int cc = 0; cc < HALF / 16; ++cc) {
+          unsigned char* hb = box + (cc & 1) * 2048;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store before last has been read
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<float4*>(hb + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+                make_float4(acc[cc * 16 + 4 * c], acc[cc * 16 + 4 * c + 1], acc[cc * 16 + 4 * c + 2], acc[cc * 16 + 4 * c + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (col0 + cc * 16 < p.N && row_base < p.M)
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
+                           "r"(smem_u32(hb)), "r"(col0 + cc * 16), "r"(row_base)
+                           : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");       // always commit: keeps the group count in step with cc
+          }
+        }
+      } else if (!(p.dbg & 1)) {
         // Stores: a lane owns an output ROW, so storing straight from registers makes every warp store touch 32 rows
         // (16 bytes each; ncu showed the LSU queue throttling the K = 1260 product).  Instead each 32 x 32 block goes
         // through a padded shared-memory transpose and leaves as 32 stores of 128 contiguous bytes.
-        float* stage = reinterpret_cast<float*>(smem + S::kEpiOff) + (warp - 4) * 32 * 33;
+        float* stage = reinterpret_cast<float*>(smem + S::kEpiOff + (warp - 4) * S::kEpiWarpBytes);
         const int row_base = mt * HBM_ + q * 32;
         float* cbase = p.C + (size_t)sp * p.split_stride + (size_t)row_base * p.ldc;
 #pragma unroll
@@ -271,6 +306,7 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     }
   }
 
+  if (warp >= 4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this lane's bulk stores have landed
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -293,14 +329,14 @@ __global__ void f16_splitk_reduce_kernel(const float* __restrict__ ws, int split
 
 template <int BN, int TBK, bool A_KM, bool B_KM>
 int launch_h(const CUtensorMap& tAh, const CUtensorMap& tAl, const CUtensorMap& tBh, const CUtensorMap& tBl,
-             const HParams& p, cudaStream_t st) {
+             const CUtensorMap& tC, const HParams& p, cudaStream_t st) {
   using S = HSmem<BN, TBK, A_KM, B_KM>;
   auto kern = gemm3x_f16_kernel<BN, TBK, A_KM, B_KM>;
   SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
   int grid = sm_count();
   const int total = p.m_tiles * p.n_tiles * p.splits;
   if (grid > total) grid = total;
-  kern<<<grid, kHThreads, S::kTotal, st>>>(tAh, tAl, tBh, tBl, p);
+  kern<<<grid, kHThreads, S::kTotal, st>>>(tAh, tAl, tBh, tBl, tC, p);
   SPOTV2_CUDA_OK(cudaGetLastError());
   return SPOTV2_OK;
 }
@@ -555,6 +591,10 @@ int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, c
   p.amax_out = reinterpret_cast<unsigned*>(amax_out);
   p.amax_cols = amax_cols;
   p.single = single ? 1 : 0;
+  {
+    static const int dbg = getenv("SPOTV2_GEMM_DBG") ? atoi(getenv("SPOTV2_GEMM_DBG")) : 0;
+    p.dbg = dbg;
+  }
   if (amax_out) {
     if (splits > 1) return fail(SPOTV2_ERR_INVALID_ARG, "gemm3x_f16: amax_out needs splits == 1");
     SPOTV2_CUDA_OK(cudaMemsetAsync(amax_out, 0, sizeof(float), st));
@@ -566,8 +606,14 @@ int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, c
     p.C = static_cast<float*>(ws); p.ldc = N; p.split_stride = (size_t)M * N;
     p.scale_in_kernel = 0;
   }
-  CUtensorMap tAh, tAl, tBh, tBl;
+  CUtensorMap tAh, tAl, tBh, tBl, tC;
   int rc;
+  memset(&tC, 0, sizeof(tC));
+  p.tma_store = 0;
+  if (p.splits == 1 && aligned16(C) && ldc % 4 == 0) {      // C tiles through TMA bulk stores: 32-row x 16-column fp32 boxes, 64B swizzle
+    if ((rc = make_tmap(&tC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    p.tma_store = 1;
+  }
   // K-major operand: tensor [rows = M|N, cols = K], box TBK(k) x tile rows (rows of 128 or 64 bytes).
   // MN-major operand: tensor [rows = K, cols = M|N], box 64(m|n) x TBK(k); one box per 64-wide block.
   const CUtensorMapSwizzle kSw = TBK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -586,7 +632,7 @@ int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, c
     if ((rc = make_tmap_f16(&tBh, B.hi, K, N, B.ld, 64, TBK, mnSw))) return rc;
     if ((rc = make_tmap_f16(&tBl, B.lo, K, N, B.ld, 64, TBK, mnSw))) return rc;
   }
-#define SPOTV2_H(BN_, TBK_, AK, BK_) rc = launch_h<BN_, TBK_, AK, BK_>(tAh, tAl, tBh, tBl, p, st)
+#define SPOTV2_H(BN_, TBK_, AK, BK_) rc = launch_h<BN_, TBK_, AK, BK_>(tAh, tAl, tBh, tBl, tC, p, st)
 #define SPOTV2_H_MAJ(BN_, TBK_)                            \
   do {                                                     \
     if (a_kc && b_kc) SPOTV2_H(BN_, TBK_, true, true);     \
