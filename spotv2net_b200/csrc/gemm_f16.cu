@@ -19,6 +19,7 @@
 // Kernel shape: persistent, one CTA per SM, 384 threads (warp 0 TMA, warp 1 MMA issue, warp 2 TMEM
 // allocator, warps 4-11 accumulate + epilogue), tile 128 x 256 x TBK, TBK = 64 | 32 fp16 elements.
 #include <cuda_fp16.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -592,7 +593,13 @@ int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, c
   p.amax_cols = amax_cols;
   p.single = single ? 1 : 0;
   {
-    static const int dbg = getenv("SPOTV2_GEMM_DBG") ? atoi(getenv("SPOTV2_GEMM_DBG")) : 0;
+    // bring-up probe (tools/gemm_fill_probe.py): skips parts of the epilogue to time them; results are WRONG when set
+    static const int dbg = [] {
+      const char* e = getenv("SPOTV2_GEMM_DBG");
+      const int v = e ? atoi(e) : 0;
+      if (v) fprintf(stderr, "libspotv2_gat: SPOTV2_GEMM_DBG=%d - timing probe active, GEMM results are invalid\n", v);
+      return v;
+    }();
     p.dbg = dbg;
   }
   if (amax_out) {
