@@ -135,7 +135,8 @@ int spotv2_gat_fold(const spotv2_gat_desc* d, const float* W, const float* a_src
  * operand pairs), 0 when they take the exact-fp32 CUDA-core kernel (gemm_algo == 1). */
 int spotv2_gat_uses_tensor_cores(const spotv2_gat_desc* d);
 
-/* Leading dimension (elements) of an fp16-pair array holding `cols` columns: cols rounded up to 8. */
+/* Leading dimension (elements) of an fp16-pair array holding `cols` columns: cols rounded up to 16, so that
+ * every row starts on a 32-byte sector (the kernels themselves only need ld16 % 8 == 0). */
 int32_t spotv2_gat_ld16(int32_t cols);
 
 /* Tensor-core operand preparation ("fp16 pair").  src [rows, cols] fp32 (row pitch ld) becomes

@@ -57,7 +57,7 @@ struct F16Operand {
   int split_at;
 };
 constexpr int kScaleBlockFloats = 8;   // [0,1] amax bits, [2,3] inverse scales, [4,5] scales
-inline int ld16_of(int cols) { return (cols + 7) / 8 * 8; }
+inline int ld16_of(int cols) { return (cols + 15) / 16 * 16; }   // rows of fp16 operands start on 32-byte sectors
 // blk[0] <- bit pattern of max |src| (blk is zeroed first)
 int amax_flat(const float* src, size_t n, float* blk, cudaStream_t st);
 // src [rows, cols] (pitch ld) -> hi/lo fp16 [rows, ld16]; two scale groups along split_dim (0 rows, 1 cols) at
