@@ -31,11 +31,22 @@ int bgemm_simt(bool a_kc, bool b_kc, BGemm g, int batches, cudaStream_t st);
 
 // Split-K factor used for the weight-gradient GEMM (contraction over all B*N node rows): keeps
 // every fp32 accumulation chain short (<= ~8K terms) and fills the machine.
-inline int weight_grad_splits(int rows) {
-  int s = (rows + 8191) / 8192;
-  if (s < 1) s = 1;
-  if (s > 32) s = 32;
-  return s;
+inline int weight_grad_splits(int rows, int m, int n) {
+  int base = (rows + 8191) / 8192;
+  if (base < 1) base = 1;
+  if (base > 32) base = 32;
+  if (base == 1) return 1;
+  // among base .. 1.25 base, the count whose (128 x 256 tile, split) work items fill the 148 persistent CTAs' last wave best
+  // (config A: 120 tiles x 15 splits = 12.16 waves, x 16 = 12.97)
+  const int tiles = ((m + 127) / 128) * ((n + 255) / 256);
+  int best = base;
+  double best_eff = 0.0;
+  for (int s = base; s <= base + base / 4 + 1 && s <= 32; ++s) {
+    const int items = tiles * s;
+    const double eff = (double)items / (double)(((items + 147) / 148) * 148);
+    if (eff > best_eff + 1e-9) { best = s; best_eff = eff; }
+  }
+  return best;
 }
 
 // fp32-accurate tensor-core GEMM (tcgen05, 3xTF32, chunked accumulation) on operands pre-split into
