@@ -51,7 +51,7 @@ struct HParams {
   unsigned* amax_out;   // optional: bit pattern of max |C[m, n]| over n < amax_cols (splits == 1 only)
   int amax_cols;
   int single;           // 1: half-precision class (gemm_algo 3): only the A_hi * B_hi product, lo tiles not even loaded
-  int tma_store;        // 1: C tiles leave through TMA bulk stores (splits == 1, 16-byte aligned rows); 0: st.global
+  int tma_store;        // 1: C tiles / split-K partials leave through TMA bulk stores (16-byte aligned rows); 0: st.global
   int dbg;              // bring-up probe (env SPOTV2_GEMM_DBG): bit 0 skip the global stores, bit 1 skip scale + amax,
                         // bit 2 skip the per-chunk register accumulation (results are then wrong: timing only)
 };
@@ -273,8 +273,8 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           __syncwarp();
           if (lane == 0) {
             if (col0 + cc * 16 < p.N && row_base < p.M)
-              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
-                           "r"(smem_u32(hb)), "r"(col0 + cc * 16), "r"(row_base)
+              asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmC),
+                           "r"(smem_u32(hb)), "r"(col0 + cc * 16), "r"(row_base), "r"(sp)
                            : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");       // always commit: keeps the group count in step with cc
           }
@@ -617,8 +617,11 @@ int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, c
   int rc;
   memset(&tC, 0, sizeof(tC));
   p.tma_store = 0;
-  if (p.splits == 1 && aligned16(C) && ldc % 4 == 0) {      // C tiles through TMA bulk stores: 32-row x 16-column fp32 boxes, 64B swizzle
-    if ((rc = make_tmap(&tC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if (aligned16(p.C) && p.ldc % 4 == 0 && (p.splits == 1 || p.split_stride % 4 == 0)) {
+    // C tiles (or split-K partials: plane = split) through TMA bulk stores: 32-row x 16-column fp32 boxes, 64B swizzle
+    if ((rc = make_tmap3(&tC, p.C, (uint64_t)p.splits, p.splits > 1 ? p.split_stride : (uint64_t)M * p.ldc, (uint64_t)M, (uint64_t)N,
+                         (uint64_t)p.ldc, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B)))
+      return rc;
     p.tma_store = 1;
   }
   // K-major operand: tensor [rows = M|N, cols = K], box TBK(k) x tile rows (rows of 128 or 64 bytes).
