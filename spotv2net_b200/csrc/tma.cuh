@@ -28,7 +28,8 @@ inline bool tma_available() { return encode_fn() != nullptr; }
 // 2-D tensor [rows, cols] (cols contiguous, row pitch ld elements), box = box_cols x box_rows, given
 // shared-memory swizzle, out-of-bounds elements read as zero.
 inline int make_tmap_typed(CUtensorMap* tm, const void* base, CUtensorMapDataType dtype, size_t elem_bytes, uint64_t rows,
-                           uint64_t cols, uint64_t ld, uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz) {
+                           uint64_t cols, uint64_t ld, uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz,
+                           CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(SPOTV2_ERR_NO_DEVICE, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {cols, rows};
@@ -36,13 +37,13 @@ inline int make_tmap_typed(CUtensorMap* tm, const void* base, CUtensorMapDataTyp
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, dtype, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SPOTV2_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return SPOTV2_OK;
 }
 inline int make_tmap(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
-                     uint32_t box_rows, CUtensorMapSwizzle swz) {
-  return make_tmap_typed(tm, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, sizeof(float), rows, cols, ld, box_cols, box_rows, swz);
+                     uint32_t box_rows, CUtensorMapSwizzle swz, CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
+  return make_tmap_typed(tm, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, sizeof(float), rows, cols, ld, box_cols, box_rows, swz, promo);
 }
 // fp32 tensor [planes][rows][ld >= cols] with a (box_cols x box_rows x 1) box: the output side of the split-K GEMM
 inline int make_tmap3(CUtensorMap* tm, const float* base, uint64_t planes, uint64_t plane_stride, uint64_t rows, uint64_t cols,
