@@ -246,6 +246,11 @@ int spotv2_diag_gemm(int a_kc, int b_kc, int M, int N, int K, const float* A, in
  * Profiling aid only. */
 int spotv2_diag_counters(unsigned long long* host_out, int reset);
 
+/* Split-K factor spotv2_gat_proj_bwd_weight uses for dW_aug[m, n] = sum over `rows` (host-side rule, no device work):
+ * ceil(rows / 8192) clamped to [1, 32], then raised by up to a quarter so that (128 x 256 output tiles) x splits fills
+ * the last wave of the 148 persistent CTAs.  spotv2_gat_workspace_bytes sizes the partial buffers with the same rule. */
+int32_t spotv2_diag_weight_grad_splits(int32_t rows, int32_t m, int32_t n);
+
 #ifdef __cplusplus
 }
 #endif

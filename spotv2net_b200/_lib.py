@@ -56,6 +56,7 @@ SIGNATURES = {
     "spotv2_alpha_to_pyg": (C.c_int, [_DP, _vp, _vp, _vp, _vp]),
     "spotv2_collate_windows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "spotv2_diag_counters": (C.c_int, [_vp, C.c_int]),
+    "spotv2_diag_weight_grad_splits": (_i32, [_i32, _i32, _i32]),
     "spotv2_diag_gemm": (C.c_int, [C.c_int] * 5 + [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int] + [C.c_int] * 4 + [_vp, _sz, _vp]),
 }
 

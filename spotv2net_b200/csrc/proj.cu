@@ -47,6 +47,7 @@ size_t pair_bytes(size_t rows, size_t ld16) { return 2 * round_up(rows * ld16 * 
 }  // namespace
 
 extern "C" int32_t spotv2_gat_ld16(int32_t cols) { return ld16_of(cols); }
+extern "C" int32_t spotv2_diag_weight_grad_splits(int32_t rows, int32_t m, int32_t n) { return weight_grad_splits(rows, m, n); }
 
 extern "C" int spotv2_gat_workspace_bytes(const spotv2_gat_desc* d, size_t* proj_fwd,
                                           size_t* attn_bwd, size_t* proj_bwd) {

@@ -76,3 +76,22 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_host_side_sizing_rules_without_a_gpu():
+    """fp16-pair row pitch and the weight-gradient split-K factor are host-side rules the workspace query shares."""
+    lib = spotv2net_b200.load_library()
+    # rows of fp16 operand pairs start on 32-byte sectors
+    assert [lib.spotv2_gat_ld16(c) for c in (1, 16, 17, 1260, 3012)] == [16, 16, 32, 1264, 3024]
+    # config A: dW_aug [3012, 1260] over 122 880 rows -> 24 x 5 tiles; 16 splits fill 12.97 waves of 148 CTAs (15: 12.16)
+    assert lib.spotv2_diag_weight_grad_splits(4096 * 30, 3012, 1260) == 16
+    # small problems are not split; the factor never exceeds 32 and never drops below ceil(rows / 8192)
+    assert lib.spotv2_diag_weight_grad_splits(30, 3012, 1260) == 1
+    assert lib.spotv2_diag_weight_grad_splits(8192, 64, 64) == 1
+    for rows, m, n in [(20000, 3012, 1260), (122880, 2064, 2048), (10 ** 6, 512, 512), (65536, 100, 100)]:
+        s = lib.spotv2_diag_weight_grad_splits(rows, m, n)
+        base = min(32, max(1, -(-rows // 8192)))
+        assert base <= s <= min(32, base + base // 4 + 1)
+        tiles = -(-m // 128) * -(-n // 256)
+        eff = lambda k: tiles * k / (-(-(tiles * k) // 148) * 148)
+        assert eff(s) >= eff(base) - 1e-12
