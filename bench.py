@@ -152,8 +152,12 @@ def run_reference(args):
 class HotPath:
     """The hot path through the C ABI on preallocated buffers (what GATConv.forward/backward call)."""
 
-    def __init__(self, B: int, device, seed: int, structured: bool = False):
+    def __init__(self, B: int, device, seed: int, structured: bool = False, first: int = 0, total: int = 0):
+        """B graphs = windows [first, first + B) of a synthetic stack holding `total` (default B) windows; weights, data
+        and dout are functions of (seed, total) only, so ranks given the same seed and disjoint window ranges hold
+        shards of one global batch (dp_selfcheck)."""
         self.structured = structured
+        total = total or B
         import spotv2net_b200 as sv
         from spotv2net_b200 import _lib
         self.sv, self._lib = sv, _lib
@@ -162,13 +166,14 @@ class HotPath:
         N, Fin, Fe, H, Cc = cfg_dims()
         self.B, self.N, self.Fin, self.Fe, self.H, self.Cc = B, N, Fin, Fe, H, Cc
         g = torch.Generator(device=device).manual_seed(seed)
-        T = B + CFG["L"] + 1
+        T = total + CFG["L"] + 1
         mats = []
         for _ in range(2):                       # synthetic standardized H5 content: symmetric N(0,1) [T, N, N]
             a = torch.randn(T, N, N, device=device, generator=g)
             mats.append((a + a.transpose(1, 2)) / 2 ** 0.5)
         self.ds = sv.WindowDataset(mats[0], mats[1], seq_length=CFG["L"], device=device, drop_first=0)
-        self.batch = self.ds.collate(torch.arange(B))
+        self.batch = self.ds.collate(torch.arange(first, first + B))
+        self.win = sv.WindowSource(self.ds.volvol, torch.arange(first, first + B, device=device, dtype=torch.int32), CFG["L"], checked=True)
         torch.manual_seed(seed)
         self.layer = sv.GATConv(Fin, Cc, heads=H, concat=False, negative_slope=CFG["slope"], edge_dim=Fe).to(device)
         n, HC = B * N, H * Cc
@@ -195,7 +200,7 @@ class HotPath:
         _lib.check(self.lib.spotv2_edge_terms_from_windows_workspace_bytes(C.byref(self.desc), C.byref(wet)), "edge_terms ws")
         self.ws_w = torch.empty(wet.value, device=device, dtype=torch.uint8) if (structured and wet.value) else None
         self.out = torch.empty(n, Cc, **f32)
-        self.dout = torch.randn(n, Cc, generator=g, **f32)
+        self.dout = torch.randn(total * N, Cc, generator=g, **f32)[first * N:(first + B) * N].contiguous()
         self.tc = bool(self.lib.spotv2_gat_uses_tensor_cores(C.byref(self.desc)))
         # tensor-core operand pairs (scaled fp16 hi/lo + 8-float scale block): x once per step, dP from attn_bwd
         f16 = dict(device=device, dtype=torch.float16)
@@ -243,7 +248,7 @@ class HotPath:
         chk(lib.spotv2_proj_fwd(d, p(self.batch.x), p(xh), p(xl), p(self.x_blk), p(self.W_aug), p(self.P_aug), p(self.p_amax),
                                 p(self.ws), self.ws.numel(), st), "proj_fwd")
         mark("proj_fwd")
-        win = self.batch.spot_windows
+        win = self.win
         if self.structured:      # structured edge source: the [L,N,N] windows instead of the materialised edge rows
             chk(lib.spotv2_edge_terms_from_windows(d, p(win.volvol), win.volvol.shape[0], win.L, p(win.t0), p(self.v),
                                                    p(self.edge_terms), p(self.ws_w), self.ws_w.numel() if self.ws_w is not None else 0,
@@ -301,6 +306,7 @@ def run_ours(args):
             os.dup2(saved, 1)
             os.close(saved)
     B = args.batch
+    dp_check = dp_selfcheck(dev, rank, world) if world > 1 else None
     hp = HotPath(B, dev, seed=1234 + rank)
 
     def allreduce(t):
@@ -455,11 +461,39 @@ def run_ours(args):
                              f"P {B * N * H * Cc * 4 / 1e6:.0f} MB per step) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"dp{world}", "launch": "eager launches, CUDA events between the entry points"},
             "phase_ms": phase_ms, "roofline": roofline, "roofline_projection": proj, "cpu_baseline": cpu_baseline,
-            "cuda_graph_replay": graph_info, "structured_edge_source": structured, "e2e": e2e, "e2e_windows": e2e_win, "gpu_launches": hp.kernels_per_step * args.steps, "clocks": clocks,
+            "dp_gradient_check": dp_check, "cuda_graph_replay": graph_info, "structured_edge_source": structured, "e2e": e2e, "e2e_windows": e2e_win, "gpu_launches": hp.kernels_per_step * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def dp_selfcheck(dev, rank, world, per_rank: int = 64):
+    """N > 1 correctness on the hardware being timed (SURVEY.md:279): every rank runs its shard (64 graphs) of ONE global
+    batch through the hot path and the arena is all-reduced exactly as in the timed loop; rank 0 also runs the whole
+    concatenated batch on its own GPU.  AVG-all-reduced arena x world must equal the single-GPU gradient to 1e-5
+    (max-norm relative, per parameter tensor).  Raises on mismatch: a wrong multi-GPU number is never printed."""
+    import torch.distributed as dist
+    hp = HotPath(per_rank, dev, seed=4321, first=rank * per_rank, total=world * per_rank)
+    hp.step(allreduce=lambda t: dist.all_reduce(t, op=dist.ReduceOp.AVG))
+    torch.cuda.synchronize(dev)
+    worst = torch.zeros(1, device=dev, dtype=torch.float64)
+    if rank == 0:
+        full = HotPath(world * per_rank, dev, seed=4321)
+        full.step()
+        torch.cuda.synchronize(dev)
+        for mine, ref in zip((hp.g_W, hp.g_as, hp.g_ad, hp.g_We, hp.g_ae, hp.g_b),
+                             (full.g_W, full.g_as, full.g_ad, full.g_We, full.g_ae, full.g_b)):
+            err = ((mine.double() * world - ref.double()).abs().max() / ref.double().abs().max()).item()
+            worst[0] = max(worst.item(), err)
+        del full
+    dist.broadcast(worst, 0)
+    del hp
+    torch.cuda.empty_cache()
+    if not worst.item() <= 1e-5:
+        raise SystemExit(f"bench.py: all-reduced gradient differs from the single-GPU gradient on the concatenated batch "
+                         f"by {worst.item():.2e} (> 1e-5)")
+    return {"max_rel_err_vs_single_gpu": worst.item(), "graphs": world * per_rank, "ok": True}
 
 
 def run_structured(args, dev, world, rank, barrier):

@@ -39,12 +39,12 @@ int check_desc(const spotv2_gat_desc* d) {
 }
 
 int sm_count() {
-  static int cached = 0;
-  if (cached) return cached;
+  static int cached[64] = {0};          // per device: ranks of one process may drive different GPUs
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev];
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-  cached = n;
+  if (dev >= 0 && dev < 64) cached[dev] = n;
   return n;
 }
 

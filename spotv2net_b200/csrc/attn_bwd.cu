@@ -706,7 +706,8 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
   if (f16) {
     a.dsd = reinterpret_cast<float*>(w + part);
     // |dP_h[j,c]| = |g sum_i alpha_h[i,j] dO[i,c]| <= g N max|dout|  (g = 1/H for the head mean)
-    a.bound = (float)d->N * (d->concat ? 1.f : 1.f / (float)d->H);
+    // (attention dropout scales the kept coefficients by 1/(1-p): the bound grows with it)
+    a.bound = (float)d->N * (d->concat ? 1.f : 1.f / (float)d->H) * a.p.drop.scale;
     SPOTV2_CUDA_OK(cudaMemsetAsync(dp_scale_or_null, 0, kScaleBlockFloats * sizeof(float), st));
   }
   const int np = (d->N + 1) / 2;

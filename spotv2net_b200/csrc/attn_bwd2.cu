@@ -423,7 +423,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
   const float s_P = dp_scale_from_amax(__uint_as_float(*reinterpret_cast<const unsigned*>(args.p_amax)));
   constexpr float s_al = 16384.f;
   const float k_dalpha = g_scale / (s_dO * s_P);                 // accumulator -> dalpha
-  const float k_dp = g_scale * dp_scale / (s_al * s_dO);          // accumulator -> (scaled) dP
+  const float k_dp = g_scale * dp_scale / (s_al * s_dO) * (DROP ? p.drop.scale : 1.f);   // accumulator -> (scaled) dP
   const bool vec4_out = (C % 4 == 0);     // 8-byte aligned groups of 4 fp16 columns (ldp16 % 8 == 0)
   AttnSmem asm_{};                        // what softmax_phase reads
   asm_.NS = NS; asm_.KS = pl.KS; asm_.NT = 1;
@@ -828,10 +828,12 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
             float2 x1 = j1 < N ? *reinterpret_cast<const float2*>(&tile[(h * N + j1) * NS + ia]) : z;
             if (DROP) {            // alpha[h][source j][target ia | ia+1] * m: keep bits of the TARGET rows, bit = source
               const uint32_t ka = ia < N ? keep_mask[h * N + ia] : 0u, kb = ia + 1 < N ? keep_mask[h * N + ia + 1] : 0u;
-              x0.x = ((ka >> j0) & 1u) ? x0.x * p.drop.scale : 0.f;
-              x0.y = ((kb >> j0) & 1u) ? x0.y * p.drop.scale : 0.f;
-              x1.x = ((ka >> j1) & 1u) ? x1.x * p.drop.scale : 0.f;
-              x1.y = ((kb >> j1) & 1u) ? x1.y * p.drop.scale : 0.f;
+              // the 1/(1-p) factor rides in k_dp (fp32 post-scale), never in the fp16 operand: alpha/(1-p) * 2^14
+              // would leave the fp16 range from p = 0.75 on
+              x0.x = ((ka >> j0) & 1u) ? x0.x : 0.f;
+              x0.y = ((kb >> j0) & 1u) ? x0.y : 0.f;
+              x1.x = ((ka >> j1) & 1u) ? x1.x : 0.f;
+              x1.y = ((kb >> j1) & 1u) ? x1.y : 0.f;
             }
             cvt_pair(x0.x, x0.y, s_al, ah[ks][2 * hf], al[ks][2 * hf]);
             cvt_pair(x1.x, x1.y, s_al, ah[ks][2 * hf + 1], al[ks][2 * hf + 1]);

@@ -52,9 +52,15 @@ struct HParams {
   int amax_cols;
   int single;           // 1: half-precision class (gemm_algo 3): only the A_hi * B_hi product, lo tiles not even loaded
   int tma_store;        // 1: C tiles / split-K partials leave through TMA bulk stores (16-byte aligned rows); 0: st.global
-  int dbg;              // bring-up probe (env SPOTV2_GEMM_DBG): bit 0 skip the global stores, bit 1 skip scale + amax,
-                        // bit 2 skip the per-chunk register accumulation (results are then wrong: timing only)
+  int dbg;              // bring-up probe, compiled in only with -DSPOTV2_BRINGUP (env SPOTV2_GEMM_DBG): bit 0 skip the
+                        // global stores, bit 1 skip scale + amax, bit 2 skip the per-chunk register accumulation
+                        // (results are then wrong: timing only).  The product library carries none of it.
 };
+#ifdef SPOTV2_BRINGUP
+#define SPOTV2_DBG(p) ((p).dbg)
+#else
+#define SPOTV2_DBG(p) 0
+#endif
 
 template <int BN, int TBK, bool A_KM, bool B_KM>
 struct HSmem {
@@ -226,7 +232,7 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           uint32_t r[32];
           tmem_ld32(taddr + c0, r);
 #pragma unroll
-          if (!(p.dbg & 4))
+          if (!(SPOTV2_DBG(p) & 4))
 #pragma unroll
             for (int e = 0; e < 32; ++e) acc[c0 + e] += __uint_as_float(r[e]);   // round-to-nearest adds
           else acc[c0] += __uint_as_float(r[0]);
@@ -238,7 +244,7 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
       const int row = mt * HBM_ + q * 32 + lane;
       const int col0 = nt * BN + ch * HALF;
       float row_amax = 0.f;
-      if (row < p.M && col0 < p.N && !(p.dbg & 2)) {
+      if (row < p.M && col0 < p.N && !(SPOTV2_DBG(p) & 2)) {
         if (p.scale_in_kernel) {      // powers of two: exact
           const float ra = p.a_inv ? p.a_inv[row >= p.a_split ? 1 : 0] : 1.f;
           const float cb0 = ra * (p.b_inv ? p.b_inv[0] : 1.f), cb1 = ra * (p.b_inv ? p.b_inv[1] : 1.f);
@@ -253,7 +259,7 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           row_amax = mx;
         }
       }
-      if (p.tma_store && !(p.dbg & 1)) {
+      if (p.tma_store && !(SPOTV2_DBG(p) & 1)) {
         // Asynchronous stores (measured: with st.global the epilogue warps sat in the LSU queue for ~0.5 ms of the K = 1260
         // product while the MMA warp waited for them to drain TMEM).  Each warp parks 32 x 16 pieces of its block in two
         // alternating swizzled shared-memory boxes and one lane hands each to the TMA engine; the warp only waits for the
@@ -279,7 +285,7 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");       // always commit: keeps the group count in step with cc
           }
         }
-      } else if (!(p.dbg & 1)) {
+      } else if (!(SPOTV2_DBG(p) & 1)) {
         // Stores: a lane owns an output ROW, so storing straight from registers makes every warp store touch 32 rows
         // (16 bytes each; ncu showed the LSU queue throttling the K = 1260 product).  Instead each 32 x 32 block goes
         // through a padded shared-memory transpose and leaves as 32 stores of 128 contiguous bytes.
@@ -592,6 +598,8 @@ int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, c
   p.amax_out = reinterpret_cast<unsigned*>(amax_out);
   p.amax_cols = amax_cols;
   p.single = single ? 1 : 0;
+  p.dbg = 0;
+#ifdef SPOTV2_BRINGUP
   {
     // bring-up probe (tools/gemm_fill_probe.py): skips parts of the epilogue to time them; results are WRONG when set
     static const int dbg = [] {
@@ -602,6 +610,7 @@ int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, c
     }();
     p.dbg = dbg;
   }
+#endif
   if (amax_out) {
     if (splits > 1) return fail(SPOTV2_ERR_INVALID_ARG, "gemm3x_f16: amax_out needs splits == 1");
     SPOTV2_CUDA_OK(cudaMemsetAsync(amax_out, 0, sizeof(float), st));

@@ -143,14 +143,16 @@ class WindowDataset:
         ea = None if self.structured else torch.empty(B * N * (N - 1), 3 * L, device=dev, dtype=torch.float32)
         y = torch.empty(B * N, device=dev, dtype=torch.float32)
         lib = _lib.load()
-        check(lib.spotv2_collate_windows(ptr(self.vol), ptr(self.volvol), self.T, N, L, ptr(t0), B, ptr(x), ptr(ea),
-                                         ptr(y), stream_ptr(dev)), "spotv2_collate_windows")
+        with torch.cuda.device(dev):
+            check(lib.spotv2_collate_windows(ptr(self.vol), ptr(self.volvol), self.T, N, L, ptr(t0), B, ptr(x), ptr(ea),
+                                             ptr(y), stream_ptr(dev)), "spotv2_collate_windows")
         if self.future_steps is not None:        # [B, K, N] gather of the next K diagonals -> [B*N*K], node major
             K = self.future_steps
             t = (t0.to(torch.int64) + L).view(B, 1) + torch.arange(K, device=dev).view(1, K)
             y = self.vol.diagonal(dim1=1, dim2=2)[t].permute(0, 2, 1).reshape(-1).contiguous()
         ei, topo = batched_topology(B, N, dev)
-        return SpotBatch(x, ei, ea, y, B, N, topo, WindowSource(self.volvol, t0, L))
+        # window references ride only on structured batches: with a materialised edge_attr the layers must use it
+        return SpotBatch(x, ei, ea, y, B, N, topo, WindowSource(self.volvol, t0, L, checked=True) if self.structured else None)
 
     def __getitem__(self, k):
         if isinstance(k, slice):

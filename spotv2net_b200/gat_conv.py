@@ -32,6 +32,7 @@ class WindowSource:
     volvol: Tensor         # [T, N, N] fp32 on the device
     t0: Tensor             # [B] int32 on the device
     L: int                 # seq_length; edge_dim must be 3 * L
+    checked: bool = False  # t0 + L <= T already verified (WindowDataset.collate checks on the host)
 
 
 @dataclass
@@ -65,8 +66,9 @@ def _try_topology(edge_index: Tensor, n_nodes: int, N: int) -> Optional[Topology
     dev = edge_index.device
     table = torch.empty(R, dtype=torch.int32, device=dev)
     status = torch.empty(4 + N * N, dtype=torch.int32, device=dev)
-    check(lib.spotv2_edge_table_build(ptr(edge_index), E, B, N, R, ptr(table), ptr(status), stream_ptr(dev)),
-          "spotv2_edge_table_build")
+    with torch.cuda.device(dev):
+        check(lib.spotv2_edge_table_build(ptr(edge_index), E, B, N, R, ptr(table), ptr(status), stream_ptr(dev)),
+              "spotv2_edge_table_build")
     ok, where, reason = status[:3].tolist()              # one sync per new topology
     if not ok:
         _try_topology.last_failure = f"{_REASONS.get(reason, reason)} (first offending index {where})"
@@ -157,6 +159,13 @@ class _GatLayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, edge_attr, W, a_src, a_dst, W_e, a_edge, bias, topo, H, Cc, concat, slope, want_alpha,
                 dropout_p=0.0, seed=0, gemm_algo=None, windows=None):
+        with torch.cuda.device(x.device):        # launches, attribute calls and tensor maps go to the CURRENT device
+            return _GatLayerFn._forward(ctx, x, edge_attr, W, a_src, a_dst, W_e, a_edge, bias, topo, H, Cc, concat, slope,
+                                        want_alpha, dropout_p, seed, gemm_algo, windows)
+
+    @staticmethod
+    def _forward(ctx, x, edge_attr, W, a_src, a_dst, W_e, a_edge, bias, topo, H, Cc, concat, slope, want_alpha,
+                 dropout_p, seed, gemm_algo, windows):
         lib = _lib.load()
         dev = x.device
         st = stream_ptr(dev)
@@ -220,6 +229,11 @@ class _GatLayerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _dalpha=None):
+        with torch.cuda.device(dout.device):
+            return _GatLayerFn._backward(ctx, dout)
+
+    @staticmethod
+    def _backward(ctx, dout):
         lib = _lib.load()
         x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk, p_amax, et = ctx.saved_tensors
         desc, topo, Fe = ctx.desc, ctx.topo, ctx.Fe
@@ -383,6 +397,22 @@ class GATConv(nn.Module):
             if edge_attr.dim() == 1:
                 edge_attr = edge_attr.view(-1, 1)
         topo = topology or topology_from_edge_index(edge_index, x.shape[0], self.nodes_per_graph)
+        # a caller-supplied topology / window source is checked against this call's tensors: a Topology built for
+        # another batch size would make the kernels read and write past x / out
+        if x.shape[0] != topo.B * topo.N:
+            raise SpotV2Error(f"topology describes {topo.B} graphs of {topo.N} nodes, x has {x.shape[0]} rows")
+        if torch.is_tensor(edge_index) and edge_index.dim() == 2 and edge_index.shape[1] != topo.B * topo.R:
+            raise SpotV2Error(f"topology describes {topo.B * topo.R} edges, edge_index has {edge_index.shape[1]}")
+        if windows is not None:
+            if edge_attr is not None:
+                windows = None          # a materialised edge_attr always wins (the caller may have edited it)
+            elif windows.volvol.dim() != 3 or windows.volvol.shape[1] != topo.N or windows.volvol.shape[2] != topo.N:
+                raise SpotV2Error("windows.volvol must be [T, N, N] with this batch's N")
+            elif int(windows.t0.numel()) == topo.B and not windows.checked:
+                t_hi = int(windows.t0.max().item()) + windows.L          # once per WindowSource (one sync)
+                if int(windows.t0.min().item()) < 0 or t_hi > windows.volvol.shape[0]:
+                    raise SpotV2Error(f"window [t0, t0 + L) reaches {t_hi} past the {windows.volvol.shape[0]} matrices")
+                windows.checked = True
         # structured edge source (batches of spotv2net_b200.WindowDataset): usable when this layer's edge_dim is the
         # dataset's 3L on graphs the fused kernels cover; otherwise the materialised edge_attr is required
         had_windows = windows is not None
@@ -417,8 +447,9 @@ class GATConv(nn.Module):
                        float(self.negative_slope), lib.spotv2_gat_ldp(H, self.out_channels), 0, 0, 0.0, 0, 0, 0)
         n = topo.B * topo.N
         alpha = torch.empty(topo.B * topo.R + n, H, device=dev, dtype=torch.float32)
-        check(lib.spotv2_alpha_to_pyg(C.byref(desc), ptr(alpha_tile), ptr(topo.table), ptr(alpha), stream_ptr(dev)),
-              "spotv2_alpha_to_pyg")
+        with torch.cuda.device(dev):
+            check(lib.spotv2_alpha_to_pyg(C.byref(desc), ptr(alpha_tile), ptr(topo.table), ptr(alpha), stream_ptr(dev)),
+                  "spotv2_alpha_to_pyg")
         loops = torch.arange(n, device=dev, dtype=edge_index.dtype)
         if topo.has_skips:                               # PyG drops input self loops before appending its own
             keep = edge_index[0] != edge_index[1]

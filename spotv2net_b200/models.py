@@ -84,7 +84,9 @@ class GATModel(nn.Module):
             self.attention_weights = []
         # batches of a structured WindowDataset carry window references: the layers read the [L, N, N] windows instead of
         # edge_attr (not with standardize=True: BatchNorm changes the edge features, which then must be materialised)
-        win = None if self.standardize else getattr(data, "spot_windows", None)
+        # A materialised edge_attr always wins: the caller may have edited it (train() scales it by scale_up,
+        # 5_train_SpotV2Net.py:145-147), and the windows would silently ignore that.
+        win = None if (self.standardize or edge_attr is not None) else getattr(data, "spot_windows", None)
         for layer in self.gat_layers:
             if self.collect_attention:
                 x, att = layer(x, edge_index, edge_attr, return_attention_weights=True, topology=topo, windows=win)

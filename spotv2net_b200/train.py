@@ -23,6 +23,7 @@ import yaml
 
 from .data import WindowDataset, WindowLoader, load_matrix_stack
 from .dp import FlatGradArena, shard_snapshots
+from .gat_conv import WindowSource
 from .models import GATModel
 
 
@@ -57,9 +58,15 @@ def build_optimizer(p: dict, params):
 
 
 def _scaled(batch, scale):
+    """5_train_SpotV2Net.py:145-147 / 173-175: x, edge_attr and the targets times ``scale_up``.  A structured batch
+    has no edge_attr to scale: its edge features are the vol-of-vol windows, so the window stack is scaled instead."""
     if scale:
         batch.x = batch.x * scale
-        batch.edge_attr = batch.edge_attr * scale
+        if batch.edge_attr is not None:
+            batch.edge_attr = batch.edge_attr * scale
+        win = getattr(batch, "spot_windows", None)
+        if win is not None:
+            batch.spot_windows = WindowSource(win.volvol * scale, win.t0, win.L, win.checked)
         batch.y_x = batch.y_x * scale
     return batch
 

@@ -28,17 +28,43 @@ def relerr(a, ref):
     return ((a - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
 
 
+# (test-name fragment, tensor) pairs that may pass on the "within 3x the fp32 oracle's own error" allowance instead of
+# the 1e-5 bar.  Everything else must meet 1e-5 outright.  Filled from a recording run on the B200
+# (SPOTV2_PARITY_RECORD=<file> logs every use instead of asserting; tools/runs/ keeps the log it was filled from).
+ALLOWANCE_WHITELIST = {
+}
+ALLOWANCE_USED = []          # (test id, tensor, our error, fp32-oracle error) of this session, for the report
+
+
+def _current_test():
+    return os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0].split("::")[-1]
+
+
 def parity_failures(ours: dict, ref64: dict, ref32: dict, tol=TOL):
     """The bar: ||ours - ref64||_inf / ||ref64||_inf <= 1e-5.  Some gradients are ill-conditioned in
     fp32 whatever the implementation (d/d att_dst sums softmax-gradient rows that cancel to ~0; with
     N = 2 several gradients are identically zero): for those the PyG-order fp32 oracle itself misses
-    1e-5, so a tensor also passes when our error is within 3x the fp32 oracle's own error against fp64."""
+    1e-5, so a tensor ALSO passes when our error is within 3x the fp32 oracle's own error against fp64 -
+    but only for the (test, tensor) pairs listed in ALLOWANCE_WHITELIST; any other use is a failure."""
     bad = {}
+    test = _current_test()
     for k, r64 in ref64.items():
         e = relerr(ours[k], r64)
+        if e <= tol:
+            continue
         e32 = relerr(ref32[k], r64)
-        if not (e <= tol or e <= 3.0 * e32):
-            bad[k] = (e, e32)
+        if e <= 3.0 * e32:
+            ALLOWANCE_USED.append((test, k, e, e32))
+            rec = os.environ.get("SPOTV2_PARITY_RECORD")
+            if rec:
+                with open(rec, "a") as f:
+                    f.write(f"{test}\t{k}\t{e:.3e}\t{e32:.3e}\n")
+                continue
+            if any(frag in test and k == name for frag, name in ALLOWANCE_WHITELIST):
+                continue
+            bad[k] = (e, e32, "used the 3x-fp32 allowance without being whitelisted")
+            continue
+        bad[k] = (e, e32)
     return bad
 
 
@@ -446,9 +472,25 @@ def test_attention_dropout_in_training_mode_replays_in_the_oracle(cuda_lib, case
         gat_conv.ATTN_BWD_ALGO = old_algo
 
 
-def _dropout_case(B, N, Fin, Fe, H, C_, concat, pdrop):
+@pytest.mark.parametrize("bwd_algo", [0, 1], ids=["pipelined_bwd", "serial_bwd"])
+@pytest.mark.parametrize("pdrop", [0.7, 0.9])
+def test_attention_dropout_at_high_rates_with_peaked_rows(cuda_lib, pdrop, bwd_algo):
+    """p = 0.7 is the top of the reference's HPO range, 0.9 is beyond it; GATConv accepts any p in [0, 1).  Weights
+    scaled x4 concentrate the softmax (rows with one coefficient near 1), so kept coefficients reach 1/(1-p) = 10:
+    the backward's fp16 operands must not carry that factor (it rides in the fp32 post-scale) and the bound that
+    sizes the dP scale must include it."""
+    from spotv2net_b200 import gat_conv
+    old_algo = gat_conv.ATTN_BWD_ALGO
+    gat_conv.ATTN_BWD_ALGO = bwd_algo
+    try:
+        _dropout_case(6, 30, 40, 126, 6, 20, False, pdrop, wscale=4.0)
+    finally:
+        gat_conv.ATTN_BWD_ALGO = old_algo
+
+
+def _dropout_case(B, N, Fin, Fe, H, C_, concat, pdrop, wscale=1.0):
     import copy
-    ref, ours = make_layers(Fin, C_, H, concat, Fe, 0.2, seed=N)
+    ref, ours = make_layers(Fin, C_, H, concat, Fe, 0.2, seed=N, wscale=wscale)
     ours.dropout = ref.dropout = pdrop
     bt = synth.random_complete_batch(B, N, Fin, Fe, seed=31)
     dout = torch.randn(B * N, H * C_ if concat else C_)
@@ -918,6 +960,35 @@ def test_structured_and_materialised_model_steps_agree(cuda_lib):
         sv.GATModel(**dict(kw, standardize=True)).to(DEV)(ds.collate([0, 1]))      # BatchNorm needs the edge features
 
 
+def test_scale_up_reaches_the_edge_features_on_both_batch_kinds(cuda_lib):
+    """train()'s scale_up multiplies x, edge_attr and y_x (5_train_SpotV2Net.py:145-147).  A materialised batch must use
+    the scaled edge_attr (never the raw windows), a structured batch gets its window stack scaled: same loss, same
+    gradients, and both differ from the un-scaled edge features."""
+    from spotv2net_b200.train import _scaled
+    N, L, B = 30, 5, 6
+    vol, vv = synth.synthetic_matrices(L + B + 2, N, seed=9)
+    torch.manual_seed(3)
+    model = sv.GATModel(N * L, 3 * L, 3, 1, [12]).to(DEV)
+    res = []
+    for structured in (False, True):
+        ds = sv.WindowDataset(vol, vv, seq_length=L, device=DEV, drop_first=0, structured=structured)
+        bt = _scaled(ds.collate(list(range(B))), 50.0)
+        model.zero_grad()
+        loss = torch.nn.functional.mse_loss(model(bt), bt.y_x)
+        loss.backward()
+        res.append((loss.item(), {k: p.grad.clone() for k, p in model.named_parameters()}))
+    ref = pyg_gat.OracleGATModel(N * L, 3 * L, 3, 1, [12]).double()
+    ref.load_state_dict({k: v.double().cpu() for k, v in model.state_dict().items()})
+    bt = synth.make_batch(vol, vv, list(range(B)), L)
+    bt.x, bt.edge_attr, bt.y_x = bt.x.double() * 50.0, bt.edge_attr.double() * 50.0, bt.y_x.double() * 50.0
+    loss_ref = torch.nn.functional.mse_loss(ref(bt), bt.y_x)
+    loss_ref.backward()
+    for loss, grads in res:
+        assert abs(loss - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
+        for k, p in ref.named_parameters():
+            assert relerr(grads[k], p.grad) < 1e-4, k          # through a ReLU (kinks): same bar as the two-path test above
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_full_batch_properties(cuda_lib):
     """B = 4096 at the default geometry (BASELINE config 2).  The oracle cannot run this size, so:
@@ -961,8 +1032,57 @@ def test_full_batch_properties(cuda_lib):
     assert relerr(acc, gW) < TOL
 
 
+def test_full_batch_gradients_match_chunked_oracle(cuda_lib):
+    """B = 4096 at the default geometry: EVERY parameter gradient against the fp64 edge-list oracle.  The oracle
+    cannot hold 4096 graphs (2 x 44 GB of PyG intermediates), but its parameter gradients are sums over graphs, so it
+    runs in 64 chunks of 64 graphs and autograd accumulates them in fp64.  Covers what the small cases cannot: the
+    per-CTA partial reductions of dv / dbias / ds|dd over 4096 graphs on 148 CTAs and the 16-way split-K of the
+    weight-gradient GEMM (what the reference does in one pass: 5_train_SpotV2Net.py:150-159)."""
+    import copy
+    B, N, L, H, C_ = 4096, 30, 42, 6, 500
+    Fin, Fe, chunk = N * L, 3 * L, 64
+    torch.manual_seed(11)
+    ref = pyg_gat.OracleGATConv(Fin, C_, heads=H, concat=False, edge_dim=Fe)
+    with torch.no_grad():
+        ref.bias.normal_()
+    ours = sv.GATConv(Fin, C_, heads=H, concat=False, edge_dim=Fe)
+    ours.load_state_dict(ref.state_dict())
+    ours.to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(B * N, Fin, device=DEV, generator=g)
+    ea = torch.randn(B * N * (N - 1), Fe, device=DEV, generator=g)
+    dout = torch.randn(B * N, C_, device=DEV, generator=g)
+    ei, _ = sv.batched_topology(B, N, DEV)
+    out = ours(x, ei, ea)
+    out.backward(dout)
+    torch.cuda.synchronize()
+    ei_c = sv.batched_topology(chunk, N, "cuda:0")[0].cpu()
+    torch.set_num_threads(os.cpu_count() or 1)
+
+    def oracle_grads(dtype):
+        m = copy.deepcopy(ref).to(dtype)
+        worst = 0.0
+        for c0 in range(0, B, chunk):
+            rows, erows = slice(c0 * N, (c0 + chunk) * N), slice(c0 * N * (N - 1), (c0 + chunk) * N * (N - 1))
+            o = m(x[rows].cpu().to(dtype), ei_c, ea[erows].cpu().to(dtype))
+            o.backward(dout[rows].cpu().to(dtype))            # .grad accumulates over the chunks
+            worst = max(worst, relerr(out[rows], o.detach()))
+        return {"g_" + k: p.grad for k, p in m.named_parameters()}, worst
+
+    g64, worst_out = oracle_grads(torch.float64)
+    assert worst_out < TOL, worst_out
+    mine = {"g_" + k: p.grad for k, p in ours.named_parameters()}
+    errs = {k: relerr(mine[k], g64[k]) for k in g64}
+    print("B=4096 gradient errors vs the chunked fp64 oracle:", {k: f"{v:.2e}" for k, v in errs.items()})
+    bad = {}
+    if max(errs.values()) > TOL:        # only then pay for the fp32 oracle (calibrates ill-conditioned sums; whitelisted uses only)
+        bad = parity_failures(mine, g64, oracle_grads(torch.float32)[0])
+    assert not bad, f"(our error, fp32-oracle error) above the bar at B=4096: {bad}"
+
+
 # ------------------------------------------------------------------ the caller: training harness
-def test_training_harness_loss_curve_matches_oracle_loop(cuda_lib, tmp_path):
+@pytest.mark.parametrize("scale_up", [None, 100.0], ids=["no_scale_up", "scale_up_100"])
+def test_training_harness_loss_curve_matches_oracle_loop(cuda_lib, tmp_path, scale_up):
     """spotv2net_b200.train.train (5_train_SpotV2Net.py:23-203 restated) against the same loop run with the
     oracle model on the CPU: same seed, same split, same shuffle, Adam; per-epoch train/test losses agree."""
     from spotv2net_b200.train import train
@@ -971,7 +1091,7 @@ def test_training_harness_loss_curve_matches_oracle_loop(cuda_lib, tmp_path):
     p = dict(modelname="t", modeltype="gat", seq_length=L, batch_size=8, dim_hidden_layers=[16], output_node_channels=1,
              num_heads=3, concat_heads=True, activation="relu", optimizer="adam", learning_rate=1e-3, negative_slope=0.2,
              dropout_att=0.0, dropout=0.0, standardize=False, num_epochs=2, tolerance=1e-9, split_proportion=0.8,
-             scale_up=None, seed=5)
+             scale_up=scale_up, seed=5)      # scale_up: x, edge_attr AND targets scaled (5_train_SpotV2Net.py:145-147)
     tr, te = train(p=dict(p), vol=vol, volvol=vv, device=DEV, output_root=str(tmp_path), drop_first=2, verbose=False)
     assert os.path.exists(tmp_path / "t_3" / "t_weights_seed_5.pth") and os.path.exists(tmp_path / "t_3" / "test_losses_seed_5.npy")
     # oracle loop
@@ -983,12 +1103,18 @@ def test_training_harness_loss_curve_matches_oracle_loop(cuda_lib, tmp_path):
     gen = torch.Generator().manual_seed(5)
     crit = torch.nn.MSELoss()
     tr_ref, te_ref = [], []
+
+    def scaled(bt):
+        if scale_up:
+            bt.x, bt.edge_attr, bt.y_x = bt.x * scale_up, bt.edge_attr * scale_up, bt.y_x * scale_up
+        return bt
+
     for _ in range(2):
         model.train()
         order = torch.randperm(n_train, generator=gen)
         tot, steps = 0.0, 0
         for s in range(0, n_train, 8):
-            bt = synth.make_batch(vol, vv, [int(i) + 2 for i in order[s:s + 8]], L)
+            bt = scaled(synth.make_batch(vol, vv, [int(i) + 2 for i in order[s:s + 8]], L))
             loss = crit(model(bt), bt.y_x)
             opt.zero_grad(); loss.backward(); opt.step()
             tot += loss.item(); steps += 1
@@ -997,7 +1123,7 @@ def test_training_harness_loss_curve_matches_oracle_loop(cuda_lib, tmp_path):
         tot, nb = 0.0, 0
         with torch.no_grad():
             for s in range(n_train, n, 8):
-                bt = synth.make_batch(vol, vv, [i + 2 for i in range(s, min(s + 8, n))], L)
+                bt = scaled(synth.make_batch(vol, vv, [i + 2 for i in range(s, min(s + 8, n))], L))
                 tot += crit(model(bt), bt.y_x).item(); nb += 1
         te_ref.append(tot / nb)
     assert np.allclose(tr, tr_ref, rtol=2e-4) and np.allclose(te, te_ref, rtol=2e-4), (tr, tr_ref, te, te_ref)
