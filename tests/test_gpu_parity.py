@@ -32,6 +32,15 @@ def relerr(a, ref):
 # the 1e-5 bar.  Everything else must meet 1e-5 outright.  Filled from a recording run on the B200
 # (SPOTV2_PARITY_RECORD=<file> logs every use instead of asserting; tools/runs/ keeps the log it was filled from).
 ALLOWANCE_WHITELIST = {
+    # d/d att_dst = sum over sources of softmax-gradient rows, which cancel to ~0 (a softmax row's gradient sums to
+    # zero): the fp32 PyG-order oracle itself is at 1.5e-4 / 2e-5 on these cases (tools/runs/r2a_allowance.tsv)
+    ("test_layer_matches_edge_list_oracle[B3N12F16Fe8H7C12mean", "g_att_dst"),
+    ("test_attention_dropout_at_high_rates_with_peaked_rows", "g_att_dst"),
+    # N = 2, H = 1: one real source per target, so these three gradients are identically zero in exact arithmetic and
+    # the "relative error" compares rounding noise with rounding noise (ours 3e8..1e9, fp32 oracle 4e8..1.4e9)
+    ("test_layer_matches_edge_list_oracle[B2N2F4Fe3H1C2cat", "g_att_dst"),
+    ("test_layer_matches_edge_list_oracle[B2N2F4Fe3H1C2cat", "g_att_edge"),
+    ("test_layer_matches_edge_list_oracle[B2N2F4Fe3H1C2cat", "g_lin_edge.weight"),
 }
 ALLOWANCE_USED = []          # (test id, tensor, our error, fp32-oracle error) of this session, for the report
 
@@ -529,7 +538,7 @@ def _dropout_case(B, N, Fin, Fe, H, C_, concat, pdrop, wscale=1.0):
     assert not bad, bad
     ours.eval()                                                          # eval mode: no dropout
     out_eval, (_, a_eval) = ours(xg, eig, eag, return_attention_weights=True)
-    assert (a_eval > 0).all()
+    assert (a_eval >= 0).all() and (wscale != 1.0 or (a_eval > 0).all())   # (peaked rows underflow to exact zeros)
     ref_eval = copy.deepcopy(ref).eval()(bt.x.double(), bt.edge_index, bt.edge_attr.double())
     assert relerr(out_eval, ref_eval) < TOL
 
