@@ -588,7 +588,8 @@ size_t attn_bwd_partials_bytes(const spotv2_gat_desc* d) {
   const size_t ctas = 2 * (size_t)sm_count();
   const size_t ldo = d->concat ? (size_t)d->H * d->C : (size_t)d->C;
   const size_t legacy = round_up(ctas * ((size_t)d->H * d->Fe + ldo) * sizeof(float), 256);
-  const size_t piped = attn_bwd2_partials_bytes(d);
+  size_t piped = attn_bwd2_partials_bytes(d);
+  if (attn_bwd3_partials_bytes(d) > piped) piped = attn_bwd3_partials_bytes(d);
   return legacy > piped ? legacy : piped;
 }
 size_t attn_bwd_ws_bytes(const spotv2_gat_desc* d) {
@@ -714,9 +715,18 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
   int rc;
   // d->attn_bwd_algo selects the kernel: 0 = pipelined (attn_bwd2.cu) whenever its shared-memory plan fits,
   // 1 = the phase-serial kernel of this file, 2 = pipelined or error
-  if (structured && !attn_bwd2_fits(a.p))
+  // d->attn_bwd_algo: 0 = the library's choice (tcgen05 kernel where it applies, else the pipelined mma.sync kernel
+  // when its shared-memory plan fits, else the phase-serial kernel), 1 = phase-serial, 2 = pipelined or error,
+  // 3 = tcgen05 or error
+  const bool tc5 = (d->attn_bwd_algo == 0 || d->attn_bwd_algo == 3) && attn_bwd3_applies(a.p);
+  if (d->attn_bwd_algo == 3 && !tc5)
+    return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd: the tcgen05 kernel covers head-mean layers with N <= 31, C %% 4 == 0, even Fe <= 128 "
+                                        "and the forward's edge terms");
+  if (structured && !tc5 && !attn_bwd2_fits(a.p))
     return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd: edge_mode 1 needs the pipelined kernel, whose shared-memory plan does not fit this shape");
-  if (d->attn_bwd_algo != 1 && (attn_bwd2_fits(a.p) || d->attn_bwd_algo == 2))
+  if (tc5)
+    rc = launch_attn_bwd3(a, structured ? nullptr : dv_or_null, dbias_or_null, ws, ws_bytes, st);
+  else if (d->attn_bwd_algo != 1 && (attn_bwd2_fits(a.p) || d->attn_bwd_algo == 2))
     rc = launch_attn_bwd2(a, structured ? nullptr : dv_or_null, dbias_or_null, ws, ws_bytes, st);
   else if (np <= 4) rc = launch_bwd<4>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
   else if (np <= 8) rc = launch_bwd<8>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);

@@ -44,6 +44,11 @@ int launch_attn_bwd2(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t w
 size_t attn_bwd2_partials_bytes(const spotv2_gat_desc* d);
 int bwd2_diag_add(unsigned long long* host_out, int reset);      // adds its phase counters into host_out[0..5]
 
+// tcgen05 kernel (attn_bwd3.cu): head-mean layers, N <= 31, edge terms kept by the forward.
+bool attn_bwd3_applies(const AttnParams& p);
+int launch_attn_bwd3(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t attn_bwd3_partials_bytes(const spotv2_gat_desc* d);
+
 // Large-universe path (attn_large.cu): N > 32, several CTAs per graph, attention tile in HBM.
 bool attn_large_applies(const spotv2_gat_desc* d);
 size_t attn_large_fwd_ws_bytes(const spotv2_gat_desc* d);
