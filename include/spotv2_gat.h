@@ -72,9 +72,9 @@ typedef struct spotv2_gat_desc {
   int32_t gemm_algo;      /* 0 | 2 tcgen05, fp32-accurate (fp16 operand pairs, 3 products); 1 fp32 CUDA
                              cores; 3 tcgen05 half-precision class (one fp16 product, fp32
                              accumulate: BASELINE config C's "bf16" variant, error ~1e-3)       */
-  int32_t attn_bwd_algo;  /* 0 auto (tcgen05 kernel for head-mean layers with N <= 31, else the pipelined
-                             mma.sync kernel when its shared-memory plan fits, else phase-serial),
-                             1 phase-serial kernel, 2 pipelined mma.sync or error, 3 tcgen05 or error */
+  int32_t attn_bwd_algo;  /* 0 auto (pipelined mma.sync kernel when its shared-memory plan fits, else phase-serial),
+                             1 phase-serial kernel, 2 pipelined mma.sync or error, 3 tcgen05/TMEM kernel or error
+                             (head-mean layers, N <= 31; opt-in: measured slower than 2 on B200)        */
   float   dropout_p;      /* attention dropout of this call: 0 = none (eval mode, or PyG's
                              dropout=0.0 default, config/GNN_param.yaml:36).  In (0,1): every
                              attention coefficient is zeroed with probability p and the rest

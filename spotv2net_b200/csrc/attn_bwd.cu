@@ -636,7 +636,8 @@ int bwd_diag_read(unsigned long long* host_out, int reset) {
     unsigned long long zeros[kNumCounters] = {0};
     SPOTV2_CUDA_OK(cudaMemcpyToSymbol(g_bwd_counters, zeros, sizeof(zeros)));
   }
-  return bwd2_diag_add(host_out, reset);       // whichever kernel ran contributes; the other adds zeros
+  if (int rc = bwd2_diag_add(host_out, reset)) return rc;       // whichever kernel ran contributes; the others add zeros
+  return bwd3_diag_add(host_out, reset);
 }
 }  // namespace spotv2
 
@@ -715,10 +716,11 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
   int rc;
   // d->attn_bwd_algo selects the kernel: 0 = pipelined (attn_bwd2.cu) whenever its shared-memory plan fits,
   // 1 = the phase-serial kernel of this file, 2 = pipelined or error
-  // d->attn_bwd_algo: 0 = the library's choice (tcgen05 kernel where it applies, else the pipelined mma.sync kernel
-  // when its shared-memory plan fits, else the phase-serial kernel), 1 = phase-serial, 2 = pipelined or error,
-  // 3 = tcgen05 or error
-  const bool tc5 = (d->attn_bwd_algo == 0 || d->attn_bwd_algo == 3) && attn_bwd3_applies(a.p);
+  // d->attn_bwd_algo: 0 = the library's choice (the pipelined mma.sync kernel when its shared-memory plan fits, else the
+  // phase-serial kernel), 1 = phase-serial, 2 = pipelined or error, 3 = the tcgen05 kernel (attn_bwd3.cu) or error.
+  // The tcgen05 kernel is NOT the default: measured on B200 it is bound by the shared-memory port (operand split passes
+  // plus tf32 operand reads) and runs 2.0-2.2 ms where the pipelined kernel runs 1.95 ms.
+  const bool tc5 = d->attn_bwd_algo == 3 && attn_bwd3_applies(a.p);
   if (d->attn_bwd_algo == 3 && !tc5)
     return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd: the tcgen05 kernel covers head-mean layers with N <= 31, C %% 4 == 0, even Fe <= 128 "
                                         "and the forward's edge terms");

@@ -48,6 +48,7 @@ int bwd2_diag_add(unsigned long long* host_out, int reset);      // adds its pha
 bool attn_bwd3_applies(const AttnParams& p);
 int launch_attn_bwd3(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t attn_bwd3_partials_bytes(const spotv2_gat_desc* d);
+int bwd3_diag_add(unsigned long long* host_out, int reset);     // adds its 16 wait / work counters into host_out[0..15]
 
 // Large-universe path (attn_large.cu): N > 32, several CTAs per graph, attention tile in HBM.
 bool attn_large_applies(const spotv2_gat_desc* d);
