@@ -207,8 +207,14 @@ class HotPath:
         self.ldf16, self.ldp16 = self.lib.spotv2_gat_ld16(Fin), self.lib.spotv2_gat_ld16(HC + 2 * H)
         self.dP_aug = None if self.tc else torch.empty(n, self.desc.ldp, **f32)
         self.dP16 = torch.empty(2, n, self.ldp16, **f16) if self.tc else None
-        self.x16 = torch.empty(2, n, self.ldf16, **f16) if self.tc else None
-        self.x_blk = torch.empty(8, **f32) if self.tc else None
+        # x as the GEMMs' operand pair: emitted by the collation (spotv2_collate_windows_pair; the dataset fixes the scale),
+        # as a WindowDataset batch delivers it; --split-x-in-step re-derives it from the fp32 x inside the step (round 1)
+        self.x_from_collation = self.tc and not getattr(HotPath, "SPLIT_X_IN_STEP", False) and self.batch.spot_x16 is not None
+        if self.x_from_collation:
+            self.x16, self.x_blk = self.batch.spot_x16
+        else:
+            self.x16 = torch.empty(2, n, self.ldf16, **f16) if self.tc else None
+            self.x_blk = torch.empty(8, **f32) if self.tc else None
         self.dp_blk = torch.empty(8, **f32) if self.tc else None
         self.dW_aug = torch.empty(HC + 2 * H, Fin, **f32)
         self.dv = torch.empty(H, Fe, **f32)
@@ -242,7 +248,7 @@ class HotPath:
         xl = self.x16[1] if self.tc else None
         ph = self.dP16[0] if self.tc else None
         pl = self.dP16[1] if self.tc else None
-        if self.tc:      # x becomes an fp16 operand pair once per step (forward); the weight-gradient GEMM reuses it
+        if self.tc and not self.x_from_collation:      # x given as fp32 only: one amax + one split pass per step
             chk(lib.spotv2_split_f16(p(self.batch.x), self.B * self.N, self.Fin, self.Fin, 0, 0, p(xh), p(xl), self.ldf16,
                                      p(self.x_blk), st), "split_f16")
         chk(lib.spotv2_proj_fwd(d, p(self.batch.x), p(xh), p(xl), p(self.x_blk), p(self.W_aug), p(self.P_aug), p(self.p_amax),
@@ -649,8 +655,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-structured", action="store_true", help="skip the structured-edge-source side measurement")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay side measurement")
+    ap.add_argument("--split-x-in-step", action="store_true", help="derive x's operand pair from the fp32 x inside every step (round-1 behaviour)")
     args = ap.parse_args()
     CFG["N"] = CONFIGS[args.config]["N"]
+    HotPath.SPLIT_X_IN_STEP = args.split_x_in_step
     if args.batch <= 0:
         args.batch = CONFIGS[args.config]["batch"]
     if args.impl == "reference":

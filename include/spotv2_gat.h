@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SPOTV2_ABI_VERSION 3
+#define SPOTV2_ABI_VERSION 4
 
 typedef enum spotv2_status {
   SPOTV2_OK = 0,
@@ -229,6 +229,17 @@ int spotv2_alpha_to_pyg(const spotv2_gat_desc* d, const float* alpha_tile, const
 int spotv2_collate_windows(const float* M_vol, const float* M_vv, int32_t T, int32_t N, int32_t L,
                            const int32_t* t0, int32_t B, float* x, float* edge_attr, float* y,
                            void* stream);
+
+/* Collation that also emits x as the tensor-core operand pair (see spotv2_split_f16), so that the training step holds
+ * neither an amax pass nor a split pass over x (619 MB per 4096-graph batch).  x values are entries of M_vol, hence the
+ * pair's power-of-two scale is a property of the dataset: spotv2_stack_scale fills an 8-float scale block from
+ * max |M_vol| once (count = T*N*N), and every batch collated from that stack shares it.  x_or_null: also write the fp32
+ * x [B*N, N*L] (the reference layout, utils/dataset.py:250,278); x_hi / x_lo: [B*N, ld16] fp16, ld16 = spotv2_gat_ld16(N*L).
+ * Pass (x_hi, x_lo, x_scale) to spotv2_proj_fwd / spotv2_proj_bwd_weight as their x operand. */
+int spotv2_stack_scale(const float* M, int64_t count, float* scale_block, void* stream);
+int spotv2_collate_windows_pair(const float* M_vol, const float* M_vv, int32_t T, int32_t N, int32_t L,
+                                const int32_t* t0, int32_t B, float* x_or_null, void* x_hi, void* x_lo, int32_t ld16,
+                                const float* x_scale, float* edge_attr, float* y, void* stream);
 
 /* ---- diagnostics (bring-up and parity tests of the GEMM back ends; not reference-facing) ----
  * C[M,N] (ld ldc) = sum_k A(m,k) B(n,k).  a_kc/b_kc = 1: operand stored [rows, K] (K contiguous),

@@ -55,6 +55,8 @@ SIGNATURES = {
     "spotv2_gat_unfold": (C.c_int, [_DP] + [_vp] * 13),
     "spotv2_alpha_to_pyg": (C.c_int, [_DP, _vp, _vp, _vp, _vp]),
     "spotv2_collate_windows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "spotv2_stack_scale": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "spotv2_collate_windows_pair": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "spotv2_diag_counters": (C.c_int, [_vp, C.c_int]),
     "spotv2_diag_weight_grad_splits": (_i32, [_i32, _i32, _i32]),
     "spotv2_diag_gemm": (C.c_int, [C.c_int] * 5 + [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int] + [C.c_int] * 4 + [_vp, _sz, _vp]),
@@ -78,8 +80,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.spotv2_abi_version() != 3:
-        raise SpotV2Error(f"ABI version mismatch: library reports {lib.spotv2_abi_version()}, binding expects 3")
+    if lib.spotv2_abi_version() != 4:
+        raise SpotV2Error(f"ABI version mismatch: library reports {lib.spotv2_abi_version()}, binding expects 4")
     _lib = lib
     return lib
 

@@ -1,6 +1,9 @@
 // Parameter folding / gradient unfolding, the edge-row table, the PyG-order view of the attention
 // tile and the device-side window collation.  All small, bandwidth-trivial kernels.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
+#include "gemm.cuh"
 
 namespace spotv2 {
 
@@ -174,6 +177,45 @@ __global__ void collate_x_kernel(const float* __restrict__ M_vol, const int32_t*
   if (threadIdx.x == 0) y[node] = M_vol[((size_t)(start + L) * N + i) * N + i];
 }
 
+// Same gather, and the row also leaves as the projection GEMMs' fp16 operand pair: x values are entries of the
+// [T, N, N] stack, so the pair's power-of-two scale comes from the stack-wide maximum (spotv2_stack_scale, once per
+// dataset) and neither an amax pass nor a split pass over x is left in the training step.
+__global__ void collate_x_pair_kernel(const float* __restrict__ M_vol, const int32_t* __restrict__ t0, int N, int L,
+                                      float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int ld16,
+                                      const float* __restrict__ blk, float* __restrict__ y) {
+  const int node = blockIdx.x;            // b*N + i
+  const int b = node / N, i = node - b * N;
+  const int start = t0[b];
+  const int NL = N * L;
+  const float s = blk[4];
+  for (int k = threadIdx.x; k < NL; k += blockDim.x) {
+    const int c = k / L, t = k - c * L;
+    const float v = M_vol[((size_t)(start + t) * N + i) * N + c];
+    if (x) x[(size_t)node * NL + k] = v;
+    const float w = v * s;
+    const __half h = __float2half_rn(w);
+    hi[(size_t)node * ld16 + k] = h;
+    lo[(size_t)node * ld16 + k] = __float2half_rn(w - __half2float(h));
+  }
+  for (int k = NL + threadIdx.x; k < ld16; k += blockDim.x) {          // row padding: finite zeros
+    hi[(size_t)node * ld16 + k] = __float2half_rn(0.f);
+    lo[(size_t)node * ld16 + k] = __float2half_rn(0.f);
+  }
+  if (threadIdx.x == 0) y[node] = M_vol[((size_t)(start + L) * N + i) * N + i];
+}
+
+// blk[0] holds the bit pattern of max |.|: fill in the inverse scale [2] and the scale [4] (same rule as gemm_f16.cu)
+__global__ void finish_scale_block_kernel(float* blk) {
+  const float amax = __uint_as_float(reinterpret_cast<const unsigned*>(blk)[0]);
+  float s = 1.f;
+  if (amax > 0.f && amax < INFINITY) {
+    int ex;
+    frexpf(amax, &ex);
+    s = exp2f((float)(15 - ex));
+  }
+  blk[1] = 0.f; blk[2] = 1.f / s; blk[3] = 1.f / s; blk[4] = s; blk[5] = s; blk[6] = 0.f; blk[7] = 0.f;
+}
+
 __device__ __forceinline__ void tri_decode(int idx, int N, int& r, int& c) {
   // idx = r*(2N-r-1)/2 + (c-r-1), r < c
   const float fn = (float)(2 * N - 1);
@@ -298,6 +340,32 @@ extern "C" int spotv2_collate_windows(const float* M_vol, const float* M_vv, int
   cudaStream_t st = as_stream(stream);
   collate_x_kernel<<<B * N, 256, 0, st>>>(M_vol, t0, N, L, x, y);
   if (edge_attr) {            // null: the caller keeps the edges structured (window references, csrc/windows.cu)
+    dim3 ge((N * (N - 1) + 7) / 8, B);
+    collate_edge_kernel<<<ge, 256, 0, st>>>(M_vv, t0, N, L, edge_attr);
+  }
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
+extern "C" int spotv2_stack_scale(const float* M, int64_t count, float* scale_block, void* stream) {
+  SPOTV2_REQUIRE(M && scale_block && count > 0, "stack_scale: null pointer or empty stack");
+  cudaStream_t st = as_stream(stream);
+  if (int rc = amax_flat(M, (size_t)count, scale_block, st)) return rc;
+  finish_scale_block_kernel<<<1, 1, 0, st>>>(scale_block);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
+extern "C" int spotv2_collate_windows_pair(const float* M_vol, const float* M_vv, int32_t T, int32_t N, int32_t L,
+                                           const int32_t* t0, int32_t B, float* x_or_null, void* x_hi, void* x_lo,
+                                           int32_t ld16, const float* x_scale, float* edge_attr, float* y, void* stream) {
+  SPOTV2_REQUIRE(M_vol && M_vv && t0 && x_hi && x_lo && x_scale && y, "collate_windows_pair: null pointer");
+  SPOTV2_REQUIRE(T > L && N > 1 && L > 0 && B > 0, "collate_windows_pair: need T > L, N > 1, L > 0, B > 0");
+  SPOTV2_REQUIRE(ld16 >= N * L && ld16 % 8 == 0, "collate_windows_pair: ld16 must be >= N*L and a multiple of 8");
+  cudaStream_t st = as_stream(stream);
+  collate_x_pair_kernel<<<B * N, 256, 0, st>>>(M_vol, t0, N, L, x_or_null, static_cast<__half*>(x_hi), static_cast<__half*>(x_lo),
+                                               ld16, x_scale, y);
+  if (edge_attr) {
     dim3 ge((N * (N - 1) + 7) / 8, B);
     collate_edge_kernel<<<ge, 256, 0, st>>>(M_vv, t0, N, L, edge_attr);
   }

@@ -36,10 +36,14 @@ def complete_graph_edge_index(N: int) -> Tensor:
 class SpotBatch:
     """Duck-typed PyG ``Batch`` for identical complete graphs."""
 
-    def __init__(self, x, edge_index, edge_attr, y_x, num_graphs, nodes_per_graph, spot_topology=None, spot_windows=None):
+    def __init__(self, x, edge_index, edge_attr, y_x, num_graphs, nodes_per_graph, spot_topology=None, spot_windows=None,
+                 spot_x16=None):
         self.x, self.edge_index, self.edge_attr, self.y_x = x, edge_index, edge_attr, y_x
         self.num_graphs, self.nodes_per_graph, self.spot_topology = num_graphs, nodes_per_graph, spot_topology
         self.spot_windows = spot_windows        # WindowSource: lets the GAT layers read the windows instead of edge_attr
+        # (pair [2, B*N, ld16] fp16, scale block [8]): x as the projection GEMMs' operand pair, emitted by the collation.
+        # It also rides on the tensor itself (x._spot_pair, with the tensor's version), which is where GATConv looks.
+        self.spot_x16 = spot_x16
 
     @property
     def batch(self) -> Tensor:
@@ -126,6 +130,12 @@ class WindowDataset:
         self.volvol = volvol.to(self.device, torch.float32).contiguous()
         self.num_node_features = self.N * self.L
         self.num_edge_features = 3 * self.L
+        # x values are entries of vol: the fp16 operand pair of every batch shares one power-of-two scale, fixed here
+        self.x_scale = torch.empty(8, device=self.device, dtype=torch.float32)
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            check(lib.spotv2_stack_scale(ptr(self.vol), self.vol.numel(), ptr(self.x_scale), stream_ptr(self.device)),
+                  "spotv2_stack_scale")
 
     def __len__(self) -> int:
         return self.T - self._tail - self.drop_first
@@ -143,16 +153,21 @@ class WindowDataset:
         ea = None if self.structured else torch.empty(B * N * (N - 1), 3 * L, device=dev, dtype=torch.float32)
         y = torch.empty(B * N, device=dev, dtype=torch.float32)
         lib = _lib.load()
+        ld16 = lib.spotv2_gat_ld16(N * L)
+        x16 = torch.empty(2, B * N, ld16, device=dev, dtype=torch.float16)
         with torch.cuda.device(dev):
-            check(lib.spotv2_collate_windows(ptr(self.vol), ptr(self.volvol), self.T, N, L, ptr(t0), B, ptr(x), ptr(ea),
-                                             ptr(y), stream_ptr(dev)), "spotv2_collate_windows")
+            check(lib.spotv2_collate_windows_pair(ptr(self.vol), ptr(self.volvol), self.T, N, L, ptr(t0), B, ptr(x), ptr(x16[0]),
+                                                  ptr(x16[1]), ld16, ptr(self.x_scale), ptr(ea), ptr(y), stream_ptr(dev)),
+                  "spotv2_collate_windows_pair")
+        x._spot_pair = (x16, self.x_scale, x._version)
         if self.future_steps is not None:        # [B, K, N] gather of the next K diagonals -> [B*N*K], node major
             K = self.future_steps
             t = (t0.to(torch.int64) + L).view(B, 1) + torch.arange(K, device=dev).view(1, K)
             y = self.vol.diagonal(dim1=1, dim2=2)[t].permute(0, 2, 1).reshape(-1).contiguous()
         ei, topo = batched_topology(B, N, dev)
         # window references ride only on structured batches: with a materialised edge_attr the layers must use it
-        return SpotBatch(x, ei, ea, y, B, N, topo, WindowSource(self.volvol, t0, L, checked=True) if self.structured else None)
+        return SpotBatch(x, ei, ea, y, B, N, topo, WindowSource(self.volvol, t0, L, checked=True) if self.structured else None,
+                         (x16, self.x_scale))
 
     def __getitem__(self, k):
         if isinstance(k, slice):

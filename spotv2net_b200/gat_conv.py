@@ -158,14 +158,14 @@ class _GatLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, edge_attr, W, a_src, a_dst, W_e, a_edge, bias, topo, H, Cc, concat, slope, want_alpha,
-                dropout_p=0.0, seed=0, gemm_algo=None, windows=None):
+                dropout_p=0.0, seed=0, gemm_algo=None, windows=None, x_pair=None):
         with torch.cuda.device(x.device):        # launches, attribute calls and tensor maps go to the CURRENT device
             return _GatLayerFn._forward(ctx, x, edge_attr, W, a_src, a_dst, W_e, a_edge, bias, topo, H, Cc, concat, slope,
-                                        want_alpha, dropout_p, seed, gemm_algo, windows)
+                                        want_alpha, dropout_p, seed, gemm_algo, windows, x_pair)
 
     @staticmethod
     def _forward(ctx, x, edge_attr, W, a_src, a_dst, W_e, a_edge, bias, topo, H, Cc, concat, slope, want_alpha,
-                 dropout_p, seed, gemm_algo, windows):
+                 dropout_p, seed, gemm_algo, windows, x_pair):
         lib = _lib.load()
         dev = x.device
         st = stream_ptr(dev)
@@ -192,7 +192,9 @@ class _GatLayerFn(torch.autograd.Function):
         p_amax = torch.empty(8, device=dev, dtype=torch.float32)      # max|P|, sizes the backward's fp16 operand scale
         # tensor-core path: x becomes an fp16 operand pair once; the weight-gradient GEMM reuses it
         x16 = x_blk = None
-        if lib.spotv2_gat_uses_tensor_cores(C.byref(desc)):
+        if lib.spotv2_gat_uses_tensor_cores(C.byref(desc)) and x_pair is not None:
+            x16, x_blk = x_pair                    # emitted by the collation (WindowDataset): no amax / split pass over x
+        elif lib.spotv2_gat_uses_tensor_cores(C.byref(desc)):
             ld16 = lib.spotv2_gat_ld16(x.shape[1])
             x16 = torch.empty(2, n, ld16, device=dev, dtype=torch.float16)
             x_blk = torch.empty(8, device=dev, dtype=torch.float32)
@@ -290,7 +292,7 @@ class _GatLayerFn(torch.autograd.Function):
                                     ptr(da_dst), ptr(dW_e), ptr(da_edge), st), "spotv2_gat_unfold")
         if not Fe and W_e is not None:          # layer has lin_edge but was called with edge_attr=None
             dW_e, da_edge = torch.zeros_like(W_e), torch.zeros_like(a_edge)
-        return (dx, None, dW, da_src, da_dst, dW_e, da_edge, dbias) + (None,) * 10
+        return (dx, None, dW, da_src, da_dst, dW_e, da_edge, dbias) + (None,) * 11
 
 
 # --------------------------------------------------------------------------- module
@@ -429,11 +431,17 @@ class GATConv(nn.Module):
         if use_edge and windows is None and edge_attr.shape[0] != topo.B * topo.R:
             raise SpotV2Error(f"edge_attr has {edge_attr.shape[0]} rows, edge_index has {topo.B * topo.R} edges")
         want_alpha = isinstance(return_attention_weights, bool)
+        # x as the GEMMs' fp16 operand pair, if the collation attached one to this very tensor and nobody wrote to it since
+        x_pair = None
+        tag = getattr(x, "_spot_pair", None)
+        if tag is not None and tag[2] == x._version and tag[0].device == x.device and tag[0].shape[1] == x.shape[0] and \
+                tag[0].shape[2] == _lib.load().spotv2_gat_ld16(x.shape[1]):
+            x_pair = (tag[0], tag[1])
         out, alpha_tile = _GatLayerFn.apply(
             x, edge_attr if (use_edge and windows is None) else None, self.lin_src.weight, self.att_src, self.att_dst,
             self.lin_edge.weight if self.lin_edge is not None else None, self.att_edge, self.bias,
             topo, self.heads, self.out_channels, self.concat, self.negative_slope, want_alpha, drop_p, seed,
-            PRECISIONS[self.precision], windows if use_edge else None)
+            PRECISIONS[self.precision], windows if use_edge else None, x_pair)
         if not want_alpha:
             return out
         return out, self._attention_weights(alpha_tile, topo, edge_index)

@@ -125,7 +125,7 @@ def train(seed: Optional[int] = None, trial=None, p: Optional[dict] = None, *, c
     prev_test = float("inf")
     for epoch in range(p["num_epochs"]):
         model.train()
-        total = 0.0
+        total = torch.zeros((), device=device, dtype=torch.float64)      # summed on the device: no sync per step
         n_train = len(train_set)
         order = torch.randperm(n_train, generator=gen)
         steps = 0
@@ -139,9 +139,15 @@ def train(seed: Optional[int] = None, trial=None, p: Optional[dict] = None, *, c
             if arena is not None:
                 arena.all_reduce()
             optimizer.step()
-            total += loss.item()
+            total += loss.detach().double()
             steps += 1
-        avg_train = total / max(steps, 1)
+        if world > 1:
+            # a rank's loss is the mean over ITS shard of the global batch; the reported figure is the mean over ranks
+            # (equal shards), so that it equals the single-process number (batches that did not split evenly were run
+            # whole by every rank: the mean over ranks is then that same value)
+            dist.all_reduce(total)
+            total /= world
+        avg_train = total.item() / max(steps, 1)
         train_losses.append(avg_train)
 
         model.eval()

@@ -20,7 +20,7 @@ def _declared():
 
 def test_library_is_built_and_loads():
     lib = spotv2net_b200.load_library()
-    assert lib.spotv2_abi_version() == 3
+    assert lib.spotv2_abi_version() == 4
 
 
 def test_every_declared_symbol_is_exported_and_bound():
