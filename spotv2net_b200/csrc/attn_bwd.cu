@@ -13,6 +13,8 @@
 //   B4  dv[h,:] += sum_e dz'[e,h] * edge_attr[e,:]: second pass over the edge rows         [ring]
 // The ring and the B2 staging alias the same shared memory.  dv and dbias are accumulated per
 // CTA and reduced in a fixed order by a second kernel (deterministic).
+#include <algorithm>
+
 #include "attn_bwd.cuh"
 
 namespace spotv2 {
@@ -577,6 +579,58 @@ partial_reduce_kernel(const float* __restrict__ part, int nparts, int len, float
   }
 }
 
+// two reductions behind one launch: blocks [0, blocks_a) serve the first, the rest the second
+__global__ void __launch_bounds__(256)
+partial_reduce2_kernel(const float* __restrict__ pa, int na, int la, float* __restrict__ oa, int blocks_a,
+                       const float* __restrict__ pb, int nb, int lb, float* __restrict__ ob) {
+  __shared__ float red[8][33];
+  const bool first = (int)blockIdx.x < blocks_a;
+  const float* part = first ? pa : pb;
+  const int nparts = first ? na : nb, len = first ? la : lb;
+  float* out = first ? oa : ob;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int k = ((int)blockIdx.x - (first ? 0 : blocks_a)) * 32 + tx;
+  float s = 0.f;
+  if (k < len)
+    for (int c = ty; c < nparts; c += 8) s += part[(size_t)c * len + k];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && k < len) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][tx];
+    out[k] = t;
+  }
+}
+
+int reduce_partials2(const float* part_a, int nparts_a, int len_a, float* out_a, const float* part_b, int nparts_b, int len_b,
+                     float* out_b, cudaStream_t st) {
+  if (!out_a) len_a = 0;
+  if (!out_b) len_b = 0;
+  const int ba = (len_a + 31) / 32, bb = (len_b + 31) / 32;
+  if (ba + bb == 0) return SPOTV2_OK;
+  partial_reduce2_kernel<<<ba + bb, 256, 0, st>>>(part_a, nparts_a, len_a, out_a, ba, part_b, nparts_b, len_b, out_b);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
+// ds | dd [rows, 2H] fp32 -> columns [HC, HC + 2H) of the dP operand pair; the group maximum was collected by the attention
+// kernel itself (dp_blk[1], atomicMax of bit patterns), so this is the only pass: scale, split, publish the scale.
+__global__ void __launch_bounds__(256)
+split_dsd_kernel(const float* __restrict__ dsd, size_t total, int cols, __half* __restrict__ hi, __half* __restrict__ lo, int ld16,
+                 float* __restrict__ dp_blk) {
+  const float s = dp_scale_from_amax(__uint_as_float(reinterpret_cast<const unsigned*>(dp_blk)[1]));
+  if (blockIdx.x == 0 && threadIdx.x == 0) { dp_blk[3] = 1.f / s; dp_blk[5] = s; }
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = idx / cols;
+    const int c = (int)(idx - r * cols);
+    const float w = dsd[idx] * s;
+    const __half h = __float2half_rn(w);
+    hi[r * ld16 + c] = h;
+    lo[r * ld16 + c] = __float2half_rn(w - __half2float(h));
+  }
+}
+
 int reduce_partials(const float* part, int nparts, int len, float* out, cudaStream_t st) {
   partial_reduce_kernel<<<(len + 31) / 32, 256, 0, st>>>(part, nparts, len, out);
   SPOTV2_CUDA_OK(cudaGetLastError());
@@ -684,7 +738,7 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
   a.dP_hi16 = static_cast<__half*>(dP_hi_or_null); a.dP_lo16 = static_cast<__half*>(dP_lo_or_null);
   const int HC = d->H * d->C;
   a.ldp16 = ld16_of(HC + 2 * d->H);
-  a.dout_blk = nullptr; a.p_amax = nullptr; a.bound = 1.f; a.dsd = nullptr; a.dp_blk = dp_scale_or_null;
+  a.dout_blk = nullptr; a.p_amax = nullptr; a.bound = 1.f; a.dsd = nullptr; a.dp_blk = dp_scale_or_null; a.dsd_amax = nullptr;
   cudaStream_t st = as_stream(stream);
   if (attn_large_applies(d))       // N > 32: several CTAs per graph (attn_large.cu); emits the pair through a split pass
     return attn_large_bwd(d, a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
@@ -726,9 +780,13 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
                                         "and the forward's edge terms");
   if (structured && !tc5 && !attn_bwd2_fits(a.p))
     return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd: edge_mode 1 needs the pipelined kernel, whose shared-memory plan does not fit this shape");
+  // the pipelined and the tcgen05 kernels collect max |ds|, |dd| themselves (dp_scale block entry 1, zeroed above)
+  const bool piped = !tc5 && d->attn_bwd_algo != 1 && (attn_bwd2_fits(a.p) || d->attn_bwd_algo == 2);
+  const bool dsd_fused = f16 && (tc5 || piped);
+  if (dsd_fused) a.dsd_amax = reinterpret_cast<unsigned*>(dp_scale_or_null) + 1;
   if (tc5)
     rc = launch_attn_bwd3(a, structured ? nullptr : dv_or_null, dbias_or_null, ws, ws_bytes, st);
-  else if (d->attn_bwd_algo != 1 && (attn_bwd2_fits(a.p) || d->attn_bwd_algo == 2))
+  else if (piped)
     rc = launch_attn_bwd2(a, structured ? nullptr : dv_or_null, dbias_or_null, ws, ws_bytes, st);
   else if (np <= 4) rc = launch_bwd<4>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
   else if (np <= 8) rc = launch_bwd<8>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
@@ -736,7 +794,12 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
   else if (np <= 16) rc = launch_bwd<16>(a, dv_or_null, dbias_or_null, ws, ws_bytes, st);
   else return fail(SPOTV2_ERR_UNSUPPORTED, "N=%d > 32: the one-CTA-per-graph kernel covers N <= 32", d->N);
   if (rc) return rc;
-  if (f16) {
+  if (dsd_fused) {
+    const size_t total = rows * 2 * (size_t)d->H;
+    split_dsd_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, (size_t)8 * 148), 256, 0, st>>>(
+        a.dsd, total, 2 * d->H, a.dP_hi16 + HC, a.dP_lo16 + HC, a.ldp16, dp_scale_or_null);
+    SPOTV2_CUDA_OK(cudaGetLastError());
+  } else if (f16) {
     // ds | dd: own scale group (columns [HC, HC + 2H) of the fp16 pair arrays)
     const int none = 0x7fffffff;
     if ((rc = split_f16(a.dsd, (int)rows, 2 * d->H, 2 * d->H, 0, none, nullptr, 0, a.dP_hi16 + HC, a.dP_lo16 + HC,

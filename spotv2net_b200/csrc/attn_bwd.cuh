@@ -23,6 +23,7 @@ struct AttnBwdArgs {
   const float* p_amax;     // [0] = bit pattern of max |P| over the H*C projection columns (pipelined kernel)
   float bound;
   float* dsd;
+  unsigned* dsd_amax;  // pipelined / tcgen05 kernels: receives (atomicMax) the bit pattern of max |ds|, |dd|; null = off
   float* dp_blk;       // receives inverse scale [2] and scale [4] of the dP group
   float* dv_part;      // [grid][H*Fe]
   float* dbias_part;   // [grid][ldo]
@@ -37,6 +38,9 @@ __device__ __forceinline__ float dp_scale_from_amax(float amax) {   // same rule
 
 // out[k] = sum_c part[c][k] in a fixed order (deterministic)
 int reduce_partials(const float* part, int nparts, int len, float* out, cudaStream_t st);
+// two such reductions in one launch (either may be empty: out == nullptr or len == 0)
+int reduce_partials2(const float* part_a, int nparts_a, int len_a, float* out_a, const float* part_b, int nparts_b, int len_b,
+                     float* out_b, cudaStream_t st);
 
 // Pipelined kernel.  Returns SPOTV2_ERR_UNSUPPORTED (without setting an error) when the plan does not fit.
 bool attn_bwd2_fits(const AttnParams& p);

@@ -484,6 +484,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
     if (++slot == pl.n_slots) { slot = 0; sph ^= 1; }
   };
 
+  float dsd_max = 0.f;                   // max |ds|, |dd| this thread wrote: sizes the fp16 scale of the ds|dd operand columns
   long long ph[6] = {0, 0, 0, 0, 0, 0};
   long long t_ph = clock64();
   auto lap = [&](int k) { const long long now = clock64(); ph[k] += now - t_ph; t_ph = now; };
@@ -699,10 +700,12 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
         dii1 += __shfl_xor_sync(0xffffffffu, dii1, 1); dii1 += __shfl_xor_sync(0xffffffffu, dii1, 2);
         if (t == 0) {
           if (i0 < N) {
+            dsd_max = fmaxf(dsd_max, fabsf(dd0));
             if (args.dsd) args.dsd[((size_t)b * N + i0) * 2 * H + H + h] = dd0;
             else args.dP_aug[((size_t)b * N + i0) * p.ldp + HC + H + h] = dd0;
           }
           if (i1 < N) {
+            dsd_max = fmaxf(dsd_max, fabsf(dd1));
             if (args.dsd) args.dsd[((size_t)b * N + i1) * 2 * H + H + h] = dd1;
             else args.dP_aug[((size_t)b * N + i1) * p.ldp + HC + H + h] = dd1;
           }
@@ -734,6 +737,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
     for (int idx = tid; idx < H * N; idx += kCT) {       // ds_j = sum over both target tiles
       const int h = idx / N, j = idx - h * N;
       const float ds = ds_part[h * 32 + j] + ds_part[(H + h) * 32 + j];
+      dsd_max = fmaxf(dsd_max, fabsf(ds));
       if (args.dsd) args.dsd[((size_t)b * N + j) * 2 * H + h] = ds;
       else args.dP_aug[((size_t)b * N + j) * p.ldp + HC + h] = ds;
     }
@@ -963,6 +967,10 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
   }
   if (tid == 0)
     for (int k = 0; k < 6; ++k) atomicAdd(&g_bwd2_counters[k], (unsigned long long)ph[k]);
+  if (args.dsd_amax) {
+    for (int o = 16; o > 0; o >>= 1) dsd_max = fmaxf(dsd_max, __shfl_xor_sync(0xffffffffu, dsd_max, o));
+    if (lane == 0 && dsd_max > 0.f) atomicMax(args.dsd_amax, __float_as_uint(dsd_max));
+  }
 
   // ---- per-CTA partials: dv_part[(cta * dv_rg + rg)][h][f], dbias_part[cta][col] ----
   if (Fe > 0) {
@@ -1026,12 +1034,7 @@ int launch_attn_bwd2(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t w
   SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
   kern<<<grid, kB2Threads, pl.total, st>>>(a, pl, tmP, tmG);
   SPOTV2_CUDA_OK(cudaGetLastError());
-  if (dv && p.Fe > 0) {
-    if (int rc = reduce_partials(a.dv_part, grid * rg, p.H * p.Fe, dv, st)) return rc;
-  }
-  if (dbias)
-    if (int rc = reduce_partials(a.dbias_part, grid, p.ldo, dbias, st)) return rc;
-  return SPOTV2_OK;
+  return reduce_partials2(a.dv_part, grid * rg, (dv && p.Fe > 0) ? p.H * p.Fe : 0, dv, a.dbias_part, grid, dbias ? p.ldo : 0, dbias, st);
 }
 
 int bwd2_diag_add(unsigned long long* host_out, int reset) {

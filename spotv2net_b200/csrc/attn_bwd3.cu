@@ -545,6 +545,7 @@ gat_attn_bwd3_kernel(const AttnBwdArgs args, const Bwd3Plan pl, const __grid_con
     const float inv_nm1 = 1.f / (float)(N > 1 ? N - 1 : 1);
     SlotCursor cur{0, 0u, pl.n_slots};
     long long w_t = 0, t_sm = 0, w_da = 0, t_sb = 0, w_vfull = 0, t_v = 0;
+    float dsd_max = 0.f;                 // max |ds|, |dd| written by this thread
     // phase V: a warp takes every 8th row of a chunk; a lane owns features 2l, 2l+1, 64+2l, 64+2l+1 and all heads
     constexpr int kHP = HT ? (HT + 1) / 2 : kMaxHeads / 2;      // head pairs
     const int f0 = 2 * lane, f1 = 64 + 2 * lane;
@@ -678,6 +679,7 @@ gat_attn_bwd3_kernel(const AttnBwdArgs args, const Bwd3Plan pl, const __grid_con
             if (j == i) dii = dz;
           }
         share = dii * inv_nm1;
+        dsd_max = fmaxf(dsd_max, fabsf(dd));
         if (args.dsd) args.dsd[((size_t)b * N + i) * 2 * H + H + h] = dd;
         else args.dP_aug[((size_t)b * N + i) * p.ldp + HC + H + h] = dd;
       }
@@ -686,6 +688,7 @@ gat_attn_bwd3_kernel(const AttnBwdArgs args, const Bwd3Plan pl, const __grid_con
         const uint32_t row = a_work + (uint32_t)((h * N + lane) * kNS3) * 4u;
         float ds = 0.f;
         for (int k = 0; k < N; ++k) ds += ldsa(row + (uint32_t)k * 4u);
+        dsd_max = fmaxf(dsd_max, fabsf(ds));
         if (args.dsd) args.dsd[((size_t)b * N + lane) * 2 * H + h] = ds;
         else args.dP_aug[((size_t)b * N + lane) * p.ldp + HC + h] = ds;
       }
@@ -764,6 +767,10 @@ gat_attn_bwd3_kernel(const AttnBwdArgs args, const Bwd3Plan pl, const __grid_con
 #pragma unroll
           for (int k = 0; k < kHP; ++k) { run[f][k].x += acc[f][k].x; run[f][k].y += acc[f][k].y; }   // two-level sum
       }
+    }
+    if (args.dsd_amax) {
+      for (int o = 16; o > 0; o >>= 1) dsd_max = fmaxf(dsd_max, __shfl_xor_sync(0xffffffffu, dsd_max, o));
+      if (lane == 0 && dsd_max > 0.f) atomicMax(args.dsd_amax, __float_as_uint(dsd_max));
     }
     // per-CTA partials: dv_part[cta * kSmWarps + warp][h][f]
     if (has_v) {
@@ -856,11 +863,7 @@ int launch_attn_bwd3(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t w
   SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
   kern<<<grid, kB3Threads, pl.total, st>>>(a, pl, tmP, tmG, tmGt);
   SPOTV2_CUDA_OK(cudaGetLastError());
-  if (dv && rg > 0)
-    if (int rc = reduce_partials(a.dv_part, grid * rg, p.H * p.Fe, dv, st)) return rc;
-  if (dbias)
-    if (int rc = reduce_partials(a.dbias_part, grid, p.ldo, dbias, st)) return rc;
-  return SPOTV2_OK;
+  return reduce_partials2(a.dv_part, grid * rg, (dv && rg > 0) ? p.H * p.Fe : 0, dv, a.dbias_part, grid, dbias ? p.ldo : 0, dbias, st);
 }
 
 int bwd3_diag_add(unsigned long long* host_out, int reset) {
