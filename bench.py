@@ -31,7 +31,14 @@ UNIT = "graphs/s"
 CFG = dict(N=30, L=42, H=6, C=500, slope=0.2, concat=False)
 # The bench line is BASELINE configs[1] ("A").  --config D times the 500-node universe (configs[3]) through the
 # same code for DESIGN.md; it is a parity-test case, not the headline.
-CONFIGS = {"A": dict(N=30, batch=4096, name="BASELINE configs[1]: default GNN_param.yaml hyper-parameters, batch 4096 snapshots per GPU"),
+METRIC_BY_CONFIG = {
+    "A": METRIC,
+    "C": "SpotV2Net wide multi-head variant (8 heads, hidden [256,256], two GAT layers) fwd+bwd graphs/sec (30-node, batch 4096)",
+    "D": "SpotV2Net GAT fwd+bwd graphs/sec (500-node universe, batch 32)",
+}
+CONFIGS = {"C": dict(N=30, batch=4096, name="BASELINE configs[2]: wide multi-head variant (8 heads, hidden [256, 256], concat: layer 0 1260 -> 8x256 "
+                                            "concat, layer 1 2048 -> 256 head mean), batch 4096 snapshots per GPU"),
+           "A": dict(N=30, batch=4096, name="BASELINE configs[1]: default GNN_param.yaml hyper-parameters, batch 4096 snapshots per GPU"),
            "D": dict(N=500, batch=32, name="BASELINE configs[3]: 500-node complete graph (249,500 edges per snapshot), batch 32 snapshots per GPU, "
                                            "multi-CTA-per-graph attention")}
 
@@ -433,6 +440,12 @@ def run_ours(args):
             structured = run_structured(args, dev, world, rank, barrier)
         except Exception as ex:
             structured = {"value": None, "error": repr(ex)[:300]}
+    train_step = None
+    if not args.no_structured and args.config == "A":
+        try:
+            train_step = run_train_step(args, dev, world, rank, barrier)
+        except Exception as ex:
+            train_step = {"value": None, "error": repr(ex)[:300]}
     e2e = e2e_win = None
     if not args.no_e2e:
         try:
@@ -457,7 +470,7 @@ def run_ours(args):
     if rank == 0:
         N, Fin, Fe, H, Cc = cfg_dims()
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC_BY_CONFIG[args.config], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": CONFIGS[args.config]["name"] + ", fp32, GATConv fwd+bwd" +
@@ -467,7 +480,7 @@ def run_ours(args):
                              f"P {B * N * H * Cc * 4 / 1e6:.0f} MB per step) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"dp{world}", "launch": "eager launches, CUDA events between the entry points"},
             "phase_ms": phase_ms, "roofline": roofline, "roofline_projection": proj, "cpu_baseline": cpu_baseline,
-            "dp_gradient_check": dp_check, "cuda_graph_replay": graph_info, "structured_edge_source": structured, "e2e": e2e, "e2e_windows": e2e_win, "gpu_launches": hp.kernels_per_step * args.steps, "clocks": clocks,
+            "dp_gradient_check": dp_check, "cuda_graph_replay": graph_info, "structured_edge_source": structured, "train_step": train_step, "e2e": e2e, "e2e_windows": e2e_win, "gpu_launches": hp.kernels_per_step * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -500,6 +513,134 @@ def dp_selfcheck(dev, rank, world, per_rank: int = 64):
         raise SystemExit(f"bench.py: all-reduced gradient differs from the single-GPU gradient on the concatenated batch "
                          f"by {worst.item():.2e} (> 1e-5)")
     return {"max_rel_err_vs_single_gpu": worst.item(), "graphs": world * per_rank, "ok": True}
+
+
+def run_config_c(args):
+    """BASELINE configs[2] through the public module API: GATModel(8 heads, hidden [256, 256], concat_heads) forward + MSE +
+    autograd backward on one collated 4096-graph batch (utils/models.py:90-104; config/GNN_param.yaml:28-38 widened).  The
+    line's value is the reduced-precision mode the config names ("half": one fp16 tensor-core product per projection, fp32
+    accumulate; the attention kernels keep fp32 storage - no bf16-storage attention exists yet); the fp32-accurate mode is
+    reported beside it.  The attention kernels' share comes from one extra step under torch.profiler (kernel durations by
+    name), never from the timed steps."""
+    import spotv2net_b200 as sv
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a CUDA device: the hot path has no CPU fallback")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B, N, L, H, Cc = args.batch, 30, CFG["L"], 8, 256
+    g = torch.Generator(device=dev).manual_seed(1234)
+    mats = []
+    for _ in range(2):
+        a = torch.randn(B + L + 1, N, N, device=dev, generator=g)
+        mats.append((a + a.transpose(1, 2)) / 2 ** 0.5)
+    ds = sv.WindowDataset(mats[0], mats[1], seq_length=L, device=dev, drop_first=0)
+    bt = ds.collate(torch.arange(B))
+    torch.manual_seed(0)
+    model = sv.GATModel(N * L, 3 * L, H, 1, dim_hidden_layers=[Cc, Cc], concat_heads=True).to(dev)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.mse_loss(model(bt), bt.y_x)
+        loss.backward()
+        return loss
+
+    sampler = ClockSampler(dev.index or 0)
+    res = {}
+    for prec in ("fp32", "half"):
+        model.set_precision(prec)
+        for _ in range(max(args.warmup, 3)):
+            step()
+        torch.cuda.synchronize(dev)
+        if prec == "half":
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / args.steps
+        res[prec] = {"ms_per_step": ms, "value": B / (ms * 1e-3), "unit": UNIT, "loss": loss.item()}
+    clocks = sampler.stop()
+    # attention bytes, fp32 storage, per graph: layer 0 (concat: out and dout are H*C wide), layer 1 (head mean)
+    edge = N * (N - 1) * 3 * L * 4
+    Pb = N * H * Cc * 4
+    l0 = (edge + Pb + N * H * Cc * 4) + (edge + Pb + N * H * Cc * 4 + Pb)
+    l1 = (edge + Pb + N * Cc * 4) + (edge + Pb + N * Cc * 4 + Pb)
+    attn_ms = None
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize(dev)
+        attn_ms = sum(e.device_time_total for e in prof.key_averages() if "gat_attn" in e.key) * 1e-3
+    except Exception:
+        attn_ms = None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    ach = (l0 + l1) * B / (attn_ms * 1e-3) / 1e9 if attn_ms else None
+    line = {"metric": METRIC_BY_CONFIG["C"], "value": res["half"]["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": res["half"]["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 projections (one tensor-core product, fp32 accumulate), f32 attention storage",
+            "data": "synthetic",
+            "config": {"workload": CONFIGS["C"]["name"] + ", GATModel forward + MSE + autograd backward", "nodes": N, "heads": H,
+                       "hidden": [Cc, Cc], "batch_per_gpu": B, "parallelism": "dp1",
+                       "l2": "inputs (x 619 MB, edge_attr 1.80 GB, P 983 MB per layer) exceed the 126 MB L2; no flush needed"},
+            "fp32_mode": res["fp32"],
+            "roofline": {"bound": "hbm", "kernel": "gat_attn_fwd_kernel + gat_attn_bwd2_kernel, both layers (fp32 storage)",
+                         "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm if ach else None, "traffic": None,
+                         "attention_ms_profiled_step": attn_ms, "algorithmic_bytes_per_step": (l0 + l1) * B,
+                         "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": None, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
+
+def run_train_step(args, dev, world, rank, barrier):
+    """Side measurement (SURVEY 8d "full train-step graphs/s"): what one iteration of the reference's loop costs
+    (5_train_SpotV2Net.py:150-160) - GATModel forward (GATConv + ReLU + Linear), MSE loss, backward, Adam - on a collated
+    4096-graph batch of the default configuration, through the public module API; device time over the timed steps."""
+    import spotv2net_b200 as sv
+    B, L, N = args.batch, CFG["L"], CFG["N"]
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    mats = []
+    for _ in range(2):
+        a = torch.randn(B + L + 1, N, N, device=dev, generator=g)
+        mats.append((a + a.transpose(1, 2)) / 2 ** 0.5)
+    ds = sv.WindowDataset(mats[0], mats[1], seq_length=L, device=dev, drop_first=0)
+    bt = ds.collate(torch.arange(B))
+    torch.manual_seed(7)
+    model = sv.GATModel(N * L, 3 * L, CFG["H"], 1, [CFG["C"]], negative_slope=CFG["slope"]).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    crit = torch.nn.MSELoss()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(bt), bt.y_x)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        step()
+    barrier()
+    steps = max(2, min(args.steps, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    loss.item()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    del model, opt, bt, ds
+    torch.cuda.empty_cache()
+    return {"value": world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "what": "spotv2net_b200.GATModel (default config: GATConv 1260 -> 6 x 500 mean, ReLU, Linear 500 -> 1) forward + MSELoss + "
+                    "backward + torch.optim.Adam step on one collated batch; per-rank device time, no all-reduce"}
 
 
 def run_structured(args, dev, world, rank, barrier):
@@ -543,29 +684,55 @@ def run_e2e_windows(args, hp, dev, world, rank, barrier):
     `e2e` leg (`run_e2e`) ships the already-expanded PyG tensors (x, edge_index, edge_attr: 83x the bytes) the
     way the reference's `data.to(device)` does."""
     # structured=True: the batches carry window references, edge_attr is never materialised in HBM (SURVEY 8f-2)
-    ds = hp.sv.WindowDataset(hp.ds.vol, hp.ds.volvol, seq_length=CFG["L"], device=dev, drop_first=0, structured=True)
     layer, dout = hp.layer, hp.dout
-    vol_h, vv_h = ds.vol.cpu().pin_memory(), ds.volvol.cpu().pin_memory()
+    vol_h, vv_h = hp.ds.vol.cpu().pin_memory(), hp.ds.volvol.cpu().pin_memory()
     idx = torch.arange(hp.B)
     h2d = (vol_h.numel() + vv_h.numel()) * 4 + hp.B * 4        # both stacks + the window starts
     steps = max(2, min(args.steps, args.e2e_steps))
 
-    def step():
-        ds.vol.copy_(vol_h, non_blocking=True)
-        ds.volvol.copy_(vv_h, non_blocking=True)
-        bt = ds.collate(idx)                                # window starts H2D + device-side gather
+    # Two stack copies on the device, filled alternately on a copy stream: the H2D of step i+1 and the host-side launch work
+    # of step i+1 run under the kernels of step i.  Every step's loss is still read back inside the timed region - one step
+    # late, so that the host never waits on the step it has just launched.
+    copy_stream = torch.cuda.Stream(dev)
+    main_stream = torch.cuda.current_stream(dev)
+    sets = [hp.sv.WindowDataset(hp.ds.vol.clone(), hp.ds.volvol.clone(), seq_length=CFG["L"], device=dev, drop_first=0, structured=True) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    for s_ in range(2):
+        freed[s_].record(main_stream)
+
+    def issue_copy(s_):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s_])
+            sets[s_].vol.copy_(vol_h, non_blocking=True)
+            sets[s_].volvol.copy_(vv_h, non_blocking=True)
+            ready[s_].record(copy_stream)
+
+    def launch(s_):
+        main_stream.wait_event(ready[s_])
+        bt = sets[s_].collate(idx)                           # window starts H2D + device-side gather (x, its operand pair, y)
         layer.zero_grad(set_to_none=True)
         out = layer(bt.x, bt.edge_index, bt.edge_attr, topology=bt.spot_topology, windows=bt.spot_windows)
         loss = (out * dout).sum()
         loss.backward()
-        return loss.item()                                  # D2H read of the step's result
+        freed[s_].record(main_stream)
+        return loss
 
-    step()
+    issue_copy(0)
+    launch(0).item()                                         # warm-up
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(steps):
-        step()
+    issue_copy(0)
+    pending = None
+    for i in range(steps):
+        if i + 1 < steps:
+            issue_copy((i + 1) & 1)
+        loss = launch(i & 1)
+        if pending is not None:
+            pending.item()                                   # D2H read of the previous step's result
+        pending = loss
+    pending.item()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / steps
@@ -576,9 +743,10 @@ def run_e2e_windows(args, hp, dev, world, rank, barrier):
         ms = t.item()
     return {"value": world * hp.B / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
             "ms_per_step": ms, "steps": steps,
-            "api": "pinned host [T,N,N] vol / vol-of-vol stacks -> H2D -> spotv2net_b200.WindowDataset(structured=True).collate "
-                   "(device; edge_attr never materialised) -> GATConv forward + autograd backward on the window references -> "
-                   "loss.item(); no overlap between steps"}
+            "api": "pinned host [T,N,N] vol / vol-of-vol stacks -> H2D (copy stream, two device copies) -> "
+                   "spotv2net_b200.WindowDataset(structured=True).collate (device; edge_attr never materialised; x also as the GEMM "
+                   "operand pair) -> GATConv forward + autograd backward on the window references -> loss.item() (read one step "
+                   "late, inside the timed region)"}
 
 
 def run_e2e(args, hp, dev, world, rank, barrier):
@@ -618,6 +786,25 @@ def run_e2e(args, hp, dev, world, rank, barrier):
 
     for s in range(2):
         freed[s].record(main_stream)
+    # the host side's ceiling: the same pinned -> device copies with no compute, all ranks at once
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(copy_stream):
+        c0.record(copy_stream)
+        for _ in range(3):
+            for k in keys:
+                bufs[0][k].copy_(host[k], non_blocking=True)
+        c1.record(copy_stream)
+    barrier()
+    copy_only = 3 * h2d / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    copy_stats = {"h2d_GBs_copy_only": copy_only}
+    if world > 1:
+        import torch.distributed as dist
+        g = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(g, torch.tensor([copy_only], device=dev, dtype=torch.float64))
+        per_rank = [t.item() for t in g]
+        copy_stats = {"h2d_GBs_copy_only_per_rank": per_rank, "h2d_GBs_copy_only_sum": sum(per_rank),
+                      "note": "all ranks copy at once, no compute: what the host (memory + PCIe fabric) delivers"}
     issue_copy(0); compute(0)                   # warm-up (also validates and caches nothing across steps)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -636,7 +823,7 @@ def run_e2e(args, hp, dev, world, rank, barrier):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
     return {"value": world * hp.B / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-            "ms_per_step": ms, "steps": steps, "h2d_GBs": h2d / (ms * 1e-3) / 1e9,
+            "ms_per_step": ms, "steps": steps, "h2d_GBs": h2d / (ms * 1e-3) / 1e9, "host_ceiling": copy_stats,
             "api": "spotv2net_b200.GATConv forward + autograd backward; pinned host inputs, copy of step i+1 overlapped "
                    "with step i on a second stream"}
 
@@ -648,7 +835,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="graphs per GPU (default: 4096 for config A, 32 for config D)")
-    ap.add_argument("--config", default="A", choices=sorted(CONFIGS), help="A = the bench line (default); D = 500-node universe")
+    ap.add_argument("--config", default="A", choices=sorted(CONFIGS), help="A = the bench line (default); C = wide two-layer variant; D = 500-node universe")
     ap.add_argument("--cpu-batch", type=int, default=128)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -663,6 +850,8 @@ def main():
         args.batch = CONFIGS[args.config]["batch"]
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "C":
+        run_config_c(args)
     else:
         run_ours(args)
 

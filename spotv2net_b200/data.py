@@ -130,6 +130,12 @@ class WindowDataset:
         self.volvol = volvol.to(self.device, torch.float32).contiguous()
         self.num_node_features = self.N * self.L
         self.num_edge_features = 3 * self.L
+        # per-matrix sums of the co-volatility stack: batch statistics of edge_attr (GATModel standardize=True) without a pass
+        # over the edges (WindowSource.edge_stats)
+        vv64 = self.volvol.double()
+        up, dg = vv64.triu(1), vv64.diagonal(dim1=1, dim2=2)
+        self.mat_stats = torch.stack([up.sum((1, 2)), (up * up).sum((1, 2)), dg.sum(1), (dg * dg).sum(1)], dim=1).contiguous()
+        del vv64, up, dg
         # x values are entries of vol: the fp16 operand pair of every batch shares one power-of-two scale, fixed here
         self.x_scale = torch.empty(8, device=self.device, dtype=torch.float32)
         lib = _lib.load()
@@ -166,8 +172,10 @@ class WindowDataset:
             y = self.vol.diagonal(dim1=1, dim2=2)[t].permute(0, 2, 1).reshape(-1).contiguous()
         ei, topo = batched_topology(B, N, dev)
         # window references ride only on structured batches: with a materialised edge_attr the layers must use it
-        return SpotBatch(x, ei, ea, y, B, N, topo, WindowSource(self.volvol, t0, L, checked=True) if self.structured else None,
-                         (x16, self.x_scale))
+        src = WindowSource(self.volvol, t0, L, checked=True, mat_stats=self.mat_stats)
+        if ea is not None:
+            ea._spot_stats_src = (src, ea._version)       # where GATModel finds the statistics of this very tensor
+        return SpotBatch(x, ei, ea, y, B, N, topo, src if self.structured else None, (x16, self.x_scale))
 
     def __getitem__(self, k):
         if isinstance(k, slice):

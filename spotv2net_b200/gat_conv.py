@@ -33,6 +33,20 @@ class WindowSource:
     t0: Tensor             # [B] int32 on the device
     L: int                 # seq_length; edge_dim must be 3 * L
     checked: bool = False  # t0 + L <= T already verified (WindowDataset.collate checks on the host)
+    # [T, 4] float64 per-matrix sums (upper triangle: sum, sum of squares; diagonal: sum, sum of squares), kept by the
+    # dataset: the batch statistics of edge_attr (standardize=True) follow from them without touching an edge
+    mat_stats: Optional[Tensor] = None
+
+    def edge_stats(self):
+        """(sum, sum of squares, count) per edge feature over the batch's B*N*(N-1) real edges, float64 [3L] each.
+        Feature k*L + t (utils/dataset.py:228-242): k = 0 the pair's co-volatility - every upper-triangle entry of matrix
+        t0 + t twice (once per direction); k = 1 / 2 the source / target variance - every diagonal entry N - 1 times."""
+        N, L = self.volvol.shape[1], self.L
+        idx = self.t0.long().view(-1, 1) + torch.arange(L, device=self.t0.device).view(1, L)
+        m = self.mat_stats[idx].sum(0)                                   # [L, 4]
+        se = torch.cat([2.0 * m[:, 0], (N - 1.0) * m[:, 2], (N - 1.0) * m[:, 2]])
+        qe = torch.cat([2.0 * m[:, 1], (N - 1.0) * m[:, 3], (N - 1.0) * m[:, 3]])
+        return se, qe, float(self.t0.numel() * N * (N - 1))
 
 
 @dataclass
@@ -158,14 +172,14 @@ class _GatLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, edge_attr, W, a_src, a_dst, W_e, a_edge, bias, topo, H, Cc, concat, slope, want_alpha,
-                dropout_p=0.0, seed=0, gemm_algo=None, windows=None, x_pair=None):
+                dropout_p=0.0, seed=0, gemm_algo=None, windows=None, x_pair=None, edge_scale=None, edge_mean=None):
         with torch.cuda.device(x.device):        # launches, attribute calls and tensor maps go to the CURRENT device
             return _GatLayerFn._forward(ctx, x, edge_attr, W, a_src, a_dst, W_e, a_edge, bias, topo, H, Cc, concat, slope,
-                                        want_alpha, dropout_p, seed, gemm_algo, windows, x_pair)
+                                        want_alpha, dropout_p, seed, gemm_algo, windows, x_pair, edge_scale, edge_mean)
 
     @staticmethod
     def _forward(ctx, x, edge_attr, W, a_src, a_dst, W_e, a_edge, bias, topo, H, Cc, concat, slope, want_alpha,
-                 dropout_p, seed, gemm_algo, windows, x_pair):
+                 dropout_p, seed, gemm_algo, windows, x_pair, edge_scale, edge_mean):
         lib = _lib.load()
         dev = x.device
         st = stream_ptr(dev)
@@ -186,6 +200,11 @@ class _GatLayerFn(torch.autograd.Function):
         v = torch.empty(H, Fe, device=dev, dtype=torch.float32) if Fe else None
         check(lib.spotv2_gat_fold(C.byref(desc), ptr(W), ptr(a_src), ptr(a_dst), ptr(W_e) if Fe else None,
                                   ptr(a_edge) if Fe else None, ptr(W_aug), ptr(v), st), "spotv2_gat_fold")
+        if Fe and edge_scale is not None:
+            # per-feature scale of the edge features (BatchNorm1d(affine=False) of the model's standardize=True): its
+            # 1/sqrt(var + eps) rides on v; its mean is a per-head constant -<mean, v'> INSIDE the LeakyReLU, added to the
+            # target term d after the projection (below)
+            v.mul_(edge_scale.view(1, Fe))
         ws_f, _, _ = _workspace(desc)
         ws = torch.empty(ws_f, device=dev, dtype=torch.uint8)
         P_aug = torch.empty(n, desc.ldp, device=dev, dtype=torch.float32)
@@ -203,6 +222,10 @@ class _GatLayerFn(torch.autograd.Function):
         check(lib.spotv2_proj_fwd(C.byref(desc), ptr(x), ptr(x16[0]) if x16 is not None else None,
                                   ptr(x16[1]) if x16 is not None else None, ptr(x_blk), ptr(W_aug), ptr(P_aug), ptr(p_amax),
                                   ptr(ws), ws_f, st), "spotv2_proj_fwd")
+        if Fe and edge_scale is not None and edge_mean is not None:
+            # <e_hat, v> = <e, v'> - <mean, v'>: the same shift on every logit of the head, self loop included (its fill is the
+            # mean of the real edges' e_hat) - carried by the d columns of P_aug, which both attention kernels read
+            P_aug[:, HC + H:HC + 2 * H].sub_((v @ edge_mean.view(Fe, 1)).view(1, H))
         out = torch.empty(n, HC if concat else Cc, device=dev, dtype=torch.float32)
         alpha = torch.empty(topo.B, H, topo.N, topo.N, device=dev, dtype=torch.float32) if want_alpha else None
         # N > 32 only: the [B,H,N,N] attention tile lives in a workspace unless the caller asked for alpha itself
@@ -223,6 +246,8 @@ class _GatLayerFn(torch.autograd.Function):
         check(lib.spotv2_gat_attn_fwd(C.byref(desc), ptr(P_aug), ptr(ea), ptr(topo.table) if (Fe and windows is None) else None, ptr(v),
                                       ptr(bias_c), ptr(out), ptr(alpha), ptr(et), ptr(ws_attn), ws_t, st), "spotv2_gat_attn_fwd")
         ctx.desc, ctx.topo, ctx.Fe, ctx.has_bias, ctx.windows = desc, topo, Fe, bias is not None, windows
+        ctx.edge_scale = edge_scale if Fe else None
+        ctx.edge_mean = edge_mean if (Fe and edge_scale is not None) else None
         ctx.save_for_backward(x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk, p_amax, et)
         if want_alpha:
             ctx.mark_non_differentiable(alpha)
@@ -271,6 +296,17 @@ class _GatLayerFn(torch.autograd.Function):
             ws_dv = torch.empty(wsz.value, device=dev, dtype=torch.uint8)
             check(lib.spotv2_windows_dv(C.byref(desc), ptr(win.volvol), win.volvol.shape[0], win.L, ptr(win.t0), ptr(d_et),
                                         ptr(dv), ptr(ws_dv), wsz.value, st), "spotv2_windows_dv")
+        if ctx.edge_scale is not None:
+            # the layer saw e_hat = (e - mean) * scale through v' = scale * v and the per-head logit shift -<mean, v'> on the
+            # d columns.  d/dv = scale * (sum dz' e - mean * sum of ALL dz of the head): the kernels formed the first sum (dv),
+            # the second is the column sum of the dd block (LeakyReLU keeps a softmax row's dz from summing to zero).
+            if tc:
+                T = ((dP16[0][:, HC + H:HC + 2 * H].float() + dP16[1][:, HC + H:HC + 2 * H].float()).sum(0) * dp_blk[3])
+            else:
+                T = dP_aug[:, HC + H:HC + 2 * H].sum(0)
+            if ctx.edge_mean is not None:
+                dv.sub_(T.view(H, 1) * ctx.edge_mean.view(1, Fe))
+            dv.mul_(ctx.edge_scale.view(1, Fe))
         dW_aug = torch.empty_like(W_aug)
         xh = x16[0] if x16 is not None else None
         xl = x16[1] if x16 is not None else None
@@ -292,7 +328,7 @@ class _GatLayerFn(torch.autograd.Function):
                                     ptr(da_dst), ptr(dW_e), ptr(da_edge), st), "spotv2_gat_unfold")
         if not Fe and W_e is not None:          # layer has lin_edge but was called with edge_attr=None
             dW_e, da_edge = torch.zeros_like(W_e), torch.zeros_like(a_edge)
-        return (dx, None, dW, da_src, da_dst, dW_e, da_edge, dbias) + (None,) * 11
+        return (dx, None, dW, da_src, da_dst, dW_e, da_edge, dbias) + (None,) * 13
 
 
 # --------------------------------------------------------------------------- module
@@ -383,7 +419,8 @@ class GATConv(nn.Module):
 
     def forward(self, x: Tensor, edge_index, edge_attr: Optional[Tensor] = None, size=None,
                 return_attention_weights=None, topology: Optional[Topology] = None,
-                windows: Optional[WindowSource] = None):
+                windows: Optional[WindowSource] = None, edge_scale: Optional[Tensor] = None,
+                edge_mean: Optional[Tensor] = None):
         assert x.dim() == 2, "Static graphs not supported in 'GATConv'"
         _lib.require_cuda(x, "x")
         # attention dropout (dropout_att; 0.0 by default, config/GNN_param.yaml:36): a fresh 64-bit Philox key per
@@ -441,7 +478,8 @@ class GATConv(nn.Module):
             x, edge_attr if (use_edge and windows is None) else None, self.lin_src.weight, self.att_src, self.att_dst,
             self.lin_edge.weight if self.lin_edge is not None else None, self.att_edge, self.bias,
             topo, self.heads, self.out_channels, self.concat, self.negative_slope, want_alpha, drop_p, seed,
-            PRECISIONS[self.precision], windows if use_edge else None, x_pair)
+            PRECISIONS[self.precision], windows if use_edge else None, x_pair, edge_scale if use_edge else None,
+            edge_mean if use_edge else None)
         if not want_alpha:
             return out
         return out, self._attention_weights(alpha_tile, topo, edge_index)

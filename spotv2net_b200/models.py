@@ -11,6 +11,7 @@ import sys
 from typing import Sequence
 
 import torch
+import torch.distributed as dist
 import torch.nn.functional as F
 from torch import nn
 
@@ -68,13 +69,58 @@ class GATModel(nn.Module):
             layer.precision = precision
         return self
 
+    def _standardize(self, data, x, edge_attr, win):
+        """``bnorm_node(x)`` / ``bnorm_edge(edge_attr)`` of the reference (BatchNorm1d(affine=False), utils/models.py:80-82,
+        142-144) without a pass that rewrites the 1.8 GB of edge features: the statistics come from the batch (training) or
+        from the running buffers (eval), x is normalised by one fused elementwise pass, and the edge normalisation is handed
+        to the layers as a per-feature (mean, scale) pair - the scale rides on the folded edge vector v, the mean becomes a
+        per-head constant -<mean, v'> on every logit of the head, inside the LeakyReLU (the backward corrects dv for it).  For batches of a
+        WindowDataset the edge statistics are formed from per-matrix sums of the [T, N, N] stack (no pass over edges at all).
+        Under torch.distributed the batch statistics are all-reduced (2 (F + Fe) + 2 numbers): every rank normalises with
+        the statistics of the GLOBAL batch, as a single process would."""
+        bn_x, bn_e = self.bnorm_node, self.bnorm_edge
+        if self.training:
+            nx = float(x.shape[0])
+            sx, qx = x.sum(0, dtype=torch.float64), (x * x).sum(0, dtype=torch.float64)
+            src = win if (win is not None and win.mat_stats is not None) else None
+            if edge_attr is not None:
+                tag = getattr(edge_attr, "_spot_stats_src", None)      # attached by WindowDataset.collate to this very tensor
+                src = tag[0] if (tag is not None and tag[1] == edge_attr._version) else None
+            if src is not None:
+                se, qe, ne = src.edge_stats()                          # [Fe] float64 sums over the batch's real edges
+            else:
+                if edge_attr is None:
+                    raise ValueError("standardize=True needs edge_attr or a WindowDataset batch")
+                ne = float(edge_attr.shape[0])
+                se, qe = edge_attr.sum(0, dtype=torch.float64), (edge_attr * edge_attr).sum(0, dtype=torch.float64)
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                buf = torch.cat([sx, qx, se, qe, torch.tensor([nx, ne], device=x.device, dtype=torch.float64)])
+                dist.all_reduce(buf)
+                F_, Fe_ = sx.numel(), se.numel()
+                sx, qx, se, qe = buf[:F_], buf[F_:2 * F_], buf[2 * F_:2 * F_ + Fe_], buf[2 * F_ + Fe_:2 * F_ + 2 * Fe_]
+                nx, ne = buf[-2].item(), buf[-1].item()
+            mx, me = sx / nx, se / ne
+            vx, ve = (qx / nx - mx * mx).clamp_min(0.0), (qe / ne - me * me).clamp_min(0.0)
+            with torch.no_grad():                                      # running statistics, as nn.BatchNorm1d keeps them
+                for bn, m, v, n in ((bn_x, mx, vx, nx), (bn_e, me, ve, ne)):
+                    mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
+                    bn.running_mean.mul_(1 - mom).add_(mom * m.to(bn.running_mean.dtype))
+                    bn.running_var.mul_(1 - mom).add_(mom * (v * (n / max(n - 1.0, 1.0))).to(bn.running_var.dtype))
+                    bn.num_batches_tracked += 1
+        else:
+            mx, vx, me, ve = bn_x.running_mean.double(), bn_x.running_var.double(), bn_e.running_mean.double(), bn_e.running_var.double()
+        rx, re = torch.rsqrt(vx + bn_x.eps).float(), torch.rsqrt(ve + bn_e.eps).float()
+        x = (x - mx.float()) * rx
+        return x, me.float().contiguous(), re.contiguous()
+
     def forward(self, data):
         x, edge_index, edge_attr = data.x, data.edge_index, data.edge_attr
+        # A materialised edge_attr always wins over window references: the caller may have edited it (train() scales it by
+        # scale_up, 5_train_SpotV2Net.py:145-147), and the windows would silently ignore that.
+        win = None if edge_attr is not None else getattr(data, "spot_windows", None)
+        e_mean = e_scale = None
         if self.standardize:
-            if edge_attr is None:
-                raise ValueError("standardize=True normalises edge_attr: collate with structured=False")
-            x = self.bnorm_node(x)
-            edge_attr = self.bnorm_edge(edge_attr)
+            x, e_mean, e_scale = self._standardize(data, x, edge_attr, win)
         # one topology check per batch, shared by all layers (a batch produced by
         # spotv2net_b200.data carries it already)
         topo = getattr(data, "spot_topology", None)
@@ -82,17 +128,13 @@ class GATModel(nn.Module):
             topo = topology_from_edge_index(edge_index, x.shape[0], getattr(data, "nodes_per_graph", None))
         if self.collect_attention:
             self.attention_weights = []
-        # batches of a structured WindowDataset carry window references: the layers read the [L, N, N] windows instead of
-        # edge_attr (not with standardize=True: BatchNorm changes the edge features, which then must be materialised)
-        # A materialised edge_attr always wins: the caller may have edited it (train() scales it by scale_up,
-        # 5_train_SpotV2Net.py:145-147), and the windows would silently ignore that.
-        win = None if (self.standardize or edge_attr is not None) else getattr(data, "spot_windows", None)
         for layer in self.gat_layers:
             if self.collect_attention:
-                x, att = layer(x, edge_index, edge_attr, return_attention_weights=True, topology=topo, windows=win)
+                x, att = layer(x, edge_index, edge_attr, return_attention_weights=True, topology=topo, windows=win,
+                               edge_scale=e_scale, edge_mean=e_mean)
                 self.attention_weights.append(att)
             else:
-                x = layer(x, edge_index, edge_attr, topology=topo, windows=win)
+                x = layer(x, edge_index, edge_attr, topology=topo, windows=win, edge_scale=e_scale, edge_mean=e_mean)
             x = self.a(x)
             if self.dropout:
                 x = F.dropout(x, p=self.dropout, training=self.training)

@@ -66,7 +66,9 @@ def _scaled(batch, scale):
             batch.edge_attr = batch.edge_attr * scale
         win = getattr(batch, "spot_windows", None)
         if win is not None:
-            batch.spot_windows = WindowSource(win.volvol * scale, win.t0, win.L, win.checked)
+            ms = None if win.mat_stats is None else win.mat_stats * torch.tensor([scale, scale * scale, scale, scale * scale],
+                                                                                dtype=torch.float64, device=win.mat_stats.device)
+            batch.spot_windows = WindowSource(win.volvol * scale, win.t0, win.L, win.checked, ms)
         batch.y_x = batch.y_x * scale
     return batch
 

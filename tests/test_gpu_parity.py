@@ -987,8 +987,61 @@ def test_structured_and_materialised_model_steps_agree(cuda_lib):
     # layer-1 gradients are exact functions of the same activations; layer-0's pass through a ReLU (kinks): 1e-4
     for k in grads[0][1]:
         assert relerr(grads[1][1][k], grads[0][1][k]) < 1e-4, k
-    with pytest.raises(ValueError):
-        sv.GATModel(**dict(kw, standardize=True)).to(DEV)(ds.collate([0, 1]))      # BatchNorm needs the edge features
+
+
+@pytest.mark.parametrize("layers", [[20], [16, 12]], ids=["one_layer", "two_layers"])
+def test_standardize_on_every_batch_kind_matches_the_oracle_model(cuda_lib, layers):
+    """standardize=True (BatchNorm1d(affine=False) on x and on the real edges, utils/models.py:80-82,142-144) without a
+    normalising pass over edge_attr: the edge statistics ride into the layers as (mean, scale), from torch sums (a PyG-style
+    batch), from the dataset's per-matrix sums (WindowDataset, materialised) or with no edge tensor at all (structured).
+    Data with a clear offset (means of 2 .. 3 standard deviations), so the mean's cancellation in the softmax and its
+    correction in dv are both exercised.  Loss, every gradient, the running statistics and the eval-mode output against
+    OracleGATModel(standardize=True) in fp64."""
+    import copy
+    N, L, B = 30, 4, 7
+    vol, vv = synth.synthetic_matrices(L + B + 2, N, seed=13)
+    vol, vv = vol * 0.7 + 2.0, vv * 0.4 + 1.2                # not standardised: that is when the flag is used
+    kw = dict(num_node_features=N * L, num_edge_features=3 * L, num_heads=3, output_node_channels=1, dim_hidden_layers=layers,
+              concat_heads=True, standardize=True)
+    torch.manual_seed(2)
+    ref = pyg_gat.OracleGATModel(**kw).double()
+    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}           # weights and FRESH running statistics
+    bt = synth.make_batch(vol, vv, list(range(B)), L)
+    d64 = synth.Batch(x=bt.x.double(), edge_index=bt.edge_index, edge_attr=bt.edge_attr.double())
+    ref.train()
+    loss_ref = torch.nn.functional.mse_loss(ref(d64), bt.y_x.double())
+    loss_ref.backward()
+    ref32 = pyg_gat.OracleGATModel(**kw)
+    ref32.load_state_dict({k: (v.float() if v.is_floating_point() else v) for k, v in sd0.items()})
+    ref32.train()
+    torch.nn.functional.mse_loss(ref32(synth.Batch(x=bt.x, edge_index=bt.edge_index, edge_attr=bt.edge_attr)), bt.y_x).backward()
+    ref.eval()
+    out_eval_ref = ref(d64).detach()                          # eval: the running statistics after ONE training step
+    g64 = {k: p.grad for k, p in ref.named_parameters()}
+    g32 = {k: p.grad for k, p in ref32.named_parameters()}
+    for kind in ("pyg_batch", "materialised", "structured"):
+        ours = sv.GATModel(**kw)
+        ours.load_state_dict({k: (v.float() if v.is_floating_point() else v) for k, v in sd0.items()})
+        ours.to(DEV)
+        if kind == "pyg_batch":
+            data = copy.deepcopy(bt).to(DEV)
+        else:
+            ds = sv.WindowDataset(vol, vv, seq_length=L, device=DEV, drop_first=0, structured=kind == "structured")
+            data = ds.collate(list(range(B)))
+            assert (data.edge_attr is None) == (kind == "structured")
+        ours.train()
+        loss = torch.nn.functional.mse_loss(ours(data), data.y_x)
+        loss.backward()
+        assert abs(loss.item() - loss_ref.item()) <= 2e-5 * abs(loss_ref.item()), kind
+        bad = parity_failures({k: p.grad for k, p in ours.named_parameters()}, g64, g32)
+        assert not bad, (kind, bad)
+        for name in ("bnorm_node", "bnorm_edge"):
+            mine, want = getattr(ours, name), getattr(ref, name)
+            assert relerr(mine.running_mean, want.running_mean) < 1e-5 and relerr(mine.running_var, want.running_var) < 1e-5, (kind, name)
+            assert int(mine.num_batches_tracked) == 1
+        ours.eval()
+        with torch.no_grad():
+            assert relerr(ours(data), out_eval_ref) < 2e-5, kind
 
 
 def test_scale_up_reaches_the_edge_features_on_both_batch_kinds(cuda_lib):
