@@ -184,17 +184,25 @@ class HotPath:
         torch.manual_seed(seed)
         self.layer = sv.GATConv(Fin, Cc, heads=H, concat=False, negative_slope=CFG["slope"], edge_dim=Fe).to(device)
         n, HC = B * N, H * Cc
+        # p_format 1 (the library's default wherever its kernels apply): the projection travels as the fp16 operand pair the
+        # GEMM epilogue writes; --p-format 0 keeps the fp32 P_aug of round 1
+        pf = getattr(HotPath, "P_FORMAT", None)
+        if pf is None:
+            pf = 1 if sv.gat_conv.pair_format_applies(N, Fe, Cc, 0, 0) else 0
+        self.pair = pf == 1
         self.desc = _lib.GatDesc(B, N, Fin, Fe, H, Cc, N * (N - 1), 0, CFG["slope"], self.lib.spotv2_gat_ldp(H, Cc), 0, 0,
-                                 0.0, 1 if structured else 0)
+                                 0.0, 1 if structured else 0, 0, 0, pf)
+        n_aug = self.lib.spotv2_gat_n_aug(C.byref(self.desc))
         a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
         _lib.check(self.lib.spotv2_gat_workspace_bytes(C.byref(self.desc), C.byref(a), C.byref(b), C.byref(c)), "ws")
         f32 = dict(device=device, dtype=torch.float32)
         f = C.c_size_t()
         _lib.check(self.lib.spotv2_gat_attn_fwd_workspace_bytes(C.byref(self.desc), C.byref(f)), "attn_fwd ws")
         self.ws = torch.empty(max(a.value, b.value, c.value, f.value), device=device, dtype=torch.uint8)
-        self.W_aug = torch.empty(HC + 2 * H, Fin, **f32)
+        self.W_aug = torch.empty(n_aug, Fin, **f32)
         self.v = torch.empty(H, Fe, **f32)
-        self.P_aug = torch.empty(n, self.desc.ldp, **f32)
+        self.P_aug = (torch.empty(2, n, self.lib.spotv2_gat_ld16(n_aug), device=device, dtype=torch.float16) if self.pair
+                      else torch.empty(n, self.desc.ldp, **f32))
         self.p_amax = torch.empty(8, **f32)
         et = C.c_size_t()
         _lib.check(self.lib.spotv2_gat_edge_terms_bytes(C.byref(self.desc), C.byref(et)), "edge_terms_bytes")
@@ -211,7 +219,7 @@ class HotPath:
         self.tc = bool(self.lib.spotv2_gat_uses_tensor_cores(C.byref(self.desc)))
         # tensor-core operand pairs (scaled fp16 hi/lo + 8-float scale block): x once per step, dP from attn_bwd
         f16 = dict(device=device, dtype=torch.float16)
-        self.ldf16, self.ldp16 = self.lib.spotv2_gat_ld16(Fin), self.lib.spotv2_gat_ld16(HC + 2 * H)
+        self.ldf16, self.ldp16 = self.lib.spotv2_gat_ld16(Fin), self.lib.spotv2_gat_ld16(n_aug)
         self.dP_aug = None if self.tc else torch.empty(n, self.desc.ldp, **f32)
         self.dP16 = torch.empty(2, n, self.ldp16, **f16) if self.tc else None
         # x as the GEMMs' operand pair: emitted by the collation (spotv2_collate_windows_pair; the dataset fixes the scale),
@@ -223,7 +231,7 @@ class HotPath:
             self.x16 = torch.empty(2, n, self.ldf16, **f16) if self.tc else None
             self.x_blk = torch.empty(8, **f32) if self.tc else None
         self.dp_blk = torch.empty(8, **f32) if self.tc else None
-        self.dW_aug = torch.empty(HC + 2 * H, Fin, **f32)
+        self.dW_aug = torch.empty(n_aug, Fin, **f32)
         self.dv = torch.empty(H, Fe, **f32)
         # flat gradient arena: the one buffer the data-parallel all-reduce moves
         sizes = [HC * Fin, HC, HC, HC * Fe, HC, Cc]
@@ -258,8 +266,12 @@ class HotPath:
         if self.tc and not self.x_from_collation:      # x given as fp32 only: one amax + one split pass per step
             chk(lib.spotv2_split_f16(p(self.batch.x), self.B * self.N, self.Fin, self.Fin, 0, 0, p(xh), p(xl), self.ldf16,
                                      p(self.x_blk), st), "split_f16")
-        chk(lib.spotv2_proj_fwd(d, p(self.batch.x), p(xh), p(xl), p(self.x_blk), p(self.W_aug), p(self.P_aug), p(self.p_amax),
-                                p(self.ws), self.ws.numel(), st), "proj_fwd")
+        if self.pair:
+            chk(lib.spotv2_proj_fwd_pair(d, p(xh), p(xl), p(self.x_blk), p(self.W_aug), p(self.P_aug[0]), p(self.P_aug[1]),
+                                         p(self.p_amax), p(self.ws), self.ws.numel(), st), "proj_fwd_pair")
+        else:
+            chk(lib.spotv2_proj_fwd(d, p(self.batch.x), p(xh), p(xl), p(self.x_blk), p(self.W_aug), p(self.P_aug), p(self.p_amax),
+                                    p(self.ws), self.ws.numel(), st), "proj_fwd")
         mark("proj_fwd")
         win = self.win
         if self.structured:      # structured edge source: the [L,N,N] windows instead of the materialised edge rows
@@ -269,13 +281,22 @@ class HotPath:
             mark("edge_terms")
         ea = None if self.structured else self.batch.edge_attr
         tbl = None if self.structured else self.batch.spot_topology.table
-        chk(lib.spotv2_gat_attn_fwd(d, p(self.P_aug), p(ea), p(tbl), p(self.v), p(L.bias), p(self.out), None,
-                                    p(self.edge_terms), p(self.ws), self.ws.numel(), st), "attn_fwd")
-        mark("attn_fwd")
-        chk(lib.spotv2_gat_attn_bwd(d, p(self.P_aug), p(self.p_amax), p(ea), p(self.edge_terms), p(tbl),
-                                    p(self.v), p(self.dout), p(self.dP_aug), p(ph), p(pl), p(self.dp_blk),
-                                    None if self.structured else p(self.dv), p(self.d_edge_terms),
-                                    p(self.g_b), p(self.ws), self.ws.numel(), st), "attn_bwd")
+        if self.pair:
+            chk(lib.spotv2_gat_attn_fwd_pair(d, p(self.P_aug[0]), p(self.P_aug[1]), p(self.p_amax), p(ea), p(tbl), p(self.v),
+                                             p(L.bias), p(self.out), None, p(self.edge_terms), st), "attn_fwd_pair")
+            mark("attn_fwd")
+            chk(lib.spotv2_gat_attn_bwd_pair(d, p(self.P_aug[0]), p(self.P_aug[1]), p(self.p_amax), p(ea), p(self.edge_terms),
+                                             p(tbl), p(self.v), p(self.dout), p(ph), p(pl), p(self.dp_blk),
+                                             None if self.structured else p(self.dv), p(self.d_edge_terms),
+                                             p(self.g_b), p(self.ws), self.ws.numel(), st), "attn_bwd_pair")
+        else:
+            chk(lib.spotv2_gat_attn_fwd(d, p(self.P_aug), p(ea), p(tbl), p(self.v), p(L.bias), p(self.out), None,
+                                        p(self.edge_terms), p(self.ws), self.ws.numel(), st), "attn_fwd")
+            mark("attn_fwd")
+            chk(lib.spotv2_gat_attn_bwd(d, p(self.P_aug), p(self.p_amax), p(ea), p(self.edge_terms), p(tbl),
+                                        p(self.v), p(self.dout), p(self.dP_aug), p(ph), p(pl), p(self.dp_blk),
+                                        None if self.structured else p(self.dv), p(self.d_edge_terms),
+                                        p(self.g_b), p(self.ws), self.ws.numel(), st), "attn_bwd")
         mark("attn_bwd")
         if self.structured:
             chk(lib.spotv2_windows_dv(d, p(win.volvol), win.volvol.shape[0], win.L, p(win.t0), p(self.d_edge_terms), p(self.dv),
@@ -842,10 +863,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-structured", action="store_true", help="skip the structured-edge-source side measurement")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay side measurement")
+    ap.add_argument("--p-format", type=int, default=None, choices=[0, 1], help="0: fp32 P_aug between GEMM and attention (round 1); 1: fp16 operand pair (default where it applies)")
     ap.add_argument("--split-x-in-step", action="store_true", help="derive x's operand pair from the fp32 x inside every step (round-1 behaviour)")
     args = ap.parse_args()
     CFG["N"] = CONFIGS[args.config]["N"]
     HotPath.SPLIT_X_IN_STEP = args.split_x_in_step
+    HotPath.P_FORMAT = args.p_format
     if args.batch <= 0:
         args.batch = CONFIGS[args.config]["batch"]
     if args.impl == "reference":

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SPOTV2_ABI_VERSION 4
+#define SPOTV2_ABI_VERSION 5
 
 typedef enum spotv2_status {
   SPOTV2_OK = 0,
@@ -87,6 +87,18 @@ typedef struct spotv2_gat_desc {
   uint32_t dropout_seed_lo, dropout_seed_hi;   /* Philox4x32-10 key of the mask; element (b,h,i,j)
                              uses counter ((((b*H+h)*N+i)*N+j) >> 2), lane (.. & 3); pass
                              the same key to attn_fwd and attn_bwd of one step              */
+  int32_t p_format;       /* how the projection travels between proj_fwd and the attention kernels, and dP back:
+                             0: fp32 P_aug [B*N, ldp] (the contract above; every kernel covers it).
+                             1: "pair" - P never exists in fp32: the projection GEMM's epilogue emits the fp16 operand
+                                pair (hi, lo planes [B*N, ld16(n_aug)], n_aug = H*Cp + 2H, head pitch Cp = C rounded up
+                                to 8 so that every (head, channel block) tile starts on a 16-byte boundary for TMA) with
+                                a power-of-two scale per column group taken from an a-priori bound
+                                |P| <= max|x| * max_j ||W_aug[j,:]||_1, and the attention kernels feed the planes to
+                                the tensor cores without converting anything.  W_aug, dW_aug and the dP pair use the
+                                same padded row / column layout (pad rows of W_aug are zero).  N <= 32, tensor-core
+                                GEMM only (gemm_algo 0 | 2 | 3); with gemm_algo 3 only the hi planes exist (fp16
+                                storage of P and dP: BASELINE config C's reduced-precision variant).
+                             Use the *_pair entry points below with p_format 1.                                  */
 } spotv2_gat_desc;
 
 /* Row table entry: (i << 16) | j  = "this edge row is j -> i" (i target, j source),
@@ -99,6 +111,11 @@ int32_t     spotv2_abi_version(void);
 
 /* Smallest legal ldp for (H, C). */
 int32_t spotv2_gat_ldp(int32_t H, int32_t C);
+/* Rows of W_aug / dW_aug and columns of the P / dP pair planes for this descriptor: H*Cp + 2H with the head pitch
+ * Cp = C (p_format 0) or C rounded up to 8 (p_format 1); head h's channel c sits at h*Cp + c, s_h at H*Cp + h,
+ * d_h at H*Cp + H + h. */
+int32_t spotv2_gat_n_aug(const spotv2_gat_desc* d);
+int32_t spotv2_gat_head_pitch(const spotv2_gat_desc* d);
 
 /* Bytes of scratch each phase wants (device memory, 256-byte aligned). */
 int spotv2_gat_workspace_bytes(const spotv2_gat_desc* d, size_t* proj_fwd, size_t* attn_bwd,
@@ -183,6 +200,27 @@ int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug, const floa
                         void* dP_hi_or_null, void* dP_lo_or_null, float* dp_scale_or_null,
                         float* dv_or_null, float* d_edge_terms_or_null, float* dbias_or_null, void* ws, size_t ws_bytes,
                         void* stream);
+
+/* ---- p_format 1: the projection as an fp16 operand pair end to end ---------------------------------------------
+ * Same operators as spotv2_proj_fwd / spotv2_gat_attn_fwd / spotv2_gat_attn_bwd ([PyG] F.linear, edge_update,
+ * softmax, propagate and their autograd), different intermediate: P_hi / P_lo are [B*N, ld16(n_aug)] fp16 planes
+ * (P_lo may be null with gemm_algo 3), p_scale an 8-float scale block ({bound bits x2, inverse scales x2, scales x2}:
+ * group 0 the H*Cp projection columns, group 1 the s|d columns) written by proj_fwd_pair and read by the other two.
+ * x must be given as a pair (x_hi, x_lo, x_scale; spotv2_split_f16 or spotv2_collate_windows_pair): the bound needs
+ * max|x|, which the scale block holds.  W_aug is spotv2_gat_fold's output for the same descriptor ([n_aug, F]).
+ * attn_bwd_pair emits dP as the pair [B*N, ld16(n_aug)] in the padded layout (pad columns zero), consumed by
+ * spotv2_proj_bwd_weight / spotv2_proj_bwd_input with the same descriptor. */
+int spotv2_proj_fwd_pair(const spotv2_gat_desc* d, const void* x_hi, const void* x_lo, const float* x_scale,
+                         const float* W_aug, void* P_hi, void* P_lo_or_null, float* p_scale, void* ws, size_t ws_bytes,
+                         void* stream);
+int spotv2_gat_attn_fwd_pair(const spotv2_gat_desc* d, const void* P_hi, const void* P_lo_or_null, const float* p_scale,
+                             const float* edge_rows, const int32_t* table, const float* v, const float* bias_or_null,
+                             float* out, float* alpha_or_null, float* edge_terms_or_null, void* stream);
+int spotv2_gat_attn_bwd_pair(const spotv2_gat_desc* d, const void* P_hi, const void* P_lo_or_null, const float* p_scale,
+                             const float* edge_rows, const float* edge_terms_or_null, const int32_t* table,
+                             const float* v, const float* dout, void* dP_hi, void* dP_lo_or_null, float* dp_scale,
+                             float* dv_or_null, float* d_edge_terms_or_null, float* dbias_or_null, void* ws,
+                             size_t ws_bytes, void* stream);
 
 /* ---- structured edge source (csrc/windows.cu) ---------------------------------------------------
  * In the reference's dataset (utils/dataset.py:228-242) edge_attr is a pure function of the window of co-volatility

@@ -21,7 +21,8 @@ class GatDesc(C.Structure):
     _fields_ = [("B", _i32), ("N", _i32), ("F", _i32), ("Fe", _i32), ("H", _i32), ("C", _i32),
                 ("R", _i32), ("concat", _i32), ("negative_slope", _f32), ("ldp", _i32),
                 ("gemm_algo", _i32), ("attn_bwd_algo", _i32),
-                ("dropout_p", _f32), ("edge_mode", _i32), ("dropout_seed_lo", C.c_uint32), ("dropout_seed_hi", C.c_uint32)]
+                ("dropout_p", _f32), ("edge_mode", _i32), ("dropout_seed_lo", C.c_uint32), ("dropout_seed_hi", C.c_uint32),
+                ("p_format", _i32)]
 
 
 class SpotV2Error(RuntimeError):
@@ -34,7 +35,12 @@ SIGNATURES = {
     "spotv2_last_error": (C.c_char_p, []),
     "spotv2_abi_version": (_i32, []),
     "spotv2_gat_ldp": (_i32, [_i32, _i32]),
+    "spotv2_gat_n_aug": (_i32, [_DP]),
+    "spotv2_gat_head_pitch": (_i32, [_DP]),
     "spotv2_gat_workspace_bytes": (C.c_int, [_DP, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
+    "spotv2_proj_fwd_pair": (C.c_int, [_DP] + [_vp] * 8 + [_sz, _vp]),
+    "spotv2_gat_attn_fwd_pair": (C.c_int, [_DP] + [_vp] * 11),
+    "spotv2_gat_attn_bwd_pair": (C.c_int, [_DP] + [_vp] * 15 + [_sz, _vp]),
     "spotv2_edge_table_build": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
     "spotv2_edge_table_dense": (C.c_int, [_i32, _vp, _vp]),
     "spotv2_gat_fold": (C.c_int, [_DP] + [_vp] * 8),
@@ -80,8 +86,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.spotv2_abi_version() != 4:
-        raise SpotV2Error(f"ABI version mismatch: library reports {lib.spotv2_abi_version()}, binding expects 4")
+    if lib.spotv2_abi_version() != 5:
+        raise SpotV2Error(f"ABI version mismatch: library reports {lib.spotv2_abi_version()}, binding expects 5")
     _lib = lib
     return lib
 

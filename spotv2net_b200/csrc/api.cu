@@ -35,6 +35,9 @@ int check_desc(const spotv2_gat_desc* d) {
   if (!(d->dropout_p >= 0.f && d->dropout_p < 1.f))
     return fail(SPOTV2_ERR_INVALID_ARG, "dropout_p=%g must be in [0, 1)", (double)d->dropout_p);
   if (d->Fe > 0 && d->R <= 0) return fail(SPOTV2_ERR_INVALID_ARG, "R must be positive when Fe > 0");
+  if (d->p_format != 0 && d->p_format != 1) return fail(SPOTV2_ERR_INVALID_ARG, "p_format=%d must be 0 (fp32) or 1 (fp16 pair)", d->p_format);
+  if (d->p_format == 1 && (d->N > 32 || d->gemm_algo == 1))
+    return fail(SPOTV2_ERR_UNSUPPORTED, "p_format 1 covers N <= 32 on the tensor-core GEMM (gemm_algo 0, 2 or 3)");
   return SPOTV2_OK;
 }
 
@@ -55,6 +58,8 @@ using namespace spotv2;
 extern "C" const char* spotv2_last_error(void) { return g_err; }
 extern "C" int32_t spotv2_abi_version(void) { return SPOTV2_ABI_VERSION; }
 // >= 32 floats so one P_aug row always spans a full 128-byte TMA tile row
+extern "C" int32_t spotv2_gat_n_aug(const spotv2_gat_desc* d) { return d ? n_aug_of(d) : 0; }
+extern "C" int32_t spotv2_gat_head_pitch(const spotv2_gat_desc* d) { return d ? head_pitch_of(d) : 0; }
 extern "C" int32_t spotv2_gat_ldp(int32_t H, int32_t C) {
   const int32_t w = (H * C + 2 * H + 3) / 4 * 4;
   return w < 32 ? 32 : w;

@@ -627,7 +627,7 @@ split_dsd_kernel(const float* __restrict__ dsd, size_t total, int cols, __half* 
     const float w = dsd[idx] * s;
     const __half h = __float2half_rn(w);
     hi[r * ld16 + c] = h;
-    lo[r * ld16 + c] = __float2half_rn(w - __half2float(h));
+    if (lo) lo[r * ld16 + c] = __float2half_rn(w - __half2float(h));
   }
 }
 
@@ -808,5 +808,73 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
     SPOTV2_CUDA_OK(cudaMemcpyAsync(dp_scale_or_null + 3, blk_tmp + 2, sizeof(float), cudaMemcpyDeviceToDevice, st));
     SPOTV2_CUDA_OK(cudaMemcpyAsync(dp_scale_or_null + 5, blk_tmp + 4, sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
+  return SPOTV2_OK;
+}
+
+
+// p_format 1: same operator, P as the fp16 operand pair, dP emitted in the padded head pitch (attn_bwd2.cu, P16 instantiations)
+extern "C" int spotv2_gat_attn_bwd_pair(const spotv2_gat_desc* d, const void* P_hi, const void* P_lo_or_null, const float* p_scale,
+                                        const float* edge_rows, const float* edge_terms_or_null, const int32_t* table,
+                                        const float* v, const float* dout, void* dP_hi, void* dP_lo_or_null, float* dp_scale,
+                                        float* dv_or_null, float* d_edge_terms_or_null, float* dbias_or_null, void* ws,
+                                        size_t ws_bytes, void* stream) {
+  if (int rc = check_desc(d)) return rc;
+  SPOTV2_REQUIRE(d->p_format == 1, "attn_bwd_pair: the descriptor must say p_format 1");
+  const bool single = d->gemm_algo == 3;
+  SPOTV2_REQUIRE(P_hi && p_scale && dout && dP_hi && dp_scale, "attn_bwd_pair: P_hi, p_scale, dout, dP_hi and dp_scale must be non-null");
+  SPOTV2_REQUIRE(single || (P_lo_or_null && dP_lo_or_null), "attn_bwd_pair: the lo planes may be omitted with gemm_algo 3 only");
+  const bool structured = d->edge_mode == 1 && d->Fe > 0;
+  SPOTV2_REQUIRE(d->Fe == 0 || structured || (edge_rows && table && v), "attn_bwd_pair: edge_rows, table and v are required when Fe > 0");
+  SPOTV2_REQUIRE(!structured || (edge_terms_or_null && d_edge_terms_or_null && aligned16(d_edge_terms_or_null)),
+                 "attn_bwd_pair: edge_mode 1 needs edge_terms and a 16-byte aligned d_edge_terms buffer");
+  SPOTV2_REQUIRE(aligned16(P_hi) && aligned16(dout) && aligned16(dP_hi) && (single || (aligned16(P_lo_or_null) && aligned16(dP_lo_or_null))),
+                 "attn_bwd_pair: P / dout / dP must be 16-byte aligned");
+  if (d->H > kMaxHeads) return fail(SPOTV2_ERR_UNSUPPORTED, "H=%d > %d", d->H, kMaxHeads);
+  if (d->Fe > kMaxFe) return fail(SPOTV2_ERR_UNSUPPORTED, "Fe=%d > %d", d->Fe, kMaxFe);
+  AttnBwdArgs a;
+  a.p.B = d->B; a.p.N = d->N; a.p.F = d->F; a.p.Fe = d->Fe; a.p.H = d->H; a.p.C = d->C;
+  a.p.R = d->R; a.p.concat = d->concat; a.p.ldp = d->ldp;
+  a.p.ldo = d->concat ? d->H * d->C : d->C;
+  a.p.slope = d->negative_slope;
+  a.p.drop = dropout_params(d);
+  a.p.lg_tensor_cores = 1;
+  SPOTV2_REQUIRE(!edge_terms_or_null || aligned16(edge_terms_or_null), "attn_bwd_pair: edge_terms must be 16-byte aligned");
+  a.p.edge_terms = d->Fe > 0 ? const_cast<float*>(edge_terms_or_null) : nullptr;
+  a.p.terms_in = structured ? 1 : 0;
+  a.p.dterms_out = structured ? d_edge_terms_or_null : nullptr;
+  a.p.P_aug = nullptr; a.p.edge_rows = edge_rows; a.p.table = table; a.p.v = v;
+  a.p.P_hi = static_cast<const __half*>(P_hi);
+  a.p.P_lo = single ? nullptr : static_cast<const __half*>(P_lo_or_null);
+  a.p.p_blk = p_scale;
+  a.p.hp = head_pitch_of(d);
+  a.p.ldp16 = ld16_of(n_aug_of(d));
+  a.p.bulk_ok = d->Fe > 0 && aligned16(edge_rows) && ((size_t)d->R * d->Fe) % 4 == 0;
+  a.p.vec2_ok = (d->C % 2 == 0);
+  a.dout = dout; a.dP_aug = nullptr; a.dv_part = nullptr; a.dbias_part = nullptr;
+  a.dP_hi16 = static_cast<__half*>(dP_hi);
+  a.dP_lo16 = single ? nullptr : static_cast<__half*>(dP_lo_or_null);
+  a.ldp16 = a.p.ldp16;
+  a.dp_blk = dp_scale; a.p_amax = nullptr;
+  cudaStream_t st = as_stream(stream);
+  if (!attn_bwd2_fits(a.p))
+    return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd_pair: the pipelined kernel's shared-memory plan does not fit this shape");
+  const size_t rows = (size_t)d->B * d->N;
+  if (!ws || ws_bytes < attn_bwd_ws_bytes(d))
+    return fail(SPOTV2_ERR_WORKSPACE, "attn_bwd_pair needs %zu B of workspace, got %zu", attn_bwd_ws_bytes(d), ws_bytes);
+  const size_t part = attn_bwd_partials_bytes(d);
+  unsigned char* w = static_cast<unsigned char*>(ws);
+  float* blk_dout = reinterpret_cast<float*>(w + part + round_up(rows * 2 * d->H * sizeof(float), 256));
+  a.dout_blk = blk_dout;
+  if (int rc = amax_flat(dout, rows * (size_t)a.p.ldo, blk_dout, st)) return rc;
+  a.dsd = reinterpret_cast<float*>(w + part);
+  a.bound = (float)d->N * (d->concat ? 1.f : 1.f / (float)d->H) * a.p.drop.scale;
+  SPOTV2_CUDA_OK(cudaMemsetAsync(dp_scale, 0, kScaleBlockFloats * sizeof(float), st));
+  a.dsd_amax = reinterpret_cast<unsigned*>(dp_scale) + 1;
+  if (int rc = launch_attn_bwd2(a, structured ? nullptr : dv_or_null, dbias_or_null, ws, ws_bytes, st)) return rc;
+  const size_t total = rows * 2 * (size_t)d->H;
+  const int HCp = d->H * a.p.hp;
+  split_dsd_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, (size_t)8 * 148), 256, 0, st>>>(
+      a.dsd, total, 2 * d->H, a.dP_hi16 + HCp, a.dP_lo16 ? a.dP_lo16 + HCp : nullptr, a.ldp16, dp_scale);
+  SPOTV2_CUDA_OK(cudaGetLastError());
   return SPOTV2_OK;
 }

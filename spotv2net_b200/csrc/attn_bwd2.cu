@@ -229,24 +229,29 @@ bool plan_is_fixed_geom(const AttnParams& p, const Bwd2Plan& s) {
 
 // DROP: attention dropout in training mode (the mask is regenerated from the descriptor's Philox key, see attn_common.cuh);
 // a separate instantiation so that the default path carries none of it.
-template <bool FIX, bool DROP>
+// P16: p_format 1 - P arrives as the fp16 operand pair (hi | lo halves of each 4 KB tile slot, 64B swizzle): phase A takes
+// its B fragments with ldmatrix and converts nothing of P; dP leaves in the padded head pitch.  SINGLE (with P16): the
+// half-precision class - hi planes only, one product per MMA step.
+template <bool FIX, bool DROP, bool P16, bool SINGLE>
 __global__ void __launch_bounds__(kB2Threads, 1)
 gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_constant__ CUtensorMap tmP,
-                     const __grid_constant__ CUtensorMap tmG) {
+                     const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmPl) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   AttnParams p = args.p;
   Bwd2Plan pl = pl_;
   if (FIX) {
     using F = FixedGeom;
     p.N = F::N; p.H = F::H; p.C = F::C; p.Fe = F::Fe; p.R = F::R; p.ldp = F::ldp; p.ldo = F::ldo;
-    p.concat = 0; p.bulk_ok = 1; p.vec2_ok = 1;
+    p.concat = 0; p.bulk_ok = 1; p.vec2_ok = 1; p.hp = P16 ? 504 : F::C;
     pl.KS = F::KS; pl.chunk_rows = F::chunk_rows; pl.nchunks = F::nchunks; pl.n_cb = F::n_cb; pl.hpr = F::hpr;
     pl.n_rounds = F::n_rounds; pl.n_mt_chunk = F::n_mt_chunk; pl.ksplit = F::ksplit; pl.n_mtiles = F::n_mtiles;
     pl.dv_rg = F::dv_rg; pl.dv_rpu = F::dv_rpu; pl.dv_units = F::dv_units; pl.cbs_per_grp_d = F::cbs_per_grp_d;
     pl.n_slots = F::n_slots; pl.slot_bytes = F::slot_bytes; pl.tma_ok = 1;
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = p.N, H = p.H, C = p.C, Fe = p.Fe, HC = H * C;
+  const int N = p.N, H = p.H, C = p.C, Fe = p.Fe;
+  const int Cp = P16 ? p.hp : C;          // head pitch of the P / dP columns
+  const int HC = H * Cp;
   constexpr int NS = kNS2;
   const int tile_floats = H * N * NS;
 
@@ -298,7 +303,14 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
 
   if (warp == kW) {
     // =========================================== producer ===========================================
-    if (lane == 0) { prefetch_tmap(&tmP); prefetch_tmap(&tmG); }
+    if (lane == 0) { prefetch_tmap(&tmP); prefetch_tmap(&tmG); if (P16 && !SINGLE) prefetch_tmap(&tmPl); }
+    // p_format 1: a P tile slot holds the hi plane's 32 x 32 fp16 box in its first 2 KB and the lo plane's in the second
+    auto put_p16 = [&](unsigned char* dst, int col0, int row0, uint64_t* full) {
+      if (lane == 0) {
+        tma_load_2d_hint(dst, &tmP, col0, row0, full, kEvictFirst);
+        if (!SINGLE) tma_load_2d_hint(dst + 2048, &tmPl, col0, row0, full, kEvictFirst);
+      }
+    };
     const long long n_rows = (long long)p.B * N;
     // one tile: TMA, or (C % 4 != 0: tile starts are not 16-byte aligned) a cooperative gather into the
     // same swizzled layout
@@ -367,16 +379,21 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
         for (int cb = 0; cb < n_cb; ++cb) {
           unsigned char* gb = acquire();
           const int ntiles = p.concat ? 2 * nh : 1 + nh;
-          if (pl.tma_ok && lane == 0) mbar_expect_tx(&full[slot], (uint32_t)ntiles * kTile);
+          const uint32_t p_tile_bytes = (P16 && SINGLE) ? kTile / 2 : kTile;
+          if (pl.tma_ok && lane == 0)
+            mbar_expect_tx(&full[slot], (uint32_t)(ntiles - nh) * kTile + (uint32_t)nh * p_tile_bytes);
           if (p.concat) {
             for (int hl = 0; hl < nh; ++hl) {
               put_tile(gb + (2 * hl) * kTile, &tmG, args.dout, p.ldo, (h0 + hl) * C + cb * 32, b * N, &full[slot]);
-              put_tile(gb + (2 * hl + 1) * kTile, &tmP, p.P_aug, p.ldp, (h0 + hl) * C + cb * 32, b * N, &full[slot]);
+              if (P16) put_p16(gb + (2 * hl + 1) * kTile, (h0 + hl) * Cp + cb * 32, b * N, &full[slot]);
+              else put_tile(gb + (2 * hl + 1) * kTile, &tmP, p.P_aug, p.ldp, (h0 + hl) * C + cb * 32, b * N, &full[slot]);
             }
           } else {
             put_tile(gb, &tmG, args.dout, p.ldo, cb * 32, b * N, &full[slot]);
-            for (int hl = 0; hl < nh; ++hl)
-              put_tile(gb + (1 + hl) * kTile, &tmP, p.P_aug, p.ldp, (h0 + hl) * C + cb * 32, b * N, &full[slot]);
+            for (int hl = 0; hl < nh; ++hl) {
+              if (P16) put_p16(gb + (1 + hl) * kTile, (h0 + hl) * Cp + cb * 32, b * N, &full[slot]);
+              else put_tile(gb + (1 + hl) * kTile, &tmP, p.P_aug, p.ldp, (h0 + hl) * C + cb * 32, b * N, &full[slot]);
+            }
           }
           publish(pl.tma_ok != 0);
         }
@@ -420,7 +437,8 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
   }
   // fp16-pair operand scales of the two big products: dO and P from their tensors' maxima, alpha <= 1 fixed
   const float s_dO = dp_scale_from_amax(__uint_as_float(*reinterpret_cast<const unsigned*>(args.dout_blk)));
-  const float s_P = dp_scale_from_amax(__uint_as_float(*reinterpret_cast<const unsigned*>(args.p_amax)));
+  const float s_P = P16 ? p.p_blk[4] : dp_scale_from_amax(__uint_as_float(*reinterpret_cast<const unsigned*>(args.p_amax)));
+  const float inv_sd = P16 ? p.p_blk[3] : 1.f;
   constexpr float s_al = 16384.f;
   const float k_dalpha = g_scale / (s_dO * s_P);                 // accumulator -> dalpha
   const float k_dp = g_scale * dp_scale / (s_al * s_dO) * (DROP ? p.drop.scale : 1.f);   // accumulator -> (scaled) dP
@@ -441,6 +459,14 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
   const uint32_t fb_k0 = (uint32_t)((2 * t) * 128 + ((((g >> 2) ^ (2 * t))) << 4) + ((g & 3) << 2));
   const uint32_t fb_k1 = (uint32_t)((2 * t + 1) * 128 + ((((g >> 2) ^ (2 * t + 1))) << 4) + ((g & 3) << 2));
 
+  // p_format 1, phase A: B fragments (k = channel pairs, n = source j) by ldmatrix.x4 from the [j][c] fp16 tile: matrix
+  // = lane >> 3: (j 0-7, chunk 2ks) (j 0-7, chunk 2ks+1) (j 8-15, chunk 2ks) (j 8-15, chunk 2ks+1) = b0,b1 of n-block 2np
+  // and b0,b1 of n-block 2np+1
+  uint32_t lmB[2][2];                 // [k16 step][n pair]
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int np = 0; np < 2; ++np) lmB[ks][np] = sw64(16 * np + (lane & 7) + ((lane >> 4) & 1) * 8, 2 * ks + ((lane >> 3) & 1));
   // phase V units of this warp (feature tile, row group): fixed for the whole kernel
   int dv_mt[kMaxDvUnits], dv_rb[kMaxDvUnits];
   float dv_run[kMaxDvUnits][4];
@@ -494,7 +520,14 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
     // ------------------------------------------------ L: edge logits ------------------------------------------------
     for (int idx = tid; idx < N * 2 * H; idx += kCT) {
       const int j = idx / (2 * H), k = idx - j * 2 * H;
-      sd[idx] = p.P_aug[((size_t)b * N + j) * p.ldp + HC + k];
+      if (P16) {
+        const size_t o = ((size_t)b * N + j) * p.ldp16 + HC + k;
+        float v = __half2float(p.P_hi[o]);
+        if (!SINGLE) v += __half2float(p.P_lo[o]);
+        sd[idx] = v * inv_sd;
+      } else {
+        sd[idx] = p.P_aug[((size_t)b * N + j) * p.ldp + HC + k];
+      }
     }
     for (int idx = tid; idx < 2 * H * 32; idx += kCT) ds_part[idx] = 0.f;
     if (use_terms) {
@@ -615,6 +648,27 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
               cvt_pair(x1.x, x1.y, s_dO, ah[ks][2 * hf + 1], al[ks][2 * hf + 1]);
             }
           }
+          if (P16) {
+            const uint32_t pt = sa + (uint32_t)((p.concat ? 2 * hl + 1 : 1 + hl) * kTile);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+              for (int np = 0; np < 2; ++np) {
+                uint32_t bh[4], bl[4];
+                ldsm_x4(pt + lmB[ks][np], bh[0], bh[1], bh[2], bh[3]);
+                if (!SINGLE) ldsm_x4(pt + 2048 + lmB[ks][np], bl[0], bl[1], bl[2], bl[3]);
+#pragma unroll
+                for (int nn = 0; nn < 2; ++nn) {
+                  const int n = 2 * np + nn;
+                  if (!SINGLE) {
+                    mma_f16_k16(cacc[n], al[ks], bh[2 * nn], bh[2 * nn + 1]);        // small terms first
+                    mma_f16_k16(cacc[n], ah[ks], bl[2 * nn], bl[2 * nn + 1]);
+                  }
+                  mma_f16_k16(cacc[n], ah[ks], bh[2 * nn], bh[2 * nn + 1]);
+                }
+              }
+            }
+          } else
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
@@ -882,8 +936,10 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
                 uint32_t bh[2], bl[2];
                 cvt_pair(x0, x1, s_dO, bh[0], bl[0]);
                 cvt_pair(x2, x3, s_dO, bh[1], bl[1]);
-                mma_f16_16x8x16(cacc[n], al[ks], bh);      // small terms first
-                mma_f16_16x8x16(cacc[n], ah[ks], bl);
+                if (!(P16 && SINGLE)) {
+                  mma_f16_16x8x16(cacc[n], al[ks], bh);    // small terms first
+                  mma_f16_16x8x16(cacc[n], ah[ks], bl);
+                }
                 mma_f16_16x8x16(cacc[n], ah[ks], bh);
               }
             }
@@ -913,10 +969,12 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
                   const uint32_t lb0 = __shfl_sync(0xffffffffu, lo32[2 * pr], src + 1), lb1 = __shfl_sync(0xffffffffu, lo32[2 * pr + 1], src + 1);
                   const bool up = (t >> 1) != 0;           // lanes 2,3 of the quad take the second n-tile of the pair
                   const int c = cb * 32 + 16 * pr + 8 * (t >> 1) + 4 * (t & 1);
-                  if (j < N && c < C) {
-                    const size_t off = ((size_t)b * N + j) * args.ldp16 + (size_t)h * C + c;
-                    *reinterpret_cast<uint2*>(args.dP_hi16 + off) = make_uint2(up ? ha1 : ha0, up ? hb1 : hb0);
-                    *reinterpret_cast<uint2*>(args.dP_lo16 + off) = make_uint2(up ? la1 : la0, up ? lb1 : lb0);
+                  if (j < N && c < Cp) {                   // columns [C, Cp): the padded head pitch's zero columns
+                    const size_t off = ((size_t)b * N + j) * args.ldp16 + (size_t)h * Cp + c;
+                    const bool pad = c >= C;
+                    *reinterpret_cast<uint2*>(args.dP_hi16 + off) = pad ? make_uint2(0u, 0u) : make_uint2(up ? ha1 : ha0, up ? hb1 : hb0);
+                    if (!(P16 && SINGLE))
+                      *reinterpret_cast<uint2*>(args.dP_lo16 + off) = pad ? make_uint2(0u, 0u) : make_uint2(up ? la1 : la0, up ? lb1 : lb0);
                   }
                 }
               }
@@ -927,16 +985,19 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
                 for (int hf = 0; hf < 2; ++hf) {
                   const int j = hf ? j1 : j0;
                   const int c = cb * 32 + 8 * n + 2 * t;
-                  if (j < N && c < C) {
-                    // k_dp carries dp_scale (1 in fp32 mode)
-                    const float v0 = cacc[n][2 * hf] * k_dp, v1 = cacc[n][2 * hf + 1] * k_dp;
-                    const bool has1 = c + 1 < C;
+                  if (j < N && c < Cp) {
+                    // k_dp carries dp_scale (1 in fp32 mode); columns [C, Cp) are the padded head pitch's zero columns
+                    const float v0 = c < C ? cacc[n][2 * hf] * k_dp : 0.f, v1 = c + 1 < C ? cacc[n][2 * hf + 1] * k_dp : 0.f;
+                    const bool has1 = c + 1 < Cp;
                     if (args.dP_hi16) {
-                      const size_t off = ((size_t)b * N + j) * args.ldp16 + (size_t)h * C + c;
+                      const size_t off = ((size_t)b * N + j) * args.ldp16 + (size_t)h * Cp + c;
                       const float w0 = v0, w1 = v1;
                       const __half h0_ = __float2half_rn(w0), h1_ = __float2half_rn(w1);
                       const __half l0_ = __float2half_rn(w0 - __half2float(h0_)), l1_ = __float2half_rn(w1 - __half2float(h1_));
-                      if (p.vec2_ok) {
+                      if (P16) {           // h * Cp + c is even and c + 1 < Cp: aligned pairs
+                        *reinterpret_cast<__half2*>(args.dP_hi16 + off) = __halves2half2(h0_, h1_);
+                        if (!SINGLE) *reinterpret_cast<__half2*>(args.dP_lo16 + off) = __halves2half2(l0_, l1_);
+                      } else if (p.vec2_ok) {
                         *reinterpret_cast<__half2*>(args.dP_hi16 + off) = __halves2half2(h0_, h1_);
                         *reinterpret_cast<__half2*>(args.dP_lo16 + off) = __halves2half2(l0_, l1_);
                       } else {
@@ -1015,10 +1076,23 @@ int launch_attn_bwd2(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t w
   if (!ws || ws_bytes < need) return fail(SPOTV2_ERR_WORKSPACE, "attn_bwd needs %zu B of workspace, got %zu", need, ws_bytes);
   a.dv_part = static_cast<float*>(ws);
   a.dbias_part = a.dv_part + (size_t)grid * rg * p.H * p.Fe;
-  CUtensorMap tmP, tmG;
+  CUtensorMap tmP, tmG, tmPl;
   memset(&tmP, 0, sizeof(tmP));
   memset(&tmG, 0, sizeof(tmG));
-  if (pl.tma_ok) {
+  memset(&tmPl, 0, sizeof(tmPl));
+  const bool p16 = p.P_hi != nullptr, single = p16 && p.P_lo == nullptr;
+  if (p16) {
+    if (!pl.tma_ok) return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd (p_format 1): C %% 4 == 0 required (dout tiles by TMA)");
+    const uint64_t rows = (uint64_t)p.B * p.N, cols = (uint64_t)p.H * p.hp + 2 * p.H;
+    if (int rc = make_tmap_f16(&tmP, p.P_hi, rows, cols, (uint64_t)p.ldp16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE))
+      return rc;
+    if (int rc = make_tmap_f16(&tmPl, single ? p.P_hi : p.P_lo, rows, cols, (uint64_t)p.ldp16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B,
+                               CU_TENSOR_MAP_L2_PROMOTION_NONE))
+      return rc;
+    if (int rc = make_tmap(&tmG, a.dout, (uint64_t)p.B * p.N, (uint64_t)p.ldo, (uint64_t)p.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_NONE))
+      return rc;
+  } else if (pl.tma_ok) {
     // no L2 promotion: the 128-byte tile rows start anywhere in a 12 KB / 2 KB row, and fetching the enclosing 256-byte
     // blocks cost 0.4 GB of extra DRAM reads per launch (ncu: 5.02 -> 4.61 GB) for no gain in time
     if (int rc = make_tmap(&tmP, p.P_aug, (uint64_t)p.B * p.N, (uint64_t)p.ldp, (uint64_t)p.ldp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1028,11 +1102,16 @@ int launch_attn_bwd2(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t w
                            CU_TENSOR_MAP_L2_PROMOTION_NONE))
       return rc;
   }
-  const bool fixg = plan_is_fixed_geom(p, pl), drop = p.drop.p > 0.f;
-  auto kern = drop ? (fixg ? gat_attn_bwd2_kernel<true, true> : gat_attn_bwd2_kernel<false, true>)
-                   : (fixg ? gat_attn_bwd2_kernel<true, false> : gat_attn_bwd2_kernel<false, false>);
+  const bool fixg = plan_is_fixed_geom(p, pl) && (!p16 || p.hp == 504), drop = p.drop.p > 0.f;
+  auto kern = drop ? (fixg ? gat_attn_bwd2_kernel<true, true, false, false> : gat_attn_bwd2_kernel<false, true, false, false>)
+                   : (fixg ? gat_attn_bwd2_kernel<true, false, false, false> : gat_attn_bwd2_kernel<false, false, false, false>);
+  if (p16 && !single)
+    kern = drop ? (fixg ? gat_attn_bwd2_kernel<true, true, true, false> : gat_attn_bwd2_kernel<false, true, true, false>)
+                : (fixg ? gat_attn_bwd2_kernel<true, false, true, false> : gat_attn_bwd2_kernel<false, false, true, false>);
+  else if (p16)
+    kern = drop ? gat_attn_bwd2_kernel<false, true, true, true> : gat_attn_bwd2_kernel<false, false, true, true>;
   SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
-  kern<<<grid, kB2Threads, pl.total, st>>>(a, pl, tmP, tmG);
+  kern<<<grid, kB2Threads, pl.total, st>>>(a, pl, tmP, tmG, tmPl);
   SPOTV2_CUDA_OK(cudaGetLastError());
   return reduce_partials2(a.dv_part, grid * rg, (dv && p.Fe > 0) ? p.H * p.Fe : 0, dv, a.dbias_part, grid, dbias ? p.ldo : 0, dbias, st);
 }

@@ -2,6 +2,8 @@
 // shared-memory carve-up, the edge-row ring (1-D bulk async copies), the 3xTF32
 // mma.sync edge-logit phase and the per-(head, target) softmax.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace spotv2 {
@@ -89,6 +91,13 @@ struct AttnParams {
   float* edge_terms;
   int terms_in;          // edge_mode 1: edge_terms is an INPUT (spotv2_edge_terms_from_windows); there are no edge rows
   float* dterms_out;     // backward, edge_mode 1: receives dz' (gradient w.r.t. the edge terms) in the same tile layout
+  // p_format 1: the projection arrives as an fp16 operand pair (planes [B*N, ldp16], head pitch hp, scale block p_blk:
+  // [2],[3] inverse scales of the projection / s|d column groups, [4],[5] the scales); P_aug is null then.  P_lo null =
+  // half-precision class (hi plane only).
+  const __half* P_hi = nullptr;
+  const __half* P_lo = nullptr;
+  const float* p_blk = nullptr;
+  int ldp16 = 0, hp = 0;
   int lg_tensor_cores;   // large-universe path: batched GEMMs on mma.sync (3xTF32) unless gemm_algo == 1 (exact-fp32 FFMA2)
 };
 

@@ -37,13 +37,6 @@ constexpr int kCbPerPass = 8;         // channel blocks per pass: one per MMA wa
 // wait-cycle diagnostics of this kernel (see spotv2_diag_counters)
 __device__ unsigned long long g_diag_counters[kNumCounters];
 
-struct AttnFwdArgs {
-  AttnParams p;
-  const float* bias;
-  float* out;
-  float* alpha_out;
-};
-
 __device__ __forceinline__ void bar_sync_group_a() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync_group_b() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
@@ -351,6 +344,10 @@ gat_attn_fwd_kernel(const AttnFwdArgs args, const AttnSmem sm_, const uint32_t o
             }
           const uint32_t q = q_base + wb;
           const int slot = q % kPSlots;
+          // a slot's consecutive uses may belong to different warps when the tiles per step change between passes: a warp
+          // running ahead must not take the slot's previous fill for its own (parity cannot tell fill r from r - 2), so it
+          // first waits until the previous use has been released
+          mbar_wait_timed(&ptile_empty[slot], ((q / kPSlots) & 1) ^ 1, w_pf);
           mbar_wait_timed(&ptile_full[slot], (q / kPSlots) & 1, w_pf);
           // k-major fragment (rows 8ks+t | +4 = sources, cols 8n+g = channels) of the 128B-swizzled tile:
           // (base ^ (n << 5)) + ks*1024, two per-lane bases for the +0 / +4 rows

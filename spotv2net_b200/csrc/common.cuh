@@ -30,6 +30,9 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
 int check_desc(const spotv2_gat_desc* d);
+// p_format 1 pads every head's channel block to a multiple of 8 columns (16-byte aligned TMA tile starts for fp16 planes)
+inline int head_pitch_of(const spotv2_gat_desc* d) { return d->p_format == 1 ? (d->C + 7) / 8 * 8 : d->C; }
+inline int n_aug_of(const spotv2_gat_desc* d) { return d->H * head_pitch_of(d) + 2 * d->H; }
 int sm_count();
 size_t attn_bwd_ws_bytes(const spotv2_gat_desc* d);      // attn_bwd.cu
 

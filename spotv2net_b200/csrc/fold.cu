@@ -55,10 +55,11 @@ unfold_kernel(const float* __restrict__ W, const float* __restrict__ a_src,
               const float* __restrict__ a_edge, const float* __restrict__ dW_aug,
               const float* __restrict__ dv, float* __restrict__ dW, float* __restrict__ da_src,
               float* __restrict__ da_dst, float* __restrict__ dWe, float* __restrict__ da_edge,
-              int H, int C, int F, int Fe) {
+              int H, int C, int Cp, int F, int Fe) {
   __shared__ float red[4];
   const int hc = blockIdx.x, h = hc / C;
-  const int HC = H * C;
+  const int HC = H * Cp;                               // dW_aug rows: head pitch Cp (>= C; pad rows ignored)
+  const size_t row = (size_t)h * Cp + (hc - h * C);
   const float as = a_src[hc], ad = a_dst[hc];
   const float* dUs = dW_aug + (size_t)(HC + h) * F;
   const float* dUd = dW_aug + (size_t)(HC + H + h) * F;
@@ -66,7 +67,7 @@ unfold_kernel(const float* __restrict__ W, const float* __restrict__ a_src,
   for (int f = threadIdx.x; f < F; f += 128) {
     const float w = W[(size_t)hc * F + f];
     const float us = dUs[f], ud = dUd[f];
-    dW[(size_t)hc * F + f] = dW_aug[(size_t)hc * F + f] + as * us + ad * ud;
+    dW[(size_t)hc * F + f] = dW_aug[row * F + f] + as * us + ad * ud;
     ps = fmaf(w, us, ps);
     pd = fmaf(w, ud, pd);
   }
@@ -83,6 +84,19 @@ unfold_kernel(const float* __restrict__ W, const float* __restrict__ a_src,
     }
     pe = block_sum_128(pe, red);
     if (threadIdx.x == 0) da_edge[hc] = pe;
+  }
+}
+
+// W_aug rows [0, H*Cp): head h's C rows of W, then Cp - C zero rows (p_format 1: padded head pitch)
+__global__ void __launch_bounds__(256)
+fold_copy_padded_kernel(const float* __restrict__ W, float* __restrict__ W_aug, int C, int Cp, int F) {
+  const int r = blockIdx.x, h = r / Cp, c = r - h * Cp;
+  float* dst = W_aug + (size_t)r * F;
+  if (c < C) {
+    const float* src = W + ((size_t)h * C + c) * F;
+    for (int f = threadIdx.x; f < F; f += 256) dst[f] = src[f];
+  } else {
+    for (int f = threadIdx.x; f < F; f += 256) dst[f] = 0.f;
   }
 }
 
@@ -269,8 +283,12 @@ extern "C" int spotv2_gat_fold(const spotv2_gat_desc* d, const float* W, const f
   SPOTV2_REQUIRE(W && a_src && a_dst && W_aug, "fold: W, a_src, a_dst, W_aug must be non-null");
   SPOTV2_REQUIRE(d->Fe == 0 || (W_e && a_edge && v), "fold: W_e, a_edge, v required when Fe > 0");
   cudaStream_t st = as_stream(stream);
-  const int HC = d->H * d->C;
-  SPOTV2_CUDA_OK(cudaMemcpyAsync(W_aug, W, (size_t)HC * d->F * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const int Cp = head_pitch_of(d);
+  const int HC = d->H * Cp;
+  if (Cp == d->C)
+    SPOTV2_CUDA_OK(cudaMemcpyAsync(W_aug, W, (size_t)HC * d->F * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  else
+    fold_copy_padded_kernel<<<HC, 256, 0, st>>>(W, W_aug, d->C, Cp, d->F);
   dim3 g1((d->F + 31) / 32, d->H);
   fold_kernel<8><<<g1, dim3(32, 8), 0, st>>>(W, a_src, a_dst, W_aug + (size_t)HC * d->F,
                                              W_aug + (size_t)(HC + d->H) * d->F, d->C, d->F);
@@ -292,7 +310,7 @@ extern "C" int spotv2_gat_unfold(const spotv2_gat_desc* d, const float* W, const
                  "unfold: edge pointers required when Fe > 0");
   unfold_kernel<<<d->H * d->C, 128, 0, as_stream(stream)>>>(W, a_src, a_dst, W_e, a_edge, dW_aug, dv,
                                                             dW, da_src, da_dst, dW_e, da_edge, d->H,
-                                                            d->C, d->F, d->Fe);
+                                                            d->C, head_pitch_of(d), d->F, d->Fe);
   SPOTV2_CUDA_OK(cudaGetLastError());
   return SPOTV2_OK;
 }

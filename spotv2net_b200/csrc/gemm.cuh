@@ -67,6 +67,14 @@ struct F16Operand {
   const float* inv;
   int split_at;
 };
+// Output of gemm3x_f16 as an fp16 operand pair instead of fp32 (p_format 1): C * scale[col >= B.split_at] is split into
+// hi (and lo, unless null) planes [M, ld] by the epilogue and leaves through TMA stores; scale -> 2 floats on the device.
+struct PairOut {
+  void* hi;
+  void* lo;             // null: hi plane only (half-precision class)
+  int ld;               // elements, % 8 == 0
+  const float* scale;
+};
 constexpr int kScaleBlockFloats = 8;   // [0,1] amax bits, [2,3] inverse scales, [4,5] scales
 inline int ld16_of(int cols) { return (cols + 15) / 16 * 16; }   // rows of fp16 operands start on 32-byte sectors
 // blk[0] <- bit pattern of max |src| (blk is zeroed first)
@@ -78,7 +86,11 @@ int split_f16(const float* src, int rows, int cols, size_t ld, int split_dim, in
 int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, const F16Operand& B, float* C, int ldc,
                int splits, int bn, int kb_per_chunk, void* ws, size_t ws_bytes, cudaStream_t st,
                float* amax_out = nullptr, int amax_cols = 0,    // amax_out[0] <- bits of max |C[:, :amax_cols]|
-               bool single = false);   // true: one fp16 product (A_hi * B_hi) - the half-precision class of gemm_algo 3
+               bool single = false,    // true: one fp16 product (A_hi * B_hi) - the half-precision class of gemm_algo 3
+               const PairOut* pair = nullptr);   // non-null: C is ignored, the result leaves as an fp16 pair (splits == 1)
+// Scale block of a pair output C = x . W^T from the bound |C| <= max|x| * max_row ||W||_1 (x_blk[0] = bits of max|x|);
+// two groups: rows of W below / at-or-above split_at.
+int pair_out_scale(const float* W, int rows, int cols, int split_at, const float* x_blk, float* blk, cudaStream_t st);
 // blk[0] <- bits of max |src[r, c]| over a [rows, cols] matrix with row pitch ld (blk is zeroed first)
 int amax_2d(const float* src, int rows, int cols, size_t ld, float* blk, cudaStream_t st);
 

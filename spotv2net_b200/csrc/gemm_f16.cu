@@ -51,6 +51,8 @@ struct HParams {
   unsigned* amax_out;   // optional: bit pattern of max |C[m, n]| over n < amax_cols (splits == 1 only)
   int amax_cols;
   int single;           // 1: half-precision class (gemm_algo 3): only the A_hi * B_hi product, lo tiles not even loaded
+  int pair_out;         // 0: fp32 C; 1: C leaves as an fp16 hi | lo pair (planes of tmC); 2: hi plane only
+  const float* out_scale;   // pair_out: 2 power-of-two scales of the output's column groups (col < / >= b_split)
   int tma_store;        // 1: C tiles / split-K partials leave through TMA bulk stores (16-byte aligned rows); 0: st.global
   int dbg;              // bring-up probe, compiled in only with -DSPOTV2_BRINGUP (env SPOTV2_GEMM_DBG): bit 0 skip the
                         // global stores, bit 1 skip scale + amax, bit 2 skip the per-chunk register accumulation
@@ -247,7 +249,8 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
       if (row < p.M && col0 < p.N && !(SPOTV2_DBG(p) & 2)) {
         if (p.scale_in_kernel) {      // powers of two: exact
           const float ra = p.a_inv ? p.a_inv[row >= p.a_split ? 1 : 0] : 1.f;
-          const float cb0 = ra * (p.b_inv ? p.b_inv[0] : 1.f), cb1 = ra * (p.b_inv ? p.b_inv[1] : 1.f);
+          const float os0 = p.pair_out ? p.out_scale[0] : 1.f, os1 = p.pair_out ? p.out_scale[1] : 1.f;
+          const float cb0 = ra * (p.b_inv ? p.b_inv[0] : 1.f) * os0, cb1 = ra * (p.b_inv ? p.b_inv[1] : 1.f) * os1;
 #pragma unroll
           for (int e = 0; e < HALF; ++e) acc[e] *= (col0 + e >= p.b_split) ? cb1 : cb0;
         }
@@ -259,7 +262,47 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           row_amax = mx;
         }
       }
-      if (p.tma_store && !(SPOTV2_DBG(p) & 1)) {
+      if (p.pair_out) {
+        // The tile leaves as the fp16 operand pair of the scaled result: 32 x 32 pieces, hi plane then lo plane, each a
+        // 2 KB box (64-byte rows, 64B swizzle) handed to the TMA engine; the two boxes of this warp alternate, and a box is
+        // refilled once the engine has read the store issued from it two stores ago.
+        unsigned char* box = smem + S::kEpiOff + (warp - 4) * 4096;
+        const int row_base = mt * HBM_ + q * 32;
+#pragma unroll
+        for (int cc = 0; cc < HALF / 32; ++cc) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float y0 = acc[cc * 32 + 2 * e], y1 = acc[cc * 32 + 2 * e + 1];
+            const __half2 h = __floats2half2_rn(y0, y1);
+            const float2 b = __half22float2(h);
+            const __half2 l = __floats2half2_rn(y0 - b.x, y1 - b.y);
+            hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+#pragma unroll
+          for (int pln = 0; pln < 2; ++pln) {
+            if (pln == 1 && p.pair_out != 1) break;
+            unsigned char* hb = box + (p.pair_out == 1 ? pln : (cc & 1)) * 2048;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<uint4*>(hb + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+                  pln ? make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3])
+                      : make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (col0 + cc * 32 < p.N && row_base < p.M)
+                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmC),
+                             "r"(smem_u32(hb)), "r"(col0 + cc * 32), "r"(row_base), "r"(pln)
+                             : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+        }
+      } else if (p.tma_store && !(SPOTV2_DBG(p) & 1)) {
         // Asynchronous stores (measured: with st.global the epilogue warps sat in the LSU queue for ~0.5 ms of the K = 1260
         // product while the MMA warp waited for them to drain TMEM).  Each warp parks 32 x 16 pieces of its block in two
         // alternating swizzled shared-memory boxes and one lane hands each to the TMA engine; the warp only waits for the
@@ -505,6 +548,40 @@ __global__ void amax_flat_kernel(const float* __restrict__ src, size_t n, unsign
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
 }
 
+// ---- scale of a pair OUTPUT, known before the product runs ---------------------------------------------
+// |sum_k x[i,k] W[j,k]| <= max|x| * ||W[j,:]||_1.  One warp per row of W; bits[g] <- max over the rows of group g
+// (rows < / >= split_at) of the row's L1 norm (atomicMax on the bit pattern: all values are >= 0).
+__global__ void __launch_bounds__(256)
+row_l1_max_kernel(const float* __restrict__ W, int rows, int cols, int split_at, unsigned* __restrict__ bits) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* w = W + (size_t)r * cols;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += fabsf(w[c]);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0 && s > 0.f) atomicMax(bits + (r >= split_at ? 1 : 0), __float_as_uint(s));
+}
+// blk: [0,1] hold the row-L1 maxima (bits) on entry; on exit [0,1] = bits of the bounds max|x| * L1 * (1 + 2^-10),
+// [2,3] inverse scales, [4,5] scales (power of two: bound * scale in [2^14, 2^15))
+__global__ void pair_out_scale_kernel(float* blk, const float* __restrict__ x_blk) {
+  if (threadIdx.x >= 2) return;
+  const float xmax = __uint_as_float(reinterpret_cast<const unsigned*>(x_blk)[0]);
+  const float l1 = __uint_as_float(reinterpret_cast<const unsigned*>(blk)[threadIdx.x]);
+  const float bound = xmax * l1 * 1.0009765625f;
+  const float s = scale_from_amax(bound);
+  blk[threadIdx.x] = bound;
+  blk[2 + threadIdx.x] = 1.f / s;
+  blk[4 + threadIdx.x] = s;
+}
+
+int pair_out_scale(const float* W, int rows, int cols, int split_at, const float* x_blk, float* blk, cudaStream_t st) {
+  SPOTV2_CUDA_OK(cudaMemsetAsync(blk, 0, kScaleBlockFloats * sizeof(float), st));
+  row_l1_max_kernel<<<(rows + 7) / 8, 256, 0, st>>>(W, rows, cols, split_at, reinterpret_cast<unsigned*>(blk));
+  pair_out_scale_kernel<<<1, 32, 0, st>>>(blk, x_blk);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
+}
+
 int amax_flat(const float* src, size_t n, float* blk, cudaStream_t st) {
   SPOTV2_CUDA_OK(cudaMemsetAsync(blk, 0, 8 * sizeof(float), st));
   const bool al = aligned16(src);
@@ -576,7 +653,7 @@ int split_f16(const float* src, int rows, int cols, size_t ld, int split_dim, in
 // C[M,N] = A . B^T with operands pre-split into scaled fp16 pairs.  bn: 256 -> TBK 64, 256 + 16 -> TBK 32.
 int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, const F16Operand& B, float* C, int ldc,
                int splits, int bn, int kb_per_chunk, void* ws, size_t ws_bytes, cudaStream_t st, float* amax_out,
-               int amax_cols, bool single) {
+               int amax_cols, bool single, const PairOut* pair) {
   const int TBK = (bn & 16) ? 32 : 64;
   bn &= ~16;
   if (!tma_available()) return fail(SPOTV2_ERR_NO_DEVICE, "tensor-core GEMM: TMA descriptor encoding is not available");
@@ -598,6 +675,13 @@ int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, c
   p.amax_out = reinterpret_cast<unsigned*>(amax_out);
   p.amax_cols = amax_cols;
   p.single = single ? 1 : 0;
+  p.pair_out = 0; p.out_scale = nullptr;
+  if (pair) {
+    if (splits > 1 || !pair->hi || !pair->scale || pair->ld % 8 != 0 || !aligned16(pair->hi) || (pair->lo && !aligned16(pair->lo)))
+      return fail(SPOTV2_ERR_INVALID_ARG, "gemm3x_f16: pair output needs splits == 1, 16-byte aligned planes, ld %% 8 == 0 and a scale");
+    p.pair_out = pair->lo ? 1 : 2;
+    p.out_scale = pair->scale;
+  }
   p.dbg = 0;
 #ifdef SPOTV2_BRINGUP
   {
@@ -626,7 +710,15 @@ int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, c
   int rc;
   memset(&tC, 0, sizeof(tC));
   p.tma_store = 0;
-  if (aligned16(p.C) && p.ldc % 4 == 0 && (p.splits == 1 || p.split_stride % 4 == 0)) {
+  if (pair) {
+    // planes [hi, lo] of [M, ld] fp16; 32 x 32 boxes with 64-byte rows
+    const uint64_t plane_stride = pair->lo ? (uint64_t)((const __half*)pair->lo - (const __half*)pair->hi) : (uint64_t)M * pair->ld;
+    if (pair->lo && ((const __half*)pair->lo <= (const __half*)pair->hi || plane_stride % 8 != 0))
+      return fail(SPOTV2_ERR_INVALID_ARG, "gemm3x_f16: the lo plane must follow the hi plane at a multiple of 16 bytes");
+    if ((rc = make_tmap3_f16(&tC, pair->hi, pair->lo ? 2 : 1, plane_stride, (uint64_t)M, (uint64_t)N, (uint64_t)pair->ld, 32, 32,
+                             CU_TENSOR_MAP_SWIZZLE_64B)))
+      return rc;
+  } else if (aligned16(p.C) && p.ldc % 4 == 0 && (p.splits == 1 || p.split_stride % 4 == 0)) {
     // C tiles (or split-K partials: plane = split) through TMA bulk stores: 32-row x 16-column fp32 boxes, 64B swizzle
     if ((rc = make_tmap3(&tC, p.C, (uint64_t)p.splits, p.splits > 1 ? p.split_stride : (uint64_t)M * p.ldc, (uint64_t)M, (uint64_t)N,
                          (uint64_t)p.ldc, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B)))

@@ -19,9 +19,9 @@ struct ProjShape {
   int rows, n_aug, HC, F, ldp, ldf16, ldp16;
 };
 
-ProjShape shape_of(const spotv2_gat_desc* d) {
-  const int n_aug = d->H * d->C + 2 * d->H;
-  return {d->B * d->N, n_aug, d->H * d->C, d->F, d->ldp, ld16_of(d->F), ld16_of(n_aug)};
+ProjShape shape_of(const spotv2_gat_desc* d) {       // HC: first row / column of the s|d group (head pitch padded in p_format 1)
+  const int n_aug = n_aug_of(d);
+  return {d->B * d->N, n_aug, d->H * head_pitch_of(d), d->F, d->ldp, ld16_of(d->F), ld16_of(n_aug)};
 }
 
 bool use_tc(const spotv2_gat_desc* d) { return d->gemm_algo != 1; }
@@ -126,11 +126,36 @@ extern "C" int spotv2_proj_fwd(const spotv2_gat_desc* d, const float* x, const v
                     single_product(d));
 }
 
+extern "C" int spotv2_proj_fwd_pair(const spotv2_gat_desc* d, const void* x_hi, const void* x_lo, const float* x_scale,
+                                    const float* W_aug, void* P_hi, void* P_lo_or_null, float* p_scale, void* ws,
+                                    size_t ws_bytes, void* stream) {
+  if (int rc = check_desc(d)) return rc;
+  SPOTV2_REQUIRE(d->p_format == 1, "proj_fwd_pair: the descriptor must say p_format 1");
+  SPOTV2_REQUIRE(x_hi && x_lo && x_scale && W_aug && P_hi && p_scale, "proj_fwd_pair: null pointer");
+  SPOTV2_REQUIRE(P_lo_or_null || single_product(d), "proj_fwd_pair: the lo plane may be omitted with gemm_algo 3 only");
+  const ProjShape s = shape_of(d);
+  cudaStream_t st = as_stream(stream);
+  Carver c{static_cast<unsigned char*>(ws), ws ? ws_bytes : 0};
+  float* wblk = static_cast<float*>(c.take(2 * kScaleBlockFloats * sizeof(float)));
+  void* wh = c.take((size_t)s.n_aug * s.ldf16 * 2);
+  void* wl = c.take((size_t)s.n_aug * s.ldf16 * 2);
+  if (!wblk || !wh || !wl) return fail(SPOTV2_ERR_WORKSPACE, "proj_fwd_pair: workspace too small (%zu B)", ws_bytes);
+  if (int rc = split_f16(W_aug, s.n_aug, s.F, s.F, 0, s.HC, nullptr, 0, wh, wl, s.ldf16, wblk, st)) return rc;
+  if (int rc = pair_out_scale(W_aug, s.n_aug, s.F, s.HC, x_scale, p_scale, st)) return rc;
+  F16Operand A{x_hi, x_lo, s.ldf16, x_scale + 2, kNone}, B{wh, wl, s.ldf16, wblk + 2, s.HC};
+  PairOut out{P_hi, single_product(d) ? nullptr : P_lo_or_null, s.ldp16, p_scale + 4};
+  return gemm3x_f16(true, true, s.rows, s.n_aug, s.F, A, B, nullptr, 0, 1, 256, 0, nullptr, 0, st, nullptr, 0, single_product(d),
+                    &out);
+}
+
 extern "C" int spotv2_proj_bwd_weight(const spotv2_gat_desc* d, const float* x, const void* x_hi, const void* x_lo,
                                       const float* x_scale, const float* dP_aug, const void* dP_hi, const void* dP_lo,
                                       const float* dp_scale, float* dW_aug, void* ws, size_t ws_bytes, void* stream) {
   if (int rc = check_desc(d)) return rc;
-  SPOTV2_REQUIRE(x && dW_aug && (dP_aug || dP_hi), "proj_bwd_weight: null pointer");
+  SPOTV2_REQUIRE((x || x_hi) && dW_aug && (dP_aug || dP_hi), "proj_bwd_weight: null pointer");
+  if (d->p_format == 1 && single_product(d) && dP_hi && !dP_lo) dP_lo = dP_hi;      // hi planes only: lo is never loaded
+  SPOTV2_REQUIRE(d->p_format == 0 || (dP_hi && dP_lo && dp_scale && x_hi && x_lo && x_scale),
+                 "proj_bwd_weight: p_format 1 takes x and dP as pairs");
   const ProjShape s = shape_of(d);
   cudaStream_t st = as_stream(stream);
   const int splits = weight_grad_splits(s.rows, s.n_aug, s.F);
@@ -167,6 +192,8 @@ extern "C" int spotv2_proj_bwd_input(const spotv2_gat_desc* d, const float* dP_a
                                      void* stream) {
   if (int rc = check_desc(d)) return rc;
   SPOTV2_REQUIRE(W_aug && dX && (dP_aug || dP_hi), "proj_bwd_input: null pointer");
+  if (d->p_format == 1 && single_product(d) && dP_hi && !dP_lo) dP_lo = dP_hi;      // hi planes only: lo is never loaded
+  SPOTV2_REQUIRE(d->p_format == 0 || (dP_hi && dP_lo && dp_scale), "proj_bwd_input: p_format 1 takes dP as a pair");
   const ProjShape s = shape_of(d);
   cudaStream_t st = as_stream(stream);
   if (!use_tc(d)) {

@@ -135,17 +135,31 @@ def topology_from_edge_index(edge_index: Tensor, n_nodes: int, nodes_per_graph: 
 # Kernel selection knobs of spotv2_gat_desc (0 = the library's choice); tests set them to run every back end.
 GEMM_ALGO = 0
 ATTN_BWD_ALGO = 0
+# How the projection travels between the GEMM and the attention kernels (spotv2_gat_desc.p_format): None = the library's
+# choice (the fp16 operand pair whenever the shapes allow it), 0 = always fp32 P_aug, 1 = the pair or an error.
+P_FORMAT = None
 
 
 PRECISIONS = {"fp32": None, "half": 3}      # "half": single fp16 tensor-core product in the projections (config C)
 
 
+def pair_format_applies(N: int, Fe: int, Cc: int, gemm_algo: int, attn_bwd_algo: int) -> bool:
+    """Shapes the p_format 1 kernels cover: one CTA per graph, tensor-core GEMM, dout tiles by TMA, the pipelined backward."""
+    return N <= 32 and gemm_algo != 1 and Cc % 4 == 0 and Fe <= 384 and attn_bwd_algo in (0, 2)
+
+
 def _desc(topo: Topology, F_in: int, Fe: int, H: int, Cc: int, concat: bool, slope: float,
-          dropout_p: float = 0.0, seed: int = 0, gemm_algo: Optional[int] = None, edge_mode: int = 0) -> GatDesc:
+          dropout_p: float = 0.0, seed: int = 0, gemm_algo: Optional[int] = None, edge_mode: int = 0,
+          p_format: Optional[int] = None) -> GatDesc:
     lib = _lib.load()
+    algo = GEMM_ALGO if gemm_algo is None else gemm_algo
+    if p_format is None:
+        p_format = P_FORMAT
+    if p_format is None:
+        p_format = 1 if pair_format_applies(topo.N, Fe, Cc, algo, ATTN_BWD_ALGO) else 0
     return GatDesc(topo.B, topo.N, F_in, Fe, H, Cc, topo.R, int(concat), float(slope),
-                   lib.spotv2_gat_ldp(H, Cc), GEMM_ALGO if gemm_algo is None else gemm_algo, ATTN_BWD_ALGO,
-                   float(dropout_p), int(edge_mode), seed & 0xffffffff, (seed >> 32) & 0xffffffff)
+                   lib.spotv2_gat_ldp(H, Cc), algo, ATTN_BWD_ALGO,
+                   float(dropout_p), int(edge_mode), seed & 0xffffffff, (seed >> 32) & 0xffffffff, int(p_format))
 
 
 def _workspace(desc: GatDesc):
@@ -187,8 +201,12 @@ class _GatLayerFn(torch.autograd.Function):
         if windows is not None:                     # structured edge source: the edge rows are never touched
             Fe, edge_attr = 3 * windows.L, None
         # the descriptor (incl. this step's dropout key) is kept for the backward, which regenerates the same mask
-        desc = _desc(topo, x.shape[1], Fe, H, Cc, concat, slope, dropout_p, seed, gemm_algo, 1 if windows is not None else 0)
+        # (standardize=True shifts the d columns of an fp32 P_aug: that path keeps p_format 0)
+        desc = _desc(topo, x.shape[1], Fe, H, Cc, concat, slope, dropout_p, seed, gemm_algo, 1 if windows is not None else 0,
+                     0 if (edge_mean is not None and Fe) else None)
+        pair = desc.p_format == 1
         n, HC = x.shape[0], H * Cc
+        n_aug = lib.spotv2_gat_n_aug(C.byref(desc))
         x = x.contiguous()
         ea = edge_attr.contiguous() if (Fe and windows is None) else None
         # every tensor whose address is handed to the library is held in a local until the call returns
@@ -196,7 +214,7 @@ class _GatLayerFn(torch.autograd.Function):
         W_e = W_e.contiguous() if W_e is not None else None
         a_edge = a_edge.contiguous() if a_edge is not None else None
         bias_c = bias.contiguous() if bias is not None else None
-        W_aug = torch.empty(HC + 2 * H, x.shape[1], device=dev, dtype=torch.float32)
+        W_aug = torch.empty(n_aug, x.shape[1], device=dev, dtype=torch.float32)
         v = torch.empty(H, Fe, device=dev, dtype=torch.float32) if Fe else None
         check(lib.spotv2_gat_fold(C.byref(desc), ptr(W), ptr(a_src), ptr(a_dst), ptr(W_e) if Fe else None,
                                   ptr(a_edge) if Fe else None, ptr(W_aug), ptr(v), st), "spotv2_gat_fold")
@@ -207,8 +225,11 @@ class _GatLayerFn(torch.autograd.Function):
             v.mul_(edge_scale.view(1, Fe))
         ws_f, _, _ = _workspace(desc)
         ws = torch.empty(ws_f, device=dev, dtype=torch.uint8)
-        P_aug = torch.empty(n, desc.ldp, device=dev, dtype=torch.float32)
         p_amax = torch.empty(8, device=dev, dtype=torch.float32)      # max|P|, sizes the backward's fp16 operand scale
+        if pair:     # P as the GEMM-written fp16 operand pair (hi | lo planes; hi only in the half-precision class); p_amax = its scale block
+            P_aug = torch.empty(1 if desc.gemm_algo == 3 else 2, n, lib.spotv2_gat_ld16(n_aug), device=dev, dtype=torch.float16)
+        else:
+            P_aug = torch.empty(n, desc.ldp, device=dev, dtype=torch.float32)
         # tensor-core path: x becomes an fp16 operand pair once; the weight-gradient GEMM reuses it
         x16 = x_blk = None
         if lib.spotv2_gat_uses_tensor_cores(C.byref(desc)) and x_pair is not None:
@@ -219,9 +240,14 @@ class _GatLayerFn(torch.autograd.Function):
             x_blk = torch.empty(8, device=dev, dtype=torch.float32)
             check(lib.spotv2_split_f16(ptr(x), n, x.shape[1], x.shape[1], 0, 0, ptr(x16[0]), ptr(x16[1]), ld16,
                                        ptr(x_blk), st), "spotv2_split_f16")
-        check(lib.spotv2_proj_fwd(C.byref(desc), ptr(x), ptr(x16[0]) if x16 is not None else None,
-                                  ptr(x16[1]) if x16 is not None else None, ptr(x_blk), ptr(W_aug), ptr(P_aug), ptr(p_amax),
-                                  ptr(ws), ws_f, st), "spotv2_proj_fwd")
+        if pair:
+            check(lib.spotv2_proj_fwd_pair(C.byref(desc), ptr(x16[0]), ptr(x16[1]), ptr(x_blk), ptr(W_aug), ptr(P_aug[0]),
+                                           ptr(P_aug[1]) if P_aug.shape[0] > 1 else None, ptr(p_amax), ptr(ws), ws_f, st),
+                  "spotv2_proj_fwd_pair")
+        else:
+            check(lib.spotv2_proj_fwd(C.byref(desc), ptr(x), ptr(x16[0]) if x16 is not None else None,
+                                      ptr(x16[1]) if x16 is not None else None, ptr(x_blk), ptr(W_aug), ptr(P_aug), ptr(p_amax),
+                                      ptr(ws), ws_f, st), "spotv2_proj_fwd")
         if Fe and edge_scale is not None and edge_mean is not None:
             # <e_hat, v> = <e, v'> - <mean, v'>: the same shift on every logit of the head, self loop included (its fill is the
             # mean of the real edges' e_hat) - carried by the d columns of P_aug, which both attention kernels read
@@ -243,8 +269,14 @@ class _GatLayerFn(torch.autograd.Function):
             check(lib.spotv2_edge_terms_from_windows(C.byref(desc), ptr(windows.volvol), windows.volvol.shape[0], windows.L,
                                                      ptr(windows.t0), ptr(v), ptr(et), ptr(ws_w), wsz.value, st),
                   "spotv2_edge_terms_from_windows")
-        check(lib.spotv2_gat_attn_fwd(C.byref(desc), ptr(P_aug), ptr(ea), ptr(topo.table) if (Fe and windows is None) else None, ptr(v),
-                                      ptr(bias_c), ptr(out), ptr(alpha), ptr(et), ptr(ws_attn), ws_t, st), "spotv2_gat_attn_fwd")
+        tbl = ptr(topo.table) if (Fe and windows is None) else None
+        if pair:
+            check(lib.spotv2_gat_attn_fwd_pair(C.byref(desc), ptr(P_aug[0]), ptr(P_aug[1]) if P_aug.shape[0] > 1 else None, ptr(p_amax),
+                                               ptr(ea), tbl, ptr(v), ptr(bias_c), ptr(out), ptr(alpha), ptr(et), st),
+                  "spotv2_gat_attn_fwd_pair")
+        else:
+            check(lib.spotv2_gat_attn_fwd(C.byref(desc), ptr(P_aug), ptr(ea), tbl, ptr(v),
+                                          ptr(bias_c), ptr(out), ptr(alpha), ptr(et), ptr(ws_attn), ws_t, st), "spotv2_gat_attn_fwd")
         ctx.desc, ctx.topo, ctx.Fe, ctx.has_bias, ctx.windows = desc, topo, Fe, bias is not None, windows
         ctx.edge_scale = edge_scale if Fe else None
         ctx.edge_mean = edge_mean if (Fe and edge_scale is not None) else None
@@ -275,21 +307,31 @@ class _GatLayerFn(torch.autograd.Function):
         ws = torch.empty(max(ws_a, ws_p), device=dev, dtype=torch.uint8)
         # on the tensor-core path the attention backward emits dP directly as the GEMMs' fp16 operand pair
         tc = bool(lib.spotv2_gat_uses_tensor_cores(C.byref(desc)))
+        pair = desc.p_format == 1
         dP_aug = dP16 = dp_blk = None
-        if tc:
+        if pair:
+            dP16 = torch.empty_like(P_aug)          # same planes, same padded head pitch
+            dp_blk = torch.empty(8, device=dev, dtype=torch.float32)
+        elif tc:
             dP16 = torch.empty(2, P_aug.shape[0], lib.spotv2_gat_ld16(HC + 2 * H), device=dev, dtype=torch.float16)
             dp_blk = torch.empty(8, device=dev, dtype=torch.float32)
         else:
             dP_aug = torch.empty_like(P_aug)
-        ph, pl = (dP16[0], dP16[1]) if tc else (None, None)
+        ph, pl = (dP16[0], dP16[1] if dP16.shape[0] > 1 else None) if tc else (None, None)
         dv = torch.empty(H, Fe, device=dev, dtype=torch.float32) if Fe else None
         dbias = torch.empty(dout.shape[1], device=dev, dtype=torch.float32) if ctx.has_bias else None
         win = ctx.windows
         d_et = torch.empty_like(et) if win is not None else None     # structured source: d(edge terms) out, dv from the windows
-        check(lib.spotv2_gat_attn_bwd(C.byref(desc), ptr(P_aug), ptr(p_amax), ptr(ea), ptr(et),
-                                      ptr(topo.table) if (Fe and win is None) else None, ptr(v),
-                                      ptr(dout), ptr(dP_aug), ptr(ph), ptr(pl), ptr(dp_blk), ptr(dv) if win is None else None,
-                                      ptr(d_et), ptr(dbias), ptr(ws), ws.numel(), st), "spotv2_gat_attn_bwd")
+        if pair:
+            check(lib.spotv2_gat_attn_bwd_pair(C.byref(desc), ptr(P_aug[0]), ptr(P_aug[1]) if P_aug.shape[0] > 1 else None, ptr(p_amax),
+                                               ptr(ea), ptr(et), ptr(topo.table) if (Fe and win is None) else None, ptr(v),
+                                               ptr(dout), ptr(ph), ptr(pl), ptr(dp_blk), ptr(dv) if win is None else None,
+                                               ptr(d_et), ptr(dbias), ptr(ws), ws.numel(), st), "spotv2_gat_attn_bwd_pair")
+        else:
+            check(lib.spotv2_gat_attn_bwd(C.byref(desc), ptr(P_aug), ptr(p_amax), ptr(ea), ptr(et),
+                                          ptr(topo.table) if (Fe and win is None) else None, ptr(v),
+                                          ptr(dout), ptr(dP_aug), ptr(ph), ptr(pl), ptr(dp_blk), ptr(dv) if win is None else None,
+                                          ptr(d_et), ptr(dbias), ptr(ws), ws.numel(), st), "spotv2_gat_attn_bwd")
         if win is not None:
             wsz = C.c_size_t()
             check(lib.spotv2_windows_dv_workspace_bytes(C.byref(desc), C.byref(wsz)), "windows_dv_workspace_bytes")
@@ -300,11 +342,11 @@ class _GatLayerFn(torch.autograd.Function):
             # the layer saw e_hat = (e - mean) * scale through v' = scale * v and the per-head logit shift -<mean, v'> on the
             # d columns.  d/dv = scale * (sum dz' e - mean * sum of ALL dz of the head): the kernels formed the first sum (dv),
             # the second is the column sum of the dd block (LeakyReLU keeps a softmax row's dz from summing to zero).
-            if tc:
-                T = ((dP16[0][:, HC + H:HC + 2 * H].float() + dP16[1][:, HC + H:HC + 2 * H].float()).sum(0) * dp_blk[3])
-            else:
-                T = dP_aug[:, HC + H:HC + 2 * H].sum(0)
-            if ctx.edge_mean is not None:
+            if ctx.edge_mean is not None:            # (p_format 0 by construction: see _forward)
+                if tc:
+                    T = ((dP16[0][:, HC + H:HC + 2 * H].float() + dP16[1][:, HC + H:HC + 2 * H].float()).sum(0) * dp_blk[3])
+                else:
+                    T = dP_aug[:, HC + H:HC + 2 * H].sum(0)
                 dv.sub_(T.view(H, 1) * ctx.edge_mean.view(1, Fe))
             dv.mul_(ctx.edge_scale.view(1, Fe))
         dW_aug = torch.empty_like(W_aug)

@@ -20,7 +20,7 @@ def _declared():
 
 def test_library_is_built_and_loads():
     lib = spotv2net_b200.load_library()
-    assert lib.spotv2_abi_version() == 4
+    assert lib.spotv2_abi_version() == 5
 
 
 def test_every_declared_symbol_is_exported_and_bound():
@@ -34,10 +34,10 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 
 def test_descriptor_layout_matches_header():
-    assert ctypes.sizeof(_lib.GatDesc) == 16 * 4
+    assert ctypes.sizeof(_lib.GatDesc) == 17 * 4
     assert [f[0] for f in _lib.GatDesc._fields_] == ["B", "N", "F", "Fe", "H", "C", "R", "concat",
                                                      "negative_slope", "ldp", "gemm_algo", "attn_bwd_algo",
-                                                     "dropout_p", "edge_mode", "dropout_seed_lo", "dropout_seed_hi"]
+                                                     "dropout_p", "edge_mode", "dropout_seed_lo", "dropout_seed_hi", "p_format"]
 
 
 def test_ldp_query_and_argument_validation_without_a_gpu():
