@@ -506,6 +506,7 @@ extern "C" int spotv2_diag_counters(unsigned long long* host_out, int reset) {
     unsigned long long zeros[kNumCounters] = {0};
     SPOTV2_CUDA_OK(cudaMemcpyToSymbol(g_diag_counters, zeros, sizeof(zeros)));
   }
+  if (int rc = fwd16_diag_add(host_out, reset)) return rc;      // whichever forward ran contributes; the other adds zeros
   return bwd_diag_read(host_out + kNumCounters, reset);      // entries 16..31: backward phase times
 }
 

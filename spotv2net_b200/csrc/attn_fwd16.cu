@@ -2,12 +2,14 @@
 // (attn_fwd.cu is the fp32-P version of the same operator; [PyG] gat_conv.py edge_update / softmax / propagate, reached
 // from /root/reference/utils/models.py:146).
 //
-// Same roles as attn_fwd.cu - group A (3 warps) edge logits on 3xTF32 mma.sync, group B (8 warps) softmax + aggregation,
-// one TMA producer warp, pipelined across graphs - but no thread converts an MMA operand in the aggregation:
+// Roles: group A (3 warps) edge logits on 3xTF32 mma.sync, THEN the softmax and its conversion into the aggregation's A
+// operand (double buffered); group B (8 warps) nothing but the aggregation MMAs; one TMA producer warp; all pipelined
+// across graphs (group A works on graph b+1 while group B aggregates graph b, so the P stream never waits for a softmax).
+// No thread converts an MMA operand in the aggregation:
 //   * P tiles are 32 source rows x 32 channels of fp16, hi and lo planes side by side in a 4 KB slot (64B swizzle); the B
 //     fragments of mma.sync.m16n8k16 come out of ldmatrix.x4.trans (one instruction per k16 x n16 block);
 //   * the softmax output is converted ONCE per graph into an fp16 hi/lo tile [h][target i][source j] and the A fragments
-//     come out of ldmatrix.x4; the fp32 alpha tile is released to the logit group right after that conversion;
+//     come out of ldmatrix.x4;
 //   * out[i, c] = (sum_h sum_j alpha_h[i,j] P[j, h, c]) with lo*hi + hi*lo + hi*hi per product (hi*hi only for the
 //     half-precision class), 48 instead of 96 MMAs per (head, channel block) and 16 ldmatrix instead of ~130 loads/splits.
 #include "attn_bwd.cuh"
@@ -50,6 +52,11 @@ __device__ __forceinline__ int q_ldsi(uint32_t a) {
   return v;
 }
 __device__ __forceinline__ void q_sts(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+// cycle accounting per role (one sampling thread each; read through spotv2_diag_counters, entries [0, 16)):
+// 0 A: edge ring wait, 1 A: alpha buffer free, 2 B: alpha buffer ready, 3 B: P tiles, 4 P: slot free, 5/6/7 role totals,
+// 8 A: logits arithmetic, 9 A: softmax, 10 A: conversions, 11 A: s|d tile, 12 A: group barriers
+__device__ unsigned long long g_fwd16_counters[kNumCounters];
+
 // bounded wait that says WHICH barrier starved before it traps (a lost arrival must fail loudly, never hang the box)
 __device__ __noinline__ void wait_report(int id, int it, uint32_t parity) {
   printf("attn_fwd16: wait %d timed out (block %d thread %d graph-iteration %d parity %u)\n", id, (int)blockIdx.x, (int)threadIdx.x, it, parity);
@@ -62,6 +69,11 @@ __device__ __forceinline__ void wait_id(uint64_t* bar, uint32_t parity, int id, 
     __nanosleep(64);
     if (clock64() - t0 > 400000000LL) { wait_report(id, it, parity); __trap(); }
   }
+}
+__device__ __forceinline__ void wait_id_t(uint64_t* bar, uint32_t parity, int id, int it, long long& acc) {
+  const long long t0 = clock64();
+  wait_id(bar, parity, id, it);
+  acc += clock64() - t0;
 }
 __device__ __forceinline__ void split_raw(float x, uint32_t& hi, uint32_t& lo) {    // tf32: hi = raw fp32 (top 19 bits are read)
   hi = __float_as_uint(x);
@@ -86,21 +98,24 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
   const int tile_floats = H * N * NS;
   const int n_slots = pl.n_slots;
 
-  // barriers: [0,1] edge ring, [2,3] tile_full, [4,5] tile_empty, [6,7] sd_full, [8,9] sd_empty, then slot full / empty
+  // barriers: [0,1] edge ring, [2,3] ap_full (alpha pair buffer written), [4,5] ap_empty (aggregated), [6,7] sd_full,
+  // [8,9] sd_empty, then slot full / empty; the last one: the structured source's edge-term copy into the tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + pl.off_bar);
-  uint64_t* tile_full = bars + 2;
-  uint64_t* tile_empty = bars + 4;
+  uint64_t* ap_full = bars + 2;
+  uint64_t* ap_empty = bars + 4;
   uint64_t* sd_full = bars + 6;
   uint64_t* sd_empty = bars + 8;
+  uint64_t* terms_bar = bars + 10 + 2 * kMaxPSlots;
   uint64_t* p_full = bars + 10;
   uint64_t* p_empty = p_full + kMaxPSlots;
   const int n_cb = (C + 31) / 32;
   const int n_pass = (n_cb + kCbPass - 1) / kCbPass;
   int32_t* table_s = reinterpret_cast<int32_t*>(smem_raw + pl.off_table);
   float4* vfrag = reinterpret_cast<float4*>(smem_raw + pl.off_vfrag);
-  float* sd0 = reinterpret_cast<float*>(smem_raw + pl.off_sd);              // [2][N][2H] fp32
-  float* tile0 = reinterpret_cast<float*>(smem_raw + pl.off_tile);          // [2][H][N][NS] fp32
+  float* sd = reinterpret_cast<float*>(smem_raw + pl.off_sd);               // [N][2H] fp32 (group A only)
+  float* tile = reinterpret_cast<float*>(smem_raw + pl.off_tile);           // [H][N][NS] fp32: edge terms, then alpha (group A only)
   const int sd_floats = N * 2 * H;
+  const uint32_t ap_bytes = (uint32_t)H * 2048u;                            // one plane of one alpha pair buffer
 
   const int nchunks = (p.Fe > 0 && !p.terms_in) ? (p.R + pl.chunk_rows - 1) / pl.chunk_rows : 0;
   const int my_graphs = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -109,11 +124,12 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     for (int r = 0; r < 2; ++r) {
-      mbar_init(&tile_full[r], kGA);
-      mbar_init(&tile_empty[r], kGB);
+      mbar_init(&ap_full[r], kGA);
+      mbar_init(&ap_empty[r], kGB / 32);
       mbar_init(&sd_full[r], 1);
       mbar_init(&sd_empty[r], 1);
     }
+    mbar_init(terms_bar, 1);
     for (int r = 0; r < n_slots; ++r) { mbar_init(&p_full[r], 1); mbar_init(&p_empty[r], grp); }
     fence_mbar_init();
   }
@@ -127,7 +143,7 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
     reinterpret_cast<float4*>(smem_raw + pl.off_ahi)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
   fence_proxy_async();
   if (p.Fe > 0 && !p.terms_in) build_vfrag(vfrag, p.v, H, p.Fe, pl.KS, 1, tid, kF16Threads);
-  for (int idx = tid; idx < 2 * tile_floats; idx += kF16Threads) tile0[idx] = 0.f;
+  for (int idx = tid; idx < tile_floats; idx += kF16Threads) tile[idx] = 0.f;
   __syncthreads();
 
   if (tid < kGA) {
@@ -153,33 +169,37 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
       if (total_chunks > 1) issue(1);
     }
     int k = 0;
+    const float out_scale = p.concat ? 1.f : 1.f / (float)H;
+    const float inv_sd = p.p_blk[3];
+    long long w_ring = 0, w_ape = 0, w_sd = 0, t_log = 0, t_smx = 0, t_cnv = 0, t_bar = 0;
+    const long long t_role = clock64();
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
       const int buf = it & 1;
-      float* tile = tile0 + buf * tile_floats;
-      wait_id(&tile_empty[buf], ((it >> 1) & 1) ^ 1, 1, it);
       if (p.terms_in) {
+        // structured edge source: the caller computed the edge terms; one bulk copy drops them into the tile
         if (tid == 0) {
           const uint32_t bytes = (uint32_t)tile_floats * 4u;
-          mbar_expect_tx(&tile_full[buf], bytes);
-          bulk_g2s(tile, p.edge_terms + (size_t)b * tile_floats, bytes, &tile_full[buf]);
-        } else {
-          arrive(&tile_full[buf]);
+          mbar_expect_tx(terms_bar, bytes);
+          bulk_g2s(tile, p.edge_terms + (size_t)b * tile_floats, bytes, terms_bar);
         }
-        continue;
+        wait_id(terms_bar, it & 1, 1, it);
       }
-      if (nchunks == 0)
+      if (nchunks == 0 && !p.terms_in) {
         for (int idx = tid; idx < tile_floats; idx += kGA) tile[idx] = 0.f;
+        bar_a();
+      }
       for (int c = 0; c < nchunks; ++c, ++k) {
         const int s = k & 1;
         const int rows = rows_in(c);
         if (p.bulk_ok) {
-          wait_id(&bars[s], (k >> 1) & 1, 2, it);
+          wait_id_t(&bars[s], (k >> 1) & 1, 2, it, w_ring);
         } else {
           const float* src = p.edge_rows + ((size_t)b * p.R + (size_t)c * pl.chunk_rows) * p.Fe;
           for (int idx = tid; idx < rows * p.Fe; idx += kGA) stage[s][idx] = src[idx];
           bar_a();
         }
+        const long long tl0 = clock64();
         if (warp * 16 < rows) {
           const uint32_t r0 = ring_a[s] + (uint32_t)(((warp * 16 + 2 * g) * p.Fe + t) * 4), r1 = r0 + (uint32_t)(p.Fe * 4);
           float acc[3][4];
@@ -214,7 +234,7 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
           const int rl = warp * 16 + 2 * g, row_base = c * pl.chunk_rows + rl;
           const int to0 = rl < rows ? q_ldsi(a_table + (uint32_t)row_base * 4u) : -1;
           const int to1 = rl + 1 < rows ? q_ldsi(a_table + (uint32_t)(row_base + 1) * 4u) : -1;
-          const uint32_t tb = a_tile0 + (uint32_t)(buf * tile_floats * 4) + (uint32_t)(2 * t) * head_bytes;
+          const uint32_t tb = a_tile0 + (uint32_t)(2 * t) * head_bytes;
           if (to0 >= 0) {
             if (2 * t < H) q_sts(tb + (uint32_t)to0, (acc[0][0] + acc[1][0]) + acc[2][0]);
             if (2 * t + 1 < H) q_sts(tb + head_bytes + (uint32_t)to0, (acc[0][1] + acc[1][1]) + acc[2][1]);
@@ -224,16 +244,75 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
             if (2 * t + 1 < H) q_sts(tb + head_bytes + (uint32_t)to1, (acc[0][3] + acc[1][3]) + acc[2][3]);
           }
         }
+        const long long tl1 = clock64();
         bar_a();
+        t_log += tl1 - tl0;
+        t_bar += clock64() - tl1;
         if (p.bulk_ok && tid == 0 && k + 2 < total_chunks) issue(k + 2);
       }
       if (p.edge_terms && !p.terms_in && NS == kEdgeTermNS) {
-        if (nchunks == 0) bar_a();
+        // keep the edge terms for the backward (6 floats per edge instead of the Fe-wide rows); every scatter is behind a bar_a
         float4* dst = reinterpret_cast<float4*>(p.edge_terms + (size_t)b * tile_floats);
         const float4* src = reinterpret_cast<const float4*>(tile);
         for (int idx = tid; idx < tile_floats / 4; idx += kGA) dst[idx] = src[idx];
       }
-      arrive(&tile_full[buf]);
+      // s | d columns of this graph: fp16 pair tile -> packed fp32 [N][2H]
+      wait_id_t(&sd_full[buf], (it >> 1) & 1, 3, it, w_sd);
+      const long long tc0 = clock64();
+      {
+        const unsigned char* sl = smem_raw + pl.off_sdslot + buf * kSlotBytes;
+        for (int idx = tid; idx < sd_floats; idx += kGA) {
+          const int j = idx / (2 * H), kk = idx - j * 2 * H;
+          const uint32_t off = sw64(j, kk >> 3) + (uint32_t)(kk & 7) * 2u;
+          float v = __half2float(*reinterpret_cast<const __half*>(sl + off));
+          if (!SINGLE) v += __half2float(*reinterpret_cast<const __half*>(sl + 2048 + off));
+          sd[idx] = v * inv_sd;
+        }
+      }
+      bar_a();
+      if (tid == 0) arrive(&sd_empty[buf]);
+      const long long ts0 = clock64();
+      t_cnv += ts0 - tc0;
+      softmax_phase(p, AttnSmem{NS, pl.KS, 1, pl.chunk_rows, 0, 0, 0, 0, 0, 0, 0, 0}, tile, sd, out_scale,
+                    args.alpha_out ? args.alpha_out + (size_t)b * H * N * N : nullptr, nullptr, tid, kGA, -1, 0, nullptr, b);
+      bar_a();                                             // alpha tile complete
+      t_smx += clock64() - ts0;
+      // alpha[h][j][i] fp32 -> fp16 hi | lo tiles [h][i][j] (64-byte rows, swizzled): the A operand of the aggregation,
+      // double buffered against group B
+      wait_id_t(&ap_empty[buf], ((it >> 1) & 1) ^ 1, 4, it, w_ape);
+      const long long tc1 = clock64();
+      {
+        unsigned char* ahi = smem_raw + pl.off_ahi + (uint32_t)buf * 2u * ap_bytes;
+        unsigned char* alo = ahi + ap_bytes;
+        const int njp = (N + 1) / 2;
+        for (int idx = tid; idx < H * njp * N; idx += kGA) {
+          const int i = idx % N, r = idx / N, jp = r % njp, h = r / njp;
+          const float* base = tile + (size_t)h * N * NS + i;
+          const float y0 = base[(2 * jp) * NS] * pl.s_alpha;
+          const float y1 = (2 * jp + 1 < N) ? base[(2 * jp + 1) * NS] * pl.s_alpha : 0.f;
+          const __half2 hh = __floats2half2_rn(y0, y1);
+          const uint32_t off = (uint32_t)h * 2048u + sw64(i, jp >> 2) + (uint32_t)(jp & 3) * 4u;
+          *reinterpret_cast<__half2*>(ahi + off) = hh;
+          if (!SINGLE) {
+            const float2 bk = __half22float2(hh);
+            *reinterpret_cast<__half2*>(alo + off) = __floats2half2_rn(y0 - bk.x, y1 - bk.y);
+          }
+        }
+      }
+      if (p.terms_in) fence_proxy_async();               // generic-proxy accesses to the tile precede the next bulk copy into it
+      arrive(&ap_full[buf]);                               // release: this graph's coefficients are visible to group B
+      bar_a();                                             // everyone is done with the tile before the next graph's terms land
+      t_cnv += clock64() - tc1;
+    }
+    if (tid == 0) {
+      atomicAdd(&g_fwd16_counters[0], (unsigned long long)w_ring);
+      atomicAdd(&g_fwd16_counters[1], (unsigned long long)w_ape);
+      atomicAdd(&g_fwd16_counters[5], (unsigned long long)(clock64() - t_role));
+      atomicAdd(&g_fwd16_counters[8], (unsigned long long)t_log);
+      atomicAdd(&g_fwd16_counters[9], (unsigned long long)t_smx);
+      atomicAdd(&g_fwd16_counters[10], (unsigned long long)t_cnv);
+      atomicAdd(&g_fwd16_counters[11], (unsigned long long)w_sd);
+      atomicAdd(&g_fwd16_counters[12], (unsigned long long)t_bar);
     }
   } else if (tid < kGA + kGB) {
     // ================================ group B: softmax + aggregation ================================
@@ -241,7 +320,7 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
     const int wb = tb_ >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const uint32_t sbase = smem_u32(smem_raw);
-    const uint32_t a_slots = sbase + pl.off_slots, a_ahi = sbase + pl.off_ahi, a_alo = sbase + pl.off_alo;
+    const uint32_t a_slots = sbase + pl.off_slots;
     // ldmatrix lane roles (identical for the alpha A fragments and the P B fragments): matrix = lane >> 3,
     // row = (lane & 7) + 8 * (matrix & 1), 16-byte chunk = matrix >> 1
     const int lm_row = (lane & 7) + ((lane >> 3) & 1) * 8, lm_chunk = lane >> 4;
@@ -250,52 +329,15 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
     for (int rb = 0; rb < 2; ++rb)
 #pragma unroll
       for (int cp = 0; cp < 2; ++cp) lm_off[rb][cp] = sw64(16 * rb + lm_row, 2 * cp + lm_chunk);
-    const float out_scale = p.concat ? 1.f : 1.f / (float)H;
-    const float inv_sd = p.p_blk[3];
     const float k_out = p.p_blk[2] / pl.s_alpha;          // accumulator -> out
     uint32_t q_base = 0;
+    long long w_apf = 0, w_pf = 0;
+    const long long t_role = clock64();
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
       const int buf = it & 1;
-      float* tile = tile0 + buf * tile_floats;
-      float* sd = sd0 + buf * sd_floats;
-      wait_id(&sd_full[buf], (it >> 1) & 1, 3, it);
-      {   // s|d columns: fp16 pair tile -> packed fp32 [N][2H]
-        const unsigned char* sl = smem_raw + pl.off_sdslot + buf * kSlotBytes;
-        for (int idx = tb_; idx < sd_floats; idx += kGB) {
-          const int j = idx / (2 * H), k = idx - j * 2 * H;
-          const uint32_t off = sw64(j, k >> 3) + (uint32_t)(k & 7) * 2u;
-          float v = __half2float(*reinterpret_cast<const __half*>(sl + off));
-          if (!SINGLE) v += __half2float(*reinterpret_cast<const __half*>(sl + 2048 + off));
-          sd[idx] = v * inv_sd;
-        }
-      }
-      wait_id(&tile_full[buf], (it >> 1) & 1, 4, it);
-      bar_b();                                           // sd complete (and everyone is past the previous graph's MMAs)
-      if (tb_ == 0) arrive(&sd_empty[buf]);
-      softmax_phase(p, AttnSmem{NS, pl.KS, 1, pl.chunk_rows, 0, 0, 0, 0, 0, 0, 0, 0}, tile, sd, out_scale,
-                    args.alpha_out ? args.alpha_out + (size_t)b * H * N * N : nullptr, nullptr, tb_, kGB, -1, 0, nullptr, b);
-      bar_b();                                           // alpha tile complete
-      // alpha[h][j][i] fp32 -> fp16 hi | lo tiles [h][i][j] (64-byte rows, swizzled): the A operand of the aggregation
-      {
-        const int njp = (N + 1) / 2;
-        for (int idx = tb_; idx < H * njp * N; idx += kGB) {
-          const int i = idx % N, r = idx / N, jp = r % njp, h = r / njp;
-          const float* base = tile + (size_t)h * N * NS + i;
-          const float y0 = base[(2 * jp) * NS] * pl.s_alpha;
-          const float y1 = (2 * jp + 1 < N) ? base[(2 * jp + 1) * NS] * pl.s_alpha : 0.f;
-          const __half2 hh = __floats2half2_rn(y0, y1);
-          const uint32_t off = (uint32_t)h * 2048u + sw64(i, jp >> 2) + (uint32_t)(jp & 3) * 4u;
-          *reinterpret_cast<__half2*>(smem_raw + pl.off_ahi + off) = hh;
-          if (!SINGLE) {
-            const float2 bk = __half22float2(hh);
-            *reinterpret_cast<__half2*>(smem_raw + pl.off_alo + off) = __floats2half2_rn(y0 - bk.x, y1 - bk.y);
-          }
-        }
-      }
-      if (p.terms_in) fence_proxy_async();               // generic-proxy writes to the tile precede the next bulk copy into it
-      arrive(&tile_empty[buf]);                          // the fp32 tile is free for the logit group
-      bar_b();                                           // alpha pair tiles complete
+      const uint32_t a_ahi = sbase + pl.off_ahi + (uint32_t)buf * 2u * ap_bytes, a_alo = a_ahi + ap_bytes;
+      wait_id_t(&ap_full[buf], (it >> 1) & 1, 9, it, w_apf);
       for (int pass = 0; pass < n_pass; ++pass) {
         const int G = min(kCbPass, n_cb - pass * kCbPass);
         const bool mine = wb < G;
@@ -353,8 +395,8 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
           // A slot's consecutive uses may belong to different warps: a warp that runs ahead must not take the slot's
           // PREVIOUS fill for its own (the parity test cannot tell fill r from fill r - 2), so it first waits until the
           // previous use has been released - only then can fill r be pending.
-          wait_id(&p_empty[slot], ((q / n_slots) & 1) ^ 1, 8, it);
-          wait_id(&p_full[slot], (q / n_slots) & 1, 5, it);
+          wait_id_t(&p_empty[slot], ((q / n_slots) & 1) ^ 1, 8, it, w_pf);
+          wait_id_t(&p_full[slot], (q / n_slots) & 1, 5, it, w_pf);
           if (mine) {
             const uint32_t th = a_slots + (uint32_t)slot * slot_bytes + (uint32_t)ti * 2048u, tl = th + (uint32_t)grp * 2048u;
 #pragma unroll
@@ -390,6 +432,13 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
         }
         if (!p.concat && mine) store(0);
       }
+      __syncwarp();
+      if (lane == 0) arrive(&ap_empty[buf]);               // this warp has taken its last fragment of the alpha pair buffer
+    }
+    if (tid == kGA) {
+      atomicAdd(&g_fwd16_counters[2], (unsigned long long)w_apf);
+      atomicAdd(&g_fwd16_counters[3], (unsigned long long)w_pf);
+      atomicAdd(&g_fwd16_counters[6], (unsigned long long)(clock64() - t_role));
     }
   } else {
     // ================================ producer warp ================================
@@ -399,6 +448,8 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
       prefetch_tmap(&tmG);
       if (!SINGLE) prefetch_tmap(&tmL);
       uint32_t q = 0;
+      long long w_pe = 0;
+      const long long t_role = clock64();
       for (int it = 0; it < my_graphs; ++it) {
         const int b = blockIdx.x + it * gridDim.x;
         {
@@ -416,18 +467,31 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
             for (int k = 0; k < n_g; ++k, ++q) {
               const int slot = q % n_slots;
               unsigned char* dst = smem_raw + pl.off_slots + (size_t)slot * slot_bytes;
-              wait_id(&p_empty[slot], ((q / n_slots) & 1) ^ 1, 7, it);
+              wait_id_t(&p_empty[slot], ((q / n_slots) & 1) ^ 1, 7, it, w_pe);
               mbar_expect_tx(&p_full[slot], (uint32_t)grp * (SINGLE ? 2048u : 4096u));
               tma_load_4d(dst, &tmG, h * Cp + (pass * kCbPass + k * grp) * 32, b * N, 0, 0, &p_full[slot]);
             }
           }
         }
       }
+      atomicAdd(&g_fwd16_counters[4], (unsigned long long)w_pe);
+      atomicAdd(&g_fwd16_counters[7], (unsigned long long)(clock64() - t_role));
     }
   }
 }
 
 }  // namespace
+
+int fwd16_diag_add(unsigned long long* host_out, int reset) {
+  unsigned long long tmp[kNumCounters];
+  SPOTV2_CUDA_OK(cudaMemcpyFromSymbol(tmp, g_fwd16_counters, sizeof(tmp)));
+  for (int k = 0; k < kNumCounters; ++k) host_out[k] += tmp[k];
+  if (reset) {
+    unsigned long long zeros[kNumCounters] = {0};
+    SPOTV2_CUDA_OK(cudaMemcpyToSymbol(g_fwd16_counters, zeros, sizeof(zeros)));
+  }
+  return SPOTV2_OK;
+}
 
 int attn_fwd16_dispatch(const AttnFwdArgs& a, cudaStream_t st) {
   const AttnParams& p = a.p;
@@ -449,11 +513,11 @@ int attn_fwd16_dispatch(const AttnFwdArgs& a, cudaStream_t st) {
     pl.off_bar = (uint32_t)o;    o += 512;
     pl.off_table = (uint32_t)o;  o += round_up((size_t)(p.R > 0 ? p.R : 1) * 4, 16);
     pl.off_vfrag = (uint32_t)o;  o += (size_t)(p.Fe > 0 ? pl.KS : 0) * 32 * 16;
-    pl.off_sd = (uint32_t)o;     o += 2 * sd_bytes;
-    pl.off_tile = (uint32_t)o;   o += 2 * tile_bytes;
+    pl.off_sd = (uint32_t)o;     o += sd_bytes;
+    pl.off_tile = (uint32_t)o;   o += tile_bytes;
     o = round_up(o, 128);
-    pl.off_ahi = (uint32_t)o;    o += (size_t)p.H * 2048;
-    pl.off_alo = (uint32_t)o;    o += (size_t)p.H * 2048;
+    pl.off_ahi = (uint32_t)o;    o += 4 * (size_t)p.H * 2048;              // two buffers x (hi | lo)
+    pl.off_alo = pl.off_ahi;
     pl.off_ring = (uint32_t)o;
     pl.ring_stage = (uint32_t)round_up((size_t)rows * p.Fe * 4, 128);
     o += (p.Fe > 0 && !p.terms_in) ? 2 * (size_t)pl.ring_stage + 256 : 0;     // + zero pad behind the ring (k-steps past Fe)
