@@ -2,14 +2,12 @@
 // (attn_fwd.cu is the fp32-P version of the same operator; [PyG] gat_conv.py edge_update / softmax / propagate, reached
 // from /root/reference/utils/models.py:146).
 //
-// Roles: group A (3 warps) edge logits on 3xTF32 mma.sync, THEN the softmax and its conversion into the aggregation's A
-// operand (double buffered); group B (8 warps) nothing but the aggregation MMAs; one TMA producer warp; all pipelined
-// across graphs (group A works on graph b+1 while group B aggregates graph b, so the P stream never waits for a softmax).
-// No thread converts an MMA operand in the aggregation:
+// Same roles as attn_fwd.cu - group A (3 warps) edge logits on 3xTF32 mma.sync, group B (8 warps) softmax + aggregation,
+// one TMA producer warp, pipelined across graphs - but no thread converts an MMA operand in the aggregation:
 //   * P tiles are 32 source rows x 32 channels of fp16, hi and lo planes side by side in a 4 KB slot (64B swizzle); the B
 //     fragments of mma.sync.m16n8k16 come out of ldmatrix.x4.trans (one instruction per k16 x n16 block);
 //   * the softmax output is converted ONCE per graph into an fp16 hi/lo tile [h][target i][source j] and the A fragments
-//     come out of ldmatrix.x4;
+//     come out of ldmatrix.x4; the fp32 alpha tile is released to the logit group right after that conversion;
 //   * out[i, c] = (sum_h sum_j alpha_h[i,j] P[j, h, c]) with lo*hi + hi*lo + hi*hi per product (hi*hi only for the
 //     half-precision class), 48 instead of 96 MMAs per (head, channel block) and 16 ldmatrix instead of ~130 loads/splits.
 #include "attn_bwd.cuh"
@@ -53,8 +51,8 @@ __device__ __forceinline__ int q_ldsi(uint32_t a) {
 }
 __device__ __forceinline__ void q_sts(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 // cycle accounting per role (one sampling thread each; read through spotv2_diag_counters, entries [0, 16)):
-// 0 A: edge ring wait, 1 A: alpha buffer free, 2 B: alpha buffer ready, 3 B: P tiles, 4 P: slot free, 5/6/7 role totals,
-// 8 A: logits arithmetic, 9 A: softmax, 10 A: conversions, 11 A: s|d tile, 12 A: group barriers
+// 0 A: edge ring wait, 1 A: tile buffer free, 2 B: edge terms ready, 3 B: P tiles, 4 P: slot free, 5/6/7 role totals,
+// 8 A: logits arithmetic, 9 B: softmax, 10 B: conversions, 11 B: s|d tile, 12 A: chunk barriers, 13 A: edge-term copy-out
 __device__ unsigned long long g_fwd16_counters[kNumCounters];
 
 // bounded wait that says WHICH barrier starved before it traps (a lost arrival must fail loudly, never hang the box)
@@ -98,24 +96,21 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
   const int tile_floats = H * N * NS;
   const int n_slots = pl.n_slots;
 
-  // barriers: [0,1] edge ring, [2,3] ap_full (alpha pair buffer written), [4,5] ap_empty (aggregated), [6,7] sd_full,
-  // [8,9] sd_empty, then slot full / empty; the last one: the structured source's edge-term copy into the tile
+  // barriers: [0,1] edge ring, [2,3] tile_full, [4,5] tile_empty, [6,7] sd_full, [8,9] sd_empty, then slot full / empty
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + pl.off_bar);
-  uint64_t* ap_full = bars + 2;
-  uint64_t* ap_empty = bars + 4;
+  uint64_t* tile_full = bars + 2;
+  uint64_t* tile_empty = bars + 4;
   uint64_t* sd_full = bars + 6;
   uint64_t* sd_empty = bars + 8;
-  uint64_t* terms_bar = bars + 10 + 2 * kMaxPSlots;
   uint64_t* p_full = bars + 10;
   uint64_t* p_empty = p_full + kMaxPSlots;
   const int n_cb = (C + 31) / 32;
   const int n_pass = (n_cb + kCbPass - 1) / kCbPass;
   int32_t* table_s = reinterpret_cast<int32_t*>(smem_raw + pl.off_table);
   float4* vfrag = reinterpret_cast<float4*>(smem_raw + pl.off_vfrag);
-  float* sd = reinterpret_cast<float*>(smem_raw + pl.off_sd);               // [N][2H] fp32 (group A only)
-  float* tile = reinterpret_cast<float*>(smem_raw + pl.off_tile);           // [H][N][NS] fp32: edge terms, then alpha (group A only)
+  float* sd0 = reinterpret_cast<float*>(smem_raw + pl.off_sd);              // [2][N][2H] fp32
+  float* tile0 = reinterpret_cast<float*>(smem_raw + pl.off_tile);          // [2][H][N][NS] fp32
   const int sd_floats = N * 2 * H;
-  const uint32_t ap_bytes = (uint32_t)H * 2048u;                            // one plane of one alpha pair buffer
 
   const int nchunks = (p.Fe > 0 && !p.terms_in) ? (p.R + pl.chunk_rows - 1) / pl.chunk_rows : 0;
   const int my_graphs = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -124,12 +119,11 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     for (int r = 0; r < 2; ++r) {
-      mbar_init(&ap_full[r], kGA);
-      mbar_init(&ap_empty[r], kGB / 32);
+      mbar_init(&tile_full[r], kGA);
+      mbar_init(&tile_empty[r], kGB);
       mbar_init(&sd_full[r], 1);
       mbar_init(&sd_empty[r], 1);
     }
-    mbar_init(terms_bar, 1);
     for (int r = 0; r < n_slots; ++r) { mbar_init(&p_full[r], 1); mbar_init(&p_empty[r], grp); }
     fence_mbar_init();
   }
@@ -143,7 +137,7 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
     reinterpret_cast<float4*>(smem_raw + pl.off_ahi)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
   fence_proxy_async();
   if (p.Fe > 0 && !p.terms_in) build_vfrag(vfrag, p.v, H, p.Fe, pl.KS, 1, tid, kF16Threads);
-  for (int idx = tid; idx < tile_floats; idx += kF16Threads) tile[idx] = 0.f;
+  for (int idx = tid; idx < 2 * tile_floats; idx += kF16Threads) tile0[idx] = 0.f;
   __syncthreads();
 
   if (tid < kGA) {
@@ -169,26 +163,25 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
       if (total_chunks > 1) issue(1);
     }
     int k = 0;
-    const float out_scale = p.concat ? 1.f : 1.f / (float)H;
-    const float inv_sd = p.p_blk[3];
-    long long w_ring = 0, w_ape = 0, w_sd = 0, t_log = 0, t_smx = 0, t_cnv = 0, t_bar = 0;
+    long long w_ring = 0, w_te = 0, t_log = 0, t_bar = 0, t_out = 0;
     const long long t_role = clock64();
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
       const int buf = it & 1;
+      float* tile = tile0 + buf * tile_floats;
+      wait_id_t(&tile_empty[buf], ((it >> 1) & 1) ^ 1, 1, it, w_te);
       if (p.terms_in) {
-        // structured edge source: the caller computed the edge terms; one bulk copy drops them into the tile
         if (tid == 0) {
           const uint32_t bytes = (uint32_t)tile_floats * 4u;
-          mbar_expect_tx(terms_bar, bytes);
-          bulk_g2s(tile, p.edge_terms + (size_t)b * tile_floats, bytes, terms_bar);
+          mbar_expect_tx(&tile_full[buf], bytes);
+          bulk_g2s(tile, p.edge_terms + (size_t)b * tile_floats, bytes, &tile_full[buf]);
+        } else {
+          arrive(&tile_full[buf]);
         }
-        wait_id(terms_bar, it & 1, 1, it);
+        continue;
       }
-      if (nchunks == 0 && !p.terms_in) {
+      if (nchunks == 0)
         for (int idx = tid; idx < tile_floats; idx += kGA) tile[idx] = 0.f;
-        bar_a();
-      }
       for (int c = 0; c < nchunks; ++c, ++k) {
         const int s = k & 1;
         const int rows = rows_in(c);
@@ -202,11 +195,14 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
         const long long tl0 = clock64();
         if (warp * 16 < rows) {
           const uint32_t r0 = ring_a[s] + (uint32_t)(((warp * 16 + 2 * g) * p.Fe + t) * 4), r1 = r0 + (uint32_t)(p.Fe * 4);
-          float acc[3][4];
+          // two accumulator sets (even / odd k-steps): the dependent chain per accumulator is 8 MMAs per chunk, not 16
+          float acc[2][3][4];
 #pragma unroll
-          for (int pr = 0; pr < 3; ++pr)
+          for (int e = 0; e < 2; ++e)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[pr][q] = 0.f;
+            for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc[e][pr][q] = 0.f;
           for (int ks0 = 0; ks0 < pl.KS; ks0 += 8) {
             const uint32_t ko = (uint32_t)ks0 * 32u, vf = a_vfrag + ((uint32_t)ks0 * 32u + (uint32_t)lane) * 16u;
             float a[8][4];
@@ -226,22 +222,25 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
               for (int q = 0; q < 4; ++q) split_raw(a[sl][q], ah[q], al[q]);
               const uint32_t bh[2] = {__float_as_uint(bf[sl].x), __float_as_uint(bf[sl].y)};
               const uint32_t bl[2] = {__float_as_uint(bf[sl].z), __float_as_uint(bf[sl].w)};
-              mma_tf32_16x8x8(acc[0], al, bh);
-              mma_tf32_16x8x8(acc[1], ah, bl);
-              mma_tf32_16x8x8(acc[2], ah, bh);
+              mma_tf32_16x8x8(acc[sl & 1][0], al, bh);
+              mma_tf32_16x8x8(acc[sl & 1][1], ah, bl);
+              mma_tf32_16x8x8(acc[sl & 1][2], ah, bh);
             }
           }
+          float res[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) res[q] = ((acc[0][0][q] + acc[1][0][q]) + (acc[0][1][q] + acc[1][1][q])) + (acc[0][2][q] + acc[1][2][q]);
           const int rl = warp * 16 + 2 * g, row_base = c * pl.chunk_rows + rl;
           const int to0 = rl < rows ? q_ldsi(a_table + (uint32_t)row_base * 4u) : -1;
           const int to1 = rl + 1 < rows ? q_ldsi(a_table + (uint32_t)(row_base + 1) * 4u) : -1;
-          const uint32_t tb = a_tile0 + (uint32_t)(2 * t) * head_bytes;
+          const uint32_t tb = a_tile0 + (uint32_t)(buf * tile_floats * 4) + (uint32_t)(2 * t) * head_bytes;
           if (to0 >= 0) {
-            if (2 * t < H) q_sts(tb + (uint32_t)to0, (acc[0][0] + acc[1][0]) + acc[2][0]);
-            if (2 * t + 1 < H) q_sts(tb + head_bytes + (uint32_t)to0, (acc[0][1] + acc[1][1]) + acc[2][1]);
+            if (2 * t < H) q_sts(tb + (uint32_t)to0, res[0]);
+            if (2 * t + 1 < H) q_sts(tb + head_bytes + (uint32_t)to0, res[1]);
           }
           if (to1 >= 0) {
-            if (2 * t < H) q_sts(tb + (uint32_t)to1, (acc[0][2] + acc[1][2]) + acc[2][2]);
-            if (2 * t + 1 < H) q_sts(tb + head_bytes + (uint32_t)to1, (acc[0][3] + acc[1][3]) + acc[2][3]);
+            if (2 * t < H) q_sts(tb + (uint32_t)to1, res[2]);
+            if (2 * t + 1 < H) q_sts(tb + head_bytes + (uint32_t)to1, res[3]);
           }
         }
         const long long tl1 = clock64();
@@ -251,68 +250,31 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
         if (p.bulk_ok && tid == 0 && k + 2 < total_chunks) issue(k + 2);
       }
       if (p.edge_terms && !p.terms_in && NS == kEdgeTermNS) {
-        // keep the edge terms for the backward (6 floats per edge instead of the Fe-wide rows); every scatter is behind a bar_a
-        float4* dst = reinterpret_cast<float4*>(p.edge_terms + (size_t)b * tile_floats);
-        const float4* src = reinterpret_cast<const float4*>(tile);
-        for (int idx = tid; idx < tile_floats / 4; idx += kGA) dst[idx] = src[idx];
-      }
-      // s | d columns of this graph: fp16 pair tile -> packed fp32 [N][2H]
-      wait_id_t(&sd_full[buf], (it >> 1) & 1, 3, it, w_sd);
-      const long long tc0 = clock64();
-      {
-        const unsigned char* sl = smem_raw + pl.off_sdslot + buf * kSlotBytes;
-        for (int idx = tid; idx < sd_floats; idx += kGA) {
-          const int j = idx / (2 * H), kk = idx - j * 2 * H;
-          const uint32_t off = sw64(j, kk >> 3) + (uint32_t)(kk & 7) * 2u;
-          float v = __half2float(*reinterpret_cast<const __half*>(sl + off));
-          if (!SINGLE) v += __half2float(*reinterpret_cast<const __half*>(sl + 2048 + off));
-          sd[idx] = v * inv_sd;
+        // keep the edge terms for the backward (6 floats per edge instead of the Fe-wide rows): ONE bulk store of the tile
+        // by the copy engine (a thread-by-thread copy sat in the LSU queue for ~12 K cycles per graph).  The generic-proxy
+        // scatters are fenced and behind a barrier; thread 0 holds its arrival on tile_full until the engine has read
+        // the tile, because the softmax group rewrites it in place.
+        const long long to0 = clock64();
+        fence_proxy_async();
+        bar_a();
+        if (tid == 0) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.edge_terms + (size_t)b * tile_floats),
+                       "r"(smem_u32(tile)), "r"((uint32_t)tile_floats * 4u)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
+        t_out += clock64() - to0;
       }
-      bar_a();
-      if (tid == 0) arrive(&sd_empty[buf]);
-      const long long ts0 = clock64();
-      t_cnv += ts0 - tc0;
-      softmax_phase(p, AttnSmem{NS, pl.KS, 1, pl.chunk_rows, 0, 0, 0, 0, 0, 0, 0, 0}, tile, sd, out_scale,
-                    args.alpha_out ? args.alpha_out + (size_t)b * H * N * N : nullptr, nullptr, tid, kGA, -1, 0, nullptr, b);
-      bar_a();                                             // alpha tile complete
-      t_smx += clock64() - ts0;
-      // alpha[h][j][i] fp32 -> fp16 hi | lo tiles [h][i][j] (64-byte rows, swizzled): the A operand of the aggregation,
-      // double buffered against group B
-      wait_id_t(&ap_empty[buf], ((it >> 1) & 1) ^ 1, 4, it, w_ape);
-      const long long tc1 = clock64();
-      {
-        unsigned char* ahi = smem_raw + pl.off_ahi + (uint32_t)buf * 2u * ap_bytes;
-        unsigned char* alo = ahi + ap_bytes;
-        const int njp = (N + 1) / 2;
-        for (int idx = tid; idx < H * njp * N; idx += kGA) {
-          const int i = idx % N, r = idx / N, jp = r % njp, h = r / njp;
-          const float* base = tile + (size_t)h * N * NS + i;
-          const float y0 = base[(2 * jp) * NS] * pl.s_alpha;
-          const float y1 = (2 * jp + 1 < N) ? base[(2 * jp + 1) * NS] * pl.s_alpha : 0.f;
-          const __half2 hh = __floats2half2_rn(y0, y1);
-          const uint32_t off = (uint32_t)h * 2048u + sw64(i, jp >> 2) + (uint32_t)(jp & 3) * 4u;
-          *reinterpret_cast<__half2*>(ahi + off) = hh;
-          if (!SINGLE) {
-            const float2 bk = __half22float2(hh);
-            *reinterpret_cast<__half2*>(alo + off) = __floats2half2_rn(y0 - bk.x, y1 - bk.y);
-          }
-        }
-      }
-      if (p.terms_in) fence_proxy_async();               // generic-proxy accesses to the tile precede the next bulk copy into it
-      arrive(&ap_full[buf]);                               // release: this graph's coefficients are visible to group B
-      bar_a();                                             // everyone is done with the tile before the next graph's terms land
-      t_cnv += clock64() - tc1;
+      arrive(&tile_full[buf]);
     }
     if (tid == 0) {
       atomicAdd(&g_fwd16_counters[0], (unsigned long long)w_ring);
-      atomicAdd(&g_fwd16_counters[1], (unsigned long long)w_ape);
+      atomicAdd(&g_fwd16_counters[1], (unsigned long long)w_te);
       atomicAdd(&g_fwd16_counters[5], (unsigned long long)(clock64() - t_role));
       atomicAdd(&g_fwd16_counters[8], (unsigned long long)t_log);
-      atomicAdd(&g_fwd16_counters[9], (unsigned long long)t_smx);
-      atomicAdd(&g_fwd16_counters[10], (unsigned long long)t_cnv);
-      atomicAdd(&g_fwd16_counters[11], (unsigned long long)w_sd);
       atomicAdd(&g_fwd16_counters[12], (unsigned long long)t_bar);
+      atomicAdd(&g_fwd16_counters[13], (unsigned long long)t_out);
     }
   } else if (tid < kGA + kGB) {
     // ================================ group B: softmax + aggregation ================================
@@ -320,7 +282,7 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
     const int wb = tb_ >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const uint32_t sbase = smem_u32(smem_raw);
-    const uint32_t a_slots = sbase + pl.off_slots;
+    const uint32_t a_slots = sbase + pl.off_slots, a_ahi = sbase + pl.off_ahi, a_alo = sbase + pl.off_alo;
     // ldmatrix lane roles (identical for the alpha A fragments and the P B fragments): matrix = lane >> 3,
     // row = (lane & 7) + 8 * (matrix & 1), 16-byte chunk = matrix >> 1
     const int lm_row = (lane & 7) + ((lane >> 3) & 1) * 8, lm_chunk = lane >> 4;
@@ -329,15 +291,60 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
     for (int rb = 0; rb < 2; ++rb)
 #pragma unroll
       for (int cp = 0; cp < 2; ++cp) lm_off[rb][cp] = sw64(16 * rb + lm_row, 2 * cp + lm_chunk);
+    const float out_scale = p.concat ? 1.f : 1.f / (float)H;
+    const float inv_sd = p.p_blk[3];
     const float k_out = p.p_blk[2] / pl.s_alpha;          // accumulator -> out
     uint32_t q_base = 0;
-    long long w_apf = 0, w_pf = 0;
+    long long w_tf = 0, w_pf = 0, w_sd = 0, t_smx = 0, t_cnv = 0;
     const long long t_role = clock64();
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
       const int buf = it & 1;
-      const uint32_t a_ahi = sbase + pl.off_ahi + (uint32_t)buf * 2u * ap_bytes, a_alo = a_ahi + ap_bytes;
-      wait_id_t(&ap_full[buf], (it >> 1) & 1, 9, it, w_apf);
+      float* tile = tile0 + buf * tile_floats;
+      float* sd = sd0 + buf * sd_floats;
+      wait_id_t(&sd_full[buf], (it >> 1) & 1, 3, it, w_sd);
+      const long long tc0 = clock64();
+      {   // s|d columns: fp16 pair tile -> packed fp32 [N][2H]
+        const unsigned char* sl = smem_raw + pl.off_sdslot + buf * kSlotBytes;
+        for (int idx = tb_; idx < sd_floats; idx += kGB) {
+          const int j = idx / (2 * H), k = idx - j * 2 * H;
+          const uint32_t off = sw64(j, k >> 3) + (uint32_t)(k & 7) * 2u;
+          float v = __half2float(*reinterpret_cast<const __half*>(sl + off));
+          if (!SINGLE) v += __half2float(*reinterpret_cast<const __half*>(sl + 2048 + off));
+          sd[idx] = v * inv_sd;
+        }
+      }
+      const long long tc1 = clock64();
+      wait_id_t(&tile_full[buf], (it >> 1) & 1, 4, it, w_tf);
+      const long long ts0 = clock64();
+      bar_b();                                           // sd complete (and everyone is past the previous graph's MMAs)
+      if (tb_ == 0) arrive(&sd_empty[buf]);
+      softmax_phase(p, AttnSmem{NS, pl.KS, 1, pl.chunk_rows, 0, 0, 0, 0, 0, 0, 0, 0}, tile, sd, out_scale,
+                    args.alpha_out ? args.alpha_out + (size_t)b * H * N * N : nullptr, nullptr, tb_, kGB, -1, 0, nullptr, b);
+      bar_b();                                           // alpha tile complete
+      const long long tc2 = clock64();
+      t_smx += tc2 - ts0;
+      // alpha[h][j][i] fp32 -> fp16 hi | lo tiles [h][i][j] (64-byte rows, swizzled): the A operand of the aggregation
+      {
+        const int njp = (N + 1) / 2;
+        for (int idx = tb_; idx < H * njp * N; idx += kGB) {
+          const int i = idx % N, r = idx / N, jp = r % njp, h = r / njp;
+          const float* base = tile + (size_t)h * N * NS + i;
+          const float y0 = base[(2 * jp) * NS] * pl.s_alpha;
+          const float y1 = (2 * jp + 1 < N) ? base[(2 * jp + 1) * NS] * pl.s_alpha : 0.f;
+          const __half2 hh = __floats2half2_rn(y0, y1);
+          const uint32_t off = (uint32_t)h * 2048u + sw64(i, jp >> 2) + (uint32_t)(jp & 3) * 4u;
+          *reinterpret_cast<__half2*>(smem_raw + pl.off_ahi + off) = hh;
+          if (!SINGLE) {
+            const float2 bk = __half22float2(hh);
+            *reinterpret_cast<__half2*>(smem_raw + pl.off_alo + off) = __floats2half2_rn(y0 - bk.x, y1 - bk.y);
+          }
+        }
+      }
+      if (p.terms_in) fence_proxy_async();               // generic-proxy writes to the tile precede the next bulk copy into it
+      arrive(&tile_empty[buf]);                          // the fp32 tile is free for the logit group
+      bar_b();                                           // alpha pair tiles complete
+      t_cnv += (tc1 - tc0) + (clock64() - tc2);
       for (int pass = 0; pass < n_pass; ++pass) {
         const int G = min(kCbPass, n_cb - pass * kCbPass);
         const bool mine = wb < G;
@@ -351,6 +358,18 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
 #pragma unroll
               for (int e = 0; e < 4; ++e) cmain[m][n][e] = ccorr[m][n][e] = 0.f;
         };
+        // the bias of this warp's 8 output columns, fetched BEFORE the MMAs that produce them (a load per stored element
+        // inside store() cost 12 % of the kernel's samples in long-scoreboard stalls)
+        float bv[4][2];
+        auto load_bias = [&](int col0) {
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = cb * 32 + n * 8 + 2 * t + e;
+              bv[n][e] = (args.bias && mine && c < C) ? __ldg(args.bias + col0 + c) : 0.f;
+            }
+        };
         auto store = [&](int col0) {
 #pragma unroll
           for (int m = 0; m < 2; ++m)
@@ -362,9 +381,9 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
                 if (i < N && c < C) {
                   const int col = col0 + c;
                   float* dst = args.out + ((size_t)b * N + i) * p.ldo + col;
-                  const float o0 = (cmain[m][n][2 * hf] + ccorr[m][n][2 * hf]) * k_out + (args.bias ? args.bias[col] : 0.f);
+                  const float o0 = (cmain[m][n][2 * hf] + ccorr[m][n][2 * hf]) * k_out + bv[n][0];
                   if (c + 1 < C) {
-                    const float o1 = (cmain[m][n][2 * hf + 1] + ccorr[m][n][2 * hf + 1]) * k_out + (args.bias ? args.bias[col + 1] : 0.f);
+                    const float o1 = (cmain[m][n][2 * hf + 1] + ccorr[m][n][2 * hf + 1]) * k_out + bv[n][1];
                     if (p.vec2_ok) *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
                     else { dst[0] = o0; dst[1] = o1; }
                   } else {
@@ -374,10 +393,12 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
               }
         };
         clear();
+        if (!p.concat) load_bias(0);
         const int n_g = (G + grp - 1) / grp;               // tile groups (ring slots) of one (pass, head) step
         const int gi = wb / grp, ti = wb - gi * grp;       // this warp's group and its tile inside it
         for (int h = 0; h < H; ++h, q_base += n_g) {
           if (gi >= n_g) continue;
+          if (p.concat) load_bias(h * C);
           uint32_t ah[2][2][4], al[2][2][4];
           if (mine) {
 #pragma unroll
@@ -432,13 +453,14 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
         }
         if (!p.concat && mine) store(0);
       }
-      __syncwarp();
-      if (lane == 0) arrive(&ap_empty[buf]);               // this warp has taken its last fragment of the alpha pair buffer
     }
     if (tid == kGA) {
-      atomicAdd(&g_fwd16_counters[2], (unsigned long long)w_apf);
+      atomicAdd(&g_fwd16_counters[2], (unsigned long long)w_tf);
       atomicAdd(&g_fwd16_counters[3], (unsigned long long)w_pf);
       atomicAdd(&g_fwd16_counters[6], (unsigned long long)(clock64() - t_role));
+      atomicAdd(&g_fwd16_counters[9], (unsigned long long)t_smx);
+      atomicAdd(&g_fwd16_counters[10], (unsigned long long)t_cnv);
+      atomicAdd(&g_fwd16_counters[11], (unsigned long long)w_sd);
     }
   } else {
     // ================================ producer warp ================================
@@ -513,11 +535,11 @@ int attn_fwd16_dispatch(const AttnFwdArgs& a, cudaStream_t st) {
     pl.off_bar = (uint32_t)o;    o += 512;
     pl.off_table = (uint32_t)o;  o += round_up((size_t)(p.R > 0 ? p.R : 1) * 4, 16);
     pl.off_vfrag = (uint32_t)o;  o += (size_t)(p.Fe > 0 ? pl.KS : 0) * 32 * 16;
-    pl.off_sd = (uint32_t)o;     o += sd_bytes;
-    pl.off_tile = (uint32_t)o;   o += tile_bytes;
+    pl.off_sd = (uint32_t)o;     o += 2 * sd_bytes;
+    pl.off_tile = (uint32_t)o;   o += 2 * tile_bytes;
     o = round_up(o, 128);
-    pl.off_ahi = (uint32_t)o;    o += 4 * (size_t)p.H * 2048;              // two buffers x (hi | lo)
-    pl.off_alo = pl.off_ahi;
+    pl.off_ahi = (uint32_t)o;    o += (size_t)p.H * 2048;
+    pl.off_alo = (uint32_t)o;    o += (size_t)p.H * 2048;
     pl.off_ring = (uint32_t)o;
     pl.ring_stage = (uint32_t)round_up((size_t)rows * p.Fe * 4, 128);
     o += (p.Fe > 0 && !p.terms_in) ? 2 * (size_t)pl.ring_stage + 256 : 0;     // + zero pad behind the ring (k-steps past Fe)

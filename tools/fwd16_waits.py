@@ -4,8 +4,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 dev = torch.device("cuda", 0)
-names = ["A: edge ring wait", "A: alpha buffer free", "B: alpha buffer ready", "B: P tiles", "P: slot free", "A total", "B total", "P total",
-         "A: logits arithmetic", "A: softmax", "A: conversions", "A: s|d tile wait", "A: chunk barriers"]
+names = ["A: edge ring wait", "A: tile buffer free", "B: edge terms ready", "B: P tiles", "P: slot free", "A total", "B total", "P total",
+         "A: logits arithmetic", "B: softmax", "B: conversions", "B: s|d tile wait", "A: chunk barriers", "A: edge-term copy-out"]
 for structured in (False, True):
     hp = bench.HotPath(4096, dev, 1234, structured=structured)
     buf = (C.c_ulonglong * 32)()
