@@ -204,6 +204,7 @@ class HotPath:
         self.P_aug = (torch.empty(2, n, self.lib.spotv2_gat_ld16(n_aug), device=device, dtype=torch.float16) if self.pair
                       else torch.empty(n, self.desc.ldp, **f32))
         self.p_amax = torch.empty(8, **f32)
+        self.sd32 = torch.empty(n, 2 * H, **f32) if self.pair else None
         et = C.c_size_t()
         _lib.check(self.lib.spotv2_gat_edge_terms_bytes(C.byref(self.desc), C.byref(et)), "edge_terms_bytes")
         self.edge_terms = torch.empty(et.value // 4, **f32)       # <e_ij, v_h>: written by attn_fwd, read by attn_bwd
@@ -268,7 +269,7 @@ class HotPath:
                                      p(self.x_blk), st), "split_f16")
         if self.pair:
             chk(lib.spotv2_proj_fwd_pair(d, p(xh), p(xl), p(self.x_blk), p(self.W_aug), p(self.P_aug[0]), p(self.P_aug[1]),
-                                         p(self.p_amax), p(self.ws), self.ws.numel(), st), "proj_fwd_pair")
+                                         p(self.p_amax), p(self.sd32), p(self.ws), self.ws.numel(), st), "proj_fwd_pair")
         else:
             chk(lib.spotv2_proj_fwd(d, p(self.batch.x), p(xh), p(xl), p(self.x_blk), p(self.W_aug), p(self.P_aug), p(self.p_amax),
                                     p(self.ws), self.ws.numel(), st), "proj_fwd")
@@ -282,10 +283,10 @@ class HotPath:
         ea = None if self.structured else self.batch.edge_attr
         tbl = None if self.structured else self.batch.spot_topology.table
         if self.pair:
-            chk(lib.spotv2_gat_attn_fwd_pair(d, p(self.P_aug[0]), p(self.P_aug[1]), p(self.p_amax), p(ea), p(tbl), p(self.v),
+            chk(lib.spotv2_gat_attn_fwd_pair(d, p(self.P_aug[0]), p(self.P_aug[1]), p(self.p_amax), p(self.sd32), p(ea), p(tbl), p(self.v),
                                              p(L.bias), p(self.out), None, p(self.edge_terms), st), "attn_fwd_pair")
             mark("attn_fwd")
-            chk(lib.spotv2_gat_attn_bwd_pair(d, p(self.P_aug[0]), p(self.P_aug[1]), p(self.p_amax), p(ea), p(self.edge_terms),
+            chk(lib.spotv2_gat_attn_bwd_pair(d, p(self.P_aug[0]), p(self.P_aug[1]), p(self.p_amax), p(self.sd32), p(ea), p(self.edge_terms),
                                              p(tbl), p(self.v), p(self.dout), p(ph), p(pl), p(self.dp_blk),
                                              None if self.structured else p(self.dv), p(self.d_edge_terms),
                                              p(self.g_b), p(self.ws), self.ws.numel(), st), "attn_bwd_pair")

@@ -205,19 +205,21 @@ int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug, const floa
  * Same operators as spotv2_proj_fwd / spotv2_gat_attn_fwd / spotv2_gat_attn_bwd ([PyG] F.linear, edge_update,
  * softmax, propagate and their autograd), different intermediate: P_hi / P_lo are [B*N, ld16(n_aug)] fp16 planes
  * (P_lo may be null with gemm_algo 3), p_scale an 8-float scale block ({bound bits x2, inverse scales x2, scales x2}:
- * group 0 the H*Cp projection columns, group 1 the s|d columns) written by proj_fwd_pair and read by the other two.
+ * group 0 the H*Cp projection columns, group 1 the s|d columns) written by proj_fwd_pair and read by the other two;
+ * sd [B*N, 2H] fp32 receives the logit terms s | d as the GEMM accumulated them (the attention kernels read these, not the
+ * planes' s|d columns: the LeakyReLU kinks of the logits must not depend on the pair's 22-bit rounding).
  * x must be given as a pair (x_hi, x_lo, x_scale; spotv2_split_f16 or spotv2_collate_windows_pair): the bound needs
  * max|x|, which the scale block holds.  W_aug is spotv2_gat_fold's output for the same descriptor ([n_aug, F]).
  * attn_bwd_pair emits dP as the pair [B*N, ld16(n_aug)] in the padded layout (pad columns zero), consumed by
  * spotv2_proj_bwd_weight / spotv2_proj_bwd_input with the same descriptor. */
 int spotv2_proj_fwd_pair(const spotv2_gat_desc* d, const void* x_hi, const void* x_lo, const float* x_scale,
-                         const float* W_aug, void* P_hi, void* P_lo_or_null, float* p_scale, void* ws, size_t ws_bytes,
-                         void* stream);
+                         const float* W_aug, void* P_hi, void* P_lo_or_null, float* p_scale, float* sd, void* ws,
+                         size_t ws_bytes, void* stream);
 int spotv2_gat_attn_fwd_pair(const spotv2_gat_desc* d, const void* P_hi, const void* P_lo_or_null, const float* p_scale,
-                             const float* edge_rows, const int32_t* table, const float* v, const float* bias_or_null,
+                             const float* sd, const float* edge_rows, const int32_t* table, const float* v, const float* bias_or_null,
                              float* out, float* alpha_or_null, float* edge_terms_or_null, void* stream);
 int spotv2_gat_attn_bwd_pair(const spotv2_gat_desc* d, const void* P_hi, const void* P_lo_or_null, const float* p_scale,
-                             const float* edge_rows, const float* edge_terms_or_null, const int32_t* table,
+                             const float* sd, const float* edge_rows, const float* edge_terms_or_null, const int32_t* table,
                              const float* v, const float* dout, void* dP_hi, void* dP_lo_or_null, float* dp_scale,
                              float* dv_or_null, float* d_edge_terms_or_null, float* dbias_or_null, void* ws,
                              size_t ws_bytes, void* stream);
@@ -288,6 +290,14 @@ int spotv2_collate_windows_pair(const float* M_vol, const float* M_vv, int32_t T
 int spotv2_diag_gemm(int a_kc, int b_kc, int M, int N, int K, const float* A, int lda, const float* B,
                      int ldb, float* C, int ldc, int algo, int splits, int bn, int kb_per_chunk,
                      void* ws, size_t ws_bytes, void* stream);
+
+/* The operand preparation spotv2_gat_attn_bwd_pair runs on dout (csrc/attn_prep.cu), exposed for the parity tests:
+ * dout [B*N, upg*C] fp32 -> hi | lo [B*N, ld16] fp16 with one power-of-two scale per unit (upg = 1: a graph; upg = H: a
+ * (graph, head) block of a concat layer), scales [B*upg], scale_block[0] = bit pattern of max|dout|, dbias [upg*C] column
+ * sums (null: skipped).  ws: at least spotv2_diag_dout_pair_ws_bytes(B, C, upg) bytes. */
+size_t spotv2_diag_dout_pair_ws_bytes(int32_t B, int32_t C, int32_t upg);
+int spotv2_diag_dout_pair(const float* dout, int32_t B, int32_t N, int32_t C, int32_t upg, void* hi, void* lo_or_null,
+                          int32_t ld16, float* scales, float* scale_block, float* dbias_or_null, void* ws, void* stream);
 
 /* Copies (and optionally resets) 32 device-side cycle counters.  [0,16): forward kernel, cycles one
  * sampling thread per role spent parked on the edge ring, alpha-tile empty/full, P-tile full/empty, then

@@ -38,9 +38,9 @@ SIGNATURES = {
     "spotv2_gat_n_aug": (_i32, [_DP]),
     "spotv2_gat_head_pitch": (_i32, [_DP]),
     "spotv2_gat_workspace_bytes": (C.c_int, [_DP, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
-    "spotv2_proj_fwd_pair": (C.c_int, [_DP] + [_vp] * 8 + [_sz, _vp]),
-    "spotv2_gat_attn_fwd_pair": (C.c_int, [_DP] + [_vp] * 11),
-    "spotv2_gat_attn_bwd_pair": (C.c_int, [_DP] + [_vp] * 15 + [_sz, _vp]),
+    "spotv2_proj_fwd_pair": (C.c_int, [_DP] + [_vp] * 9 + [_sz, _vp]),
+    "spotv2_gat_attn_fwd_pair": (C.c_int, [_DP] + [_vp] * 12),
+    "spotv2_gat_attn_bwd_pair": (C.c_int, [_DP] + [_vp] * 16 + [_sz, _vp]),
     "spotv2_edge_table_build": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
     "spotv2_edge_table_dense": (C.c_int, [_i32, _vp, _vp]),
     "spotv2_gat_fold": (C.c_int, [_DP] + [_vp] * 8),
@@ -63,6 +63,8 @@ SIGNATURES = {
     "spotv2_collate_windows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "spotv2_stack_scale": (C.c_int, [_vp, _i64, _vp, _vp]),
     "spotv2_collate_windows_pair": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "spotv2_diag_dout_pair_ws_bytes": (_sz, [_i32, _i32, _i32]),
+    "spotv2_diag_dout_pair": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "spotv2_diag_counters": (C.c_int, [_vp, C.c_int]),
     "spotv2_diag_weight_grad_splits": (_i32, [_i32, _i32, _i32]),
     "spotv2_diag_gemm": (C.c_int, [C.c_int] * 5 + [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int] + [C.c_int] * 4 + [_vp, _sz, _vp]),

@@ -18,7 +18,7 @@ CSRC = PKG / "csrc"
 OBJ = PKG / "_build"
 LIB = PKG / "libspotv2_gat.so"
 
-SOURCES = ["api.cu", "fold.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_f16.cu", "proj.cu", "attn_fwd.cu", "attn_fwd16.cu", "attn_bwd.cu", "attn_bwd2.cu", "attn_bwd3.cu", "attn_large.cu", "windows.cu"]
+SOURCES = ["api.cu", "fold.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_f16.cu", "proj.cu", "attn_fwd.cu", "attn_fwd16.cu", "attn_prep.cu", "attn_bwd.cu", "attn_bwd2.cu", "attn_bwd3.cu", "attn_large.cu", "windows.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",

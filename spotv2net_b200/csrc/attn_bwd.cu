@@ -646,10 +646,18 @@ size_t attn_bwd_partials_bytes(const spotv2_gat_desc* d) {
   if (attn_bwd3_partials_bytes(d) > piped) piped = attn_bwd3_partials_bytes(d);
   return legacy > piped ? legacy : piped;
 }
+// p_format 1: dout's operand pair (2 planes [B*N, ld16(ldo)]) | unit scales | the prepass's dbias partials
+static size_t attn_bwd_pair_extra_bytes(const spotv2_gat_desc* d) {
+  if (d->p_format != 1) return 0;
+  const size_t rows = (size_t)d->B * d->N, ldo = d->concat ? (size_t)d->H * d->C : (size_t)d->C;
+  const int upg = d->concat ? d->H : 1;
+  return 2 * round_up(rows * ld16_of((int)ldo) * 2, 256) + round_up((size_t)d->B * upg * sizeof(float), 256) +
+         round_up((size_t)dout_pair_grid(d->B * upg, upg) * ldo * sizeof(float), 256);
+}
 size_t attn_bwd_ws_bytes(const spotv2_gat_desc* d) {
   if (attn_large_applies(d)) return attn_large_bwd_ws_bytes(d);
-  // partials | ds,dd in fp32 [B*N, 2H] | two scale blocks
-  return attn_bwd_partials_bytes(d) + round_up((size_t)d->B * d->N * 2 * d->H * sizeof(float), 256) + 256;
+  // partials | ds,dd in fp32 [B*N, 2H] | two scale blocks | (p_format 1) the dout pair and its by-products
+  return attn_bwd_partials_bytes(d) + round_up((size_t)d->B * d->N * 2 * d->H * sizeof(float), 256) + 256 + attn_bwd_pair_extra_bytes(d);
 }
 
 template <int NPAIRS>
@@ -814,14 +822,14 @@ extern "C" int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug,
 
 // p_format 1: same operator, P as the fp16 operand pair, dP emitted in the padded head pitch (attn_bwd2.cu, P16 instantiations)
 extern "C" int spotv2_gat_attn_bwd_pair(const spotv2_gat_desc* d, const void* P_hi, const void* P_lo_or_null, const float* p_scale,
-                                        const float* edge_rows, const float* edge_terms_or_null, const int32_t* table,
+                                        const float* sd, const float* edge_rows, const float* edge_terms_or_null, const int32_t* table,
                                         const float* v, const float* dout, void* dP_hi, void* dP_lo_or_null, float* dp_scale,
                                         float* dv_or_null, float* d_edge_terms_or_null, float* dbias_or_null, void* ws,
                                         size_t ws_bytes, void* stream) {
   if (int rc = check_desc(d)) return rc;
   SPOTV2_REQUIRE(d->p_format == 1, "attn_bwd_pair: the descriptor must say p_format 1");
   const bool single = d->gemm_algo == 3;
-  SPOTV2_REQUIRE(P_hi && p_scale && dout && dP_hi && dp_scale, "attn_bwd_pair: P_hi, p_scale, dout, dP_hi and dp_scale must be non-null");
+  SPOTV2_REQUIRE(P_hi && p_scale && sd && dout && dP_hi && dp_scale, "attn_bwd_pair: P_hi, p_scale, sd, dout, dP_hi and dp_scale must be non-null");
   SPOTV2_REQUIRE(single || (P_lo_or_null && dP_lo_or_null), "attn_bwd_pair: the lo planes may be omitted with gemm_algo 3 only");
   const bool structured = d->edge_mode == 1 && d->Fe > 0;
   SPOTV2_REQUIRE(d->Fe == 0 || structured || (edge_rows && table && v), "attn_bwd_pair: edge_rows, table and v are required when Fe > 0");
@@ -846,6 +854,7 @@ extern "C" int spotv2_gat_attn_bwd_pair(const spotv2_gat_desc* d, const void* P_
   a.p.P_hi = static_cast<const __half*>(P_hi);
   a.p.P_lo = single ? nullptr : static_cast<const __half*>(P_lo_or_null);
   a.p.p_blk = p_scale;
+  a.p.sd32 = sd;
   a.p.hp = head_pitch_of(d);
   a.p.ldp16 = ld16_of(n_aug_of(d));
   a.p.bulk_ok = d->Fe > 0 && aligned16(edge_rows) && ((size_t)d->R * d->Fe) % 4 == 0;
@@ -865,7 +874,19 @@ extern "C" int spotv2_gat_attn_bwd_pair(const spotv2_gat_desc* d, const void* P_
   unsigned char* w = static_cast<unsigned char*>(ws);
   float* blk_dout = reinterpret_cast<float*>(w + part + round_up(rows * 2 * d->H * sizeof(float), 256));
   a.dout_blk = blk_dout;
-  if (int rc = amax_flat(dout, rows * (size_t)a.p.ldo, blk_dout, st)) return rc;
+  // dout -> operand pair, unit scales, max|dout|, dbias: one pass (attn_prep.cu)
+  {
+    const int upg = d->concat ? d->H : 1;
+    const int ldo16 = ld16_of(a.p.ldo);
+    const size_t plane = round_up(rows * (size_t)ldo16 * 2, 256);
+    unsigned char* x = reinterpret_cast<unsigned char*>(blk_dout) + 256;
+    __half* dhi = reinterpret_cast<__half*>(x);
+    __half* dlo = single ? nullptr : reinterpret_cast<__half*>(x + plane);
+    float* scales = reinterpret_cast<float*>(x + 2 * plane);
+    float* bpart = reinterpret_cast<float*>(x + 2 * plane + round_up((size_t)d->B * upg * sizeof(float), 256));
+    if (int rc = dout_pair_prepass(dout, d->B, d->N, d->C, upg, dhi, dlo, ldo16, scales, blk_dout, dbias_or_null, bpart, st)) return rc;
+    a.dO_hi = dhi; a.dO_lo = dlo; a.dO_scale = scales; a.ldo16 = ldo16; a.units_per_graph = upg;
+  }
   a.dsd = reinterpret_cast<float*>(w + part);
   a.bound = (float)d->N * (d->concat ? 1.f : 1.f / (float)d->H) * a.p.drop.scale;
   SPOTV2_CUDA_OK(cudaMemsetAsync(dp_scale, 0, kScaleBlockFloats * sizeof(float), st));

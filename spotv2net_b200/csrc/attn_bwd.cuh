@@ -54,7 +54,16 @@ struct AttnBwdArgs {
   float* dp_blk;       // receives inverse scale [2] and scale [4] of the dP group
   float* dv_part;      // [grid][H*Fe]
   float* dbias_part;   // [grid][ldo]
+  // p_format 1: dout as an fp16 operand pair made by dout_pair_prepass (attn_prep.cu): planes [B*N, ldo16], one power-of-two
+  // scale per unit (graph, or (graph, head) for concat layers: units_per_graph = H); the kernel then forms no dbias.
+  const __half* dO_hi = nullptr;
+  const __half* dO_lo = nullptr;
+  const float* dO_scale = nullptr;
+  int ldo16 = 0, units_per_graph = 1;
 };
+int dout_pair_grid(int n_units, int upg);
+int dout_pair_prepass(const float* dout, int B, int N, int C, int upg, __half* hi, __half* lo, int ld16, float* scales, float* blk,
+                      float* dbias, float* dbias_part, cudaStream_t st);
 
 __device__ __forceinline__ float dp_scale_from_amax(float amax) {   // same rule as gemm_f16.cu
   if (!(amax > 0.f) || !(amax < INFINITY)) return 1.f;

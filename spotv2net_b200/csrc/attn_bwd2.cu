@@ -45,6 +45,7 @@ __device__ unsigned long long g_bwd2_counters[kNumCounters];
 struct Bwd2Plan {
   int KS, chunk_rows, nchunks, n_cb, hpr, n_rounds, n_mt_chunk, ksplit;
   int n_mtiles, dv_rg, dv_rpu, dv_units, cbs_per_grp_d, tma_ok, n_slots;
+  int hb;      // p_format 1: heads per TMA box of a phase-A slot (min(hpr, H))
   uint32_t off_bar, off_table, off_vfrag, off_sd, off_mask, off_dspart, off_dbias, off_tile, off_D, off_slots,
       slot_bytes, total;
 };
@@ -61,6 +62,7 @@ Bwd2Plan make_plan(const AttnParams& p) {
   const int nh_max = H < s.hpr ? H : s.hpr;
   s.cbs_per_grp_d = p.concat ? (kGrpTiles / nh_max > 0 ? kGrpTiles / nh_max : 1) : kGrpTiles;
   s.tma_ok = (C % 4 == 0) ? 1 : 0;
+  s.hb = nh_max;
   uint32_t o = 0;
   s.off_bar = o;    o += 128;
   s.off_table = o;  o += (uint32_t)round_up((size_t)(p.R > 0 ? p.R : 1) * 4, 16);
@@ -229,9 +231,13 @@ bool plan_is_fixed_geom(const AttnParams& p, const Bwd2Plan& s) {
 
 // DROP: attention dropout in training mode (the mask is regenerated from the descriptor's Philox key, see attn_common.cuh);
 // a separate instantiation so that the default path carries none of it.
-// P16: p_format 1 - P arrives as the fp16 operand pair (hi | lo halves of each 4 KB tile slot, 64B swizzle): phase A takes
-// its B fragments with ldmatrix and converts nothing of P; dP leaves in the padded head pitch.  SINGLE (with P16): the
-// half-precision class - hi planes only, one product per MMA step.
+// P16: p_format 1 - P AND dout arrive as fp16 operand pairs (32 x 32 tiles of 64-byte rows, 64B swizzle; P from the GEMM
+// epilogue, dout from dout_pair_prepass with one scale per graph | (graph, head)): every MMA operand fragment of phases A
+// and D comes out of ldmatrix, nothing is converted in registers, no tail masks (the head-aware tensor maps zero-fill
+// columns past a head's C), one TMA load per phase-A slot part (all heads of a channel block in one box); the bias gradient
+// comes from the prepass; dP leaves in the padded head pitch.  SINGLE (with P16): the half-precision class - hi planes only,
+// one product per MMA step.  In P16 tmP = P seen head by head (box: hb heads), tmG = dout pair (box: one head),
+// tmPl = dout pair (box: hb heads; concat layers' phase A).
 template <bool FIX, bool DROP, bool P16, bool SINGLE>
 __global__ void __launch_bounds__(kB2Threads, 1)
 gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_constant__ CUtensorMap tmP,
@@ -303,14 +309,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
 
   if (warp == kW) {
     // =========================================== producer ===========================================
-    if (lane == 0) { prefetch_tmap(&tmP); prefetch_tmap(&tmG); if (P16 && !SINGLE) prefetch_tmap(&tmPl); }
-    // p_format 1: a P tile slot holds the hi plane's 32 x 32 fp16 box in its first 2 KB and the lo plane's in the second
-    auto put_p16 = [&](unsigned char* dst, int col0, int row0, uint64_t* full) {
-      if (lane == 0) {
-        tma_load_2d_hint(dst, &tmP, col0, row0, full, kEvictFirst);
-        if (!SINGLE) tma_load_2d_hint(dst + 2048, &tmPl, col0, row0, full, kEvictFirst);
-      }
-    };
+    if (lane == 0) { prefetch_tmap(&tmP); prefetch_tmap(&tmG); if (P16) prefetch_tmap(&tmPl); }
     const long long n_rows = (long long)p.B * N;
     // one tile: TMA, or (C % 4 != 0: tile starts are not 16-byte aligned) a cooperative gather into the
     // same swizzled layout
@@ -378,22 +377,28 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
         const int nh = min(pl.hpr, H - h0);
         for (int cb = 0; cb < n_cb; ++cb) {
           unsigned char* gb = acquire();
+          if (P16) {
+            // slot: [dout hi: hbd tiles][dout lo][P hi: hb tiles][P lo]   (hbd = hb for concat layers, 1 for the head mean)
+            const int hbd = p.concat ? pl.hb : 1;
+            const uint32_t planes = SINGLE ? 1u : 2u;
+            if (lane == 0) {
+              mbar_expect_tx(&full[slot], planes * (uint32_t)(hbd + pl.hb) * 2048u);
+              tma_load_4d_hint(gb, p.concat ? &tmPl : &tmG, cb * 32, b * N, p.concat ? h0 : 0, 0, &full[slot], kEvictFirst);
+              tma_load_4d_hint(gb + planes * (uint32_t)hbd * 2048u, &tmP, cb * 32, b * N, h0, 0, &full[slot], kEvictFirst);
+            }
+          } else {
           const int ntiles = p.concat ? 2 * nh : 1 + nh;
-          const uint32_t p_tile_bytes = (P16 && SINGLE) ? kTile / 2 : kTile;
-          if (pl.tma_ok && lane == 0)
-            mbar_expect_tx(&full[slot], (uint32_t)(ntiles - nh) * kTile + (uint32_t)nh * p_tile_bytes);
+          if (pl.tma_ok && lane == 0) mbar_expect_tx(&full[slot], (uint32_t)ntiles * kTile);
           if (p.concat) {
             for (int hl = 0; hl < nh; ++hl) {
               put_tile(gb + (2 * hl) * kTile, &tmG, args.dout, p.ldo, (h0 + hl) * C + cb * 32, b * N, &full[slot]);
-              if (P16) put_p16(gb + (2 * hl + 1) * kTile, (h0 + hl) * Cp + cb * 32, b * N, &full[slot]);
-              else put_tile(gb + (2 * hl + 1) * kTile, &tmP, p.P_aug, p.ldp, (h0 + hl) * C + cb * 32, b * N, &full[slot]);
+              put_tile(gb + (2 * hl + 1) * kTile, &tmP, p.P_aug, p.ldp, (h0 + hl) * C + cb * 32, b * N, &full[slot]);
             }
           } else {
             put_tile(gb, &tmG, args.dout, p.ldo, cb * 32, b * N, &full[slot]);
-            for (int hl = 0; hl < nh; ++hl) {
-              if (P16) put_p16(gb + (1 + hl) * kTile, (h0 + hl) * Cp + cb * 32, b * N, &full[slot]);
-              else put_tile(gb + (1 + hl) * kTile, &tmP, p.P_aug, p.ldp, (h0 + hl) * C + cb * 32, b * N, &full[slot]);
-            }
+            for (int hl = 0; hl < nh; ++hl)
+              put_tile(gb + (1 + hl) * kTile, &tmP, p.P_aug, p.ldp, (h0 + hl) * C + cb * 32, b * N, &full[slot]);
+          }
           }
           publish(pl.tma_ok != 0);
         }
@@ -407,6 +412,19 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
           const int cb0 = gi * pl.cbs_per_grp_d;
           const int ncb = min(pl.cbs_per_grp_d, n_cb - cb0);
           const int ntiles = p.concat ? ncb * nh : ncb;
+          if (P16) {      // a tile = [hi 2 KB][lo 2 KB] from one load of the pair's one-head box
+            if (lane == 0) {
+              mbar_expect_tx(&full[slot], (uint32_t)ntiles * (SINGLE ? 2048u : 4096u));
+              for (int k = 0; k < ncb; ++k) {
+                if (p.concat) {
+                  for (int hl = 0; hl < nh; ++hl)
+                    tma_load_4d_hint(gb + (k * nh + hl) * kTile, &tmG, (cb0 + k) * 32, b * N, h0 + hl, 0, &full[slot], kEvictFirst);
+                } else {
+                  tma_load_4d_hint(gb + k * kTile, &tmG, (cb0 + k) * 32, b * N, 0, 0, &full[slot], kEvictFirst);
+                }
+              }
+            }
+          } else {
           if (pl.tma_ok && lane == 0) mbar_expect_tx(&full[slot], (uint32_t)ntiles * kTile);
           for (int k = 0; k < ncb; ++k) {
             if (p.concat) {
@@ -415,6 +433,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
             } else {
               put_tile(gb + k * kTile, &tmG, args.dout, p.ldo, (cb0 + k) * 32, b * N, &full[slot]);
             }
+          }
           }
           publish(pl.tma_ok != 0);
         }
@@ -438,10 +457,11 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
   // fp16-pair operand scales of the two big products: dO and P from their tensors' maxima, alpha <= 1 fixed
   const float s_dO = dp_scale_from_amax(__uint_as_float(*reinterpret_cast<const unsigned*>(args.dout_blk)));
   const float s_P = P16 ? p.p_blk[4] : dp_scale_from_amax(__uint_as_float(*reinterpret_cast<const unsigned*>(args.p_amax)));
-  const float inv_sd = P16 ? p.p_blk[3] : 1.f;
   constexpr float s_al = 16384.f;
-  const float k_dalpha = g_scale / (s_dO * s_P);                 // accumulator -> dalpha
-  const float k_dp = g_scale * dp_scale / (s_al * s_dO) * (DROP ? p.drop.scale : 1.f);   // accumulator -> (scaled) dP
+  // (p_format 1: dout's pair carries one scale per graph | (graph, head): the two factors are rebuilt per unit)
+  const float k_dalpha0 = g_scale / s_P, k_dp0 = g_scale * dp_scale / s_al * (DROP ? p.drop.scale : 1.f);
+  float k_dalpha = k_dalpha0 / s_dO;                             // accumulator -> dalpha
+  float k_dp = k_dp0 / s_dO;                                     // accumulator -> (scaled) dP
   const bool vec4_out = (C % 4 == 0);     // 8-byte aligned groups of 4 fp16 columns (ldp16 % 8 == 0)
   AttnSmem asm_{};                        // what softmax_phase reads
   asm_.NS = NS; asm_.KS = pl.KS; asm_.NT = 1;
@@ -467,6 +487,13 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
   for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
     for (int np = 0; np < 2; ++np) lmB[ks][np] = sw64(16 * np + (lane & 7) + ((lane >> 4) & 1) * 8, 2 * ks + ((lane >> 3) & 1));
+  // operand fragments of a [row][col] fp16 tile with 16 rows per block: matrix = lane >> 3, row = (lane & 7) + 8 * (matrix & 1),
+  // chunk = matrix >> 1: A fragments (ldmatrix: rows = m, cols = k) and, transposed, B fragments of a [k][n] tile
+  uint32_t lmX[2][2];                 // [16-row block][chunk pair]
+#pragma unroll
+  for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+    for (int cp = 0; cp < 2; ++cp) lmX[rb][cp] = sw64(16 * rb + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * cp + (lane >> 4));
   // phase V units of this warp (feature tile, row group): fixed for the whole kernel
   int dv_mt[kMaxDvUnits], dv_rb[kMaxDvUnits];
   float dv_run[kMaxDvUnits][4];
@@ -521,10 +548,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
     for (int idx = tid; idx < N * 2 * H; idx += kCT) {
       const int j = idx / (2 * H), k = idx - j * 2 * H;
       if (P16) {
-        const size_t o = ((size_t)b * N + j) * p.ldp16 + HC + k;
-        float v = __half2float(p.P_hi[o]);
-        if (!SINGLE) v += __half2float(p.P_lo[o]);
-        sd[idx] = v * inv_sd;
+        sd[idx] = p.sd32[((size_t)b * N + j) * 2 * H + k];
       } else {
         sd[idx] = p.P_aug[((size_t)b * N + j) * p.ldp + HC + k];
       }
@@ -619,6 +643,10 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
       const int hl = warp >> 1, m = warp & 1;
       const bool active = (warp < 2 * nh) && (16 * m < N);
       const int h = h0 + hl;
+      if (P16) {
+        const float sdo = active ? args.dO_scale[(size_t)b * args.units_per_graph + (p.concat ? h : 0)] : 1.f;
+        k_dalpha = k_dalpha0 / sdo;
+      }
       const uint32_t d_off = (uint32_t)((p.concat ? 2 * hl : 0) * kTile + m * 2048) + fb_row64;
       const uint32_t p_off = (uint32_t)((p.concat ? 2 * hl + 1 : 1 + hl) * kTile) + fb_row64;
       const int i0 = 16 * m + g, i1 = i0 + 8;
@@ -633,6 +661,35 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
           const uint32_t da = sa + d_off, pa = sa + p_off;
           const bool tail = (cb * 32 + 32 > C);          // channels beyond C: next head's columns (concat) or padding
           uint32_t ah[2][4], al[2][4];
+          if (P16) {
+            // slot: [dout hi: hbd tiles][dout lo][P hi: hb tiles][P lo]; A fragments (rows = targets 16m.., k = channels)
+            const uint32_t hbd = p.concat ? (uint32_t)pl.hb : 1u, planes = SINGLE ? 1u : 2u;
+            const uint32_t dt = sa + (p.concat ? (uint32_t)hl * 2048u : 0u);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              ldsm_x4(dt + lmX[m][ks], ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3]);
+              if (!SINGLE) ldsm_x4(dt + hbd * 2048u + lmX[m][ks], al[ks][0], al[ks][1], al[ks][2], al[ks][3]);
+            }
+            const uint32_t pt = sa + planes * hbd * 2048u + (uint32_t)hl * 2048u, plo = (uint32_t)pl.hb * 2048u;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+              for (int np = 0; np < 2; ++np) {
+                uint32_t bh[4], bl[4];
+                ldsm_x4(pt + lmB[ks][np], bh[0], bh[1], bh[2], bh[3]);
+                if (!SINGLE) ldsm_x4(pt + plo + lmB[ks][np], bl[0], bl[1], bl[2], bl[3]);
+#pragma unroll
+                for (int nn = 0; nn < 2; ++nn) {
+                  const int n = 2 * np + nn;
+                  if (!SINGLE) {
+                    mma_f16_k16(cacc[n], al[ks], bh[2 * nn], bh[2 * nn + 1]);        // small terms first
+                    mma_f16_k16(cacc[n], ah[ks], bl[2 * nn], bl[2 * nn + 1]);
+                  }
+                  mma_f16_k16(cacc[n], ah[ks], bh[2 * nn], bh[2 * nn + 1]);
+                }
+              }
+            }
+          } else {
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
@@ -648,27 +705,6 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
               cvt_pair(x1.x, x1.y, s_dO, ah[ks][2 * hf + 1], al[ks][2 * hf + 1]);
             }
           }
-          if (P16) {
-            const uint32_t pt = sa + (uint32_t)((p.concat ? 2 * hl + 1 : 1 + hl) * kTile);
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-#pragma unroll
-              for (int np = 0; np < 2; ++np) {
-                uint32_t bh[4], bl[4];
-                ldsm_x4(pt + lmB[ks][np], bh[0], bh[1], bh[2], bh[3]);
-                if (!SINGLE) ldsm_x4(pt + 2048 + lmB[ks][np], bl[0], bl[1], bl[2], bl[3]);
-#pragma unroll
-                for (int nn = 0; nn < 2; ++nn) {
-                  const int n = 2 * np + nn;
-                  if (!SINGLE) {
-                    mma_f16_k16(cacc[n], al[ks], bh[2 * nn], bh[2 * nn + 1]);        // small terms first
-                    mma_f16_k16(cacc[n], ah[ks], bl[2 * nn], bl[2 * nn + 1]);
-                  }
-                  mma_f16_k16(cacc[n], ah[ks], bh[2 * nn], bh[2 * nn + 1]);
-                }
-              }
-            }
-          } else
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
@@ -688,6 +724,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
               mma_f16_16x8x16(cacc[n], ah[ks], bl);
               mma_f16_16x8x16(cacc[n], ah[ks], bh);
             }
+          }
           }
         }
         release_slot();
@@ -874,6 +911,10 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
       const bool active = (warp < 2 * nh) && (16 * m < N);
       const int h = h0 + hl;
       const int j0 = 16 * m + g, j1 = j0 + 8;
+      if (P16) {
+        const float sdo = active ? args.dO_scale[(size_t)b * args.units_per_graph + (p.concat ? h : 0)] : 1.f;
+        k_dp = k_dp0 / sdo;
+      }
       uint32_t ah[2][4], al[2][4];
       if (active) {
 #pragma unroll
@@ -904,7 +945,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
         const int ncb = min(pl.cbs_per_grp_d, n_cb - cb0);
         // dbias: column sums of the staged dO tiles, one tile per warp, one column per lane (tiles of the shared
         // dO in head-mean mode are summed in round 0 only)
-        if (p.concat || r == 0) {
+        if (!P16 && (p.concat || r == 0)) {
           const int n_t = p.concat ? ncb * nh : ncb;
           for (int k = warp; k < n_t; k += kW) {
             const int kc = p.concat ? k / nh : k, khl = p.concat ? k - kc * nh : 0;
@@ -926,6 +967,27 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
             for (int n = 0; n < 4; ++n)
 #pragma unroll
               for (int q = 0; q < 4; ++q) cacc[n][q] = 0.f;
+            if (P16) {
+              // B fragments (k = target rows of dO, n = channels) of the [i][c] fp16 tile by ldmatrix.trans: hi at ta, lo + 2 KB
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+                for (int np = 0; np < 2; ++np) {
+                  uint32_t bh[4], bl[4];
+                  ldsm_x4_t(ta + lmX[ks][np], bh[0], bh[1], bh[2], bh[3]);
+                  if (!SINGLE) ldsm_x4_t(ta + 2048 + lmX[ks][np], bl[0], bl[1], bl[2], bl[3]);
+#pragma unroll
+                  for (int nn = 0; nn < 2; ++nn) {
+                    const int n = 2 * np + nn;
+                    if (!SINGLE) {
+                      mma_f16_k16(cacc[n], al[ks], bh[2 * nn], bh[2 * nn + 1]);      // small terms first
+                      mma_f16_k16(cacc[n], ah[ks], bl[2 * nn], bl[2 * nn + 1]);
+                    }
+                    mma_f16_k16(cacc[n], ah[ks], bh[2 * nn], bh[2 * nn + 1]);
+                  }
+                }
+              }
+            } else
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
@@ -1048,7 +1110,8 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
       }
     }
   }
-  for (int idx = tid; idx < p.ldo; idx += kCT) args.dbias_part[(size_t)blockIdx.x * p.ldo + idx] = dbias_s[idx];
+  if (!P16)
+    for (int idx = tid; idx < p.ldo; idx += kCT) args.dbias_part[(size_t)blockIdx.x * p.ldo + idx] = dbias_s[idx];
 }
 
 }  // namespace
@@ -1082,15 +1145,21 @@ int launch_attn_bwd2(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t w
   memset(&tmPl, 0, sizeof(tmPl));
   const bool p16 = p.P_hi != nullptr, single = p16 && p.P_lo == nullptr;
   if (p16) {
-    if (!pl.tma_ok) return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd (p_format 1): C %% 4 == 0 required (dout tiles by TMA)");
-    const uint64_t rows = (uint64_t)p.B * p.N, cols = (uint64_t)p.H * p.hp + 2 * p.H;
-    if (int rc = make_tmap_f16(&tmP, p.P_hi, rows, cols, (uint64_t)p.ldp16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE))
+    if (!a.dO_hi || !a.dO_scale) return fail(SPOTV2_ERR_INVALID_ARG, "attn_bwd (p_format 1): the dout pair is missing");
+    if (p.concat && p.C % 8 != 0) return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd (p_format 1): concat layers need C %% 8 == 0");
+    const uint64_t rows = (uint64_t)p.B * p.N;
+    const uint32_t planes = single ? 1 : 2;
+    const uint64_t p_stride = single ? 0 : (uint64_t)(p.P_lo - p.P_hi), g_stride = single ? 0 : (uint64_t)(a.dO_lo - a.dO_hi);
+    if (!single && (p.P_lo <= p.P_hi || a.dO_lo <= a.dO_hi || p_stride % 8 != 0 || g_stride % 8 != 0))
+      return fail(SPOTV2_ERR_INVALID_ARG, "attn_bwd (p_format 1): lo planes must follow their hi planes at multiples of 16 bytes");
+    const uint64_t upg = (uint64_t)a.units_per_graph;
+    // P head by head (box: hb heads); dout head by head (one head per box; hb heads per box for concat layers' phase A)
+    if (int rc = make_tmap_heads_f16(&tmP, p.P_hi, p_stride, planes, rows, (uint64_t)p.C, (uint64_t)p.hp, (uint64_t)p.H, (uint64_t)p.ldp16,
+                                     (uint32_t)pl.hb))
       return rc;
-    if (int rc = make_tmap_f16(&tmPl, single ? p.P_hi : p.P_lo, rows, cols, (uint64_t)p.ldp16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B,
-                               CU_TENSOR_MAP_L2_PROMOTION_NONE))
-      return rc;
-    if (int rc = make_tmap(&tmG, a.dout, (uint64_t)p.B * p.N, (uint64_t)p.ldo, (uint64_t)p.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_NONE))
+    if (int rc = make_tmap_heads_f16(&tmG, a.dO_hi, g_stride, planes, rows, (uint64_t)p.C, (uint64_t)p.C, upg, (uint64_t)a.ldo16, 1)) return rc;
+    if (int rc = make_tmap_heads_f16(&tmPl, a.dO_hi, g_stride, planes, rows, (uint64_t)p.C, (uint64_t)p.C, upg, (uint64_t)a.ldo16,
+                                     p.concat ? (uint32_t)pl.hb : 1))
       return rc;
   } else if (pl.tma_ok) {
     // no L2 promotion: the 128-byte tile rows start anywhere in a 12 KB / 2 KB row, and fetching the enclosing 256-byte
@@ -1113,7 +1182,9 @@ int launch_attn_bwd2(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t w
   SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
   kern<<<grid, kB2Threads, pl.total, st>>>(a, pl, tmP, tmG, tmPl);
   SPOTV2_CUDA_OK(cudaGetLastError());
-  return reduce_partials2(a.dv_part, grid * rg, (dv && p.Fe > 0) ? p.H * p.Fe : 0, dv, a.dbias_part, grid, dbias ? p.ldo : 0, dbias, st);
+  // (p_format 1: the bias gradient was formed by dout_pair_prepass)
+  return reduce_partials2(a.dv_part, grid * rg, (dv && p.Fe > 0) ? p.H * p.Fe : 0, dv, a.dbias_part, grid, (dbias && !p16) ? p.ldo : 0,
+                          p16 ? nullptr : dbias, st);
 }
 
 int bwd2_diag_add(unsigned long long* host_out, int reset) {

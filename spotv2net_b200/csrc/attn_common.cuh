@@ -97,6 +97,7 @@ struct AttnParams {
   const __half* P_hi = nullptr;
   const __half* P_lo = nullptr;
   const float* p_blk = nullptr;
+  const float* sd32 = nullptr;     // [B*N, 2H] fp32: the logit terms s | d (the planes' own s|d columns are not read)
   int ldp16 = 0, hp = 0;
   int lg_tensor_cores;   // large-universe path: batched GEMMs on mma.sync (3xTF32) unless gemm_algo == 1 (exact-fp32 FFMA2)
 };

@@ -195,14 +195,13 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
         const long long tl0 = clock64();
         if (warp * 16 < rows) {
           const uint32_t r0 = ring_a[s] + (uint32_t)(((warp * 16 + 2 * g) * p.Fe + t) * 4), r1 = r0 + (uint32_t)(p.Fe * 4);
-          // two accumulator sets (even / odd k-steps): the dependent chain per accumulator is 8 MMAs per chunk, not 16
-          float acc[2][3][4];
+          // (same summation order as attn_fwd.cu: the edge terms - and with them every LeakyReLU kink - are bit-identical in
+          // both formats; two accumulator sets were tried and bought nothing: the phase is bound by per-warp issue)
+          float acc[3][4];
 #pragma unroll
-          for (int e = 0; e < 2; ++e)
+          for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
-            for (int pr = 0; pr < 3; ++pr)
-#pragma unroll
-              for (int q = 0; q < 4; ++q) acc[e][pr][q] = 0.f;
+            for (int q = 0; q < 4; ++q) acc[pr][q] = 0.f;
           for (int ks0 = 0; ks0 < pl.KS; ks0 += 8) {
             const uint32_t ko = (uint32_t)ks0 * 32u, vf = a_vfrag + ((uint32_t)ks0 * 32u + (uint32_t)lane) * 16u;
             float a[8][4];
@@ -222,14 +221,14 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
               for (int q = 0; q < 4; ++q) split_raw(a[sl][q], ah[q], al[q]);
               const uint32_t bh[2] = {__float_as_uint(bf[sl].x), __float_as_uint(bf[sl].y)};
               const uint32_t bl[2] = {__float_as_uint(bf[sl].z), __float_as_uint(bf[sl].w)};
-              mma_tf32_16x8x8(acc[sl & 1][0], al, bh);
-              mma_tf32_16x8x8(acc[sl & 1][1], ah, bl);
-              mma_tf32_16x8x8(acc[sl & 1][2], ah, bh);
+              mma_tf32_16x8x8(acc[0], al, bh);
+              mma_tf32_16x8x8(acc[1], ah, bl);
+              mma_tf32_16x8x8(acc[2], ah, bh);
             }
           }
           float res[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) res[q] = ((acc[0][0][q] + acc[1][0][q]) + (acc[0][1][q] + acc[1][1][q])) + (acc[0][2][q] + acc[1][2][q]);
+          for (int q = 0; q < 4; ++q) res[q] = (acc[0][q] + acc[1][q]) + acc[2][q];
           const int rl = warp * 16 + 2 * g, row_base = c * pl.chunk_rows + rl;
           const int to0 = rl < rows ? q_ldsi(a_table + (uint32_t)row_base * 4u) : -1;
           const int to1 = rl + 1 < rows ? q_ldsi(a_table + (uint32_t)(row_base + 1) * 4u) : -1;
@@ -292,7 +291,6 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
 #pragma unroll
       for (int cp = 0; cp < 2; ++cp) lm_off[rb][cp] = sw64(16 * rb + lm_row, 2 * cp + lm_chunk);
     const float out_scale = p.concat ? 1.f : 1.f / (float)H;
-    const float inv_sd = p.p_blk[3];
     const float k_out = p.p_blk[2] / pl.s_alpha;          // accumulator -> out
     uint32_t q_base = 0;
     long long w_tf = 0, w_pf = 0, w_sd = 0, t_smx = 0, t_cnv = 0;
@@ -302,23 +300,13 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
       const int buf = it & 1;
       float* tile = tile0 + buf * tile_floats;
       float* sd = sd0 + buf * sd_floats;
-      wait_id_t(&sd_full[buf], (it >> 1) & 1, 3, it, w_sd);
       const long long tc0 = clock64();
-      {   // s|d columns: fp16 pair tile -> packed fp32 [N][2H]
-        const unsigned char* sl = smem_raw + pl.off_sdslot + buf * kSlotBytes;
-        for (int idx = tb_; idx < sd_floats; idx += kGB) {
-          const int j = idx / (2 * H), k = idx - j * 2 * H;
-          const uint32_t off = sw64(j, k >> 3) + (uint32_t)(k & 7) * 2u;
-          float v = __half2float(*reinterpret_cast<const __half*>(sl + off));
-          if (!SINGLE) v += __half2float(*reinterpret_cast<const __half*>(sl + 2048 + off));
-          sd[idx] = v * inv_sd;
-        }
-      }
+      // s | d of this graph: fp32, as the GEMM accumulated them (L2-resident: written one kernel ago)
+      for (int idx = tb_; idx < sd_floats; idx += kGB) sd[idx] = __ldg(p.sd32 + (size_t)b * sd_floats + idx);
       const long long tc1 = clock64();
       wait_id_t(&tile_full[buf], (it >> 1) & 1, 4, it, w_tf);
       const long long ts0 = clock64();
       bar_b();                                           // sd complete (and everyone is past the previous graph's MMAs)
-      if (tb_ == 0) arrive(&sd_empty[buf]);
       softmax_phase(p, AttnSmem{NS, pl.KS, 1, pl.chunk_rows, 0, 0, 0, 0, 0, 0, 0, 0}, tile, sd, out_scale,
                     args.alpha_out ? args.alpha_out + (size_t)b * H * N * N : nullptr, nullptr, tb_, kGB, -1, 0, nullptr, b);
       bar_b();                                           // alpha tile complete
@@ -474,14 +462,6 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
       const long long t_role = clock64();
       for (int it = 0; it < my_graphs; ++it) {
         const int b = blockIdx.x + it * gridDim.x;
-        {
-          const int sb = it & 1;
-          unsigned char* dst = smem_raw + pl.off_sdslot + sb * kSlotBytes;
-          wait_id(&sd_empty[sb], ((it >> 1) & 1) ^ 1, 6, it);
-          mbar_expect_tx(&sd_full[sb], SINGLE ? 2048u : 4096u);
-          tma_load_2d(dst, &tmH, H * Cp, b * N, &sd_full[sb]);
-          if (!SINGLE) tma_load_2d(dst + 2048, &tmL, H * Cp, b * N, &sd_full[sb]);
-        }
         for (int pass = 0; pass < n_pass; ++pass) {
           const int G = min(kCbPass, n_cb - pass * kCbPass);
           const int n_g = (G + grp - 1) / grp;
@@ -544,7 +524,7 @@ int attn_fwd16_dispatch(const AttnFwdArgs& a, cudaStream_t st) {
     pl.ring_stage = (uint32_t)round_up((size_t)rows * p.Fe * 4, 128);
     o += (p.Fe > 0 && !p.terms_in) ? 2 * (size_t)pl.ring_stage + 256 : 0;     // + zero pad behind the ring (k-steps past Fe)
     o = round_up(o, 1024);
-    pl.off_sdslot = (uint32_t)o; o += 2 * kSlotBytes;
+    pl.off_sdslot = (uint32_t)o;                           // (end of the zero-filled region; the P slots start here)
     pl.off_slots = (uint32_t)o;
     const size_t cap = 227 * 1024;
     pl.n_slots = o < cap ? (int)((cap - o) / ((size_t)pl.grp * kSlotBytes)) : 0;
@@ -584,11 +564,11 @@ int attn_fwd16_dispatch(const AttnFwdArgs& a, cudaStream_t st) {
 using namespace spotv2;
 
 extern "C" int spotv2_gat_attn_fwd_pair(const spotv2_gat_desc* d, const void* P_hi, const void* P_lo_or_null, const float* p_scale,
-                                        const float* edge_rows, const int32_t* table, const float* v, const float* bias_or_null,
+                                        const float* sd, const float* edge_rows, const int32_t* table, const float* v, const float* bias_or_null,
                                         float* out, float* alpha_or_null, float* edge_terms_or_null, void* stream) {
   if (int rc = check_desc(d)) return rc;
   SPOTV2_REQUIRE(d->p_format == 1, "attn_fwd_pair: the descriptor must say p_format 1");
-  SPOTV2_REQUIRE(P_hi && p_scale && out, "attn_fwd_pair: P_hi, p_scale and out must be non-null");
+  SPOTV2_REQUIRE(P_hi && p_scale && sd && out, "attn_fwd_pair: P_hi, p_scale, sd and out must be non-null");
   SPOTV2_REQUIRE(P_lo_or_null || d->gemm_algo == 3, "attn_fwd_pair: the lo plane may be omitted with gemm_algo 3 only");
   const bool structured = d->edge_mode == 1 && d->Fe > 0;
   SPOTV2_REQUIRE(d->Fe == 0 || structured || (edge_rows && table && v), "attn_fwd_pair: edge_rows, table and v are required when Fe > 0");
@@ -607,6 +587,7 @@ extern "C" int spotv2_gat_attn_fwd_pair(const spotv2_gat_desc* d, const void* P_
   a.p.P_hi = static_cast<const __half*>(P_hi);
   a.p.P_lo = d->gemm_algo == 3 ? nullptr : static_cast<const __half*>(P_lo_or_null);
   a.p.p_blk = p_scale;
+  a.p.sd32 = sd;
   a.p.hp = head_pitch_of(d);
   a.p.ldp16 = ld16_of(n_aug_of(d));
   a.p.bulk_ok = d->Fe > 0 && aligned16(edge_rows) && ((size_t)d->R * d->Fe) % 4 == 0;

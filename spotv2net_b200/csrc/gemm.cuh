@@ -74,6 +74,8 @@ struct PairOut {
   void* lo;             // null: hi plane only (half-precision class)
   int ld;               // elements, % 8 == 0
   const float* scale;
+  float* tail32;        // optional: the columns >= B.split_at also leave in fp32, unscaled, as [M, tail_ld] (the attention
+  int tail_ld;          // logit terms s | d: their LeakyReLU kinks must not depend on the pair's rounding)
 };
 constexpr int kScaleBlockFloats = 8;   // [0,1] amax bits, [2,3] inverse scales, [4,5] scales
 inline int ld16_of(int cols) { return (cols + 15) / 16 * 16; }   // rows of fp16 operands start on 32-byte sectors

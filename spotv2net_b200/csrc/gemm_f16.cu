@@ -53,6 +53,8 @@ struct HParams {
   int single;           // 1: half-precision class (gemm_algo 3): only the A_hi * B_hi product, lo tiles not even loaded
   int pair_out;         // 0: fp32 C; 1: C leaves as an fp16 hi | lo pair (planes of tmC); 2: hi plane only
   const float* out_scale;   // pair_out: 2 power-of-two scales of the output's column groups (col < / >= b_split)
+  float* tail32;            // pair_out: fp32 copy of the columns >= b_split, [M, tail_ld] (null: none)
+  int tail_ld;
   int tma_store;        // 1: C tiles / split-K partials leave through TMA bulk stores (16-byte aligned rows); 0: st.global
   int dbg;              // bring-up probe, compiled in only with -DSPOTV2_BRINGUP (env SPOTV2_GEMM_DBG): bit 0 skip the
                         // global stores, bit 1 skip scale + amax, bit 2 skip the per-chunk register accumulation
@@ -261,6 +263,14 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             if (col0 + e < p.amax_cols) mx = fmaxf(mx, fabsf(acc[e]));
           row_amax = mx;
         }
+      }
+      if (p.pair_out && p.tail32 && row < p.M && col0 + HALF > p.b_split && col0 < p.N) {
+        // the second column group (s | d) also in fp32, free of the pair's scale (a power of two: exact)
+        const float un = 1.f / p.out_scale[1];
+        float* dst = p.tail32 + (size_t)row * p.tail_ld - p.b_split;
+#pragma unroll
+        for (int e = 0; e < HALF; ++e)
+          if (col0 + e >= p.b_split && col0 + e < p.N) dst[col0 + e] = acc[e] * un;
       }
       if (p.pair_out) {
         // The tile leaves as the fp16 operand pair of the scaled result: 32 x 32 pieces, hi plane then lo plane, each a
@@ -675,12 +685,13 @@ int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, c
   p.amax_out = reinterpret_cast<unsigned*>(amax_out);
   p.amax_cols = amax_cols;
   p.single = single ? 1 : 0;
-  p.pair_out = 0; p.out_scale = nullptr;
+  p.pair_out = 0; p.out_scale = nullptr; p.tail32 = nullptr; p.tail_ld = 0;
   if (pair) {
     if (splits > 1 || !pair->hi || !pair->scale || pair->ld % 8 != 0 || !aligned16(pair->hi) || (pair->lo && !aligned16(pair->lo)))
       return fail(SPOTV2_ERR_INVALID_ARG, "gemm3x_f16: pair output needs splits == 1, 16-byte aligned planes, ld %% 8 == 0 and a scale");
     p.pair_out = pair->lo ? 1 : 2;
     p.out_scale = pair->scale;
+    p.tail32 = pair->tail32; p.tail_ld = pair->tail_ld;
   }
   p.dbg = 0;
 #ifdef SPOTV2_BRINGUP

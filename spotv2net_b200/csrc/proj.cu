@@ -127,11 +127,11 @@ extern "C" int spotv2_proj_fwd(const spotv2_gat_desc* d, const float* x, const v
 }
 
 extern "C" int spotv2_proj_fwd_pair(const spotv2_gat_desc* d, const void* x_hi, const void* x_lo, const float* x_scale,
-                                    const float* W_aug, void* P_hi, void* P_lo_or_null, float* p_scale, void* ws,
+                                    const float* W_aug, void* P_hi, void* P_lo_or_null, float* p_scale, float* sd, void* ws,
                                     size_t ws_bytes, void* stream) {
   if (int rc = check_desc(d)) return rc;
   SPOTV2_REQUIRE(d->p_format == 1, "proj_fwd_pair: the descriptor must say p_format 1");
-  SPOTV2_REQUIRE(x_hi && x_lo && x_scale && W_aug && P_hi && p_scale, "proj_fwd_pair: null pointer");
+  SPOTV2_REQUIRE(x_hi && x_lo && x_scale && W_aug && P_hi && p_scale && sd, "proj_fwd_pair: null pointer");
   SPOTV2_REQUIRE(P_lo_or_null || single_product(d), "proj_fwd_pair: the lo plane may be omitted with gemm_algo 3 only");
   const ProjShape s = shape_of(d);
   cudaStream_t st = as_stream(stream);
@@ -143,7 +143,7 @@ extern "C" int spotv2_proj_fwd_pair(const spotv2_gat_desc* d, const void* x_hi, 
   if (int rc = split_f16(W_aug, s.n_aug, s.F, s.F, 0, s.HC, nullptr, 0, wh, wl, s.ldf16, wblk, st)) return rc;
   if (int rc = pair_out_scale(W_aug, s.n_aug, s.F, s.HC, x_scale, p_scale, st)) return rc;
   F16Operand A{x_hi, x_lo, s.ldf16, x_scale + 2, kNone}, B{wh, wl, s.ldf16, wblk + 2, s.HC};
-  PairOut out{P_hi, single_product(d) ? nullptr : P_lo_or_null, s.ldp16, p_scale + 4};
+  PairOut out{P_hi, single_product(d) ? nullptr : P_lo_or_null, s.ldp16, p_scale + 4, sd, 2 * d->H};
   return gemm3x_f16(true, true, s.rows, s.n_aug, s.F, A, B, nullptr, 0, 1, 256, 0, nullptr, 0, st, nullptr, 0, single_product(d),
                     &out);
 }

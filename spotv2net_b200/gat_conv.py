@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import weakref
 from dataclasses import dataclass
 from typing import Optional
@@ -137,15 +138,18 @@ GEMM_ALGO = 0
 ATTN_BWD_ALGO = 0
 # How the projection travels between the GEMM and the attention kernels (spotv2_gat_desc.p_format): None = the library's
 # choice (the fp16 operand pair whenever the shapes allow it), 0 = always fp32 P_aug, 1 = the pair or an error.
-P_FORMAT = None
+P_FORMAT = None if os.environ.get("SPOTV2_P_FORMAT") is None else int(os.environ["SPOTV2_P_FORMAT"])      # A/B switch
+_KEEP = None      # tools/ set this to a dict to receive the backward's dP (bring-up aid)
 
 
 PRECISIONS = {"fp32": None, "half": 3}      # "half": single fp16 tensor-core product in the projections (config C)
 
 
-def pair_format_applies(N: int, Fe: int, Cc: int, gemm_algo: int, attn_bwd_algo: int) -> bool:
-    """Shapes the p_format 1 kernels cover: one CTA per graph, tensor-core GEMM, dout tiles by TMA, the pipelined backward."""
-    return N <= 32 and gemm_algo != 1 and Cc % 4 == 0 and Fe <= 384 and attn_bwd_algo in (0, 2)
+def pair_format_applies(N: int, Fe: int, Cc: int, gemm_algo: int, attn_bwd_algo: int, concat: bool = False) -> bool:
+    """Shapes the p_format 1 kernels cover: one CTA per graph, tensor-core GEMM, the pipelined backward, head blocks of dout
+    that one CTA of the prepass holds in registers and whose tiles start on 16-byte boundaries."""
+    return (N <= 32 and gemm_algo != 1 and Cc % 4 == 0 and Cc <= 1024 and Fe <= 384 and attn_bwd_algo in (0, 2)
+            and (not concat or Cc % 8 == 0))
 
 
 def _desc(topo: Topology, F_in: int, Fe: int, H: int, Cc: int, concat: bool, slope: float,
@@ -156,7 +160,7 @@ def _desc(topo: Topology, F_in: int, Fe: int, H: int, Cc: int, concat: bool, slo
     if p_format is None:
         p_format = P_FORMAT
     if p_format is None:
-        p_format = 1 if pair_format_applies(topo.N, Fe, Cc, algo, ATTN_BWD_ALGO) else 0
+        p_format = 1 if pair_format_applies(topo.N, Fe, Cc, algo, ATTN_BWD_ALGO, bool(concat)) else 0
     return GatDesc(topo.B, topo.N, F_in, Fe, H, Cc, topo.R, int(concat), float(slope),
                    lib.spotv2_gat_ldp(H, Cc), algo, ATTN_BWD_ALGO,
                    float(dropout_p), int(edge_mode), seed & 0xffffffff, (seed >> 32) & 0xffffffff, int(p_format))
@@ -240,9 +244,10 @@ class _GatLayerFn(torch.autograd.Function):
             x_blk = torch.empty(8, device=dev, dtype=torch.float32)
             check(lib.spotv2_split_f16(ptr(x), n, x.shape[1], x.shape[1], 0, 0, ptr(x16[0]), ptr(x16[1]), ld16,
                                        ptr(x_blk), st), "spotv2_split_f16")
+        sd32 = torch.empty(n, 2 * H, device=dev, dtype=torch.float32) if pair else None      # the logit terms s | d in fp32
         if pair:
             check(lib.spotv2_proj_fwd_pair(C.byref(desc), ptr(x16[0]), ptr(x16[1]), ptr(x_blk), ptr(W_aug), ptr(P_aug[0]),
-                                           ptr(P_aug[1]) if P_aug.shape[0] > 1 else None, ptr(p_amax), ptr(ws), ws_f, st),
+                                           ptr(P_aug[1]) if P_aug.shape[0] > 1 else None, ptr(p_amax), ptr(sd32), ptr(ws), ws_f, st),
                   "spotv2_proj_fwd_pair")
         else:
             check(lib.spotv2_proj_fwd(C.byref(desc), ptr(x), ptr(x16[0]) if x16 is not None else None,
@@ -272,7 +277,7 @@ class _GatLayerFn(torch.autograd.Function):
         tbl = ptr(topo.table) if (Fe and windows is None) else None
         if pair:
             check(lib.spotv2_gat_attn_fwd_pair(C.byref(desc), ptr(P_aug[0]), ptr(P_aug[1]) if P_aug.shape[0] > 1 else None, ptr(p_amax),
-                                               ptr(ea), tbl, ptr(v), ptr(bias_c), ptr(out), ptr(alpha), ptr(et), st),
+                                               ptr(sd32), ptr(ea), tbl, ptr(v), ptr(bias_c), ptr(out), ptr(alpha), ptr(et), st),
                   "spotv2_gat_attn_fwd_pair")
         else:
             check(lib.spotv2_gat_attn_fwd(C.byref(desc), ptr(P_aug), ptr(ea), tbl, ptr(v),
@@ -280,7 +285,7 @@ class _GatLayerFn(torch.autograd.Function):
         ctx.desc, ctx.topo, ctx.Fe, ctx.has_bias, ctx.windows = desc, topo, Fe, bias is not None, windows
         ctx.edge_scale = edge_scale if Fe else None
         ctx.edge_mean = edge_mean if (Fe and edge_scale is not None) else None
-        ctx.save_for_backward(x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk, p_amax, et)
+        ctx.save_for_backward(x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk, p_amax, et, sd32)
         if want_alpha:
             ctx.mark_non_differentiable(alpha)
             return out, alpha
@@ -294,7 +299,7 @@ class _GatLayerFn(torch.autograd.Function):
     @staticmethod
     def _backward(ctx, dout):
         lib = _lib.load()
-        x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk, p_amax, et = ctx.saved_tensors
+        x, ea, W, a_src, a_dst, W_e, a_edge, W_aug, v, P_aug, x16, x_blk, p_amax, et, sd32 = ctx.saved_tensors
         desc, topo, Fe = ctx.desc, ctx.topo, ctx.Fe
         if ctx.needs_input_grad[1]:
             raise SpotV2Error("gradient w.r.t. edge_attr is not provided (the reference never needs it)")
@@ -324,7 +329,7 @@ class _GatLayerFn(torch.autograd.Function):
         d_et = torch.empty_like(et) if win is not None else None     # structured source: d(edge terms) out, dv from the windows
         if pair:
             check(lib.spotv2_gat_attn_bwd_pair(C.byref(desc), ptr(P_aug[0]), ptr(P_aug[1]) if P_aug.shape[0] > 1 else None, ptr(p_amax),
-                                               ptr(ea), ptr(et), ptr(topo.table) if (Fe and win is None) else None, ptr(v),
+                                               ptr(sd32), ptr(ea), ptr(et), ptr(topo.table) if (Fe and win is None) else None, ptr(v),
                                                ptr(dout), ptr(ph), ptr(pl), ptr(dp_blk), ptr(dv) if win is None else None,
                                                ptr(d_et), ptr(dbias), ptr(ws), ws.numel(), st), "spotv2_gat_attn_bwd_pair")
         else:
@@ -349,6 +354,9 @@ class _GatLayerFn(torch.autograd.Function):
                     T = dP_aug[:, HC + H:HC + 2 * H].sum(0)
                 dv.sub_(T.view(H, 1) * ctx.edge_mean.view(1, Fe))
             dv.mul_(ctx.edge_scale.view(1, Fe))
+        if _KEEP is not None:                      # bring-up aid (tools/): the kernel-level gradient of the projection
+            _KEEP.update(dP16=dP16, dp_blk=dp_blk, dP_aug=dP_aug, n_aug=lib.spotv2_gat_n_aug(C.byref(desc)),
+                         head_pitch=lib.spotv2_gat_head_pitch(C.byref(desc)))
         dW_aug = torch.empty_like(W_aug)
         xh = x16[0] if x16 is not None else None
         xl = x16[1] if x16 is not None else None

@@ -1183,40 +1183,59 @@ def test_training_harness_loss_curve_matches_oracle_loop(cuda_lib, tmp_path, sca
              scale_up=scale_up, seed=5)      # scale_up: x, edge_attr AND targets scaled (5_train_SpotV2Net.py:145-147)
     tr, te = train(p=dict(p), vol=vol, volvol=vv, device=DEV, output_root=str(tmp_path), drop_first=2, verbose=False)
     assert os.path.exists(tmp_path / "t_3" / "t_weights_seed_5.pth") and os.path.exists(tmp_path / "t_3" / "test_losses_seed_5.npy")
-    # oracle loop
+    # oracle loop, in fp32 (what the reference runs) and in fp64 (the yardstick)
     n = T - L - 2
     n_train = int(0.8 * n)
-    torch.manual_seed(5)
-    model = pyg_gat.OracleGATModel(N * L, 3 * L, 3, 1, [16], concat_heads=True)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    gen = torch.Generator().manual_seed(5)
-    crit = torch.nn.MSELoss()
-    tr_ref, te_ref = [], []
 
-    def scaled(bt):
+    def oracle_loop(dtype):
+        torch.manual_seed(5)
+        model = pyg_gat.OracleGATModel(N * L, 3 * L, 3, 1, [16], concat_heads=True).to(dtype)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        gen = torch.Generator().manual_seed(5)
+        crit = torch.nn.MSELoss()
+        tr_ref, te_ref = [], []
+
+        def prep(bt):
+            s_ = scale_up if scale_up else 1.0
+            return synth.Batch(x=(bt.x * s_).to(dtype), edge_index=bt.edge_index, edge_attr=(bt.edge_attr * s_).to(dtype)), (bt.y_x * s_).to(dtype)
+
+        for _ in range(2):
+            model.train()
+            order = torch.randperm(n_train, generator=gen)
+            tot, steps = 0.0, 0
+            for s in range(0, n_train, 8):
+                bt, y = prep(synth.make_batch(vol, vv, [int(i) + 2 for i in order[s:s + 8]], L))
+                loss = crit(model(bt), y)
+                opt.zero_grad(); loss.backward(); opt.step()
+                tot += loss.item(); steps += 1
+            tr_ref.append(tot / steps)
+            model.eval()
+            tot, nb = 0.0, 0
+            with torch.no_grad():
+                for s in range(n_train, n, 8):
+                    bt, y = prep(synth.make_batch(vol, vv, [i + 2 for i in range(s, min(s + 8, n))], L))
+                    tot += crit(model(bt), y).item(); nb += 1
+            te_ref.append(tot / nb)
+        return np.array(tr_ref), np.array(te_ref), model
+
+    tr32, te32, model = oracle_loop(torch.float32)
+    tr64, te64, _ = oracle_loop(torch.float64)
+    # The bar is 2e-4 against the fp64 loop (3x the fp32 reference loop's own distance where that is larger).  One exception,
+    # measured (tools/pair_model_check.py): with scale_up = 100 every logit is 100x larger, the softmax saturates, and the
+    # gradient w.r.t. att_dst - a per-target shift the softmax is invariant to, up to LeakyReLU kinks - is max|dd| = 3.9e-6
+    # against max|ds| = 11.5, i.e. ONE fp32 ulp of the dz entries it sums.  Adam normalises that rounding noise into full-size
+    # steps of att_dst, which move kinks; from the second epoch on the loss curve of ANY fp32 implementation depends on its
+    # summation order at the 1e-3 level (p_format 0 lands at 3e-6, p_format 1 at 8e-4, both with identical per-step
+    # gradients to 3e-7 for every other parameter).  So: epoch 1 at the bar, later epochs of the scaled run at 2e-3.
+    tr, te = np.array(tr), np.array(te)
+    for name, ours_, r32, r64 in (("train", tr, tr32, tr64), ("test", te, te32, te64)):
+        err = np.abs(ours_ - r64) / np.abs(r64)
+        ref_err = np.abs(r32 - r64) / np.abs(r64)
+        bar = np.maximum(2e-4, 3.0 * ref_err)
         if scale_up:
-            bt.x, bt.edge_attr, bt.y_x = bt.x * scale_up, bt.edge_attr * scale_up, bt.y_x * scale_up
-        return bt
-
-    for _ in range(2):
-        model.train()
-        order = torch.randperm(n_train, generator=gen)
-        tot, steps = 0.0, 0
-        for s in range(0, n_train, 8):
-            bt = scaled(synth.make_batch(vol, vv, [int(i) + 2 for i in order[s:s + 8]], L))
-            loss = crit(model(bt), bt.y_x)
-            opt.zero_grad(); loss.backward(); opt.step()
-            tot += loss.item(); steps += 1
-        tr_ref.append(tot / steps)
-        model.eval()
-        tot, nb = 0.0, 0
-        with torch.no_grad():
-            for s in range(n_train, n, 8):
-                bt = scaled(synth.make_batch(vol, vv, [i + 2 for i in range(s, min(s + 8, n))], L))
-                tot += crit(model(bt), bt.y_x).item(); nb += 1
-        te_ref.append(tot / nb)
-    # scale_up = 100 makes every logit 100x larger: the softmax is sharply peaked and both loops (ours and the fp32 CPU
-    # reference loop) sit at ~1e-4 of fp32 noise on the held-out loss after two epochs of Adam
-    assert np.allclose(tr, tr_ref, rtol=2e-4) and np.allclose(te, te_ref, rtol=5e-4 if scale_up else 2e-4), (tr, tr_ref, te, te_ref)
+            bar[1:] = np.maximum(bar[1:], 2e-3)
+        if (err > 2e-4).any() or os.environ.get("SPOTV2_VERBOSE_TESTS"):
+            print(f"training harness [{'scale_up' if scale_up else 'plain'}] {name} loss: ours {err}, fp32 reference loop {ref_err} (relative to the fp64 loop)")
+        assert (err <= bar).all(), (name, ours_, r32, r64)
     sd = torch.load(tmp_path / "t_3" / "t_weights_seed_5.pth")
     assert list(sd.keys()) == list(model.state_dict().keys())

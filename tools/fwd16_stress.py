@@ -14,14 +14,14 @@ lib, d, p, L = hp.lib, C.byref(hp.desc), hp._lib.ptr, hp.layer
 st = torch.cuda.current_stream(dev).cuda_stream
 chk = hp._lib.check
 chk(lib.spotv2_gat_fold(d, p(L.lin_src.weight), p(L.att_src), p(L.att_dst), p(L.lin_edge.weight), p(L.att_edge), p(hp.W_aug), p(hp.v), st), "fold")
-chk(lib.spotv2_proj_fwd_pair(d, p(hp.x16[0]), p(hp.x16[1]), p(hp.x_blk), p(hp.W_aug), p(hp.P_aug[0]), p(hp.P_aug[1]), p(hp.p_amax), p(hp.ws), hp.ws.numel(), st), "proj")
+chk(lib.spotv2_proj_fwd_pair(d, p(hp.x16[0]), p(hp.x16[1]), p(hp.x_blk), p(hp.W_aug), p(hp.P_aug[0]), p(hp.P_aug[1]), p(hp.p_amax), p(hp.sd32), p(hp.ws), hp.ws.numel(), st), "proj")
 torch.cuda.synchronize()
 ref = None
 worst = 0.0
 for i in range(iters):
     t0 = time.time()
     try:
-        chk(lib.spotv2_gat_attn_fwd_pair(d, p(hp.P_aug[0]), p(hp.P_aug[1]), p(hp.p_amax), p(hp.batch.edge_attr), p(hp.batch.spot_topology.table),
+        chk(lib.spotv2_gat_attn_fwd_pair(d, p(hp.P_aug[0]), p(hp.P_aug[1]), p(hp.p_amax), p(hp.sd32), p(hp.batch.edge_attr), p(hp.batch.spot_topology.table),
                                          p(hp.v), p(L.bias), p(hp.out), None, p(hp.edge_terms), st), "fwd")
         torch.cuda.synchronize()
     except Exception as ex:
