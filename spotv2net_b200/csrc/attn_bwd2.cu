@@ -46,6 +46,7 @@ struct Bwd2Plan {
   int KS, chunk_rows, nchunks, n_cb, hpr, n_rounds, n_mt_chunk, ksplit;
   int n_mtiles, dv_rg, dv_rpu, dv_units, cbs_per_grp_d, tma_ok, n_slots;
   int hb;      // p_format 1: heads per TMA box of a phase-A slot (min(hpr, H))
+  int stage_ok;   // p_format 1: the dz' tile (idle during phase D) can hold every warp's 2 KB dP staging tile for TMA stores
   uint32_t off_bar, off_table, off_vfrag, off_sd, off_mask, off_dspart, off_dbias, off_tile, off_D, off_slots,
       slot_bytes, total;
 };
@@ -72,7 +73,9 @@ Bwd2Plan make_plan(const AttnParams& p) {
   s.off_dspart = o; o += (uint32_t)(2 * H * 32 * 4);
   s.off_dbias = o;  o += (uint32_t)round_up((size_t)p.ldo * 4, 16);
   s.off_tile = o;   o += (uint32_t)round_up((size_t)H * N * kNS2 * 4, 16);
+  o = (uint32_t)round_up(o, 1024);       // (the dP staging tiles of phase D live here: swizzled TMA boxes want 512-byte alignment)
   s.off_D = o;      o += (uint32_t)round_up((size_t)H * N * kNS2 * 4, 16);
+  s.stage_ok = ((size_t)H * N * kNS2 * 4 >= (size_t)kW * 2048) ? 1 : 0;
   s.off_slots = (uint32_t)round_up(o, 1024);
   // a slot holds one tile group (7 tiles) or one edge chunk (a multiple of 16 rows, at most 96)
   s.slot_bytes = kGrpTiles * kTile;
@@ -241,7 +244,8 @@ bool plan_is_fixed_geom(const AttnParams& p, const Bwd2Plan& s) {
 template <bool FIX, bool DROP, bool P16, bool SINGLE>
 __global__ void __launch_bounds__(kB2Threads, 1)
 gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_constant__ CUtensorMap tmP,
-                     const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmPl) {
+                     const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmPl,
+                     const __grid_constant__ CUtensorMap tmD0, const __grid_constant__ CUtensorMap tmD1) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   AttnParams p = args.p;
   Bwd2Plan pl = pl_;
@@ -309,7 +313,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
 
   if (warp == kW) {
     // =========================================== producer ===========================================
-    if (lane == 0) { prefetch_tmap(&tmP); prefetch_tmap(&tmG); if (P16) prefetch_tmap(&tmPl); }
+    if (lane == 0) { prefetch_tmap(&tmP); prefetch_tmap(&tmG); if (P16) { prefetch_tmap(&tmPl); prefetch_tmap(&tmD0); prefetch_tmap(&tmD1); } }
     const long long n_rows = (long long)p.B * N;
     // one tile: TMA, or (C % 4 != 0: tile starts are not 16-byte aligned) a cooperative gather into the
     // same swizzled layout
@@ -903,6 +907,8 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
       release_slot();
     }
     lap(5);
+    // (the dP staging tiles reuse the dz' tile: every warp must be done reading it - phase V, or the edge_mode 1 copy-out)
+    if (P16 && pl.stage_ok) bar_sync_compute();
     // ------------------------------------------------ D: dP = g alpha^T dO ------------------------------------------------
     for (int r = 0; r < pl.n_rounds; ++r) {
       const int h0 = r * pl.hpr;
@@ -1005,7 +1011,37 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
                 mma_f16_16x8x16(cacc[n], ah[ks], bh);
               }
             }
-            if (args.dP_hi16 && vec4_out) {
+            if (P16 && pl.stage_ok) {
+              // dP leaves through the TMA engine: the warp parks its 16-source x 32-channel tile (hi plane, then lo plane:
+              // one box of rows x 64 B each, 64B swizzle, conflict-free 4-byte stores) in its 2 KB piece of the idle dz'
+              // tile and one lane stores both planes with one instruction.  Pad columns [C, Cp) are exact zeros (the dout
+              // box zero-fills past C), columns past Cp and rows past N are outside the box.  (The per-row st.global stream
+              // this replaces bounded the phase: 38 K cycles per graph with the MMA loop at a third of that.)
+              const int rows_m = m == 0 ? min(16, N) : N - 16;
+              const uint32_t stg = a_D + (uint32_t)warp * 2048u;
+              if (lane == 0) tma_store_wait_read();                 // the previous tile's store has read the staging
+              __syncwarp();
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                const int rr = g + 8 * hf;                          // row inside the tile; tall-tile row of the lo plane: rows_m + rr
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                  const float w0 = cacc[n][2 * hf] * k_dp, w1 = cacc[n][2 * hf + 1] * k_dp;
+                  const __half2 hh = __floats2half2_rn(w0, w1);
+                  if (rr < rows_m) {
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + sw64(rr, n) + 4u * t), "r"(*reinterpret_cast<const uint32_t*>(&hh)) : "memory");
+                    if (!SINGLE) {
+                      const float2 back = __half22float2(hh);
+                      const __half2 ll = __floats2half2_rn(w0 - back.x, w1 - back.y);
+                      asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + sw64(rows_m + rr, n) + 4u * t), "r"(*reinterpret_cast<const uint32_t*>(&ll)) : "memory");
+                    }
+                  }
+                }
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) tma_store_4d(m == 0 ? &tmD0 : &tmD1, stg, cb * 32, b * N + 16 * m, h, 0);
+            } else if (args.dP_hi16 && vec4_out) {
               // fp16 pairs, coalesced: a quad exchange gives every lane 4 consecutive columns, so one 8-byte
               // store per lane writes 32 contiguous bytes per row (the fragment's native 4-byte pieces cost
               // one partial sector each and bounded this phase)
@@ -1083,11 +1119,13 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
         release_slot();
       }
     }
+    if (P16 && pl.stage_ok && lane == 0) tma_store_wait_read();   // the engine has read this warp's last dP staging tile
     bar_sync_compute();                                   // every warp is done with alpha and with the dz' tile
     for (int idx = tid; idx < tile_floats; idx += kCT) tile[idx] = 0.f;      // next graph's logits accumulate into zeros
     bar_sync_compute();
     lap(4);
   }
+  if (P16 && pl.stage_ok && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this lane's dP stores have landed
   if (tid == 0)
     for (int k = 0; k < 6; ++k) atomicAdd(&g_bwd2_counters[k], (unsigned long long)ph[k]);
   if (args.dsd_amax) {
@@ -1171,6 +1209,24 @@ int launch_attn_bwd2(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t w
                            CU_TENSOR_MAP_L2_PROMOTION_NONE))
       return rc;
   }
+  CUtensorMap tmD0, tmD1;
+  memset(&tmD0, 0, sizeof(tmD0));
+  memset(&tmD1, 0, sizeof(tmD1));
+  if (p16 && pl.stage_ok) {
+    // dP planes head by head with the padded pitch as the head's width (the pad columns are written, as zeros); boxes of
+    // 16 (first source tile) and N - 16 (second) rows
+    const uint64_t rows = (uint64_t)p.B * p.N;
+    const uint64_t d_stride = single ? 0 : (uint64_t)(a.dP_lo16 - a.dP_hi16);
+    if (!single && (a.dP_lo16 <= a.dP_hi16 || d_stride % 8 != 0))
+      return fail(SPOTV2_ERR_INVALID_ARG, "attn_bwd (p_format 1): the dP lo plane must follow the hi plane at a multiple of 16 bytes");
+    if (int rc = make_tmap_heads_f16(&tmD0, a.dP_hi16, d_stride, single ? 1 : 2, rows, (uint64_t)p.hp, (uint64_t)p.hp, (uint64_t)p.H,
+                                     (uint64_t)a.ldp16, 1, CU_TENSOR_MAP_L2_PROMOTION_NONE, (uint32_t)(p.N < 16 ? p.N : 16)))
+      return rc;
+    if (p.N > 16)
+      if (int rc = make_tmap_heads_f16(&tmD1, a.dP_hi16, d_stride, single ? 1 : 2, rows, (uint64_t)p.hp, (uint64_t)p.hp, (uint64_t)p.H,
+                                       (uint64_t)a.ldp16, 1, CU_TENSOR_MAP_L2_PROMOTION_NONE, (uint32_t)(p.N - 16)))
+        return rc;
+  }
   const bool fixg = plan_is_fixed_geom(p, pl) && (!p16 || p.hp == 504), drop = p.drop.p > 0.f;
   auto kern = drop ? (fixg ? gat_attn_bwd2_kernel<true, true, false, false> : gat_attn_bwd2_kernel<false, true, false, false>)
                    : (fixg ? gat_attn_bwd2_kernel<true, false, false, false> : gat_attn_bwd2_kernel<false, false, false, false>);
@@ -1180,7 +1236,7 @@ int launch_attn_bwd2(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t w
   else if (p16)
     kern = drop ? gat_attn_bwd2_kernel<false, true, true, true> : gat_attn_bwd2_kernel<false, false, true, true>;
   SPOTV2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
-  kern<<<grid, kB2Threads, pl.total, st>>>(a, pl, tmP, tmG, tmPl);
+  kern<<<grid, kB2Threads, pl.total, st>>>(a, pl, tmP, tmG, tmPl, tmD0, tmD1);
   SPOTV2_CUDA_OK(cudaGetLastError());
   // (p_format 1: the bias gradient was formed by dout_pair_prepass)
   return reduce_partials2(a.dv_part, grid * rg, (dv && p.Fe > 0) ? p.H * p.Fe : 0, dv, a.dbias_part, grid, (dbias && !p16) ? p.ldo : 0,

@@ -101,18 +101,26 @@ inline int make_tmap_tile_groups_f16(CUtensorMap* tm, const void* base, uint64_t
 // box_heads, planes) lands as [plane][head][row][64 B], every 32 x 32 tile in the 2-D 64B-swizzled layout.
 inline int make_tmap_heads_f16(CUtensorMap* tm, const void* base, uint64_t plane_stride, uint32_t planes, uint64_t rows,
                                uint64_t cols_per_head, uint64_t head_pitch, uint64_t heads, uint64_t ld, uint32_t box_heads,
-                               CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_NONE) {
+                               CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_NONE, uint32_t box_rows = 32) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(SPOTV2_ERR_NO_DEVICE, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[4] = {cols_per_head, rows, heads, planes};
   cuuint64_t strides[3] = {ld * 2, (heads > 1 ? head_pitch : 8) * 2, (planes > 1 ? plane_stride : 8) * 2};
-  cuuint32_t box[4] = {32, 32, box_heads, planes};
+  cuuint32_t box[4] = {32, box_rows, box_heads, planes};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SPOTV2_ERR_CUDA, "cuTensorMapEncodeTiled (4-D heads) failed with CUresult %d", (int)r);
   return SPOTV2_OK;
 }
+// shared -> global tensor store (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tm), "r"(smem_src), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
