@@ -540,9 +540,9 @@ def dp_selfcheck(dev, rank, world, per_rank: int = 64):
 def run_config_c(args):
     """BASELINE configs[2] through the public module API: GATModel(8 heads, hidden [256, 256], concat_heads) forward + MSE +
     autograd backward on one collated 4096-graph batch (utils/models.py:90-104; config/GNN_param.yaml:28-38 widened).  The
-    line's value is the reduced-precision mode the config names ("half": one fp16 tensor-core product per projection, fp32
-    accumulate; the attention kernels keep fp32 storage - no bf16-storage attention exists yet); the fp32-accurate mode is
-    reported beside it.  The attention kernels' share comes from one extra step under torch.profiler (kernel durations by
+    line's value is the reduced-precision mode the config names ("half": one fp16 tensor-core product per MMA step with fp32
+    accumulate in the projections AND the attention kernels, P / dP / dout stored as fp16 hi planes - half the attention
+    bytes); the fp32-accurate mode is reported beside it.  The attention kernels' share comes from one extra step under torch.profiler (kernel durations by
     name), never from the timed steps."""
     import spotv2net_b200 as sv
     if not torch.cuda.is_available():
@@ -567,7 +567,7 @@ def run_config_c(args):
         return loss
 
     sampler = ClockSampler(dev.index or 0)
-    res = {}
+    res, attn_ms = {}, {}
     for prec in ("fp32", "half"):
         model.set_precision(prec)
         for _ in range(max(args.warmup, 3)):
@@ -583,40 +583,53 @@ def run_config_c(args):
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / args.steps
         res[prec] = {"ms_per_step": ms, "value": B / (ms * 1e-3), "unit": UNIT, "loss": loss.item()}
-    clocks = sampler.stop()
-    # attention bytes, fp32 storage, per graph: layer 0 (concat: out and dout are H*C wide), layer 1 (head mean)
+        if prec == "half":
+            clocks = sampler.stop()
+        # the attention kernels' share (incl. the backward's operand preparation of dout): one extra step under torch.profiler
+        try:
+            from torch.profiler import profile, ProfilerActivity
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                step()
+                torch.cuda.synchronize(dev)
+            attn_ms[prec] = sum(e.device_time_total for e in prof.key_averages() if "gat_attn" in e.key or "dout_pair" in e.key) * 1e-3
+        except Exception:
+            attn_ms[prec] = None
+    # algorithmic attention bytes per graph: layer 0 (concat: out and dout are H*C wide), layer 1 (head mean); eb = bytes per
+    # stored element of P and dP: 4 in the fp32-accurate mode (an fp16 hi|lo pair, or fp32), 2 in the half mode (hi plane only)
     edge = N * (N - 1) * 3 * L * 4
-    Pb = N * H * Cc * 4
-    l0 = (edge + Pb + N * H * Cc * 4) + (edge + Pb + N * H * Cc * 4 + Pb)
-    l1 = (edge + Pb + N * Cc * 4) + (edge + Pb + N * Cc * 4 + Pb)
-    attn_ms = None
-    try:
-        from torch.profiler import profile, ProfilerActivity
-        with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            step()
-            torch.cuda.synchronize(dev)
-        attn_ms = sum(e.device_time_total for e in prof.key_averages() if "gat_attn" in e.key) * 1e-3
-    except Exception:
-        attn_ms = None
+
+    def attn_bytes(eb):
+        Pb = N * H * Cc * eb
+        l0 = (edge + Pb + N * H * Cc * 4) + (edge + Pb + N * H * Cc * 4 + Pb)
+        l1 = (edge + Pb + N * Cc * 4) + (edge + Pb + N * Cc * 4 + Pb)
+        return l0 + l1
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm = peaks.get("hbm_gbs", 6650.0)
-    ach = (l0 + l1) * B / (attn_ms * 1e-3) / 1e9 if attn_ms else None
+
+    def roof(prec, eb):
+        ms = attn_ms.get(prec)
+        ach = attn_bytes(eb) * B / (ms * 1e-3) / 1e9 if ms else None
+        return {"bound": "hbm", "kernel": "gat_attn_fwd16_kernel + dout_pair_kernel + gat_attn_bwd2_kernel, both layers",
+                "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm if ach else None, "traffic": None,
+                "attention_ms_profiled_step": ms, "algorithmic_bytes_per_step": attn_bytes(eb) * B, "bytes_per_P_element": eb,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"}
+
+    res["fp32"]["roofline"] = roof("fp32", 4)
     line = {"metric": METRIC_BY_CONFIG["C"], "value": res["half"]["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": res["half"]["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16 projections (one tensor-core product, fp32 accumulate), f32 attention storage",
+            "vs_baseline": None,
+            "dtype": "f16 (one tensor-core product per MMA step, fp32 accumulate; P, dP and dout travel as fp16 hi planes: p_format 1 "
+                     "with gemm_algo 3 - the config's reduced-precision class; the fp32-accurate mode is under fp32_mode)",
             "data": "synthetic",
             "config": {"workload": CONFIGS["C"]["name"] + ", GATModel forward + MSE + autograd backward", "nodes": N, "heads": H,
                        "hidden": [Cc, Cc], "batch_per_gpu": B, "parallelism": "dp1",
-                       "l2": "inputs (x 619 MB, edge_attr 1.80 GB, P 983 MB per layer) exceed the 126 MB L2; no flush needed"},
+                       "l2": "inputs (x 619 MB, edge_attr 1.80 GB, P 0.5 - 1 GB per layer) exceed the 126 MB L2; no flush needed"},
             "fp32_mode": res["fp32"],
-            "roofline": {"bound": "hbm", "kernel": "gat_attn_fwd_kernel + gat_attn_bwd2_kernel, both layers (fp32 storage)",
-                         "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm if ach else None, "traffic": None,
-                         "attention_ms_profiled_step": attn_ms, "algorithmic_bytes_per_step": (l0 + l1) * B,
-                         "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"},
+            "roofline": roof("half", 2),
             "cpu_baseline": None, "e2e": None, "gpu_launches": None, "clocks": clocks}
     print(json.dumps(line), flush=True)
 

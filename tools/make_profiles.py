@@ -3,7 +3,7 @@ the launch list with each kernel's share of a step, the headline ncu metrics of 
 profiles/attn_traffic.json (DRAM bytes per launch of the attention kernels, read by bench.py)."""
 import csv, collections, json, subprocess, sys, os
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1z"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
 out = "profiles"
 rows = [r for r in csv.reader(open("gpurun_out/launches.csv")) if len(r) > 14 and r[0].isdigit()]
 # steps = warmup 3 + timed 3; keep the launches of the last step: find the last 'fold_kernel' occurrence pattern
@@ -13,8 +13,9 @@ unit = rows[0][13]
 scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0}.get(unit, 1e-6)
 short = lambda n: n.split("(")[0].replace("void ", "").replace("spotv2::", "").replace("<unnamed>::", "")[:70]
 # last step = launches after the last launch of the first kernel name of a step (fold_kernel)
-idx = [i for i, n in enumerate(names) if "fold_kernel<8>" in n or "fold_kernel<(int)8>" in n]
-first = idx[-1] if idx else 0                    # a step starts with fold_kernel<8> (W_aug rows), then fold_kernel<32> (v)
+idx = [i for i, n in enumerate(names) if "fold_copy_padded_kernel" in n] or \
+      [i for i, n in enumerate(names) if "fold_kernel<8>" in n or "fold_kernel<(int)8>" in n]
+first = idx[-1] if idx else 0                    # a step starts with the W_aug copy (p_format 1) | fold_kernel<8>, then fold_kernel<32> (v)
 step = list(zip(names[first:], times[first:]))
 agg = collections.OrderedDict()
 for n, t in step:
