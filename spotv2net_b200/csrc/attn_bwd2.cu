@@ -944,6 +944,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
             cvt_pair(x1.x, x1.y, s_al, ah[ks][2 * hf + 1], al[ks][2 * hf + 1]);
           }
       }
+      uint32_t carry_h[2] = {0u, 0u}, carry_l[2] = {0u, 0u};     // last 8-column chunk of the previous dP tile (shifted stores)
       const int n_grp = (n_cb + pl.cbs_per_grp_d - 1) / pl.cbs_per_grp_d;
       for (int gi = 0; gi < n_grp; ++gi) {
         const uint32_t sa = wait_slot();
@@ -1019,28 +1020,62 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
               // this replaces bounded the phase: 38 K cycles per graph with the MMA loop at a third of that.)
               const int rows_m = m == 0 ? min(16, N) : N - 16;
               const uint32_t stg = a_D + (uint32_t)warp * 2048u;
+              // A head whose first column sits 16 bytes into a 32-byte sector (odd heads when Cp % 16 == 8) would write every
+              // 64-byte row piece over three sectors, two of them partially - and the L2 fills a partially written sector from
+              // DRAM (measured: 0.8 GB of extra reads per launch).  Such a head stores its tiles shifted left by one 8-column
+              // chunk: box k covers [32k - 8, 32k + 24) = the last chunk of tile k - 1 (kept in registers) and the first three
+              // of tile k; columns past Cp are outside the tensor map's head and are not written.
+              // (tile 0 goes out unshifted: a negative box coordinate faults on a store; its last chunk is then written twice,
+              // with the same values)
+              const bool shift = ((h * Cp) & 15) != 0 && cb > 0;
+              uint32_t cur_h[2][4], cur_l[2][4];
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                  const float w0 = cacc[n][2 * hf] * k_dp, w1 = cacc[n][2 * hf + 1] * k_dp;
+                  const __half2 hh = __floats2half2_rn(w0, w1);
+                  const float2 back = __half22float2(hh);
+                  const __half2 ll = __floats2half2_rn(w0 - back.x, w1 - back.y);
+                  cur_h[hf][n] = *reinterpret_cast<const uint32_t*>(&hh);
+                  cur_l[hf][n] = *reinterpret_cast<const uint32_t*>(&ll);
+                }
               if (lane == 0) tma_store_wait_read();                 // the previous tile's store has read the staging
               __syncwarp();
 #pragma unroll
               for (int hf = 0; hf < 2; ++hf) {
                 const int rr = g + 8 * hf;                          // row inside the tile; tall-tile row of the lo plane: rows_m + rr
+                if (rr < rows_m) {
 #pragma unroll
-                for (int n = 0; n < 4; ++n) {
-                  const float w0 = cacc[n][2 * hf] * k_dp, w1 = cacc[n][2 * hf + 1] * k_dp;
-                  const __half2 hh = __floats2half2_rn(w0, w1);
-                  if (rr < rows_m) {
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + sw64(rr, n) + 4u * t), "r"(*reinterpret_cast<const uint32_t*>(&hh)) : "memory");
-                    if (!SINGLE) {
-                      const float2 back = __half22float2(hh);
-                      const __half2 ll = __floats2half2_rn(w0 - back.x, w1 - back.y);
-                      asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + sw64(rows_m + rr, n) + 4u * t), "r"(*reinterpret_cast<const uint32_t*>(&ll)) : "memory");
-                    }
+                  for (int q = 0; q < 4; ++q) {                     // staging chunk q <- tile chunk q (or q - 1, chunk 0 <- the carried one)
+                    const uint32_t vh = !shift ? cur_h[hf][q] : (q == 0 ? carry_h[hf] : cur_h[hf][q - 1]);
+                    const uint32_t vl = !shift ? cur_l[hf][q] : (q == 0 ? carry_l[hf] : cur_l[hf][q - 1]);
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + sw64(rr, q) + 4u * t), "r"(vh) : "memory");
+                    if (!SINGLE) asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + sw64(rows_m + rr, q) + 4u * t), "r"(vl) : "memory");
                   }
                 }
+                carry_h[hf] = cur_h[hf][3];
+                carry_l[hf] = cur_l[hf][3];
               }
               fence_proxy_async();
               __syncwarp();
-              if (lane == 0) tma_store_4d(m == 0 ? &tmD0 : &tmD1, stg, cb * 32, b * N + 16 * m, h, 0);
+              if (lane == 0) tma_store_4d(m == 0 ? &tmD0 : &tmD1, stg, cb * 32 - (shift ? 8 : 0), b * N + 16 * m, h, 0);
+              if (((h * Cp) & 15) != 0 && cb == n_cb - 1 && n_cb > 1 && 32 * n_cb - 8 < Cp) {
+                // the carried last chunk still holds columns the head owns: one more box, only its first chunk inside Cp
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                  const int rr = g + 8 * hf;
+                  if (rr < rows_m) {
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + sw64(rr, 0) + 4u * t), "r"(carry_h[hf]) : "memory");
+                    if (!SINGLE) asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + sw64(rows_m + rr, 0) + 4u * t), "r"(carry_l[hf]) : "memory");
+                  }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tma_store_4d(m == 0 ? &tmD0 : &tmD1, stg, n_cb * 32 - 8, b * N + 16 * m, h, 0);
+              }
             } else if (args.dP_hi16 && vec4_out) {
               // fp16 pairs, coalesced: a quad exchange gives every lane 4 consecutive columns, so one 8-byte
               // store per lane writes 32 contiguous bytes per row (the fragment's native 4-byte pieces cost
