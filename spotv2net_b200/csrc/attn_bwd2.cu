@@ -388,7 +388,9 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
             if (lane == 0) {
               mbar_expect_tx(&full[slot], planes * (uint32_t)(hbd + pl.hb) * 2048u);
               tma_load_4d_hint(gb, p.concat ? &tmPl : &tmG, cb * 32, b * N, p.concat ? h0 : 0, 0, &full[slot], kEvictFirst);
-              tma_load_4d_hint(gb + planes * (uint32_t)hbd * 2048u, &tmP, cb * 32, b * N, h0, 0, &full[slot], kEvictFirst);
+              // (no eviction hint, 256-byte promotion: the 64-byte row pieces of heads that start mid-sector would otherwise be
+              // fetched as two 64-byte DRAM bursts each; promoted lines are shared with the next channel block's box)
+              tma_load_4d(gb + planes * (uint32_t)hbd * 2048u, &tmP, cb * 32, b * N, h0, 0, &full[slot]);
             }
           } else {
           const int ntiles = p.concat ? 2 * nh : 1 + nh;
@@ -1228,7 +1230,7 @@ int launch_attn_bwd2(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t w
     const uint64_t upg = (uint64_t)a.units_per_graph;
     // P head by head (box: hb heads); dout head by head (one head per box; hb heads per box for concat layers' phase A)
     if (int rc = make_tmap_heads_f16(&tmP, p.P_hi, p_stride, planes, rows, (uint64_t)p.C, (uint64_t)p.hp, (uint64_t)p.H, (uint64_t)p.ldp16,
-                                     (uint32_t)pl.hb))
+                                     (uint32_t)pl.hb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
       return rc;
     if (int rc = make_tmap_heads_f16(&tmG, a.dO_hi, g_stride, planes, rows, (uint64_t)p.C, (uint64_t)p.C, upg, (uint64_t)a.ldo16, 1)) return rc;
     if (int rc = make_tmap_heads_f16(&tmPl, a.dO_hi, g_stride, planes, rows, (uint64_t)p.C, (uint64_t)p.C, upg, (uint64_t)a.ldo16,
