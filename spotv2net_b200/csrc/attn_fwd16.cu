@@ -202,20 +202,25 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
           for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[pr][q] = 0.f;
-          for (int ks0 = 0; ks0 < pl.KS; ks0 += 8) {
-            const uint32_t ko = (uint32_t)ks0 * 32u, vf = a_vfrag + ((uint32_t)ks0 * 32u + (uint32_t)lane) * 16u;
-            float a[8][4];
-            float4 bf[8];
+          // software pipeline over batches of four k-steps: the operand loads of the next batch are in flight while this
+          // batch is split and multiplied (one warp per scheduler has nobody else to hide its shared-memory latency);
+          // k-steps and accumulators keep their order, so the sums are bit-identical to the un-pipelined loop
+          float a0[4][4], a1[4][4];
+          float4 b0[4], b1[4];
+          auto load4 = [&](float (&a)[4][4], float4 (&bf)[4], int ks) {
+            const uint32_t ko = (uint32_t)ks * 32u, vf = a_vfrag + ((uint32_t)ks * 32u + (uint32_t)lane) * 16u;
 #pragma unroll
-            for (int sl = 0; sl < 8; ++sl) {
+            for (int sl = 0; sl < 4; ++sl) {
               a[sl][0] = q_lds(r0 + ko + sl * 32);
               a[sl][1] = q_lds(r1 + ko + sl * 32);
               a[sl][2] = q_lds(r0 + ko + sl * 32 + 16);
               a[sl][3] = q_lds(r1 + ko + sl * 32 + 16);
               bf[sl] = q_lds128(vf + sl * 512);
             }
+          };
+          auto mma4 = [&](const float (&a)[4][4], const float4 (&bf)[4]) {
 #pragma unroll
-            for (int sl = 0; sl < 8; ++sl) {
+            for (int sl = 0; sl < 4; ++sl) {
               uint32_t ah[4], al[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) split_raw(a[sl][q], ah[q], al[q]);
@@ -225,6 +230,13 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
               mma_tf32_16x8x8(acc[1], ah, bl);
               mma_tf32_16x8x8(acc[2], ah, bh);
             }
+          };
+          load4(a0, b0, 0);
+          for (int ks0 = 0; ks0 < pl.KS; ks0 += 8) {         // KS is a multiple of 8
+            load4(a1, b1, ks0 + 4);
+            mma4(a0, b0);
+            if (ks0 + 8 < pl.KS) load4(a0, b0, ks0 + 8);
+            mma4(a1, b1);
           }
           float res[4];
 #pragma unroll
