@@ -1239,3 +1239,103 @@ def test_training_harness_loss_curve_matches_oracle_loop(cuda_lib, tmp_path, sca
         assert (err <= bar).all(), (name, ours_, r32, r64)
     sd = torch.load(tmp_path / "t_3" / "t_weights_seed_5.pth")
     assert list(sd.keys()) == list(model.state_dict().keys())
+
+
+# ------------------------------------------------------------------ p_format 1: the projection as an fp16 operand pair
+@pytest.mark.parametrize("shape", [(8, 30, 500, 1), (593, 30, 500, 1), (1184, 30, 500, 1), (70, 30, 256, 8), (300, 7, 12, 3), (5, 1, 1024, 1)],
+                         ids=lambda s: "B%dN%dC%dupg%d" % s)
+def test_dout_operand_pair_prepass(cuda_lib, shape):
+    """csrc/attn_prep.cu through spotv2_diag_dout_pair: one pass turns dout into hi | lo planes with one power-of-two
+    scale per unit (a graph, or a (graph, head) block of a concat layer), the bias gradient and max|dout|.  Units whose
+    magnitudes differ by orders (rows scaled by a random factor) each keep 22 bits; more units than CTAs (593, 1184)."""
+    B, N, C_, upg = shape
+    ldo = upg * C_
+    g = torch.Generator(device=DEV).manual_seed(B)
+    dout = torch.randn(B * N, ldo, device=DEV, generator=g) * torch.rand(B, 1, 1, device=DEV, generator=g).expand(B, N, 1).reshape(B * N, 1) ** 4
+    ld16 = cuda_lib.spotv2_gat_ld16(ldo)
+    planes = torch.zeros(2, B * N, ld16, device=DEV, dtype=torch.float16)
+    scales, blk, dbias = torch.zeros(B * upg, device=DEV), torch.zeros(8, device=DEV), torch.zeros(ldo, device=DEV)
+    ws = torch.empty(cuda_lib.spotv2_diag_dout_pair_ws_bytes(B, C_, upg), device=DEV, dtype=torch.uint8)
+    check(cuda_lib.spotv2_diag_dout_pair(ptr(dout), B, N, C_, upg, ptr(planes[0]), ptr(planes[1]), ld16, ptr(scales), ptr(blk),
+                                         ptr(dbias), ptr(ws), st()), "spotv2_diag_dout_pair")
+    units = dout.view(B, N, upg, C_)
+    umax = units.abs().amax(dim=(1, 3))
+    want_s = torch.where(umax > 0, torch.exp2(15 - torch.frexp(umax)[1].float()), torch.ones_like(umax))
+    assert torch.equal(scales.view(B, upg), want_s)                                  # amax * scale in [2^14, 2^15): exact rule
+    assert (planes[0].float().abs().max() < 32768.5)
+    rec = (planes[0, :, :ldo].double() + planes[1, :, :ldo].double()).view(B, N, upg, C_) / scales.view(B, 1, upg, 1).double()
+    per_unit = (rec - units.double()).abs().amax(dim=(1, 3)) / umax.double().clamp_min(1e-300)
+    assert per_unit.max().item() < 2.0 ** -21                                        # 22 bits relative to EACH unit's maximum
+    assert blk.view(torch.int32)[0].item() == units.abs().max().view(torch.int32).item()
+    assert relerr(dbias, dout.double().sum(0)) < 2e-6
+
+
+@pytest.mark.parametrize("geom", [(4, 30, 1260, 6, 500, 0), (3, 30, 90, 3, 16, 0), (2, 30, 2048, 8, 256, 0), (2, 7, 33, 5, 12, 0), (4, 30, 1260, 8, 256, 3)],
+                         ids=lambda g_: "B%dN%dF%dH%dC%dalgo%d" % g_)
+def test_projection_as_an_operand_pair(cuda_lib, geom):
+    """spotv2_proj_fwd_pair: P never exists in fp32 - the GEMM epilogue emits hi | lo planes in the padded head pitch with
+    the a-priori scale (max|x| * row-L1 bound), and the logit terms s | d in fp32 beside them.  Against an fp64 matmul:
+    hi + lo to 1e-5 of max|P| (fp32 class) or 2e-3 (half class: hi plane only), pad columns exactly zero, the bound holds."""
+    B, N, Fin, H, C_, algo = geom
+    n = B * N
+    d = GatDesc(B, N, Fin, 0, H, C_, 0, 0, 0.2, cuda_lib.spotv2_gat_ldp(H, C_), algo, 0, 0.0, 0, 0, 0, 1)
+    Cp, n_aug = cuda_lib.spotv2_gat_head_pitch(C.byref(d)), cuda_lib.spotv2_gat_n_aug(C.byref(d))
+    assert Cp % 8 == 0 and Cp >= C_ and n_aug == H * Cp + 2 * H
+    g = torch.Generator(device=DEV).manual_seed(Fin)
+    x = torch.randn(n, Fin, device=DEV, generator=g) * 3.0
+    W = torch.randn(H * C_, Fin, device=DEV, generator=g) * 0.05
+    a_s, a_d = torch.randn(1, H, C_, device=DEV, generator=g), torch.randn(1, H, C_, device=DEV, generator=g)
+    W_aug = torch.empty(n_aug, Fin, device=DEV)
+    check(cuda_lib.spotv2_gat_fold(C.byref(d), ptr(W), ptr(a_s), ptr(a_d), None, None, ptr(W_aug), None, st()), "fold")
+    Wv = W_aug[:H * Cp].view(H, Cp, Fin)
+    assert torch.equal(Wv[:, :C_].reshape(H * C_, Fin), W) and (Wv[:, C_:] == 0).all()      # padded rows are zero rows
+    ldx = cuda_lib.spotv2_gat_ld16(Fin)
+    x16, xblk = torch.empty(2, n, ldx, device=DEV, dtype=torch.float16), torch.empty(8, device=DEV)
+    check(cuda_lib.spotv2_split_f16(ptr(x), n, Fin, Fin, 0, 0, ptr(x16[0]), ptr(x16[1]), ldx, ptr(xblk), st()), "split_f16")
+    ldp16 = cuda_lib.spotv2_gat_ld16(n_aug)
+    P16 = torch.full((2, n, ldp16), float("nan"), device=DEV, dtype=torch.float16)
+    pblk, sd = torch.empty(8, device=DEV), torch.empty(n, 2 * H, device=DEV)
+    a_, _, _ = (C.c_size_t(), C.c_size_t(), C.c_size_t())
+    check(cuda_lib.spotv2_gat_workspace_bytes(C.byref(d), C.byref(a_), None, None), "ws")
+    ws = torch.empty(a_.value, device=DEV, dtype=torch.uint8)
+    check(cuda_lib.spotv2_proj_fwd_pair(C.byref(d), ptr(x16[0]), ptr(x16[1]), ptr(xblk), ptr(W_aug), ptr(P16[0]),
+                                        ptr(P16[1]) if algo != 3 else None, ptr(pblk), ptr(sd), ptr(ws), ws.numel(), st()), "proj_fwd_pair")
+    ref = x.double() @ W_aug.double().t()                                             # [n, n_aug]
+    full = P16[0, :, :n_aug].double() + (P16[1, :, :n_aug].double() if algo != 3 else 0.0)
+    P = full[:, :H * Cp] * pblk[2].double()
+    tol = 2e-3 if algo == 3 else TOL
+    assert relerr(P, ref[:, :H * Cp]) < tol
+    assert (full[:, :H * Cp].view(n, H, Cp)[:, :, C_:] == 0).all()                    # pad columns: exact zeros
+    assert relerr(sd, ref[:, H * Cp:]) < tol                                          # fp32 logit terms
+    assert relerr(full[:, H * Cp:] * pblk[3].double(), ref[:, H * Cp:]) < tol         # and their copy in the planes' second group
+    bound = pblk[:2].double()
+    assert ref[:, :H * Cp].abs().max() <= bound[0] and ref[:, H * Cp:].abs().max() <= bound[1]
+    assert (full.abs().max() < 32768.0) and float(pblk[4]) * float(pblk[2]) == 1.0
+
+
+@pytest.mark.parametrize("case", [(6, 30, 1260, 126, 6, 500, False), (5, 30, 64, 126, 8, 256, True), (4, 13, 9, 5, 3, 8, True), (7, 30, 90, 9, 3, 16, True),
+                                  (3, 30, 40, 0, 4, 36, False)],
+                         ids=lambda c: "B%dN%dF%dFe%dH%dC%d%s" % (c[:6] + ("cat" if c[6] else "mean",)))
+def test_both_projection_formats_agree(cuda_lib, case, monkeypatch):
+    """One layer step with P as fp32 (p_format 0) and as the operand pair (p_format 1): same operator, same logits (the
+    s | d terms and the edge terms are bit-identical by construction, so every LeakyReLU kink falls on the same side),
+    outputs and gradients equal to fp32 rounding."""
+    from spotv2net_b200 import gat_conv
+    B, N, Fin, Fe, H, C_, concat = case
+    torch.manual_seed(B)
+    layer = sv.GATConv(Fin, C_, heads=H, concat=concat, edge_dim=Fe or None).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x0 = torch.randn(B * N, Fin, device=DEV, generator=g)
+    ea = torch.randn(B * N * (N - 1), Fe, device=DEV, generator=g) if Fe else None
+    dout = torch.randn(B * N, H * C_ if concat else C_, device=DEV, generator=g)
+    ei, _ = sv.batched_topology(B, N, DEV)
+    res = {}
+    for pf in (0, 1):
+        monkeypatch.setattr(gat_conv, "P_FORMAT", pf)
+        layer.zero_grad()
+        x = x0.clone().requires_grad_()
+        out = layer(x, ei, ea)
+        out.backward(dout)
+        res[pf] = dict(out=out.detach(), dx=x.grad, **{k: p.grad.clone() for k, p in layer.named_parameters() if p.grad is not None})
+    for k in res[0]:
+        assert relerr(res[1][k], res[0][k]) < 2e-6, k
