@@ -68,10 +68,17 @@ __device__ __forceinline__ void wait_id(uint64_t* bar, uint32_t parity, int id, 
     if (clock64() - t0 > 400000000LL) { wait_report(id, it, parity); __trap(); }
   }
 }
+// role counters cost ~4 K cycles per graph on the logit warps' critical path: compiled in with -DSPOTV2_BRINGUP only
+// (tools/fwd16_waits.py reads them); the product build measures nothing
+#ifdef SPOTV2_BRINGUP
+__device__ __forceinline__ long long tick() { return clock64(); }
+#else
+__device__ __forceinline__ long long tick() { return 0; }
+#endif
 __device__ __forceinline__ void wait_id_t(uint64_t* bar, uint32_t parity, int id, int it, long long& acc) {
-  const long long t0 = clock64();
+  const long long t0 = tick();
   wait_id(bar, parity, id, it);
-  acc += clock64() - t0;
+  acc += tick() - t0;
 }
 __device__ __forceinline__ void split_raw(float x, uint32_t& hi, uint32_t& lo) {    // tf32: hi = raw fp32 (top 19 bits are read)
   hi = __float_as_uint(x);
@@ -164,7 +171,7 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
     }
     int k = 0;
     long long w_ring = 0, w_te = 0, t_log = 0, t_bar = 0, t_out = 0;
-    const long long t_role = clock64();
+    const long long t_role = tick();
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
       const int buf = it & 1;
@@ -192,7 +199,7 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
           for (int idx = tid; idx < rows * p.Fe; idx += kGA) stage[s][idx] = src[idx];
           bar_a();
         }
-        const long long tl0 = clock64();
+        const long long tl0 = tick();
         if (warp * 16 < rows) {
           const uint32_t r0 = ring_a[s] + (uint32_t)(((warp * 16 + 2 * g) * p.Fe + t) * 4), r1 = r0 + (uint32_t)(p.Fe * 4);
           // (same summation order as attn_fwd.cu: the edge terms - and with them every LeakyReLU kink - are bit-identical in
@@ -254,10 +261,10 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
             if (2 * t + 1 < H) q_sts(tb + head_bytes + (uint32_t)to1, res[3]);
           }
         }
-        const long long tl1 = clock64();
+        const long long tl1 = tick();
         bar_a();
         t_log += tl1 - tl0;
-        t_bar += clock64() - tl1;
+        t_bar += tick() - tl1;
         if (p.bulk_ok && tid == 0 && k + 2 < total_chunks) issue(k + 2);
       }
       if (p.edge_terms && !p.terms_in && NS == kEdgeTermNS) {
@@ -265,7 +272,7 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
         // by the copy engine (a thread-by-thread copy sat in the LSU queue for ~12 K cycles per graph).  The generic-proxy
         // scatters are fenced and behind a barrier; thread 0 holds its arrival on tile_full until the engine has read
         // the tile, because the softmax group rewrites it in place.
-        const long long to0 = clock64();
+        const long long to0 = tick();
         fence_proxy_async();
         bar_a();
         if (tid == 0) {
@@ -275,14 +282,14 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
-        t_out += clock64() - to0;
+        t_out += tick() - to0;
       }
       arrive(&tile_full[buf]);
     }
     if (tid == 0) {
       atomicAdd(&g_fwd16_counters[0], (unsigned long long)w_ring);
       atomicAdd(&g_fwd16_counters[1], (unsigned long long)w_te);
-      atomicAdd(&g_fwd16_counters[5], (unsigned long long)(clock64() - t_role));
+      atomicAdd(&g_fwd16_counters[5], (unsigned long long)(tick() - t_role));
       atomicAdd(&g_fwd16_counters[8], (unsigned long long)t_log);
       atomicAdd(&g_fwd16_counters[12], (unsigned long long)t_bar);
       atomicAdd(&g_fwd16_counters[13], (unsigned long long)t_out);
@@ -306,23 +313,23 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
     const float k_out = p.p_blk[2] / pl.s_alpha;          // accumulator -> out
     uint32_t q_base = 0;
     long long w_tf = 0, w_pf = 0, w_sd = 0, t_smx = 0, t_cnv = 0;
-    const long long t_role = clock64();
+    const long long t_role = tick();
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
       const int buf = it & 1;
       float* tile = tile0 + buf * tile_floats;
       float* sd = sd0 + buf * sd_floats;
-      const long long tc0 = clock64();
+      const long long tc0 = tick();
       // s | d of this graph: fp32, as the GEMM accumulated them (L2-resident: written one kernel ago)
       for (int idx = tb_; idx < sd_floats; idx += kGB) sd[idx] = __ldg(p.sd32 + (size_t)b * sd_floats + idx);
-      const long long tc1 = clock64();
+      const long long tc1 = tick();
       wait_id_t(&tile_full[buf], (it >> 1) & 1, 4, it, w_tf);
-      const long long ts0 = clock64();
+      const long long ts0 = tick();
       bar_b();                                           // sd complete (and everyone is past the previous graph's MMAs)
       softmax_phase(p, AttnSmem{NS, pl.KS, 1, pl.chunk_rows, 0, 0, 0, 0, 0, 0, 0, 0}, tile, sd, out_scale,
                     args.alpha_out ? args.alpha_out + (size_t)b * H * N * N : nullptr, nullptr, tb_, kGB, -1, 0, nullptr, b);
       bar_b();                                           // alpha tile complete
-      const long long tc2 = clock64();
+      const long long tc2 = tick();
       t_smx += tc2 - ts0;
       // alpha[h][j][i] fp32 -> fp16 hi | lo tiles [h][i][j] (64-byte rows, swizzled): the A operand of the aggregation
       {
@@ -344,7 +351,7 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
       if (p.terms_in) fence_proxy_async();               // generic-proxy writes to the tile precede the next bulk copy into it
       arrive(&tile_empty[buf]);                          // the fp32 tile is free for the logit group
       bar_b();                                           // alpha pair tiles complete
-      t_cnv += (tc1 - tc0) + (clock64() - tc2);
+      t_cnv += (tc1 - tc0) + (tick() - tc2);
       for (int pass = 0; pass < n_pass; ++pass) {
         const int G = min(kCbPass, n_cb - pass * kCbPass);
         const bool mine = wb < G;
@@ -457,7 +464,7 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
     if (tid == kGA) {
       atomicAdd(&g_fwd16_counters[2], (unsigned long long)w_tf);
       atomicAdd(&g_fwd16_counters[3], (unsigned long long)w_pf);
-      atomicAdd(&g_fwd16_counters[6], (unsigned long long)(clock64() - t_role));
+      atomicAdd(&g_fwd16_counters[6], (unsigned long long)(tick() - t_role));
       atomicAdd(&g_fwd16_counters[9], (unsigned long long)t_smx);
       atomicAdd(&g_fwd16_counters[10], (unsigned long long)t_cnv);
       atomicAdd(&g_fwd16_counters[11], (unsigned long long)w_sd);
@@ -471,7 +478,7 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
       if (!SINGLE) prefetch_tmap(&tmL);
       uint32_t q = 0;
       long long w_pe = 0;
-      const long long t_role = clock64();
+      const long long t_role = tick();
       for (int it = 0; it < my_graphs; ++it) {
         const int b = blockIdx.x + it * gridDim.x;
         for (int pass = 0; pass < n_pass; ++pass) {
@@ -489,7 +496,7 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
         }
       }
       atomicAdd(&g_fwd16_counters[4], (unsigned long long)w_pe);
-      atomicAdd(&g_fwd16_counters[7], (unsigned long long)(clock64() - t_role));
+      atomicAdd(&g_fwd16_counters[7], (unsigned long long)(tick() - t_role));
     }
   }
 }
