@@ -19,6 +19,7 @@ namespace {
 
 constexpr int kGA = 96, kGB = 256, kF16Threads = kGA + kGB + 32;
 constexpr int kChunkRows = 48;
+constexpr int kEdgeStages = 3;        // edge-row ring depth: two chunks in flight while a third is consumed
 constexpr int kSlotBytes = 4096;      // per tile: hi (2 KB) + lo (2 KB); a slot holds `grp` tiles: [hi tiles][lo tiles]
 constexpr int kMaxPSlots = 24;
 constexpr int kCbPass = 8;
@@ -103,12 +104,10 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
   const int tile_floats = H * N * NS;
   const int n_slots = pl.n_slots;
 
-  // barriers: [0,1] edge ring, [2,3] tile_full, [4,5] tile_empty, [6,7] sd_full, [8,9] sd_empty, then slot full / empty
+  // barriers: [0,3) edge ring, [4,5] tile_full, [6,7] tile_empty, then slot full / empty
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + pl.off_bar);
-  uint64_t* tile_full = bars + 2;
-  uint64_t* tile_empty = bars + 4;
-  uint64_t* sd_full = bars + 6;
-  uint64_t* sd_empty = bars + 8;
+  uint64_t* tile_full = bars + 4;
+  uint64_t* tile_empty = bars + 6;
   uint64_t* p_full = bars + 10;
   uint64_t* p_empty = p_full + kMaxPSlots;
   const int n_cb = (C + 31) / 32;
@@ -123,13 +122,10 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
   const int my_graphs = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    for (int r = 0; r < kEdgeStages; ++r) mbar_init(&bars[r], 1);
     for (int r = 0; r < 2; ++r) {
       mbar_init(&tile_full[r], kGA);
       mbar_init(&tile_empty[r], kGB);
-      mbar_init(&sd_full[r], 1);
-      mbar_init(&sd_empty[r], 1);
     }
     for (int r = 0; r < n_slots; ++r) { mbar_init(&p_full[r], 1); mbar_init(&p_empty[r], grp); }
     fence_mbar_init();
@@ -152,22 +148,21 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const uint32_t sbase = smem_u32(smem_raw);
-    const uint32_t ring_a[2] = {sbase + pl.off_ring, sbase + pl.off_ring + pl.ring_stage};
+    const uint32_t ring_a0 = sbase + pl.off_ring;
     const uint32_t a_vfrag = sbase + pl.off_vfrag, a_table = sbase + pl.off_table;
     const uint32_t a_tile0 = sbase + pl.off_tile, head_bytes = (uint32_t)(N * NS * 4);
-    float* stage[2] = {reinterpret_cast<float*>(smem_raw + pl.off_ring), reinterpret_cast<float*>(smem_raw + pl.off_ring + pl.ring_stage)};
+    auto stage = [&](int s_) { return reinterpret_cast<float*>(smem_raw + pl.off_ring + (size_t)s_ * pl.ring_stage); };
     const int total_chunks = my_graphs * nchunks;
     auto rows_in = [&](int c) { const int r = p.R - c * pl.chunk_rows; return r < pl.chunk_rows ? r : pl.chunk_rows; };
     auto issue = [&](int k) {
       const int it = k / nchunks, c = k - it * nchunks;
       const int b = blockIdx.x + it * gridDim.x;
       const uint32_t bytes = (uint32_t)rows_in(c) * p.Fe * 4u;
-      mbar_expect_tx(&bars[k & 1], bytes);
-      bulk_g2s(stage[k & 1], p.edge_rows + ((size_t)b * p.R + (size_t)c * pl.chunk_rows) * p.Fe, bytes, &bars[k & 1]);
+      mbar_expect_tx(&bars[k % kEdgeStages], bytes);
+      bulk_g2s(stage(k % kEdgeStages), p.edge_rows + ((size_t)b * p.R + (size_t)c * pl.chunk_rows) * p.Fe, bytes, &bars[k % kEdgeStages]);
     };
     if (p.bulk_ok && tid == 0) {
-      if (total_chunks > 0) issue(0);
-      if (total_chunks > 1) issue(1);
+      for (int k0 = 0; k0 < kEdgeStages && k0 < total_chunks; ++k0) issue(k0);
     }
     int k = 0;
     long long w_ring = 0, w_te = 0, t_log = 0, t_bar = 0, t_out = 0;
@@ -190,18 +185,18 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
       if (nchunks == 0)
         for (int idx = tid; idx < tile_floats; idx += kGA) tile[idx] = 0.f;
       for (int c = 0; c < nchunks; ++c, ++k) {
-        const int s = k & 1;
+        const int s = k % kEdgeStages;
         const int rows = rows_in(c);
         if (p.bulk_ok) {
-          wait_id_t(&bars[s], (k >> 1) & 1, 2, it, w_ring);
+          wait_id_t(&bars[s], (k / kEdgeStages) & 1, 2, it, w_ring);
         } else {
           const float* src = p.edge_rows + ((size_t)b * p.R + (size_t)c * pl.chunk_rows) * p.Fe;
-          for (int idx = tid; idx < rows * p.Fe; idx += kGA) stage[s][idx] = src[idx];
+          for (int idx = tid; idx < rows * p.Fe; idx += kGA) stage(s)[idx] = src[idx];
           bar_a();
         }
         const long long tl0 = tick();
         if (warp * 16 < rows) {
-          const uint32_t r0 = ring_a[s] + (uint32_t)(((warp * 16 + 2 * g) * p.Fe + t) * 4), r1 = r0 + (uint32_t)(p.Fe * 4);
+          const uint32_t r0 = ring_a0 + (uint32_t)s * pl.ring_stage + (uint32_t)(((warp * 16 + 2 * g) * p.Fe + t) * 4), r1 = r0 + (uint32_t)(p.Fe * 4);
           // (same summation order as attn_fwd.cu: the edge terms - and with them every LeakyReLU kink - are bit-identical in
           // both formats; two accumulator sets were tried and bought nothing: the phase is bound by per-warp issue)
           float acc[3][4];
@@ -265,7 +260,7 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
         bar_a();
         t_log += tl1 - tl0;
         t_bar += tick() - tl1;
-        if (p.bulk_ok && tid == 0 && k + 2 < total_chunks) issue(k + 2);
+        if (p.bulk_ok && tid == 0 && k + kEdgeStages < total_chunks) issue(k + kEdgeStages);
       }
       if (p.edge_terms && !p.terms_in && NS == kEdgeTermNS) {
         // keep the edge terms for the backward (6 floats per edge instead of the Fe-wide rows): ONE bulk store of the tile
@@ -541,7 +536,7 @@ int attn_fwd16_dispatch(const AttnFwdArgs& a, cudaStream_t st) {
     pl.off_alo = (uint32_t)o;    o += (size_t)p.H * 2048;
     pl.off_ring = (uint32_t)o;
     pl.ring_stage = (uint32_t)round_up((size_t)rows * p.Fe * 4, 128);
-    o += (p.Fe > 0 && !p.terms_in) ? 2 * (size_t)pl.ring_stage + 256 : 0;     // + zero pad behind the ring (k-steps past Fe)
+    o += (p.Fe > 0 && !p.terms_in) ? kEdgeStages * (size_t)pl.ring_stage + 256 : 0;     // + zero pad behind the ring (k-steps past Fe)
     o = round_up(o, 1024);
     pl.off_sdslot = (uint32_t)o;                           // (end of the zero-filled region; the P slots start here)
     pl.off_slots = (uint32_t)o;
