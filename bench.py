@@ -592,7 +592,7 @@ def run_config_c(args):
     res, attn_ms = {}, {}
     for prec in ("fp32", "half"):
         model.set_precision(prec)
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(max(args.warmup, 3) + 2):          # (+2: the first mode also pays the caching allocator's growth)
             step()
         torch.cuda.synchronize(dev)
         if prec == "half":
