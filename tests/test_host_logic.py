@@ -67,3 +67,28 @@ def test_unsupported_layer_options_fail_loudly():
 def test_edge_index_order_matches_reference_dataset():
     for N in (2, 5, 30):
         assert torch.equal(sv.complete_graph_edge_index(N), synth.complete_graph_edge_index(N))
+
+
+def test_projection_format_choice_and_padded_sizes():
+    """Host-side rule for spotv2_gat_desc.p_format (gat_conv.pair_format_applies / _desc) and the sizes that follow from it
+    (no GPU: spotv2_gat_n_aug / spotv2_gat_head_pitch are plain host functions of the descriptor)."""
+    import ctypes as C
+    from spotv2net_b200 import _lib, gat_conv
+    ok = gat_conv.pair_format_applies
+    assert ok(30, 126, 500, 0, 0) and ok(30, 126, 256, 3, 2, concat=True) and ok(1, 0, 4, 0, 0)
+    assert not ok(33, 126, 500, 0, 0)              # several CTAs per graph: fp32 P_aug
+    assert not ok(30, 126, 500, 1, 0)              # CUDA-core GEMM
+    assert not ok(30, 126, 500, 0, 1)              # phase-serial backward
+    assert not ok(30, 126, 502, 0, 0)              # dout tiles by TMA need C % 4 == 0
+    assert not ok(30, 126, 36, 0, 0, concat=True)  # concat layers: head blocks of dout start on 16-byte boundaries only if C % 8 == 0
+    assert not ok(30, 400, 500, 0, 0) and not ok(30, 126, 1028, 0, 0)
+    lib = _lib.load()
+    topo = gat_conv.Topology(4, 30, 870, None, False)
+    d1 = gat_conv._desc(topo, 1260, 126, 6, 500, False, 0.2)
+    assert d1.p_format == 1 and lib.spotv2_gat_head_pitch(C.byref(d1)) == 504 and lib.spotv2_gat_n_aug(C.byref(d1)) == 6 * 504 + 12
+    d0 = gat_conv._desc(topo, 1260, 126, 6, 500, False, 0.2, p_format=0)
+    assert d0.p_format == 0 and lib.spotv2_gat_head_pitch(C.byref(d0)) == 500 and lib.spotv2_gat_n_aug(C.byref(d0)) == 3012
+    dc = gat_conv._desc(topo, 1260, 126, 8, 256, True, 0.2, gemm_algo=3)
+    assert dc.p_format == 1 and lib.spotv2_gat_head_pitch(C.byref(dc)) == 256
+    bad = _lib.GatDesc(4, 40, 1260, 126, 6, 500, 1560, 0, 0.2, 3012, 0, 0, 0.0, 0, 0, 0, 1)
+    assert lib.spotv2_gat_workspace_bytes(C.byref(bad), None, None, None) != 0 and b"p_format 1" in lib.spotv2_last_error()
