@@ -309,14 +309,34 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
     uint32_t q_base = 0;
     long long w_tf = 0, w_pf = 0, w_sd = 0, t_smx = 0, t_cnv = 0;
     const long long t_role = tick();
+    // s | d (fp32, as the GEMM accumulated them; N * 2H <= 512 values per graph): fetched one graph ahead into two registers
+    // per thread, so that the global-load latency never sits in front of a softmax
+    float sd_nx[2] = {0.f, 0.f};
+    auto fetch_sd = [&](int b_) {
+#pragma unroll
+      for (int r_ = 0; r_ < 2; ++r_) {
+        const int idx = tb_ + r_ * kGB;
+        sd_nx[r_] = idx < sd_floats ? __ldg(p.sd32 + (size_t)b_ * sd_floats + idx) : 0.f;
+      }
+    };
+    if (my_graphs > 0) fetch_sd(blockIdx.x);
+    // slot cursor of this warp's next P-tile group: advanced by the groups of every (pass, head) step (no division in the loop)
+    int cur_slot = 0;
+    uint32_t cur_ph = 0;
+    auto advance = [&](int k_) {
+      cur_slot += k_;
+      while (cur_slot >= n_slots) { cur_slot -= n_slots; cur_ph ^= 1u; }
+    };
     for (int it = 0; it < my_graphs; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
       const int buf = it & 1;
       float* tile = tile0 + buf * tile_floats;
       float* sd = sd0 + buf * sd_floats;
       const long long tc0 = tick();
-      // s | d of this graph: fp32, as the GEMM accumulated them (L2-resident: written one kernel ago)
-      for (int idx = tb_; idx < sd_floats; idx += kGB) sd[idx] = __ldg(p.sd32 + (size_t)b * sd_floats + idx);
+#pragma unroll
+      for (int r_ = 0; r_ < 2; ++r_)
+        if (tb_ + r_ * kGB < sd_floats) sd[tb_ + r_ * kGB] = sd_nx[r_];
+      if (it + 1 < my_graphs) fetch_sd(b + gridDim.x);
       const long long tc1 = tick();
       wait_id_t(&tile_full[buf], (it >> 1) & 1, 4, it, w_tf);
       const long long ts0 = tick();
@@ -398,7 +418,7 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
         if (!p.concat) load_bias(0);
         const int n_g = (G + grp - 1) / grp;               // tile groups (ring slots) of one (pass, head) step
         const int gi = wb / grp, ti = wb - gi * grp;       // this warp's group and its tile inside it
-        for (int h = 0; h < H; ++h, q_base += n_g) {
+        for (int h = 0; h < H; ++h, q_base += n_g, advance(n_g)) {
           if (gi >= n_g) continue;
           if (p.concat) load_bias(h * C);
           uint32_t ah[2][2][4], al[2][2][4];
@@ -413,13 +433,14 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
                 if (!SINGLE) ldsm_x4(a_alo + o, al[m][ks][0], al[m][ks][1], al[m][ks][2], al[m][ks][3]);
               }
           }
-          const uint32_t q = q_base + gi;
-          const int slot = q % n_slots;
+          int slot = cur_slot + gi;
+          uint32_t sph = cur_ph;
+          while (slot >= n_slots) { slot -= n_slots; sph ^= 1u; }
           // A slot's consecutive uses may belong to different warps: a warp that runs ahead must not take the slot's
           // PREVIOUS fill for its own (the parity test cannot tell fill r from fill r - 2), so it first waits until the
           // previous use has been released - only then can fill r be pending.
-          wait_id_t(&p_empty[slot], ((q / n_slots) & 1) ^ 1, 8, it, w_pf);
-          wait_id_t(&p_full[slot], (q / n_slots) & 1, 5, it, w_pf);
+          wait_id_t(&p_empty[slot], sph ^ 1u, 8, it, w_pf);
+          wait_id_t(&p_full[slot], sph, 5, it, w_pf);
           if (mine) {
             const uint32_t th = a_slots + (uint32_t)slot * slot_bytes + (uint32_t)ti * 2048u, tl = th + (uint32_t)grp * 2048u;
 #pragma unroll
