@@ -22,7 +22,7 @@ __device__ __forceinline__ float unit_scale(float amax) {   // same rule as gemm
 
 // KP: column pairs per thread (C <= 512 * KP).  grid: a multiple of units_per_graph, so a CTA only ever sees one head.
 template <int KP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, KP == 1 ? 3 : 1)      // three CTAs per SM: one loading, one reducing, one storing
 dout_pair_kernel(const float* __restrict__ dout, int n_units, int N, int C, int upg, int ldo, __half* __restrict__ hi,
                  __half* __restrict__ lo, int ld16, float* __restrict__ scales, unsigned* __restrict__ amax_bits,
                  float* __restrict__ dbias_part) {
@@ -98,7 +98,7 @@ dout_pair_kernel(const float* __restrict__ dout, int n_units, int N, int C, int 
 }  // namespace
 
 int dout_pair_grid(int n_units, int upg) {
-  int grid = 4 * sm_count();
+  int grid = 6 * sm_count();
   if (grid > n_units) grid = n_units;
   grid = grid / upg * upg;
   return grid < upg ? upg : grid;
