@@ -346,4 +346,68 @@ __device__ __forceinline__ void softmax_phase(const AttnParams& p, const AttnSme
   }
 }
 
+
+// The same phase with the row held in registers between the passes (N <= 32): one pass of shared-memory loads and one of
+// stores per row instead of four and three.  Arithmetic and its order are those of softmax_phase - the results are
+// bit-identical (the LeakyReLU kinks and the attention coefficients of the forward and of the recomputing backward must
+// not depend on which of the two a kernel calls).  sd is the packed [N][2H] array.
+__device__ __forceinline__ void softmax_phase_regs(const AttnParams& p, int NS, float* tile, const float* sd, float out_scale,
+                                                   float* alpha_out_b, uint32_t* pos_mask, int tid, int nthreads,
+                                                   const float* tile_add = nullptr, int drop_graph = -1) {
+  const int N = p.N, H = p.H;
+  for (int idx = tid; idx < H * N; idx += nthreads) {
+    const int h = idx / N, i = idx - h * N;
+    float* col = tile + (size_t)h * N * NS + i;
+    float r[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = j < N ? col[j * NS] : 0.f;
+    if (tile_add) {
+      const float* col2 = tile_add + (size_t)h * N * NS + i;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < N && j != i) r[j] += col2[j * NS];
+    }
+    float gsum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < N) gsum += (j != i) ? r[j] : 0.f;
+    const float gii = gsum / (float)(N > 1 ? N - 1 : 1);
+    const float di = sd[i * 2 * H + H + h];
+    float mx = -INFINITY;
+    uint32_t mask = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < N) {
+        const float z = (j == i ? gii : r[j]) + sd[j * 2 * H + h] + di;
+        if (z > 0.f) mask |= 1u << j;
+        const float l = z > 0.f ? z : z * p.slope;
+        mx = fmaxf(mx, l);
+        r[j] = l;
+      }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < N) {
+        const float e = expf(r[j] - mx);
+        sum += e;
+        r[j] = e;
+      }
+    const float inv = 1.f / (sum + 1e-16f);
+    uint32_t keep = 0xffffffffu;
+    float kscale = 1.f;
+    if (drop_graph >= 0 && p.drop.p > 0.f) {
+      keep = dropout_keep_bits(p.drop, (((unsigned long long)drop_graph * H + h) * N + i) * N, N);
+      kscale = p.drop.scale;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < N) {
+        const float a = ((keep >> j) & 1u) ? r[j] * inv * kscale : 0.f;
+        if (alpha_out_b) alpha_out_b[((size_t)h * N + j) * N + i] = a;
+        col[j * NS] = a * out_scale;
+      }
+    if (pos_mask) pos_mask[idx] = mask;
+  }
+}
+
 }  // namespace spotv2

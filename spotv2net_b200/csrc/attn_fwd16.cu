@@ -341,8 +341,8 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
       wait_id_t(&tile_full[buf], (it >> 1) & 1, 4, it, w_tf);
       const long long ts0 = tick();
       bar_b();                                           // sd complete (and everyone is past the previous graph's MMAs)
-      softmax_phase(p, AttnSmem{NS, pl.KS, 1, pl.chunk_rows, 0, 0, 0, 0, 0, 0, 0, 0}, tile, sd, out_scale,
-                    args.alpha_out ? args.alpha_out + (size_t)b * H * N * N : nullptr, nullptr, tb_, kGB, -1, 0, nullptr, b);
+      softmax_phase_regs(p, NS, tile, sd, out_scale, args.alpha_out ? args.alpha_out + (size_t)b * H * N * N : nullptr, nullptr, tb_,
+                         kGB, nullptr, b);
       bar_b();                                           // alpha tile complete
       const long long tc2 = tick();
       t_smx += tc2 - ts0;
