@@ -544,9 +544,15 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
   };
 
   float dsd_max = 0.f;                   // max |ds|, |dd| this thread wrote: sizes the fp16 scale of the ds|dd operand columns
+  // phase cycle counters (spotv2_diag_counters, tools/fwd_waits.py): 14 registers that stay live across the whole kernel -
+  // compiled in with -DSPOTV2_BRINGUP only (the product build spilled because of them)
+#ifdef SPOTV2_BRINGUP
   long long ph[6] = {0, 0, 0, 0, 0, 0};
   long long t_ph = clock64();
   auto lap = [&](int k) { const long long now = clock64(); ph[k] += now - t_ph; t_ph = now; };
+#else
+  auto lap = [&](int) {};
+#endif
 
   for (int it = 0; it < my_graphs; ++it) {
     const int b = blockIdx.x + it * gridDim.x;
@@ -1163,8 +1169,10 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
     lap(4);
   }
   if (P16 && pl.stage_ok && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this lane's dP stores have landed
+#ifdef SPOTV2_BRINGUP
   if (tid == 0)
     for (int k = 0; k < 6; ++k) atomicAdd(&g_bwd2_counters[k], (unsigned long long)ph[k]);
+#endif
   if (args.dsd_amax) {
     for (int o = 16; o > 0; o >>= 1) dsd_max = fmaxf(dsd_max, __shfl_xor_sync(0xffffffffu, dsd_max, o));
     if (lane == 0 && dsd_max > 0.f) atomicMax(args.dsd_amax, __float_as_uint(dsd_max));

@@ -1,4 +1,5 @@
-"""GPU box: where each warp role of the p_format 1 forward spends its cycles (spotv2_diag_counters), materialised and structured."""
+"""(Counters exist only in a bring-up build: `SPOTV2_BRINGUP=1 python -m spotv2net_b200.build -f` before shipping to the box.)
+GPU box: where each warp role of the p_format 1 forward spends its cycles (spotv2_diag_counters), materialised and structured."""
 import ctypes as C, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,4 +1,5 @@
-"""GPU box: run the forward attention kernel at B=4096 and print where each warp role spends its cycles
+"""(Counters exist only in a bring-up build: `SPOTV2_BRINGUP=1 python -m spotv2net_b200.build -f` before shipping to the box.)
+GPU box: run the forward attention kernel at B=4096 and print where each warp role spends its cycles
 (spotv2_diag_counters), plus the single failing odd-shape case under CUDA_LAUNCH_BLOCKING."""
 import ctypes as C, os, sys
 import torch
