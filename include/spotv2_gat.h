@@ -115,6 +115,10 @@ int32_t spotv2_gat_ldp(int32_t H, int32_t C);
  * Cp = C (p_format 0) or C rounded up to 8 (p_format 1); head h's channel c sits at h*Cp + c, s_h at H*Cp + h,
  * d_h at H*Cp + H + h. */
 int32_t spotv2_gat_n_aug(const spotv2_gat_desc* d);
+/* 1 when the p_format 1 kernels cover this problem (N <= 32, tensor-core GEMM, pipelined backward, C % 4 == 0 - % 8 for
+ * concat layers -, C <= 1024, and the shared-memory plans of both attention kernels fit), else 0: use p_format 0.
+ * The descriptor's own p_format field is ignored.  Host-side, no device work. */
+int spotv2_gat_pair_format_supported(const spotv2_gat_desc* d);
 int32_t spotv2_gat_head_pitch(const spotv2_gat_desc* d);
 
 /* Bytes of scratch each phase wants (device memory, 256-byte aligned). */

@@ -36,6 +36,7 @@ SIGNATURES = {
     "spotv2_abi_version": (_i32, []),
     "spotv2_gat_ldp": (_i32, [_i32, _i32]),
     "spotv2_gat_n_aug": (_i32, [_DP]),
+    "spotv2_gat_pair_format_supported": (C.c_int, [_DP]),
     "spotv2_gat_head_pitch": (_i32, [_DP]),
     "spotv2_gat_workspace_bytes": (C.c_int, [_DP, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
     "spotv2_proj_fwd_pair": (C.c_int, [_DP] + [_vp] * 9 + [_sz, _vp]),

@@ -899,3 +899,20 @@ extern "C" int spotv2_gat_attn_bwd_pair(const spotv2_gat_desc* d, const void* P_
   SPOTV2_CUDA_OK(cudaGetLastError());
   return SPOTV2_OK;
 }
+
+
+// 1 when every p_format 1 kernel covers this problem (shapes, alignment rules and the shared-memory plans of the forward
+// and of the pipelined backward); callers fall back to p_format 0 otherwise.  Host-side only: no device work.
+extern "C" int spotv2_gat_pair_format_supported(const spotv2_gat_desc* d) {
+  if (!d || d->B <= 0 || d->N <= 0 || d->N > 32 || d->H <= 0 || d->H > kMaxHeads || d->C <= 0 || d->Fe < 0 || d->Fe > kMaxFe) return 0;
+  if (d->gemm_algo == 1 || d->attn_bwd_algo == 1 || d->attn_bwd_algo == 3) return 0;
+  if (d->C % 4 != 0 || d->C > 1024 || (d->concat && d->C % 8 != 0)) return 0;
+  AttnParams p{};
+  p.B = d->B; p.N = d->N; p.F = d->F; p.Fe = d->Fe; p.H = d->H; p.C = d->C; p.R = d->R; p.concat = d->concat; p.ldp = d->ldp;
+  p.ldo = d->concat ? d->H * d->C : d->C;
+  p.drop = dropout_params(d);
+  p.terms_in = (d->edge_mode == 1 && d->Fe > 0) ? 1 : 0;
+  p.hp = (d->C + 7) / 8 * 8;
+  p.ldp16 = ld16_of(d->H * p.hp + 2 * d->H);
+  return (attn_fwd16_fits(p) && attn_bwd2_fits(p)) ? 1 : 0;
+}

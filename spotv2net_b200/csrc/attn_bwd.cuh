@@ -17,6 +17,7 @@ struct AttnFwdArgs {
 };
 // p_format 1 forward (attn_fwd16.cu): P as an fp16 operand pair, aggregation on m16n8k16 from ldmatrix fragments
 int attn_fwd16_dispatch(const AttnFwdArgs& a, cudaStream_t st);
+bool attn_fwd16_fits(const AttnParams& p);                        // its shared-memory plan fits this problem
 int fwd16_diag_add(unsigned long long* host_out, int reset);     // adds its role counters into host_out[0..15]
 
 // ldmatrix: four 8x8 b16 matrices; lane l supplies the address of row (l & 7) of matrix (l >> 3)

@@ -530,11 +530,8 @@ int fwd16_diag_add(unsigned long long* host_out, int reset) {
   return SPOTV2_OK;
 }
 
-int attn_fwd16_dispatch(const AttnFwdArgs& a, cudaStream_t st) {
-  const AttnParams& p = a.p;
-  if (p.N > 32) return fail(SPOTV2_ERR_UNSUPPORTED, "attn_fwd (p_format 1): N=%d > 32", p.N);
-  if (p.hp % 8 != 0 || p.ldp16 % 8 != 0) return fail(SPOTV2_ERR_INVALID_ARG, "attn_fwd (p_format 1): head pitch and ld16 must be multiples of 8");
-  const bool single = p.P_lo == nullptr;
+// Shared-memory carve-up of the p_format 1 forward for a problem; n_slots * grp < 4 means it does not fit.
+static Fwd16Plan fwd16_plan(const AttnParams& p) {
   Fwd16Plan pl{};
   pl.NS = 36;
   pl.KS = ((p.Fe + 7) / 8 + 7) / 8 * 8;
@@ -572,6 +569,21 @@ int attn_fwd16_dispatch(const AttnFwdArgs& a, cudaStream_t st) {
   pl.grp = ((p.H - 1) * p.hp + (n_cb_ + 3) / 4 * 4 * 32 <= p.ldp16) ? 4 : 1;
   layout(kChunkRows);
   for (int rows = kChunkRows - 16; rows >= 16 && pl.n_slots * pl.grp < 12; rows -= 16) layout(rows);
+  return pl;
+}
+
+bool attn_fwd16_fits(const AttnParams& p) {
+  if (p.N > 32 || p.H > kMaxHeads || p.Fe > kMaxFe || p.hp % 8 != 0 || p.ldp16 % 8 != 0) return false;
+  const Fwd16Plan pl = fwd16_plan(p);
+  return pl.n_slots * pl.grp >= 4;
+}
+
+int attn_fwd16_dispatch(const AttnFwdArgs& a, cudaStream_t st) {
+  const AttnParams& p = a.p;
+  if (p.N > 32) return fail(SPOTV2_ERR_UNSUPPORTED, "attn_fwd (p_format 1): N=%d > 32", p.N);
+  if (p.hp % 8 != 0 || p.ldp16 % 8 != 0) return fail(SPOTV2_ERR_INVALID_ARG, "attn_fwd (p_format 1): head pitch and ld16 must be multiples of 8");
+  const bool single = p.P_lo == nullptr;
+  Fwd16Plan pl = fwd16_plan(p);
   if (pl.n_slots * pl.grp < 4) return fail(SPOTV2_ERR_UNSUPPORTED, "attn_fwd (p_format 1): shared-memory plan does not fit (Fe=%d, H=%d)", p.Fe, p.H);
   CUtensorMap tmH, tmL;
   const uint64_t rows = (uint64_t)p.B * p.N, cols = (uint64_t)p.H * p.hp + 2 * p.H;

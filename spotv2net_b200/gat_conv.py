@@ -159,11 +159,14 @@ def _desc(topo: Topology, F_in: int, Fe: int, H: int, Cc: int, concat: bool, slo
     algo = GEMM_ALGO if gemm_algo is None else gemm_algo
     if p_format is None:
         p_format = P_FORMAT
-    if p_format is None:
-        p_format = 1 if pair_format_applies(topo.N, Fe, Cc, algo, ATTN_BWD_ALGO, bool(concat)) else 0
-    return GatDesc(topo.B, topo.N, F_in, Fe, H, Cc, topo.R, int(concat), float(slope),
-                   lib.spotv2_gat_ldp(H, Cc), algo, ATTN_BWD_ALGO,
-                   float(dropout_p), int(edge_mode), seed & 0xffffffff, (seed >> 32) & 0xffffffff, int(p_format))
+    d = GatDesc(topo.B, topo.N, F_in, Fe, H, Cc, topo.R, int(concat), float(slope),
+                lib.spotv2_gat_ldp(H, Cc), algo, ATTN_BWD_ALGO,
+                float(dropout_p), int(edge_mode), seed & 0xffffffff, (seed >> 32) & 0xffffffff, 0)
+    if p_format is None:      # the library's own answer (shape rules AND the kernels' shared-memory plans); else p_format 0
+        p_format = 1 if (pair_format_applies(topo.N, Fe, Cc, algo, ATTN_BWD_ALGO, bool(concat))
+                         and lib.spotv2_gat_pair_format_supported(C.byref(d))) else 0
+    d.p_format = int(p_format)
+    return d
 
 
 def _workspace(desc: GatDesc):

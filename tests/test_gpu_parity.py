@@ -1314,7 +1314,7 @@ def test_projection_as_an_operand_pair(cuda_lib, geom):
 
 
 @pytest.mark.parametrize("case", [(6, 30, 1260, 126, 6, 500, False), (5, 30, 64, 126, 8, 256, True), (4, 13, 9, 5, 3, 8, True), (7, 30, 90, 9, 3, 16, True),
-                                  (3, 30, 40, 0, 4, 36, False)],
+                                  (3, 30, 40, 0, 4, 36, False), (3, 17, 40, 360, 2, 64, True), (300, 32, 24, 200, 8, 72, False), (2, 2, 8, 4, 2, 1024, False)],
                          ids=lambda c: "B%dN%dF%dFe%dH%dC%d%s" % (c[:6] + ("cat" if c[6] else "mean",)))
 def test_both_projection_formats_agree(cuda_lib, case, monkeypatch):
     """One layer step with P as fp32 (p_format 0) and as the operand pair (p_format 1): same operator, same logits (the
@@ -1337,5 +1337,7 @@ def test_both_projection_formats_agree(cuda_lib, case, monkeypatch):
         out = layer(x, ei, ea)
         out.backward(dout)
         res[pf] = dict(out=out.detach(), dx=x.grad, **{k: p.grad.clone() for k, p in layer.named_parameters() if p.grad is not None})
+    d = gat_conv._desc(sv.batched_topology(B, N, DEV)[1], Fin, Fe, H, C_, concat, 0.2)
+    assert d.p_format == 1, "the library should have chosen the pair format for this shape"
     for k in res[0]:
         assert relerr(res[1][k], res[0][k]) < 2e-6, k

@@ -90,5 +90,10 @@ def test_projection_format_choice_and_padded_sizes():
     assert d0.p_format == 0 and lib.spotv2_gat_head_pitch(C.byref(d0)) == 500 and lib.spotv2_gat_n_aug(C.byref(d0)) == 3012
     dc = gat_conv._desc(topo, 1260, 126, 8, 256, True, 0.2, gemm_algo=3)
     assert dc.p_format == 1 and lib.spotv2_gat_head_pitch(C.byref(dc)) == 256
+    # the library's own answer adds the kernels' shared-memory plans to the shape rules
+    fits = lambda N, Fe, H, Cc, cat: lib.spotv2_gat_pair_format_supported(C.byref(_lib.GatDesc(8, N, 64, Fe, H, Cc, N * (N - 1), cat, 0.2,
+                                                                                               lib.spotv2_gat_ldp(H, Cc), 0, 0)))
+    assert fits(30, 126, 6, 500, 0) == 1 and fits(30, 126, 8, 256, 1) == 1 and fits(32, 384, 8, 512, 0) == 1
+    assert fits(32, 512, 8, 256, 0) == 0 and fits(2, 3, 1, 2, 1) == 0 and fits(33, 126, 6, 500, 0) == 0
     bad = _lib.GatDesc(4, 40, 1260, 126, 6, 500, 1560, 0, 0.2, 3012, 0, 0, 0.0, 0, 0, 0, 1)
     assert lib.spotv2_gat_workspace_bytes(C.byref(bad), None, None, None) != 0 and b"p_format 1" in lib.spotv2_last_error()
