@@ -1,27 +1,32 @@
-// Fused GAT attention backward, pipelined version (the default; attn_bwd.cu is the any-shape fallback).
-// Same mathematics as attn_bwd.cu (attention recomputed from P_aug and the edge
-// rows), organised like the forward kernel: one persistent CTA per SM, 12 compute warps + 1 producer warp,
-// every operand arrives through asynchronous copies that run ahead of the arithmetic, across phases and
-// across graphs, and every product runs on the tensor cores (mma.sync m16n8k8 TF32 with the 3x split).
+// Fused GAT attention backward, pipelined version (the default; attn_bwd.cu is the any-shape fallback of p_format 0).
+// Same mathematics as attn_bwd.cu (attention recomputed, nothing of size E x H stored), organised
+// like the forward kernel: one persistent CTA per SM, 12 compute warps + 1 producer warp, every operand arrives through
+// asynchronous copies that run ahead of the arithmetic, across phases and across graphs, and every product runs on the
+// tensor cores (mma.sync; fp16 operand pairs on m16n8k16 for the two big products, 3xTF32 on m16n8k8 for logits and dv).
 //
-//   producer warp   ONE in-order stream of fixed-size slots (28 KB each, 5 of them at the default geometry),
-//                   filled in exactly the order the compute warps consume them, as far ahead as the ring allows
-//                   (enough bytes in flight to cover the HBM latency at this SM's bandwidth share):
-//                   * edge rows: 1-D bulk copies, 48-row chunks (twice per graph: logits, then dv)
-//                   * tile groups: up to 7 32x32 fp32 TMA tiles (128B-swizzled) of dout and P
+//   producer warp   ONE in-order stream of fixed-size slots (28 KB each, 5 of them at the default geometry), filled in
+//                   exactly the order the compute warps consume them, as far ahead as the ring allows:
+//                   * the forward's edge-term tile (one bulk copy) - or, without it, the edge rows a first time (logits)
+//                   * phase A slots: the dout tile and the P tiles of all heads for one 32-channel block
+//                   * edge rows: 1-D bulk copies, 48-row chunks (for dv)
+//                   * phase D slots: groups of up to 7 dout tiles
 //   compute warps   per graph
-//     L  g[e,h] = <edge row, v_h>        two half-groups of 6 warps take alternate chunks; a half-group =
-//                                        3 m16 row tiles x 2 k halves, red.shared into the tile (2 addends: exact order)
+//     L  edge terms: copied from the slot (or recomputed: g[e,h] = <edge row, v_h>, 3xTF32, two half-groups of 6 warps)
 //     S  self-loop mean fill, LeakyReLU, softmax -> alpha[h][j][i], z>0 masks       (thread per (h, i))
-//     A  dalpha_h = g dO_h P_h^T         warp = (head, 16-target tile); K = channels streamed as tile groups;
+//     A  dalpha_h = g dO_h P_h^T         warp = (head, 16-target tile); K = channels streamed slot by slot;
 //        softmax/LeakyReLU backward directly on the accumulator fragments (row sums by 4-lane shuffles),
 //        dd -> global, ds partials, dz' (mean-fill redistributed) -> shared D tile
-//     (V runs before D so that the second pass over the edge rows still finds them in L2: the first pass
-//      loads them with an evict-last hint, everything else streams evict-first)
-//     D  dP_h = g alpha_h^T dO_h         warp = (head, 16-source tile), alpha^T fragments in registers,
-//        results stored as scaled fp16 hi/lo pairs (tensor-core GEMM operand) or fp32; dbias column sums
-//     V  dv^T[f,h] += T^T dz'            warp = (16-feature tile, row group) over the second edge pass
-// Measured mma.sync facts this layout relies on (profiles/r1_mma_sync_latency_throughput.txt): 21-cycle
+//     V  dv^T[f,h] += T^T dz'            warp = (16-feature tile, row group) over the edge rows
+//     D  dP_h = g alpha_h^T dO_h         warp = (head, 16-source tile), alpha^T fragments in registers
+//
+// Two instantiation families (template parameter P16):
+//   p_format 0  P_aug and dout are fp32 (128B-swizzled fp32 tiles); every warp converts its fragments into fp16 pairs in
+//               registers; dP leaves as fp16 pairs (or fp32) through per-lane global stores; dbias column sums in phase D.
+//   p_format 1  P and dout arrive as fp16 operand pairs (P from the GEMM epilogue, dout from attn_prep.cu with a scale per
+//               graph | (graph, head)): head-aware 4-D tensor maps bring a whole phase-A slot part with one TMA load and
+//               zero-fill past a head's C, every fragment comes out of ldmatrix, dP leaves through TMA stores from per-warp
+//               staging tiles (sector-aligned boxes), the bias gradient comes from the prepass.  SINGLE: hi planes only.
+// Measured mma.sync facts this layout relies on (profiles/history/r1_mma_sync_latency_throughput.txt): 21-cycle
 // dependent latency, one MMA per 8 cycles per SM sub-partition, so 3 chains per warp keep a tensor unit busy.
 #include <string.h>
 

@@ -4,12 +4,17 @@
 //
 // Same roles as attn_fwd.cu - group A (3 warps) edge logits on 3xTF32 mma.sync, group B (8 warps) softmax + aggregation,
 // one TMA producer warp, pipelined across graphs - but no thread converts an MMA operand in the aggregation:
-//   * P tiles are 32 source rows x 32 channels of fp16, hi and lo planes side by side in a 4 KB slot (64B swizzle); the B
-//     fragments of mma.sync.m16n8k16 come out of ldmatrix.x4.trans (one instruction per k16 x n16 block);
-//   * the softmax output is converted ONCE per graph into an fp16 hi/lo tile [h][target i][source j] and the A fragments
-//     come out of ldmatrix.x4; the fp32 alpha tile is released to the logit group right after that conversion;
+//   * P tiles are 32 source rows x 32 channels of fp16 (64B swizzle); ONE TMA load brings four adjacent tiles of both
+//     planes (a 4-D tensor map whose tile dimension overlaps the column dimension); the B fragments of mma.sync.m16n8k16
+//     come out of ldmatrix.x4.trans (one instruction per k16 x n16 block);
+//   * the softmax (row held in registers between its passes) is converted ONCE per graph into an fp16 hi/lo tile
+//     [h][target i][source j]; the A fragments come out of ldmatrix.x4; the fp32 tile goes back to the logit group right
+//     after that conversion;
 //   * out[i, c] = (sum_h sum_j alpha_h[i,j] P[j, h, c]) with lo*hi + hi*lo + hi*hi per product (hi*hi only for the
-//     half-precision class), 48 instead of 96 MMAs per (head, channel block) and 16 ldmatrix instead of ~130 loads/splits.
+//     half-precision class), 48 instead of 96 MMAs per (head, channel block) and 16 ldmatrix instead of ~130 loads/splits;
+//   * the edge rows stream through a THREE-stage ring (two chunks in flight while one is consumed), the finished edge-term
+//     tile leaves for the backward through one bulk store, the logit terms s|d come in fp32 one graph ahead.
+// Every wait is bounded and reports which barrier starved before it traps.  Role cycle counters: -DSPOTV2_BRINGUP.
 #include "attn_bwd.cuh"
 #include "tma.cuh"
 
