@@ -241,7 +241,10 @@ class HotPath:
         # counted from the ncu launch list (profiles/r1t_launch_list_summary.txt): fold x2 (W_aug rows, v); amax x5 (x, W_aug x2,
         # dout, ds|dd); split x3 (x, W_aug, ds|dd); GEMM fwd; attn fwd; attn bwd + 2 partial reduces; GEMM bwd + split-K
         # reduce; unfold
-        self.kernels_per_step = 18 if self.tc else 11
+        # counted from the ncu launch list (profiles/r2b_launch_list_summary.txt): p_format 1: fold, W_aug statistics + split, GEMM, attention
+        # forward, dout prepass, attention backward, partial reduce, ds|dd split, GEMM, split-K reduce, unfold = 12; p_format 0 on the
+        # tensor-core GEMM: 17 (amax / split passes over W_aug, dout, ds|dd); CUDA-core GEMM: 10
+        self.kernels_per_step = (12 if self.pair else 17) if self.tc else 10
         if N > 32:   # large-universe path (profiles/r1t_config_D_launch_list_summary.txt): attn fwd 3 (logits, softmax, GEMM);
             # attn bwd 11 (+ amax/split of dP on the tensor-core path); fold x2, amax/split of x and W_aug, two projection
             # GEMMs + split-K reduce, unfold

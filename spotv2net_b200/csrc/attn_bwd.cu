@@ -884,8 +884,13 @@ extern "C" int spotv2_gat_attn_bwd_pair(const spotv2_gat_desc* d, const void* P_
     __half* dlo = single ? nullptr : reinterpret_cast<__half*>(x + plane);
     float* scales = reinterpret_cast<float*>(x + 2 * plane);
     float* bpart = reinterpret_cast<float*>(x + 2 * plane + round_up((size_t)d->B * upg * sizeof(float), 256));
-    if (int rc = dout_pair_prepass(dout, d->B, d->N, d->C, upg, dhi, dlo, ldo16, scales, blk_dout, dbias_or_null, bpart, st)) return rc;
+    // (the bias gradient's per-CTA partials are reduced together with the dv partials, behind the attention kernel)
+    int n_parts = 0;
+    if (int rc = dout_pair_prepass(dout, d->B, d->N, d->C, upg, dhi, dlo, ldo16, scales, blk_dout, nullptr, dbias_or_null ? bpart : nullptr, st,
+                                   &n_parts))
+      return rc;
     a.dO_hi = dhi; a.dO_lo = dlo; a.dO_scale = scales; a.ldo16 = ldo16; a.units_per_graph = upg;
+    a.prep_dbias_part = dbias_or_null ? bpart : nullptr; a.prep_dbias_n = n_parts;
   }
   a.dsd = reinterpret_cast<float*>(w + part);
   a.bound = (float)d->N * (d->concat ? 1.f : 1.f / (float)d->H) * a.p.drop.scale;

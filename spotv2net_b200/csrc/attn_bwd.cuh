@@ -61,10 +61,14 @@ struct AttnBwdArgs {
   const __half* dO_lo = nullptr;
   const float* dO_scale = nullptr;
   int ldo16 = 0, units_per_graph = 1;
+  const float* prep_dbias_part = nullptr;   // the prepass's per-CTA column sums [prep_dbias_n][ldo], reduced with the dv partials
+  int prep_dbias_n = 0;
 };
 int dout_pair_grid(int n_units, int upg);
+// dbias != null: reduce the partials here (one more launch); dbias == null with dbias_part != null: leave the partials
+// ([*n_parts][upg * C]) to the caller
 int dout_pair_prepass(const float* dout, int B, int N, int C, int upg, __half* hi, __half* lo, int ld16, float* scales, float* blk,
-                      float* dbias, float* dbias_part, cudaStream_t st);
+                      float* dbias, float* dbias_part, cudaStream_t st, int* n_parts = nullptr);
 
 __device__ __forceinline__ float dp_scale_from_amax(float amax) {   // same rule as gemm_f16.cu
   if (!(amax > 0.f) || !(amax < INFINITY)) return 1.f;

@@ -1289,8 +1289,10 @@ int launch_attn_bwd2(AttnBwdArgs& a, float* dv, float* dbias, void* ws, size_t w
   kern<<<grid, kB2Threads, pl.total, st>>>(a, pl, tmP, tmG, tmPl, tmD0, tmD1);
   SPOTV2_CUDA_OK(cudaGetLastError());
   // (p_format 1: the bias gradient was formed by dout_pair_prepass)
-  return reduce_partials2(a.dv_part, grid * rg, (dv && p.Fe > 0) ? p.H * p.Fe : 0, dv, a.dbias_part, grid, (dbias && !p16) ? p.ldo : 0,
-                          p16 ? nullptr : dbias, st);
+  if (p16)
+    return reduce_partials2(a.dv_part, grid * rg, (dv && p.Fe > 0) ? p.H * p.Fe : 0, dv, a.prep_dbias_part, a.prep_dbias_n,
+                            (dbias && a.prep_dbias_part) ? p.ldo : 0, dbias, st);
+  return reduce_partials2(a.dv_part, grid * rg, (dv && p.Fe > 0) ? p.H * p.Fe : 0, dv, a.dbias_part, grid, dbias ? p.ldo : 0, dbias, st);
 }
 
 int bwd2_diag_add(unsigned long long* host_out, int reset) {

@@ -107,12 +107,13 @@ int dout_pair_grid(int n_units, int upg) {
 // dout [B*N, ldo] -> hi | lo [B*N, ld16] (lo may be null), scales [B * upg], blk[0] = bits of max|dout| (blk zeroed here),
 // dbias [ldo] (null: skipped) through dbias_part [grid][ldo].  upg = 1 (head mean: ldo == C) or H (concat: ldo == H * C).
 int dout_pair_prepass(const float* dout, int B, int N, int C, int upg, __half* hi, __half* lo, int ld16, float* scales, float* blk,
-                      float* dbias, float* dbias_part, cudaStream_t st) {
+                      float* dbias, float* dbias_part, cudaStream_t st, int* n_parts) {
   if (C % 2 != 0 || C > 1024) return fail(SPOTV2_ERR_UNSUPPORTED, "attn_bwd (p_format 1): even C <= 1024 required, got %d", C);
   const int ldo = upg * C, n_units = B * upg;
   const int grid = dout_pair_grid(n_units, upg);
   SPOTV2_CUDA_OK(cudaMemsetAsync(blk, 0, kScaleBlockFloats * sizeof(float), st));
-  float* part = dbias ? dbias_part : nullptr;
+  float* part = dbias_part;
+  if (n_parts) *n_parts = grid;
   if (C <= 512)
     dout_pair_kernel<1><<<grid, 256, 0, st>>>(dout, n_units, N, C, upg, ldo, hi, lo, ld16, scales, reinterpret_cast<unsigned*>(blk), part);
   else

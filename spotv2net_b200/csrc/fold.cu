@@ -7,38 +7,6 @@
 
 namespace spotv2 {
 
-// out_k[h][f] = sum_c M[(h*C + c)*F + f] * a_k[h][c]  (k = 0, 1; a_1 may be null).
-// Block = 32 features x NY channel slices: coalesced 128-byte row reads, NY-way split of the C-long sum,
-// fixed-order shared-memory reduction (deterministic).
-template <int NY>
-__global__ void __launch_bounds__(32 * NY)
-fold_kernel(const float* __restrict__ M, const float* __restrict__ a0, const float* __restrict__ a1,
-            float* __restrict__ out0, float* __restrict__ out1, int C, int F) {
-  __shared__ float red[2][NY][33];
-  const int h = blockIdx.y;
-  const int f = blockIdx.x * 32 + threadIdx.x;
-  const int y = threadIdx.y;
-  float s0 = 0.f, s1 = 0.f;
-  if (f < F) {
-    const float* Mh = M + (size_t)h * C * F + f;
-    for (int c = y; c < C; c += NY) {
-      const float w = Mh[(size_t)c * F];
-      s0 = fmaf(w, a0[h * C + c], s0);
-      if (a1) s1 = fmaf(w, a1[h * C + c], s1);
-    }
-  }
-  red[0][y][threadIdx.x] = s0;
-  red[1][y][threadIdx.x] = s1;
-  __syncthreads();
-  if (y == 0 && f < F) {
-    float t0 = 0.f, t1 = 0.f;
-#pragma unroll
-    for (int k = 0; k < NY; ++k) { t0 += red[0][k][threadIdx.x]; t1 += red[1][k][threadIdx.x]; }
-    out0[(size_t)h * F + f] = t0;
-    if (a1) out1[(size_t)h * F + f] = t1;
-  }
-}
-
 __device__ __forceinline__ float block_sum_128(float x, float* red) {
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
   const int w = threadIdx.x >> 5;
@@ -87,16 +55,65 @@ unfold_kernel(const float* __restrict__ W, const float* __restrict__ a_src,
   }
 }
 
-// W_aug rows [0, H*Cp): head h's C rows of W, then Cp - C zero rows (p_format 1: padded head pitch)
+// The whole fold in one launch (256 threads = 32 features x 8 channel slices), three kinds of blocks:
+//   [0, H*Cp)                     copy: W_aug row r <- head h's row of W, or zeros for the Cp - C pad rows (p_format 1)
+//   then ceil(F/32) * H blocks    u_src | u_dst rows of W_aug: u_k[h][f] = sum_c W[(h*C + c)*F + f] * a_k[h][c]
+//   then ceil(Fe/32) * H blocks   v[h][f] = sum_c W_e[(h*C + c)*Fe + f] * a_edge[h][c]
+// Fixed-order shared-memory reductions (deterministic).
 __global__ void __launch_bounds__(256)
-fold_copy_padded_kernel(const float* __restrict__ W, float* __restrict__ W_aug, int C, int Cp, int F) {
-  const int r = blockIdx.x, h = r / Cp, c = r - h * Cp;
-  float* dst = W_aug + (size_t)r * F;
-  if (c < C) {
-    const float* src = W + ((size_t)h * C + c) * F;
-    for (int f = threadIdx.x; f < F; f += 256) dst[f] = src[f];
-  } else {
-    for (int f = threadIdx.x; f < F; f += 256) dst[f] = 0.f;
+fold_all_kernel(const float* __restrict__ W, const float* __restrict__ a_src, const float* __restrict__ a_dst,
+                const float* __restrict__ We, const float* __restrict__ a_edge, float* __restrict__ W_aug, float* __restrict__ v,
+                int H, int C, int Cp, int F, int Fe) {
+  __shared__ float red[2][32][33];
+  const int n_copy = H * Cp, fb = (F + 31) / 32;
+  int blk = blockIdx.x;
+  if (blk < n_copy) {
+    const int h = blk / Cp, c = blk - h * Cp;
+    float* dst = W_aug + (size_t)blk * F;
+    if (c < C) {
+      const float* src = W + ((size_t)h * C + c) * F;
+      for (int f = threadIdx.x; f < F; f += 256) dst[f] = src[f];
+    } else {
+      for (int f = threadIdx.x; f < F; f += 256) dst[f] = 0.f;
+    }
+    return;
+  }
+  blk -= n_copy;
+  const bool edge = blk >= fb * H;
+  if (edge) blk -= fb * H;
+  const int nb = edge ? (Fe + 31) / 32 : fb, Fd = edge ? Fe : F;
+  const int h = blk / nb, tx = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const int f = (blk - h * nb) * 32 + tx;
+  // channel slices: 8 for the u rows, 32 for v (four per thread) - the partial sums and their order are those of the
+  // two kernels this one replaced, so every folded value keeps its bits
+  const int NY = edge ? 32 : 8, NQ = edge ? 4 : 1;
+  const float* M = edge ? We : W;
+  const float* a0 = edge ? a_edge : a_src;
+  const float* a1 = edge ? nullptr : a_dst;
+  for (int q = 0; q < NQ; ++q) {
+    const int sl = y + 8 * q;
+    float s0 = 0.f, s1 = 0.f;
+    if (f < Fd) {
+      const float* Mh = M + (size_t)h * C * Fd + f;
+      for (int c = sl; c < C; c += NY) {
+        const float w = Mh[(size_t)c * Fd];
+        s0 = fmaf(w, a0[h * C + c], s0);
+        if (a1) s1 = fmaf(w, a1[h * C + c], s1);
+      }
+    }
+    red[0][sl][tx] = s0;
+    red[1][sl][tx] = s1;
+  }
+  __syncthreads();
+  if (y == 0 && f < Fd) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int k = 0; k < NY; ++k) { t0 += red[0][k][tx]; t1 += red[1][k][tx]; }
+    if (edge) {
+      v[(size_t)h * Fe + f] = t0;
+    } else {
+      W_aug[((size_t)H * Cp + h) * F + f] = t0;
+      W_aug[((size_t)H * Cp + H + h) * F + f] = t1;
+    }
   }
 }
 
@@ -284,18 +301,9 @@ extern "C" int spotv2_gat_fold(const spotv2_gat_desc* d, const float* W, const f
   SPOTV2_REQUIRE(d->Fe == 0 || (W_e && a_edge && v), "fold: W_e, a_edge, v required when Fe > 0");
   cudaStream_t st = as_stream(stream);
   const int Cp = head_pitch_of(d);
-  const int HC = d->H * Cp;
-  if (Cp == d->C)
-    SPOTV2_CUDA_OK(cudaMemcpyAsync(W_aug, W, (size_t)HC * d->F * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  else
-    fold_copy_padded_kernel<<<HC, 256, 0, st>>>(W, W_aug, d->C, Cp, d->F);
-  dim3 g1((d->F + 31) / 32, d->H);
-  fold_kernel<8><<<g1, dim3(32, 8), 0, st>>>(W, a_src, a_dst, W_aug + (size_t)HC * d->F,
-                                             W_aug + (size_t)(HC + d->H) * d->F, d->C, d->F);
-  if (d->Fe > 0) {
-    dim3 g2((d->Fe + 31) / 32, d->H);
-    fold_kernel<32><<<g2, dim3(32, 32), 0, st>>>(W_e, a_edge, nullptr, v, nullptr, d->C, d->Fe);
-  }
+  const int blocks = d->H * Cp + ((d->F + 31) / 32) * d->H + (d->Fe > 0 ? ((d->Fe + 31) / 32) * d->H : 0);
+  fold_all_kernel<<<blocks, 256, 0, st>>>(W, a_src, a_dst, d->Fe > 0 ? W_e : nullptr, d->Fe > 0 ? a_edge : nullptr, W_aug, v, d->H, d->C, Cp,
+                                          d->F, d->Fe);
   SPOTV2_CUDA_OK(cudaGetLastError());
   return SPOTV2_OK;
 }

@@ -93,6 +93,9 @@ int gemm3x_f16(bool a_kc, bool b_kc, int M, int N, int K, const F16Operand& A, c
 // Scale block of a pair output C = x . W^T from the bound |C| <= max|x| * max_row ||W||_1 (x_blk[0] = bits of max|x|);
 // two groups: rows of W below / at-or-above split_at.
 int pair_out_scale(const float* W, int rows, int cols, int split_at, const float* x_blk, float* blk, cudaStream_t st);
+// W's own operand pair and the pair-output scale block in two launches (statistics, split)
+int w_pair_and_out_scale(const float* W, int rows, int cols, int split_at, void* hi, void* lo, size_t ld16, float* wblk,
+                         const float* x_blk, float* out_blk, cudaStream_t st);
 // blk[0] <- bits of max |src[r, c]| over a [rows, cols] matrix with row pitch ld (blk is zeroed first)
 int amax_2d(const float* src, int rows, int cols, size_t ld, float* blk, cudaStream_t st);
 

@@ -479,10 +479,19 @@ constexpr int kSplitRows = 4;
 __global__ void __launch_bounds__(256)
 split_f16_rows_kernel(const float* __restrict__ src, int rows, int cols4, size_t ld, int split_dim, int split_at,
                       const float* __restrict__ pre2, int pre_split, __half* __restrict__ hi, __half* __restrict__ lo,
-                      size_t ld16, float* __restrict__ blk) {
+                      size_t ld16, float* __restrict__ blk, float* __restrict__ out_blk = nullptr,
+                      const float* __restrict__ x_blk = nullptr) {
   const unsigned* bits = reinterpret_cast<const unsigned*>(blk);
   const float s0 = scale_from_amax(__uint_as_float(bits[0])), s1 = scale_from_amax(__uint_as_float(bits[1]));
   if (blockIdx.x == 0 && threadIdx.x == 0) { blk[2] = 1.f / s0; blk[3] = 1.f / s1; blk[4] = s0; blk[5] = s1; }
+  // optional: finish the scale block of a pair OUTPUT whose [0,1] hold the row-L1 maxima of this matrix (w_stats_kernel)
+  if (out_blk && blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 34) {
+    const int gq = threadIdx.x - 32;
+    const float xmax = __uint_as_float(reinterpret_cast<const unsigned*>(x_blk)[0]);
+    const float bound = xmax * __uint_as_float(reinterpret_cast<const unsigned*>(out_blk)[gq]) * 1.0009765625f;
+    const float so = scale_from_amax(bound);
+    out_blk[gq] = bound; out_blk[2 + gq] = 1.f / so; out_blk[4 + gq] = so;
+  }
   for (int r0 = blockIdx.x * kSplitRows; r0 < rows; r0 += gridDim.x * kSplitRows) {
     for (int c4 = threadIdx.x; c4 < cols4; c4 += 256) {
       float4 v[kSplitRows];
@@ -582,6 +591,49 @@ __global__ void pair_out_scale_kernel(float* blk, const float* __restrict__ x_bl
   blk[threadIdx.x] = bound;
   blk[2 + threadIdx.x] = 1.f / s;
   blk[4 + threadIdx.x] = s;
+}
+
+// One pass over W [rows, cols]: per group (rows < / >= split_at) the largest magnitude (-> amax_bits[g], sizes W's own operand
+// scale) and the largest row L1 norm (-> l1_bits[g], bounds the pair output).  One warp per row.
+__global__ void __launch_bounds__(256)
+w_stats_kernel(const float* __restrict__ W, int rows, int cols, int split_at, unsigned* __restrict__ amax_bits, unsigned* __restrict__ l1_bits) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* w = W + (size_t)r * cols;
+  float s = 0.f, m = 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    const float a = fabsf(w[c]);
+    s += a;
+    m = fmaxf(m, a);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  }
+  if (lane == 0) {
+    const int gq = r >= split_at ? 1 : 0;
+    if (s > 0.f) atomicMax(l1_bits + gq, __float_as_uint(s));
+    if (m > 0.f) atomicMax(amax_bits + gq, __float_as_uint(m));
+  }
+}
+
+// W_aug [rows, cols] -> its fp16 operand pair (two row groups at split_at) AND the scale block of the pair output x . W^T, in
+// two launches (statistics, split); falls back to split_f16 + pair_out_scale when the vectorised split does not apply.
+int w_pair_and_out_scale(const float* W, int rows, int cols, int split_at, void* hi, void* lo, size_t ld16, float* wblk,
+                         const float* x_blk, float* out_blk, cudaStream_t st) {
+  const bool vec4 = (cols % 4 == 0) && (ld16 % 4 == 0) && aligned16(W) && ((reinterpret_cast<uintptr_t>(hi) & 7) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(lo) & 7) == 0) && cols / 4 >= 64;
+  if (!vec4) {
+    if (int rc = split_f16(W, rows, cols, (size_t)cols, 0, split_at, nullptr, 0, hi, lo, ld16, wblk, st)) return rc;
+    return pair_out_scale(W, rows, cols, split_at, x_blk, out_blk, st);
+  }
+  SPOTV2_CUDA_OK(cudaMemsetAsync(wblk, 0, kScaleBlockFloats * sizeof(float), st));
+  SPOTV2_CUDA_OK(cudaMemsetAsync(out_blk, 0, kScaleBlockFloats * sizeof(float), st));
+  w_stats_kernel<<<(rows + 7) / 8, 256, 0, st>>>(W, rows, cols, split_at, reinterpret_cast<unsigned*>(wblk), reinterpret_cast<unsigned*>(out_blk));
+  split_f16_rows_kernel<<<std::min((rows + kSplitRows - 1) / kSplitRows, 32 * 148), 256, 0, st>>>(
+      W, rows, cols / 4, (size_t)cols, 0, split_at, nullptr, 0, static_cast<__half*>(hi), static_cast<__half*>(lo), ld16, wblk, out_blk, x_blk);
+  SPOTV2_CUDA_OK(cudaGetLastError());
+  return SPOTV2_OK;
 }
 
 int pair_out_scale(const float* W, int rows, int cols, int split_at, const float* x_blk, float* blk, cudaStream_t st) {

@@ -140,8 +140,7 @@ extern "C" int spotv2_proj_fwd_pair(const spotv2_gat_desc* d, const void* x_hi, 
   void* wh = c.take((size_t)s.n_aug * s.ldf16 * 2);
   void* wl = c.take((size_t)s.n_aug * s.ldf16 * 2);
   if (!wblk || !wh || !wl) return fail(SPOTV2_ERR_WORKSPACE, "proj_fwd_pair: workspace too small (%zu B)", ws_bytes);
-  if (int rc = split_f16(W_aug, s.n_aug, s.F, s.F, 0, s.HC, nullptr, 0, wh, wl, s.ldf16, wblk, st)) return rc;
-  if (int rc = pair_out_scale(W_aug, s.n_aug, s.F, s.HC, x_scale, p_scale, st)) return rc;
+  if (int rc = w_pair_and_out_scale(W_aug, s.n_aug, s.F, s.HC, wh, wl, s.ldf16, wblk, x_scale, p_scale, st)) return rc;
   F16Operand A{x_hi, x_lo, s.ldf16, x_scale + 2, kNone}, B{wh, wl, s.ldf16, wblk + 2, s.HC};
   PairOut out{P_hi, single_product(d) ? nullptr : P_lo_or_null, s.ldp16, p_scale + 4, sd, 2 * d->H};
   return gemm3x_f16(true, true, s.rows, s.n_aug, s.F, A, B, nullptr, 0, 1, 256, 0, nullptr, 0, st, nullptr, 0, single_product(d),

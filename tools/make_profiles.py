@@ -13,9 +13,10 @@ unit = rows[0][13]
 scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0}.get(unit, 1e-6)
 short = lambda n: n.split("(")[0].replace("void ", "").replace("spotv2::", "").replace("<unnamed>::", "")[:70]
 # last step = launches after the last launch of the first kernel name of a step (fold_kernel)
-idx = [i for i, n in enumerate(names) if "fold_copy_padded_kernel" in n] or \
+idx = [i for i, n in enumerate(names) if "fold_all_kernel" in n] or \
+      [i for i, n in enumerate(names) if "fold_copy_padded_kernel" in n] or \
       [i for i, n in enumerate(names) if "fold_kernel<8>" in n or "fold_kernel<(int)8>" in n]
-first = idx[-1] if idx else 0                    # a step starts with the W_aug copy (p_format 1) | fold_kernel<8>, then fold_kernel<32> (v)
+first = idx[-1] if idx else 0                    # a step starts with the fold (one launch since r2c; W_aug copy | fold_kernel<8> before)
 step = list(zip(names[first:], times[first:]))
 agg = collections.OrderedDict()
 for n, t in step:
