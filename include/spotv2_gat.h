@@ -145,7 +145,8 @@ int spotv2_edge_table_build(const int64_t* edge_index, int64_t num_edges, int32_
 int spotv2_edge_table_dense(int32_t N, int32_t* table, void* stream);
 
 /* Folds the attention vectors into the linear maps:
- *   W_aug [H*C + 2H, F] = [ W ; u_src ; u_dst ],  u_src,h = W_h^T a_src,h
+ *   W_aug [n_aug, F] = [ W ; u_src ; u_dst ],  u_src,h = W_h^T a_src,h   (n_aug = spotv2_gat_n_aug(d): H*C + 2H, or with
+ *                        p_format 1 every head's C rows followed by Cp - C zero rows, Cp = spotv2_gat_head_pitch(d))
  *   v     [H, Fe]       = W_e,h^T a_edge,h            (skipped when Fe == 0)
  * Stands in for `(x_src * att_src).sum(-1)`, `(x_dst * att_dst).sum(-1)` and
  * `lin_edge(edge_attr)` + `(e * att_edge).sum(-1)` of [PyG] gat_conv.py. */
@@ -243,7 +244,8 @@ int spotv2_windows_dv_workspace_bytes(const spotv2_gat_desc* d, size_t* bytes);
 int spotv2_windows_dv(const spotv2_gat_desc* d, const float* M_vv, int32_t T, int32_t L, const int32_t* t0,
                       const float* d_edge_terms, float* dv, void* ws, size_t ws_bytes, void* stream);
 
-/* lin_src backward: dW_aug [H*C+2H, F] = dP_aug^T . x  and  dX [B*N, F] = dP_aug . W_aug.
+/* lin_src backward: dW_aug [n_aug, F] = dP_aug^T . x  and  dX [B*N, F] = dP_aug . W_aug  (p_format 1: dP as the pair in the
+ * padded layout, required; x as a pair for the weight gradient).
  * x and dP_aug are taken as fp16 pairs when given (hi, lo, scale block: all three), else as fp32 and
  * prepared inside the workspace. */
 int spotv2_proj_bwd_weight(const spotv2_gat_desc* d, const float* x, const void* x_hi, const void* x_lo,

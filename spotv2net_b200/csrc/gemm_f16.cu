@@ -16,6 +16,10 @@
 // The accumulation-chain limit of gemm_tc.cu applies unchanged (the tensor core's fp32 adder truncates):
 // TMEM holds 128-element K chunks, eight consumer warps fold them into fp32 registers round-to-nearest.
 //
+// Output: fp32 C (or split-K partials) through 3-D TMA stores - or, for the forward projection of p_format 1, the fp16
+// operand PAIR of C * s (hi | lo planes; s from an a-priori bound, see pair_out_scale), split in the epilogue registers and
+// stored through the same TMA path; the second column group (the logit terms s | d) additionally in fp32.
+//
 // Kernel shape: persistent, one CTA per SM, 384 threads (warp 0 TMA, warp 1 MMA issue, warp 2 TMEM
 // allocator, warps 4-11 accumulate + epilogue), tile 128 x 256 x TBK, TBK = 64 | 32 fp16 elements.
 #include <cuda_fp16.h>
