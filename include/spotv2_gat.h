@@ -216,7 +216,11 @@ int spotv2_gat_attn_bwd(const spotv2_gat_desc* d, const float* P_aug, const floa
  * x must be given as a pair (x_hi, x_lo, x_scale; spotv2_split_f16 or spotv2_collate_windows_pair): the bound needs
  * max|x|, which the scale block holds.  W_aug is spotv2_gat_fold's output for the same descriptor ([n_aug, F]).
  * attn_bwd_pair emits dP as the pair [B*N, ld16(n_aug)] in the padded layout (pad columns zero), consumed by
- * spotv2_proj_bwd_weight / spotv2_proj_bwd_input with the same descriptor. */
+ * spotv2_proj_bwd_weight / spotv2_proj_bwd_input with the same descriptor.
+ * edge_terms between attn_fwd_pair and attn_bwd_pair is an OPAQUE record of the forward for the backward of the same step
+ * (same descriptor, same buffer, spotv2_gat_edge_terms_bytes): without attention dropout the forward leaves its attention
+ * coefficients there (same tile layout; LeakyReLU side in the sign bit), so the backward redoes neither logits nor softmax;
+ * with dropout_p > 0 it leaves the edge terms.  edge_mode 1: the forward overwrites the edge terms it was given. */
 int spotv2_proj_fwd_pair(const spotv2_gat_desc* d, const void* x_hi, const void* x_lo, const float* x_scale,
                          const float* W_aug, void* P_hi, void* P_lo_or_null, float* p_scale, float* sd, void* ws,
                          size_t ws_bytes, void* stream);

@@ -579,26 +579,34 @@ partial_reduce_kernel(const float* __restrict__ part, int nparts, int len, float
   }
 }
 
-// two reductions behind one launch: blocks [0, blocks_a) serve the first, the rest the second
-__global__ void __launch_bounds__(256)
+// two reductions behind one launch: blocks [0, blocks_a) serve the first, the rest the second.  32 x 32 threads: a column of
+// partials is summed by 32 threads with two independent chains each (the loads of a chain were the kernel's whole latency:
+// 444 partials over 8 threads took 30 us), then across the 32 in a fixed order - deterministic.
+__global__ void __launch_bounds__(1024)
 partial_reduce2_kernel(const float* __restrict__ pa, int na, int la, float* __restrict__ oa, int blocks_a,
                        const float* __restrict__ pb, int nb, int lb, float* __restrict__ ob) {
-  __shared__ float red[8][33];
+  __shared__ float red[32][33];
   const bool first = (int)blockIdx.x < blocks_a;
   const float* part = first ? pa : pb;
   const int nparts = first ? na : nb, len = first ? la : lb;
   float* out = first ? oa : ob;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int k = ((int)blockIdx.x - (first ? 0 : blocks_a)) * 32 + tx;
-  float s = 0.f;
-  if (k < len)
-    for (int c = ty; c < nparts; c += 8) s += part[(size_t)c * len + k];
-  red[ty][tx] = s;
+  float s0 = 0.f, s1 = 0.f;
+  if (k < len) {
+    int c = ty;
+    for (; c + 32 < nparts; c += 64) {
+      s0 += part[(size_t)c * len + k];
+      s1 += part[(size_t)(c + 32) * len + k];
+    }
+    if (c < nparts) s0 += part[(size_t)c * len + k];
+  }
+  red[ty][tx] = s0 + s1;
   __syncthreads();
   if (ty == 0 && k < len) {
     float t = 0.f;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) t += red[g][tx];
+    for (int g = 0; g < 32; ++g) t += red[g][tx];
     out[k] = t;
   }
 }
@@ -609,7 +617,7 @@ int reduce_partials2(const float* part_a, int nparts_a, int len_a, float* out_a,
   if (!out_b) len_b = 0;
   const int ba = (len_a + 31) / 32, bb = (len_b + 31) / 32;
   if (ba + bb == 0) return SPOTV2_OK;
-  partial_reduce2_kernel<<<ba + bb, 256, 0, st>>>(part_a, nparts_a, len_a, out_a, ba, part_b, nparts_b, len_b, out_b);
+  partial_reduce2_kernel<<<ba + bb, 1024, 0, st>>>(part_a, nparts_a, len_a, out_a, ba, part_b, nparts_b, len_b, out_b);
   SPOTV2_CUDA_OK(cudaGetLastError());
   return SPOTV2_OK;
 }
@@ -850,6 +858,7 @@ extern "C" int spotv2_gat_attn_bwd_pair(const spotv2_gat_desc* d, const void* P_
   a.p.edge_terms = d->Fe > 0 ? const_cast<float*>(edge_terms_or_null) : nullptr;
   a.p.terms_in = structured ? 1 : 0;
   a.p.dterms_out = structured ? d_edge_terms_or_null : nullptr;
+  a.p.alpha_rec = attn_record_of(d);
   a.p.P_aug = nullptr; a.p.edge_rows = edge_rows; a.p.table = table; a.p.v = v;
   a.p.P_hi = static_cast<const __half*>(P_hi);
   a.p.P_lo = single ? nullptr : static_cast<const __half*>(P_lo_or_null);

@@ -294,6 +294,8 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
   const uint32_t tile_bytes = (uint32_t)tile_floats * 4u;
   const int term_pieces = (int)((tile_bytes + pl.slot_bytes - 1) / pl.slot_bytes);
   const bool use_terms = p.edge_terms != nullptr && (nchunks > 0 || p.terms_in);
+  // the kept tile is the forward's record of signed attention coefficients (AttnParams::alpha_rec): phases L and S fall away
+  const bool rec = P16 && !DROP && use_terms && p.alpha_rec != 0;
   const int my_graphs = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int n_cb = pl.n_cb;
   auto rows_in = [&](int c) { const int r = p.R - c * pl.chunk_rows; return r < pl.chunk_rows ? r : pl.chunk_rows; };
@@ -562,6 +564,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
   for (int it = 0; it < my_graphs; ++it) {
     const int b = blockIdx.x + it * gridDim.x;
     // ------------------------------------------------ L: edge logits ------------------------------------------------
+    if (!rec)
     for (int idx = tid; idx < N * 2 * H; idx += kCT) {
       const int j = idx / (2 * H), k = idx - j * 2 * H;
       if (P16) {
@@ -650,8 +653,11 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
     bar_sync_compute();
     lap(0);
     // ------------------------------------------------ S: softmax ------------------------------------------------
-    softmax_phase(p, asm_, tile, sd, 1.f, nullptr, pos_mask, tid, kCT, -1, 0, (nchunks > 0 && pl.ksplit == 2 && !use_terms) ? D : nullptr);
-    bar_sync_compute();
+    // (the forward's record already IS the result of this phase: signed attention coefficients)
+    if (!rec) {
+      softmax_phase(p, asm_, tile, sd, 1.f, nullptr, pos_mask, tid, kCT, -1, 0, (nchunks > 0 && pl.ksplit == 2 && !use_terms) ? D : nullptr);
+      bar_sync_compute();
+    }
     lap(1);
     // ------------------------------------------------ A: dalpha + softmax backward ------------------------------------------------
     for (int r = 0; r < pl.n_rounds; ++r) {
@@ -776,16 +782,19 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
           for (int q = 0; q < 4; ++q) {
             const int i = (q & 2) ? i1 : i0, j = 8 * n + 2 * t + (q & 1);
             const bool valid = i < N && j < N;
-            const float a = valid ? tile[(h * N + j) * NS + i] : 0.f;
+            // al_ keeps the coefficient with the LeakyReLU side in its sign (the record's convention: negative = z <= 0)
+            const float ar = valid ? tile[(h * N + j) * NS + i] : 0.f;
+            const float a = fabsf(ar);
             float da = valid ? dacc[n][q] * k_dalpha : 0.f;
             if (DROP) da = ((((q & 2) ? keep1 : keep0) >> j) & 1u) ? da * p.drop.scale : 0.f;
-            al_[n][q] = a;
+            al_[n][q] = ar;
             dacc[n][q] = da;
             if (q & 2) dot1 = fmaf(a, da, dot1); else dot0 = fmaf(a, da, dot0);
           }
         dot0 += __shfl_xor_sync(0xffffffffu, dot0, 1); dot0 += __shfl_xor_sync(0xffffffffu, dot0, 2);
         dot1 += __shfl_xor_sync(0xffffffffu, dot1, 1); dot1 += __shfl_xor_sync(0xffffffffu, dot1, 2);
-        const uint32_t mask0 = i0 < N ? pos_mask[h * N + i0] : 0u, mask1 = i1 < N ? pos_mask[h * N + i1] : 0u;
+        uint32_t mask0 = 0u, mask1 = 0u;
+        if (!rec) { mask0 = i0 < N ? pos_mask[h * N + i0] : 0u; mask1 = i1 < N ? pos_mask[h * N + i1] : 0u; }
         float dd0 = 0.f, dd1 = 0.f, dii0 = 0.f, dii1 = 0.f;
         float dsc[4][2];
 #pragma unroll
@@ -794,9 +803,10 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int i = (q & 2) ? i1 : i0, j = 8 * n + 2 * t + (q & 1);
-            const float dl = al_[n][q] * (dacc[n][q] - ((q & 2) ? dot1 : dot0));
+            const float dl = fabsf(al_[n][q]) * (dacc[n][q] - ((q & 2) ? dot1 : dot0));
             const uint32_t mk = (q & 2) ? mask1 : mask0;
-            const float dz = ((mk >> j) & 1u) ? dl : dl * p.slope;
+            const bool pos = rec ? !(__float_as_uint(al_[n][q]) >> 31) : (((mk >> j) & 1u) != 0u);
+            const float dz = pos ? dl : dl * p.slope;
             dacc[n][q] = dz;
             if (q & 2) { dd1 += dz; if (j == i) dii1 = dz; } else { dd0 += dz; if (j == i) dii0 = dz; }
             dsc[n][q & 1] += dz;
@@ -953,8 +963,8 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
               x1.x = ((ka >> j1) & 1u) ? x1.x : 0.f;
               x1.y = ((kb >> j1) & 1u) ? x1.y : 0.f;
             }
-            cvt_pair(x0.x, x0.y, s_al, ah[ks][2 * hf], al[ks][2 * hf]);
-            cvt_pair(x1.x, x1.y, s_al, ah[ks][2 * hf + 1], al[ks][2 * hf + 1]);
+            cvt_pair(fabsf(x0.x), fabsf(x0.y), s_al, ah[ks][2 * hf], al[ks][2 * hf]);         // (record: sign = LeakyReLU side)
+            cvt_pair(fabsf(x1.x), fabsf(x1.y), s_al, ah[ks][2 * hf + 1], al[ks][2 * hf + 1]);
           }
       }
       uint32_t carry_h[2] = {0u, 0u}, carry_l[2] = {0u, 0u};     // last 8-column chunk of the previous dP tile (shifted stores)
@@ -1169,8 +1179,10 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
     }
     if (P16 && pl.stage_ok && lane == 0) tma_store_wait_read();   // the engine has read this warp's last dP staging tile
     bar_sync_compute();                                   // every warp is done with alpha and with the dz' tile
-    for (int idx = tid; idx < tile_floats; idx += kCT) tile[idx] = 0.f;      // next graph's logits accumulate into zeros
-    bar_sync_compute();
+    if (!use_terms) {                                     // (a kept tile is copied over the whole of it)
+      for (int idx = tid; idx < tile_floats; idx += kCT) tile[idx] = 0.f;      // next graph's logits accumulate into zeros
+      bar_sync_compute();
+    }
     lap(4);
   }
   if (P16 && pl.stage_ok && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this lane's dP stores have landed

@@ -34,6 +34,13 @@ inline DropoutParams dropout_params(const spotv2_gat_desc* d) {
   return r;
 }
 
+// What edge_terms carries between spotv2_gat_attn_fwd_pair and spotv2_gat_attn_bwd_pair (AttnParams::alpha_rec): 1 = the
+// signed attention coefficients.  A function of the descriptor only; attention dropout keeps the edge terms (the backward
+// needs the un-dropped coefficients of dropped edges, which the forward's tile no longer has).
+inline int attn_record_of(const spotv2_gat_desc* d) {
+  return (d->p_format == 1 && d->Fe > 0 && d->N <= 32 && !(d->dropout_p > 0.f)) ? 1 : 0;
+}
+
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
   uint32_t c2 = 0u, c3 = 0u;
 #pragma unroll
@@ -91,6 +98,11 @@ struct AttnParams {
   float* edge_terms;
   int terms_in;          // edge_mode 1: edge_terms is an INPUT (spotv2_edge_terms_from_windows); there are no edge rows
   float* dterms_out;     // backward, edge_mode 1: receives dz' (gradient w.r.t. the edge terms) in the same tile layout
+  // p_format 1 without attention dropout: what the forward leaves in edge_terms for the backward is not the edge terms but
+  // its RESULT - the attention coefficients, in the same tile layout, with the LeakyReLU side in the sign bit (+alpha: z > 0,
+  // -alpha: z <= 0; -0.0 counts).  The backward then has no logits, no s | d and no softmax to redo.  Both pair entry points
+  // derive the flag from the descriptor alone (attn_record_of), so the two calls of one step always agree.
+  int alpha_rec = 0;
   // p_format 1: the projection arrives as an fp16 operand pair (planes [B*N, ldp16], head pitch hp, scale block p_blk:
   // [2],[3] inverse scales of the projection / s|d column groups, [4],[5] the scales); P_aug is null then.  P_lo null =
   // half-precision class (hi plane only).
@@ -351,9 +363,10 @@ __device__ __forceinline__ void softmax_phase(const AttnParams& p, const AttnSme
 // stores per row instead of four and three.  Arithmetic and its order are those of softmax_phase - the results are
 // bit-identical (the LeakyReLU kinks and the attention coefficients of the forward and of the recomputing backward must
 // not depend on which of the two a kernel calls).  sd is the packed [N][2H] array.
+// signed_rec: the tile receives the record of AttnParams::alpha_rec (callers pass out_scale 1 with it).
 __device__ __forceinline__ void softmax_phase_regs(const AttnParams& p, int NS, float* tile, const float* sd, float out_scale,
                                                    float* alpha_out_b, uint32_t* pos_mask, int tid, int nthreads,
-                                                   const float* tile_add = nullptr, int drop_graph = -1) {
+                                                   const float* tile_add = nullptr, int drop_graph = -1, bool signed_rec = false) {
   const int N = p.N, H = p.H;
   for (int idx = tid; idx < H * N; idx += nthreads) {
     const int h = idx / N, i = idx - h * N;
@@ -404,7 +417,7 @@ __device__ __forceinline__ void softmax_phase_regs(const AttnParams& p, int NS, 
       if (j < N) {
         const float a = ((keep >> j) & 1u) ? r[j] * inv * kscale : 0.f;
         if (alpha_out_b) alpha_out_b[((size_t)h * N + j) * N + i] = a;
-        col[j * NS] = a * out_scale;
+        col[j * NS] = (signed_rec && !((mask >> j) & 1u)) ? -(a * out_scale) : a * out_scale;
       }
     if (pos_mask) pos_mask[idx] = mask;
   }

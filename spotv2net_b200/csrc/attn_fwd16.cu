@@ -267,7 +267,7 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
         t_bar += tick() - tl1;
         if (p.bulk_ok && tid == 0 && k + kEdgeStages < total_chunks) issue(k + kEdgeStages);
       }
-      if (p.edge_terms && !p.terms_in && NS == kEdgeTermNS) {
+      if (p.edge_terms && !p.terms_in && NS == kEdgeTermNS && !p.alpha_rec) {
         // keep the edge terms for the backward (6 floats per edge instead of the Fe-wide rows): ONE bulk store of the tile
         // by the copy engine (a thread-by-thread copy sat in the LSU queue for ~12 K cycles per graph).  The generic-proxy
         // scatters are fenced and behind a barrier; thread 0 holds its arrival on tile_full until the engine has read
@@ -309,8 +309,12 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
     for (int rb = 0; rb < 2; ++rb)
 #pragma unroll
       for (int cp = 0; cp < 2; ++cp) lm_off[rb][cp] = sw64(16 * rb + lm_row, 2 * cp + lm_chunk);
-    const float out_scale = p.concat ? 1.f : 1.f / (float)H;
-    const float k_out = p.p_blk[2] / pl.s_alpha;          // accumulator -> out
+    // alpha_rec: the tile receives the exact signed coefficients (the backward's record); the head-mean factor then rides in
+    // the accumulator scale instead of in alpha
+    const bool rec = p.alpha_rec != 0 && p.edge_terms != nullptr && NS == kEdgeTermNS;
+    const float head_scale = p.concat ? 1.f : 1.f / (float)H;
+    const float out_scale = rec ? 1.f : head_scale;
+    const float k_out = p.p_blk[2] / pl.s_alpha * (rec ? head_scale : 1.f);          // accumulator -> out
     uint32_t q_base = 0;
     long long w_tf = 0, w_pf = 0, w_sd = 0, t_smx = 0, t_cnv = 0;
     const long long t_role = tick();
@@ -347,8 +351,16 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
       const long long ts0 = tick();
       bar_b();                                           // sd complete (and everyone is past the previous graph's MMAs)
       softmax_phase_regs(p, NS, tile, sd, out_scale, args.alpha_out ? args.alpha_out + (size_t)b * H * N * N : nullptr, nullptr, tb_,
-                         kGB, nullptr, b);
+                         kGB, nullptr, b, rec);
+      if (rec) fence_proxy_async();                      // the copy engine reads what this thread wrote
       bar_b();                                           // alpha tile complete
+      if (rec && tb_ == 0) {
+        // the backward's record: ONE bulk store of the finished tile (edge_mode 1: over the edge terms this graph came from)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.edge_terms + (size_t)b * tile_floats),
+                     "r"(smem_u32(tile)), "r"((uint32_t)tile_floats * 4u)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
       const long long tc2 = tick();
       t_smx += tc2 - ts0;
       // alpha[h][j][i] fp32 -> fp16 hi | lo tiles [h][i][j] (64-byte rows, swizzled): the A operand of the aggregation
@@ -357,8 +369,8 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
         for (int idx = tb_; idx < H * njp * N; idx += kGB) {
           const int i = idx % N, r = idx / N, jp = r % njp, h = r / njp;
           const float* base = tile + (size_t)h * N * NS + i;
-          const float y0 = base[(2 * jp) * NS] * pl.s_alpha;
-          const float y1 = (2 * jp + 1 < N) ? base[(2 * jp + 1) * NS] * pl.s_alpha : 0.f;
+          const float y0 = fabsf(base[(2 * jp) * NS]) * pl.s_alpha;               // (the record carries the LeakyReLU side in the sign)
+          const float y1 = (2 * jp + 1 < N) ? fabsf(base[(2 * jp + 1) * NS]) * pl.s_alpha : 0.f;
           const __half2 hh = __floats2half2_rn(y0, y1);
           const uint32_t off = (uint32_t)h * 2048u + sw64(i, jp >> 2) + (uint32_t)(jp & 3) * 4u;
           *reinterpret_cast<__half2*>(smem_raw + pl.off_ahi + off) = hh;
@@ -369,6 +381,7 @@ gat_attn_fwd16_kernel(const AttnFwdArgs args, const Fwd16Plan pl_, const __grid_
         }
       }
       if (p.terms_in) fence_proxy_async();               // generic-proxy writes to the tile precede the next bulk copy into it
+      if (rec && tb_ == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the engine has read the record
       arrive(&tile_empty[buf]);                          // the fp32 tile is free for the logit group
       bar_b();                                           // alpha pair tiles complete
       t_cnv += (tc1 - tc0) + (tick() - tc2);
@@ -648,6 +661,7 @@ extern "C" int spotv2_gat_attn_fwd_pair(const spotv2_gat_desc* d, const void* P_
   a.p.edge_terms = d->Fe > 0 ? edge_terms_or_null : nullptr;
   a.p.terms_in = structured ? 1 : 0;
   a.p.dterms_out = nullptr;
+  a.p.alpha_rec = attn_record_of(d);
   a.bias = bias_or_null; a.out = out; a.alpha_out = alpha_or_null;
   return attn_fwd16_dispatch(a, as_stream(stream));
 }

@@ -1341,3 +1341,64 @@ def test_both_projection_formats_agree(cuda_lib, case, monkeypatch):
     assert d.p_format == 1, "the library should have chosen the pair format for this shape"
     for k in res[0]:
         assert relerr(res[1][k], res[0][k]) < 2e-6, k
+
+
+@pytest.mark.parametrize("geom", [(5, 30, 64, 126, 6, 500, False), (3, 13, 16, 5, 3, 8, True), (2, 32, 24, 40, 8, 72, False)],
+                         ids=lambda g_: "B%dN%dF%dFe%dH%dC%d%s" % (g_[:6] + ("cat" if g_[6] else "mean",)))
+def test_forward_record_for_the_backward(cuda_lib, geom):
+    """p_format 1 without attention dropout: what spotv2_gat_attn_fwd_pair leaves in edge_terms is its attention
+    coefficients ([B, H, j, 36] tile rows, target i inside a row) with the LeakyReLU side of the logit in the sign bit -
+    the backward redoes neither logits nor softmax.  |record| must be the returned alpha bit for bit, the signs those of
+    the fp64 oracle's logits (away from the kink), pad columns zero; with dropout the record is the edge terms."""
+    B, N, Fin, Fe, H, C_, concat = geom
+    bt = synth.random_complete_batch(B, N, Fin, Fe, seed=11)
+    ref, _ = make_layers(Fin, C_, H, concat, Fe, 0.2, seed=5, wscale=1.5)
+    W, a_s, a_d, We, a_e, bias = [p.detach() for p in (ref.lin_src.weight, ref.att_src, ref.att_dst,
+                                                       ref.lin_edge.weight, ref.att_edge, ref.bias)]
+    T = dense_gat.pyg_to_dense_tile(bt.edge_attr.double(), bt.edge_index, B, N)
+    fw = dense_gat.dense_forward(bt.x.double(), T, W, a_s, a_d, We, a_e, bias, H, C_, concat, 0.2)
+    n = B * N
+    topo = sv.topology_from_edge_index(bt.edge_index.to(DEV), n)
+    for pdrop in (0.0, 0.25):
+        d = GatDesc(B, N, Fin, Fe, H, C_, N * (N - 1), int(concat), 0.2, cuda_lib.spotv2_gat_ldp(H, C_), 0, 0, pdrop, 0, 7, 0, 1)
+        assert cuda_lib.spotv2_gat_pair_format_supported(C.byref(d)) == 1
+        Cp, n_aug = cuda_lib.spotv2_gat_head_pitch(C.byref(d)), cuda_lib.spotv2_gat_n_aug(C.byref(d))
+        W_aug, v = torch.empty(n_aug, Fin, device=DEV), torch.empty(H, Fe, device=DEV)
+        Wg, asg, adg, Weg, aeg, bg = [t_.float().to(DEV).contiguous() for t_ in (W, a_s, a_d, We, a_e, bias)]
+        check(cuda_lib.spotv2_gat_fold(C.byref(d), ptr(Wg), ptr(asg), ptr(adg), ptr(Weg), ptr(aeg), ptr(W_aug), ptr(v), st()), "fold")
+        x, ea = bt.x.to(DEV), bt.edge_attr.to(DEV)
+        ldx = cuda_lib.spotv2_gat_ld16(Fin)
+        x16, xblk = torch.empty(2, n, ldx, device=DEV, dtype=torch.float16), torch.empty(8, device=DEV)
+        check(cuda_lib.spotv2_split_f16(ptr(x), n, Fin, Fin, 0, 0, ptr(x16[0]), ptr(x16[1]), ldx, ptr(xblk), st()), "split_f16")
+        ldp16 = cuda_lib.spotv2_gat_ld16(n_aug)
+        P16 = torch.zeros(2, n, ldp16, device=DEV, dtype=torch.float16)
+        pblk, sd = torch.empty(8, device=DEV), torch.empty(n, 2 * H, device=DEV)
+        a_ = C.c_size_t()
+        check(cuda_lib.spotv2_gat_workspace_bytes(C.byref(d), C.byref(a_), None, None), "ws")
+        ws = torch.empty(a_.value, device=DEV, dtype=torch.uint8)
+        check(cuda_lib.spotv2_proj_fwd_pair(C.byref(d), ptr(x16[0]), ptr(x16[1]), ptr(xblk), ptr(W_aug), ptr(P16[0]), ptr(P16[1]),
+                                            ptr(pblk), ptr(sd), ptr(ws), ws.numel(), st()), "proj_fwd_pair")
+        etb = C.c_size_t()
+        check(cuda_lib.spotv2_gat_edge_terms_bytes(C.byref(d), C.byref(etb)), "edge_terms_bytes")
+        rec = torch.full((etb.value // 4,), float("nan"), device=DEV)
+        out = torch.empty(n, H * C_ if concat else C_, device=DEV)
+        alpha = torch.empty(B, H, N, N, device=DEV)
+        check(cuda_lib.spotv2_gat_attn_fwd_pair(C.byref(d), ptr(P16[0]), ptr(P16[1]), ptr(pblk), ptr(sd), ptr(ea),
+                                                ptr(topo.table), ptr(v), ptr(bg), ptr(out), ptr(alpha), ptr(rec), st()),
+              "attn_fwd_pair")
+        torch.cuda.synchronize()
+        rec = rec.view(B, H, N, 36)
+        assert torch.isfinite(rec).all()                                               # every byte of the record is written
+        g64 = fw["g"].permute(0, 3, 2, 1)                                              # edge terms [B, H, j, i]
+        off = ~torch.eye(N, dtype=torch.bool)
+        if pdrop > 0:
+            assert relerr(rec[..., :N].cpu()[..., off], g64[..., off]) < TOL           # dropout: the edge terms, as before
+            continue
+        assert relerr(out, fw["out"]) < TOL
+        assert torch.equal(rec[..., :N].abs(), alpha)                                  # the coefficients, bit for bit
+        assert (rec[..., N:] == 0).all()
+        z = fw["z"].permute(0, 3, 2, 1)                                                # logits [B, H, j, i]
+        clear = z.abs() > 1e-4 * z.abs().max()
+        neg = torch.signbit(rec[..., :N]).cpu()
+        assert torch.equal(neg[clear], (z <= 0)[clear])
+        assert 0.05 < neg.float().mean() < 0.95                                        # both sides occur
