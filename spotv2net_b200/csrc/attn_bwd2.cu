@@ -511,8 +511,10 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
   int dv_mt[kMaxDvUnits], dv_rb[kMaxDvUnits];
   float dv_run[kMaxDvUnits][4];
 #pragma unroll
+  // (a warp's two units are neighbours: same row group whenever the feature-tile count is even, so that the dz' fragments
+  // of a k-step are fetched and split once for both)
   for (int uu = 0; uu < kMaxDvUnits; ++uu) {
-    const int u = warp + uu * kW;
+    const int u = warp * kMaxDvUnits + uu;
     const bool ok = u < pl.dv_units;
     dv_mt[uu] = ok ? u % pl.n_mtiles : -1;
     dv_rb[uu] = ok ? (u / pl.n_mtiles) * pl.dv_rpu : 0;
@@ -873,6 +875,73 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
       const int rows = rows_in(c);
       const uint32_t trow = a_toff + (uint32_t)(c * pl.chunk_rows) * 4u;
       const uint32_t dgh = a_D + (uint32_t)g * head_bytes;                   // head g of the dz' tile (B fragment: n = g)
+      static_assert(kMaxDvUnits == 2, "phase V pairs the two units of a warp");
+      if (pl.dv_rpu == 16 && dv_mt[1] >= 0 && dv_rb[0] == dv_rb[1]) {
+        // Both units cover the same 16 rows (feature tiles mt, mt + 1).  A = T^T: (m = feature f0 + g | + 8, k = row).
+        // k index -> chunk row: k-step s takes rows 4t + 2s (k = t) and 4t + 2s + 1 (k = t + 4): rows 4 apart start 8 banks
+        // apart with the 126-float pitch, so a fragment load (4 rows x 8 features) is conflict-free.  The B fragments (dz' of
+        // the rows' edges, n = head g) are fetched through the row table and split once per k-step for both tiles; all
+        // operand loads of the four (tile, k-step) products are issued before the first split.
+        const int rbeg = dv_rb[0];
+        if (rbeg < rows) {                                                    // warp-uniform
+          const int rend = min(rows, rbeg + 16);
+          const uint32_t rowb = (uint32_t)(Fe * 4);
+          const int r4 = rbeg + 4 * t;
+          int to[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) to[k] = (r4 + k < rend && g < H) ? lds_i32(trow + (uint32_t)(r4 + k) * 4u) : -1;
+          float a[2][2][4];                                                   // [tile][k-step][fragment register]
+#pragma unroll
+          for (int uu = 0; uu < 2; ++uu) {
+            const uint32_t ta0 = sa + (uint32_t)r4 * rowb + (uint32_t)((dv_mt[uu] * 16 + g) * 4);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint32_t ta = ta0 + (uint32_t)(2 * ks) * rowb, tb = ta + rowb;
+              a[uu][ks][0] = lds_u32(ta);
+              a[uu][ks][1] = lds_u32(ta + 32);
+              a[uu][ks][2] = lds_u32(tb);
+              a[uu][ks][3] = lds_u32(tb + 32);
+            }
+          }
+          float bv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) bv[k] = to[k] >= 0 ? lds_u32(dgh + (uint32_t)to[k]) : 0.f;
+          if (rend < rbeg + 16) {                // rows past the chunk's end hold stale slot bytes
+#pragma unroll
+            for (int uu = 0; uu < 2; ++uu)
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                if (r4 + 2 * ks >= rend) a[uu][ks][0] = a[uu][ks][1] = 0.f;
+                if (r4 + 2 * ks + 1 >= rend) a[uu][ks][2] = a[uu][ks][3] = 0.f;
+              }
+          }
+          uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            split_lean(bv[2 * ks], bh[ks][0], bl[ks][0]);
+            split_lean(bv[2 * ks + 1], bh[ks][1], bl[ks][1]);
+          }
+#pragma unroll
+          for (int uu = 0; uu < 2; ++uu) {
+            float acc[3][4];
+#pragma unroll
+            for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc[pr][q] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              uint32_t ah[4], al[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) split_lean(a[uu][ks][q], ah[q], al[q]);
+              mma_tf32_16x8x8(acc[0], al, bh[ks]);
+              mma_tf32_16x8x8(acc[1], ah, bl[ks]);
+              mma_tf32_16x8x8(acc[2], ah, bh[ks]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dv_run[uu][q] += (acc[0][q] + acc[1][q]) + acc[2][q];
+          }
+        }
+      } else {
 #pragma unroll
       for (int uu = 0; uu < kMaxDvUnits; ++uu) {
         if (dv_mt[uu] < 0 || dv_rb[uu] >= rows) continue;                    // warp-uniform
@@ -926,6 +995,7 @@ gat_attn_bwd2_kernel(const AttnBwdArgs args, const Bwd2Plan pl_, const __grid_co
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) dv_run[uu][q] += (acc[0][q] + acc[1][q]) + acc[2][q];
+      }
       }
       release_slot();
     }
