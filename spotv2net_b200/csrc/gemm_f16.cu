@@ -75,10 +75,17 @@ struct HSmem {
   static constexpr int kAOp = HBM_ * TBK * 2;              // one A operand tile (hi or lo), bytes
   static constexpr int kBOp = BN * TBK * 2;
   static constexpr int kStage = 2 * kAOp + 2 * kBOp;
-  static constexpr int kStages = (200 * 1024) / kStage > 6 ? 6 : (200 * 1024) / kStage;
+  // K-major x K-major with 32-element k-blocks (the forward projection): three 48 KB stages and FOUR 2 KB store boxes per
+  // epilogue warp.  With two boxes the pair epilogue waited on the copy engine before six of its eight pieces (the stores
+  // queue behind the operand loads); the MMA warp, which can run only two accumulation chunks ahead, stalled for it: 0.17 ms
+  // of the K = 1260 product (bring-up probe, tools/gemm_dbg_probe.sh).
+  static constexpr bool kWideEpi = (TBK == 32) && A_KM && B_KM;
+  static constexpr int kStages = kWideEpi ? 3 : ((200 * 1024) / kStage > 6 ? 6 : (200 * 1024) / kStage);
   static constexpr int kBarOff = kStages * kStage;
   static constexpr int kEpiOff = kBarOff + 1024;                     // 8 epilogue warps x 4224 B: a 32 x 32 fp32 output block each
-  static constexpr int kEpiWarpBytes = 32 * 33 * 4;                  // ([32][33] transpose, or a 4 KB 128B-swizzled TMA store box)
+  static constexpr int kEpiWarpBytes = kWideEpi ? 8192 : 32 * 33 * 4;    // ([32][33] transpose, or 2 KB swizzled TMA store boxes)
+  static constexpr int kBoxStride = kWideEpi ? 8192 : 4096;         // store boxes of one warp
+  static constexpr int kPairBoxes = kWideEpi ? 4 : 2;
   static constexpr int kEpiBytes = kHEpiWarps * kEpiWarpBytes;
   static constexpr int kTotal = kEpiOff + kEpiBytes + 1024;
   static constexpr uint32_t kTxBytes = kStage;
@@ -276,11 +283,13 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         for (int e = 0; e < HALF; ++e)
           if (col0 + e >= p.b_split && col0 + e < p.N) dst[col0 + e] = acc[e] * un;
       }
-      if (p.pair_out) {
+      if (p.pair_out && (SPOTV2_DBG(p) & 8)) {
+        // (bring-up probe: no pair epilogue at all)
+      } else if (p.pair_out) {
         // The tile leaves as the fp16 operand pair of the scaled result: 32 x 32 pieces, hi plane then lo plane, each a
-        // 2 KB box (64-byte rows, 64B swizzle) handed to the TMA engine; the two boxes of this warp alternate, and a box is
-        // refilled once the engine has read the store issued from it two stores ago.
-        unsigned char* box = smem + S::kEpiOff + (warp - 4) * 4096;
+        // 2 KB box (64-byte rows, 64B swizzle) handed to the TMA engine; the boxes of this warp rotate, and a box is
+        // refilled once the engine has read the store issued from it kPairBoxes stores ago.
+        unsigned char* box = smem + S::kEpiOff + (warp - 4) * S::kBoxStride;
         const int row_base = mt * HBM_ + q * 32;
 #pragma unroll
         for (int cc = 0; cc < HALF / 32; ++cc) {
@@ -297,8 +306,8 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
 #pragma unroll
           for (int pln = 0; pln < 2; ++pln) {
             if (pln == 1 && p.pair_out != 1) break;
-            unsigned char* hb = box + (p.pair_out == 1 ? pln : (cc & 1)) * 2048;
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            unsigned char* hb = box + ((p.pair_out == 1 ? 2 * cc + pln : cc) & (S::kPairBoxes - 1)) * 2048;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(S::kPairBoxes - 1) : "memory");
             __syncwarp();
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -308,7 +317,7 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              if (col0 + cc * 32 < p.N && row_base < p.M)
+              if (col0 + cc * 32 < p.N && row_base < p.M && !(SPOTV2_DBG(p) & 1))
                 asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmC),
                              "r"(smem_u32(hb)), "r"(col0 + cc * 32), "r"(row_base), "r"(pln)
                              : "memory");
@@ -321,7 +330,7 @@ gemm3x_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         // product while the MMA warp waited for them to drain TMEM).  Each warp parks 32 x 16 pieces of its block in two
         // alternating swizzled shared-memory boxes and one lane hands each to the TMA engine; the warp only waits for the
         // engine to have READ the box written two pieces ago before refilling it.  Rows >= M and columns >= N are clipped by the tensor map.
-        unsigned char* box = smem + S::kEpiOff + (warp - 4) * 4096;      // two 2 KB half-boxes (32 rows x 16 columns, 64B swizzle)
+        unsigned char* box = smem + S::kEpiOff + (warp - 4) * S::kBoxStride;      // two 2 KB half-boxes (32 rows x 16 columns, 64B swizzle)
         const int row_base = mt * HBM_ + q * 32;
 #pragma unroll
         for (int cc = 0; cc < HALF / 16; ++cc) {

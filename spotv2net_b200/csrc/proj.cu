@@ -143,7 +143,7 @@ extern "C" int spotv2_proj_fwd_pair(const spotv2_gat_desc* d, const void* x_hi, 
   if (int rc = w_pair_and_out_scale(W_aug, s.n_aug, s.F, s.HC, wh, wl, s.ldf16, wblk, x_scale, p_scale, st)) return rc;
   F16Operand A{x_hi, x_lo, s.ldf16, x_scale + 2, kNone}, B{wh, wl, s.ldf16, wblk + 2, s.HC};
   PairOut out{P_hi, single_product(d) ? nullptr : P_lo_or_null, s.ldp16, p_scale + 4, sd, 2 * d->H};
-  return gemm3x_f16(true, true, s.rows, s.n_aug, s.F, A, B, nullptr, 0, 1, 256, 0, nullptr, 0, st, nullptr, 0, single_product(d),
+  return gemm3x_f16(true, true, s.rows, s.n_aug, s.F, A, B, nullptr, 0, 1, 256 + 16, 0, nullptr, 0, st, nullptr, 0, single_product(d),
                     &out);
 }
 
