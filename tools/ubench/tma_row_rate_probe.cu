@@ -24,7 +24,8 @@ static int make_map(CUtensorMap* tm, void* base, uint64_t plane_stride, uint64_t
 }
 
 // mode 0: stores, one box per (warp, column block);  mode 1: loads, one box of all heads per column block (one thread issues)
-__global__ void __launch_bounds__(384, 1) k(const __grid_constant__ CUtensorMap tm, int B, int N, int n_cb, int box_cols, int mode, int depth) {
+// shift_odd: the kernel's rule for heads that start 16 bytes into a sector - boxes after the first start 8 columns early
+__global__ void __launch_bounds__(384, 1) k(const __grid_constant__ CUtensorMap tm, int B, int N, int n_cb, int box_cols, int mode, int depth, int shift_odd) {
   extern __shared__ __align__(1024) unsigned char sm[];
   __shared__ uint64_t bar[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -39,7 +40,8 @@ __global__ void __launch_bounds__(384, 1) k(const __grid_constant__ CUtensorMap 
           if (depth == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tm),
-                       "r"(stg + (depth == 1 ? 0u : (uint32_t)(k_ & 1) * piece)), "r"(cb * box_cols), "r"(b * N + 16 * m), "r"(h), "r"(0) : "memory");
+                       "r"(stg + (depth == 1 ? 0u : (uint32_t)(k_ & 1) * piece)), "r"(cb * box_cols - ((shift_odd && (h & 1) && cb > 0) ? 8 : 0)),
+                       "r"(b * N + 16 * m), "r"(h), "r"(0) : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         __syncwarp();
@@ -82,25 +84,27 @@ int main(int argc, char** argv) {
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     printf("Cp %d ld %d; cudaMemset of both planes (%.2f GB): %.3f ms, %.0f GB/s\n", Cp, ld, plane * 4 * 1e-9, ms, plane * 4 / ms * 1e-6);
   }
-  for (int mode = 0; mode < 2; ++mode)
-    for (int box_cols = 32; box_cols <= 64; box_cols *= 2)
-      for (int depth = 1; depth <= (mode ? 4 : 2); depth *= 2) {
+  for (int mode = 0; mode < 3; ++mode)
+    for (int box_cols = 32; box_cols <= (mode == 2 ? 32 : 64); box_cols *= 2)
+      for (int depth = 1; depth <= (mode == 1 ? 4 : 2); depth *= 2) {
+        const int shift_odd = mode == 2;
+        const int kmode = mode == 2 ? 0 : mode;
         CUtensorMap tm;
-        if (make_map(&tm, d, plane, rows, Cp, H, ld, box_cols, mode ? 32 : 16, mode ? 6 : 1)) { printf("encode failed\n"); return 1; }
+        if (make_map(&tm, d, plane, rows, Cp, H, ld, box_cols, kmode ? 32 : 16, kmode ? 6 : 1)) { printf("encode failed\n"); return 1; }
         const int n_cb = (Cp + box_cols - 1) / box_cols;
-        const size_t smem = mode ? (size_t)depth * box_cols * 2 * 32 * 6 * 2 + 1024 : (size_t)12 * 2 * box_cols * 2 * 16 * 2 + 1024;
+        const size_t smem = kmode ? (size_t)depth * box_cols * 2 * 32 * 6 * 2 + 1024 : (size_t)12 * 2 * box_cols * 2 * 16 * 2 + 1024;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         for (int rep = 0; rep < 3; ++rep) {
           cudaEventRecord(e0);
-          k<<<148, 384, smem>>>(tm, B, N, n_cb, box_cols, mode, depth);
+          k<<<148, 384, smem>>>(tm, B, N, n_cb, box_cols, kmode, depth, shift_odd);
           cudaEventRecord(e1);
           cudaError_t e = cudaDeviceSynchronize();
           if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
         }
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         const double bytes = (double)rows * H * Cp * 2 * 2;
-        printf("%s box %2d cols (%3d-byte rows) depth %d: %.3f ms, %.0f GB/s, %.2f cycles per box row per SM at 1.9 GHz\n", mode ? "load " : "store",
+        printf("%s box %2d cols (%3d-byte rows) depth %d: %.3f ms, %.0f GB/s, %.2f cycles per box row per SM at 1.9 GHz\n", mode == 1 ? "load " : (mode == 2 ? "store (odd heads shifted by 8 columns)" : "store"),
                box_cols, box_cols * 2, depth, ms, bytes / ms * 1e-6, ms * 1e-3 * 1.9e9 / ((double)rows * H * 2 * n_cb / 148.0));
       }
   return 0;
