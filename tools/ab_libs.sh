@@ -1,6 +1,8 @@
 #!/bin/bash
 # GPU box: A/B two builds of the library on the same box (base = tools/ab/libspotv2_gat_base.so, new = the in-tree one):
 # phase times of the default bench, alternating, so that box-to-box differences cancel.
+# Base build: git stash; python -m spotv2net_b200.build; mkdir -p tools/ab; cp spotv2net_b200/libspotv2_gat.so tools/ab/libspotv2_gat_base.so;
+# git stash pop; python -m spotv2net_b200.build   (tools/ab/*.so is git-ignored and travels with the gpurun snapshot; delete it afterwards)
 for rep in 1 2 3; do
   for which in base new; do
     if [ $which = base ]; then export SPOTV2_GAT_LIB=$PWD/tools/ab/libspotv2_gat_base.so; else unset SPOTV2_GAT_LIB; fi
