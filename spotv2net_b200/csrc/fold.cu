@@ -56,18 +56,22 @@ unfold_kernel(const float* __restrict__ W, const float* __restrict__ a_src,
 }
 
 // The whole fold in one launch (256 threads = 32 features x 8 channel slices), three kinds of blocks:
-//   [0, H*Cp)                     copy: W_aug row r <- head h's row of W, or zeros for the Cp - C pad rows (p_format 1)
-//   then ceil(F/32) * H blocks    u_src | u_dst rows of W_aug: u_k[h][f] = sum_c W[(h*C + c)*F + f] * a_k[h][c]
+//   ceil(F/32) * H blocks         u_src | u_dst rows of W_aug: u_k[h][f] = sum_c W[(h*C + c)*F + f] * a_k[h][c]
 //   then ceil(Fe/32) * H blocks   v[h][f] = sum_c W_e[(h*C + c)*Fe + f] * a_edge[h][c]
+//   then H*Cp blocks              copy: W_aug row r <- head h's row of W, or zeros for the Cp - C pad rows (p_format 1)
 // Fixed-order shared-memory reductions (deterministic).
 __global__ void __launch_bounds__(256)
 fold_all_kernel(const float* __restrict__ W, const float* __restrict__ a_src, const float* __restrict__ a_dst,
                 const float* __restrict__ We, const float* __restrict__ a_edge, float* __restrict__ W_aug, float* __restrict__ v,
                 int H, int C, int Cp, int F, int Fe) {
   __shared__ float red[2][32][33];
-  const int n_copy = H * Cp, fb = (F + 31) / 32;
+  const int fb = (F + 31) / 32;
+  const int n_red = fb * H + (We ? ((Fe + 31) / 32) * H : 0);
   int blk = blockIdx.x;
-  if (blk < n_copy) {
+  // the reduction blocks come FIRST in the grid: each thread walks C / 8 (or C / 32) rows in a dependent chain, and with
+  // the thousands of short copy blocks scheduled ahead of them they were the kernel's tail
+  if (blk >= n_red) {
+    blk -= n_red;
     const int h = blk / Cp, c = blk - h * Cp;
     float* dst = W_aug + (size_t)blk * F;
     if (c < C) {
@@ -78,7 +82,6 @@ fold_all_kernel(const float* __restrict__ W, const float* __restrict__ a_src, co
     }
     return;
   }
-  blk -= n_copy;
   const bool edge = blk >= fb * H;
   if (edge) blk -= fb * H;
   const int nb = edge ? (Fe + 31) / 32 : fb, Fd = edge ? Fe : F;
@@ -95,6 +98,7 @@ fold_all_kernel(const float* __restrict__ W, const float* __restrict__ a_src, co
     float s0 = 0.f, s1 = 0.f;
     if (f < Fd) {
       const float* Mh = M + (size_t)h * C * Fd + f;
+#pragma unroll 8
       for (int c = sl; c < C; c += NY) {
         const float w = Mh[(size_t)c * Fd];
         s0 = fmaf(w, a0[h * C + c], s0);
