@@ -6,17 +6,19 @@
 //
 //   producer warp   ONE in-order stream of fixed-size slots (28 KB each, 5 of them at the default geometry), filled in
 //                   exactly the order the compute warps consume them, as far ahead as the ring allows:
-//                   * the forward's edge-term tile (one bulk copy) - or, without it, the edge rows a first time (logits)
+//                   * the forward's record (one bulk copy: its signed attention coefficients, or - with attention dropout -
+//                     its edge terms) - or, without it, the edge rows a first time (logits)
 //                   * phase A slots: the dout tile and the P tiles of all heads for one 32-channel block
 //                   * edge rows: 1-D bulk copies, 48-row chunks (for dv)
 //                   * phase D slots: groups of up to 7 dout tiles
 //   compute warps   per graph
-//     L  edge terms: copied from the slot (or recomputed: g[e,h] = <edge row, v_h>, 3xTF32, two half-groups of 6 warps)
-//     S  self-loop mean fill, LeakyReLU, softmax -> alpha[h][j][i], z>0 masks       (thread per (h, i))
+//     L  the record: copied from the slot (or edge terms recomputed: g[e,h] = <edge row, v_h>, 3xTF32, two half-groups of 6 warps)
+//     S  self-loop mean fill, LeakyReLU, softmax -> alpha[h][j][i], z>0 masks       (thread per (h, i)) - skipped when the
+//        record already is +-alpha (sign = LeakyReLU side; AttnParams::alpha_rec)
 //     A  dalpha_h = g dO_h P_h^T         warp = (head, 16-target tile); K = channels streamed slot by slot;
 //        softmax/LeakyReLU backward directly on the accumulator fragments (row sums by 4-lane shuffles),
 //        dd -> global, ds partials, dz' (mean-fill redistributed) -> shared D tile
-//     V  dv^T[f,h] += T^T dz'            warp = (16-feature tile, row group) over the edge rows
+//     V  dv^T[f,h] += T^T dz'            warp = two 16-feature tiles of one 16-row group (shared dz' fragments) over the edge rows
 //     D  dP_h = g alpha_h^T dO_h         warp = (head, 16-source tile), alpha^T fragments in registers
 //
 // Two instantiation families (template parameter P16):
