@@ -784,8 +784,9 @@ def run_e2e_windows(args, hp, dev, world, rank, barrier):
         freed[s_].record(main_stream)
         return loss
 
-    issue_copy(0)
-    launch(0).item()                                         # warm-up
+    for _ in range(3):                                       # warm-up
+        issue_copy(0)
+        launch(0).item()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -871,7 +872,8 @@ def run_e2e(args, hp, dev, world, rank, barrier):
         per_rank = [t.item() for t in g]
         copy_stats = {"h2d_GBs_copy_only_per_rank": per_rank, "h2d_GBs_copy_only_sum": sum(per_rank),
                       "note": "all ranks copy at once, no compute: what the host (memory + PCIe fabric) delivers"}
-    issue_copy(0); compute(0)                   # warm-up (also validates and caches nothing across steps)
+    for _ in range(3):                          # warm-up (also validates and caches nothing across steps)
+        issue_copy(0); compute(0)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
